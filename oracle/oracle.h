@@ -1,0 +1,159 @@
+/*
+ * oracle.h -- CPU restatement of the ygz-slam tracking + local-BA hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / the timed CPU baseline.
+ * The product (ygz_slam_b200/csrc) never links or calls it.
+ *
+ * Every function cites the reference file:line it restates (paths relative to
+ * /root/reference).  Arithmetic owned by third-party code that is NOT in the
+ * reference tree (uzh-rpg `fast`, OpenCV, g2o, Ceres -- SURVEY.md 8c) is restated
+ * from the published algorithm; the OpenCV-owned pieces are pinned against
+ * cv2 4.13 in tests/test_oracle_cv2.py, FAST / g2o / Ceres are "parity unpinned"
+ * (no reference test asserts a value for them) and are pinned only structurally
+ * (brute-force cross-implementations, known-answer scenes).
+ *
+ * Build: oracle/Makefile.  Two flavours of the same sources:
+ *   liboracle.so       -O2 -ffp-contract=off      (the parity checker: no FMA contraction)
+ *   liboracle_native.so -O3 -march=native         (the reference's own flags, CMakeLists.txt:14-16;
+ *                                                  the timed CPU baseline)
+ */
+#ifndef YGZ_ORACLE_H_
+#define YGZ_ORACLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORA_MAX_LEVELS 10
+
+/* ---- image pyramid (src/Basic/Frame.cpp:22-40; OpenCV cvtColor / pyrDown) ------------- */
+void ora_bgr2gray(const uint8_t* bgr, int w, int h, uint8_t* gray);
+void ora_pyrdown(const uint8_t* src, int w, int h, uint8_t* dst);
+/* packed pyramid: levels stored back to back, each level continuous (pitch == width), like the
+ * cv::Mat outputs of pyrDown.  Fills lw/lh/off for n_levels and returns the total byte count. */
+size_t ora_pyramid_layout(int w, int h, int n_levels, int* lw, int* lh, size_t* off);
+void ora_build_pyramid(const uint8_t* gray, int w, int h, int n_levels, uint8_t* pyr);
+
+/* ---- FAST-10 (uzh-rpg/fast; call sites src/Algorithm/FeatureDetector.cpp:365-381) ------- */
+/* raster-order corner list; returns the number found (corners beyond `cap` are counted but not stored) */
+int ora_fast10_detect(const uint8_t* img, int w, int h, int stride, int barrier, int16_t* xy, int cap);
+void ora_fast10_score(const uint8_t* img, int stride, const int16_t* xy, int n, int barrier, int32_t* scores);
+int ora_fast_nonmax_3x3(const int16_t* xy, const int32_t* scores, int n, int32_t* keep_idx);
+
+/* ---- FeatureDetector (src/Algorithm/FeatureDetector.cpp:299-596) ------------------------ */
+typedef struct {
+    int image_width, image_height; /* image.width / image.height            */
+    int cell_size;                 /* feature.cell (10)                     */
+    int threshold;                 /* short(feature.detection_threshold)=15 */
+    int n_levels;                  /* Frame::Option::_pyramid_level (3)     */
+} ora_detect_params;
+
+typedef struct {
+    int n;
+    double* px;      /* full-resolution pixel = level coord * 2^level */
+    double* py;
+    int32_t* level;
+    float* score;    /* Shi-Tomasi */
+    float* angle;    /* degrees */
+    uint8_t* desc;   /* n x 32 */
+    int32_t* cell;   /* grid cell index of each feature */
+} ora_features;
+
+/* FeatureDetector::Detect.  `occupied` = grid_rows*grid_cols bytes (non-zero = cell already holds an
+ * old feature, SetExistingFeatures) or NULL.  Output arrays must hold grid_rows*grid_cols entries. */
+int ora_detect(const uint8_t* pyr, const ora_detect_params* p, const uint8_t* occupied, ora_features* out);
+float ora_shi_tomasi(const uint8_t* img, int w, int h, int u, int v);
+/* IC_Angle + ComputeOrbDescriptor for given full-res pixels (ComputeAngleAndDescriptor, :580-588) */
+void ora_describe(const uint8_t* pyr, int w, int h, int n_levels, int n, const double* px, const double* py,
+                  const int32_t* level, float* angle, uint8_t* desc);
+float ora_fast_atan2(float y, float x);
+int ora_cv_round_f(float v);
+int ora_cv_round_d(double v);
+
+/* ---- matching (src/Algorithm/Matcher.cpp:30-84; test/test_orb_match.cpp:86-105) --------- */
+int ora_descriptor_distance(const uint8_t* a, const uint8_t* b);
+/* cv::BFMatcher(NORM_HAMMING, crossCheck).match: train_idx[i] = -1 when query i has no match */
+void ora_match_bf(const uint8_t* A, int nA, const uint8_t* B, int nB, int cross_check, int32_t* train_idx,
+                  int32_t* dist);
+/* test_orb_match.cpp:97-105: keep[i]=1 iff matched and dist < 3*clamp(min dist,20,50); returns count */
+int ora_good_matches(const int32_t* train_idx, const int32_t* dist, int nA, uint8_t* keep);
+/* Matcher::CheckFrameDescriptors core: keep[k]=1 iff d_k < 3.0*clamp(min d, init_low, init_high) */
+int ora_check_descriptors(const uint8_t* A, const uint8_t* B, const int32_t* ia, const int32_t* ib, int n,
+                          int init_low, int init_high, int32_t* dist, uint8_t* keep);
+
+/* ---- patch alignment (src/Algorithm/CVUtils.cpp:186-318; Matcher.cpp:356-466) ----------- */
+int ora_align2d(const uint8_t* img, int w, int h, const uint8_t* ref_with_border /*100*/,
+                const uint8_t* ref /*64*/, int n_iter, double* u, double* v);
+int ora_align1d(const uint8_t* img, int w, int h, float dirx, float diry, const uint8_t* ref_with_border,
+                const uint8_t* ref, int n_iter, double* u, double* v, double* h_inv);
+
+typedef struct { float fx, fy, cx, cy; } ora_camera; /* Camera.h:14-22: stored as float */
+
+/* pose = T_cw as 3x4 row-major [R|t] (12 doubles) at this boundary; quaternion inside like Sophus */
+/* Matcher::FindDirectProjection(ref,curr,Feature*,px,level) (Matcher.cpp:385-417) for a batch */
+void ora_find_direct_projection(const uint8_t* ref_pyr, const uint8_t* cur_pyr, int w, int h, int n_levels,
+                                const ora_camera* cam, const double* T_cw_ref, const double* T_cw_cur, int n,
+                                const double* ref_px /*2n*/, const double* ref_depth, const int32_t* ref_level,
+                                double* cur_px_inout /*2n*/, int32_t* search_level, uint8_t* ok);
+
+/* ---- sparse image alignment (src/Algorithm/SparseImageAlign.cpp; NLSSolver_impl.hpp) ---- */
+/* returns n_meas/16 (SparseImgAlign::run); T_cw_cur updated in place */
+size_t ora_sparse_align(const uint8_t* ref_pyr, const uint8_t* cur_pyr, int w, int h, int n_levels,
+                        const ora_camera* cam, int n, const double* px /*2n*/, const double* depth,
+                        const uint8_t* has_mappoint, const double* T_cw_ref, double* T_cw_cur, int max_level,
+                        int min_level, int n_iter, double eps, int32_t* iters_per_level /*may be NULL*/);
+/* Matcher::SparseImageAlignment (Matcher.cpp:468-492): returns 1/0, T_cw_cur in/out */
+int ora_matcher_sparse_alignment(const uint8_t* ref_pyr, const uint8_t* cur_pyr, int w, int h, int n_levels,
+                                 const ora_camera* cam, int n, const double* px, const double* depth,
+                                 const uint8_t* has_mappoint, const double* T_cw_ref, double* T_cw_cur);
+
+/* ---- Sophus (thirdparty/Sophus/sophus/so3.cpp:127-202, se3.cpp:59-95,170-220) ----------- */
+void ora_se3_exp(const double* upsilon_omega /*6*/, double* T /*12*/);
+void ora_se3_log(const double* T /*12*/, double* upsilon_omega /*6*/);
+
+/* ---- bundle adjustment (src/Algorithm/BA.cpp; include/ygz/G2oTypes.h) ------------------- */
+typedef struct {
+    int max_iters;        /* optimizer.optimize(20)            */
+    double huber_delta;   /* 5.991 (BA.cpp:451); <=0 : no loss */
+    double chi2_outlier;  /* 5.991 (BA.cpp:508)                */
+    double tau;           /* g2o LM tau 1e-5                   */
+    int max_trials;       /* g2o LM maxTrialsAfterFailure 10   */
+} ora_ba_params;
+
+typedef struct {
+    int iters;
+    int lm_trials;
+    double chi2_initial, chi2_final, lambda_final;
+    int n_outliers;
+} ora_ba_stats;
+
+/* ba::LocalBAG2O.  poses: n_kf x 6 in g2o order [omega; upsilon] (G2oTypes.h:38-45), in/out.
+ * fixed[k] != 0 : vertex fixed.  pts: n_pt x 3 in/out.  obs: (kf_idx, pt_idx, px) x n_obs. */
+int ora_local_ba_g2o(const ora_camera* cam, int n_kf, double* poses, const uint8_t* fixed, int n_pt, double* pts,
+                     int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px,
+                     const ora_ba_params* prm, uint8_t* outlier, ora_ba_stats* stats);
+
+/* ba::OptimizeCurrentPoseOnly (BA.cpp:188-264).  T_cw in/out, inlier[] out (1 = !_bad), depth[] out */
+int ora_pose_only(const ora_camera* cam, int n, const double* pt_world /*3n*/, const double* px /*2n*/,
+                  double* T_cw, uint8_t* inlier, double* depth);
+
+/* ---- KLT (src/Algorithm/Tracker.cpp:65-113 -> cv::calcOpticalFlowPyrLK) ------------------ */
+typedef struct {
+    int win;        /* 21 */
+    int max_level;  /* 4  */
+    int max_iter;   /* 30 */
+    double eps;     /* 0.001 */
+    double min_eig; /* 1e-4  */
+} ora_klt_params;
+void ora_klt(const uint8_t* ref, const uint8_t* cur, int w, int h, int n, const float* ref_xy,
+             float* cur_xy_inout, uint8_t* status, float* err, const ora_klt_params* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,297 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle*.so).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+MAX_LEVELS = 10
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so / liboracle_native.so with oracle/Makefile (g++)."""
+    if force or not (_HERE / "liboracle.so").exists() or not (_HERE / "liboracle_native.so").exists():
+        subprocess.run(["make", "-C", str(_HERE), "-j4"] + (["-B"] if force else []), check=True,
+                       stdout=subprocess.DEVNULL)
+
+
+class DetectParams(C.Structure):
+    _fields_ = [("image_width", C.c_int), ("image_height", C.c_int), ("cell_size", C.c_int),
+                ("threshold", C.c_int), ("n_levels", C.c_int)]
+
+
+class Features(C.Structure):
+    _fields_ = [("n", C.c_int), ("px", C.c_void_p), ("py", C.c_void_p), ("level", C.c_void_p),
+                ("score", C.c_void_p), ("angle", C.c_void_p), ("desc", C.c_void_p), ("cell", C.c_void_p)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class BAParams(C.Structure):
+    _fields_ = [("max_iters", C.c_int), ("huber_delta", C.c_double), ("chi2_outlier", C.c_double),
+                ("tau", C.c_double), ("max_trials", C.c_int)]
+
+
+class BAStats(C.Structure):
+    _fields_ = [("iters", C.c_int), ("lm_trials", C.c_int), ("chi2_initial", C.c_double),
+                ("chi2_final", C.c_double), ("lambda_final", C.c_double), ("n_outliers", C.c_int)]
+
+
+class KLTParams(C.Structure):
+    _fields_ = [("win", C.c_int), ("max_level", C.c_int), ("max_iter", C.c_int), ("eps", C.c_double),
+                ("min_eig", C.c_double)]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_camera() -> Camera:
+    return Camera(520.9, 521.0, 325.1, 249.7)
+
+
+class Oracle:
+    """Thin numpy front-end.  `native=True` loads the -O3 AVX2/FMA build (the timed CPU baseline)."""
+
+    def __init__(self, native: bool = False):
+        build()
+        self.lib = C.CDLL(str(_HERE / ("liboracle_native.so" if native else "liboracle.so")))
+        L = self.lib
+        L.ora_pyramid_layout.restype = C.c_size_t
+        L.ora_shi_tomasi.restype = C.c_float
+        L.ora_fast_atan2.restype = C.c_float
+        L.ora_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.ora_cv_round_f.argtypes = [C.c_float]
+        L.ora_cv_round_d.argtypes = [C.c_double]
+        if hasattr(L, "ora_sparse_align"):
+            L.ora_sparse_align.restype = C.c_size_t
+
+    # ---- pyramid ---------------------------------------------------------------------------
+    def layout(self, w, h, n_levels):
+        lw = (C.c_int * MAX_LEVELS)()
+        lh = (C.c_int * MAX_LEVELS)()
+        off = (C.c_size_t * MAX_LEVELS)()
+        total = self.lib.ora_pyramid_layout(w, h, n_levels, lw, lh, off)
+        return list(lw)[:n_levels], list(lh)[:n_levels], list(off)[:n_levels], total
+
+    def bgr2gray(self, bgr):
+        h, w, _ = bgr.shape
+        out = np.empty((h, w), np.uint8)
+        self.lib.ora_bgr2gray(_p(np.ascontiguousarray(bgr)), w, h, _p(out))
+        return out
+
+    def pyrdown(self, img):
+        h, w = img.shape
+        out = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+        self.lib.ora_pyrdown(_p(np.ascontiguousarray(img)), w, h, _p(out))
+        return out
+
+    def build_pyramid(self, gray, n_levels):
+        h, w = gray.shape
+        _, _, _, total = self.layout(w, h, n_levels)
+        pyr = np.empty(total, np.uint8)
+        self.lib.ora_build_pyramid(_p(np.ascontiguousarray(gray)), w, h, n_levels, _p(pyr))
+        return pyr
+
+    def level_view(self, pyr, w, h, n_levels, L):
+        lw, lh, off, _ = self.layout(w, h, n_levels)
+        return pyr[off[L]: off[L] + lw[L] * lh[L]].reshape(lh[L], lw[L])
+
+    # ---- FAST ------------------------------------------------------------------------------
+    def fast_detect(self, img, barrier=15, arc=10):
+        h, w = img.shape
+        img = np.ascontiguousarray(img)
+        xy = np.empty((w * h, 2), np.int16)
+        n = self.lib.ora_fastN_detect(_p(img), w, h, w, barrier, arc, _p(xy), w * h)
+        return xy[:n].copy()
+
+    def fast_score(self, img, xy, barrier=15):
+        img = np.ascontiguousarray(img)
+        xy = np.ascontiguousarray(xy, np.int16)
+        s = np.empty(len(xy), np.int32)
+        self.lib.ora_fast10_score(_p(img), img.shape[1], _p(xy), len(xy), barrier, _p(s))
+        return s
+
+    def fast_nonmax(self, xy, scores):
+        xy = np.ascontiguousarray(xy, np.int16)
+        scores = np.ascontiguousarray(scores, np.int32)
+        keep = np.empty(max(len(xy), 1), np.int32)
+        n = self.lib.ora_fast_nonmax_3x3(_p(xy), _p(scores), len(xy), _p(keep))
+        return keep[:n].copy()
+
+    # ---- detector --------------------------------------------------------------------------
+    def detect(self, pyr, w=640, h=480, n_levels=3, cell=10, threshold=15, occupied=None):
+        prm = DetectParams(w, h, cell, threshold, n_levels)
+        ncell = -(-w // cell) * -(-h // cell)
+        px = np.empty(ncell, np.float64)
+        py = np.empty(ncell, np.float64)
+        level = np.empty(ncell, np.int32)
+        score = np.empty(ncell, np.float32)
+        angle = np.empty(ncell, np.float32)
+        desc = np.empty((ncell, 32), np.uint8)
+        cellidx = np.empty(ncell, np.int32)
+        f = Features(0, *[a.ctypes.data for a in (px, py, level, score, angle, desc, cellidx)])
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        n = self.lib.ora_detect(_p(pyr), C.byref(prm), _p(occ), C.byref(f))
+        return dict(n=n, px=px[:n].copy(), py=py[:n].copy(), level=level[:n].copy(), score=score[:n].copy(),
+                    angle=angle[:n].copy(), desc=desc[:n].copy(), cell=cellidx[:n].copy())
+
+    def shi_tomasi(self, img, u, v):
+        img = np.ascontiguousarray(img)
+        return float(self.lib.ora_shi_tomasi(_p(img), img.shape[1], img.shape[0], int(u), int(v)))
+
+    def describe(self, pyr, w, h, n_levels, px, py, level):
+        n = len(px)
+        px = np.ascontiguousarray(px, np.float64)
+        py = np.ascontiguousarray(py, np.float64)
+        level = np.ascontiguousarray(level, np.int32)
+        angle = np.empty(n, np.float32)
+        desc = np.empty((n, 32), np.uint8)
+        self.lib.ora_describe(_p(pyr), w, h, n_levels, n, _p(px), _p(py), _p(level), _p(angle), _p(desc))
+        return angle, desc
+
+    def fast_atan2(self, y, x):
+        return float(self.lib.ora_fast_atan2(float(y), float(x)))
+
+    # ---- matching --------------------------------------------------------------------------
+    def match_bf(self, A, B, cross_check=True):
+        A = np.ascontiguousarray(A, np.uint8)
+        B = np.ascontiguousarray(B, np.uint8)
+        idx = np.empty(len(A), np.int32)
+        dist = np.empty(len(A), np.int32)
+        self.lib.ora_match_bf(_p(A), len(A), _p(B), len(B), int(cross_check), _p(idx), _p(dist))
+        return idx, dist
+
+    def good_matches(self, idx, dist):
+        keep = np.empty(len(idx), np.uint8)
+        n = self.lib.ora_good_matches(_p(np.ascontiguousarray(idx, np.int32)),
+                                      _p(np.ascontiguousarray(dist, np.int32)), len(idx), _p(keep))
+        return keep.astype(bool), n
+
+    def check_descriptors(self, A, B, ia, ib, init_low=30, init_high=100):
+        A = np.ascontiguousarray(A, np.uint8)
+        B = np.ascontiguousarray(B, np.uint8)
+        ia = np.ascontiguousarray(ia, np.int32)
+        ib = np.ascontiguousarray(ib, np.int32)
+        dist = np.empty(len(ia), np.int32)
+        keep = np.empty(len(ia), np.uint8)
+        n = self.lib.ora_check_descriptors(_p(A), _p(B), _p(ia), _p(ib), len(ia), init_low, init_high, _p(dist),
+                                           _p(keep))
+        return dist, keep.astype(bool), n
+
+    # ---- alignment -------------------------------------------------------------------------
+    def align2d(self, img, ref_border, ref, u, v, n_iter=10):
+        img = np.ascontiguousarray(img)
+        uu = C.c_double(u)
+        vv = C.c_double(v)
+        ok = self.lib.ora_align2d(_p(img), img.shape[1], img.shape[0], _p(np.ascontiguousarray(ref_border, np.uint8)),
+                                  _p(np.ascontiguousarray(ref, np.uint8)), n_iter, C.byref(uu), C.byref(vv))
+        return bool(ok), uu.value, vv.value
+
+    def align1d(self, img, dirx, diry, ref_border, ref, u, v, n_iter=10):
+        img = np.ascontiguousarray(img)
+        uu = C.c_double(u)
+        vv = C.c_double(v)
+        hinv = C.c_double(0)
+        ok = self.lib.ora_align1d(_p(img), img.shape[1], img.shape[0], C.c_float(dirx), C.c_float(diry),
+                                  _p(np.ascontiguousarray(ref_border, np.uint8)),
+                                  _p(np.ascontiguousarray(ref, np.uint8)), n_iter, C.byref(uu), C.byref(vv),
+                                  C.byref(hinv))
+        return bool(ok), uu.value, vv.value, hinv.value
+
+    def find_direct_projection(self, ref_pyr, cur_pyr, w, h, n_levels, T_ref, T_cur, ref_px, ref_depth, ref_level,
+                               cur_px, cam=None):
+        cam = cam or default_camera()
+        n = len(ref_depth)
+        ref_px = np.ascontiguousarray(ref_px, np.float64)
+        cur = np.ascontiguousarray(cur_px, np.float64).copy()
+        lvl = np.empty(n, np.int32)
+        ok = np.empty(n, np.uint8)
+        self.lib.ora_find_direct_projection(_p(ref_pyr), _p(cur_pyr), w, h, n_levels, C.byref(cam),
+                                            _p(np.ascontiguousarray(T_ref, np.float64)),
+                                            _p(np.ascontiguousarray(T_cur, np.float64)), n, _p(ref_px),
+                                            _p(np.ascontiguousarray(ref_depth, np.float64)),
+                                            _p(np.ascontiguousarray(ref_level, np.int32)), _p(cur), _p(lvl), _p(ok))
+        return cur, lvl, ok.astype(bool)
+
+    def sparse_align(self, ref_pyr, cur_pyr, w, h, n_levels, px, depth, has_mp, T_ref, T_cur, max_level=2,
+                     min_level=0, n_iter=30, eps=1e-6, cam=None):
+        cam = cam or default_camera()
+        n = len(depth)
+        T = np.ascontiguousarray(T_cur, np.float64).copy()
+        iters = np.zeros(MAX_LEVELS, np.int32)
+        nm = self.lib.ora_sparse_align(_p(ref_pyr), _p(cur_pyr), w, h, n_levels, C.byref(cam), n,
+                                       _p(np.ascontiguousarray(px, np.float64)),
+                                       _p(np.ascontiguousarray(depth, np.float64)),
+                                       _p(np.ascontiguousarray(has_mp, np.uint8)),
+                                       _p(np.ascontiguousarray(T_ref, np.float64)), _p(T), max_level, min_level,
+                                       n_iter, C.c_double(eps), _p(iters))
+        return T, int(nm), iters
+
+    def matcher_sparse_alignment(self, ref_pyr, cur_pyr, w, h, n_levels, px, depth, has_mp, T_ref, T_cur, cam=None):
+        cam = cam or default_camera()
+        T = np.ascontiguousarray(T_cur, np.float64).copy()
+        ok = self.lib.ora_matcher_sparse_alignment(_p(ref_pyr), _p(cur_pyr), w, h, n_levels, C.byref(cam),
+                                                   len(depth), _p(np.ascontiguousarray(px, np.float64)),
+                                                   _p(np.ascontiguousarray(depth, np.float64)),
+                                                   _p(np.ascontiguousarray(has_mp, np.uint8)),
+                                                   _p(np.ascontiguousarray(T_ref, np.float64)), _p(T))
+        return bool(ok), T
+
+    # ---- Sophus ----------------------------------------------------------------------------
+    def se3_exp(self, v):
+        T = np.empty(12, np.float64)
+        self.lib.ora_se3_exp(_p(np.ascontiguousarray(v, np.float64)), _p(T))
+        return T.reshape(3, 4)
+
+    def se3_log(self, T):
+        v = np.empty(6, np.float64)
+        self.lib.ora_se3_log(_p(np.ascontiguousarray(T, np.float64)), _p(v))
+        return v
+
+    # ---- BA --------------------------------------------------------------------------------
+    def local_ba(self, poses, fixed, pts, kf_idx, pt_idx, px, max_iters=20, huber=5.991, cam=None):
+        cam = cam or default_camera()
+        poses = np.ascontiguousarray(poses, np.float64).copy()
+        pts = np.ascontiguousarray(pts, np.float64).copy()
+        prm = BAParams(max_iters, huber, 5.991, 1e-5, 10)
+        st = BAStats()
+        outl = np.zeros(len(kf_idx), np.uint8)
+        self.lib.ora_local_ba_g2o(C.byref(cam), len(poses), _p(poses), _p(np.ascontiguousarray(fixed, np.uint8)),
+                                  len(pts), _p(pts), len(kf_idx), _p(np.ascontiguousarray(kf_idx, np.int32)),
+                                  _p(np.ascontiguousarray(pt_idx, np.int32)),
+                                  _p(np.ascontiguousarray(px, np.float64)), C.byref(prm), _p(outl), C.byref(st))
+        stats = {k: getattr(st, k) for k, _ in BAStats._fields_}
+        return poses, pts, outl.astype(bool), stats
+
+    def pose_only(self, pt_world, px, T_cw, cam=None):
+        cam = cam or default_camera()
+        n = len(pt_world)
+        T = np.ascontiguousarray(T_cw, np.float64).copy()
+        inl = np.zeros(n, np.uint8)
+        depth = np.zeros(n, np.float64)
+        cnt = self.lib.ora_pose_only(C.byref(cam), n, _p(np.ascontiguousarray(pt_world, np.float64)),
+                                     _p(np.ascontiguousarray(px, np.float64)), _p(T), _p(inl), _p(depth))
+        return T, inl.astype(bool), depth, cnt
+
+    # ---- KLT -------------------------------------------------------------------------------
+    def klt(self, ref, cur, ref_xy, cur_xy, win=21, max_level=4, max_iter=30, eps=0.001):
+        h, w = ref.shape
+        n = len(ref_xy)
+        out = np.ascontiguousarray(cur_xy, np.float32).copy()
+        status = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32)
+        prm = KLTParams(win, max_level, max_iter, eps, 1e-4)
+        self.lib.ora_klt(_p(np.ascontiguousarray(ref)), _p(np.ascontiguousarray(cur)), w, h, n,
+                         _p(np.ascontiguousarray(ref_xy, np.float32)), _p(out), _p(status), _p(err), C.byref(prm))
+        return out, status, err
