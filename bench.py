@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the ygz-slam hot path on B200 (contract: task statement, section 4).
+
+Workload (BASELINE.json configs[1], "C2"): FAST+ORB extract + brute-force Hamming match on a synthetic
+640x480 stream, 8-level pyramid, ~1000-1300 keypoints/frame.  One STEP = one batch of `--batch` frames:
+    pyramid (7 pyrDown levels) -> fused FAST-10/score/nonmax/grid-cell selection on all 8 levels
+    -> IC angle + ORB descriptors -> cross-checked brute-force match of frame i against frame i+1.
+metric = tracked frames/sec (whole job, all ranks).
+
+  value : frames already resident in HBM (level 0 in the slot storage) when the timed region starts;
+          CUDA events on the library's stream, max over ranks.
+  e2e   : same metric through the public C ABI with HOST buffers: every step copies the batch from
+          pinned host memory (H2D) and reads keypoints + matches back (D2H) inside the timed region.
+  roofline      : dominant kernel (largest share of the step, timed live with CUDA events around each
+                  launch) -- algorithmic bytes / duration against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  : the CPU oracle (-O3 AVX2/FMA build of the reference restatement) on a bounded sample
+                  of the same frames, rank 0 only.
+  --impl reference : the reference's CPU path (oracle restatement: the reference itself cannot be built
+                  here) on all host threads, frame-parallel, same metric/config.
+Multi-GPU: independent frame batches (streams) per rank, no data-path collective ("weak" scaling);
+torch.distributed (NCCL) only for the barrier and the max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H, LEVELS = 640, 480, 8
+FRAME_BYTES = W * H
+PYR_BYTES = sum(((W + (1 << L) - 1) >> L) * ((H + (1 << L) - 1) >> L) for L in range(LEVELS))  # 409,600
+
+
+def make_frames(n: int, seed: int) -> np.ndarray:
+    """n distinct 640x480 grey frames: sliding crops of one perspective render + per-frame noise."""
+    from ygz_slam_b200 import synth
+    tex = synth.texture(0x59475A00 + seed, 2048)
+    bw, bh = W + 2 * 512 + 16, H + 64
+    base, _ = synth.render_plane(tex, synth.trajectory(seed), w=bw, h=bh)
+    rng = np.random.default_rng(seed + 1)
+    out = np.empty((n, H, W), np.uint8)
+    for k in range(n):
+        x0, y0 = (2 * k) % 1024, (7 * k) % 64
+        crop = base[y0:y0 + H, x0:x0 + W].astype(np.int16)
+        crop += np.rint(rng.normal(0, 2.0, (H, W))).astype(np.int16)
+        out[k] = np.clip(crop, 0, 255).astype(np.uint8)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (profiling guide recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # the busiest half of the samples = under load
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> tuple:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_step(ora, frames: np.ndarray, lo: int, hi: int, out_counts=None) -> int:
+    """Reference CPU path for frames [lo, hi): pyramid + Detect on each, BF match of k against k+1."""
+    n_feat = 0
+    prev = None
+    for k in range(lo, hi + 1):  # one extra so that every frame in [lo,hi) has its successor
+        g = frames[k % len(frames)]
+        pyr = ora.build_pyramid(g, LEVELS)
+        f = ora.detect(pyr, n_levels=LEVELS)
+        if prev is not None:
+            ora.match_bf(prev["desc"], f["desc"], True)
+        if k < hi:
+            n_feat += f["n"]
+        prev = f
+    return n_feat
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """--impl reference: CPU path on all host threads (rank 0 only prints)."""
+    if rank != 0:
+        return
+    from oracle.pyoracle import Oracle
+    ora = Oracle(native=True)
+    threads = os.cpu_count() or 1
+    per_thread = 4                      # frames per thread per step -> bounded sample
+    n = threads * per_thread
+    frames = make_frames(min(n + 1, 512), 0)
+
+    def step():
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda t: cpu_step(ora, frames, t * per_thread, (t + 1) * per_thread), range(threads)))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "tracked frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(n, "host threads, frame-parallel"),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} frames/step ({per_thread} per thread) x {args.steps} steps, oracle -O3 AVX2/FMA build"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(batch: int, how: str) -> dict:
+    return {"workload": "C2: FAST-10+ORB extract (grid 10px, thr 15) + cross-checked brute-force Hamming match, "
+                        "640x480 u8, 8-level pyramid, frame i matched against frame i+1",
+            "frames_per_step": batch, "keypoints_per_frame": "~1100-1300 (grid yield on the synthetic stream)",
+            "batching": how,
+            "l2_policy": "inputs larger than L2: %.0f MB of level-0 pixels per step vs 126 MB L2" % (batch * FRAME_BYTES / 1e6)}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the bounded cpu_baseline sample")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ygz_slam_b200 import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    ctx = Context(local_rank, n_levels=LEVELS)
+    fr = ctx.frames(B)
+    frames = make_frames(B, seed=rank)             # every rank owns an independent stream of frames
+    pinned = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = frames
+    slots = np.arange(B, dtype=np.int32)
+    nxt = (slots + 1) % B
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        fr.build_pyramid(0, B)
+        fr.detect(slots, fetch=False)
+        fr.match(slots, nxt, True, fetch=False)
+
+    d2h_bytes = [0]
+
+    def e2e_step():
+        fr.upload_raw(pinned.data_ptr(), B, 1, FRAME_BYTES)
+        off, _ = fr.detect_packed(slots)
+        qoff, _, _ = fr.match_packed(slots, nxt, True)
+        nf = int(off[-1])
+        d2h_bytes[0] = nf * (4 + 4 + 1 + 4 + 4 + 32 + 4) + (B + 1) * 4 + int(qoff[-1]) * 8 + (B + 1) * 4
+        return nf
+
+    # ---- resident leg (value) -------------------------------------------------------------------
+    fr.upload_raw(pinned.data_ptr(), B, 1, FRAME_BYTES)   # level 0 resident before the timed region
+    ctx.synchronize()
+    for _ in range(args.warmup):
+        resident_step()
+    ctx.synchronize()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        ev0.record()
+    for _ in range(args.steps):
+        resident_step()
+    with torch.cuda.stream(ext):
+        ev1.record()
+    barrier()
+    ms_resident = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+
+    # ---- e2e leg ----------------------------------------------------------------------------------
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    with torch.cuda.stream(ext):
+        ev0.record()
+    for _ in range(args.steps):
+        nfeat = e2e_step()
+    with torch.cuda.stream(ext):
+        ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+
+    # ---- per-kernel shares (CUDA events around every launch; separate pass so the timed legs stay clean)
+    ctx.profile(True)
+    for _ in range(max(3, args.steps // 2)):
+        resident_step()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    n_prof_steps = max(3, args.steps // 2)
+
+    if world > 1:
+        t = torch.tensor([ms_resident, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_resident, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = world * B * args.steps / (ms_resident * 1e-3)
+        e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        total_ms = sum(v[0] for v in prof.values()) or 1.0
+        shares = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches_per_step": v[1] / n_prof_steps,
+                      "share": v[0] / total_ms} for k, v in prof.items() if v[1]}
+        kpf = nfeat / B
+        alg_bytes = {  # ALGORITHMIC bytes per launch
+            "match": B * (32 * 2 * kpf + 8 * kpf),
+            "fast_cells": B * PYR_BYTES,
+            "pyrdown": None, "describe": B * kpf * (961 + 32), "merge_cells": None,
+        }
+        dom = max(shares, key=lambda k: shares[k]["share"])
+        roof = []
+        for k in ("match", "fast_cells", "describe"):
+            if k in shares and alg_bytes.get(k):
+                dur = shares[k]["ms_per_launch"] * 1e-3
+                ach = alg_bytes[k] / dur / 1e9
+                roof.append({"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                             "frac": ach / peak, "traffic": None, "share_of_step": shares[k]["share"],
+                             "us_per_launch": dur * 1e6, "algorithmic_bytes_per_launch": alg_bytes[k]})
+        main_roof = next((r for r in roof if r["kernel"] == dom), roof[0] if roof else None)
+        if main_roof is not None:
+            main_roof = dict(main_roof)
+            main_roof["peak_source"] = peak_src
+            if dom == "match":
+                # the matcher is bound by the integer POPC pipe, not by HBM: report that roofline beside it
+                sm_mhz = clocks.get("sm_mhz") or 1965.0
+                popc_peak = 148 * 16 * sm_mhz * 1e6               # POPC lanes/clk/SM x SMs x clock
+                popc = B * kpf * kpf * 8 / (shares["match"]["ms_per_launch"] * 1e-3)
+                main_roof["popc_pipe"] = {"achieved_gpopc_s": popc / 1e9, "peak_gpopc_s": popc_peak / 1e9,
+                                          "frac": popc / popc_peak,
+                                          "note": "peak = 148 SMs x 16 POPC/clk/SM x sampled SM clock"}
+
+        # ---- bounded CPU baseline (rank 0, N=1 only) ----------------------------------------------
+        cpu = None
+        if world == 1:
+            from oracle.pyoracle import Oracle
+            ora = Oracle(native=True)
+            ns = args.cpu_sample
+            cpu_step(ora, frames, 0, 2)
+            t0 = time.perf_counter()
+            cpu_step(ora, frames, 0, ns)
+            dt = time.perf_counter() - t0
+            cpu = {"value": ns / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                   "sample": f"{ns} frames of the same batch (pyramid+Detect+cross-checked BF match), oracle -O3 AVX2/FMA "
+                             f"build, single thread like the reference's own code; host has {os.cpu_count()} logical CPUs"}
+
+        line = {
+            "metric": "tracked frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(B, "one batch of independent frames per GPU per step"),
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES, "d2h_bytes_per_step": d2h_bytes[0],
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": main_roof,
+            "roofline_kernels": roof,
+            "kernel_shares": shares,
+            "cpu_baseline": cpu,
+            "keypoints_per_frame": kpf,
+        }
+        print(json.dumps(line))
+    fr.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

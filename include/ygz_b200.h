@@ -1,0 +1,146 @@
+/*
+ * ygz_b200.h -- C ABI of libygz_b200.so: the B200 (sm_100a) implementation of the ygz-slam
+ * per-frame tracking + local-BA hot path.
+ *
+ * The reference (PaoPaoRobot/ygz-slam) has no plugin / FFI layer: its boundary for this path is the
+ * public C++ API of libygz-algorithm.so.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference root).  The C++ shim classes in
+ * ygz_slam_b200/host/ keep the reference's class/method names on top of this ABI so that
+ * the reference callers under src/Module compile against them unchanged.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer, the context owns device memory;
+ *   - every call returns YGZB_OK (0) or a negative error code and never throws; ygzb_last_error()
+ *     returns the message of the last failure on that context;
+ *   - one context = one device + one stream; thread-compatible (one context per host thread), like
+ *     the reference's per-instance scratch (Matcher.h:143-150, FeatureDetector.h:93-98);
+ *   - all batched calls take `n` independent items (frames, pairs, patches) -- n = 1 is the
+ *     reference's one-frame-at-a-time call;
+ *   - there is NO CPU fallback: without a usable sm_100 device ygzb_create fails.
+ *   - poses T_cw are 3x4 row-major [R|t] doubles (12 per pose) unless stated otherwise.
+ */
+#ifndef YGZ_B200_H_
+#define YGZ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YGZB_OK 0
+#define YGZB_ERR_INVALID (-1)   /* bad argument */
+#define YGZB_ERR_CUDA (-2)      /* CUDA runtime error (message in ygzb_last_error) */
+#define YGZB_ERR_NO_DEVICE (-3) /* no sm_100 device: there is no CPU fallback */
+#define YGZB_ERR_CAPACITY (-4)  /* an output or scratch capacity was exceeded */
+
+#define YGZB_MAX_LEVELS 10
+
+typedef struct ygzb_ctx ygzb_ctx;
+typedef struct ygzb_frames ygzb_frames;
+
+/* Filled from the reference's YAML keys (config/default.yaml) and Option structs.            */
+typedef struct {
+    int image_width;     /* image.width  (640)                                                */
+    int image_height;    /* image.height (480)                                                */
+    int n_levels;        /* Frame::Option::_pyramid_level (include/ygz/Basic/Frame.h:22-24)   */
+    int cell_size;       /* feature.cell (10)           FeatureDetector.cpp:335               */
+    int fast_threshold;  /* short(feature.detection_threshold) = 15   FeatureDetector.cpp:338 */
+    float fx, fy, cx, cy;/* camera.* -- stored as float like PinholeCamera (Camera.h:14-22)   */
+} ygzb_params;
+
+void ygzb_default_params(ygzb_params* p);
+int ygzb_create(int device, const ygzb_params* p, ygzb_ctx** out);
+void ygzb_destroy(ygzb_ctx* ctx);
+const char* ygzb_last_error(const ygzb_ctx* ctx);
+int ygzb_synchronize(ygzb_ctx* ctx);
+/* the context's cudaStream_t, for callers that time or order work themselves */
+void* ygzb_stream(ygzb_ctx* ctx);
+/* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
+long long ygzb_launch_count(const ygzb_ctx* ctx);
+
+/* optional per-stage device timing: when enabled every kernel launch is bracketed by CUDA events on
+ * the context stream; ygzb_profile_read synchronises, sums the elapsed ms and launch counts per stage
+ * (arrays of ygzb_profile_stage_count() entries) and resets the record.                          */
+int ygzb_profile_enable(ygzb_ctx* ctx, int on);
+int ygzb_profile_read(ygzb_ctx* ctx, double* ms, int32_t* launches);
+int ygzb_profile_stage_count(void);
+const char* ygzb_profile_stage_name(int stage);
+
+/* page-locked host memory for the batched entry points (plain malloc'ed buffers also work) */
+int ygzb_host_alloc(void** ptr, size_t bytes);
+int ygzb_host_free(void* ptr);
+
+/* ---- frames: device-resident image pyramids -------------------------------------------------
+ * replaces Frame::InitFrame / CreateImagePyramid (src/Basic/Frame.cpp:22-40: cvtColor + pyrDown). */
+int ygzb_frames_create(ygzb_ctx* ctx, int capacity, ygzb_frames** out);
+void ygzb_frames_destroy(ygzb_frames* f);
+/* host -> device copy of `count` images into slots [first, first+count) and pyramid build.
+ * channels 1 (grey) or 3 (BGR); frame_stride = bytes between consecutive host images.          */
+int ygzb_frames_upload(ygzb_frames* f, int first, int count, const uint8_t* host, int channels,
+                       size_t frame_stride);
+/* pyramid build only, for level-0 images already resident in slot storage (bench "value" leg) */
+int ygzb_frames_build_pyramid(ygzb_frames* f, int first, int count);
+/* device pointer / geometry of slot storage, level 0 first, every level pitch-linear */
+int ygzb_frames_layout(const ygzb_frames* f, int* lw, int* lh, int* lpitch, size_t* loff, size_t* slot_stride);
+void* ygzb_frames_device_ptr(ygzb_frames* f);
+/* copy one level of one slot back to the host (tests) */
+int ygzb_frames_download_level(ygzb_frames* f, int slot, int level, uint8_t* host /* lw*lh, packed */);
+
+/* ---- FeatureDetector ------------------------------------------------------------------------
+ * replaces FeatureDetector::Detect (src/Algorithm/FeatureDetector.cpp:345-444; header
+ * include/ygz/Algorithm/FeatureDetector.h:63): grid FAST-10 over the pyramid, 3x3 non-max, best
+ * Shi-Tomasi per cell, IC angle, rotated-BRIEF descriptor.  Results stay on the device (slot feature
+ * store) for ygzb_match_frames and are returned packed, frame after frame, in cell-index order. */
+typedef struct {
+    int32_t* offsets; /* n+1 : features of item i are [offsets[i], offsets[i+1])                 */
+    float* x;         /* full-resolution pixel = level coordinate * 2^level  (Feature::_pixel)   */
+    float* y;
+    uint8_t* level;   /* Feature::_level */
+    float* score;     /* Feature::_score (Shi-Tomasi) */
+    float* angle;     /* Feature::_angle, degrees */
+    uint8_t* desc;    /* 32 bytes per feature (Feature::_desc) */
+    int32_t* cell;    /* grid cell of the feature (may be NULL) */
+    int capacity;     /* capacity of the packed arrays, in features */
+} ygzb_keypoints;
+
+/* slots[i] selects the frame of item i.  occupied: n * grid_rows*grid_cols bytes (non-zero = cell
+ * holds an old feature: SetExistingFeatures, :446-464) or NULL (= overwrite_existing_features).
+ * out may be NULL (results only kept on the device).                                          */
+int ygzb_detect(ygzb_frames* f, const int32_t* slots, int n, const uint8_t* occupied, ygzb_keypoints* out);
+int ygzb_grid_dims(const ygzb_ctx* ctx, int* rows, int* cols);
+
+/* replaces FeatureDetector::ComputeAngleAndDescriptor (:580-588) for caller-supplied pixels:
+ * item i owns features [offsets[i], offsets[i+1]) of x/y/level (full-res pixels, double like
+ * Feature::_pixel); angle/desc are outputs.                                                  */
+int ygzb_describe(ygzb_frames* f, const int32_t* slots, int n, const int32_t* offsets, const double* x,
+                  const double* y, const uint8_t* level, float* angle, uint8_t* desc);
+
+/* parity/debug view of the FAST stage of one slot and level (the call sites at
+ * FeatureDetector.cpp:365-381): raster-order corner list, bisection scores and the indices kept by
+ * fast_nonmax_3x3 -- the "FAST keypoint indices" the north star asks to match bit-exactly.     */
+int ygzb_fast_debug(ygzb_frames* f, int slot, int level, int capacity, int16_t* xy, int32_t* scores,
+                    int32_t* n_corners, int32_t* nonmax_idx, int32_t* n_nonmax);
+/* per-level counters of the last ygzb_detect: stats[(i*n_levels + L)*2 + {0,1}] = corners, nonmax */
+int ygzb_detect_stats(ygzb_frames* f, int n, int32_t* stats);
+
+/* ---- Matcher: descriptors -------------------------------------------------------------------
+ * replaces cv::BFMatcher(cv::NORM_HAMMING, crossCheck).match (test/test_orb_match.cpp:87-92) with
+ * Matcher::DescriptorDistance (src/Algorithm/Matcher.cpp:30-43) as the metric.
+ * train_idx[i] = -1 / dist[i] = -1 when query i has no (cross-checked) match.                  */
+int ygzb_match_bf(ygzb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B, int nB, int cross_check,
+                  int32_t* train_idx, int32_t* dist);
+/* same, on the device-resident features of n_pairs slot pairs (a_slots[i] = query frame,
+ * b_slots[i] = train frame); results packed per pair: query q of pair i is at q_offsets[i]+q.  */
+int ygzb_match_frames(ygzb_frames* f, const int32_t* a_slots, const int32_t* b_slots, int n_pairs,
+                      int cross_check, int32_t* q_offsets /* n_pairs+1 */, int32_t* train_idx, int32_t* dist,
+                      int capacity);
+/* replaces the distance loop of Matcher::CheckFrameDescriptors (Matcher.cpp:45-84) */
+int ygzb_hamming_pairs(ygzb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* ia,
+                       const int32_t* ib, int n, int32_t* dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YGZ_B200_H_ */

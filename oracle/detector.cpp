@@ -125,7 +125,7 @@ void orb_descriptor(const Level& im, double px, double py, int level, float angl
     const long c = (long)ora_cv_round_d(py / scale) * im.w + ora_cv_round_d(px / scale);
     const int step = im.w;
     const int8_t* pat = kOrbPattern;
-    for (int i = 0; i < 32; ++i, pat += 64) {
+    for (int i = 0; i < 32; ++i, pat += 32) {  // 16 cv::Point = 8 tests per byte
         int val = 0;
         for (int k = 0; k < 8; ++k) {
             const int x0 = pat[4 * k], y0 = pat[4 * k + 1], x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];

@@ -17,10 +17,14 @@ MAX_LEVELS = 10
 
 
 def build(force: bool = False) -> None:
-    """Compile liboracle.so / liboracle_native.so with oracle/Makefile (g++)."""
-    if force or not (_HERE / "liboracle.so").exists() or not (_HERE / "liboracle_native.so").exists():
+    """Compile liboracle.so / liboracle_native.so with oracle/Makefile (g++); make tracks staleness."""
+    have = (_HERE / "liboracle.so").exists() and (_HERE / "liboracle_native.so").exists()
+    try:
         subprocess.run(["make", "-C", str(_HERE), "-j4"] + (["-B"] if force else []), check=True,
-                       stdout=subprocess.DEVNULL)
+                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    except (subprocess.CalledProcessError, FileNotFoundError) as e:
+        if not have:
+            raise RuntimeError(f"cannot build the oracle: {getattr(e, 'stderr', e)}")
 
 
 class DetectParams(C.Structure):

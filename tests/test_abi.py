@@ -1,0 +1,41 @@
+"""CPU suite: the C-ABI library builds, loads and exports every symbol include/ygz_b200.h declares.
+No compute calls (no GPU here); creating a context must fail loudly, not fall back to a CPU path."""
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "ygz_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ygzb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ygz_slam_b200 import capi
+    lib = capi.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(capi.EXPORTS) == syms
+
+
+def test_no_cpu_fallback():
+    import torch
+    from ygz_slam_b200 import Context, YgzbError
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu suite")
+    with pytest.raises(YgzbError):
+        Context(0)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may use oracle/ (checker, never shipped)."""
+    for p in (ROOT / "ygz_slam_b200").rglob("*"):
+        if p.suffix in {".py", ".cu", ".cuh", ".cpp", ".h", ".hpp"}:
+            txt = p.read_text(errors="ignore")
+            assert "pyoracle" not in txt and "liboracle" not in txt and "oracle.h" not in txt, p

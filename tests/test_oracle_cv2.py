@@ -1,0 +1,147 @@
+"""CPU suite: pins the oracle's OpenCV-owned arithmetic against cv2 (the reference's own dependency,
+importable here) and its FAST restatement structurally.  No GPU."""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+
+def test_bgr2gray_matches_cv2(oracle):
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    assert np.array_equal(oracle.bgr2gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (15, 20), (15, 21), (8, 10), (4, 5), (30, 40), (7, 9)])
+def test_pyrdown_matches_cv2(oracle, shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(oracle.pyrdown(img), cv2.pyrDown(img))
+
+
+def test_pyramid_8_levels_matches_cv2(oracle, synth_frames):
+    g = synth_frames[0][0]
+    pyr = oracle.build_pyramid(g, 8)
+    lv = g
+    for L in range(1, 8):
+        lv = cv2.pyrDown(lv)
+        assert np.array_equal(oracle.level_view(pyr, 640, 480, 8, L), lv)
+    assert lv.shape == (4, 5)
+
+
+def test_fast_atan2_matches_cv2(oracle):
+    rng = np.random.default_rng(1)
+    ys = rng.integers(-40000, 40000, 5000).astype(np.float32)
+    xs = rng.integers(-40000, 40000, 5000).astype(np.float32)
+    for y, x in zip(ys, xs):
+        assert oracle.fast_atan2(y, x) == np.float32(cv2.fastAtan2(float(y), float(x)))
+    assert oracle.fast_atan2(0.0, 0.0) == np.float32(cv2.fastAtan2(0.0, 0.0))
+
+
+def test_fast_ring_geometry_against_cv2_fast9(oracle, synth_frames):
+    """cv2 only ships FAST 9/16; with the arc length switched to 9 the oracle's segment test must
+    give the same corner set, which pins the ring offsets, strictness and the scan range."""
+    g = synth_frames[0][0]
+    f = cv2.FastFeatureDetector_create(threshold=15, nonmaxSuppression=False, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    want = sorted((int(k.pt[1]), int(k.pt[0])) for k in f.detect(g))
+    got = sorted((int(y), int(x)) for x, y in oracle.fast_detect(g, 15, arc=9))
+    assert got == want and len(got) > 1000
+
+
+def test_fast10_score_closed_form_and_raster_order(oracle, synth_frames):
+    g = synth_frames[0][0]
+    xy = oracle.fast_detect(g, 15)
+    assert len(xy) > 1000
+    lin = xy[:, 1].astype(np.int64) * 640 + xy[:, 0]
+    assert np.all(np.diff(lin) > 0)  # raster order
+    sc = oracle.fast_score(g, xy)
+    ring = [(0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, -3), (-1, -3), (-2, -2), (-3, -1),
+            (-3, 0), (-3, 1), (-2, 2), (-1, 3)]
+    gi = g.astype(np.int32)
+    for i in range(0, len(xy), 7):
+        x, y = xy[i]
+        d = [gi[y + dy, x + dx] - gi[y, x] for dx, dy in ring]
+        best = max(max(min(d[(s + k) % 16] for k in range(10)), min(-d[(s + k) % 16] for k in range(10)))
+                   for s in range(16))
+        assert best - 1 == sc[i]
+    assert sc.min() >= 15
+
+
+def test_fast_nonmax_equals_dense_8_neighbour_rule(oracle, synth_frames):
+    g = synth_frames[1][0]
+    xy = oracle.fast_detect(g, 15)
+    sc = oracle.fast_score(g, xy)
+    nm = oracle.fast_nonmax(xy, sc)
+    S = np.zeros((480, 640), np.int32)
+    S[xy[:, 1], xy[:, 0]] = sc
+    keep = []
+    for i, (x, y) in enumerate(xy):
+        nb = S[y - 1:y + 2, x - 1:x + 2].copy()
+        nb[1, 1] = -1
+        if not (nb >= sc[i]).any():
+            keep.append(i)
+    assert np.array_equal(np.array(keep, np.int32), nm)
+
+
+def test_bf_match_matches_cv2(oracle, synth_frames):
+    f1 = oracle.detect(oracle.build_pyramid(synth_frames[0][0], 3))
+    f2 = oracle.detect(oracle.build_pyramid(synth_frames[1][0], 3))
+    assert f1["n"] > 500 and f2["n"] > 500
+    for cross in (True, False):
+        idx, dist = oracle.match_bf(f1["desc"], f2["desc"], cross)
+        ms = cv2.BFMatcher(cv2.NORM_HAMMING, cross).match(f1["desc"], f2["desc"])
+        cvidx = -np.ones(f1["n"], np.int32)
+        cvd = -np.ones(f1["n"], np.int32)
+        for m in ms:
+            cvidx[m.queryIdx] = m.trainIdx
+            cvd[m.queryIdx] = int(m.distance)
+        assert np.array_equal(idx, cvidx) and np.array_equal(dist, cvd)
+    # ties: duplicated rows must resolve like OpenCV (first minimum; the later of two tied queries is dropped)
+    A = np.repeat(f1["desc"][:50], 2, axis=0)
+    B = np.repeat(f2["desc"][:60], 2, axis=0)
+    idx, dist = oracle.match_bf(A, B, True)
+    ms = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(A, B)
+    cvidx = -np.ones(len(A), np.int32)
+    for m in ms:
+        cvidx[m.queryIdx] = m.trainIdx
+    assert np.array_equal(idx, cvidx)
+
+
+def test_descriptor_distance_is_popcount(oracle):
+    rng = np.random.default_rng(3)
+    A = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    d, keep, n = oracle.check_descriptors(A, B, np.arange(64), np.arange(64))
+    want = np.unpackbits(A ^ B, axis=1).sum(1)
+    assert np.array_equal(d, want)
+    best = min(max(want.min(), 30), 100)
+    assert np.array_equal(keep, want < 3.0 * best) and n == keep.sum()
+
+
+def test_detect_semantics(oracle, synth_frames):
+    """Grid selection invariants of FeatureDetector::Detect on a synthetic frame."""
+    g = synth_frames[0][0]
+    pyr = oracle.build_pyramid(g, 3)
+    f = oracle.detect(pyr)
+    assert 800 < f["n"] <= 3072
+    # one feature per cell, emitted in cell order; pixel = level coordinate * 2^level
+    assert np.all(np.diff(f["cell"]) > 0)
+    gx = (f["px"] // 10).astype(int)
+    gy = (f["py"] // 10).astype(int)
+    assert np.array_equal(gy * 64 + gx, f["cell"])
+    assert np.all(f["px"] % (1 << f["level"]) == 0)
+    # the double-scaled InFrame (hazard 3): level-L coordinates must be >= 20 * 2^L
+    lx = f["px"] / (1 << f["level"])
+    assert np.all(lx >= 20 * (1 << f["level"]))
+    assert set(np.unique(f["level"])) <= {0, 1, 2}
+    # levels >= 3 can never contribute: an 8-level pyramid yields the same features
+    f8 = oracle.detect(oracle.build_pyramid(g, 8), n_levels=8)
+    assert f8["n"] == f["n"] and np.array_equal(f8["desc"], f["desc"])
+    # occupied cells are skipped (SetExistingFeatures)
+    occ = np.zeros(3072, np.uint8)
+    occ[f["cell"][::2]] = 1
+    f2 = oracle.detect(pyr, occupied=occ)
+    assert np.array_equal(f2["cell"], f["cell"][1::2])
+    # describe() on the detected pixels reproduces angle + descriptor
+    ang, desc = oracle.describe(pyr, 640, 480, 3, f["px"], f["py"], f["level"])
+    assert np.array_equal(ang, f["angle"]) and np.array_equal(desc, f["desc"])

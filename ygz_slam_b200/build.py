@@ -1,0 +1,71 @@
+"""Build libygz_b200.so (hand-written sm_100a CUDA + the extern "C" ABI) in-tree with nvcc."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB = HERE / "libygz_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
+    "-Xptxas", "-v",
+]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(exe).exists():
+        raise RuntimeError("nvcc not found: libygz_b200.so cannot be built (there is no CPU fallback)")
+    return exe
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + [HERE.parent / "include" / "ygz_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    objdir = HERE / "build"
+    objdir.mkdir(exist_ok=True)
+    objs = []
+    procs = []
+    for src in sources():
+        obj = objdir / (src.stem + ".o")
+        objs.append(obj)
+        cmd = [nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src.name}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src.name}")
+    (objdir / "ptxas.log").write_text("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", LIB)

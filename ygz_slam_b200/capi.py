@@ -1,0 +1,328 @@
+"""ctypes binding of libygz_b200.so (include/ygz_b200.h).  Plumbing only: numpy arrays in/out."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+MAX_LEVELS = 10
+_LIB = None
+
+
+class YgzbError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return HERE / "libygz_b200.so"
+
+
+class Params(C.Structure):
+    _fields_ = [("image_width", C.c_int), ("image_height", C.c_int), ("n_levels", C.c_int), ("cell_size", C.c_int),
+                ("fast_threshold", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class Keypoints(C.Structure):
+    _fields_ = [("offsets", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p), ("level", C.c_void_p),
+                ("score", C.c_void_p), ("angle", C.c_void_p), ("desc", C.c_void_p), ("cell", C.c_void_p),
+                ("capacity", C.c_int)]
+
+
+# every symbol include/ygz_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "ygzb_default_params", "ygzb_create", "ygzb_destroy", "ygzb_last_error", "ygzb_synchronize", "ygzb_stream",
+    "ygzb_launch_count", "ygzb_profile_enable", "ygzb_profile_read", "ygzb_profile_stage_count",
+    "ygzb_profile_stage_name", "ygzb_host_alloc", "ygzb_host_free", "ygzb_frames_create", "ygzb_frames_destroy",
+    "ygzb_frames_upload", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
+    "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
+    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs",
+]
+
+
+def load_library(build_if_missing: bool = True):
+    """Load libygz_b200.so; fails loudly if it is missing and cannot be built (no CPU fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not p.exists():
+        if not build_if_missing:
+            raise YgzbError(f"{p} is missing: build it with `python -m ygz_slam_b200.build` (there is no CPU fallback)")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(str(p))
+    lib.ygzb_last_error.restype = C.c_char_p
+    lib.ygzb_last_error.argtypes = [C.c_void_p]
+    lib.ygzb_stream.restype = C.c_void_p
+    lib.ygzb_stream.argtypes = [C.c_void_p]
+    lib.ygzb_launch_count.restype = C.c_longlong
+    lib.ygzb_launch_count.argtypes = [C.c_void_p]
+    lib.ygzb_frames_device_ptr.restype = C.c_void_p
+    lib.ygzb_frames_device_ptr.argtypes = [C.c_void_p]
+    lib.ygzb_destroy.argtypes = [C.c_void_p]
+    lib.ygzb_destroy.restype = None
+    lib.ygzb_frames_destroy.argtypes = [C.c_void_p]
+    lib.ygzb_frames_destroy.restype = None
+    lib.ygzb_default_params.restype = None
+    lib.ygzb_profile_stage_name.restype = C.c_char_p
+    _LIB = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device + one stream (ygzb_ctx)."""
+
+    def __init__(self, device: int = 0, **overrides):
+        self.lib = load_library()
+        prm = Params()
+        self.lib.ygzb_default_params(C.byref(prm))
+        for k, v in overrides.items():
+            if not hasattr(prm, k):
+                raise TypeError(f"unknown parameter {k}")
+            setattr(prm, k, v)
+        self.params = prm
+        h = C.c_void_p()
+        rc = self.lib.ygzb_create(device, C.byref(prm), C.byref(h))
+        self.h = h
+        if rc != 0:
+            msg = self.lib.ygzb_last_error(h).decode() if h else ""
+            if h:
+                self.lib.ygzb_destroy(h)
+                self.h = None
+            raise YgzbError(f"ygzb_create failed (rc={rc}): {msg or 'no usable sm_100 device; there is no CPU fallback'}")
+        rows, cols = C.c_int(), C.c_int()
+        self.lib.ygzb_grid_dims(self.h, C.byref(rows), C.byref(cols))
+        self.grid_rows, self.grid_cols = rows.value, cols.value
+        self.n_cells = rows.value * cols.value
+        self.n_levels = prm.n_levels
+
+    def check(self, rc: int, what: str = ""):
+        if rc != 0:
+            raise YgzbError(f"{what} failed (rc={rc}): {self.lib.ygzb_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ygzb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self.check(self.lib.ygzb_synchronize(self.h), "ygzb_synchronize")
+
+    @property
+    def stream(self) -> int:
+        return self.lib.ygzb_stream(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return self.lib.ygzb_launch_count(self.h)
+
+    def profile(self, on: bool):
+        self.check(self.lib.ygzb_profile_enable(self.h, int(on)), "ygzb_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{stage: (total ms, launches)} since the last read (CUDA events around each kernel)."""
+        n = self.lib.ygzb_profile_stage_count()
+        ms = (C.c_double * n)()
+        cnt = (C.c_int32 * n)()
+        self.check(self.lib.ygzb_profile_read(self.h, ms, cnt), "ygzb_profile_read")
+        return {self.lib.ygzb_profile_stage_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
+
+    def frames(self, capacity: int) -> "Frames":
+        return Frames(self, capacity)
+
+    # ---- Matcher -------------------------------------------------------------------------------
+    def match_bf(self, A, B, cross_check=True):
+        A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32)
+        B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+        idx = np.full(len(A), -1, np.int32)
+        dist = np.full(len(A), -1, np.int32)
+        self.check(self.lib.ygzb_match_bf(self.h, _p(A), len(A), _p(B), len(B), int(cross_check), _p(idx), _p(dist)),
+                   "ygzb_match_bf")
+        return idx, dist
+
+    def hamming_pairs(self, A, B, ia, ib):
+        A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32)
+        B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+        ia = np.ascontiguousarray(ia, np.int32)
+        ib = np.ascontiguousarray(ib, np.int32)
+        dist = np.empty(len(ia), np.int32)
+        self.check(self.lib.ygzb_hamming_pairs(self.h, _p(A), len(A), _p(B), len(B), _p(ia), _p(ib), len(ia), _p(dist)),
+                   "ygzb_hamming_pairs")
+        return dist
+
+
+class Frames:
+    """Device-resident pyramids + feature store for `capacity` frame slots (ygzb_frames)."""
+
+    def __init__(self, ctx: Context, capacity: int):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.capacity = capacity
+        h = C.c_void_p()
+        ctx.check(self.lib.ygzb_frames_create(ctx.h, capacity, C.byref(h)), "ygzb_frames_create")
+        self.h = h
+        lw = (C.c_int * MAX_LEVELS)()
+        lh = (C.c_int * MAX_LEVELS)()
+        lp = (C.c_int * MAX_LEVELS)()
+        lo = (C.c_size_t * MAX_LEVELS)()
+        ss = C.c_size_t()
+        self.lib.ygzb_frames_layout(self.h, lw, lh, lp, lo, C.byref(ss))
+        n = ctx.n_levels
+        self.lw, self.lh, self.lpitch, self.loff = list(lw)[:n], list(lh)[:n], list(lp)[:n], list(lo)[:n]
+        self.slot_stride = ss.value
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.lib.ygzb_frames_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_ptr(self) -> int:
+        return self.lib.ygzb_frames_device_ptr(self.h)
+
+    def upload(self, images, first: int = 0):
+        """images: (n,h,w) grey or (n,h,w,3) BGR uint8 (or a raw pointer + n via upload_raw)."""
+        images = np.ascontiguousarray(images, np.uint8)
+        if images.ndim == 2:
+            images = images[None]
+        channels = 3 if images.ndim == 4 else 1
+        n = images.shape[0]
+        stride = images.strides[0]
+        self.ctx.check(self.lib.ygzb_frames_upload(self.h, first, n, _p(images), channels, C.c_size_t(stride)),
+                       "ygzb_frames_upload")
+
+    def upload_raw(self, ptr: int, n: int, channels: int, frame_stride: int, first: int = 0):
+        self.ctx.check(self.lib.ygzb_frames_upload(self.h, first, n, C.c_void_p(ptr), channels, C.c_size_t(frame_stride)),
+                       "ygzb_frames_upload")
+
+    def build_pyramid(self, first: int, count: int):
+        self.ctx.check(self.lib.ygzb_frames_build_pyramid(self.h, first, count), "ygzb_frames_build_pyramid")
+
+    def download_level(self, slot: int, level: int) -> np.ndarray:
+        out = np.empty((self.lh[level], self.lw[level]), np.uint8)
+        self.ctx.check(self.lib.ygzb_frames_download_level(self.h, slot, level, _p(out)), "ygzb_frames_download_level")
+        return out
+
+    # ---- FeatureDetector -------------------------------------------------------------------------
+    def detect(self, slots, occupied=None, fetch: bool = True):
+        slots = np.ascontiguousarray(slots, np.int32)
+        n = len(slots)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8).reshape(n, self.ctx.n_cells)
+        if not fetch:
+            self.ctx.check(self.lib.ygzb_detect(self.h, _p(slots), n, _p(occ), None), "ygzb_detect")
+            return None
+        cap = n * self.ctx.n_cells
+        if getattr(self, "_kp_cap", 0) < cap:
+            self._kp = dict(offsets=np.empty(self.capacity + 1, np.int32), x=np.empty(cap, np.float32),
+                            y=np.empty(cap, np.float32), level=np.empty(cap, np.uint8), score=np.empty(cap, np.float32),
+                            angle=np.empty(cap, np.float32), desc=np.empty((cap, 32), np.uint8), cell=np.empty(cap, np.int32))
+            self._kp_cap = cap
+        b = self._kp
+        kp = Keypoints(*[b[k].ctypes.data for k in ("offsets", "x", "y", "level", "score", "angle", "desc", "cell")], cap)
+        self.ctx.check(self.lib.ygzb_detect(self.h, _p(slots), n, _p(occ), C.byref(kp)), "ygzb_detect")
+        off = b["offsets"][: n + 1].copy()
+        out = []
+        for i in range(n):
+            s, e = off[i], off[i + 1]
+            out.append(dict(n=int(e - s), px=b["x"][s:e].astype(np.float64), py=b["y"][s:e].astype(np.float64),
+                            level=b["level"][s:e].astype(np.int32), score=b["score"][s:e].copy(),
+                            angle=b["angle"][s:e].copy(), desc=b["desc"][s:e].copy(), cell=b["cell"][s:e].copy()))
+        return out
+
+    def detect_packed(self, slots, occupied=None):
+        """Like detect() but returns (offsets[n+1], packed arrays dict) without per-frame splitting."""
+        slots = np.ascontiguousarray(slots, np.int32)
+        n = len(slots)
+        occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8).reshape(n, self.ctx.n_cells)
+        cap = n * self.ctx.n_cells
+        if getattr(self, "_kp_cap", 0) < cap:
+            self._kp = dict(offsets=np.empty(self.capacity + 1, np.int32), x=np.empty(cap, np.float32),
+                            y=np.empty(cap, np.float32), level=np.empty(cap, np.uint8), score=np.empty(cap, np.float32),
+                            angle=np.empty(cap, np.float32), desc=np.empty((cap, 32), np.uint8), cell=np.empty(cap, np.int32))
+            self._kp_cap = cap
+        b = self._kp
+        kp = Keypoints(*[b[k].ctypes.data for k in ("offsets", "x", "y", "level", "score", "angle", "desc", "cell")], cap)
+        self.ctx.check(self.lib.ygzb_detect(self.h, _p(slots), n, _p(occ), C.byref(kp)), "ygzb_detect")
+        return b["offsets"][: n + 1], b
+
+    def match_packed(self, a_slots, b_slots, cross_check=True):
+        a = np.ascontiguousarray(a_slots, np.int32)
+        b = np.ascontiguousarray(b_slots, np.int32)
+        n = len(a)
+        cap = n * self.ctx.n_cells
+        if getattr(self, "_mp_cap", 0) < cap:
+            self._mp = (np.empty(n + 1, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32))
+            self._mp_cap = cap
+        qoff, idx, dist = self._mp
+        if len(qoff) < n + 1:
+            qoff = np.empty(n + 1, np.int32)
+            self._mp = (qoff, idx, dist)
+        self.ctx.check(self.lib.ygzb_match_frames(self.h, _p(a), _p(b), n, int(cross_check), _p(qoff), _p(idx), _p(dist),
+                                                  cap), "ygzb_match_frames")
+        return qoff[: n + 1], idx, dist
+
+    def detect_stats(self, n: int) -> np.ndarray:
+        st = np.empty((n, self.ctx.n_levels, 2), np.int32)
+        self.ctx.check(self.lib.ygzb_detect_stats(self.h, n, _p(st)), "ygzb_detect_stats")
+        return st
+
+    def describe(self, slots, offsets, px, py, level):
+        slots = np.ascontiguousarray(slots, np.int32)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        px = np.ascontiguousarray(px, np.float64)
+        py = np.ascontiguousarray(py, np.float64)
+        level = np.ascontiguousarray(level, np.uint8)
+        total = int(offsets[-1])
+        angle = np.empty(total, np.float32)
+        desc = np.empty((total, 32), np.uint8)
+        self.ctx.check(self.lib.ygzb_describe(self.h, _p(slots), len(slots), _p(offsets), _p(px), _p(py), _p(level),
+                                              _p(angle), _p(desc)), "ygzb_describe")
+        return angle, desc
+
+    def fast_debug(self, slot: int, level: int):
+        cap = self.lw[level] * self.lh[level]
+        xy = np.empty((cap, 2), np.int16)
+        scores = np.empty(cap, np.int32)
+        nm = np.empty(cap, np.int32)
+        nc, nn = C.c_int32(), C.c_int32()
+        self.ctx.check(self.lib.ygzb_fast_debug(self.h, slot, level, cap, _p(xy), _p(scores), C.byref(nc), _p(nm),
+                                                C.byref(nn)), "ygzb_fast_debug")
+        return xy[: nc.value].copy(), scores[: nc.value].copy(), nm[: nn.value].copy()
+
+    # ---- Matcher -----------------------------------------------------------------------------------
+    def match(self, a_slots, b_slots, cross_check=True, fetch: bool = True):
+        a = np.ascontiguousarray(a_slots, np.int32)
+        b = np.ascontiguousarray(b_slots, np.int32)
+        n = len(a)
+        if not fetch:
+            self.ctx.check(self.lib.ygzb_match_frames(self.h, _p(a), _p(b), n, int(cross_check), None, None, None, 0),
+                           "ygzb_match_frames")
+            return None
+        cap = n * self.ctx.n_cells
+        if getattr(self, "_m_cap", 0) < cap:
+            self._m = (np.empty(self.capacity * 4 + 1, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32))
+            self._m_cap = cap
+        qoff, idx, dist = self._m
+        if len(qoff) < n + 1:
+            qoff = np.empty(n + 1, np.int32)
+        self.ctx.check(self.lib.ygzb_match_frames(self.h, _p(a), _p(b), n, int(cross_check), _p(qoff), _p(idx), _p(dist),
+                                                  cap), "ygzb_match_frames")
+        return [(idx[qoff[i]: qoff[i + 1]].copy(), dist[qoff[i]: qoff[i + 1]].copy()) for i in range(n)]

@@ -1,0 +1,144 @@
+// common.cuh -- shared declarations of libygz_b200.so (context, slot storage, launch helpers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ygz_b200.h"
+
+namespace ygzb {
+
+constexpr int kMaxLevels = YGZB_MAX_LEVELS;
+
+// FAST / cell-selection tile (level pixels).  80 x 40 is a whole number of 10-px grid cells on the
+// three levels that can yield features (8x4, 16x8, 32x16 cells).
+constexpr int kTileW = 80;
+constexpr int kTileH = 40;
+
+struct LevelGeom {
+    int w, h, pitch;   // pitch in bytes, multiple of 16
+    unsigned off;      // byte offset of the level inside a slot
+};
+
+struct Geometry {
+    LevelGeom lv[kMaxLevels];
+    int n_levels;
+    int n_sel_levels;  // levels [0, n_sel_levels) can pass Frame::InFrame(px, 20, L); the others never yield features
+    int W, H;          // full resolution (image.width / image.height)
+    int cell_size, grid_cols, grid_rows, n_cells;
+    int threshold;
+    int tile_begin[kMaxLevels + 1];  // prefix sums of tiles per level
+    int tiles_x[kMaxLevels];
+};
+
+}  // namespace ygzb
+
+struct ygzb_ctx {
+    int device;
+    cudaStream_t stream;
+    ygzb_params prm;
+    ygzb::Geometry geo;
+    size_t slot_stride;  // bytes per frame slot (pyramid), multiple of 256
+    int sm_count;
+    long long launches;
+    char err[512];
+    // growable device / pinned scratch owned by the context
+    void* d_scratch[8];
+    size_t d_scratch_bytes[8];
+    void* h_scratch[4];
+    size_t h_scratch_bytes[4];
+    // optional per-stage CUDA-event timing (ygzb_profile_*): events bracket each kernel on ctx->stream
+    int prof_on;
+    void* prof;  // std::vector<ygzb::ProfRec>*
+};
+
+struct ygzb_frames {
+    ygzb_ctx* ctx;
+    int capacity;
+    uint8_t* d_pyr;       // capacity * slot_stride
+    // device feature store, per slot, capacity n_cells features each (cell-index order)
+    int32_t* d_count;     // [capacity]
+    int16_t* d_fx;        // level coordinates
+    int16_t* d_fy;
+    uint8_t* d_flevel;
+    float* d_fscore;
+    float* d_fangle;
+    int32_t* d_fcell;
+    uint8_t* d_fdesc;     // [capacity][n_cells][32]
+    // detect scratch (sized for `capacity` items)
+    unsigned long long* d_best_key;   // [capacity][n_sel][n_cells]
+    unsigned long long* d_first_key;  // [capacity][n_sel][n_cells]
+    int32_t* d_stats;                 // [capacity][n_levels][2]
+    int32_t* d_slots;                 // [capacity] slot list of the current call
+    uint8_t* d_occupied;              // [capacity][n_cells]
+    int32_t* d_offsets;               // [capacity+1]
+    int last_n;
+};
+
+namespace ygzb {
+
+int set_error(ygzb_ctx* ctx, int code, const char* fmt, ...);
+int check_cuda(ygzb_ctx* ctx, cudaError_t e, const char* what);
+// grow-only scratch buffers
+void* dev_scratch(ygzb_ctx* ctx, int which, size_t bytes);
+void* host_scratch(ygzb_ctx* ctx, int which, size_t bytes);
+
+#define YGZB_CUDA(ctx, call)                                               \
+    do {                                                                   \
+        int _rc = ygzb::check_cuda((ctx), (call), #call);                  \
+        if (_rc != YGZB_OK) return _rc;                                    \
+    } while (0)
+
+#define YGZB_LAUNCHED(ctx)                                                 \
+    do {                                                                   \
+        (ctx)->launches++;                                                 \
+        int _rc = ygzb::check_cuda((ctx), cudaGetLastError(), "kernel launch"); \
+        if (_rc != YGZB_OK) return _rc;                                    \
+    } while (0)
+
+// ---- per-stage device timing -------------------------------------------------------------------
+enum Stage {
+    kStageBgr2Gray = 0, kStagePyrDown, kStageFastCells, kStageMergeCells, kStageDescribe, kStageMatch,
+    kStageMatchFinalize, kStagePack, kStageOther, kNumStages
+};
+struct ProfRec {
+    cudaEvent_t a, b;
+    int stage;
+};
+void prof_begin(ygzb_ctx* ctx, int stage);
+void prof_end(ygzb_ctx* ctx);
+struct ProfScope {
+    ygzb_ctx* c;
+    ProfScope(ygzb_ctx* ctx, int stage) : c(ctx) { if (c->prof_on) prof_begin(c, stage); }
+    ~ProfScope() { if (c->prof_on) prof_end(c); }
+};
+
+// ---- stage launchers (one .cu each) -----------------------------------------------------------
+int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr /* or null */);
+int launch_detect(ygzb_frames* f, int n, bool have_occupied);
+int launch_describe_store(ygzb_frames* f, int n);
+int launch_describe_list(ygzb_frames* f, int n, const int32_t* d_slot_of, int total, const double* d_x, const double* d_y,
+                         const uint8_t* d_level, float* d_angle, uint8_t* d_desc);
+int launch_fast_debug(ygzb_frames* f, int slot, int level, uint8_t* d_score_map, uint8_t* d_nonmax_map);
+int launch_offsets(ygzb_ctx* ctx, const int32_t* d_counts, const int32_t* d_sets, int n, int32_t* d_offsets);
+int launch_match(ygzb_ctx* ctx, const uint8_t* d_base, size_t set_stride, const int32_t* d_counts, const int32_t* d_a_sets,
+                 const int32_t* d_b_sets, int n_pairs, int cap, int cross_check, unsigned* d_fwd_key, unsigned* d_col_key,
+                 const int32_t* d_q_offsets, int32_t* d_train_idx, int32_t* d_dist);
+int launch_hamming_pairs(ygzb_ctx* ctx, const uint8_t* d_A, const uint8_t* d_B, const int32_t* d_ia, const int32_t* d_ib,
+                         int n, int32_t* d_dist);
+
+// device helpers shared by kernels ---------------------------------------------------------------
+__device__ __forceinline__ unsigned float_orderable(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float orderable_float(unsigned o) {
+    unsigned u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(u);
+}
+
+}  // namespace ygzb

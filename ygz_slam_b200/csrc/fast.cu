@@ -1,0 +1,419 @@
+// fast.cu -- FAST-10 detect + score + 3x3 non-max + per-grid-cell Shi-Tomasi selection, fused.
+//
+// Replaces the per-level body of FeatureDetector::Detect (reference
+// src/Algorithm/FeatureDetector.cpp:362-427):
+//     fast::fast_corner_detect_10_sse2 / fast_corner_score_10 / fast_nonmax_3x3     (:365-381)
+//     frame->InFrame(px, 20, L)  (include/ygz/Basic/Frame.h:67-71, double-scaled)   (:386)
+//     cell index, _old_features skip, ShiTomasiScore, keep the strictly best per cell (:391-425)
+// and FeatureDetector::ShiTomasiScore (:467-507).
+//
+// One CTA = one 80x40 tile of one pyramid level of one frame; ALL levels of ALL frames of a batch go
+// in a single launch (blockIdx.x walks the tiles of every level, blockIdx.y the frames).  The tile
+// (+5 px halo) is staged in shared memory once; every later read (16-px ring, 3x3 score
+// neighbourhood, 10x10 Shi-Tomasi window) hits shared memory, so HBM sees each pyramid byte once
+// (+ halo): algorithmic traffic = 409,600 B per 8-level frame.
+//
+// Ordering semantics without an ordered corner list: the reference walks nonmax corners level by
+// level in raster order and replaces a cell's candidate only on a STRICTLY larger score.  That is
+// "max score, ties -> earliest (level, raster)", with one twist: a NaN score on the very first
+// candidate of a cell sticks forever (nothing compares greater than NaN), a NaN later never wins.
+// Each tile owns whole cells, so it reduces candidates with two 64-bit shared-memory atomics
+//     first = min (raster << 32 | score bits)          -> the earliest candidate and its score
+//     best  = max (orderable(score) << 32 | ~raster)   -> the best non-NaN score, earliest on ties
+// and merge_cells_kernel replays the level order.  All f32 maths is unfused (-fmad=false).
+#include "common.cuh"
+
+namespace ygzb {
+
+namespace {
+
+constexpr int kSmW = 96;            // smem tile pitch : x in [x0-8, x0+88)
+constexpr int kSmH = kTileH + 10;   // 50 rows         : y in [y0-5, y0+45)
+constexpr int kScW = kTileW + 2;    // score region 82 x 42 : tile + 1 px ring
+constexpr int kScH = kTileH + 2;
+constexpr int kScPitch = 84;
+constexpr int kMaxTileCells = 512;
+constexpr unsigned long long kEmptyFirst = ~0ull;
+
+struct DetectArgs {
+    const uint8_t* pyr;
+    size_t slot_stride;
+    const int32_t* slots;
+    const uint8_t* occupied;  // [n][n_cells] or null
+    unsigned long long* best_key;
+    unsigned long long* first_key;
+    int32_t* stats;
+    Geometry g;
+};
+
+__device__ __forceinline__ bool has_run10(unsigned m16) {
+    unsigned x = m16 | (m16 << 16);
+    unsigned r2 = x & (x >> 1);
+    unsigned r4 = r2 & (r2 >> 2);
+    unsigned r8 = r4 & (r4 >> 4);
+    unsigned r10 = r8 & (r2 >> 8);
+    return (r10 & 0xFFFFu) != 0;
+}
+
+// Bresenham ring of radius 3 in circular order: RDX/RDY below (dx,dy), index 0 = (0,3)
+template <int PITCH>
+__device__ __forceinline__ bool fast_is_corner(const uint8_t* __restrict__ c, int b) {
+    const int p = *c;
+    const int cb = p + b, c_b = p - b;
+    // every 10-arc contains one pixel of each opposite pair: test (0,8) first
+    const int v0 = c[3 * PITCH], v8 = c[-3 * PITCH];
+    if (!((v0 > cb) | (v8 > cb) | (v0 < c_b) | (v8 < c_b))) return false;
+    const int v4 = c[3], v12 = c[-3];
+    if (!((v4 > cb) | (v12 > cb) | (v4 < c_b) | (v12 < c_b))) return false;
+    constexpr int RDX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr int RDY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    unsigned bright = 0, dark = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int v = c[RDY[i] * PITCH + RDX[i]];
+        bright |= (unsigned)(v > cb) << i;
+        dark |= (unsigned)(v < c_b) << i;
+    }
+    return has_run10(bright) || has_run10(dark);
+}
+
+// fast_corner_score_10 in closed form: the bisection returns the largest b for which the pixel is
+// still a corner = max over the 16 arcs of (min over the arc of the signed difference) - 1.
+template <int PITCH>
+__device__ __forceinline__ int fast_score(const uint8_t* __restrict__ c) {
+    constexpr int RDX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr int RDY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    const int p = *c;
+    int d[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = (int)c[RDY[i] * PITCH + RDX[i]] - p;
+    int lo2[16], hi2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        lo2[i] = min(d[i], d[(i + 1) & 15]);
+        hi2[i] = max(d[i], d[(i + 1) & 15]);
+    }
+    int lo4[16], hi4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        lo4[i] = min(lo2[i], lo2[(i + 2) & 15]);
+        hi4[i] = max(hi2[i], hi2[(i + 2) & 15]);
+    }
+    int best_bright = -256, best_dark = 256;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int lo8 = min(lo4[i], lo4[(i + 4) & 15]);
+        const int hi8 = max(hi4[i], hi4[(i + 4) & 15]);
+        best_bright = max(best_bright, min(lo8, lo2[(i + 8) & 15]));  // min over arc i..i+9
+        best_dark = min(best_dark, max(hi8, hi2[(i + 8) & 15]));      // max over arc i..i+9
+    }
+    return max(best_bright, -best_dark) - 1;
+}
+
+// FeatureDetector::ShiTomasiScore on a staged tile (c = centre pixel in smem)
+template <int PITCH>
+__device__ __forceinline__ float shi_tomasi(const uint8_t* __restrict__ c) {
+    float dXX = 0.f, dYY = 0.f, dXY = 0.f;  // sums of integer products < 2^24: exact in any order
+#pragma unroll
+    for (int yy = -4; yy < 4; ++yy) {
+#pragma unroll
+        for (int xx = -4; xx < 4; ++xx) {
+            const uint8_t* q = c + yy * PITCH + xx;
+            const int dx = (int)q[1] - (int)q[-1];
+            const int dy = (int)q[PITCH] - (int)q[-PITCH];
+            dXX += (float)(dx * dx);
+            dYY += (float)(dy * dy);
+            dXY += (float)(dx * dy);
+        }
+    }
+    dXX = dXX * 0.0078125f;  // / (2.0 * 64): exact
+    dYY = dYY * 0.0078125f;
+    dXY = dXY * 0.0078125f;
+    const float s = __fadd_rn(dXX, dYY);
+    const float disc = __fsub_rn(__fmul_rn(s, s), __fmul_rn(4.f, __fsub_rn(__fmul_rn(dXX, dYY), __fmul_rn(dXY, dXY))));
+    return __fmul_rn(0.5f, __fsub_rn(s, __fsqrt_rn(disc)));
+}
+
+__global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
+    __shared__ __align__(16) uint8_t s_img[kSmH * kSmW];
+    __shared__ __align__(16) uint8_t s_score[kScH * kScPitch];
+    __shared__ uint16_t s_list[kScH * kScW];
+    __shared__ unsigned long long s_best[kMaxTileCells];
+    __shared__ unsigned long long s_first[kMaxTileCells];
+    __shared__ int s_n, s_ncorner, s_nnonmax;
+
+    const Geometry& g = a.g;
+    const int tid = threadIdx.x;
+    int L = 0;
+    while (L + 1 < g.n_levels && (int)blockIdx.x >= g.tile_begin[L + 1]) ++L;
+    const int t = blockIdx.x - g.tile_begin[L];
+    const int ty = t / g.tiles_x[L], tx = t - ty * g.tiles_x[L];
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+    const LevelGeom lv = g.lv[L];
+    const int item = blockIdx.y;
+    const uint8_t* __restrict__ img = a.pyr + (size_t)a.slots[item] * a.slot_stride + lv.off;
+    const bool selectable = L < g.n_sel_levels;
+
+    if (tid == 0) s_n = s_ncorner = s_nnonmax = 0;
+    for (int i = tid; i < kScH * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(s_score)[i] = 0;
+    for (int i = tid; i < kMaxTileCells; i += 256) {
+        s_best[i] = 0ull;
+        s_first[i] = kEmptyFirst;
+    }
+    // stage tile + halo, zero outside the image (never used: FAST stays 3 px inside, Shi-Tomasi
+    // returns 0 when its window touches the border)
+    for (int i = tid; i < kSmH * (kSmW / 4); i += 256) {
+        const int r = i / (kSmW / 4), k = i - r * (kSmW / 4);
+        const int y = y0 - 5 + r, x = x0 - 8 + 4 * k;
+        uint32_t v = 0;
+        if (y >= 0 && y < lv.h) {
+            const uint8_t* row = img + (size_t)y * lv.pitch;
+            if (x >= 0 && x + 3 < lv.w) {
+                v = *reinterpret_cast<const uint32_t*>(row + x);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x + j >= 0 && x + j < lv.w) v |= (uint32_t)row[x + j] << (8 * j);
+            }
+        }
+        reinterpret_cast<uint32_t*>(s_img)[i] = v;
+    }
+    __syncthreads();
+
+    // pass A: segment test on tile + 1 px ring, corners appended to s_list (any order)
+    for (int idx = tid; idx < kScH * kScW; idx += 256) {
+        const int ry = idx / kScW, rx = idx - ry * kScW;
+        const int x = x0 - 1 + rx, y = y0 - 1 + ry;
+        if (x < 3 || x >= lv.w - 3 || y < 3 || y >= lv.h - 3) continue;
+        const uint8_t* c = s_img + (ry + 4) * kSmW + (rx + 7);
+        if (fast_is_corner<kSmW>(c, g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
+    }
+    __syncthreads();
+    const int n_corner = s_n;
+
+    // pass B: score of every corner into the dense score tile (0 = not a corner; scores are >= threshold > 0)
+    for (int i = tid; i < n_corner; i += 256) {
+        const int idx = s_list[i];
+        const int ry = idx / kScW, rx = idx - ry * kScW;
+        s_score[ry * kScPitch + rx] = (uint8_t)fast_score<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7));
+    }
+    __syncthreads();
+
+    // pass C: 3x3 non-max on the tile interior, then cell selection
+    const int scale = 1 << L;
+    const int cpt_x = kTileW * scale / g.cell_size;          // cells per tile row at this level
+    const int cx0 = x0 * scale / g.cell_size, cy0 = y0 * scale / g.cell_size;
+    for (int i = tid; i < n_corner; i += 256) {
+        const int idx = s_list[i];
+        const int ry = idx / kScW, rx = idx - ry * kScW;
+        if (rx < 1 || rx > kTileW || ry < 1 || ry > kTileH) continue;  // ring pixels belong to a neighbour tile
+        atomicAdd(&s_ncorner, 1);
+        const uint8_t* sc = s_score + ry * kScPitch + rx;
+        const int s = *sc;
+        // fast_nonmax_3x3: dropped if any 8-neighbour corner scores >= s
+        if (sc[-1] >= s || sc[1] >= s || sc[-kScPitch - 1] >= s || sc[-kScPitch] >= s || sc[-kScPitch + 1] >= s ||
+            sc[kScPitch - 1] >= s || sc[kScPitch] >= s || sc[kScPitch + 1] >= s)
+            continue;
+        atomicAdd(&s_nnonmax, 1);
+        if (!selectable) continue;
+        const int x = x0 - 1 + rx, y = y0 - 1 + ry;
+        // Frame::InFrame(Vector2d(x,y), 20, L): x/2^L >= 20 && x/2^L < W-20 (exact in integers)
+        if (x < 20 * scale || x >= (g.W - 20) * scale || y < 20 * scale || y >= (g.H - 20) * scale) continue;
+        const int gy = (y * scale) / g.cell_size, gx = (x * scale) / g.cell_size;
+        const int k = gy * g.grid_cols + gx;
+        if (k >= g.n_cells) continue;
+        if (a.occupied && a.occupied[(size_t)item * g.n_cells + k]) continue;
+        float score = 0.f;
+        if (!(x - 4 < 1 || x + 4 >= lv.w - 1 || y - 4 < 1 || y + 4 >= lv.h - 1))
+            score = shi_tomasi<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7));
+        const int li = (gy - cy0) * cpt_x + (gx - cx0);
+        const unsigned raster = (unsigned)(y * lv.w + x);
+        atomicMin(&s_first[li], ((unsigned long long)raster << 32) | __float_as_uint(score));
+        if (!isnan(score))
+            atomicMax(&s_best[li], ((unsigned long long)float_orderable(score) << 32) | (0xFFFFFFFFu - raster));
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        int32_t* st = a.stats + ((size_t)item * g.n_levels + L) * 2;
+        if (s_ncorner) atomicAdd(st, s_ncorner);
+        if (s_nnonmax) atomicAdd(st + 1, s_nnonmax);
+    }
+    if (selectable) {
+        const int cpt_y = kTileH * scale / g.cell_size;
+        const size_t base = ((size_t)item * g.n_sel_levels + L) * g.n_cells;
+        for (int li = tid; li < cpt_x * cpt_y; li += 256) {
+            const int gy = cy0 + li / cpt_x, gx = cx0 + li % cpt_x;
+            if (gy >= g.grid_rows || gx >= g.grid_cols) continue;
+            a.best_key[base + gy * g.grid_cols + gx] = s_best[li];
+            a.first_key[base + gy * g.grid_cols + gx] = s_first[li];
+        }
+    }
+}
+
+// replay of the level order per grid cell + ordered compaction into the slot's feature store
+__global__ void __launch_bounds__(1024) merge_cells_kernel(const unsigned long long* __restrict__ best_key,
+                                                           const unsigned long long* __restrict__ first_key,
+                                                           const int32_t* __restrict__ slots, Geometry g, int32_t* count,
+                                                           int16_t* fx, int16_t* fy, uint8_t* flevel, float* fscore,
+                                                           int32_t* fcell) {
+    constexpr int kMaxPerThread = 8;
+    __shared__ int s_warp[32];
+    const int item = blockIdx.x, tid = threadIdx.x;
+    const int per = (g.n_cells + 1023) / 1024;
+    const int k0 = tid * per, k1 = min(g.n_cells, k0 + per);
+    int wl[kMaxPerThread], wx[kMaxPerThread], wy[kMaxPerThread], wk[kMaxPerThread];
+    float ws[kMaxPerThread];
+    int nloc = 0;
+    for (int k = k0; k < k1; ++k) {
+        bool have = false, stuck = false;
+        int bl = 0;
+        unsigned braster = 0;
+        float bscore = 0.f;
+        for (int L = 0; L < g.n_sel_levels && !stuck; ++L) {
+            const size_t o = ((size_t)item * g.n_sel_levels + L) * g.n_cells + k;
+            const unsigned long long fk = first_key[o];
+            if (fk == kEmptyFirst) continue;
+            const unsigned long long bk = best_key[o];
+            if (!have) {
+                const float fs = __uint_as_float((unsigned)fk);
+                if (isnan(fs)) {  // first candidate of the cell is NaN: it is never replaced
+                    have = stuck = true;
+                    bl = L;
+                    braster = (unsigned)(fk >> 32);
+                    bscore = fs;
+                } else {
+                    have = true;
+                    bl = L;
+                    braster = 0xFFFFFFFFu - (unsigned)bk;
+                    bscore = orderable_float((unsigned)(bk >> 32));
+                }
+            } else if (bk != 0ull) {
+                const float s = orderable_float((unsigned)(bk >> 32));
+                if (s > bscore) {
+                    bl = L;
+                    braster = 0xFFFFFFFFu - (unsigned)bk;
+                    bscore = s;
+                }
+            }
+        }
+        if (have && nloc < kMaxPerThread) {
+            wl[nloc] = bl;
+            wy[nloc] = braster / g.lv[bl].w;
+            wx[nloc] = braster - wy[nloc] * g.lv[bl].w;
+            ws[nloc] = bscore;
+            wk[nloc] = k;
+            ++nloc;
+        }
+    }
+    // block exclusive scan of nloc
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = nloc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += u;
+        }
+        s_warp[lane] = v;
+    }
+    __syncthreads();
+    const int base = (warp ? s_warp[warp - 1] : 0) + incl - nloc;
+    const size_t so = (size_t)slots[item] * g.n_cells;
+    // cells of one thread are consecutive and its winners were pushed in cell order
+    for (int w = 0; w < nloc; ++w) {
+        fx[so + base + w] = (int16_t)wx[w];
+        fy[so + base + w] = (int16_t)wy[w];
+        flevel[so + base + w] = (uint8_t)wl[w];
+        fscore[so + base + w] = ws[w];
+        fcell[so + base + w] = wk[w];
+    }
+    if (tid == 1023) count[slots[item]] = base + nloc;
+}
+
+// ---- parity/debug: dense score map and nonmax flags of one level, straight from global memory ---
+__global__ void fast_debug_score_kernel(const uint8_t* __restrict__ img, LevelGeom lv, int threshold,
+                                        uint8_t* __restrict__ score_map) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= lv.w) return;
+    int s = 0;
+    if (x >= 3 && x < lv.w - 3 && y >= 3 && y < lv.h - 3) {
+        // gather the 7x7 neighbourhood into a private pitch-8 window so the templated code is shared
+        uint8_t win[7 * 8];
+        for (int j = 0; j < 7; ++j)
+            for (int i = 0; i < 7; ++i) win[j * 8 + i] = img[(size_t)(y - 3 + j) * lv.pitch + (x - 3 + i)];
+        const uint8_t* c = win + 3 * 8 + 3;
+        if (fast_is_corner<8>(c, threshold)) s = fast_score<8>(c);
+    }
+    score_map[(size_t)y * lv.w + x] = (uint8_t)s;
+}
+
+__global__ void fast_debug_nonmax_kernel(const uint8_t* __restrict__ score_map, int w, int h,
+                                         uint8_t* __restrict__ nonmax_map) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int s = score_map[(size_t)y * w + x];
+    int keep = s > 0;
+    for (int dy = -1; dy <= 1 && keep; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (!dx && !dy) continue;
+            const int xx = x + dx, yy = y + dy;
+            if (xx < 0 || xx >= w || yy < 0 || yy >= h) continue;
+            if (score_map[(size_t)yy * w + xx] >= s) {
+                keep = 0;
+                break;
+            }
+        }
+    nonmax_map[(size_t)y * w + x] = (uint8_t)keep;
+}
+
+}  // namespace
+
+int launch_detect(ygzb_frames* f, int n, bool have_occupied) {
+    ygzb_ctx* ctx = f->ctx;
+    const Geometry& g = ctx->geo;
+    YGZB_CUDA(ctx, cudaMemsetAsync(f->d_stats, 0, (size_t)n * g.n_levels * 2 * sizeof(int32_t), ctx->stream));
+    DetectArgs a;
+    a.pyr = f->d_pyr;
+    a.slot_stride = ctx->slot_stride;
+    a.slots = f->d_slots;
+    a.occupied = have_occupied ? f->d_occupied : nullptr;
+    a.best_key = f->d_best_key;
+    a.first_key = f->d_first_key;
+    a.stats = f->d_stats;
+    a.g = g;
+    dim3 grid(g.tile_begin[g.n_levels], n);
+    {
+        ProfScope ps(ctx, kStageFastCells);
+        fast_cells_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    }
+    YGZB_LAUNCHED(ctx);
+    ProfScope ps(ctx, kStageMergeCells);
+    merge_cells_kernel<<<n, 1024, 0, ctx->stream>>>(f->d_best_key, f->d_first_key, f->d_slots, g, f->d_count, f->d_fx,
+                                                    f->d_fy, f->d_flevel, f->d_fscore, f->d_fcell);
+    YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+int launch_fast_debug(ygzb_frames* f, int slot, int level, uint8_t* d_score_map, uint8_t* d_nonmax_map) {
+    ygzb_ctx* ctx = f->ctx;
+    const Geometry& g = ctx->geo;
+    const LevelGeom lv = g.lv[level];
+    const uint8_t* img = f->d_pyr + (size_t)slot * ctx->slot_stride + lv.off;
+    dim3 grid((lv.w + 127) / 128, lv.h);
+    fast_debug_score_kernel<<<grid, 128, 0, ctx->stream>>>(img, lv, g.threshold, d_score_map);
+    YGZB_LAUNCHED(ctx);
+    fast_debug_nonmax_kernel<<<grid, 128, 0, ctx->stream>>>(d_score_map, lv.w, lv.h, d_nonmax_map);
+    YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+}  // namespace ygzb

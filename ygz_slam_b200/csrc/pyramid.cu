@@ -1,0 +1,127 @@
+// pyramid.cu -- Frame::InitFrame / CreateImagePyramid on the device.
+//
+// Replaces (reference src/Basic/Frame.cpp:22-40):
+//     cv::cvtColor(_color, gray, CV_BGR2GRAY);  _pyramid[0] = gray;
+//     for i in 1..levels: cv::pyrDown(_pyramid[i-1], _pyramid[i]);
+// Arithmetic (OpenCV-owned, pinned against cv2 4.13 by the oracle tests):
+//     gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15
+//     pyrDown: separable [1 4 6 4 1], (sum + 128) >> 8, BORDER_REFLECT_101, dst = ((w+1)/2, (h+1)/2)
+//
+// Layout: every frame slot holds all levels back to back, each level pitch-linear with a 16-byte
+// multiple pitch (so level rows can be moved with 16-byte vectors / TMA boxes).
+// Roofline class: HBM.  Algorithmic bytes per frame (8 levels, grey in): 307,200 read + 102,400
+// written = 409,600 B.  One launch handles one level of `count` frames.
+#include "common.cuh"
+
+namespace ygzb {
+
+namespace {
+
+constexpr int kDW = 64;               // dst tile width
+constexpr int kDH = 16;               // dst tile height
+constexpr int kSrcRows = 2 * kDH + 3; // 35
+constexpr int kSrcWords = 34;         // 136 bytes: src x in [2*x0-4, 2*x0+132)
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
+                                                      LevelGeom src, LevelGeom dst) {
+    __shared__ __align__(16) uint8_t s_src[kSrcRows][kSrcWords * 4];
+    __shared__ uint16_t s_h[kSrcRows][kDW];
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kDW, y0 = blockIdx.y * kDH;
+    uint8_t* slot = pyr + (size_t)(first_slot + blockIdx.z) * slot_stride;
+    const uint8_t* __restrict__ sp = slot + src.off;
+    uint8_t* __restrict__ dp = slot + dst.off;
+
+    // stage the source window (reflect-101 at the image border)
+    const int xs = 2 * x0 - 4, ys = 2 * y0 - 2;
+    for (int i = tid; i < kSrcRows * kSrcWords; i += 256) {
+        const int r = i / kSrcWords, k = i - r * kSrcWords;
+        const int y = reflect101(ys + r, src.h);
+        const int x = xs + 4 * k;
+        const uint8_t* row = sp + (size_t)y * src.pitch;
+        uint32_t v;
+        if (x >= 0 && x + 3 < src.w) {
+            v = *reinterpret_cast<const uint32_t*>(row + x);
+        } else {
+            v = (uint32_t)row[reflect101(x, src.w)] | ((uint32_t)row[reflect101(x + 1, src.w)] << 8) |
+                ((uint32_t)row[reflect101(x + 2, src.w)] << 16) | ((uint32_t)row[reflect101(x + 3, src.w)] << 24);
+        }
+        *reinterpret_cast<uint32_t*>(&s_src[r][4 * k]) = v;
+    }
+    __syncthreads();
+
+    // horizontal [1 4 6 4 1]: dst column dx is centred on smem column 2*dx + 4
+    for (int i = tid; i < kSrcRows * kDW; i += 256) {
+        const int r = i / kDW, dx = i - r * kDW;
+        const uint8_t* s = &s_src[r][2 * dx + 2];
+        s_h[r][dx] = (uint16_t)(s[0] + 4 * s[1] + 6 * s[2] + 4 * s[3] + s[4]);
+    }
+    __syncthreads();
+
+    // vertical pass, 4 consecutive dst pixels per thread
+    const int dy = tid >> 4, dx4 = (tid & 15) * 4;
+    const int oy = y0 + dy, ox = x0 + dx4;
+    if (oy >= dst.h || ox >= dst.w) return;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int dx = dx4 + j;
+        const int v = s_h[2 * dy][dx] + 4 * s_h[2 * dy + 1][dx] + 6 * s_h[2 * dy + 2][dx] + 4 * s_h[2 * dy + 3][dx] +
+                      s_h[2 * dy + 4][dx];
+        packed |= (uint32_t)((v + 128) >> 8) << (8 * j);
+    }
+    uint8_t* out = dp + (size_t)oy * dst.pitch + ox;
+    if (ox + 3 < dst.w) {
+        *reinterpret_cast<uint32_t*>(out) = packed;  // pitch % 16 == 0 and ox % 4 == 0
+    } else {
+        for (int j = 0; j < 4 && ox + j < dst.w; ++j) out[j] = (uint8_t)(packed >> (8 * j));
+    }
+}
+
+// cv::cvtColor(BGR2GRAY), 4 pixels per thread
+__global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t* __restrict__ bgr, size_t bgr_frame_stride,
+                                                       uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
+                                                       LevelGeom l0) {
+    const int quads_per_row = (l0.w + 3) / 4;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= quads_per_row * l0.h) return;
+    const int y = q / quads_per_row, x = (q - y * quads_per_row) * 4;
+    const uint8_t* in = bgr + (size_t)blockIdx.y * bgr_frame_stride + ((size_t)y * l0.w + x) * 3;
+    uint8_t* out = pyr + (size_t)(first_slot + blockIdx.y) * slot_stride + l0.off + (size_t)y * l0.pitch + x;
+    for (int j = 0; j < 4 && x + j < l0.w; ++j) {
+        const int b = in[3 * j], g = in[3 * j + 1], r = in[3 * j + 2];
+        out[j] = (uint8_t)((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15);
+    }
+}
+
+}  // namespace
+
+int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr) {
+    ygzb_ctx* ctx = f->ctx;
+    const Geometry& g = ctx->geo;
+    if (count <= 0) return YGZB_OK;
+    if (d_bgr) {
+        const int quads = ((g.lv[0].w + 3) / 4) * g.lv[0].h;
+        dim3 grid((quads + 255) / 256, count);
+        ProfScope ps(ctx, kStageBgr2Gray);
+        bgr2gray_kernel<<<grid, 256, 0, ctx->stream>>>(d_bgr, (size_t)g.lv[0].w * g.lv[0].h * 3, f->d_pyr,
+                                                       ctx->slot_stride, first, g.lv[0]);
+        YGZB_LAUNCHED(ctx);
+    }
+    for (int L = 1; L < g.n_levels; ++L) {
+        dim3 grid((g.lv[L].w + kDW - 1) / kDW, (g.lv[L].h + kDH - 1) / kDH, count);
+        ProfScope ps(ctx, kStagePyrDown);
+        pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g.lv[L - 1], g.lv[L]);
+        YGZB_LAUNCHED(ctx);
+    }
+    return YGZB_OK;
+}
+
+}  // namespace ygzb
