@@ -18,10 +18,10 @@ namespace ygzb {
 
 namespace {
 
-__device__ __constant__ int8_t c_orb_pattern[1024] = {
+// global (not __constant__): the table is copied to shared memory with one coalesced word per thread
+__device__ const int8_t g_orb_pattern[1024] = {
 #include "orb_pattern.inc"
 };
-__device__ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 struct LevelView {
     const uint8_t* img;
@@ -56,20 +56,60 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-// one warp: angle (all lanes return it) and descriptor byte `lane`
+constexpr int kPatchR = 19;                 // EDGE_THRESHOLD: rotated pattern taps stay within +-19 px
+constexpr int kPatchW = 2 * kPatchR + 1;    // 39
+constexpr int kPatchPitch = 48;            // 12 words: a 4-byte aligned span of 44 B always covers the 39 B row
+
+// one warp: stage the (2*19+1)^2 neighbourhood of the centre in shared memory -- every entry is the
+// LINEAR-address tap c + dy*w + dx, so row wrap / outside-buffer semantics are preserved -- then
+// compute the angle (returned by all lanes) and descriptor byte `lane` from shared memory only.
 __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy, const int8_t* __restrict__ s_pat,
-                                             int lane, float* angle_out, uint8_t* byte_out) {
+                                             uint8_t* __restrict__ s_patch, int lane, float* angle_out,
+                                             uint8_t* byte_out) {
     const int c = cy * v.w + cx;
+    const int n_px = v.w * v.h;
+    const int lin_first = c - kPatchR * v.w - kPatchR;   // linear address of the window's first byte
+    const int align = lin_first & 3;
+    int ctr_off = kPatchR * kPatchPitch + kPatchR;
+    // fast path (levels 0-2 of a 640x480 frame away from the buffer ends): rows are 4-byte congruent, so the
+    // window is fetched as 39 x 11 aligned words (14 word loads per lane instead of 78 byte loads)
+    if (v.pitch == v.w && (v.w & 3) == 0 && lin_first - align >= 0 &&
+        lin_first - align + (kPatchW - 1) * v.w + 44 <= n_px) {
+        const uint8_t* src = v.img + (lin_first - align);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_patch);
+#pragma unroll
+        for (int t = 0; t < 14; ++t) {
+            const int f = lane + 32 * t;
+            if (f < kPatchW * 11) {
+                const int r = f / 11, k = f - r * 11;
+                dst[r * (kPatchPitch / 4) + k] = *reinterpret_cast<const uint32_t*>(src + (size_t)r * v.w + 4 * k);
+            }
+        }
+        ctr_off += align;
+    } else {
+        for (int r = 0; r < kPatchW; ++r) {
+            const int lin0 = lin_first + r * v.w;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc = lane + 32 * h;
+                if (cc < kPatchW) s_patch[r * kPatchPitch + cc] = (uint8_t)tap(v, lin0 + cc);
+            }
+        }
+    }
+    __syncwarp();
+    const uint8_t* ctr = s_patch + ctr_off;
+
     // IC_Angle: lane <-> column u = lane - 15 of the radius-15 disc
+    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     const int u = lane - 15;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        m10 = u * tap(v, c + u);
+        m10 = u * (int)ctr[u];
         const int au = u < 0 ? -u : u;
-#pragma unroll 1
+#pragma unroll
         for (int vv = 1; vv <= 15; ++vv) {
-            if (au <= c_umax[vv]) {
-                const int plus = tap(v, c + u + vv * v.w), minus = tap(v, c + u - vv * v.w);
+            if (au <= kUmax[vv]) {
+                const int plus = ctr[vv * kPatchPitch + u], minus = ctr[-vv * kPatchPitch + u];
                 m01 += vv * (plus - minus);
                 m10 += u * (plus + minus);
             }
@@ -80,10 +120,14 @@ __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy,
     const float angle = fast_atan2_deg((float)m01, (float)m10);
     *angle_out = angle;
 
-    // ComputeOrbDescriptor: a = cos, b = sin of angle * (float)(CV_PI/180.f)
+    // ComputeOrbDescriptor: a = cos, b = sin of angle * (float)(CV_PI/180.f); f64 evaluation on two
+    // lanes only (the FP64 pipe is narrow), broadcast by shuffle
     constexpr float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+    float cs = 0.f;
+    if (lane == 0) cs = (float)cos((double)rad);
+    if (lane == 1) cs = (float)sin((double)rad);
+    const float a = __shfl_sync(0xFFFFFFFFu, cs, 0), b = __shfl_sync(0xFFFFFFFFu, cs, 1);
     const int8_t* pat = s_pat + lane * 32;
     int val = 0;
 #pragma unroll
@@ -93,10 +137,12 @@ __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy,
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = tap(v, c + r0 * v.w + c0), t1 = tap(v, c + r1 * v.w + c1);
+        // |r|, |c| <= 19 for every pattern point (|p| <= 13*sqrt(2) < 19), so the staged window covers it
+        const int t0 = ctr[r0 * kPatchPitch + c0], t1 = ctr[r1 * kPatchPitch + c1];
         val |= (t0 < t1) << k;
     }
     *byte_out = (uint8_t)val;
+    __syncwarp();
 }
 
 // features of the slot store (written by merge_cells_kernel): level coordinates are integers
@@ -106,8 +152,9 @@ __global__ void __launch_bounds__(256) describe_store_kernel(const uint8_t* __re
                                                              const int16_t* __restrict__ fx, const int16_t* __restrict__ fy,
                                                              const uint8_t* __restrict__ flevel, float* __restrict__ fangle,
                                                              uint8_t* __restrict__ fdesc) {
-    __shared__ int8_t s_pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += 256) s_pat[i] = c_orb_pattern[i];
+    __shared__ __align__(16) int8_t s_pat[1024];
+    __shared__ __align__(16) uint8_t s_patch[8][kPatchW * kPatchPitch];
+    reinterpret_cast<uint32_t*>(s_pat)[threadIdx.x] = reinterpret_cast<const uint32_t*>(g_orb_pattern)[threadIdx.x];
     __syncthreads();
     const int slot = slots[blockIdx.y];
     const int lane = threadIdx.x & 31;
@@ -118,7 +165,7 @@ __global__ void __launch_bounds__(256) describe_store_kernel(const uint8_t* __re
     LevelView v{pyr + (size_t)slot * slot_stride + g.lv[L].off, g.lv[L].w, g.lv[L].h, g.lv[L].pitch};
     float angle;
     uint8_t byte;
-    describe_one(v, fx[o], fy[o], s_pat, lane, &angle, &byte);
+    describe_one(v, fx[o], fy[o], s_pat, s_patch[threadIdx.x >> 5], lane, &angle, &byte);
     fdesc[o * 32 + lane] = byte;
     if (lane == 0) fangle[o] = angle;
 }
@@ -129,8 +176,9 @@ __global__ void __launch_bounds__(256) describe_list_kernel(const uint8_t* __res
                                                             const double* __restrict__ px, const double* __restrict__ py,
                                                             const uint8_t* __restrict__ level, float* __restrict__ angle_out,
                                                             uint8_t* __restrict__ desc_out) {
-    __shared__ int8_t s_pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += 256) s_pat[i] = c_orb_pattern[i];
+    __shared__ __align__(16) int8_t s_pat[1024];
+    __shared__ __align__(16) uint8_t s_patch[8][kPatchW * kPatchPitch];
+    reinterpret_cast<uint32_t*>(s_pat)[threadIdx.x] = reinterpret_cast<const uint32_t*>(g_orb_pattern)[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -142,7 +190,7 @@ __global__ void __launch_bounds__(256) describe_list_kernel(const uint8_t* __res
     const int cx = __double2int_rn(px[i] / scale), cy = __double2int_rn(py[i] / scale);
     float angle;
     uint8_t byte;
-    describe_one(v, cx, cy, s_pat, lane, &angle, &byte);
+    describe_one(v, cx, cy, s_pat, s_patch[threadIdx.x >> 5], lane, &angle, &byte);
     desc_out[(size_t)i * 32 + lane] = byte;
     if (lane == 0) angle_out[i] = angle;
 }

@@ -56,17 +56,38 @@ __device__ __forceinline__ bool has_run10(unsigned m16) {
 }
 
 // Bresenham ring of radius 3 in circular order: RDX/RDY below (dx,dy), index 0 = (0,3)
+// Cheap necessary condition: a 10-arc contains at least one pixel of EVERY opposite pair, so a bright
+// (dark) corner needs a bright (dark) pixel in each of the pairs (0,8) (4,12) (2,10) (6,14).
 template <int PITCH>
-__device__ __forceinline__ bool fast_is_corner(const uint8_t* __restrict__ c, int b) {
+__device__ __forceinline__ bool fast_quick_test(const uint8_t* __restrict__ c, int b) {
     const int p = *c;
     const int cb = p + b, c_b = p - b;
-    // every 10-arc contains one pixel of each opposite pair: test (0,8) first
-    const int v0 = c[3 * PITCH], v8 = c[-3 * PITCH];
-    if (!((v0 > cb) | (v8 > cb) | (v0 < c_b) | (v8 < c_b))) return false;
-    const int v4 = c[3], v12 = c[-3];
-    if (!((v4 > cb) | (v12 > cb) | (v4 < c_b) | (v12 < c_b))) return false;
+    int v0 = c[3 * PITCH], v1 = c[-3 * PITCH];
+    bool pb = (v0 > cb) | (v1 > cb), pd = (v0 < c_b) | (v1 < c_b);
+    if (!(pb | pd)) return false;
+    v0 = c[3];
+    v1 = c[-3];
+    pb &= (v0 > cb) | (v1 > cb);
+    pd &= (v0 < c_b) | (v1 < c_b);
+    if (!(pb | pd)) return false;
+    v0 = c[2 * PITCH + 2];
+    v1 = c[-2 * PITCH - 2];
+    pb &= (v0 > cb) | (v1 > cb);
+    pd &= (v0 < c_b) | (v1 < c_b);
+    v0 = c[-2 * PITCH + 2];
+    v1 = c[2 * PITCH - 2];
+    pb &= (v0 > cb) | (v1 > cb);
+    pd &= (v0 < c_b) | (v1 < c_b);
+    return pb | pd;
+}
+
+// full segment test: >= 10 contiguous ring pixels all > p+b or all < p-b (strict)
+template <int PITCH>
+__device__ __forceinline__ bool fast_full_test(const uint8_t* __restrict__ c, int b) {
     constexpr int RDX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
     constexpr int RDY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    const int p = *c;
+    const int cb = p + b, c_b = p - b;
     unsigned bright = 0, dark = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -75,6 +96,11 @@ __device__ __forceinline__ bool fast_is_corner(const uint8_t* __restrict__ c, in
         dark |= (unsigned)(v < c_b) << i;
     }
     return has_run10(bright) || has_run10(dark);
+}
+
+template <int PITCH>
+__device__ __forceinline__ bool fast_is_corner(const uint8_t* __restrict__ c, int b) {
+    return fast_quick_test<PITCH>(c, b) && fast_full_test<PITCH>(c, b);
 }
 
 // fast_corner_score_10 in closed form: the bisection returns the largest b for which the pixel is
@@ -110,25 +136,12 @@ __device__ __forceinline__ int fast_score(const uint8_t* __restrict__ c) {
     return max(best_bright, -best_dark) - 1;
 }
 
-// FeatureDetector::ShiTomasiScore on a staged tile (c = centre pixel in smem)
-template <int PITCH>
-__device__ __forceinline__ float shi_tomasi(const uint8_t* __restrict__ c) {
-    float dXX = 0.f, dYY = 0.f, dXY = 0.f;  // sums of integer products < 2^24: exact in any order
-#pragma unroll
-    for (int yy = -4; yy < 4; ++yy) {
-#pragma unroll
-        for (int xx = -4; xx < 4; ++xx) {
-            const uint8_t* q = c + yy * PITCH + xx;
-            const int dx = (int)q[1] - (int)q[-1];
-            const int dy = (int)q[PITCH] - (int)q[-PITCH];
-            dXX += (float)(dx * dx);
-            dYY += (float)(dy * dy);
-            dXY += (float)(dx * dy);
-        }
-    }
-    dXX = dXX * 0.0078125f;  // / (2.0 * 64): exact
-    dYY = dYY * 0.0078125f;
-    dXY = dXY * 0.0078125f;
+// FeatureDetector::ShiTomasiScore tail: the three sums over the 8x8 box are integers < 2^24, so their
+// f32 values are exact whatever the summation order; the rest follows the reference operation by operation.
+__device__ __forceinline__ float shi_tomasi_from_sums(int sxx, int syy, int sxy) {
+    const float dXX = (float)sxx * 0.0078125f;  // / (2.0 * 64): exact
+    const float dYY = (float)syy * 0.0078125f;
+    const float dXY = (float)sxy * 0.0078125f;
     const float s = __fadd_rn(dXX, dYY);
     const float disc = __fsub_rn(__fmul_rn(s, s), __fmul_rn(4.f, __fsub_rn(__fmul_rn(dXX, dYY), __fmul_rn(dXY, dXY))));
     return __fmul_rn(0.5f, __fsub_rn(s, __fsqrt_rn(disc)));
@@ -140,7 +153,10 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     __shared__ uint16_t s_list[kScH * kScW];
     __shared__ unsigned long long s_best[kMaxTileCells];
     __shared__ unsigned long long s_first[kMaxTileCells];
-    __shared__ int s_n, s_ncorner, s_nnonmax;
+    __shared__ uint16_t s_cand[kTileW * kTileH / 4];
+    __shared__ uint16_t s_quick[kScH * kScW];
+    __shared__ uint8_t s_lutx[kTileW], s_luty[kTileH];
+    __shared__ int s_n, s_ncorner, s_nnonmax, s_ncand, s_nquick;
 
     const Geometry& g = a.g;
     const int tid = threadIdx.x;
@@ -154,7 +170,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     const uint8_t* __restrict__ img = a.pyr + (size_t)a.slots[item] * a.slot_stride + lv.off;
     const bool selectable = L < g.n_sel_levels;
 
-    if (tid == 0) s_n = s_ncorner = s_nnonmax = 0;
+    if (tid == 0) s_n = s_ncorner = s_nnonmax = s_ncand = s_nquick = 0;
     for (int i = tid; i < kScH * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(s_score)[i] = 0;
     for (int i = tid; i < kMaxTileCells; i += 256) {
         s_best[i] = 0ull;
@@ -180,13 +196,26 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     }
     __syncthreads();
 
-    // pass A: segment test on tile + 1 px ring, corners appended to s_list (any order)
+    // pass A1: cheap opposite-pair test on tile + 1 px ring; survivors (a few %) are compacted so that the
+    // full 16-pixel segment test (pass A2) runs on dense warps
     for (int idx = tid; idx < kScH * kScW; idx += 256) {
         const int ry = idx / kScW, rx = idx - ry * kScW;
         const int x = x0 - 1 + rx, y = y0 - 1 + ry;
         if (x < 3 || x >= lv.w - 3 || y < 3 || y >= lv.h - 3) continue;
-        const uint8_t* c = s_img + (ry + 4) * kSmW + (rx + 7);
-        if (fast_is_corner<kSmW>(c, g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
+        if (fast_quick_test<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_quick[atomicAdd(&s_nquick, 1)] = (uint16_t)idx;
+    }
+    // grid-cell lookup tables of this tile (local cell column / row of every tile pixel)
+    if (selectable) {
+        const int sc_ = 1 << L;
+        if (tid < kTileW) s_lutx[tid] = (uint8_t)(((x0 + tid) * sc_) / g.cell_size - (x0 * sc_) / g.cell_size);
+        else if (tid < kTileW + kTileH) s_luty[tid - kTileW] = (uint8_t)(((y0 + tid - kTileW) * sc_) / g.cell_size - (y0 * sc_) / g.cell_size);
+    }
+    __syncthreads();
+    const int n_quick = s_nquick;
+    for (int i = tid; i < n_quick; i += 256) {
+        const int idx = s_quick[i];
+        const int ry = idx / kScW, rx = idx - ry * kScW;
+        if (fast_full_test<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
     }
     __syncthreads();
     const int n_corner = s_n;
@@ -199,7 +228,8 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     }
     __syncthreads();
 
-    // pass C: 3x3 non-max on the tile interior, then cell selection
+    // pass C1: 3x3 non-max on the tile interior; survivors that pass InFrame / grid / occupancy become
+    // cell candidates (at most one per 2x2 block: neighbours with equal or larger score kill each other)
     const int scale = 1 << L;
     const int cpt_x = kTileW * scale / g.cell_size;          // cells per tile row at this level
     const int cx0 = x0 * scale / g.cell_size, cy0 = y0 * scale / g.cell_size;
@@ -219,18 +249,41 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
         const int x = x0 - 1 + rx, y = y0 - 1 + ry;
         // Frame::InFrame(Vector2d(x,y), 20, L): x/2^L >= 20 && x/2^L < W-20 (exact in integers)
         if (x < 20 * scale || x >= (g.W - 20) * scale || y < 20 * scale || y >= (g.H - 20) * scale) continue;
-        const int gy = (y * scale) / g.cell_size, gx = (x * scale) / g.cell_size;
+        const int gy = cy0 + s_luty[ry - 1], gx = cx0 + s_lutx[rx - 1];
         const int k = gy * g.grid_cols + gx;
         if (k >= g.n_cells) continue;
         if (a.occupied && a.occupied[(size_t)item * g.n_cells + k]) continue;
-        float score = 0.f;
-        if (!(x - 4 < 1 || x + 4 >= lv.w - 1 || y - 4 < 1 || y + 4 >= lv.h - 1))
-            score = shi_tomasi<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7));
-        const int li = (gy - cy0) * cpt_x + (gx - cx0);
-        const unsigned raster = (unsigned)(y * lv.w + x);
-        atomicMin(&s_first[li], ((unsigned long long)raster << 32) | __float_as_uint(score));
-        if (!isnan(score))
-            atomicMax(&s_best[li], ((unsigned long long)float_orderable(score) << 32) | (0xFFFFFFFFu - raster));
+        s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)idx;
+    }
+    __syncthreads();
+
+    // pass C2: one warp per candidate: Shi-Tomasi on the staged tile (2 pixels per lane, integer sums are
+    // exact so the f32 result equals the reference's sequential accumulation), then the two cell keys
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int n_cand = s_ncand;
+        for (int i = warp; i < n_cand; i += 8) {
+            const int idx = s_cand[i];
+            const int ry = idx / kScW, rx = idx - ry * kScW;
+            const int x = x0 - 1 + rx, y = y0 - 1 + ry;
+            float score = 0.f;
+            if (!(x - 4 < 1 || x + 4 >= lv.w - 1 || y - 4 < 1 || y + 4 >= lv.h - 1)) {  // warp-uniform
+                const uint8_t* q = s_img + (ry + 4 + (lane >> 2) - 4) * kSmW + (rx + 7 + (lane & 3) * 2 - 4);
+                const int dx0 = (int)q[1] - (int)q[-1], dy0 = (int)q[kSmW] - (int)q[-kSmW];
+                const int dx1 = (int)q[2] - (int)q[0], dy1 = (int)q[kSmW + 1] - (int)q[-kSmW + 1];
+                const int sxx = __reduce_add_sync(0xFFFFFFFFu, dx0 * dx0 + dx1 * dx1);
+                const int syy = __reduce_add_sync(0xFFFFFFFFu, dy0 * dy0 + dy1 * dy1);
+                const int sxy = __reduce_add_sync(0xFFFFFFFFu, dx0 * dy0 + dx1 * dy1);
+                score = shi_tomasi_from_sums(sxx, syy, sxy);
+            }
+            if (lane == 0) {
+                const int li = (int)s_luty[ry - 1] * cpt_x + (int)s_lutx[rx - 1];
+                const unsigned raster = (unsigned)(y * lv.w + x);
+                atomicMin(&s_first[li], ((unsigned long long)raster << 32) | __float_as_uint(score));
+                if (!isnan(score))
+                    atomicMax(&s_best[li], ((unsigned long long)float_orderable(score) << 32) | (0xFFFFFFFFu - raster));
+            }
+        }
     }
     __syncthreads();
 

@@ -35,9 +35,22 @@ struct MatchArgs {
     unsigned* col_key;         // [n_pairs][cap]  (dist << 16 | query), pre-set to 0xFFFFFFFF
 };
 
+// 256-bit Hamming distance.  POPC issues at 16 lanes/clk/SM on sm_100 (measured, tools/microbench.cu)
+// against 64 for LOP3, so three carry-save adder steps fold the 8 XOR words into 2 weight-1 and 3
+// weight-2 words: 5 POPC + 14 LOP3 instead of 8 POPC + 8 LOP3 balances the XU and ALU pipes.
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b ^ c;
+    carry = (a & b) | (a & c) | (b & c);
+}
+
 __device__ __forceinline__ int hamming256(const uint32_t (&q)[8], const uint4 lo, const uint4 hi) {
-    return __popc(q[0] ^ lo.x) + __popc(q[1] ^ lo.y) + __popc(q[2] ^ lo.z) + __popc(q[3] ^ lo.w) + __popc(q[4] ^ hi.x) +
-           __popc(q[5] ^ hi.y) + __popc(q[6] ^ hi.z) + __popc(q[7] ^ hi.w);
+    const uint32_t x0 = q[0] ^ lo.x, x1 = q[1] ^ lo.y, x2 = q[2] ^ lo.z, x3 = q[3] ^ lo.w;
+    const uint32_t x4 = q[4] ^ hi.x, x5 = q[5] ^ hi.y, x6 = q[6] ^ hi.z, x7 = q[7] ^ hi.w;
+    uint32_t s0, c0, s1, c1, s2, c2;
+    csa(x0, x1, x2, s0, c0);
+    csa(x3, x4, x5, s1, c1);
+    csa(s0, s1, x6, s2, c2);
+    return __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
 }
 
 template <bool kCross>

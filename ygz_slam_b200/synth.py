@@ -79,12 +79,12 @@ def trajectory(k: int) -> np.ndarray:
 
 
 def render_plane(tex: np.ndarray, T_cw: np.ndarray, plane_z: float = 2.0, metres_per_texel: float = 0.0025,
-                 noise_sigma: float = 0.0, seed: int = 1, w: int = W, h: int = H):
+                 noise_sigma: float = 0.0, seed: int = 1, w: int = W, h: int = H, cx: float = CX, cy: float = CY):
     """Render the texture lying on the world plane z = plane_z.  Returns (gray uint8 HxW, depth f64 HxW)."""
     R, t = T_cw[:, :3], T_cw[:, 3]
     u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
     # ray in camera frame, then world: X_w = R^T (d * ray - t); solve X_w.z = plane_z
-    ray = np.stack([(u - CX) / FX, (v - CY) / FY, np.ones_like(u)], -1)  # h,w,3
+    ray = np.stack([(u - cx) / FX, (v - cy) / FY, np.ones_like(u)], -1)  # h,w,3
     rw = ray @ R  # R^T ray
     cw = -R.T @ t
     d = (plane_z - cw[2]) / rw[..., 2]
