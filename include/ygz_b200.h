@@ -140,6 +140,35 @@ int ygzb_match_frames(ygzb_frames* f, const int32_t* a_slots, const int32_t* b_s
 int ygzb_hamming_pairs(ygzb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* ia,
                        const int32_t* ib, int n, int32_t* dist);
 
+/* ---- cvutils / Matcher: direct (photometric) alignment ---------------------------------------
+ * replaces cvutils::Align2D (src/Algorithm/CVUtils.cpp:186-318; include/ygz/Algorithm/CVUtils.h:163-169):
+ * inverse-compositional alignment of an 8x8 template.  Patch i is searched on pyramid level level[i] of
+ * frame slot[i]; ref_border = n x 100 bytes (10x10 template with border), ref = n x 64 bytes or NULL
+ * (then the inner 8x8 of ref_border); uv = level coordinates in/out; ok = the function's bool.
+ * One thread per patch with the reference's summation order: bit-exact (u, v, ok).               */
+int ygzb_align2d(ygzb_frames* f, int n, const int32_t* slot, const uint8_t* level, const uint8_t* ref_border,
+                 const uint8_t* ref, int n_iter, double* uv, uint8_t* ok);
+
+/* replaces Matcher::FindDirectProjection (src/Algorithm/Matcher.cpp:356-417, both overloads: the caller
+ * supplies the reference depth) incl. GetWarpAffineMatrix / GetBestSearchLevel / WarpAffine
+ * (:420-466, Matcher.h:123-134).  poses = n_poses x 12 (T_cw); candidate i uses frames ref_slot[i] /
+ * cur_slot[i] and poses ref_pose[i] / cur_pose[i]; ref_px = full-res pixel of the reference feature,
+ * cur_px = predicted full-res pixel in/out, search_level / ok = outputs.                          */
+int ygzb_project_align(ygzb_frames* f, int n, const int32_t* ref_slot, const int32_t* cur_slot, int n_poses,
+                       const double* poses, const int32_t* ref_pose, const int32_t* cur_pose, const double* ref_px,
+                       const double* ref_depth, const uint8_t* ref_level, double* cur_px, uint8_t* search_level,
+                       uint8_t* ok);
+
+/* replaces SparseImgAlign::run (src/Algorithm/SparseImageAlign.cpp:21-50; ctor args SparseImageAlign.h:21-27)
+ * for n_problems independent (ref, cur) pairs; problem p owns features [offsets[p], offsets[p+1]) of
+ * px (full-res, 2 per feature) / depth / has_mappoint.  T_cw_cur is the initial pose in, the aligned
+ * pose out; n_meas[p] = the function's return value (n_meas_/16).  Matcher::SparseImageAlignment
+ * (Matcher.cpp:468-492) = this with (2, 0, 30, eps 1e-6) plus the host-side motion-norm check.       */
+int ygzb_sparse_align(ygzb_frames* f, int n_problems, const int32_t* ref_slot, const int32_t* cur_slot,
+                      const int32_t* offsets, const double* px, const double* depth, const uint8_t* has_mappoint,
+                      const double* T_cw_ref, double* T_cw_cur, int max_level, int min_level, int n_iter, double eps,
+                      int32_t* n_meas, int32_t* iters_per_level /* n_problems x YGZB_MAX_LEVELS or NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,117 @@
+"""GPU parity suite for the photometric alignment path (BASELINE config C3): Align2D / FindDirectProjection
+are bit-exact against the oracle (one thread per patch, reference summation order); SparseImgAlign poses
+agree within ||log(T_gpu^-1 T_ref)|| < 1e-4 (block-parallel reduction of the normal equations)."""
+import numpy as np
+import pytest
+
+from ygz_slam_b200 import se3, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(oracle, k0=1, k1=4, levels=3):
+    g1, d1, T1 = synth.stream_frame(k0)
+    g2, _, T2 = synth.stream_frame(k1)
+    p1, p2 = oracle.build_pyramid(g1, levels), oracle.build_pyramid(g2, levels)
+    f = oracle.detect(p1, n_levels=levels)
+    px = np.stack([f["px"], f["py"]], 1)
+    depth = d1[f["py"].astype(int), f["px"].astype(int)]
+    Trel = se3.mul(T2, se3.inv(T1))
+    Xc = np.stack([(px[:, 0] - synth.CX) * depth / synth.FX, (px[:, 1] - synth.CY) * depth / synth.FY, depth], 1)
+    Xc2 = (Trel[:, :3] @ Xc.T).T + Trel[:, 3]
+    gt = np.stack([synth.FX * Xc2[:, 0] / Xc2[:, 2] + synth.CX, synth.FY * Xc2[:, 1] / Xc2[:, 2] + synth.CY], 1)
+    return dict(g1=g1, g2=g2, p1=p1, p2=p2, f=f, px=px, depth=depth, T1=T1, T2=T2, Trel=Trel, gt=gt)
+
+
+def test_align2d_bit_exact(ctx3, oracle):
+    s = _scene(oracle)
+    fr = ctx3.frames(2)
+    fr.upload(np.stack([s["g1"], s["g2"]]))
+    rng = np.random.default_rng(3)
+    n = 2000
+    # templates cut from frame 1 around random points on random levels, searched in frame 2 from a perturbed guess;
+    # some guesses are placed at the border so that the "window leaves the image" break is exercised
+    level = rng.integers(0, 3, n).astype(np.uint8)
+    ref_border = np.empty((n, 100), np.uint8)
+    uv = np.empty((n, 2))
+    for i in range(n):
+        L = int(level[i])
+        img = oracle.level_view(s["p1"], 640, 480, 3, L)
+        h, w = img.shape
+        x, y = int(rng.integers(6, w - 6)), int(rng.integers(6, h - 6))
+        ref_border[i] = img[y - 5:y + 5, x - 5:x + 5].reshape(-1)
+        uv[i] = (x + rng.uniform(-2.5, 2.5), y + rng.uniform(-2.5, 2.5))
+    uv[:50, 0] = rng.uniform(0, 6, 50)
+    slot = np.ones(n, np.int32)
+    got_uv, got_ok = fr.align2d(slot, level, ref_border, None, uv, 10)
+    conv = 0
+    for i in range(n):
+        img = oracle.level_view(s["p2"], 640, 480, 3, int(level[i]))
+        rb = ref_border[i].reshape(10, 10)
+        ok, u, v = oracle.align2d(img, rb, rb[1:9, 1:9], uv[i, 0], uv[i, 1], 10)
+        assert ok == got_ok[i], i
+        assert u == got_uv[i, 0] and v == got_uv[i, 1], (i, u, v, got_uv[i])
+        conv += ok
+    assert conv > 400  # small camera motion: a good part of the random patches really converges
+    fr.close()
+
+
+@pytest.mark.parametrize("identity_ref", [True, False])
+def test_find_direct_projection_bit_exact(ctx3, oracle, identity_ref):
+    s = _scene(oracle)
+    fr = ctx3.frames(2)
+    fr.upload(np.stack([s["g1"], s["g2"]]))
+    rng = np.random.default_rng(7)
+    n = len(s["depth"])
+    init = s["gt"] + rng.uniform(-2, 2, s["gt"].shape)
+    depth = s["depth"].copy()
+    depth[::97] = -1.0  # invalid depth -> false (Matcher.cpp:388-392)
+    if identity_ref:
+        Tr, Tc = np.eye(4)[:3], s["Trel"]
+    else:
+        Tr, Tc = s["T1"], s["T2"]  # exercises the world/ref-camera mix-up of GetWarpAffineMatrix
+    want_px, want_lvl, want_ok = oracle.find_direct_projection(s["p1"], s["p2"], 640, 480, 3, Tr, Tc, s["px"], depth,
+                                                               s["f"]["level"], init)
+    poses = np.stack([Tr.reshape(-1), Tc.reshape(-1)])
+    got_px, got_lvl, got_ok = fr.project_align(np.zeros(n, np.int32), np.ones(n, np.int32), poses, np.zeros(n, np.int32),
+                                               np.ones(n, np.int32), s["px"], depth, s["f"]["level"].astype(np.uint8), init)
+    assert np.array_equal(got_lvl, want_lvl)
+    assert np.array_equal(got_ok, want_ok)
+    assert np.array_equal(got_px, want_px)
+    if identity_ref:
+        assert got_ok.mean() > 0.85
+        err = np.linalg.norm(got_px - s["gt"], axis=1)[got_ok]
+        assert np.median(err) < 0.25
+    fr.close()
+
+
+def _pose_err(Ta, Tb):
+    return float(np.linalg.norm(se3.se3_log(se3.mul(se3.inv(Ta), Tb))))
+
+
+@pytest.mark.parametrize("levels,max_level", [(3, 2), (8, 3)])
+def test_sparse_align_pose_tolerance(levels, max_level, ctx3, ctx8, oracle):
+    ctx = ctx3 if levels == 3 else ctx8
+    s = _scene(oracle, levels=levels)
+    s2 = _scene(oracle, 2, 5, levels=levels)
+    fr = ctx.frames(4)
+    fr.upload(np.stack([s["g1"], s["g2"], s2["g1"], s2["g2"]]))
+    n1, n2 = len(s["depth"]), len(s2["depth"])
+    has1 = np.ones(n1, np.uint8)
+    has1[::11] = 0
+    has2 = np.ones(n2, np.uint8)
+    px = np.concatenate([s["px"], s2["px"]])
+    depth = np.concatenate([s["depth"], s2["depth"]])
+    has = np.concatenate([has1, has2])
+    T_ref = np.stack([s["T1"].reshape(-1), s2["T1"].reshape(-1)])
+    T, n_meas, iters = fr.sparse_align([0, 2], [1, 3], [0, n1, n1 + n2], px, depth, has, T_ref, T_ref, max_level=max_level)
+    for p, (sc, hm) in enumerate(((s, has1), (s2, has2))):
+        wT, wn, wit = oracle.sparse_align(sc["p1"], sc["p2"], 640, 480, levels, sc["px"], sc["depth"], hm, sc["T1"], sc["T1"],
+                                          max_level=max_level)
+        assert _pose_err(T[p], wT) < 1e-4          # stated tolerance
+        assert n_meas[p] == wn
+        assert _pose_err(T[p], sc["T2"]) < 2e-3    # and it really aligned: close to the ground-truth pose
+    # empty problem: pose untouched, zero measurements
+    T0, nm0, _ = fr.sparse_align([0], [1], [0, 0], np.zeros((0, 2)), np.zeros(0), np.zeros(0, np.uint8), T_ref[:1], T_ref[:1])
+    assert nm0[0] == 0 and np.allclose(T0[0].reshape(-1), T_ref[0])
+    fr.close()

@@ -20,6 +20,10 @@ NVCC_FLAGS = [
 ]
 
 
+# per-file extra flags: the f32/f64 parity kernels must not contract a*b+c into FMA
+PER_FILE_FLAGS = {"align.cu": ["-fmad=false"]}
+
+
 def nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not Path(exe).exists():
@@ -49,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in sources():
         obj = objdir / (src.stem + ".o")
         objs.append(obj)
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc(), *NVCC_FLAGS, *PER_FILE_FLAGS.get(src.name, []), "-c", str(src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -37,7 +37,8 @@ EXPORTS = [
     "ygzb_profile_stage_name", "ygzb_host_alloc", "ygzb_host_free", "ygzb_frames_create", "ygzb_frames_destroy",
     "ygzb_frames_upload", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
-    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs",
+    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d",
+    "ygzb_project_align", "ygzb_sparse_align",
 ]
 
 
@@ -326,3 +327,51 @@ class Frames:
         self.ctx.check(self.lib.ygzb_match_frames(self.h, _p(a), _p(b), n, int(cross_check), _p(qoff), _p(idx), _p(dist),
                                                   cap), "ygzb_match_frames")
         return [(idx[qoff[i]: qoff[i + 1]].copy(), dist[qoff[i]: qoff[i + 1]].copy()) for i in range(n)]
+
+
+# ---- photometric alignment (methods attached to Frames) ------------------------------------------------
+def _align2d(self, slot, level, ref_border, ref, uv, n_iter=10):
+    slot = np.ascontiguousarray(slot, np.int32)
+    n = len(slot)
+    level = np.ascontiguousarray(level, np.uint8)
+    rb = np.ascontiguousarray(ref_border, np.uint8).reshape(n, 100)
+    rf = None if ref is None else np.ascontiguousarray(ref, np.uint8).reshape(n, 64)
+    uv = np.ascontiguousarray(uv, np.float64).reshape(n, 2).copy()
+    ok = np.zeros(n, np.uint8)
+    self.ctx.check(self.lib.ygzb_align2d(self.h, n, _p(slot), _p(level), _p(rb), _p(rf), n_iter, _p(uv), _p(ok)), "ygzb_align2d")
+    return uv, ok.astype(bool)
+
+
+def _project_align(self, ref_slot, cur_slot, poses, ref_pose, cur_pose, ref_px, ref_depth, ref_level, cur_px):
+    ref_slot = np.ascontiguousarray(ref_slot, np.int32)
+    n = len(ref_slot)
+    cur_slot = np.ascontiguousarray(cur_slot, np.int32)
+    poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 12)
+    cur = np.ascontiguousarray(cur_px, np.float64).reshape(n, 2).copy()
+    lvl = np.zeros(n, np.uint8)
+    ok = np.zeros(n, np.uint8)
+    self.ctx.check(self.lib.ygzb_project_align(
+        self.h, n, _p(ref_slot), _p(cur_slot), len(poses), _p(poses), _p(np.ascontiguousarray(ref_pose, np.int32)),
+        _p(np.ascontiguousarray(cur_pose, np.int32)), _p(np.ascontiguousarray(ref_px, np.float64)),
+        _p(np.ascontiguousarray(ref_depth, np.float64)), _p(np.ascontiguousarray(ref_level, np.uint8)), _p(cur), _p(lvl), _p(ok)),
+        "ygzb_project_align")
+    return cur, lvl.astype(np.int32), ok.astype(bool)
+
+
+def _sparse_align(self, ref_slot, cur_slot, offsets, px, depth, has_mp, T_ref, T_cur, max_level=2, min_level=0, n_iter=30, eps=1e-6):
+    ref_slot = np.ascontiguousarray(ref_slot, np.int32)
+    P = len(ref_slot)
+    T = np.ascontiguousarray(T_cur, np.float64).reshape(P, 12).copy()
+    nm = np.zeros(P, np.int32)
+    iters = np.zeros((P, MAX_LEVELS), np.int32)
+    self.ctx.check(self.lib.ygzb_sparse_align(
+        self.h, P, _p(ref_slot), _p(np.ascontiguousarray(cur_slot, np.int32)), _p(np.ascontiguousarray(offsets, np.int32)),
+        _p(np.ascontiguousarray(px, np.float64)), _p(np.ascontiguousarray(depth, np.float64)),
+        _p(np.ascontiguousarray(has_mp, np.uint8)), _p(np.ascontiguousarray(T_ref, np.float64).reshape(P, 12)), _p(T),
+        max_level, min_level, n_iter, C.c_double(eps), _p(nm), _p(iters)), "ygzb_sparse_align")
+    return T.reshape(P, 3, 4), nm, iters
+
+
+Frames.align2d = _align2d
+Frames.project_align = _project_align
+Frames.sparse_align = _sparse_align

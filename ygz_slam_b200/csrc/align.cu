@@ -1,0 +1,519 @@
+// align.cu -- 8x8 patch alignment, direct projection (affine warp + alignment) and SVO-style sparse
+// image alignment.  Compiled with -fmad=false: every f32/f64 operation below is evaluated exactly as
+// written, in the reference's order, so the per-patch results are bit-identical to an unfused CPU build.
+//
+// Replaces:
+//   cvutils::Align2D                     reference src/Algorithm/CVUtils.cpp:186-318
+//   cvutils::GetBilateralInterpUchar     reference include/ygz/Algorithm/CVUtils.h:59-71
+//   Matcher::FindDirectProjection        reference src/Algorithm/Matcher.cpp:356-417
+//   Matcher::GetWarpAffineMatrix         reference src/Algorithm/Matcher.cpp:420-436  (incl. the world/ref-camera mix-up)
+//   Matcher::WarpAffine                  reference src/Algorithm/Matcher.cpp:438-466
+//   Matcher::GetBestSearchLevel          reference include/ygz/Algorithm/Matcher.h:123-134
+//   SparseImgAlign::{run,precomputeReferencePatches,computeResiduals,solve,update}
+//                                        reference src/Algorithm/SparseImageAlign.cpp:21-238
+//   NLLSSolver::optimizeGaussNewton      reference include/ygz/Algorithm/NLSSolver_impl.hpp:16-88
+//   cvutils::JacobXYZ2Cam                reference include/ygz/Algorithm/CVUtils.h:77-99
+//
+// Parallel mapping
+//   Align2D / FindDirectProjection: ONE THREAD PER PATCH.  The inverse-compositional loop is a chain of
+//     sequential f32 sums whose rounding decides the convergence flag; keeping the reference's summation
+//     order makes (u, v, ok) bit-exact.  A patch touches <= 1 kB, so thousands of patches per launch keep
+//     the SMs busy through thread-level parallelism (latency-bound, L1/L2-resident; HBM traffic negligible).
+//   SparseImgAlign: ONE CTA PER (ref, cur) PAIR, the whole coarse-to-fine Gauss-Newton loop runs on the
+//     device (no host round trip per iteration): threads stride over features, 16 residuals each; the
+//     6x6 normal equations (21 + 6 doubles) are reduced with warp shuffles + shared memory; thread 0
+//     solves LDL^T and applies T <- T * exp(-x).
+#include "common.cuh"
+#include "se3.cuh"
+
+namespace ygzb {
+
+namespace {
+
+struct LevelImg {
+    const uint8_t* d;
+    int w, h, pitch;
+};
+
+__device__ __forceinline__ LevelImg level_img(const uint8_t* pyr, size_t slot_stride, int slot, const Geometry& g, int L) {
+    return LevelImg{pyr + (size_t)slot * slot_stride + g.lv[L].off, g.lv[L].w, g.lv[L].h, g.lv[L].pitch};
+}
+
+// Eigen's fixed-size 3x3 inverse: cofactors, determinant from column 0, multiply by 1/det
+__device__ void inverse3f(const float H[3][3], float inv[3][3]) {
+#define COF(i, j) (H[(i + 1) % 3][(j + 1) % 3] * H[(i + 2) % 3][(j + 2) % 3] - H[(i + 1) % 3][(j + 2) % 3] * H[(i + 2) % 3][(j + 1) % 3])
+    const float c00 = COF(0, 0), c10 = COF(1, 0), c20 = COF(2, 0);
+    const float det = (c00 * H[0][0] + c10 * H[1][0]) + c20 * H[2][0];
+    const float invdet = 1.0f / det;
+    inv[0][0] = c00 * invdet; inv[0][1] = c10 * invdet; inv[0][2] = c20 * invdet;
+    inv[1][0] = COF(0, 1) * invdet; inv[1][1] = COF(1, 1) * invdet; inv[1][2] = COF(2, 1) * invdet;
+    inv[2][0] = COF(0, 2) * invdet; inv[2][1] = COF(1, 2) * invdet; inv[2][2] = COF(2, 2) * invdet;
+#undef COF
+}
+
+// cvutils::Align2D.  pwb = 10x10 template with border, ref = 8x8 template.  Returns success.
+__device__ bool align2d_dev(const LevelImg& im, const uint8_t* __restrict__ pwb, const uint8_t* __restrict__ ref, int n_iter,
+                            double* pu, double* pv) {
+    const int halfpatch = 4, patch = 8, ref_step = 10;
+    bool converged = false;
+    float H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int y = 0; y < patch; ++y) {
+        const uint8_t* it = pwb + (y + 1) * ref_step + 1;
+        for (int x = 0; x < patch; ++x, ++it) {
+            float J[3];
+            J[0] = (float)(0.5 * ((int)it[1] - (int)it[-1]));
+            J[1] = (float)(0.5 * ((int)it[ref_step] - (int)it[-ref_step]));
+            J[2] = 1.f;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) H[a][b] += J[a] * J[b];
+        }
+    }
+    float Hinv[3][3];
+    inverse3f(H, Hinv);
+    float mean_diff = 0.f;
+    float u = (float)*pu, v = (float)*pv;
+    const float min_update_squared = (float)(0.03 * 0.03);
+    float chi2 = 0.f;
+    for (int iter = 0; iter < n_iter; ++iter) {
+        chi2 = 0.f;
+        const int u_r = (int)floorf(u), v_r = (int)floorf(v);
+        if (u_r < halfpatch || v_r < halfpatch || u_r >= im.w - halfpatch || v_r >= im.h - halfpatch) break;
+        if (isnan(u) || isnan(v)) return false;
+        const float sx = u - (float)u_r, sy = v - (float)v_r;
+        const float wTL = (float)((1.0 - sx) * (1.0 - sy));
+        const float wTR = (float)(sx * (1.0 - sy));
+        const float wBL = (float)((1.0 - sx) * sy);
+        const float wBR = sx * sy;
+        float J0 = 0.f, J1 = 0.f, J2 = 0.f;
+        for (int y = 0; y < patch; ++y) {
+            const uint8_t* it = im.d + (size_t)(v_r + y - halfpatch) * im.pitch + (u_r - halfpatch);
+            const uint8_t* tb = pwb + (y + 1) * ref_step + 1;
+#pragma unroll
+            for (int x = 0; x < patch; ++x) {
+                const float search_pixel = wTL * (float)it[x] + wTR * (float)it[x + 1] + wBL * (float)it[x + im.pitch] +
+                                           wBR * (float)it[x + im.pitch + 1];
+                const float res = search_pixel - (float)ref[y * patch + x] + mean_diff;
+                const float dx = (float)(0.5 * ((int)tb[x + 1] - (int)tb[x - 1]));
+                const float dy = (float)(0.5 * ((int)tb[x + ref_step] - (int)tb[x - ref_step]));
+                J0 -= res * dx;
+                J1 -= res * dy;
+                J2 -= res;
+                chi2 += res * res;
+            }
+        }
+        const float up0 = (Hinv[0][0] * J0 + Hinv[0][1] * J1) + Hinv[0][2] * J2;
+        const float up1 = (Hinv[1][0] * J0 + Hinv[1][1] * J1) + Hinv[1][2] * J2;
+        const float up2 = (Hinv[2][0] * J0 + Hinv[2][1] * J1) + Hinv[2][2] * J2;
+        u += up0;
+        v += up1;
+        mean_diff += up2;
+        if (up0 * up0 + up1 * up1 < min_update_squared) {
+            converged = true;
+            break;
+        }
+    }
+    *pu = (double)u;
+    *pv = (double)v;
+    return converged && chi2 < 20000.f;
+}
+
+__global__ void __launch_bounds__(128) align2d_kernel(const uint8_t* __restrict__ pyr, size_t slot_stride, Geometry g, int n,
+                                                      const int32_t* __restrict__ slot, const uint8_t* __restrict__ level,
+                                                      const uint8_t* __restrict__ ref_border, const uint8_t* __restrict__ ref,
+                                                      int n_iter, double* __restrict__ uv, uint8_t* __restrict__ ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t pwb[100], rp[64];
+    for (int k = 0; k < 100; ++k) pwb[k] = ref_border[(size_t)i * 100 + k];
+    if (ref) {
+        for (int k = 0; k < 64; ++k) rp[k] = ref[(size_t)i * 64 + k];
+    } else {
+        for (int y = 1; y < 9; ++y)
+            for (int x = 0; x < 8; ++x) rp[(y - 1) * 8 + x] = pwb[y * 10 + 1 + x];
+    }
+    const LevelImg im = level_img(pyr, slot_stride, slot[i], g, level[i]);
+    double u = uv[2 * i], v = uv[2 * i + 1];
+    const bool s = align2d_dev(im, pwb, rp, n_iter, &u, &v);
+    uv[2 * i] = u;
+    uv[2 * i + 1] = v;
+    ok[i] = s ? 1 : 0;
+}
+
+struct CamF {
+    float fx, fy, cx, cy;
+};
+__device__ __forceinline__ V3d pixel2camera(const CamF& c, double px, double py, double depth) {
+    return V3d{(px - c.cx) * depth / c.fx, (py - c.cy) * depth / c.fy, depth};
+}
+__device__ __forceinline__ void camera2pixel(const CamF& c, V3d p, double* u, double* v) {
+    *u = c.fx * p.x / p.z + c.cx;
+    *v = c.fy * p.y / p.z + c.cy;
+}
+
+// cvutils::GetBilateralInterpUchar (f64 weights, truncating cast)
+__device__ __forceinline__ uint8_t interp_uchar(double x, double y, const LevelImg& im) {
+    const double xx = x - floor(x), yy = y - floor(y);
+    const uint8_t* d = im.d + (size_t)(int)y * im.pitch + (int)x;
+    return (uint8_t)((1 - xx) * (1 - yy) * d[0] + xx * (1 - yy) * d[1] + (1 - xx) * yy * d[im.pitch] + xx * yy * d[im.pitch + 1]);
+}
+
+// Matcher::FindDirectProjection(ref, curr, Feature*, px, level) for candidate i
+__global__ void __launch_bounds__(128) project_align_kernel(const uint8_t* __restrict__ pyr, size_t slot_stride, Geometry g, CamF cam,
+                                                            int n, const int32_t* __restrict__ ref_slot,
+                                                            const int32_t* __restrict__ cur_slot, const double* __restrict__ poses,
+                                                            const int32_t* __restrict__ ref_pose, const int32_t* __restrict__ cur_pose,
+                                                            const double* __restrict__ ref_px, const double* __restrict__ ref_depth,
+                                                            const uint8_t* __restrict__ ref_level, double* __restrict__ cur_px,
+                                                            uint8_t* __restrict__ search_level, uint8_t* __restrict__ ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ok[i] = 0;
+    search_level[i] = 0;
+    if (ref_depth[i] < 0) return;
+    const int half = 4;
+    const double pxr = ref_px[2 * i], pyr_ = ref_px[2 * i + 1];
+    const int lvl = ref_level[i];
+    const SE3d Tr = se3_from_mat(poses + 12 * (size_t)ref_pose[i]), Tc = se3_from_mat(poses + 12 * (size_t)cur_pose[i]);
+    const SE3d Tr_inv = se3_inverse(Tr);
+    const SE3d TCR = se3_mul(Tc, Tr_inv);
+    const V3d pt_ref = pixel2camera(cam, pxr, pyr_, ref_depth[i]);
+    const V3d pt_ref_world = transform(Tr_inv, pt_ref);
+    const V3d pt_du = pixel2camera(cam, pxr + (double)half * (1 << lvl), pyr_, pt_ref.z);
+    const V3d pt_dv = pixel2camera(cam, pxr, pyr_ + (double)half * (1 << lvl), pt_ref.z);
+    double cu, cv, duu, duv, dvu, dvv;
+    camera2pixel(cam, transform(TCR, pt_ref_world), &cu, &cv);  // sic: world point through T_CR (Matcher.cpp:425-430)
+    camera2pixel(cam, transform(TCR, pt_du), &duu, &duv);
+    camera2pixel(cam, transform(TCR, pt_dv), &dvu, &dvv);
+    const double A00 = (duu - cu) / half, A10 = (duv - cv) / half, A01 = (dvu - cu) / half, A11 = (dvv - cv) / half;
+    int sl = 0;
+    double D = A00 * A11 - A01 * A10;
+    while (D > 3.0 && sl < g.n_levels - 1) {
+        sl += 1;
+        D *= 0.25;
+    }
+    search_level[i] = (uint8_t)sl;
+    const double det = A00 * A11 - A10 * A01;
+    const double invdet = 1.0 / det;
+    const double R00 = A11 * invdet, R01 = -A01 * invdet, R10 = -A10 * invdet, R11 = A00 * invdet;
+    const LevelImg rim = level_img(pyr, slot_stride, ref_slot[i], g, lvl);
+    uint8_t pwb[100], patch[64];
+    const double rx = pxr / (1 << lvl), ry = pyr_ / (1 << lvl);
+    for (int y = 0, k = 0; y < 10; ++y)
+        for (int x = 0; x < 10; ++x, ++k) {
+            const double ppx = (double)(x - 5) * (1 << sl), ppy = (double)(y - 5) * (1 << sl);
+            const double qx = (R00 * ppx + R01 * ppy) + rx, qy = (R10 * ppx + R11 * ppy) + ry;
+            // NaN (singular warp) fails every comparison in the reference and would index out of range there;
+            // it is mapped to 0 here
+            if (!(qx >= 0 && qy >= 0 && qx < rim.w - 1 && qy < rim.h - 1)) pwb[k] = 0;
+            else pwb[k] = interp_uchar(qx, qy, rim);
+        }
+    for (int y = 1; y < 9; ++y)
+        for (int x = 0; x < 8; ++x) patch[(y - 1) * 8 + x] = pwb[y * 10 + 1 + x];
+    double su = cur_px[2 * i] / (1 << sl), sv = cur_px[2 * i + 1] / (1 << sl);
+    const LevelImg cim = level_img(pyr, slot_stride, cur_slot[i], g, sl);
+    const bool success = align2d_dev(cim, pwb, patch, 10, &su, &sv);
+    const double ou = su * (1 << sl), ov = sv * (1 << sl);
+    cur_px[2 * i] = ou;
+    cur_px[2 * i + 1] = ov;
+    const bool in = ou >= 10 && ou < g.W - 10 && ov >= 10 && ov < g.H - 10;  // curr->InFrame(px_curr), border 10
+    ok[i] = (in && success) ? 1 : 0;
+}
+
+// ---- SparseImgAlign -----------------------------------------------------------------------------------
+struct SparseArgs {
+    const uint8_t* pyr;
+    size_t slot_stride;
+    Geometry g;
+    CamF cam;
+    const int32_t* ref_slot;
+    const int32_t* cur_slot;
+    const int32_t* offsets;     // [n_problems + 1] into the per-feature arrays
+    const double* px;           // [2 total]
+    const double* depth;
+    const uint8_t* has_mp;
+    const double* T_ref;        // [12 n_problems]
+    double* T_cur;              // [12 n_problems] in/out
+    int max_level, min_level, n_iter;
+    double eps;
+    int32_t* n_meas_out;        // [n_problems]  (n_meas / 16)
+    int32_t* iters_out;         // [n_problems][kMaxLevels] or null
+    // scratch, per feature
+    float* ref_patch;           // [total][16]
+    float* gdx;                 // [total][16]
+    float* gdy;                 // [total][16]
+    double* frame_jac;          // [total][12]
+    uint8_t* visible;           // [total]
+};
+
+constexpr int kSparseThreads = 256;
+constexpr int kNormalTerms = 21 + 6 + 1;  // upper triangle of H, Jres, chi2
+
+__device__ bool ldlt_solve6(const double H[6][6], const double b[6], double x[6]) {
+    double L[6][6], D[6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) L[i][j] = 0;
+    for (int j = 0; j < 6; ++j) {
+        double d = H[j][j];
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+        D[j] = d;
+        if (!(fabs(d) > 0)) return false;
+        L[j][j] = 1;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = H[i][j];
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = s / d;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+        y[i] = s;
+    }
+    for (int i = 0; i < 6; ++i) y[i] /= D[i];
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k];
+        x[i] = s;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const SparseArgs a) {
+    __shared__ double s_red[kSparseThreads / 32][kNormalTerms];
+    __shared__ unsigned long long s_nmeas[kSparseThreads / 32];
+    __shared__ SE3d s_T, s_old;
+    __shared__ int s_flag;        // 0 continue, 1 break (rollback done / converged)
+    __shared__ double s_chi2;     // chi2_ of the solver (persists across levels, NLSSolver_impl.hpp:288-299)
+    __shared__ unsigned long long s_last_nmeas;
+
+    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f0 = a.offsets[prob], f1 = a.offsets[prob + 1];
+    const int nf = f1 - f0;
+    const Geometry& g = a.g;
+    if (nf == 0) {  // run(): no features -> returns 0, pose untouched
+        if (tid == 0) a.n_meas_out[prob] = 0;
+        return;
+    }
+    if (tid == 0) {
+        const SE3d Tref = se3_from_mat(a.T_ref + 12 * (size_t)prob);
+        s_T = se3_mul(se3_from_mat(a.T_cur + 12 * (size_t)prob), se3_inverse(Tref));  // T_cur_from_ref
+        s_chi2 = 1e10;
+        s_last_nmeas = 0;
+    }
+    for (int i = f0 + tid; i < f1; i += kSparseThreads) a.visible[i] = 0;
+    __syncthreads();
+
+    for (int lvl = a.max_level; lvl >= a.min_level; --lvl) {
+        const LevelImg rim = level_img(a.pyr, a.slot_stride, a.ref_slot[prob], g, lvl);
+        const LevelImg cim = level_img(a.pyr, a.slot_stride, a.cur_slot[prob], g, lvl);
+        const float scale = 1.0f / (float)(1 << lvl);
+        const double focal = (double)(float)((a.cam.fx + a.cam.fy) / 2);  // PinholeCamera::_f is a float
+        const double jscale = focal / (1 << lvl);
+        // precomputeReferencePatches: features that are not cached at this level keep their stale patch with a
+        // zero Jacobian (jacobian_cache_.setZero(); visible_fts_ is never cleared -- kept faithfully)
+        for (int i = f0 + tid; i < f1; i += kSparseThreads) {
+            for (int k = 0; k < 16; ++k) a.gdx[(size_t)i * 16 + k] = a.gdy[(size_t)i * 16 + k] = 0.f;
+            const float u_ref = (float)(a.px[2 * i] * scale), v_ref = (float)(a.px[2 * i + 1] * scale);
+            const int ui = (int)floorf(u_ref), vi = (int)floorf(v_ref);
+            if (!a.has_mp[i] || ui - 3 < 0 || vi - 3 < 0 || ui + 3 >= rim.w || vi + 3 >= rim.h) continue;
+            a.visible[i] = 1;
+            const V3d xyz = pixel2camera(a.cam, a.px[2 * i], a.px[2 * i + 1], a.depth[i]);
+            double* J = a.frame_jac + (size_t)i * 12;
+            const double X = xyz.x, Y = xyz.y, zi = 1. / xyz.z, zi2 = zi * zi;
+            J[0] = -zi; J[1] = 0; J[2] = X * zi2; J[3] = Y * J[2]; J[4] = -(1.0 + X * J[2]); J[5] = Y * zi;
+            J[6] = 0; J[7] = -zi; J[8] = Y * zi2; J[9] = 1.0 + Y * J[8]; J[10] = -J[3]; J[11] = -X * zi;
+            const float su = u_ref - (float)ui, sv = v_ref - (float)vi;
+            const float wtl = (float)((1.0 - su) * (1.0 - sv)), wtr = (float)(su * (1.0 - sv)), wbl = (float)((1.0 - su) * sv),
+                        wbr = su * sv;
+            const int st = rim.pitch;
+            int pc = 0;
+            for (int y = 0; y < 4; ++y) {
+                const uint8_t* p = rim.d + (size_t)(vi + y - 2) * st + (ui - 2);
+                for (int xx = 0; xx < 4; ++xx, ++p, ++pc) {
+                    a.ref_patch[(size_t)i * 16 + pc] = wtl * (float)p[0] + wtr * (float)p[1] + wbl * (float)p[st] + wbr * (float)p[st + 1];
+                    a.gdx[(size_t)i * 16 + pc] =
+                        0.5f * ((wtl * (float)p[1] + wtr * (float)p[2] + wbl * (float)p[st + 1] + wbr * (float)p[st + 2]) -
+                                (wtl * (float)p[-1] + wtr * (float)p[0] + wbl * (float)p[st - 1] + wbr * (float)p[st]));
+                    a.gdy[(size_t)i * 16 + pc] =
+                        0.5f * ((wtl * (float)p[st] + wtr * (float)p[1 + st] + wbl * (float)p[st * 2] + wbr * (float)p[st * 2 + 1]) -
+                                (wtl * (float)p[-st] + wtr * (float)p[1 - st] + wbl * (float)p[0] + wbr * (float)p[1]));
+                }
+            }
+        }
+        if (tid == 0) {
+            s_old = s_T;
+            s_flag = 0;
+        }
+        __syncthreads();
+
+        int it = 0;
+        for (it = 0; it < a.n_iter; ++it) {
+            const SE3d T = s_T;
+            double acc[kNormalTerms];
+#pragma unroll
+            for (int k = 0; k < kNormalTerms; ++k) acc[k] = 0.0;
+            unsigned long long nm = 0;
+            for (int i = f0 + tid; i < f1; i += kSparseThreads) {
+                if (!a.visible[i]) continue;
+                const V3d xyz_ref = pixel2camera(a.cam, a.px[2 * i], a.px[2 * i + 1], a.depth[i]);
+                const V3d xyz_cur = transform(T, xyz_ref);
+                double pu, pv;
+                camera2pixel(a.cam, xyz_cur, &pu, &pv);
+                const float u_cur = (float)pu * scale, v_cur = (float)pv * scale;
+                const int ui = (int)floorf(u_cur), vi = (int)floorf(v_cur);
+                if (ui < 0 || vi < 0 || ui - 3 < 0 || vi - 3 < 0 || ui + 3 >= cim.w || vi + 3 >= cim.h) continue;
+                const float su = u_cur - (float)ui, sv = v_cur - (float)vi;
+                const float wtl = (float)((1.0 - su) * (1.0 - sv)), wtr = (float)(su * (1.0 - sv)),
+                            wbl = (float)((1.0 - su) * sv), wbr = su * sv;
+                const double* FJ = a.frame_jac + (size_t)i * 12;
+                const int st = cim.pitch;
+                int pc = 0;
+                for (int y = 0; y < 4; ++y) {
+                    const uint8_t* p = cim.d + (size_t)(vi + y - 2) * st + (ui - 2);
+                    for (int xx = 0; xx < 4; ++xx, ++pc, ++p) {
+                        const float inten = wtl * (float)p[0] + wtr * (float)p[1] + wbl * (float)p[st] + wbr * (float)p[st + 1];
+                        const float res = inten - a.ref_patch[(size_t)i * 16 + pc];
+                        acc[27] += (double)(res * res);
+                        ++nm;
+                        const float dx = a.gdx[(size_t)i * 16 + pc], dy = a.gdy[(size_t)i * 16 + pc];
+                        double J[6];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) J[k] = (dx * FJ[k] + dy * FJ[6 + k]) * jscale;
+                        int t = 0;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                            for (int c = r; c < 6; ++c) acc[t++] += J[r] * J[c];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) acc[21 + k] -= J[k] * res;
+                    }
+                }
+            }
+            // block reduction (warp shuffles, then shared memory)
+#pragma unroll
+            for (int k = 0; k < kNormalTerms; ++k) {
+                double v = acc[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+                if (lane == 0) s_red[warp][k] = v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nm += __shfl_down_sync(0xFFFFFFFFu, nm, o);
+            if (lane == 0) s_nmeas[warp] = nm;
+            __syncthreads();
+            if (tid == 0) {
+                double tot[kNormalTerms];
+                unsigned long long n_meas = 0;
+                for (int k = 0; k < kNormalTerms; ++k) tot[k] = 0;
+                for (int w = 0; w < kSparseThreads / 32; ++w) {
+                    for (int k = 0; k < kNormalTerms; ++k) tot[k] += s_red[w][k];
+                    n_meas += s_nmeas[w];
+                }
+                s_last_nmeas = n_meas;
+                double H[6][6], b[6], x[6];
+                int t = 0;
+                for (int r = 0; r < 6; ++r)
+                    for (int c = r; c < 6; ++c) {
+                        H[r][c] = H[c][r] = tot[t++];
+                    }
+                for (int k = 0; k < 6; ++k) b[k] = tot[21 + k];
+                // computeResiduals returns (float chi2) / n_meas
+                const double new_chi2 = (double)((float)tot[27] / (float)n_meas);
+                bool stop = !ldlt_solve6(H, b, x) || isnan(x[0]);
+                if ((it > 0 && new_chi2 > s_chi2) || stop) {
+                    s_T = s_old;  // rollback
+                    s_flag = 1;
+                } else {
+                    double mx[6];
+                    for (int k = 0; k < 6; ++k) mx[k] = -x[k];
+                    const SE3d Tn = se3_mul(s_T, se3_exp(mx));  // update(): T_new = T_old * exp(-x)
+                    s_old = s_T;
+                    s_T = Tn;
+                    s_chi2 = new_chi2;
+                    double nmx = -1;
+                    for (int k = 0; k < 6; ++k) nmx = fabs(x[k]) > nmx ? fabs(x[k]) : nmx;
+                    if (nmx <= a.eps) s_flag = 1;
+                }
+            }
+            __syncthreads();
+            if (s_flag) break;
+        }
+        if (tid == 0 && a.iters_out) a.iters_out[prob * kMaxLevels + lvl] = it;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const SE3d Tref = se3_from_mat(a.T_ref + 12 * (size_t)prob);
+        se3_to_mat(se3_mul(s_T, Tref), a.T_cur + 12 * (size_t)prob);
+        a.n_meas_out[prob] = (int32_t)(s_last_nmeas / 16);
+    }
+}
+
+}  // namespace
+
+int launch_align2d(ygzb_frames* f, int n, const int32_t* d_slot, const uint8_t* d_level, const uint8_t* d_ref_border,
+                   const uint8_t* d_ref, int n_iter, double* d_uv, uint8_t* d_ok) {
+    ygzb_ctx* ctx = f->ctx;
+    if (n <= 0) return YGZB_OK;
+    ProfScope ps(ctx, kStageAlign2D);
+    align2d_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, ctx->geo, n, d_slot, d_level, d_ref_border,
+                                                             d_ref, n_iter, d_uv, d_ok);
+    YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+int launch_project_align(ygzb_frames* f, int n, const int32_t* d_ref_slot, const int32_t* d_cur_slot, const double* d_poses,
+                         const int32_t* d_ref_pose, const int32_t* d_cur_pose, const double* d_ref_px, const double* d_ref_depth,
+                         const uint8_t* d_ref_level, double* d_cur_px, uint8_t* d_search_level, uint8_t* d_ok) {
+    ygzb_ctx* ctx = f->ctx;
+    if (n <= 0) return YGZB_OK;
+    const CamF cam{ctx->prm.fx, ctx->prm.fy, ctx->prm.cx, ctx->prm.cy};
+    ProfScope ps(ctx, kStageProjectAlign);
+    project_align_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, ctx->geo, cam, n, d_ref_slot,
+                                                                   d_cur_slot, d_poses, d_ref_pose, d_cur_pose, d_ref_px,
+                                                                   d_ref_depth, d_ref_level, d_cur_px, d_search_level, d_ok);
+    YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slot, const int32_t* d_cur_slot,
+                        const int32_t* d_offsets, const double* d_px, const double* d_depth, const uint8_t* d_has_mp,
+                        const double* d_T_ref, double* d_T_cur, int max_level, int min_level, int n_iter, double eps,
+                        int32_t* d_n_meas, int32_t* d_iters, float* d_ref_patch, float* d_gdx, float* d_gdy, double* d_frame_jac,
+                        uint8_t* d_visible) {
+    ygzb_ctx* ctx = f->ctx;
+    if (n_problems <= 0) return YGZB_OK;
+    SparseArgs a;
+    a.pyr = f->d_pyr;
+    a.slot_stride = ctx->slot_stride;
+    a.g = ctx->geo;
+    a.cam = CamF{ctx->prm.fx, ctx->prm.fy, ctx->prm.cx, ctx->prm.cy};
+    a.ref_slot = d_ref_slot;
+    a.cur_slot = d_cur_slot;
+    a.offsets = d_offsets;
+    a.px = d_px;
+    a.depth = d_depth;
+    a.has_mp = d_has_mp;
+    a.T_ref = d_T_ref;
+    a.T_cur = d_T_cur;
+    a.max_level = max_level;
+    a.min_level = min_level;
+    a.n_iter = n_iter;
+    a.eps = eps;
+    a.n_meas_out = d_n_meas;
+    a.iters_out = d_iters;
+    a.ref_patch = d_ref_patch;
+    a.gdx = d_gdx;
+    a.gdy = d_gdy;
+    a.frame_jac = d_frame_jac;
+    a.visible = d_visible;
+    ProfScope ps(ctx, kStageSparseAlign);
+    sparse_align_kernel<<<n_problems, kSparseThreads, 0, ctx->stream>>>(a);
+    YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+}  // namespace ygzb

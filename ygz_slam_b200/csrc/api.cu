@@ -268,8 +268,9 @@ int ygzb_profile_read(ygzb_ctx* ctx, double* ms, int32_t* launches) {
 
 int ygzb_profile_stage_count(void) { return kNumStages; }
 const char* ygzb_profile_stage_name(int i) {
-    static const char* names[kNumStages] = {"bgr2gray", "pyrdown", "fast_cells", "merge_cells", "describe",
-                                            "match", "match_finalize", "pack", "other"};
+    static const char* names[kNumStages] = {"bgr2gray", "pyrdown", "fast_cells", "merge_cells", "describe", "match",
+                                            "match_finalize", "pack", "other", "align2d", "project_align", "sparse_align",
+                                            "pose_only", "local_ba", "klt"};
     return (i >= 0 && i < kNumStages) ? names[i] : "";
 }
 

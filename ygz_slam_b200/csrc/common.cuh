@@ -103,7 +103,8 @@ void* host_scratch(ygzb_ctx* ctx, int which, size_t bytes);
 // ---- per-stage device timing -------------------------------------------------------------------
 enum Stage {
     kStageBgr2Gray = 0, kStagePyrDown, kStageFastCells, kStageMergeCells, kStageDescribe, kStageMatch,
-    kStageMatchFinalize, kStagePack, kStageOther, kNumStages
+    kStageMatchFinalize, kStagePack, kStageOther, kStageAlign2D, kStageProjectAlign, kStageSparseAlign, kStagePoseOnly,
+    kStageLocalBA, kStageKLT, kNumStages
 };
 struct ProfRec {
     cudaEvent_t a, b;
@@ -130,6 +131,31 @@ int launch_match(ygzb_ctx* ctx, const uint8_t* d_base, size_t set_stride, const 
                  const int32_t* d_q_offsets, int32_t* d_train_idx, int32_t* d_dist);
 int launch_hamming_pairs(ygzb_ctx* ctx, const uint8_t* d_A, const uint8_t* d_B, const int32_t* d_ia, const int32_t* d_ib,
                          int n, int32_t* d_dist);
+int launch_align2d(ygzb_frames* f, int n, const int32_t* d_slot, const uint8_t* d_level, const uint8_t* d_ref_border,
+                   const uint8_t* d_ref, int n_iter, double* d_uv, uint8_t* d_ok);
+int launch_project_align(ygzb_frames* f, int n, const int32_t* d_ref_slot, const int32_t* d_cur_slot, const double* d_poses,
+                         const int32_t* d_ref_pose, const int32_t* d_cur_pose, const double* d_ref_px, const double* d_ref_depth,
+                         const uint8_t* d_ref_level, double* d_cur_px, uint8_t* d_search_level, uint8_t* d_ok);
+int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slot, const int32_t* d_cur_slot,
+                        const int32_t* d_offsets, const double* d_px, const double* d_depth, const uint8_t* d_has_mp,
+                        const double* d_T_ref, double* d_T_cur, int max_level, int min_level, int n_iter, double eps,
+                        int32_t* d_n_meas, int32_t* d_iters, float* d_ref_patch, float* d_gdx, float* d_gdy, double* d_frame_jac,
+                        uint8_t* d_visible);
+
+// bump allocator over one scratch buffer (all sub-buffers 256-byte aligned)
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* r = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return r;
+    }
+    size_t bytes() const { return off + 256; }
+};
 
 // device helpers shared by kernels ---------------------------------------------------------------
 __device__ __forceinline__ unsigned float_orderable(float f) {
