@@ -169,6 +169,39 @@ int ygzb_sparse_align(ygzb_frames* f, int n_problems, const int32_t* ref_slot, c
                       const double* T_cw_ref, double* T_cw_cur, int max_level, int min_level, int n_iter, double eps,
                       int32_t* n_meas, int32_t* iters_per_level /* n_problems x YGZB_MAX_LEVELS or NULL */);
 
+/* ---- ba:: ---------------------------------------------------------------------------------------
+ * replaces ba::LocalBAG2O (src/Algorithm/BA.cpp:386-543; include/ygz/Algorithm/BA.h:60-66) with
+ * VertexSE3Sophus / EdgeSophusSE3ProjectXYZ (include/ygz/G2oTypes.h:13-146): Levenberg + Schur
+ * complement over marginalised landmarks, Huber kernel.  Batched: problem p owns keyframes
+ * [kf_off[p], kf_off[p+1]), points [pt_off[p], ..), observations [obs_off[p], ..); kf_idx / pt_idx are
+ * indices LOCAL to the problem.  poses = 6 doubles per keyframe in the vertex' order [omega; upsilon]
+ * (in/out), fixed[k] != 0 = setFixed(true) (keyframe id 0 and non-local observers, BA.cpp:404-405,458-492),
+ * pts in/out, outlier[o] = 1 iff chi2 > chi2_outlier after the optimisation (Feature::_bad, :505-515).  */
+typedef struct {
+    int max_iters;        /* optimizer.optimize(20)        */
+    double huber_delta;   /* 5.991 (<= 0: no robust kernel) */
+    double chi2_outlier;  /* 5.991                          */
+    double tau;           /* g2o Levenberg tau (1e-5)       */
+    int max_trials;       /* g2o maxTrialsAfterFailure (10) */
+} ygzb_ba_params;
+typedef struct {
+    int iters, lm_trials;
+    double chi2_initial, chi2_final, lambda_final;
+    int n_outliers;
+} ygzb_ba_stats;
+void ygzb_default_ba_params(ygzb_ba_params* p);
+int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
+                  double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
+                  const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, ygzb_ba_stats* stats);
+
+/* replaces ba::OptimizeCurrentPoseOnly (src/Algorithm/BA.cpp:188-264; BA.h:44-46) with
+ * CeresReprojectionErrorPoseOnly (include/ygz/Ceres/CeresReprojectionErrorPoseOnly.h): four rounds of
+ * trust-region LM on [t; angle-axis] with re-classification of the observations between rounds.
+ * Problem p owns points [offsets[p], offsets[p+1]); T_cw (3x4) in/out; inlier[i] = !Feature::_bad;
+ * depth[i] = Feature::_depth written for inliers (-1 otherwise); n_inlier[p] = cntInlier.            */
+int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const double* pt_world, const double* px,
+                   double* T_cw, uint8_t* inlier, double* depth, int32_t* n_inlier);
+
 #ifdef __cplusplus
 }
 #endif

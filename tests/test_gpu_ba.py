@@ -1,0 +1,85 @@
+"""GPU parity suite for bundle adjustment (BASELINE config C4) and pose-only refinement: poses / landmarks
+within the stated tolerance of the oracle (||log(T_gpu^-1 T_ref)|| < 1e-4, |dX| < 1e-4 m)."""
+import numpy as np
+import pytest
+
+from ygz_slam_b200 import se3, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _g2o(v):
+    v = np.asarray(v)
+    return np.concatenate([v[..., 3:], v[..., :3]], -1)
+
+
+def _pose_diff(Pa, Pb):
+    worst = 0.0
+    for a, b in zip(Pa, Pb):
+        Ta = se3.se3_exp(np.r_[a[3:], a[:3]])
+        Tb = se3.se3_exp(np.r_[b[3:], b[:3]])
+        worst = max(worst, float(np.linalg.norm(se3.se3_log(se3.mul(se3.inv(Ta), Tb)))))
+    return worst
+
+
+@pytest.mark.parametrize("huber", [5.991, 0.0])
+def test_local_ba_c4_matches_oracle(ctx3, oracle, huber):
+    sc = synth.ba_scene()
+    fixed = np.zeros(10, np.uint8)
+    fixed[0] = 1
+    n_obs = len(sc["kf_idx"])
+    wP, wX, wout, wst = oracle.local_ba(_g2o(sc["poses_noisy"]), fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"], huber=huber)
+    P, X, out, st = ctx3.local_ba([0, 10], [0, 2000], [0, n_obs], _g2o(sc["poses_noisy"]), fixed, sc["pts_noisy"], sc["kf_idx"],
+                                  sc["pt_idx"], sc["px"], huber=huber)
+    st = st[0]
+    assert _pose_diff(P, wP) < 1e-4
+    assert np.abs(X - wX).max() < 1e-4
+    assert abs(st["chi2_final"] - wst["chi2_final"]) < 1e-6 * wst["chi2_final"]
+    assert st["iters"] == wst["iters"] and st["lm_trials"] == wst["lm_trials"]
+    assert (out != wout).sum() <= 2        # an edge sitting exactly on the 5.991 threshold may flip
+    est = np.concatenate([P[:, 3:], P[:, :3]], 1)
+    assert np.abs(est - sc["poses_true"]).max() < 0.01   # and it is the right answer
+
+
+def test_local_ba_batched_and_fixed_observers(ctx3, oracle):
+    """Two problems in one launch; the second has two fixed keyframes (non-local observers, BA.cpp:458-492)."""
+    a = synth.ba_scene(n_kf=10, n_pt=2000, target_obs=8000, seed=11)
+    b = synth.ba_scene(n_kf=6, n_pt=300, target_obs=1500, seed=12)
+    fa = np.zeros(10, np.uint8); fa[0] = 1
+    fb = np.zeros(6, np.uint8); fb[[0, 4]] = 1
+    na, nb = len(a["kf_idx"]), len(b["kf_idx"])
+    P, X, out, st = ctx3.local_ba([0, 10, 16], [0, 2000, 2300], [0, na, na + nb],
+                                  np.concatenate([_g2o(a["poses_noisy"]), _g2o(b["poses_noisy"])]), np.concatenate([fa, fb]),
+                                  np.concatenate([a["pts_noisy"], b["pts_noisy"]]), np.concatenate([a["kf_idx"], b["kf_idx"]]),
+                                  np.concatenate([a["pt_idx"], b["pt_idx"]]), np.concatenate([a["px"], b["px"]]))
+    for (sc, f, ps, xs, os_) in ((a, fa, slice(0, 10), slice(0, 2000), slice(0, na)), (b, fb, slice(10, 16), slice(2000, 2300), slice(na, na + nb))):
+        wP, wX, wout, wst = oracle.local_ba(_g2o(sc["poses_noisy"]), f, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"])
+        assert _pose_diff(P[ps], wP) < 1e-4
+        assert np.abs(X[xs] - wX).max() < 1e-4
+        assert (out[os_] != wout).sum() <= 2
+    assert np.array_equal(P[10], _g2o(b["poses_noisy"])[0]) and np.array_equal(P[14], _g2o(b["poses_noisy"])[4])
+
+
+def test_pose_only_matches_oracle(ctx3, oracle):
+    sc = synth.ba_scene()
+    rng = np.random.default_rng(5)
+    offs, pws, pxs, Ts = [0], [], [], []
+    cases = []
+    for k, (noise, outl) in enumerate(((0.002, False), (0.002, True), (0.02, False), (0.001, True))):
+        sel = sc["kf_idx"] == (k + 2)
+        pw = sc["pts_true"][sc["pt_idx"][sel]]
+        px = sc["px"][sel].copy()
+        if outl:
+            px[::10] += 30
+        Tn = se3.se3_exp(sc["poses_true"][k + 2] + rng.normal(0, noise, 6))
+        cases.append((pw, px, Tn))
+        offs.append(offs[-1] + len(pw))
+        pws.append(pw); pxs.append(px); Ts.append(Tn.reshape(-1))
+    T, inl, depth, cnt = ctx3.pose_only(offs, np.concatenate(pws), np.concatenate(pxs), np.stack(Ts))
+    for p, (pw, px, Tn) in enumerate(cases):
+        wT, winl, wdepth, wcnt = oracle.pose_only(pw, px, Tn)
+        assert np.linalg.norm(se3.se3_log(se3.mul(se3.inv(T[p]), wT))) < 1e-4
+        s = slice(offs[p], offs[p + 1])
+        assert cnt[p] == wcnt
+        assert np.array_equal(inl[s], winl)
+        assert np.allclose(depth[s], wdepth, atol=1e-6)

@@ -1,0 +1,79 @@
+"""CPU suite: known-answer scenes for the BA / pose-only restatements (g2o and Ceres are unpinned third-party
+code: the pin is the ground truth of the reference's own synthetic fixture, test/test_local_ba.cpp:9-98)."""
+import numpy as np
+
+from ygz_slam_b200 import se3, synth
+
+
+def _g2o(v):  # [upsilon; omega] -> vertex order [omega; upsilon]
+    v = np.asarray(v)
+    return np.concatenate([v[..., 3:], v[..., :3]], -1)
+
+
+def test_local_ba_fixture_scene(oracle):
+    """8 poses x 16 points of test_local_ba.cpp with its noise recipe (pose 0.1, point 0.1, pixel 1)."""
+    rot = [(0, 0, 0), (0.1, 0, 0), (0, 0.1, 0), (0, 0, 0.1), (0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0)]
+    tr = [(0, 0, 0)] * 4 + [(0.1, 0, 0), (0, 0.1, 0), (0, 0, 0.1), (0.1, 0.1, 0.1)]
+    poses_true = [se3.se3_exp(np.r_[t, w]) for w, t in zip(rot, tr)]
+    pts_true = np.array([[x, y, z] for z in (2, 3, 4, 5) for (x, y) in ((0, 0), (0, 1), (1, 0), (1, 1))], float)
+    rng = np.random.default_rng(11)
+    logs = np.array([se3.se3_log(T) for T in poses_true])
+    noisy = logs.copy()
+    noisy[1:] += rng.normal(0, 0.1, (7, 6))
+    pts = pts_true + rng.normal(0, 0.1, pts_true.shape)
+    kf, pt, px = [], [], []
+    for j in range(16):
+        for k in range(8):
+            pc = poses_true[k][:, :3] @ pts_true[j] + poses_true[k][:, 3]
+            kf.append(k)
+            pt.append(j)
+            px.append([520.9 * pc[0] / pc[2] + 325.1 + rng.normal(0, 1), 521.0 * pc[1] / pc[2] + 249.7 + rng.normal(0, 1)])
+    fixed = np.zeros(8, np.uint8)
+    fixed[0] = 1
+    P, X, outl, st = oracle.local_ba(_g2o(noisy), fixed, pts, kf, pt, px)
+    assert st["chi2_final"] < 1e-2 * st["chi2_initial"]
+    assert st["chi2_final"] < 2.5 * len(kf)            # ~ pixel noise level (sigma = 1 px, 2 residuals per edge)
+    assert np.allclose(P[0], _g2o(noisy)[0])            # keyframe 0 is fixed
+    # rotations are observable (scale is not: monocular gauge): they must come back to the truth
+    assert np.abs(P[:, :3] - logs[:, 3:]).max() < 0.03
+    assert outl.sum() <= 0.1 * len(kf)
+
+
+def test_local_ba_c4_scene(oracle):
+    sc = synth.ba_scene()
+    fixed = np.zeros(10, np.uint8)
+    fixed[0] = 1
+    P, X, outl, st = oracle.local_ba(_g2o(sc["poses_noisy"]), fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"])
+    assert 7000 < len(sc["kf_idx"]) <= 8000
+    assert st["chi2_final"] < 2e-3 * st["chi2_initial"]
+    est = np.concatenate([P[:, 3:], P[:, :3]], 1)
+    assert np.abs(est - sc["poses_true"]).max() < 0.01
+    assert np.median(np.abs(X - sc["pts_true"])) < 0.05
+    # no robust kernel (the Ceres-flavoured LocalBA has no loss): still converges on outlier-free data
+    P2, X2, _, st2 = oracle.local_ba(_g2o(sc["poses_noisy"]), fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"], huber=0.0)
+    assert st2["chi2_final"] < 2e-3 * st2["chi2_initial"]
+
+
+def test_pose_only_rejects_outliers(oracle):
+    sc = synth.ba_scene()
+    rng = np.random.default_rng(5)
+    sel = sc["kf_idx"] == 3
+    pw = sc["pts_true"][sc["pt_idx"][sel]]
+    px = sc["px"][sel].copy()
+    px[::10] += 30
+    T0 = se3.se3_exp(sc["poses_true"][3])
+    Tn = se3.se3_exp(sc["poses_true"][3] + rng.normal(0, 0.002, 6))
+    T, inl, depth, cnt = oracle.pose_only(pw, px, Tn)
+    # the classification of round r uses the pose of round r-1 (BA.cpp:231-251), so the outlier-biased pose of
+    # round 0 makes later rounds reject many good points: well below the ~85 % a fresh pose would keep
+    assert cnt == inl.sum() and 0.3 * len(pw) < cnt < 0.95 * len(pw)
+    assert not inl[::10].any()                          # the +30 px observations are classified as outliers
+    _, inl_clean, _, cnt_clean = oracle.pose_only(pw, sc["px"][sel], Tn)
+    assert cnt_clean > 0.9 * len(pw)
+    err0 = np.linalg.norm(se3.se3_log(se3.mul(Tn, se3.inv(T0))))
+    err1 = np.linalg.norm(se3.se3_log(se3.mul(T, se3.inv(T0))))
+    assert err1 < err0 and err1 < 2e-3
+    assert np.all(depth[inl] > 0)
+    # fewer than 10 inliers: the loop breaks and the pose is left at the input (BA.cpp:248-249)
+    T2, inl2, _, cnt2 = oracle.pose_only(pw[:8], px[:8] + 100, Tn)
+    assert cnt2 == 0 and np.allclose(T2, Tn, atol=1e-12)

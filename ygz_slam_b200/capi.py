@@ -38,7 +38,7 @@ EXPORTS = [
     "ygzb_frames_upload", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
     "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d",
-    "ygzb_project_align", "ygzb_sparse_align",
+    "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_pose_only",
 ]
 
 
@@ -375,3 +375,53 @@ def _sparse_align(self, ref_slot, cur_slot, offsets, px, depth, has_mp, T_ref, T
 Frames.align2d = _align2d
 Frames.project_align = _project_align
 Frames.sparse_align = _sparse_align
+
+
+# ---- bundle adjustment (methods attached to Context) ---------------------------------------------------
+class BAParams(C.Structure):
+    _fields_ = [("max_iters", C.c_int), ("huber_delta", C.c_double), ("chi2_outlier", C.c_double), ("tau", C.c_double),
+                ("max_trials", C.c_int)]
+
+
+class BAStats(C.Structure):
+    _fields_ = [("iters", C.c_int), ("lm_trials", C.c_int), ("chi2_initial", C.c_double), ("chi2_final", C.c_double),
+                ("lambda_final", C.c_double), ("n_outliers", C.c_int)]
+
+
+def _local_ba(self, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, px, max_iters=20, huber=5.991):
+    """Batched ba::LocalBAG2O.  poses: (n_kf, 6) in g2o order [omega; upsilon]."""
+    kf_off = np.ascontiguousarray(kf_off, np.int32)
+    P = len(kf_off) - 1
+    poses = np.ascontiguousarray(poses, np.float64).copy()
+    pts = np.ascontiguousarray(pts, np.float64).copy()
+    prm = BAParams()
+    self.lib.ygzb_default_ba_params(C.byref(prm))
+    prm.max_iters = max_iters
+    prm.huber_delta = huber
+    outl = np.zeros(len(kf_idx), np.uint8)
+    st = (BAStats * P)()
+    self.check(self.lib.ygzb_local_ba(self.h, P, _p(kf_off), _p(np.ascontiguousarray(pt_off, np.int32)),
+                                      _p(np.ascontiguousarray(obs_off, np.int32)), _p(poses),
+                                      _p(np.ascontiguousarray(fixed, np.uint8)), _p(pts),
+                                      _p(np.ascontiguousarray(kf_idx, np.int32)), _p(np.ascontiguousarray(pt_idx, np.int32)),
+                                      _p(np.ascontiguousarray(px, np.float64)), C.byref(prm), _p(outl), st), "ygzb_local_ba")
+    stats = [{k: getattr(s_, k) for k, _ in BAStats._fields_} for s_ in st]
+    return poses, pts, outl.astype(bool), stats
+
+
+def _pose_only(self, offsets, pt_world, px, T_cw):
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    P = len(offsets) - 1
+    n = int(offsets[-1])
+    T = np.ascontiguousarray(T_cw, np.float64).reshape(P, 12).copy()
+    inl = np.zeros(n, np.uint8)
+    depth = np.zeros(n, np.float64)
+    cnt = np.zeros(P, np.int32)
+    self.check(self.lib.ygzb_pose_only(self.h, P, _p(offsets), _p(np.ascontiguousarray(pt_world, np.float64)),
+                                       _p(np.ascontiguousarray(px, np.float64)), _p(T), _p(inl), _p(depth), _p(cnt)),
+               "ygzb_pose_only")
+    return T.reshape(P, 3, 4), inl.astype(bool), depth, cnt
+
+
+Context.local_ba = _local_ba
+Context.pose_only = _pose_only

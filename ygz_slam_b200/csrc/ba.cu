@@ -1,0 +1,1070 @@
+// ba.cu -- local bundle adjustment (g2o-style Levenberg + Schur complement) and pose-only refinement
+// (Ceres-style trust-region LM), each as ONE persistent CTA per problem: the whole optimisation loop runs
+// on the device, the host sees one launch per batch of problems.
+//
+// Replaces:
+//   ba::LocalBAG2O                   reference src/Algorithm/BA.cpp:386-543
+//   VertexSE3Sophus::oplusImpl       reference include/ygz/G2oTypes.h:38-45
+//   EdgeSophusSE3ProjectXYZ          reference include/ygz/G2oTypes.h:84-132 (computeError, linearizeOplus)
+//   ba::OptimizeCurrentPoseOnly      reference src/Algorithm/BA.cpp:188-264
+//   CeresReprojectionErrorPoseOnly   reference include/ygz/Ceres/CeresReprojectionErrorPoseOnly.h:27-58
+// g2o / Ceres themselves are outside the reference tree: the optimiser logic follows the published
+// algorithms as pinned in oracle/ba.cpp.
+//
+// Local BA, per LM trial (C4: 10 keyframes, 2000 landmarks, ~8000 observations):
+//   linearise      thread per observation : error, Huber weight, 2x3 / 2x6 Jacobians        (~300 FLOP/obs)
+//   Hll, bl        thread per landmark    : sum over its observations (CSR by landmark)
+//   Hpp, bp        warp per free pose     : warp-shuffle reduction of J^T J (21+6 terms) over its observations
+//   Schur S, b_s   warp per 6x6 block pair: S(f1,f2) -= Hpl Hll^-1 Hpl^T over the landmarks seen by both poses,
+//                                           36 partial sums per lane reduced with warp shuffles, no atomics
+//   solve          dense Cholesky of S (<= 96x96) in shared memory by the whole CTA
+//   back-subst     thread per landmark
+// Roofline class: FP64 ALU / latency (0.3 MB of unique data per iteration, ~1.1e7 FLOP): bench.py reports
+// achieved FLOP/s for the reduce, not HBM bytes.
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "se3.cuh"
+
+namespace ygzb {
+
+namespace {
+
+constexpr int kBAThreads = 512;
+constexpr int kMaxFreePoses = 16;             // S is at most 96 x 96 doubles = 72 KB of shared memory
+constexpr int kMaxPoses = 64;
+
+struct BAArgs {
+    // problem p owns poses [kf_off[p], kf_off[p+1]), points [pt_off[p], ..), observations [obs_off[p], ..)
+    const int32_t *kf_off, *pt_off, *obs_off;
+    double* poses;            // g2o order [omega; upsilon], in/out
+    const uint8_t* fixed;
+    double* pts;              // in/out
+    const int32_t* kf_idx;    // per obs, LOCAL pose index inside the problem
+    const int32_t* pt_idx;    // per obs, LOCAL point index
+    const double* obs;        // per obs (u, v)
+    // structure built on the host (index bookkeeping only)
+    const int32_t* lm_start;  // per point (global index): range in lm_obs
+    const int32_t* lm_obs;    // observation ids (global) grouped by landmark
+    const int32_t* ps_start;  // per pose (global index): range in ps_obs
+    const int32_t* ps_obs;    // observation ids grouped by pose
+    const int32_t* pair_off;  // per problem: offset into pair_start (n_free*(n_free+1)/2 + 1 entries per problem)
+    const int32_t* pair_start;
+    const int32_t* pair_o1;   // entries: observation on pose f1, observation on pose f2 (same landmark)
+    const int32_t* pair_o2;
+    // per-observation / per-landmark scratch
+    double* lin;              // [n_obs][21]: e(2) w Jl(6) Jp(12)
+    double* Hll;              // [n_pt][9]
+    double* bl;               // [n_pt][3]
+    double* Dinv;             // [n_pt][9]
+    double* xl;               // [n_pt][3]
+    double* pts_backup;       // [n_pt][3]
+    uint8_t* outlier;         // [n_obs]
+    double* stats;            // [n_problems][8]: iters, trials, chi_first, chi_last, lambda, n_outliers
+    float fx, fy, cx, cy;
+    int max_iters, max_trials;
+    double huber_delta, chi2_outlier, tau;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in every thread
+__device__ double block_sum(double v, double* s_tmp /* 33 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < (int)(blockDim.x >> 5)) ? s_tmp[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) s_tmp[32] = t;
+    }
+    __syncthreads();
+    return s_tmp[32];
+}
+
+__device__ double block_max(double v, double* s_tmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xFFFFFFFFu, v, o));
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < (int)(blockDim.x >> 5)) ? s_tmp[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_down_sync(0xFFFFFFFFu, t, o));
+        if (lane == 0) s_tmp[32] = t;
+    }
+    __syncthreads();
+    return s_tmp[32];
+}
+
+__device__ __forceinline__ SE3d pose_from_g2o(const double* est) {
+    const double v[6] = {est[3], est[4], est[5], est[0], est[1], est[2]};
+    return se3_exp(v);
+}
+
+__device__ __forceinline__ void inverse3d(const double* H /* row major 3x3 */, double* inv) {
+#define COF(i, j) (H[((i + 1) % 3) * 3 + (j + 1) % 3] * H[((i + 2) % 3) * 3 + (j + 2) % 3] - H[((i + 1) % 3) * 3 + (j + 2) % 3] * H[((i + 2) % 3) * 3 + (j + 1) % 3])
+    const double c00 = COF(0, 0), c10 = COF(1, 0), c20 = COF(2, 0);
+    const double det = (c00 * H[0] + c10 * H[3]) + c20 * H[6];
+    const double invdet = 1.0 / det;
+    inv[0] = c00 * invdet; inv[1] = c10 * invdet; inv[2] = c20 * invdet;
+    inv[3] = COF(0, 1) * invdet; inv[4] = COF(1, 1) * invdet; inv[5] = COF(2, 1) * invdet;
+    inv[6] = COF(0, 2) * invdet; inv[7] = COF(1, 2) * invdet; inv[8] = COF(2, 2) * invdet;
+#undef COF
+}
+
+// Hpl = w * Jp^T Jl (6x3) from the linearisation record
+__device__ __forceinline__ void make_hpl(const double* __restrict__ rec, double Hpl[6][3]) {
+    const double w = rec[2];
+    const double* Jl = rec + 3;
+    const double* Jp = rec + 9;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Hpl[a][b] = w * (Jp[a] * Jl[b] + Jp[6 + a] * Jl[3 + b]);
+}
+
+__global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a) {
+    extern __shared__ double s_mem[];
+    __shared__ double s_tmp[33];
+    __shared__ double s_R[kMaxPoses][12];      // [R|t] of every pose of the problem, refreshed after each update
+    __shared__ double s_backup[kMaxPoses][6];
+    __shared__ int s_free[kMaxPoses];
+    __shared__ double s_lambda, s_ni, s_rho, s_current_chi;
+    __shared__ int s_accept, s_ok;
+
+    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = kBAThreads / 32;
+    const int k0 = a.kf_off[prob], n_kf = a.kf_off[prob + 1] - k0;
+    const int p0 = a.pt_off[prob], n_pt = a.pt_off[prob + 1] - p0;
+    const int o0 = a.obs_off[prob], n_obs = a.obs_off[prob + 1] - o0;
+    if (tid == 0) {
+        int nf = 0;
+        for (int k = 0; k < n_kf; ++k) s_free[k] = a.fixed[k0 + k] ? -1 : nf++;
+        s_ok = nf;
+    }
+    __syncthreads();
+    const int np = s_ok, dimp = 6 * np;
+    double* s_S = s_mem;                         // dimp x dimp
+    double* s_Hpp = s_S + dimp * dimp;           // np x 36
+    double* s_bp = s_Hpp + np * 36;              // dimp
+    double* s_bs = s_bp + dimp;                  // dimp (rhs, then solution xp)
+    const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
+    const double dsqr = a.huber_delta * a.huber_delta;
+    const int32_t* pair_start = a.pair_start + a.pair_off[prob];
+    const int n_pairs = np * (np + 1) / 2;
+
+    auto refresh_poses = [&]() {
+        if (tid < n_kf) {
+            const SE3d T = pose_from_g2o(a.poses + 6 * (size_t)(k0 + tid));
+            se3_to_mat(T, s_R[tid]);
+        }
+        __syncthreads();
+    };
+    // robust chi2 of the current estimate (activeRobustChi2)
+    auto robust_chi2 = [&]() -> double {
+        double acc = 0;
+        for (int o = tid; o < n_obs; o += kBAThreads) {
+            const double* T = s_R[a.kf_idx[o0 + o]];
+            const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
+            const double x = T[0] * X[0] + T[1] * X[1] + T[2] * X[2] + T[3];
+            const double y = T[4] * X[0] + T[5] * X[1] + T[6] * X[2] + T[7];
+            const double z = T[8] * X[0] + T[9] * X[1] + T[10] * X[2] + T[11];
+            const double e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx), e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
+            const double e2 = e0 * e0 + e1 * e1;
+            acc += (a.huber_delta > 0 && e2 > dsqr) ? 2 * sqrt(e2) * a.huber_delta - dsqr : e2;
+        }
+        return block_sum(acc, s_tmp);
+    };
+
+    refresh_poses();
+    int iters = 0, trials_total = 0;
+    double chi_first = 0, chi_last = 0;
+
+    for (int iteration = 0; iteration < a.max_iters; ++iteration) {
+        // ---- computeActiveErrors + buildSystem -------------------------------------------------------
+        double acc = 0;
+        for (int o = tid; o < n_obs; o += kBAThreads) {
+            const int k = a.kf_idx[o0 + o];
+            const double* T = s_R[k];
+            const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
+            const double x = T[0] * X[0] + T[1] * X[1] + T[2] * X[2] + T[3];
+            const double y = T[4] * X[0] + T[5] * X[1] + T[6] * X[2] + T[7];
+            const double z = T[8] * X[0] + T[9] * X[1] + T[10] * X[2] + T[11];
+            const double e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx), e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
+            const double e2 = e0 * e0 + e1 * e1;
+            double w = 1.0;
+            if (a.huber_delta > 0 && e2 > dsqr) {
+                w = a.huber_delta / sqrt(e2);
+                acc += 2 * sqrt(e2) * a.huber_delta - dsqr;
+            } else {
+                acc += e2;
+            }
+            double* rec = a.lin + 21 * (size_t)(o0 + o);
+            rec[0] = e0; rec[1] = e1; rec[2] = w;
+            const double z_2 = z * z;
+            const double t0[3] = {fx, 0, -x / z * fx}, t1[3] = {0, fy, -y / z * fy};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                rec[3 + c] = -1. / z * (t0[0] * T[c] + t0[1] * T[4 + c] + t0[2] * T[8 + c]);
+                rec[6 + c] = -1. / z * (t1[0] * T[c] + t1[1] * T[4 + c] + t1[2] * T[8 + c]);
+            }
+            rec[9] = x * y / z_2 * fx; rec[10] = -(1 + (x * x / z_2)) * fx; rec[11] = y / z * fx;
+            rec[12] = -1. / z * fx; rec[13] = 0; rec[14] = x / z_2 * fx;
+            rec[15] = (1 + y * y / z_2) * fy; rec[16] = -x * y / z_2 * fy; rec[17] = -x / z * fy;
+            rec[18] = 0; rec[19] = -1. / z * fy; rec[20] = y / z_2 * fy;
+        }
+        const double currentChi0 = block_sum(acc, s_tmp);
+        if (tid == 0) s_current_chi = currentChi0;
+        if (iteration == 0) chi_first = currentChi0;
+        __syncthreads();
+        // Hll, bl : thread per landmark
+        double mx = 0;
+        for (int j = tid; j < n_pt; j += kBAThreads) {
+            double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};  // xx xy xz yy yz zz
+            for (int q = a.lm_start[p0 + j]; q < a.lm_start[p0 + j + 1]; ++q) {
+                const double* rec = a.lin + 21 * (size_t)a.lm_obs[q];
+                const double w = rec[2];
+                const double* J0 = rec + 3;
+                const double* J1 = rec + 6;
+                H[0] += w * (J0[0] * J0[0] + J1[0] * J1[0]); H[1] += w * (J0[0] * J0[1] + J1[0] * J1[1]);
+                H[2] += w * (J0[0] * J0[2] + J1[0] * J1[2]); H[3] += w * (J0[1] * J0[1] + J1[1] * J1[1]);
+                H[4] += w * (J0[1] * J0[2] + J1[1] * J1[2]); H[5] += w * (J0[2] * J0[2] + J1[2] * J1[2]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) b[c] += -w * (J0[c] * rec[0] + J1[c] * rec[1]);
+            }
+            double* Hj = a.Hll + 9 * (size_t)(p0 + j);
+            Hj[0] = H[0]; Hj[1] = H[1]; Hj[2] = H[2]; Hj[3] = H[1]; Hj[4] = H[3]; Hj[5] = H[4]; Hj[6] = H[2]; Hj[7] = H[4]; Hj[8] = H[5];
+            double* bj = a.bl + 3 * (size_t)(p0 + j);
+            bj[0] = b[0]; bj[1] = b[1]; bj[2] = b[2];
+            mx = fmax(mx, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
+        }
+        // Hpp, bp : warp per free pose
+        for (int k = warp; k < n_kf; k += n_warps) {
+            const int fi = s_free[k];
+            if (fi < 0) continue;
+            double h[21], g[6];
+#pragma unroll
+            for (int t = 0; t < 21; ++t) h[t] = 0;
+#pragma unroll
+            for (int t = 0; t < 6; ++t) g[t] = 0;
+            for (int q = a.ps_start[k0 + k] + lane; q < a.ps_start[k0 + k + 1]; q += 32) {
+                const double* rec = a.lin + 21 * (size_t)a.ps_obs[q];
+                const double w = rec[2];
+                const double* J0 = rec + 9;
+                const double* J1 = rec + 15;
+                int t = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                    for (int c = r; c < 6; ++c) h[t++] += w * (J0[r] * J0[c] + J1[r] * J1[c]);
+                    g[r] += -w * (J0[r] * rec[0] + J1[r] * rec[1]);
+                }
+            }
+            int t = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                for (int c = r; c < 6; ++c) {
+                    const double v = warp_sum(h[t++]);
+                    if (lane == 0) s_Hpp[fi * 36 + r * 6 + c] = s_Hpp[fi * 36 + c * 6 + r] = v;
+                }
+                const double gv = warp_sum(g[r]);
+                if (lane == 0) s_bp[fi * 6 + r] = gv;
+            }
+        }
+        __syncthreads();
+        if (iteration == 0) {  // computeLambdaInit = tau * max |diag H|
+            if (tid < dimp) mx = fmax(mx, fabs(s_Hpp[(tid / 6) * 36 + (tid % 6) * 7]));
+            const double m = block_max(mx, s_tmp);
+            if (tid == 0) {
+                s_lambda = a.tau * m;
+                s_ni = 2;
+            }
+            __syncthreads();
+        }
+
+        int qmax = 0;
+        do {
+            const double lambda = s_lambda;
+            // _optimizer->push()
+            if (tid < n_kf)
+                for (int c = 0; c < 6; ++c) s_backup[tid][c] = a.poses[6 * (size_t)(k0 + tid) + c];
+            for (int i = tid; i < 3 * n_pt; i += kBAThreads) a.pts_backup[3 * (size_t)p0 + i] = a.pts[3 * (size_t)p0 + i];
+            // Dinv per landmark; S <- Hpp + lambda I ; bs <- bp
+            for (int j = tid; j < n_pt; j += kBAThreads) {
+                double D[9];
+                const double* Hj = a.Hll + 9 * (size_t)(p0 + j);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) D[t] = Hj[t];
+                D[0] += lambda; D[4] += lambda; D[8] += lambda;
+                inverse3d(D, a.Dinv + 9 * (size_t)(p0 + j));
+            }
+            for (int i = tid; i < dimp * dimp; i += kBAThreads) {
+                const int r = i / dimp, c = i - r * dimp;
+                s_S[i] = (r / 6 == c / 6) ? s_Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)] + (r == c ? lambda : 0.0) : 0.0;
+            }
+            if (tid < dimp) s_bs[tid] = s_bp[tid];
+            __syncthreads();
+            // Schur complement: warp per block pair (f1 <= f2)
+            for (int pr = warp; pr < n_pairs; pr += n_warps) {
+                // decode (f1, f2) from the triangular index
+                int f1 = 0, rem = pr;
+                while (rem >= np - f1) {
+                    rem -= np - f1;
+                    ++f1;
+                }
+                const int f2 = f1 + rem;
+                double accS[36], accb[6];
+#pragma unroll
+                for (int t = 0; t < 36; ++t) accS[t] = 0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) accb[t] = 0;
+                for (int q = pair_start[pr] + lane; q < pair_start[pr + 1]; q += 32) {
+                    const int o1 = a.pair_o1[q], o2 = a.pair_o2[q];
+                    const int j = p0 + a.pt_idx[o1];
+                    const double* Di = a.Dinv + 9 * (size_t)j;
+                    double H1[6][3], BD[6][3];
+                    make_hpl(a.lin + 21 * (size_t)o1, H1);
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) BD[r][c] = H1[r][0] * Di[c] + H1[r][1] * Di[3 + c] + H1[r][2] * Di[6 + c];
+                    if (o1 == o2) {
+                        const double* bj = a.bl + 3 * (size_t)j;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) accb[r] += BD[r][0] * bj[0] + BD[r][1] * bj[1] + BD[r][2] * bj[2];
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H1[c][0] + BD[r][1] * H1[c][1] + BD[r][2] * H1[c][2];
+                    } else {
+                        double H2[6][3];
+                        make_hpl(a.lin + 21 * (size_t)o2, H2);
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H2[c][0] + BD[r][1] * H2[c][1] + BD[r][2] * H2[c][2];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 36; ++t) {
+                    const double v = warp_sum(accS[t]);
+                    if (lane == 0) {
+                        const int r = t / 6, c = t - r * 6;
+                        s_S[(6 * f1 + r) * dimp + 6 * f2 + c] -= v;
+                        if (f1 != f2) s_S[(6 * f2 + c) * dimp + 6 * f1 + r] -= v;
+                    }
+                }
+                if (f1 == f2) {
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+                        const double v = warp_sum(accb[r]);
+                        if (lane == 0) s_bs[6 * f1 + r] -= v;
+                    }
+                }
+            }
+            __syncthreads();
+            // dense Cholesky S = L L^T in place (lower triangle), whole CTA, then the two triangular solves
+            if (tid == 0) s_ok = 1;
+            __syncthreads();
+            for (int j = 0; j < dimp; ++j) {
+                if (tid == 0) {
+                    const double d = s_S[j * dimp + j];
+                    if (!(d > 0)) s_ok = 0;
+                    s_S[j * dimp + j] = sqrt(d);
+                }
+                __syncthreads();
+                if (!s_ok) break;
+                const double djj = s_S[j * dimp + j];
+                for (int i = j + 1 + tid; i < dimp; i += kBAThreads) s_S[i * dimp + j] /= djj;
+                __syncthreads();
+                const int rem = dimp - j - 1;
+                for (int e = tid; e < rem * rem; e += kBAThreads) {
+                    const int r = j + 1 + e / rem, c = j + 1 + e % rem;
+                    if (c <= r) s_S[r * dimp + c] -= s_S[r * dimp + j] * s_S[c * dimp + j];
+                }
+                __syncthreads();
+            }
+            if (tid == 0 && s_ok) {
+                for (int i = 0; i < dimp; ++i) {
+                    double s = s_bs[i];
+                    for (int k = 0; k < i; ++k) s -= s_S[i * dimp + k] * s_bs[k];
+                    s_bs[i] = s / s_S[i * dimp + i];
+                }
+                for (int i = dimp - 1; i >= 0; --i) {
+                    double s = s_bs[i];
+                    for (int k = i + 1; k < dimp; ++k) s -= s_S[k * dimp + i] * s_bs[k];
+                    s_bs[i] = s / s_S[i * dimp + i];
+                }
+            }
+            __syncthreads();
+            const bool ok2 = s_ok != 0;
+            // landmark back-substitution + scale term + update
+            double scale = 0;
+            for (int j = tid; j < n_pt; j += kBAThreads) {
+                const double* bj = a.bl + 3 * (size_t)(p0 + j);
+                double r[3] = {bj[0], bj[1], bj[2]};
+                for (int q = a.lm_start[p0 + j]; q < a.lm_start[p0 + j + 1]; ++q) {
+                    const int o = a.lm_obs[q];
+                    const int fi = s_free[a.kf_idx[o]];
+                    if (fi < 0) continue;
+                    double H1[6][3];
+                    make_hpl(a.lin + 21 * (size_t)o, H1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int rr = 0; rr < 6; ++rr) r[c] -= H1[rr][c] * s_bs[6 * fi + rr];
+                }
+                const double* Di = a.Dinv + 9 * (size_t)(p0 + j);
+                double* X = a.pts + 3 * (size_t)(p0 + j);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double x = Di[3 * c] * r[0] + Di[3 * c + 1] * r[1] + Di[3 * c + 2] * r[2];
+                    scale += x * (lambda * x + bj[c]);
+                    X[c] += x;
+                }
+            }
+            if (tid < dimp) scale += s_bs[tid] * (lambda * s_bs[tid] + s_bp[tid]);
+            if (tid < n_kf && s_free[tid] >= 0) {  // VertexSE3Sophus::oplusImpl
+                const double* u = s_bs + 6 * s_free[tid];
+                const double v[6] = {u[3], u[4], u[5], u[0], u[1], u[2]};
+                double* est = a.poses + 6 * (size_t)(k0 + tid);
+                const SE3d Tn = se3_mul(se3_exp(v), pose_from_g2o(est));
+                double lg[6];
+                se3_log(Tn, lg);
+                est[0] = lg[3]; est[1] = lg[4]; est[2] = lg[5]; est[3] = lg[0]; est[4] = lg[1]; est[5] = lg[2];
+            }
+            scale = block_sum(scale, s_tmp) + 1e-3;
+            refresh_poses();
+            double tempChi = robust_chi2();
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            if (tid == 0) {
+                double rho = (s_current_chi - tempChi) / scale;
+                if (rho > 0 && isfinite(tempChi)) {
+                    double alpha = 1. - pow((2 * rho - 1), 3);
+                    alpha = fmin(alpha, 2. / 3.);
+                    s_lambda *= fmax(1. / 3., alpha);
+                    s_ni = 2;
+                    s_current_chi = tempChi;
+                    s_accept = 1;
+                } else {
+                    s_lambda *= s_ni;
+                    s_ni *= 2;
+                    s_accept = 0;
+                }
+                s_rho = rho;
+            }
+            __syncthreads();
+            if (!s_accept) {  // _optimizer->pop()
+                if (tid < n_kf)
+                    for (int c = 0; c < 6; ++c) a.poses[6 * (size_t)(k0 + tid) + c] = s_backup[tid][c];
+                for (int i = tid; i < 3 * n_pt; i += kBAThreads) a.pts[3 * (size_t)p0 + i] = a.pts_backup[3 * (size_t)p0 + i];
+                __syncthreads();
+                refresh_poses();
+            }
+            ++qmax;
+            ++trials_total;
+        } while (s_rho < 0 && qmax < a.max_trials);
+        ++iters;
+        chi_last = s_current_chi;
+        if (qmax == a.max_trials || s_rho == 0) break;
+    }
+
+    // outlier flags (BA.cpp:505-515): plain chi2 > 5.991
+    double n_out = 0;
+    for (int o = tid; o < n_obs; o += kBAThreads) {
+        const double* T = s_R[a.kf_idx[o0 + o]];
+        const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
+        const double x = T[0] * X[0] + T[1] * X[1] + T[2] * X[2] + T[3];
+        const double y = T[4] * X[0] + T[5] * X[1] + T[6] * X[2] + T[7];
+        const double z = T[8] * X[0] + T[9] * X[1] + T[10] * X[2] + T[11];
+        const double e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx), e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
+        const int out = (e0 * e0 + e1 * e1 > a.chi2_outlier) ? 1 : 0;
+        a.outlier[o0 + o] = (uint8_t)out;
+        n_out += out;
+    }
+    n_out = block_sum(n_out, s_tmp);
+    if (tid == 0) {
+        double* st = a.stats + 8 * (size_t)prob;
+        st[0] = iters; st[1] = trials_total; st[2] = chi_first; st[3] = chi_last; st[4] = s_lambda; st[5] = n_out;
+    }
+}
+
+// ---- pose-only refinement ----------------------------------------------------------------------------------
+struct Jet6 {
+    double a;
+    double v[6];
+};
+__device__ __forceinline__ Jet6 jc(double c) {
+    Jet6 r;
+    r.a = c;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = 0;
+    return r;
+}
+__device__ __forceinline__ Jet6 operator+(const Jet6& x, const Jet6& y) {
+    Jet6 r;
+    r.a = x.a + y.a;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = x.v[i] + y.v[i];
+    return r;
+}
+__device__ __forceinline__ Jet6 operator-(const Jet6& x, const Jet6& y) {
+    Jet6 r;
+    r.a = x.a - y.a;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = x.v[i] - y.v[i];
+    return r;
+}
+__device__ __forceinline__ Jet6 operator*(const Jet6& x, const Jet6& y) {
+    Jet6 r;
+    r.a = x.a * y.a;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = x.a * y.v[i] + x.v[i] * y.a;
+    return r;
+}
+__device__ __forceinline__ Jet6 operator/(const Jet6& x, const Jet6& y) {
+    const double inv = 1.0 / y.a, q = x.a * inv;
+    Jet6 r;
+    r.a = q;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.v[i] = (x.v[i] - q * y.v[i]) * inv;
+    return r;
+}
+
+// ceres::AngleAxisRotatePoint, pose jets: P[0..2] = t, P[3..5] = angle-axis
+__device__ void project_jet(const double pose[6], const double X[3], Jet6* p0, Jet6* p1, Jet6* p2) {
+    Jet6 P[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        P[i] = jc(pose[i]);
+        P[i].v[i] = 1.0;
+    }
+    const Jet6 pt[3] = {jc(X[0]), jc(X[1]), jc(X[2])};
+    const Jet6 theta2 = P[3] * P[3] + P[4] * P[4] + P[5] * P[5];
+    Jet6 out[3];
+    if (theta2.a > 2.2204460492503131e-16) {
+        Jet6 theta, costheta, sintheta;
+        {
+            const double s = sqrt(theta2.a), d = 1.0 / (2.0 * s);
+            theta.a = s;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) theta.v[i] = theta2.v[i] * d;
+            const double c = cos(s), sn = sin(s);
+            costheta.a = c;
+            sintheta.a = sn;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                costheta.v[i] = -sn * theta.v[i];
+                sintheta.v[i] = c * theta.v[i];
+            }
+        }
+        const Jet6 inv = jc(1.0) / theta;
+        const Jet6 w[3] = {P[3] * inv, P[4] * inv, P[5] * inv};
+        const Jet6 wxp[3] = {w[1] * pt[2] - w[2] * pt[1], w[2] * pt[0] - w[0] * pt[2], w[0] * pt[1] - w[1] * pt[0]};
+        const Jet6 tmp = (w[0] * pt[0] + w[1] * pt[1] + w[2] * pt[2]) * (jc(1.0) - costheta);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = pt[i] * costheta + wxp[i] * sintheta + w[i] * tmp;
+    } else {
+        const Jet6 wxp[3] = {P[4] * pt[2] - P[5] * pt[1], P[5] * pt[0] - P[3] * pt[2], P[3] * pt[1] - P[4] * pt[0]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = pt[i] + wxp[i];
+    }
+    *p0 = out[0] + P[0];
+    *p1 = out[1] + P[1];
+    *p2 = out[2] + P[2];
+}
+
+struct PoseOnlyArgs {
+    const int32_t* offsets;   // per problem range of points
+    const double* pw;         // [total][3]
+    const double* px;         // [total][2]
+    double* T_cw;             // [n_problems][12] in/out
+    uint8_t* inlier;          // [total]
+    double* depth;            // [total]
+    int32_t* n_inlier;        // [n_problems]
+    uint8_t* enable;          // scratch [total]
+    float fx, fy, cx, cy;
+};
+
+constexpr int kPoseThreads = 256;
+
+__device__ bool cholesky6(double A[36], double y[6]) {
+    for (int j = 0; j < 6; ++j) {
+        double d = A[j * 6 + j];
+        for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
+        if (!(d > 0)) return false;
+        d = sqrt(d);
+        A[j * 6 + j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = A[i * 6 + j];
+            for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
+            A[i * 6 + j] = s / d;
+        }
+    }
+    for (int i = 0; i < 6; ++i) {
+        double s = y[i];
+        for (int k = 0; k < i; ++k) s -= A[i * 6 + k] * y[k];
+        y[i] = s / A[i * 6 + i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= A[k * 6 + i] * y[k];
+        y[i] = s / A[i * 6 + i];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyArgs a) {
+    __shared__ double s_tmp[33];
+    __shared__ double s_red[kPoseThreads / 32][40];
+    __shared__ double s_pose[6], s_cand[6], s_scale[6], s_sum[40];
+    __shared__ int s_state;  // 0 continue, 1 terminate
+    __shared__ int s_fail;
+    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = a.offsets[prob], n = a.offsets[prob + 1] - i0;
+    const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
+
+    // reduce `cnt` per-thread partial sums into s_sum (valid for every thread afterwards)
+    auto reduce = [&](const double* part, int cnt) {
+        for (int t = 0; t < cnt; ++t) {
+            const double v = warp_sum(part[t]);
+            if (lane == 0) s_red[warp][t] = v;
+        }
+        __syncthreads();
+        if (tid < cnt) {
+            double s = 0;
+            for (int w = 0; w < kPoseThreads / 32; ++w) s += s_red[w][tid];
+            s_sum[tid] = s;
+        }
+        __syncthreads();
+    };
+    // cost only at `pose`; sets s_fail when a residual block returns false (depth < 0)
+    auto eval_cost = [&](const double* pose) -> double {
+        if (tid == 0) s_fail = 0;
+        __syncthreads();
+        double c = 0;
+        for (int i = tid; i < n; i += kPoseThreads) {
+            if (!a.enable[i0 + i]) continue;
+            Jet6 p0, p1, p2;
+            project_jet(pose, a.pw + 3 * (size_t)(i0 + i), &p0, &p1, &p2);
+            if (p2.a < 0) {
+                s_fail = 1;
+                continue;
+            }
+            const double r0 = (a.px[2 * (size_t)(i0 + i)] - cx) / fx - p0.a / p2.a, r1 = (a.px[2 * (size_t)(i0 + i) + 1] - cy) / fy - p1.a / p2.a;
+            c += r0 * r0 + r1 * r1;
+        }
+        return 0.5 * block_sum(c, s_tmp);
+    };
+    // J^T J (21), J^T r (6), cost, column norms: scaled by s_scale when `scaled`
+    auto eval_normal = [&](const double* pose, bool scaled) {
+        if (tid == 0) s_fail = 0;
+        __syncthreads();
+        double part[34];
+#pragma unroll
+        for (int t = 0; t < 34; ++t) part[t] = 0;
+        for (int i = tid; i < n; i += kPoseThreads) {
+            if (!a.enable[i0 + i]) continue;
+            Jet6 p0, p1, p2;
+            project_jet(pose, a.pw + 3 * (size_t)(i0 + i), &p0, &p1, &p2);
+            if (p2.a < 0) {
+                s_fail = 1;
+                continue;
+            }
+            const Jet6 r0 = jc((a.px[2 * (size_t)(i0 + i)] - cx) / fx) - p0 / p2, r1 = jc((a.px[2 * (size_t)(i0 + i) + 1] - cy) / fy) - p1 / p2;
+            double j0[6], j1[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const double s = scaled ? s_scale[k] : 1.0;
+                j0[k] = r0.v[k] * s;
+                j1[k] = r1.v[k] * s;
+            }
+            int t = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                for (int c = r; c < 6; ++c) part[t++] += j0[r] * j0[c] + j1[r] * j1[c];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) part[21 + k] += j0[k] * r0.a + j1[k] * r1.a;
+            part[27] += r0.a * r0.a + r1.a * r1.a;
+        }
+        reduce(part, 28);
+    };
+
+    // initial pose = [t; so3.log()]
+    SE3d T = se3_from_mat(a.T_cw + 12 * (size_t)prob);
+    double backup[6];
+    {
+        double th;
+        const V3d rl = so3_log(T.q, &th);
+        backup[0] = T.t.x; backup[1] = T.t.y; backup[2] = T.t.z; backup[3] = rl.x; backup[4] = rl.y; backup[5] = rl.z;
+    }
+    for (int i = tid; i < n; i += kPoseThreads) {
+        a.enable[i0 + i] = 1;
+        a.inlier[i0 + i] = 1;
+        a.depth[i0 + i] = -1;
+    }
+    __syncthreads();
+    int cntInlier = 0;
+    for (int round = 0; round < 4; ++round) {
+        if (tid < 6) s_pose[tid] = backup[tid];
+        __syncthreads();
+        // ---- Ceres trust-region LM (default options) ----
+        eval_normal(s_pose, false);
+        bool run = !s_fail;
+        double cost = 0.5 * s_sum[27];
+        if (run) {
+            if (tid < 6) {
+                // diagonal index of column tid in the packed upper triangle
+                int t = 0;
+                for (int r = 0; r < tid; ++r) t += 6 - r;
+                s_scale[tid] = 1.0 / (1.0 + sqrt(s_sum[t]));
+            }
+            double gmax = 0;
+            for (int k = 0; k < 6; ++k) gmax = fmax(gmax, fabs(s_sum[21 + k]));
+            if (gmax <= 1e-10) run = false;
+        }
+        __syncthreads();
+        double radius = 1e4, decrease_factor = 2.0;
+        for (int iter = 0; run && iter < 50; ++iter) {
+            eval_normal(s_pose, true);  // scaled normal equations at the current point
+            double A[36], g[6], y[6];
+            {
+                int t = 0;
+                for (int r = 0; r < 6; ++r)
+                    for (int c = r; c < 6; ++c) {
+                        A[r * 6 + c] = A[c * 6 + r] = s_sum[t++];
+                    }
+                for (int k = 0; k < 6; ++k) g[k] = s_sum[21 + k];
+            }
+            double An[36];
+            for (int t = 0; t < 36; ++t) An[t] = A[t];
+            for (int k = 0; k < 6; ++k) {
+                const double d = fmin(fmax(A[k * 6 + k], 1e-6), 1e32);
+                An[k * 6 + k] += d / radius;
+                y[k] = -g[k];
+            }
+            bool step_ok = cholesky6(An, y);
+            double model_cost_change = 0;
+            if (step_ok) {
+                // -(Js y)^T (r + Js y / 2) = -(y^T g) - y^T A y / 2
+                double yg = 0, yAy = 0;
+                for (int r = 0; r < 6; ++r) {
+                    yg += y[r] * g[r];
+                    double s = 0;
+                    for (int c = 0; c < 6; ++c) s += A[r * 6 + c] * y[c];
+                    yAy += y[r] * s;
+                }
+                model_cost_change = -yg - 0.5 * yAy;
+                step_ok = model_cost_change > 0;
+            }
+            bool accepted = false;
+            if (step_ok) {  // uniform across the CTA: every thread computed the same numbers from s_sum
+                double step_norm = 0, x_norm = 0;
+                if (tid < 6) s_cand[tid] = s_pose[tid] + y[tid] * s_scale[tid];
+                for (int k = 0; k < 6; ++k) {
+                    const double d = y[k] * s_scale[k];
+                    step_norm += d * d;
+                    x_norm += s_pose[k] * s_pose[k];
+                }
+                step_norm = sqrt(step_norm);
+                x_norm = sqrt(x_norm);
+                __syncthreads();
+                const double new_cost = eval_cost(s_cand);
+                if (!s_fail) {
+                    const double relative_decrease = (cost - new_cost) / model_cost_change;
+                    if (relative_decrease > 1e-3) {
+                        accepted = true;
+                        if (step_norm <= 1e-8 * (x_norm + 1e-8)) break;  // parameter tolerance: stop before taking the step
+                        const double cost_change = cost - new_cost;
+                        __syncthreads();
+                        if (tid < 6) s_pose[tid] = s_cand[tid];
+                        __syncthreads();
+                        const double old_cost = cost;
+                        cost = new_cost;
+                        if (fabs(cost_change) <= 1e-6 * old_cost) break;  // function tolerance
+                        eval_normal(s_pose, false);
+                        double gmax = 0;
+                        for (int k = 0; k < 6; ++k) gmax = fmax(gmax, fabs(s_sum[21 + k]));
+                        __syncthreads();
+                        if (gmax <= 1e-10) break;                         // gradient tolerance
+                        radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3));
+                        radius = fmin(1e16, radius);
+                        decrease_factor = 2.0;
+                    }
+                }
+            }
+            if (!accepted) {
+                radius = radius / decrease_factor;
+                decrease_factor *= 2.0;
+                if (radius < 1e-32) break;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        // ---- classification with the pose of the PREVIOUS round (BA.cpp:231-251) ----
+        double cnt = 0;
+        for (int i = tid; i < n; i += kPoseThreads) {
+            const double* X = a.pw + 3 * (size_t)(i0 + i);
+            const V3d pc = transform(T, V3d{X[0], X[1], X[2]});
+            const double u = fx * pc.x / pc.z + cx, v = fy * pc.y / pc.z + cy;
+            const double dx = u - a.px[2 * (size_t)(i0 + i)], dy = v - a.px[2 * (size_t)(i0 + i) + 1];
+            const double error2 = dx * dx + dy * dy;
+            if (error2 > (double)5.991f) {
+                a.inlier[i0 + i] = 0;
+                a.enable[i0 + i] = 0;
+            } else {
+                a.depth[i0 + i] = pc.z;
+                a.inlier[i0 + i] = 1;
+                a.enable[i0 + i] = 1;
+                cnt += 1;
+            }
+        }
+        cntInlier = (int)block_sum(cnt, s_tmp);
+        if (cntInlier < 10) break;
+        double th;
+        T.q = so3_exp(V3d{s_pose[3], s_pose[4], s_pose[5]}, &th);
+        T.t = V3d{s_pose[0], s_pose[1], s_pose[2]};
+        __syncthreads();
+    }
+    if (tid == 0) {
+        se3_to_mat(T, a.T_cw + 12 * (size_t)prob);
+        a.n_inlier[prob] = cntInlier;
+    }
+}
+
+}  // namespace
+
+}  // namespace ygzb
+
+// ---- extern "C" entry points (marshalling + index bookkeeping only) ---------------------------------------
+using namespace ygzb;
+
+namespace {
+template <typename T>
+int h2d(ygzb_ctx* ctx, T* dst, const T* src, size_t count) {
+    if (!count) return YGZB_OK;
+    return check_cuda(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream), "H2D");
+}
+template <typename T>
+int d2h(ygzb_ctx* ctx, T* dst, const T* src, size_t count) {
+    if (!count) return YGZB_OK;
+    return check_cuda(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+}
+#define TRY(x)                          \
+    do {                                \
+        int _rc = (x);                  \
+        if (_rc != YGZB_OK) return _rc; \
+    } while (0)
+}  // namespace
+
+extern "C" {
+
+void ygzb_default_ba_params(ygzb_ba_params* p) {
+    p->max_iters = 20;        // optimizer.optimize(20), BA.cpp:502
+    p->huber_delta = 5.991;   // rk->setDelta(5.991), BA.cpp:451
+    p->chi2_outlier = 5.991;  // BA.cpp:508
+    p->tau = 1e-5;            // g2o OptimizationAlgorithmLevenberg
+    p->max_trials = 10;
+}
+
+int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
+                  double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
+                  const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, ygzb_ba_stats* stats) {
+    if (!ctx || n_problems < 1 || !kf_off || !pt_off || !obs_off || !poses || !fixed || !pts || !kf_idx || !pt_idx || !obs_px ||
+        !prm || !outlier)
+        return YGZB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const size_t P = (size_t)n_problems, NK = (size_t)kf_off[n_problems], NP = (size_t)pt_off[n_problems], NO = (size_t)obs_off[n_problems];
+    // ---- structure: observations grouped by landmark, by pose, and landmark-sharing observation pairs per block pair
+    std::vector<int32_t> lm_start(NP + 1, 0), lm_obs(NO), ps_start(NK + 1, 0), ps_obs(NO), pair_off(P + 1, 0), pair_start, pair_o1, pair_o2;
+    int max_free = 0;
+    for (size_t p = 0; p < P; ++p) {
+        const int k0 = kf_off[p], nk = kf_off[p + 1] - k0, p0 = pt_off[p], npt = pt_off[p + 1] - p0, o0 = obs_off[p], no = obs_off[p + 1] - o0;
+        if (nk < 1 || nk > kMaxPoses) return set_error(ctx, YGZB_ERR_INVALID, "problem %zu: %d poses (1..%d supported)", p, nk, kMaxPoses);
+        std::vector<int> free_index(nk, -1);
+        int nf = 0;
+        for (int k = 0; k < nk; ++k)
+            if (!fixed[k0 + k]) free_index[k] = nf++;
+        if (nf > kMaxFreePoses) return set_error(ctx, YGZB_ERR_INVALID, "problem %zu: %d free poses (max %d)", p, nf, kMaxFreePoses);
+        max_free = std::max(max_free, nf);
+        for (int o = 0; o < no; ++o) {
+            if (kf_idx[o0 + o] < 0 || kf_idx[o0 + o] >= nk || pt_idx[o0 + o] < 0 || pt_idx[o0 + o] >= npt)
+                return set_error(ctx, YGZB_ERR_INVALID, "observation %d: index out of range", o0 + o);
+            lm_start[p0 + pt_idx[o0 + o] + 1]++;
+            ps_start[k0 + kf_idx[o0 + o] + 1]++;
+        }
+        (void)npt;
+    }
+    for (size_t i = 0; i < NP; ++i) lm_start[i + 1] += lm_start[i];
+    for (size_t i = 0; i < NK; ++i) ps_start[i + 1] += ps_start[i];
+    {
+        std::vector<int32_t> lc(lm_start.begin(), lm_start.end() - 1), pc(ps_start.begin(), ps_start.end() - 1);
+        for (size_t p = 0; p < P; ++p)
+            for (int o = obs_off[p]; o < obs_off[p + 1]; ++o) {
+                lm_obs[lc[pt_off[p] + pt_idx[o]]++] = o;
+                ps_obs[pc[kf_off[p] + kf_idx[o]]++] = o;
+            }
+    }
+    for (size_t p = 0; p < P; ++p) {
+        const int k0 = kf_off[p], nk = kf_off[p + 1] - k0, p0 = pt_off[p], npt = pt_off[p + 1] - p0;
+        std::vector<int> free_index(nk, -1);
+        int nf = 0;
+        for (int k = 0; k < nk; ++k)
+            if (!fixed[k0 + k]) free_index[k] = nf++;
+        const int n_pairs = nf * (nf + 1) / 2;
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> buckets(n_pairs);
+        auto pair_id = [&](int f1, int f2) { return f1 * nf - f1 * (f1 - 1) / 2 + (f2 - f1); };
+        for (int j = 0; j < npt; ++j)
+            for (int q1 = lm_start[p0 + j]; q1 < lm_start[p0 + j + 1]; ++q1) {
+                const int f1 = free_index[kf_idx[lm_obs[q1]]];
+                if (f1 < 0) continue;
+                for (int q2 = lm_start[p0 + j]; q2 < lm_start[p0 + j + 1]; ++q2) {
+                    const int f2 = free_index[kf_idx[lm_obs[q2]]];
+                    if (f2 < f1 || (f2 == f1 && q2 != q1)) continue;
+                    buckets[pair_id(f1, f2)].push_back({lm_obs[q1], lm_obs[q2]});
+                }
+            }
+        pair_off[p] = (int32_t)pair_start.size();
+        for (int b = 0; b < n_pairs; ++b) {
+            pair_start.push_back((int32_t)pair_o1.size());
+            for (auto& e : buckets[b]) {
+                pair_o1.push_back(e.first);
+                pair_o2.push_back(e.second);
+            }
+        }
+        pair_start.push_back((int32_t)pair_o1.size());
+    }
+    pair_off[P] = (int32_t)pair_start.size();
+    const size_t NPAIR = pair_o1.size(), NPS = pair_start.size();
+
+    Carver sz(nullptr);
+    sz.take<int32_t>(3 * (P + 1)); sz.take<double>(6 * NK); sz.take<uint8_t>(NK); sz.take<double>(3 * NP); sz.take<int32_t>(2 * NO);
+    sz.take<double>(2 * NO); sz.take<int32_t>(NP + 1 + NO + NK + 1 + NO); sz.take<int32_t>(P + 1 + NPS + 2 * NPAIR);
+    sz.take<double>(21 * NO); sz.take<double>(9 * NP); sz.take<double>(3 * NP); sz.take<double>(9 * NP); sz.take<double>(3 * NP);
+    sz.take<double>(3 * NP); sz.take<uint8_t>(NO); sz.take<double>(8 * P);
+    void* buf = dev_scratch(ctx, 7, sz.bytes());
+    if (!buf) return YGZB_ERR_CUDA;
+    Carver c(buf);
+    int32_t* d_off = c.take<int32_t>(3 * (P + 1));
+    double* d_poses = c.take<double>(6 * NK);
+    uint8_t* d_fixed = c.take<uint8_t>(NK);
+    double* d_pts = c.take<double>(3 * NP);
+    int32_t* d_idx = c.take<int32_t>(2 * NO);
+    double* d_obs = c.take<double>(2 * NO);
+    int32_t* d_csr = c.take<int32_t>(NP + 1 + NO + NK + 1 + NO);
+    int32_t* d_pairs = c.take<int32_t>(P + 1 + NPS + 2 * NPAIR);
+    BAArgs a;
+    a.lin = c.take<double>(21 * NO);
+    a.Hll = c.take<double>(9 * NP);
+    a.bl = c.take<double>(3 * NP);
+    a.Dinv = c.take<double>(9 * NP);
+    a.xl = c.take<double>(3 * NP);
+    a.pts_backup = c.take<double>(3 * NP);
+    a.outlier = c.take<uint8_t>(NO);
+    a.stats = c.take<double>(8 * P);
+    // kf_idx / pt_idx stay LOCAL to the problem; lm_obs / ps_obs / pair entries are GLOBAL observation ids
+    TRY(h2d(ctx, d_off, kf_off, P + 1));
+    TRY(h2d(ctx, d_off + (P + 1), pt_off, P + 1));
+    TRY(h2d(ctx, d_off + 2 * (P + 1), obs_off, P + 1));
+    TRY(h2d(ctx, d_poses, poses, 6 * NK));
+    TRY(h2d(ctx, d_fixed, fixed, NK));
+    TRY(h2d(ctx, d_pts, pts, 3 * NP));
+    TRY(h2d(ctx, d_idx, kf_idx, NO));
+    TRY(h2d(ctx, d_idx + NO, pt_idx, NO));
+    TRY(h2d(ctx, d_obs, obs_px, 2 * NO));
+    TRY(h2d(ctx, d_csr, lm_start.data(), NP + 1));
+    TRY(h2d(ctx, d_csr + NP + 1, lm_obs.data(), NO));
+    TRY(h2d(ctx, d_csr + NP + 1 + NO, ps_start.data(), NK + 1));
+    TRY(h2d(ctx, d_csr + NP + 1 + NO + NK + 1, ps_obs.data(), NO));
+    TRY(h2d(ctx, d_pairs, pair_off.data(), P + 1));
+    TRY(h2d(ctx, d_pairs + P + 1, pair_start.data(), NPS));
+    TRY(h2d(ctx, d_pairs + P + 1 + NPS, pair_o1.data(), NPAIR));
+    TRY(h2d(ctx, d_pairs + P + 1 + NPS + NPAIR, pair_o2.data(), NPAIR));
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope after the launch
+    a.kf_off = d_off; a.pt_off = d_off + (P + 1); a.obs_off = d_off + 2 * (P + 1);
+    a.poses = d_poses; a.fixed = d_fixed; a.pts = d_pts; a.kf_idx = d_idx; a.pt_idx = d_idx + NO; a.obs = d_obs;
+    a.lm_start = d_csr; a.lm_obs = d_csr + NP + 1; a.ps_start = d_csr + NP + 1 + NO; a.ps_obs = d_csr + NP + 1 + NO + NK + 1;
+    a.pair_off = d_pairs; a.pair_start = d_pairs + P + 1; a.pair_o1 = d_pairs + P + 1 + NPS; a.pair_o2 = d_pairs + P + 1 + NPS + NPAIR;
+    a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
+    a.max_iters = prm->max_iters; a.max_trials = prm->max_trials; a.huber_delta = prm->huber_delta;
+    a.chi2_outlier = prm->chi2_outlier; a.tau = prm->tau;
+    const int dimp = 6 * std::max(max_free, 1);
+    const size_t smem = sizeof(double) * ((size_t)dimp * dimp + (size_t)std::max(max_free, 1) * 36 + 2 * (size_t)dimp);
+    YGZB_CUDA(ctx, cudaFuncSetAttribute(local_ba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope ps(ctx, kStageLocalBA);
+        local_ba_kernel<<<n_problems, kBAThreads, smem, ctx->stream>>>(a);
+    }
+    YGZB_LAUNCHED(ctx);
+    TRY(d2h(ctx, poses, d_poses, 6 * NK));
+    TRY(d2h(ctx, pts, d_pts, 3 * NP));
+    TRY(d2h(ctx, outlier, a.outlier, NO));
+    std::vector<double> hst(8 * P);
+    TRY(d2h(ctx, hst.data(), a.stats, 8 * P));
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats)
+        for (size_t p = 0; p < P; ++p) {
+            stats[p].iters = (int)hst[8 * p];
+            stats[p].lm_trials = (int)hst[8 * p + 1];
+            stats[p].chi2_initial = hst[8 * p + 2];
+            stats[p].chi2_final = hst[8 * p + 3];
+            stats[p].lambda_final = hst[8 * p + 4];
+            stats[p].n_outliers = (int)hst[8 * p + 5];
+        }
+    return YGZB_OK;
+}
+
+int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const double* pt_world, const double* px, double* T_cw,
+                   uint8_t* inlier, double* depth, int32_t* n_inlier) {
+    if (!ctx || n_problems < 1 || !offsets || !T_cw || !n_inlier) return YGZB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const size_t P = (size_t)n_problems, N = (size_t)offsets[n_problems];
+    if (N && (!pt_world || !px || !inlier || !depth)) return YGZB_ERR_INVALID;
+    Carver sz(nullptr);
+    sz.take<int32_t>(P + 1); sz.take<double>(3 * N); sz.take<double>(2 * N); sz.take<double>(12 * P); sz.take<uint8_t>(N);
+    sz.take<double>(N); sz.take<int32_t>(P); sz.take<uint8_t>(N);
+    void* buf = dev_scratch(ctx, 7, sz.bytes());
+    if (!buf) return YGZB_ERR_CUDA;
+    Carver c(buf);
+    PoseOnlyArgs a;
+    int32_t* d_off = c.take<int32_t>(P + 1);
+    double* d_pw = c.take<double>(3 * N);
+    double* d_px = c.take<double>(2 * N);
+    a.T_cw = c.take<double>(12 * P);
+    a.inlier = c.take<uint8_t>(N);
+    a.depth = c.take<double>(N);
+    a.n_inlier = c.take<int32_t>(P);
+    a.enable = c.take<uint8_t>(N);
+    a.offsets = d_off; a.pw = d_pw; a.px = d_px;
+    a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
+    TRY(h2d(ctx, d_off, offsets, P + 1));
+    TRY(h2d(ctx, d_pw, pt_world, 3 * N));
+    TRY(h2d(ctx, d_px, px, 2 * N));
+    TRY(h2d(ctx, a.T_cw, (const double*)T_cw, 12 * P));
+    {
+        ProfScope ps(ctx, kStagePoseOnly);
+        pose_only_kernel<<<n_problems, kPoseThreads, 0, ctx->stream>>>(a);
+    }
+    YGZB_LAUNCHED(ctx);
+    TRY(d2h(ctx, T_cw, a.T_cw, 12 * P));
+    TRY(d2h(ctx, inlier, a.inlier, N));
+    TRY(d2h(ctx, depth, a.depth, N));
+    TRY(d2h(ctx, n_inlier, a.n_inlier, P));
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return YGZB_OK;
+}
+
+}  // extern "C"
