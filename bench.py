@@ -182,6 +182,88 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(line))
 
 
+def secondary_workloads(ctx) -> dict:
+    """BASELINE configs C3 (alignment) and C4 (local BA) on one GPU next to the CPU oracle (rank 0, N=1 only).
+    Timed through the public C ABI (host buffers in, host buffers out), CUDA kernels timed by the library's
+    per-stage events."""
+    import numpy as np
+    from oracle.pyoracle import Oracle
+    from ygz_slam_b200 import se3, synth
+    ora = Oracle(native=True)
+    out = {}
+    # ---- C3: 2000 8x8 patches (FindDirectProjection) + sparse image alignment, 4-level pyramid --------
+    g1, d1, T1 = synth.stream_frame(1)
+    g2, _, T2 = synth.stream_frame(4)
+    fr = ctx.frames(2)
+    fr.upload(np.stack([g1, g2]))
+    p1, p2 = ora.build_pyramid(g1, LEVELS), ora.build_pyramid(g2, LEVELS)
+    f = ora.detect(p1, n_levels=LEVELS)
+    rng = np.random.default_rng(7)
+    idx = rng.integers(0, f["n"], 2000)
+    px = np.stack([f["px"][idx], f["py"][idx]], 1)
+    depth = d1[px[:, 1].astype(int), px[:, 0].astype(int)]
+    level = f["level"][idx]
+    Trel = se3.mul(T2, se3.inv(T1))
+    Xc = np.stack([(px[:, 0] - synth.CX) * depth / synth.FX, (px[:, 1] - synth.CY) * depth / synth.FY, depth], 1)
+    Xc2 = (Trel[:, :3] @ Xc.T).T + Trel[:, 3]
+    gt = np.stack([synth.FX * Xc2[:, 0] / Xc2[:, 2] + synth.CX, synth.FY * Xc2[:, 1] / Xc2[:, 2] + synth.CY], 1)
+    init = gt + rng.uniform(-2, 2, gt.shape)
+    I = np.eye(4)[:3]
+    poses = np.stack([I.reshape(-1), Trel.reshape(-1)])
+    z, o = np.zeros(2000, np.int32), np.ones(2000, np.int32)
+
+    def timed(fn, reps):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        return (time.perf_counter() - t0) / reps, r
+
+    ctx.profile(True)
+    t_gpu, (gpx, glvl, gok) = timed(lambda: fr.project_align(z, o, poses, z, o, px, depth, level.astype(np.uint8), init), 20)
+    prof = ctx.profile_read()
+    t_cpu, (cpx, clvl, cok) = timed(lambda: ora.find_direct_projection(p1, p2, W, H, LEVELS, I, Trel, px, depth, level, init), 3)
+    out["c3_project_align_2000_patches"] = {
+        "gpu_ms_per_call_e2e": t_gpu * 1e3, "gpu_kernel_ms": prof["project_align"][0] / max(prof["project_align"][1], 1),
+        "cpu_ms_per_call": t_cpu * 1e3, "patches_per_s_gpu_e2e": 2000 / t_gpu, "bit_exact_vs_oracle": bool(np.array_equal(gpx, cpx) and np.array_equal(gok, cok)),
+        "converged": int(gok.sum())}
+    has = np.ones(2000, np.uint8)
+    t_gpu, (gT, gn, _) = timed(lambda: fr.sparse_align([0], [1], [0, 2000], px, depth, has, T1.reshape(1, 12), T1.reshape(1, 12), max_level=3), 20)
+    prof = ctx.profile_read()
+    t_cpu, (cT, cn, _) = timed(lambda: ora.sparse_align(p1, p2, W, H, LEVELS, px, depth, has, T1, T1, max_level=3), 3)
+    out["c3_sparse_align_2000_features_4_levels"] = {
+        "gpu_ms_per_call_e2e": t_gpu * 1e3, "gpu_kernel_ms": prof["sparse_align"][0] / max(prof["sparse_align"][1], 1),
+        "cpu_ms_per_call": t_cpu * 1e3,
+        "pose_diff_vs_oracle": float(np.linalg.norm(se3.se3_log(se3.mul(se3.inv(gT[0]), cT)))),
+        "pose_err_vs_ground_truth": float(np.linalg.norm(se3.se3_log(se3.mul(se3.inv(gT[0]), T2))))}
+    fr.close()
+    # ---- C4: local BA 10 KF x 2000 landmarks x ~8000 observations, 20 LM iterations, Huber 5.991 -------
+    sc = synth.ba_scene()
+    g2o = np.concatenate([sc["poses_noisy"][:, 3:], sc["poses_noisy"][:, :3]], 1)
+    fixed = np.zeros(10, np.uint8)
+    fixed[0] = 1
+    n_obs = len(sc["kf_idx"])
+    t_gpu, (P, X, outl, st) = timed(lambda: ctx.local_ba([0, 10], [0, 2000], [0, n_obs], g2o, fixed, sc["pts_noisy"], sc["kf_idx"],
+                                                         sc["pt_idx"], sc["px"]), 10)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    t_cpu, (wP, wX, wout, wst) = timed(lambda: ora.local_ba(g2o, fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"]), 3)
+    k_ms = prof["local_ba"][0] / max(prof["local_ba"][1], 1)
+    trials = st[0]["lm_trials"]
+    kbar = n_obs / 2000.0
+    flop_per_trial = 300.0 * n_obs + 2000 * (216 * kbar**2 + 108 * kbar + 50) + 54**3 / 3.0   # SURVEY.md 8d
+    out["c4_local_ba_10kf_2000pt"] = {
+        "observations": n_obs, "gpu_ms_total_e2e": t_gpu * 1e3, "gpu_kernel_ms_total": k_ms, "gpu_iters": st[0]["iters"],
+        "gpu_lm_trials": trials, "gpu_ms_per_iter": k_ms / max(st[0]["iters"], 1), "gpu_ms_per_lm_trial": k_ms / max(trials, 1),
+        "cpu_ms_total": t_cpu * 1e3, "cpu_iters": wst["iters"], "cpu_lm_trials": wst["lm_trials"],
+        "cpu_ms_per_iter": t_cpu * 1e3 / max(wst["iters"], 1), "cpu_ms_per_lm_trial": t_cpu * 1e3 / max(wst["lm_trials"], 1),
+        "cpu_kind": "oracle restatement of g2o LM + Schur (dense Cholesky), 1 thread; Ceres/g2o are not installable here",
+        "achieved_gflops_fp64": flop_per_trial * trials / (k_ms * 1e-3) / 1e9, "flop_per_lm_trial_model": flop_per_trial,
+        "chi2_final_gpu": st[0]["chi2_final"], "chi2_final_cpu": wst["chi2_final"],
+        "max_landmark_diff_vs_oracle_m": float(np.abs(X - wX).max())}
+    return out
+
+
 def workload_config(batch: int, how: str) -> dict:
     return {"workload": "C2: FAST-10+ORB extract (grid 10px, thr 15) + cross-checked brute-force Hamming match, "
                         "640x480 u8, 8-level pyramid, frame i matched against frame i+1",
@@ -386,6 +468,13 @@ def main() -> None:
                    "sample": f"{ns} frames of the same batch (pyramid+Detect+cross-checked BF match), oracle -O3 AVX2/FMA "
                              f"build, single thread like the reference's own code; host has {os.cpu_count()} logical CPUs"}
 
+        extra = None
+        if world == 1:
+            try:
+                extra = secondary_workloads(ctx)
+            except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
+                extra = {"error": repr(e)}
+
         line = {
             "metric": "tracked frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -401,6 +490,7 @@ def main() -> None:
             "kernel_shares": shares,
             "cpu_baseline": cpu,
             "keypoints_per_frame": kpf,
+            "secondary_workloads": extra,
         }
         print(json.dumps(line))
     for c_, f_, _ in workers[1:]:

@@ -1,0 +1,64 @@
+// Builds against the C++ shim (ygz_slam_b200/host/ygz_b200.hpp) the way a reference caller would:
+// test_orb_match shape (Detect on two frames + brute-force match) followed by sparse alignment and
+// direct projection.  Input: two raw 640x480 grey frames + depth of frame 1 + the relative pose, written
+// by the Python test; prints a few summary numbers that the Python side compares with the oracle.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "../ygz_slam_b200/host/ygz_b200.hpp"
+
+using namespace ygz;
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    FILE* fp = fopen(argv[1], "rb");
+    if (!fp) return 3;
+    Frame f1, f2;
+    f1._color.create(480, 640, 1);
+    f2._color.create(480, 640, 1);
+    std::vector<float> depth(640 * 480);
+    double T2[12];
+    if (fread(f1._color.data, 1, 640 * 480, fp) != 640 * 480 || fread(f2._color.data, 1, 640 * 480, fp) != 640 * 480 ||
+        fread(depth.data(), 4, 640 * 480, fp) != 640 * 480 || fread(T2, 8, 12, fp) != 12)
+        return 4;
+    fclose(fp);
+    PinholeCamera cam;
+    Frame::SetCamera(&cam);
+    f1.InitFrame();
+    f2.InitFrame();
+    FeatureDetector det;
+    det.Detect(&f1);
+    det.Detect(&f2);
+    std::vector<int> idx, dist;
+    Matcher::BruteForceMatch(&f1, &f2, idx, dist);
+    int n_match = 0;
+    long sum_dist = 0;
+    for (size_t i = 0; i < idx.size(); ++i)
+        if (idx[i] >= 0) { ++n_match; sum_dist += dist[i]; }
+    printf("features %zu %zu matches %d dist_sum %ld\n", f1._features.size(), f2._features.size(), n_match, sum_dist);
+    // give the features of frame 1 depth + map points, then align frame 2 against it
+    std::vector<MapPoint> mps(f1._features.size());
+    for (size_t i = 0; i < f1._features.size(); ++i) {
+        Feature* f = f1._features[i];
+        f->_depth = depth[(int)f->_pixel[1] * 640 + (int)f->_pixel[0]];
+        f->_mappoint = &mps[i];
+    }
+    Matcher m;
+    const bool ok = m.SparseImageAlignment(&f1, &f2);
+    double est[12];
+    f2._TCW.matrix3x4(est);
+    double err = 0;
+    for (int i = 0; i < 12; ++i) err = std::fmax(err, std::fabs(est[i] - T2[i]));
+    printf("sparse_align ok %d max_abs_pose_diff_to_gt %.6f\n", (int)ok, err);
+    int n_ok = 0;
+    for (size_t i = 0; i < f1._features.size(); i += 4) {
+        Feature* f = f1._features[i];
+        const Vector3d pc((f->_pixel[0] - cam.cx()) * f->_depth / cam.fx(), (f->_pixel[1] - cam.cy()) * f->_depth / cam.fy(), f->_depth);
+        Vector2d px = cam.World2Pixel(pc, f2._TCW);  // T_ref = I: world == ref camera
+        int level = 0;
+        n_ok += m.FindDirectProjection(&f1, &f2, f, px, level);
+    }
+    printf("direct_projection ok %d\n", n_ok);
+    return 0;
+}

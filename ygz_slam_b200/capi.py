@@ -76,6 +76,39 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _Pinned:
+    """Keeps a page-locked host allocation (ygzb_host_alloc) alive behind a numpy view."""
+
+    def __init__(self, lib, nbytes):
+        self.lib = lib
+        self.ptr = C.c_void_p()
+        if lib.ygzb_host_alloc(C.byref(self.ptr), C.c_size_t(max(nbytes, 1))) != 0:
+            raise YgzbError("ygzb_host_alloc failed")
+
+    def __del__(self):
+        try:
+            self.lib.ygzb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory: D2H/H2D copies to it run at full PCIe rate and asynchronously."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    owner = _Pinned(lib, n * dtype.itemsize)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(owner.ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    _PINNED_OWNERS[id(arr)] = owner
+    import weakref
+    weakref.finalize(arr, _PINNED_OWNERS.pop, id(arr), None)
+    return arr
+
+
+_PINNED_OWNERS: dict = {}
+
+
 class Context:
     """One device + one stream (ygzb_ctx)."""
 
@@ -254,12 +287,13 @@ class Frames:
         n = len(slots)
         occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8).reshape(n, self.ctx.n_cells)
         cap = n * self.ctx.n_cells
-        if getattr(self, "_kp_cap", 0) < cap:
-            self._kp = dict(offsets=np.empty(self.capacity + 1, np.int32), x=np.empty(cap, np.float32),
-                            y=np.empty(cap, np.float32), level=np.empty(cap, np.uint8), score=np.empty(cap, np.float32),
-                            angle=np.empty(cap, np.float32), desc=np.empty((cap, 32), np.uint8), cell=np.empty(cap, np.int32))
-            self._kp_cap = cap
-        b = self._kp
+        if getattr(self, "_kpp_cap", 0) < cap:
+            self._kpp = dict(offsets=pinned_empty(self.capacity + 1, np.int32), x=pinned_empty(cap, np.float32),
+                             y=pinned_empty(cap, np.float32), level=pinned_empty(cap, np.uint8), score=pinned_empty(cap, np.float32),
+                             angle=pinned_empty(cap, np.float32), desc=pinned_empty((cap, 32), np.uint8),
+                             cell=pinned_empty(cap, np.int32))
+            self._kpp_cap = cap
+        b = self._kpp
         kp = Keypoints(*[b[k].ctypes.data for k in ("offsets", "x", "y", "level", "score", "angle", "desc", "cell")], cap)
         self.ctx.check(self.lib.ygzb_detect(self.h, _p(slots), n, _p(occ), C.byref(kp)), "ygzb_detect")
         return b["offsets"][: n + 1], b
@@ -270,11 +304,11 @@ class Frames:
         n = len(a)
         cap = n * self.ctx.n_cells
         if getattr(self, "_mp_cap", 0) < cap:
-            self._mp = (np.empty(n + 1, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32))
+            self._mp = (pinned_empty(n + 1, np.int32), pinned_empty(cap, np.int32), pinned_empty(cap, np.int32))
             self._mp_cap = cap
         qoff, idx, dist = self._mp
         if len(qoff) < n + 1:
-            qoff = np.empty(n + 1, np.int32)
+            qoff = pinned_empty(n + 1, np.int32)
             self._mp = (qoff, idx, dist)
         self.ctx.check(self.lib.ygzb_match_frames(self.h, _p(a), _p(b), n, int(cross_check), _p(qoff), _p(idx), _p(dist),
                                                   cap), "ygzb_match_frames")

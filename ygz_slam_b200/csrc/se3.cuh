@@ -3,7 +3,16 @@
 // quaternion (re-normalised after every product), SE3 = SO3 + translation, tangent = [upsilon; omega].
 // Eigen's Quaternion::_transformVector / toRotationMatrix / Quaternion(Matrix3) are restated.
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#else  // plain host C++ (the shim classes in ../host use the same arithmetic for SE3 composition)
+#include <cmath>
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
+using std::sqrt; using std::sin; using std::cos; using std::tan; using std::atan;
+#endif
 
 namespace ygzb {
 

@@ -1,0 +1,529 @@
+// ygz_b200.hpp -- host-side C++ mirror of the reference's call surface for the tracking + local-BA hot path,
+// implemented on top of the C ABI (include/ygz_b200.h).  Same class / method names, argument meaning and
+// bool/enum error behaviour as the reference headers, so the callers in src/Module compile against it:
+//
+//   ygz::FeatureDetector   include/ygz/Algorithm/FeatureDetector.h:43-101
+//   ygz::Matcher           include/ygz/Algorithm/Matcher.h:15-155
+//   ygz::cvutils::Align2D  include/ygz/Algorithm/CVUtils.h:163-169
+//   ygz::SparseImgAlign    include/ygz/Algorithm/SparseImageAlign.h:12-58
+//   ygz::ba::*             include/ygz/Algorithm/BA.h:23-66
+//   ygz::Frame / Feature / MapPoint / PinholeCamera   include/ygz/Basic/*.h (data carriers only)
+//   ygz::Optimizer         facade over ygz::ba for the north star's vocabulary (the reference has no such class)
+//
+// The reference's data types depend on Eigen / OpenCV / Sophus, which are not part of this repo: minimal
+// stand-ins with the same member names are provided (Vector2d, Vector3d, SE3, Mat).  A port that keeps the
+// real Eigen/Sophus types only has to replace the conversions in b200::detail.
+// No computation happens here: every method marshals AoS <-> SoA and calls ygzb_*.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <list>
+#include <map>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/ygz_b200.h"
+#include "../csrc/se3.cuh"
+
+namespace ygz {
+
+struct Vector2d {
+    double v[2]{0, 0};
+    Vector2d() = default;
+    Vector2d(double x, double y) : v{x, y} {}
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+};
+struct Vector3d {
+    double v[3]{0, 0, 0};
+    Vector3d() = default;
+    Vector3d(double x, double y, double z) : v{x, y, z} {}
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+};
+
+// stand-in for Sophus::SE3 (quaternion + translation, same arithmetic as thirdparty/Sophus)
+struct SE3 {
+    ygzb::SE3d T{{1, 0, 0, 0}, {0, 0, 0}};
+    SE3() = default;
+    explicit SE3(const ygzb::SE3d& t) : T(t) {}
+    SE3 operator*(const SE3& o) const { return SE3(ygzb::se3_mul(T, o.T)); }
+    Vector3d operator*(const Vector3d& p) const {
+        const ygzb::V3d r = ygzb::transform(T, ygzb::V3d{p[0], p[1], p[2]});
+        return Vector3d(r.x, r.y, r.z);
+    }
+    SE3 inverse() const { return SE3(ygzb::se3_inverse(T)); }
+    Vector3d translation() const { return Vector3d(T.t.x, T.t.y, T.t.z); }
+    void matrix3x4(double* out) const { ygzb::se3_to_mat(T, out); }
+    static SE3 from3x4(const double* m) { return SE3(ygzb::se3_from_mat(m)); }
+    static SE3 exp(const double* upsilon_omega) { return SE3(ygzb::se3_exp(upsilon_omega)); }
+    void log(double* upsilon_omega) const { ygzb::se3_log(T, upsilon_omega); }
+};
+
+// 8-bit image view (stand-in for the CV_8U cv::Mat members)
+struct Mat {
+    std::vector<uint8_t> buf;
+    int rows = 0, cols = 0, channels = 1;
+    uint8_t* data = nullptr;
+    void create(int r, int c, int ch = 1) {
+        rows = r; cols = c; channels = ch;
+        buf.assign((size_t)r * c * ch, 0);
+        data = buf.data();
+    }
+};
+
+struct Frame;
+struct MapPoint;
+
+struct Feature {  // include/ygz/Basic/Feature.h:15-36
+    Feature(const Vector2d& pixel, const int& level = 0, const double& score = 0) : _pixel(pixel), _level(level), _score(score) {}
+    Vector2d _pixel;
+    double _depth = -1;
+    int _level = -1;
+    double _angle = 0;
+    uint8_t _desc[32]{};
+    Frame* _frame = nullptr;
+    MapPoint* _mappoint = nullptr;
+    bool _bad = false;
+    double _score = 0;
+};
+
+struct MapPoint {  // include/ygz/Basic/MapPoint.h:17-46 (fields used on the hot path)
+    unsigned long _id = 0;
+    Vector3d _pos_world;
+    bool _bad = false;
+    int _cnt_found = 0;
+    std::map<unsigned long, Feature*> _obs;  // keyframe id -> feature
+};
+
+class PinholeCamera {  // include/ygz/Basic/Camera.h:10-112
+  public:
+    PinholeCamera(float fx = 520.9f, float fy = 521.0f, float cx = 325.1f, float cy = 249.7f) : _fx(fx), _fy(fy), _cx(cx), _cy(cy) {}
+    Vector3d World2Camera(const Vector3d& p_w, const SE3& T_c_w) const { return T_c_w * p_w; }
+    Vector2d Camera2Pixel(const Vector3d& p) const { return Vector2d(_fx * p[0] / p[2] + _cx, _fy * p[1] / p[2] + _cy); }
+    Vector2d World2Pixel(const Vector3d& p_w, const SE3& T) const { return Camera2Pixel(World2Camera(p_w, T)); }
+    float fx() const { return _fx; }
+    float fy() const { return _fy; }
+    float cx() const { return _cx; }
+    float cy() const { return _cy; }
+  protected:
+    float _fx, _fy, _cx, _cy;
+};
+
+struct Frame {  // include/ygz/Basic/Frame.h:20-166 (fields used on the hot path)
+    struct Option { int _pyramid_level = 3; } _option;
+    ~Frame() { CleanAllFeatures(); }
+    void InitFrame();  // cvtColor + pyrDown chain (src/Basic/Frame.cpp:22-40) -> device pyramid
+    bool InFrame(const Vector2d& px, const int& boarder = 10) const {
+        return px[0] >= boarder && px[0] < _color.cols - boarder && px[1] >= boarder && px[1] < _color.rows - boarder;
+    }
+    void CleanAllFeatures() {
+        for (Feature* f : _features) delete f;
+        _features.clear();
+    }
+    static void SetCamera(PinholeCamera* c) { _camera = c; }
+    unsigned long _id = 0, _keyframe_id = 0;
+    SE3 _TCW;
+    bool _is_keyframe = false;
+    std::vector<Feature*> _features;
+    Mat _color;                 // BGR (3 channels) or grey (1 channel) input image
+    int _slot = -1;             // device pyramid slot (set by InitFrame)
+    static inline PinholeCamera* _camera = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------
+namespace b200 {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// process-wide device runtime: one ygzb context + a pool of frame slots (one context per host thread:
+// like the reference, the algorithm classes are single-threaded)
+class Runtime {
+  public:
+    static Runtime& Get() {
+        static Runtime r;
+        return r;
+    }
+    void Configure(const ygzb_params& p, int device = 0, int slots = 64) {
+        Release();
+        if (ygzb_create(device, &p, &ctx_) != YGZB_OK) {
+            std::string m = ctx_ ? ygzb_last_error(ctx_) : "no sm_100 device (there is no CPU fallback)";
+            if (ctx_) ygzb_destroy(ctx_);
+            ctx_ = nullptr;
+            throw Error("ygzb_create: " + m);
+        }
+        Check(ygzb_frames_create(ctx_, slots, &frames_), "ygzb_frames_create");
+        params_ = p;
+        owner_.assign(slots, nullptr);
+        next_ = 0;
+    }
+    ygzb_ctx* ctx() { Ensure(); return ctx_; }
+    ygzb_frames* frames() { Ensure(); return frames_; }
+    const ygzb_params& params() { Ensure(); return params_; }
+    // round-robin slot assignment; a frame whose slot was recycled must call InitFrame again
+    int AcquireSlot(Frame* f) {
+        Ensure();
+        const int s = next_;
+        next_ = (next_ + 1) % (int)owner_.size();
+        if (owner_[s]) owner_[s]->_slot = -1;
+        owner_[s] = f;
+        return s;
+    }
+    void Check(int rc, const char* what) {
+        if (rc != YGZB_OK) throw Error(std::string(what) + ": " + (ctx_ ? ygzb_last_error(ctx_) : "?"));
+    }
+    void Release() {
+        if (frames_) ygzb_frames_destroy(frames_);
+        if (ctx_) ygzb_destroy(ctx_);
+        frames_ = nullptr;
+        ctx_ = nullptr;
+    }
+    ~Runtime() { Release(); }
+  private:
+    void Ensure() {
+        if (!ctx_) {
+            ygzb_params p;
+            ygzb_default_params(&p);
+            Configure(p);
+        }
+    }
+    ygzb_ctx* ctx_ = nullptr;
+    ygzb_frames* frames_ = nullptr;
+    ygzb_params params_{};
+    std::vector<Frame*> owner_;
+    int next_ = 0;
+};
+
+inline int SlotOf(Frame* f) {
+    if (f->_slot < 0) throw Error("Frame::InitFrame() has not been called (or its device slot was recycled)");
+    return f->_slot;
+}
+inline void PoseTo3x4(const SE3& T, double* out) { T.matrix3x4(out); }
+
+}  // namespace b200
+
+inline void Frame::InitFrame() {
+    auto& rt = b200::Runtime::Get();
+    _slot = rt.AcquireSlot(this);
+    rt.Check(ygzb_frames_upload(rt.frames(), _slot, 1, _color.data, _color.channels, (size_t)_color.rows * _color.cols * _color.channels),
+             "ygzb_frames_upload");
+}
+
+// ---------------------------------------------------------------------------------------------------
+class FeatureDetector {  // include/ygz/Algorithm/FeatureDetector.h
+  public:
+    struct Option {
+        int _image_width = 640, _image_height = 480;
+        int _cell_size = 10;
+        int _grid_rows = 0, _grid_cols = 0;
+        double _detection_threshold = 15.0;
+    } _option;
+    FeatureDetector() { LoadParams(); }
+    void LoadParams() {
+        const ygzb_params& p = b200::Runtime::Get().params();
+        _option._image_width = p.image_width;
+        _option._image_height = p.image_height;
+        _option._cell_size = p.cell_size;
+        _option._detection_threshold = p.fast_threshold;
+        ygzb_grid_dims(b200::Runtime::Get().ctx(), &_option._grid_rows, &_option._grid_cols);
+    }
+    // FeatureDetector.cpp:345-444
+    void Detect(Frame* frame, bool overwrite_existing_features = true) {
+        auto& rt = b200::Runtime::Get();
+        const int n_cells = _option._grid_rows * _option._grid_cols;
+        std::vector<uint8_t> occ;
+        if (overwrite_existing_features) {
+            frame->CleanAllFeatures();
+        } else {  // SetExistingFeatures (:446-464)
+            occ.assign(n_cells, 0);
+            for (Feature* fea : frame->_features) {
+                const int gx = (int)(fea->_pixel[0] / _option._cell_size), gy = (int)(fea->_pixel[1] / _option._cell_size);
+                const size_t k = (size_t)gy * _option._grid_cols + gx;
+                if (k < occ.size()) occ[k] = 1;
+            }
+        }
+        std::vector<int32_t> off(2), cell(n_cells);
+        std::vector<float> x(n_cells), y(n_cells), score(n_cells), angle(n_cells);
+        std::vector<uint8_t> level(n_cells), desc((size_t)n_cells * 32);
+        ygzb_keypoints kp{off.data(), x.data(), y.data(), level.data(), score.data(), angle.data(), desc.data(), cell.data(), n_cells};
+        const int32_t slot = b200::SlotOf(frame);
+        rt.Check(ygzb_detect(rt.frames(), &slot, 1, occ.empty() ? nullptr : occ.data(), &kp), "ygzb_detect");
+        for (int i = 0; i < off[1]; ++i) {
+            Feature* fea = new Feature(Vector2d(x[i], y[i]), level[i], score[i]);
+            fea->_frame = frame;
+            fea->_angle = angle[i];
+            std::memcpy(fea->_desc, &desc[(size_t)i * 32], 32);
+            frame->_features.push_back(fea);
+        }
+    }
+    // FeatureDetector.cpp:580-588
+    void ComputeAngleAndDescriptor(Frame* frame) {
+        auto& rt = b200::Runtime::Get();
+        const int n = (int)frame->_features.size();
+        if (!n) return;
+        std::vector<double> x(n), y(n);
+        std::vector<uint8_t> level(n), desc((size_t)n * 32);
+        std::vector<float> angle(n);
+        for (int i = 0; i < n; ++i) {
+            x[i] = frame->_features[i]->_pixel[0];
+            y[i] = frame->_features[i]->_pixel[1];
+            level[i] = (uint8_t)frame->_features[i]->_level;
+        }
+        const int32_t slot = b200::SlotOf(frame), off[2] = {0, n};
+        rt.Check(ygzb_describe(rt.frames(), &slot, 1, off, x.data(), y.data(), level.data(), angle.data(), desc.data()), "ygzb_describe");
+        for (int i = 0; i < n; ++i) {
+            frame->_features[i]->_angle = angle[i];
+            std::memcpy(frame->_features[i]->_desc, &desc[(size_t)i * 32], 32);
+        }
+    }
+};
+
+namespace cvutils {
+// include/ygz/Algorithm/CVUtils.h:163-169 -- cur_img is identified by (frame, level) instead of a cv::Mat
+inline bool Align2D(Frame* cur, int level, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter, Vector2d& cur_px_estimate) {
+    auto& rt = b200::Runtime::Get();
+    const int32_t slot = b200::SlotOf(cur);
+    const uint8_t lv = (uint8_t)level;
+    double uv[2] = {cur_px_estimate[0], cur_px_estimate[1]};
+    uint8_t ok = 0;
+    rt.Check(ygzb_align2d(rt.frames(), 1, &slot, &lv, ref_patch_with_border, ref_patch, n_iter, uv, &ok), "ygzb_align2d");
+    cur_px_estimate = Vector2d(uv[0], uv[1]);
+    return ok != 0;
+}
+}  // namespace cvutils
+
+class SparseImgAlign {  // include/ygz/Algorithm/SparseImageAlign.h:12-58
+  public:
+    enum Method { GaussNewton, LevenbergMarquardt };
+    SparseImgAlign(int max_level, int min_level, int n_iter, Method = GaussNewton, bool = false, bool = false)
+        : max_level_(max_level), min_level_(min_level), n_iter_(n_iter) {}
+    size_t run(Frame* ref_frame, Frame* cur_frame) {
+        auto& rt = b200::Runtime::Get();
+        const int n = (int)ref_frame->_features.size();
+        if (!n) return 0;
+        std::vector<double> px(2 * (size_t)n), depth(n);
+        std::vector<uint8_t> has(n);
+        for (int i = 0; i < n; ++i) {
+            const Feature* f = ref_frame->_features[i];
+            px[2 * i] = f->_pixel[0];
+            px[2 * i + 1] = f->_pixel[1];
+            depth[i] = f->_depth;
+            has[i] = f->_mappoint != nullptr;
+        }
+        double Tr[12], Tc[12];
+        b200::PoseTo3x4(ref_frame->_TCW, Tr);
+        b200::PoseTo3x4(cur_frame->_TCW, Tc);
+        const int32_t rs = b200::SlotOf(ref_frame), cs = b200::SlotOf(cur_frame), off[2] = {0, n};
+        int32_t n_meas = 0;
+        rt.Check(ygzb_sparse_align(rt.frames(), 1, &rs, &cs, off, px.data(), depth.data(), has.data(), Tr, Tc, max_level_, min_level_, n_iter_,
+                                   0.000001, &n_meas, nullptr), "ygzb_sparse_align");
+        cur_frame->_TCW = SE3::from3x4(Tc);
+        return (size_t)n_meas;
+    }
+  private:
+    int max_level_, min_level_, n_iter_;
+};
+
+class Matcher {  // include/ygz/Algorithm/Matcher.h
+  public:
+    struct Options {
+        float initMatchRatio = 3.0;
+        int init_low = 30, init_high = 100;  // matcher.init_low / init_high (config/default.yaml:59-60)
+        double _max_alignment_motion = 0.2;
+    } _options;
+    Matcher() : _align(new SparseImgAlign(2, 0, 30, SparseImgAlign::GaussNewton, false, false)) {}
+    // Matcher.cpp:30-43
+    static int DescriptorDistance(const uint8_t* a, const uint8_t* b) {
+        auto& rt = b200::Runtime::Get();
+        const int32_t z = 0;
+        int32_t d = 0;
+        rt.Check(ygzb_hamming_pairs(rt.ctx(), a, 1, b, 1, &z, &z, 1, &d), "ygzb_hamming_pairs");
+        return d;
+    }
+    // Matcher.cpp:45-84
+    int CheckFrameDescriptors(Frame* frame1, Frame* frame2, std::list<std::pair<int, int>>& matches) {
+        auto& rt = b200::Runtime::Get();
+        const int n = (int)matches.size(), n1 = (int)frame1->_features.size(), n2 = (int)frame2->_features.size();
+        if (!n) return 0;
+        std::vector<uint8_t> A((size_t)n1 * 32), B((size_t)n2 * 32);
+        for (int i = 0; i < n1; ++i) std::memcpy(&A[(size_t)i * 32], frame1->_features[i]->_desc, 32);
+        for (int i = 0; i < n2; ++i) std::memcpy(&B[(size_t)i * 32], frame2->_features[i]->_desc, 32);
+        std::vector<int32_t> ia, ib, dist(n);
+        for (auto& m : matches) { ia.push_back(m.first); ib.push_back(m.second); }
+        rt.Check(ygzb_hamming_pairs(rt.ctx(), A.data(), n1, B.data(), n2, ia.data(), ib.data(), n, dist.data()), "ygzb_hamming_pairs");
+        int best = dist[0];
+        for (int d : dist) best = d < best ? d : best;
+        best = best > _options.init_low ? best : _options.init_low;
+        best = best < _options.init_high ? best : _options.init_high;
+        int cnt_good = 0, i = 0;
+        for (auto it = matches.begin(); it != matches.end(); ++i) {
+            if (dist[i] < _options.initMatchRatio * best) { ++cnt_good; ++it; }
+            else it = matches.erase(it);
+        }
+        return cnt_good;
+    }
+    // brute-force cross-checked matching of two frames (cv::BFMatcher in test/test_orb_match.cpp:87-92)
+    static void BruteForceMatch(Frame* f1, Frame* f2, std::vector<int>& train_idx, std::vector<int>& dist, bool cross_check = true) {
+        auto& rt = b200::Runtime::Get();
+        const int n1 = (int)f1->_features.size(), n2 = (int)f2->_features.size();
+        std::vector<uint8_t> A((size_t)n1 * 32), B((size_t)n2 * 32);
+        for (int i = 0; i < n1; ++i) std::memcpy(&A[(size_t)i * 32], f1->_features[i]->_desc, 32);
+        for (int i = 0; i < n2; ++i) std::memcpy(&B[(size_t)i * 32], f2->_features[i]->_desc, 32);
+        train_idx.assign(n1, -1);
+        dist.assign(n1, -1);
+        rt.Check(ygzb_match_bf(rt.ctx(), A.data(), n1, B.data(), n2, cross_check, train_idx.data(), dist.data()), "ygzb_match_bf");
+    }
+    // Matcher.cpp:385-417 (Feature* overload) and :356-383 (MapPoint* overload)
+    bool FindDirectProjection(Frame* ref, Frame* curr, Feature* fea_ref, Vector2d& px_curr, int& search_level) {
+        if (fea_ref->_depth < 0) return false;
+        return Project(ref, curr, fea_ref->_pixel, fea_ref->_depth, fea_ref->_level, px_curr, search_level);
+    }
+    bool FindDirectProjection(Frame* ref, Frame* curr, MapPoint* mp, Vector2d& px_curr, int& search_level) {
+        Feature* fea = mp->_obs[ref->_keyframe_id];
+        const double depth = Frame::_camera->World2Camera(mp->_pos_world, ref->_TCW)[2];
+        return Project(ref, curr, fea->_pixel, depth, fea->_level, px_curr, search_level);
+    }
+    // Matcher.cpp:468-492
+    bool SparseImageAlignment(Frame* ref, Frame* current) {
+        current->_TCW = ref->_TCW;
+        _align->run(ref, current);
+        _TCR_esti = current->_TCW * ref->_TCW.inverse();
+        double lg[6], n2 = 0;
+        _TCR_esti.log(lg);
+        for (double v : lg) n2 += v * v;
+        if (std::sqrt(n2) > _options._max_alignment_motion) {
+            _TCR_esti = SE3();
+            current->_TCW = ref->_TCW;
+            return false;
+        }
+        return true;
+    }
+    void SetTCR(const SE3& TCR) { _TCR_esti = TCR; }
+    SE3 GetTCR() const { return _TCR_esti; }
+  private:
+    bool Project(Frame* ref, Frame* curr, const Vector2d& px_ref, double depth, int level, Vector2d& px_curr, int& search_level) {
+        auto& rt = b200::Runtime::Get();
+        double poses[24];
+        b200::PoseTo3x4(ref->_TCW, poses);
+        b200::PoseTo3x4(curr->_TCW, poses + 12);
+        const int32_t rs = b200::SlotOf(ref), cs = b200::SlotOf(curr), rp = 0, cp = 1;
+        const double rpx[2] = {px_ref[0], px_ref[1]};
+        double cpx[2] = {px_curr[0], px_curr[1]};
+        const uint8_t lv = (uint8_t)level;
+        uint8_t sl = 0, ok = 0;
+        rt.Check(ygzb_project_align(rt.frames(), 1, &rs, &cs, 2, poses, &rp, &cp, rpx, &depth, &lv, cpx, &sl, &ok), "ygzb_project_align");
+        px_curr = Vector2d(cpx[0], cpx[1]);
+        search_level = sl;
+        return ok != 0;
+    }
+    std::unique_ptr<SparseImgAlign> _align;
+    SE3 _TCR_esti;
+};
+
+namespace ba {  // include/ygz/Algorithm/BA.h:23-66
+// BA.cpp:188-264
+inline void OptimizeCurrentPoseOnly(Frame* current) {
+    auto& rt = b200::Runtime::Get();
+    const int n = (int)current->_features.size();
+    if (!n) return;
+    std::vector<double> pw(3 * (size_t)n), px(2 * (size_t)n), depth(n);
+    std::vector<uint8_t> inl(n);
+    for (int i = 0; i < n; ++i) {
+        const Feature* f = current->_features[i];
+        for (int k = 0; k < 3; ++k) pw[3 * i + k] = f->_mappoint->_pos_world[k];
+        px[2 * i] = f->_pixel[0];
+        px[2 * i + 1] = f->_pixel[1];
+    }
+    double T[12];
+    b200::PoseTo3x4(current->_TCW, T);
+    const int32_t off[2] = {0, n};
+    int32_t cnt = 0;
+    rt.Check(ygzb_pose_only(rt.ctx(), 1, off, pw.data(), px.data(), T, inl.data(), depth.data(), &cnt), "ygzb_pose_only");
+    current->_TCW = SE3::from3x4(T);
+    for (int i = 0; i < n; ++i) {
+        Feature* f = current->_features[i];
+        f->_bad = !inl[i];
+        if (inl[i]) f->_depth = depth[i];
+        if (!f->_bad && f->_mappoint && !f->_mappoint->_bad) f->_mappoint->_cnt_found++;  // BA.cpp:255-261
+    }
+}
+
+// BA.cpp:386-543.  `keyframe_of` resolves keyframe ids (Memory::GetKeyFrame in the reference).
+inline void LocalBAG2O(std::set<Frame*>& local_keyframes, std::set<MapPoint*>& local_map_points,
+                       const std::map<unsigned long, Frame*>& keyframe_of) {
+    auto& rt = b200::Runtime::Get();
+    std::vector<Frame*> kfs;
+    std::map<Frame*, int> index;
+    std::vector<uint8_t> fixed;
+    auto add_kf = [&](Frame* f, bool fix) {
+        auto it = index.find(f);
+        if (it == index.end()) {
+            index[f] = (int)kfs.size();
+            kfs.push_back(f);
+            fixed.push_back(fix || f->_keyframe_id == 0);
+        } else if (fix) {
+            fixed[it->second] = 1;
+        }
+        return index[f];
+    };
+    for (Frame* f : local_keyframes) add_kf(f, false);
+    std::vector<MapPoint*> pts;
+    std::vector<int32_t> kf_idx, pt_idx;
+    std::vector<double> obs;
+    std::vector<Feature*> feats;
+    for (MapPoint* mp : local_map_points) {
+        if (mp->_bad) continue;
+        const int j = (int)pts.size();
+        pts.push_back(mp);
+        for (auto& o : mp->_obs) {
+            if (o.second->_bad) continue;
+            Frame* f = keyframe_of.at(o.first);
+            const bool local = local_keyframes.count(f) != 0;
+            kf_idx.push_back(add_kf(f, !local));  // observers outside the local set are added / set fixed (:458-492)
+            pt_idx.push_back(j);
+            obs.push_back(o.second->_pixel[0]);
+            obs.push_back(o.second->_pixel[1]);
+            feats.push_back(o.second);
+        }
+    }
+    const int nk = (int)kfs.size(), np = (int)pts.size(), no = (int)kf_idx.size();
+    std::vector<double> poses(6 * (size_t)nk), X(3 * (size_t)np);
+    for (int k = 0; k < nk; ++k) {  // esti = [log.tail<3>; log.head<3>]
+        double lg[6];
+        kfs[k]->_TCW.log(lg);
+        for (int c = 0; c < 3; ++c) { poses[6 * k + c] = lg[3 + c]; poses[6 * k + 3 + c] = lg[c]; }
+    }
+    for (int j = 0; j < np; ++j)
+        for (int c = 0; c < 3; ++c) X[3 * j + c] = pts[j]->_pos_world[c];
+    ygzb_ba_params prm;
+    ygzb_default_ba_params(&prm);
+    std::vector<uint8_t> outl(no ? no : 1);
+    const int32_t ko[2] = {0, nk}, po[2] = {0, np}, oo[2] = {0, no};
+    rt.Check(ygzb_local_ba(rt.ctx(), 1, ko, po, oo, poses.data(), fixed.data(), X.data(), kf_idx.data(), pt_idx.data(), obs.data(), &prm,
+                           outl.data(), nullptr), "ygzb_local_ba");
+    for (int o = 0; o < no; ++o)
+        if (outl[o]) feats[o]->_bad = true;
+    for (Frame* f : local_keyframes) {
+        const int k = index[f];
+        const double v[6] = {poses[6 * k + 3], poses[6 * k + 4], poses[6 * k + 5], poses[6 * k], poses[6 * k + 1], poses[6 * k + 2]};
+        f->_TCW = SE3::exp(v);
+    }
+    for (int j = 0; j < np; ++j) pts[j]->_pos_world = Vector3d(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
+}
+}  // namespace ba
+
+// facade for the vocabulary of the north star ("ygz::Optimizer"); the reference's live API is namespace ygz::ba
+class Optimizer {
+  public:
+    static void PoseOnly(Frame* current) { ba::OptimizeCurrentPoseOnly(current); }
+    static void LocalBA(std::set<Frame*>& kfs, std::set<MapPoint*>& mps, const std::map<unsigned long, Frame*>& keyframe_of) {
+        ba::LocalBAG2O(kfs, mps, keyframe_of);
+    }
+};
+
+}  // namespace ygz
