@@ -202,6 +202,24 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
 int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const double* pt_world, const double* px,
                    double* T_cw, uint8_t* inlier, double* depth, int32_t* n_inlier);
 
+/* ---- Tracker ------------------------------------------------------------------------------------
+ * replaces Tracker::TrackKLT (src/Algorithm/Tracker.cpp:65-113; include/ygz/Algorithm/Tracker.h:31-58), i.e.
+ * cv::calcOpticalFlowPyrLK(ref.pyr[0], cur.pyr[0], ..., Size(21,21), 4, (COUNT+EPS, 30, 0.001),
+ * OPTFLOW_USE_INITIAL_FLOW).  Pair p tracks points [offsets[p], offsets[p+1]) from frame ref_slot[p] to
+ * cur_slot[p]; ref_xy / cur_xy are full-resolution pixels (cur_xy = initial flow in, tracked position out),
+ * status / err as OpenCV returns them.  The status filtering and Frame::InFrame(pt, 20) test of
+ * Tracker.cpp:104-112 and MeanDisparity (:115-127) stay host bookkeeping in the shim.            */
+typedef struct {
+    int win;        /* Tracker::Option::klt_win_size = 21 (only 21 is supported) */
+    int max_level;  /* 4 (Tracker.cpp:97)                                       */
+    int max_iter;   /* klt_max_iter = 30                                        */
+    double eps;     /* klt_eps = 0.001                                          */
+    double min_eig; /* OpenCV default minEigThreshold 1e-4                      */
+} ygzb_klt_params;
+void ygzb_default_klt_params(ygzb_klt_params* p);
+int ygzb_klt(ygzb_frames* f, int n_pairs, const int32_t* ref_slot, const int32_t* cur_slot, const int32_t* offsets,
+             const float* ref_xy, float* cur_xy, uint8_t* status, float* err, const ygzb_klt_params* prm);
+
 #ifdef __cplusplus
 }
 #endif

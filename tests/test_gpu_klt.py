@@ -1,0 +1,39 @@
+"""GPU parity for Tracker::TrackKLT (cv::calcOpticalFlowPyrLK): against the oracle and against cv2 itself."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("levels", [3, 8])
+def test_klt_matches_oracle_and_cv2(levels, ctx3, ctx8, oracle, synth_frames):
+    import cv2
+    ctx = ctx3 if levels == 3 else ctx8   # 3 levels: pyramid levels 3 and 4 are built on the fly for the tracker
+    g1, g2, g3 = (f[0] for f in synth_frames)
+    fr = ctx.frames(3)
+    fr.upload(np.stack([g1, g2, g3]))
+    f = oracle.detect(oracle.build_pyramid(g1, 3))
+    ref = np.stack([f["px"], f["py"]], 1).astype(np.float32)
+    extra = np.array([[2.5, 3.0], [637.0, 10.0], [320.0, 478.5], [-30.0, 50.0], [700.0, 500.0]], np.float32)
+    ref = np.concatenate([ref, extra])
+    n = len(ref)
+    init = (ref + np.float32(1.5)).astype(np.float32)
+    got, gst, gerr = fr.klt([0, 0], [2, 1], [0, n, 2 * n], np.concatenate([ref, ref]), np.concatenate([init, init]))
+    for p, cur in enumerate((g3, g2)):
+        s = slice(p * n, (p + 1) * n)
+        want, wst, werr = oracle.klt(g1, cur, ref, init)
+        wst = wst.astype(bool)
+        assert (wst != gst[s]).mean() < 0.003
+        both = wst & gst[s]
+        d = np.abs(got[s][both] - want[both]).max(1)
+        assert np.percentile(d, 99) < 0.01 and np.median(d) < 1e-3     # integer window sums vs f32 accumulation
+        assert np.abs(gerr[s][both] - werr[both]).max() < 0.05
+        cvp, cvs, _ = cv2.calcOpticalFlowPyrLK(g1, cur, ref.copy(), init.copy(), winSize=(21, 21), maxLevel=4,
+                                               criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.001),
+                                               flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        cvs = cvs.reshape(-1).astype(bool)
+        assert (cvs != gst[s]).mean() < 0.005
+        both = cvs & gst[s]
+        assert np.percentile(np.abs(got[s][both] - cvp.reshape(-1, 2)[both]).max(1), 99) < 0.01
+        assert both.sum() > 0.9 * n
+    fr.close()

@@ -39,6 +39,7 @@ EXPORTS = [
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
     "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d",
     "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_pose_only",
+    "ygzb_default_klt_params", "ygzb_klt",
 ]
 
 
@@ -459,3 +460,26 @@ def _pose_only(self, offsets, pt_world, px, T_cw):
 
 Context.local_ba = _local_ba
 Context.pose_only = _pose_only
+
+
+# ---- KLT (method attached to Frames) -------------------------------------------------------------------
+class KLTParams(C.Structure):
+    _fields_ = [("win", C.c_int), ("max_level", C.c_int), ("max_iter", C.c_int), ("eps", C.c_double), ("min_eig", C.c_double)]
+
+
+def _klt(self, ref_slot, cur_slot, offsets, ref_xy, cur_xy):
+    ref_slot = np.ascontiguousarray(ref_slot, np.int32)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    n = int(offsets[-1])
+    out = np.ascontiguousarray(cur_xy, np.float32).reshape(n, 2).copy()
+    status = np.zeros(n, np.uint8)
+    err = np.zeros(n, np.float32)
+    prm = KLTParams()
+    self.lib.ygzb_default_klt_params(C.byref(prm))
+    self.ctx.check(self.lib.ygzb_klt(self.h, len(ref_slot), _p(ref_slot), _p(np.ascontiguousarray(cur_slot, np.int32)), _p(offsets),
+                                     _p(np.ascontiguousarray(ref_xy, np.float32)), _p(out), _p(status), _p(err), C.byref(prm)),
+                   "ygzb_klt")
+    return out, status.astype(bool), err
+
+
+Frames.klt = _klt

@@ -120,6 +120,8 @@ struct ProfScope {
 
 // ---- stage launchers (one .cu each) -----------------------------------------------------------
 int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr /* or null */);
+int launch_pyrdown_ptrs(ygzb_ctx* ctx, const uint8_t* const* d_src_ptr, uint8_t* const* d_dst_ptr, int sw, int sh, int spitch,
+                        int dw, int dh, int dpitch, int count);
 int launch_detect(ygzb_frames* f, int n, bool have_occupied);
 int launch_describe_store(ygzb_frames* f, int n);
 int launch_describe_list(ygzb_frames* f, int n, const int32_t* d_slot_of, int total, const double* d_x, const double* d_y,

@@ -28,16 +28,13 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
-                                                      LevelGeom src, LevelGeom dst) {
+__device__ __forceinline__ void pyrdown_tile(const uint8_t* __restrict__ sp, uint8_t* __restrict__ dp, const LevelGeom& src,
+                                             const LevelGeom& dst) {
     __shared__ __align__(16) uint8_t s_src[kSrcRows][kSrcWords * 4];
     __shared__ uint16_t s_h[kSrcRows][kDW];
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kDW, y0 = blockIdx.y * kDH;
-    uint8_t* slot = pyr + (size_t)(first_slot + blockIdx.z) * slot_stride;
-    const uint8_t* __restrict__ sp = slot + src.off;
-    uint8_t* __restrict__ dp = slot + dst.off;
 
     // stage the source window (reflect-101 at the image border)
     const int xs = 2 * x0 - 4, ys = 2 * y0 - 2;
@@ -85,6 +82,19 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr,
     }
 }
 
+// one level of `count` consecutive slots
+__global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
+                                                      LevelGeom src, LevelGeom dst) {
+    uint8_t* slot = pyr + (size_t)(first_slot + blockIdx.z) * slot_stride;
+    pyrdown_tile(slot + src.off, slot + dst.off, src, dst);
+}
+
+// same, with explicit per-image source / destination pointers (levels beyond the slot pyramid, e.g. for KLT)
+__global__ void __launch_bounds__(256) pyrdown_ptr_kernel(const uint8_t* const* __restrict__ src_ptr,
+                                                          uint8_t* const* __restrict__ dst_ptr, LevelGeom src, LevelGeom dst) {
+    pyrdown_tile(src_ptr[blockIdx.z], dst_ptr[blockIdx.z], src, dst);
+}
+
 // cv::cvtColor(BGR2GRAY), 4 pixels per thread
 __global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t* __restrict__ bgr, size_t bgr_frame_stride,
                                                        uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
@@ -121,6 +131,17 @@ int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr) {
         pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g.lv[L - 1], g.lv[L]);
         YGZB_LAUNCHED(ctx);
     }
+    return YGZB_OK;
+}
+
+int launch_pyrdown_ptrs(ygzb_ctx* ctx, const uint8_t* const* d_src_ptr, uint8_t* const* d_dst_ptr, int sw, int sh, int spitch,
+                        int dw, int dh, int dpitch, int count) {
+    if (count <= 0) return YGZB_OK;
+    const LevelGeom src{sw, sh, spitch, 0}, dst{dw, dh, dpitch, 0};
+    dim3 grid((dw + kDW - 1) / kDW, (dh + kDH - 1) / kDH, count);
+    ProfScope ps(ctx, kStagePyrDown);
+    pyrdown_ptr_kernel<<<grid, 256, 0, ctx->stream>>>(d_src_ptr, d_dst_ptr, src, dst);
+    YGZB_LAUNCHED(ctx);
     return YGZB_OK;
 }
 
