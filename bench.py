@@ -132,20 +132,16 @@ def measured_peaks() -> tuple:
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_step(ora, frames: np.ndarray, lo: int, hi: int, out_counts=None) -> int:
-    """Reference CPU path for frames [lo, hi): pyramid + Detect on each, BF match of k against k+1."""
-    n_feat = 0
-    prev = None
-    for k in range(lo, hi + 1):  # one extra so that every frame in [lo,hi) has its successor
-        g = frames[k % len(frames)]
-        pyr = ora.build_pyramid(g, LEVELS)
-        f = ora.detect(pyr, n_levels=LEVELS)
-        if prev is not None:
-            ora.match_bf(prev["desc"], f["desc"], True)
-        if k < hi:
-            n_feat += f["n"]
-        prev = f
-    return n_feat
+def cpu_run(ora, frames: np.ndarray, count: int, threads: int):
+    """Reference CPU path (pyramid + Detect + cross-checked BF match of frame k against k+1) for `count` frames on
+    `threads` C++ threads (oracle/bench_driver.cpp; no Python inside the timed region).  Returns (seconds, features)."""
+    import ctypes as C
+    fn = ora.lib.ora_bench_extract_match
+    fn.restype = C.c_double
+    nf = C.c_long(0)
+    frames = np.ascontiguousarray(frames)
+    dt = fn(frames.ctypes.data_as(C.c_void_p), len(frames), W, H, LEVELS, int(count), int(threads), C.byref(nf))
+    return dt, nf.value
 
 
 def run_reference(args, rank: int, world: int) -> None:
@@ -155,28 +151,23 @@ def run_reference(args, rank: int, world: int) -> None:
     from oracle.pyoracle import Oracle
     ora = Oracle(native=True)
     threads = os.cpu_count() or 1
-    per_thread = 4                      # frames per thread per step -> bounded sample
+    per_thread = 8                      # frames per thread per step -> bounded sample
     n = threads * per_thread
-    frames = make_frames(min(n + 1, 512), 0)
-
-    def step():
-        with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(lambda t: cpu_step(ora, frames, t * per_thread, (t + 1) * per_thread), range(threads)))
-
+    frames = make_frames(min(n, 512), 0)
     for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
+        cpu_run(ora, frames, n, threads)
+    dt = 0.0
     for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
+        dt += cpu_run(ora, frames, n, threads)[0]
     fps = n * args.steps / dt
     line = {
         "impl": "reference", "metric": "tracked frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(n, "host threads, frame-parallel"),
+        "config": workload_config(n, "C++ host threads, frame-parallel (oracle/bench_driver.cpp)"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} frames/step ({per_thread} per thread) x {args.steps} steps, oracle -O3 AVX2/FMA build"},
+                         "sample": f"{n} frames/step ({per_thread} per thread) x {args.steps} steps; CPU restatement of the reference "
+                                   f"path (the reference cannot be built here), -O3 AVX2/FMA, {threads} std::threads"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -414,7 +405,13 @@ def main() -> None:
     ctx.profile(False)
     n_prof_steps = max(3, args.steps // 2)
 
+    per_rank = None
     if world > 1:
+        # per-rank result records gathered over NCCL (the only collective of the job: results, not pixels)
+        from ygz_slam_b200 import dist as ydist
+        rec = ydist.make_record(rank, B * args.steps, nfeat, 0, [0, 0, 0, 1, 0, 0, 0], ms_resident)
+        table, _, _ = ydist.gather_records([rec], world, device=torch.device("cuda", local_rank))
+        per_rank = [{"rank": int(r[0]), "frames": int(r[1]), "device_ms": float(r[11])} for r in table]
         t = torch.tensor([ms_resident, ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_resident, ms_e2e = t.tolist()
@@ -460,10 +457,8 @@ def main() -> None:
             from oracle.pyoracle import Oracle
             ora = Oracle(native=True)
             ns = args.cpu_sample
-            cpu_step(ora, frames, 0, 2)
-            t0 = time.perf_counter()
-            cpu_step(ora, frames, 0, ns)
-            dt = time.perf_counter() - t0
+            cpu_run(ora, frames, 2, 1)
+            dt, _ = cpu_run(ora, frames, ns, 1)
             cpu = {"value": ns / dt, "unit": "frames/s", "cores": 1, "kind": "port",
                    "sample": f"{ns} frames of the same batch (pyramid+Detect+cross-checked BF match), oracle -O3 AVX2/FMA "
                              f"build, single thread like the reference's own code; host has {os.cpu_count()} logical CPUs"}
@@ -491,6 +486,7 @@ def main() -> None:
             "cpu_baseline": cpu,
             "keypoints_per_frame": kpf,
             "secondary_workloads": extra,
+            "per_rank": per_rank,
         }
         print(json.dumps(line))
     for c_, f_, _ in workers[1:]:
