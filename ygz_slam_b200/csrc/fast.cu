@@ -196,13 +196,56 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     }
     __syncthreads();
 
-    // pass A1: cheap opposite-pair test on tile + 1 px ring; survivors (a few %) are compacted so that the
-    // full 16-pixel segment test (pass A2) runs on dense warps
-    for (int idx = tid; idx < kScH * kScW; idx += 256) {
-        const int ry = idx / kScW, rx = idx - ry * kScW;
-        const int x = x0 - 1 + rx, y = y0 - 1 + ry;
-        if (x < 3 || x >= lv.w - 3 || y < 3 || y >= lv.h - 3) continue;
-        if (fast_quick_test<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_quick[atomicAdd(&s_nquick, 1)] = (uint16_t)idx;
+    // pass A0/A1: cheap necessary condition on tile + 1 px ring; survivors (a few %) are compacted so that the
+    // exact segment test (pass A2) runs on dense warps.
+    // Measured (profiles/r1_fast_cells_v3.txt): the sign-blind SWAR prefilter passes ~30 % more pixels than the exact
+    // pair test and its per-pixel append loop eats the saving (1.67 ms vs 1.57 ms per 512 frames), so the exact
+    // per-pixel test below stays the default until the append is warp-aggregated.
+    constexpr bool kUseSwarPrefilter = false;
+    if (kUseSwarPrefilter && g.threshold <= 126) {
+        // SIMD-within-a-register prefilter, 4 horizontally adjacent pixels per thread: for each of the four opposite
+        // ring pairs at least one pixel must differ from the centre by more than the threshold (|v - p| > b, sign
+        // ignored: a superset of the exact pair test).  VABSDIFF4 gives the four byte differences in one instruction,
+        // ((x & 0x7f7f7f7f) + (127-b)*0x01010101 | x) & 0x80808080 flags the bytes > b without inter-byte carries.
+        const uint32_t kadd = 0x01010101u * (uint32_t)(127 - g.threshold);
+        constexpr int kGroups = (kScW + 3) / 4;  // 21 groups of 4 pixels per region row
+        for (int gi = tid; gi < kScH * kGroups; gi += 256) {
+            const int ry = gi / kGroups, rx0 = (gi - ry * kGroups) * 4;
+            // word-aligned base of the centre row: pixel rx0 sits at byte offset rx0 + 7 = (rx0 + 4) + 3
+            const uint32_t* rowc = reinterpret_cast<const uint32_t*>(s_img + (ry + 4) * kSmW + rx0 + 4);
+            constexpr int W = kSmW / 4;  // words per smem row
+            const uint32_t c0 = rowc[0], c1 = rowc[1], c2 = rowc[2];
+            const uint32_t ctr = __funnelshift_r(c0, c1, 24);
+#define FLAG(v) ((((__vabsdiffu4((v), ctr) & 0x7f7f7f7fu) + kadd) | __vabsdiffu4((v), ctr)) & 0x80808080u)
+            uint32_t m = FLAG(c0) | FLAG(__funnelshift_r(c1, c2, 16));                               // ring 12 (-3,0) | 4 (+3,0)
+            if (m) {
+                const uint32_t* ru = rowc - 3 * W;
+                const uint32_t* rd = rowc + 3 * W;
+                m &= FLAG(__funnelshift_r(ru[0], ru[1], 24)) | FLAG(__funnelshift_r(rd[0], rd[1], 24));  // ring 8 | 0
+            }
+            if (m) {
+                const uint32_t* ru = rowc - 2 * W;
+                const uint32_t* rd = rowc + 2 * W;
+                const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
+                m &= FLAG(__funnelshift_r(u0, u1, 8)) | FLAG(__funnelshift_r(d1, d2, 8));   // ring 10 (-2,-2) | 2 (+2,+2)
+                m &= FLAG(__funnelshift_r(u1, u2, 8)) | FLAG(__funnelshift_r(d0, d1, 8));   // ring 6 (+2,-2) | 14 (-2,+2)
+            }
+#undef FLAG
+            while (m) {
+                const int j = (__ffs(m) - 1) >> 3;  // byte index = pixel within the group
+                m &= m - 1;
+                const int rx = rx0 + j;
+                const int x = x0 - 1 + rx, y = y0 - 1 + ry;
+                if (rx < kScW && x >= 3 && x < lv.w - 3 && y >= 3 && y < lv.h - 3) s_quick[atomicAdd(&s_nquick, 1)] = (uint16_t)(ry * kScW + rx);
+            }
+        }
+    } else {
+        for (int idx = tid; idx < kScH * kScW; idx += 256) {
+            const int ry = idx / kScW, rx = idx - ry * kScW;
+            const int x = x0 - 1 + rx, y = y0 - 1 + ry;
+            if (x < 3 || x >= lv.w - 3 || y < 3 || y >= lv.h - 3) continue;
+            if (fast_quick_test<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_quick[atomicAdd(&s_nquick, 1)] = (uint16_t)idx;
+        }
     }
     // grid-cell lookup tables of this tile (local cell column / row of every tile pixel)
     if (selectable) {
@@ -215,7 +258,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     for (int i = tid; i < n_quick; i += 256) {
         const int idx = s_quick[i];
         const int ry = idx / kScW, rx = idx - ry * kScW;
-        if (fast_full_test<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
+        if (fast_is_corner<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
     }
     __syncthreads();
     const int n_corner = s_n;
