@@ -247,7 +247,7 @@ struct SparseArgs {
     uint8_t* visible;           // [total]
 };
 
-constexpr int kSparseThreads = 256;
+constexpr int kSparseThreads = 512;
 constexpr int kNormalTerms = 21 + 6 + 1;  // upper triangle of H, Jres, chi2
 
 __device__ bool ldlt_solve6(const double H[6][6], const double b[6], double x[6]) {
@@ -386,10 +386,10 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
 #pragma unroll
                         for (int r = 0; r < 6; ++r) {
 #pragma unroll
-                            for (int c = r; c < 6; ++c) acc[t++] += J[r] * J[c];
+                            for (int c = r; c < 6; ++c, ++t) acc[t] = fma(J[r], J[c], acc[t]);   // explicit FMA: the file is built with -fmad=false
                         }
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) acc[21 + k] -= J[k] * res;
+                        for (int k = 0; k < 6; ++k) acc[21 + k] = fma(-J[k], (double)res, acc[21 + k]);
                     }
                 }
             }

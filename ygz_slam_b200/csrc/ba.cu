@@ -25,6 +25,8 @@
 #include <utility>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "se3.cuh"
 
@@ -32,7 +34,7 @@ namespace ygzb {
 
 namespace {
 
-constexpr int kBAThreads = 512;
+constexpr int kBAThreads = 256;
 constexpr int kMaxFreePoses = 16;             // S is at most 96 x 96 doubles = 72 KB of shared memory
 constexpr int kMaxPoses = 64;
 
@@ -134,73 +136,107 @@ __device__ __forceinline__ void make_hpl(const double* __restrict__ rec, double 
         for (int b = 0; b < 3; ++b) Hpl[a][b] = w * (Jp[a] * Jl[b] + Jp[6 + a] * Jl[3 + b]);
 }
 
-__global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a) {
-    extern __shared__ double s_mem[];
-    __shared__ double s_tmp[33];
-    __shared__ double s_R[kMaxPoses][12];      // [R|t] of every pose of the problem, refreshed after each update
-    __shared__ double s_backup[kMaxPoses][6];
-    __shared__ int s_free[kMaxPoses];
-    __shared__ double s_lambda, s_ni, s_rho, s_current_chi;
-    __shared__ int s_accept, s_ok;
+// ---- local BA: one thread-block CLUSTER (kClusterSize CTAs on kClusterSize SMs) per problem ---------------------
+// The observation / landmark / pair-entry loops stride over the whole cluster, the per-pose and per-block-pair sums
+// are warp-reduced and combined with f64 global atomics (RED.ADD.F64) into a small L2-resident workspace, scalar
+// reductions go through per-CTA partials + barrier.cluster, and CTA 0 factorises the reduced system in shared memory.
+// Every CTA keeps its own replica of the poses and of the LM scalars and takes the same (deterministic) decisions.
+constexpr int kClusterSize = 8;
 
-    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = kBAThreads / 32;
+struct ClusterWs {            // per problem, in global memory
+    double red[4][kClusterSize][4];
+    double Hpp[kMaxFreePoses * 36];
+    double bp[kMaxFreePoses * 6];
+    double S[kMaxFreePoses * 6 * kMaxFreePoses * 6];
+    double bs[kMaxFreePoses * 6];
+    double xp[kMaxFreePoses * 6];
+    int ok;
+};
+
+__global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, ClusterWs* __restrict__ ws_all) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double s_mem[];          // CTA 0: S (dimp x dimp) + rhs
+    __shared__ double s_tmp[33];
+    __shared__ double s_R[kMaxPoses][12];
+    __shared__ double s_pose[kMaxPoses][6];    // replica of the pose estimates (g2o order)
+    __shared__ double s_backup[kMaxPoses][6];
+    __shared__ double s_xp[kMaxFreePoses * 6];
+    __shared__ int s_free[kMaxPoses];
+    __shared__ int s_np;
+
+    const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+    const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = kBAThreads, CT = C * T, ct = rank * T + tid;       // cluster-wide thread id
+    const int GW = C * (T / 32), gw = rank * (T / 32) + warp;        // cluster-wide warp id
+    ClusterWs& ws = ws_all[prob];
     const int k0 = a.kf_off[prob], n_kf = a.kf_off[prob + 1] - k0;
     const int p0 = a.pt_off[prob], n_pt = a.pt_off[prob + 1] - p0;
     const int o0 = a.obs_off[prob], n_obs = a.obs_off[prob + 1] - o0;
     if (tid == 0) {
         int nf = 0;
         for (int k = 0; k < n_kf; ++k) s_free[k] = a.fixed[k0 + k] ? -1 : nf++;
-        s_ok = nf;
+        s_np = nf;
     }
+    if (tid < n_kf)
+        for (int c = 0; c < 6; ++c) s_pose[tid][c] = a.poses[6 * (size_t)(k0 + tid) + c];
     __syncthreads();
-    const int np = s_ok, dimp = 6 * np;
-    double* s_S = s_mem;                         // dimp x dimp
-    double* s_Hpp = s_S + dimp * dimp;           // np x 36
-    double* s_bp = s_Hpp + np * 36;              // dimp
-    double* s_bs = s_bp + dimp;                  // dimp (rhs, then solution xp)
+    const int np = s_np, dimp = 6 * np;
+    double* s_S = s_mem;
+    double* s_bs = s_S + dimp * dimp;
     const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
     const double dsqr = a.huber_delta * a.huber_delta;
     const int32_t* pair_start = a.pair_start + a.pair_off[prob];
     const int n_pairs = np * (np + 1) / 2;
+    int red_slot = 0;
 
     auto refresh_poses = [&]() {
-        if (tid < n_kf) {
-            const SE3d T = pose_from_g2o(a.poses + 6 * (size_t)(k0 + tid));
-            se3_to_mat(T, s_R[tid]);
-        }
+        if (tid < n_kf) se3_to_mat(pose_from_g2o(s_pose[tid]), s_R[tid]);
         __syncthreads();
     };
-    // robust chi2 of the current estimate (activeRobustChi2)
-    auto robust_chi2 = [&]() -> double {
-        double acc = 0;
-        for (int o = tid; o < n_obs; o += kBAThreads) {
-            const double* T = s_R[a.kf_idx[o0 + o]];
-            const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
-            const double x = T[0] * X[0] + T[1] * X[1] + T[2] * X[2] + T[3];
-            const double y = T[4] * X[0] + T[5] * X[1] + T[6] * X[2] + T[7];
-            const double z = T[8] * X[0] + T[9] * X[1] + T[10] * X[2] + T[11];
-            const double e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx), e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
-            const double e2 = e0 * e0 + e1 * e1;
-            acc += (a.huber_delta > 0 && e2 > dsqr) ? 2 * sqrt(e2) * a.huber_delta - dsqr : e2;
+    // cluster-wide sum of up to 2 values (identical result in every thread of every CTA); contains a cluster barrier
+    auto cluster_sum2 = [&](double v0, double v1, double* out0, double* out1) {
+        v0 = block_sum(v0, s_tmp);
+        v1 = block_sum(v1, s_tmp);
+        const int slot = red_slot;
+        red_slot = (red_slot + 1) & 3;
+        if (tid == 0) {
+            ws.red[slot][rank][0] = v0;
+            ws.red[slot][rank][1] = v1;
         }
-        return block_sum(acc, s_tmp);
+        cluster.sync();
+        double s0 = 0, s1 = 0;
+        for (int r = 0; r < C; ++r) {
+            s0 += __ldcg(&ws.red[slot][r][0]);
+            s1 += __ldcg(&ws.red[slot][r][1]);
+        }
+        *out0 = s0;
+        *out1 = s1;
+    };
+    auto reproject = [&](int o, double* e0, double* e1, double* px, double* py, double* pz) {
+        const double* Tm = s_R[a.kf_idx[o0 + o]];
+        const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
+        const double X0 = __ldcg(X), X1 = __ldcg(X + 1), X2 = __ldcg(X + 2);
+        const double x = Tm[0] * X0 + Tm[1] * X1 + Tm[2] * X2 + Tm[3];
+        const double y = Tm[4] * X0 + Tm[5] * X1 + Tm[6] * X2 + Tm[7];
+        const double z = Tm[8] * X0 + Tm[9] * X1 + Tm[10] * X2 + Tm[11];
+        *e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx);
+        *e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
+        *px = x; *py = y; *pz = z;
     };
 
     refresh_poses();
     int iters = 0, trials_total = 0;
-    double chi_first = 0, chi_last = 0;
+    double chi_first = 0, chi_last = 0, lambda = 0, ni = 2, rho = 0, currentChi = 0;
 
     for (int iteration = 0; iteration < a.max_iters; ++iteration) {
-        // ---- computeActiveErrors + buildSystem -------------------------------------------------------
+        // ---- computeActiveErrors + buildSystem -------------------------------------------------------------------
+        for (int i = ct; i < np * 36; i += CT) ws.Hpp[i] = 0.0;
+        for (int i = ct; i < dimp; i += CT) ws.bp[i] = 0.0;
         double acc = 0;
-        for (int o = tid; o < n_obs; o += kBAThreads) {
-            const int k = a.kf_idx[o0 + o];
-            const double* T = s_R[k];
-            const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
-            const double x = T[0] * X[0] + T[1] * X[1] + T[2] * X[2] + T[3];
-            const double y = T[4] * X[0] + T[5] * X[1] + T[6] * X[2] + T[7];
-            const double z = T[8] * X[0] + T[9] * X[1] + T[10] * X[2] + T[11];
-            const double e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx), e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
+        for (int o = ct; o < n_obs; o += CT) {
+            double e0, e1, x, y, z;
+            reproject(o, &e0, &e1, &x, &y, &z);
             const double e2 = e0 * e0 + e1 * e1;
             double w = 1.0;
             if (a.huber_delta > 0 && e2 > dsqr) {
@@ -209,28 +245,28 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a) {
             } else {
                 acc += e2;
             }
+            const double* Tm = s_R[a.kf_idx[o0 + o]];
             double* rec = a.lin + 21 * (size_t)(o0 + o);
             rec[0] = e0; rec[1] = e1; rec[2] = w;
-            const double z_2 = z * z;
-            const double t0[3] = {fx, 0, -x / z * fx}, t1[3] = {0, fy, -y / z * fy};
+            const double z_2 = z * z, iz = -1. / z;
+            const double t02 = -x / z * fx, t12 = -y / z * fy;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                rec[3 + c] = -1. / z * (t0[0] * T[c] + t0[1] * T[4 + c] + t0[2] * T[8 + c]);
-                rec[6 + c] = -1. / z * (t1[0] * T[c] + t1[1] * T[4 + c] + t1[2] * T[8 + c]);
+                rec[3 + c] = iz * (fx * Tm[c] + t02 * Tm[8 + c]);
+                rec[6 + c] = iz * (fy * Tm[4 + c] + t12 * Tm[8 + c]);
             }
             rec[9] = x * y / z_2 * fx; rec[10] = -(1 + (x * x / z_2)) * fx; rec[11] = y / z * fx;
             rec[12] = -1. / z * fx; rec[13] = 0; rec[14] = x / z_2 * fx;
             rec[15] = (1 + y * y / z_2) * fy; rec[16] = -x * y / z_2 * fy; rec[17] = -x / z * fy;
             rec[18] = 0; rec[19] = -1. / z * fy; rec[20] = y / z_2 * fy;
         }
-        const double currentChi0 = block_sum(acc, s_tmp);
-        if (tid == 0) s_current_chi = currentChi0;
-        if (iteration == 0) chi_first = currentChi0;
-        __syncthreads();
+        double dummy;
+        cluster_sum2(acc, 0.0, &currentChi, &dummy);   // (barrier: lin[] and the zeroed Hpp/bp are visible cluster-wide)
+        if (iteration == 0) chi_first = currentChi;
         // Hll, bl : thread per landmark
         double mx = 0;
-        for (int j = tid; j < n_pt; j += kBAThreads) {
-            double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};  // xx xy xz yy yz zz
+        for (int j = ct; j < n_pt; j += CT) {
+            double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
             for (int q = a.lm_start[p0 + j]; q < a.lm_start[p0 + j + 1]; ++q) {
                 const double* rec = a.lin + 21 * (size_t)a.lm_obs[q];
                 const double w = rec[2];
@@ -248,170 +284,205 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a) {
             bj[0] = b[0]; bj[1] = b[1]; bj[2] = b[2];
             mx = fmax(mx, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
         }
-        // Hpp, bp : warp per free pose
-        for (int k = warp; k < n_kf; k += n_warps) {
-            const int fi = s_free[k];
-            if (fi < 0) continue;
-            double h[21], g[6];
+        // Hpp, bp : (free pose, chunk) tasks over all warps of the cluster, f64 atomics into the workspace
+        if (np > 0) {
+            const int CH = max(1, GW / np);
+            for (int task = gw; task < np * CH; task += GW) {
+                const int fi = task % np, chunk = task / np;
+                int k = 0;
+                while (s_free[k] != fi) ++k;
+                double h[21], g[6];
 #pragma unroll
-            for (int t = 0; t < 21; ++t) h[t] = 0;
+                for (int t = 0; t < 21; ++t) h[t] = 0;
 #pragma unroll
-            for (int t = 0; t < 6; ++t) g[t] = 0;
-            for (int q = a.ps_start[k0 + k] + lane; q < a.ps_start[k0 + k + 1]; q += 32) {
-                const double* rec = a.lin + 21 * (size_t)a.ps_obs[q];
-                const double w = rec[2];
-                const double* J0 = rec + 9;
-                const double* J1 = rec + 15;
+                for (int t = 0; t < 6; ++t) g[t] = 0;
+                for (int q = a.ps_start[k0 + k] + chunk * 32 + lane; q < a.ps_start[k0 + k + 1]; q += CH * 32) {
+                    const double* rec = a.lin + 21 * (size_t)a.ps_obs[q];
+                    const double w = rec[2];
+                    const double* J0 = rec + 9;
+                    const double* J1 = rec + 15;
+                    int t = 0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int c = r; c < 6; ++c) h[t++] += w * (J0[r] * J0[c] + J1[r] * J1[c]);
+                        g[r] += -w * (J0[r] * rec[0] + J1[r] * rec[1]);
+                    }
+                }
                 int t = 0;
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
 #pragma unroll
-                    for (int c = r; c < 6; ++c) h[t++] += w * (J0[r] * J0[c] + J1[r] * J1[c]);
-                    g[r] += -w * (J0[r] * rec[0] + J1[r] * rec[1]);
+                    for (int c = r; c < 6; ++c) {
+                        const double v = warp_sum(h[t++]);
+                        if (lane == 0) {
+                            atomicAdd(&ws.Hpp[fi * 36 + r * 6 + c], v);
+                            if (c != r) atomicAdd(&ws.Hpp[fi * 36 + c * 6 + r], v);
+                        }
+                    }
+                    const double gv = warp_sum(g[r]);
+                    if (lane == 0) atomicAdd(&ws.bp[fi * 6 + r], gv);
                 }
-            }
-            int t = 0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                for (int c = r; c < 6; ++c) {
-                    const double v = warp_sum(h[t++]);
-                    if (lane == 0) s_Hpp[fi * 36 + r * 6 + c] = s_Hpp[fi * 36 + c * 6 + r] = v;
-                }
-                const double gv = warp_sum(g[r]);
-                if (lane == 0) s_bp[fi * 6 + r] = gv;
             }
         }
-        __syncthreads();
-        if (iteration == 0) {  // computeLambdaInit = tau * max |diag H|
-            if (tid < dimp) mx = fmax(mx, fabs(s_Hpp[(tid / 6) * 36 + (tid % 6) * 7]));
-            const double m = block_max(mx, s_tmp);
-            if (tid == 0) {
-                s_lambda = a.tau * m;
-                s_ni = 2;
+        {
+            double m0, m1;
+            // max |diag| via two sums is wrong; use a dedicated max reduction through the same partial slots
+            const double bm = block_max(mx, s_tmp);
+            const int slot = red_slot;
+            red_slot = (red_slot + 1) & 3;
+            if (tid == 0) ws.red[slot][rank][0] = bm;
+            cluster.sync();                                   // also publishes Hll/bl and the Hpp/bp atomics
+            m0 = 0;
+            for (int r = 0; r < C; ++r) m0 = fmax(m0, __ldcg(&ws.red[slot][r][0]));
+            if (iteration == 0) {  // computeLambdaInit = tau * max |diag H|
+                for (int i = 0; i < dimp; ++i) m0 = fmax(m0, fabs(__ldcg(&ws.Hpp[(i / 6) * 36 + (i % 6) * 7])));
+                lambda = a.tau * m0;
+                ni = 2;
             }
-            __syncthreads();
+            (void)m1;
         }
 
         int qmax = 0;
         do {
-            const double lambda = s_lambda;
-            // _optimizer->push()
+            // _optimizer->push(): pose replica in shared memory, landmarks per owner thread
             if (tid < n_kf)
-                for (int c = 0; c < 6; ++c) s_backup[tid][c] = a.poses[6 * (size_t)(k0 + tid) + c];
-            for (int i = tid; i < 3 * n_pt; i += kBAThreads) a.pts_backup[3 * (size_t)p0 + i] = a.pts[3 * (size_t)p0 + i];
-            // Dinv per landmark; S <- Hpp + lambda I ; bs <- bp
-            for (int j = tid; j < n_pt; j += kBAThreads) {
+                for (int c = 0; c < 6; ++c) s_backup[tid][c] = s_pose[tid][c];
+            for (int j = ct; j < n_pt; j += CT) {
                 double D[9];
                 const double* Hj = a.Hll + 9 * (size_t)(p0 + j);
 #pragma unroll
                 for (int t = 0; t < 9; ++t) D[t] = Hj[t];
                 D[0] += lambda; D[4] += lambda; D[8] += lambda;
                 inverse3d(D, a.Dinv + 9 * (size_t)(p0 + j));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a.pts_backup[3 * (size_t)(p0 + j) + c] = a.pts[3 * (size_t)(p0 + j) + c];
             }
-            for (int i = tid; i < dimp * dimp; i += kBAThreads) {
-                const int r = i / dimp, c = i - r * dimp;
-                s_S[i] = (r / 6 == c / 6) ? s_Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)] + (r == c ? lambda : 0.0) : 0.0;
-            }
-            if (tid < dimp) s_bs[tid] = s_bp[tid];
-            __syncthreads();
-            // Schur complement: warp per block pair (f1 <= f2)
-            for (int pr = warp; pr < n_pairs; pr += n_warps) {
-                // decode (f1, f2) from the triangular index
-                int f1 = 0, rem = pr;
-                while (rem >= np - f1) {
-                    rem -= np - f1;
-                    ++f1;
-                }
-                const int f2 = f1 + rem;
-                double accS[36], accb[6];
+            for (int i = ct; i < dimp * dimp; i += CT) ws.S[i] = 0.0;
+            for (int i = ct; i < dimp; i += CT) ws.bs[i] = 0.0;
+            cluster.sync();
+            // Schur complement: (block pair, chunk) tasks over all warps of the cluster
+            if (n_pairs > 0) {
+                const int CH = max(1, GW / n_pairs);
+                for (int task = gw; task < n_pairs * CH; task += GW) {
+                    const int pr = task % n_pairs, chunk = task / n_pairs;
+                    int f1 = 0, rem = pr;
+                    while (rem >= np - f1) {
+                        rem -= np - f1;
+                        ++f1;
+                    }
+                    const int f2 = f1 + rem;
+                    double accS[36], accb[6];
 #pragma unroll
-                for (int t = 0; t < 36; ++t) accS[t] = 0;
+                    for (int t = 0; t < 36; ++t) accS[t] = 0;
 #pragma unroll
-                for (int t = 0; t < 6; ++t) accb[t] = 0;
-                for (int q = pair_start[pr] + lane; q < pair_start[pr + 1]; q += 32) {
-                    const int o1 = a.pair_o1[q], o2 = a.pair_o2[q];
-                    const int j = p0 + a.pt_idx[o1];
-                    const double* Di = a.Dinv + 9 * (size_t)j;
-                    double H1[6][3], BD[6][3];
-                    make_hpl(a.lin + 21 * (size_t)o1, H1);
-#pragma unroll
-                    for (int r = 0; r < 6; ++r)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) BD[r][c] = H1[r][0] * Di[c] + H1[r][1] * Di[3 + c] + H1[r][2] * Di[6 + c];
-                    if (o1 == o2) {
-                        const double* bj = a.bl + 3 * (size_t)j;
-#pragma unroll
-                        for (int r = 0; r < 6; ++r) accb[r] += BD[r][0] * bj[0] + BD[r][1] * bj[1] + BD[r][2] * bj[2];
+                    for (int t = 0; t < 6; ++t) accb[t] = 0;
+                    for (int q = pair_start[pr] + chunk * 32 + lane; q < pair_start[pr + 1]; q += CH * 32) {
+                        const int o1 = a.pair_o1[q], o2 = a.pair_o2[q];
+                        const int j = p0 + a.pt_idx[o1];
+                        const double* Di = a.Dinv + 9 * (size_t)j;
+                        double H1[6][3], BD[6][3];
+                        make_hpl(a.lin + 21 * (size_t)o1, H1);
 #pragma unroll
                         for (int r = 0; r < 6; ++r)
 #pragma unroll
-                            for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H1[c][0] + BD[r][1] * H1[c][1] + BD[r][2] * H1[c][2];
-                    } else {
-                        double H2[6][3];
-                        make_hpl(a.lin + 21 * (size_t)o2, H2);
+                            for (int c = 0; c < 3; ++c) BD[r][c] = H1[r][0] * Di[c] + H1[r][1] * Di[3 + c] + H1[r][2] * Di[6 + c];
+                        if (o1 == o2) {
+                            const double* bj = a.bl + 3 * (size_t)j;
 #pragma unroll
-                        for (int r = 0; r < 6; ++r)
+                            for (int r = 0; r < 6; ++r) accb[r] += BD[r][0] * bj[0] + BD[r][1] * bj[1] + BD[r][2] * bj[2];
 #pragma unroll
-                            for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H2[c][0] + BD[r][1] * H2[c][1] + BD[r][2] * H2[c][2];
+                            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                                for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H1[c][0] + BD[r][1] * H1[c][1] + BD[r][2] * H1[c][2];
+                        } else {
+                            double H2[6][3];
+                            make_hpl(a.lin + 21 * (size_t)o2, H2);
+#pragma unroll
+                            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                                for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H2[c][0] + BD[r][1] * H2[c][1] + BD[r][2] * H2[c][2];
+                        }
                     }
-                }
 #pragma unroll
-                for (int t = 0; t < 36; ++t) {
-                    const double v = warp_sum(accS[t]);
-                    if (lane == 0) {
-                        const int r = t / 6, c = t - r * 6;
-                        s_S[(6 * f1 + r) * dimp + 6 * f2 + c] -= v;
-                        if (f1 != f2) s_S[(6 * f2 + c) * dimp + 6 * f1 + r] -= v;
+                    for (int t = 0; t < 36; ++t) {
+                        const double v = warp_sum(accS[t]);
+                        if (lane == 0) {
+                            const int r = t / 6, c = t - r * 6;
+                            atomicAdd(&ws.S[(6 * f1 + r) * dimp + 6 * f2 + c], -v);
+                            if (f1 != f2) atomicAdd(&ws.S[(6 * f2 + c) * dimp + 6 * f1 + r], -v);
+                        }
                     }
-                }
-                if (f1 == f2) {
+                    if (f1 == f2) {
 #pragma unroll
-                    for (int r = 0; r < 6; ++r) {
-                        const double v = warp_sum(accb[r]);
-                        if (lane == 0) s_bs[6 * f1 + r] -= v;
+                        for (int r = 0; r < 6; ++r) {
+                            const double v = warp_sum(accb[r]);
+                            if (lane == 0) atomicAdd(&ws.bs[6 * f1 + r], -v);
+                        }
                     }
                 }
             }
-            __syncthreads();
-            // dense Cholesky S = L L^T in place (lower triangle), whole CTA, then the two triangular solves
-            if (tid == 0) s_ok = 1;
-            __syncthreads();
-            for (int j = 0; j < dimp; ++j) {
-                if (tid == 0) {
-                    const double d = s_S[j * dimp + j];
-                    if (!(d > 0)) s_ok = 0;
-                    s_S[j * dimp + j] = sqrt(d);
+            cluster.sync();
+            // CTA 0: S = Hpp + lambda I - sum, dense Cholesky in shared memory, triangular solves by warp 0
+            if (rank == 0) {
+                for (int i = tid; i < dimp * dimp; i += T) {
+                    const int r = i / dimp, c = i - r * dimp;
+                    double v = __ldcg(&ws.S[i]);
+                    if (r / 6 == c / 6) v += __ldcg(&ws.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)]) + (r == c ? lambda : 0.0);
+                    s_S[i] = v;
+                }
+                if (tid < dimp) s_bs[tid] = __ldcg(&ws.bs[tid]) + __ldcg(&ws.bp[tid]);
+                __shared__ int s_ok;
+                if (tid == 0) s_ok = 1;
+                __syncthreads();
+                for (int j = 0; j < dimp; ++j) {
+                    if (tid == 0) {
+                        const double d = s_S[j * dimp + j];
+                        if (!(d > 0)) s_ok = 0;
+                        s_S[j * dimp + j] = sqrt(d);
+                    }
+                    __syncthreads();
+                    if (!s_ok) break;
+                    const double djj = s_S[j * dimp + j];
+                    const int rem = dimp - j - 1;
+                    // column scale fused into the trailing update: L(i,j) = S(i,j)/djj is recomputed by the readers
+                    for (int e = tid; e < rem * rem; e += T) {
+                        const int r = j + 1 + e / rem, c = j + 1 + e % rem;
+                        if (c <= r) s_S[r * dimp + c] -= (s_S[r * dimp + j] / djj) * (s_S[c * dimp + j] / djj);
+                    }
+                    __syncthreads();
+                    // column j is final after this scaling and is not read again before the solves
+                    for (int i = j + 1 + tid; i < dimp; i += T) s_S[i * dimp + j] /= djj;
                 }
                 __syncthreads();
-                if (!s_ok) break;
-                const double djj = s_S[j * dimp + j];
-                for (int i = j + 1 + tid; i < dimp; i += kBAThreads) s_S[i * dimp + j] /= djj;
-                __syncthreads();
-                const int rem = dimp - j - 1;
-                for (int e = tid; e < rem * rem; e += kBAThreads) {
-                    const int r = j + 1 + e / rem, c = j + 1 + e % rem;
-                    if (c <= r) s_S[r * dimp + c] -= s_S[r * dimp + j] * s_S[c * dimp + j];
+                if (s_ok && warp == 0) {
+                    // forward then backward substitution, one row at a time, the dot product split over the lanes
+                    for (int i = 0; i < dimp; ++i) {
+                        double s = 0;
+                        for (int k = lane; k < i; k += 32) s += s_S[i * dimp + k] * s_bs[k];
+                        s = warp_sum(s);
+                        if (lane == 0) s_bs[i] = (s_bs[i] - s) / s_S[i * dimp + i];
+                        __syncwarp();
+                    }
+                    for (int i = dimp - 1; i >= 0; --i) {
+                        double s = 0;
+                        for (int k = i + 1 + lane; k < dimp; k += 32) s += s_S[k * dimp + i] * s_bs[k];
+                        s = warp_sum(s);
+                        if (lane == 0) s_bs[i] = (s_bs[i] - s) / s_S[i * dimp + i];
+                        __syncwarp();
+                    }
                 }
                 __syncthreads();
+                if (tid < dimp) ws.xp[tid] = s_bs[tid];
+                if (tid == 0) ws.ok = s_ok;
             }
-            if (tid == 0 && s_ok) {
-                for (int i = 0; i < dimp; ++i) {
-                    double s = s_bs[i];
-                    for (int k = 0; k < i; ++k) s -= s_S[i * dimp + k] * s_bs[k];
-                    s_bs[i] = s / s_S[i * dimp + i];
-                }
-                for (int i = dimp - 1; i >= 0; --i) {
-                    double s = s_bs[i];
-                    for (int k = i + 1; k < dimp; ++k) s -= s_S[k * dimp + i] * s_bs[k];
-                    s_bs[i] = s / s_S[i * dimp + i];
-                }
-            }
+            cluster.sync();
+            const bool ok2 = __ldcg(&ws.ok) != 0;
+            if (tid < dimp) s_xp[tid] = __ldcg(&ws.xp[tid]);
             __syncthreads();
-            const bool ok2 = s_ok != 0;
-            // landmark back-substitution + scale term + update
+            // landmark back-substitution + update (owner thread), pose update (replicated), scale term
             double scale = 0;
-            for (int j = tid; j < n_pt; j += kBAThreads) {
+            for (int j = ct; j < n_pt; j += CT) {
                 const double* bj = a.bl + 3 * (size_t)(p0 + j);
                 double r[3] = {bj[0], bj[1], bj[2]};
                 for (int q = a.lm_start[p0 + j]; q < a.lm_start[p0 + j + 1]; ++q) {
@@ -423,7 +494,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
 #pragma unroll
-                        for (int rr = 0; rr < 6; ++rr) r[c] -= H1[rr][c] * s_bs[6 * fi + rr];
+                        for (int rr = 0; rr < 6; ++rr) r[c] -= H1[rr][c] * s_xp[6 * fi + rr];
                 }
                 const double* Di = a.Dinv + 9 * (size_t)(p0 + j);
                 double* X = a.pts + 3 * (size_t)(p0 + j);
@@ -434,69 +505,80 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a) {
                     X[c] += x;
                 }
             }
-            if (tid < dimp) scale += s_bs[tid] * (lambda * s_bs[tid] + s_bp[tid]);
-            if (tid < n_kf && s_free[tid] >= 0) {  // VertexSE3Sophus::oplusImpl
-                const double* u = s_bs + 6 * s_free[tid];
+            if (rank == 0 && tid < dimp) scale += s_xp[tid] * (lambda * s_xp[tid] + __ldcg(&ws.bp[tid]));
+            if (tid < n_kf && s_free[tid] >= 0) {  // VertexSE3Sophus::oplusImpl on the replica
+                const double* u = s_xp + 6 * s_free[tid];
                 const double v[6] = {u[3], u[4], u[5], u[0], u[1], u[2]};
-                double* est = a.poses + 6 * (size_t)(k0 + tid);
-                const SE3d Tn = se3_mul(se3_exp(v), pose_from_g2o(est));
+                const SE3d Tn = se3_mul(se3_exp(v), pose_from_g2o(s_pose[tid]));
                 double lg[6];
                 se3_log(Tn, lg);
-                est[0] = lg[3]; est[1] = lg[4]; est[2] = lg[5]; est[3] = lg[0]; est[4] = lg[1]; est[5] = lg[2];
-            }
-            scale = block_sum(scale, s_tmp) + 1e-3;
-            refresh_poses();
-            double tempChi = robust_chi2();
-            if (!ok2) tempChi = 1.7976931348623157e308;
-            if (tid == 0) {
-                double rho = (s_current_chi - tempChi) / scale;
-                if (rho > 0 && isfinite(tempChi)) {
-                    double alpha = 1. - pow((2 * rho - 1), 3);
-                    alpha = fmin(alpha, 2. / 3.);
-                    s_lambda *= fmax(1. / 3., alpha);
-                    s_ni = 2;
-                    s_current_chi = tempChi;
-                    s_accept = 1;
-                } else {
-                    s_lambda *= s_ni;
-                    s_ni *= 2;
-                    s_accept = 0;
-                }
-                s_rho = rho;
+                s_pose[tid][0] = lg[3]; s_pose[tid][1] = lg[4]; s_pose[tid][2] = lg[5];
+                s_pose[tid][3] = lg[0]; s_pose[tid][4] = lg[1]; s_pose[tid][5] = lg[2];
             }
             __syncthreads();
-            if (!s_accept) {  // _optimizer->pop()
+            refresh_poses();
+            double scale_tot, dummy2;
+            cluster_sum2(scale, 0.0, &scale_tot, &dummy2);    // (barrier: updated landmarks visible cluster-wide)
+            scale_tot += 1e-3;
+            double chi_part = 0;
+            for (int o = ct; o < n_obs; o += CT) {
+                double e0, e1, x, y, z;
+                reproject(o, &e0, &e1, &x, &y, &z);
+                const double e2 = e0 * e0 + e1 * e1;
+                chi_part += (a.huber_delta > 0 && e2 > dsqr) ? 2 * sqrt(e2) * a.huber_delta - dsqr : e2;
+            }
+            double tempChi;
+            cluster_sum2(chi_part, 0.0, &tempChi, &dummy2);
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            rho = (currentChi - tempChi) / scale_tot;
+            bool accept;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+                accept = true;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                accept = false;
+            }
+            if (!accept) {  // _optimizer->pop()
                 if (tid < n_kf)
-                    for (int c = 0; c < 6; ++c) a.poses[6 * (size_t)(k0 + tid) + c] = s_backup[tid][c];
-                for (int i = tid; i < 3 * n_pt; i += kBAThreads) a.pts[3 * (size_t)p0 + i] = a.pts_backup[3 * (size_t)p0 + i];
+                    for (int c = 0; c < 6; ++c) s_pose[tid][c] = s_backup[tid][c];
+                for (int j = ct; j < n_pt; j += CT)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a.pts[3 * (size_t)(p0 + j) + c] = a.pts_backup[3 * (size_t)(p0 + j) + c];
                 __syncthreads();
                 refresh_poses();
             }
             ++qmax;
             ++trials_total;
-        } while (s_rho < 0 && qmax < a.max_trials);
+        } while (rho < 0 && qmax < a.max_trials);
         ++iters;
-        chi_last = s_current_chi;
-        if (qmax == a.max_trials || s_rho == 0) break;
+        chi_last = currentChi;
+        if (qmax == a.max_trials || rho == 0) break;
     }
-
+    cluster.sync();  // a rejected last trial restored landmarks owned by other CTAs
     // outlier flags (BA.cpp:505-515): plain chi2 > 5.991
     double n_out = 0;
-    for (int o = tid; o < n_obs; o += kBAThreads) {
-        const double* T = s_R[a.kf_idx[o0 + o]];
-        const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
-        const double x = T[0] * X[0] + T[1] * X[1] + T[2] * X[2] + T[3];
-        const double y = T[4] * X[0] + T[5] * X[1] + T[6] * X[2] + T[7];
-        const double z = T[8] * X[0] + T[9] * X[1] + T[10] * X[2] + T[11];
-        const double e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx), e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
+    for (int o = ct; o < n_obs; o += CT) {
+        double e0, e1, x, y, z;
+        reproject(o, &e0, &e1, &x, &y, &z);
         const int out = (e0 * e0 + e1 * e1 > a.chi2_outlier) ? 1 : 0;
         a.outlier[o0 + o] = (uint8_t)out;
         n_out += out;
     }
-    n_out = block_sum(n_out, s_tmp);
-    if (tid == 0) {
-        double* st = a.stats + 8 * (size_t)prob;
-        st[0] = iters; st[1] = trials_total; st[2] = chi_first; st[3] = chi_last; st[4] = s_lambda; st[5] = n_out;
+    double n_out_tot, dummy3;
+    cluster_sum2(n_out, 0.0, &n_out_tot, &dummy3);
+    if (rank == 0) {
+        if (tid < n_kf)
+            for (int c = 0; c < 6; ++c) a.poses[6 * (size_t)(k0 + tid) + c] = s_pose[tid][c];
+        if (tid == 0) {
+            double* st = a.stats + 8 * (size_t)prob;
+            st[0] = iters; st[1] = trials_total; st[2] = chi_first; st[3] = chi_last; st[4] = lambda; st[5] = n_out_tot;
+        }
     }
 }
 
@@ -1002,11 +1084,26 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
     a.max_iters = prm->max_iters; a.max_trials = prm->max_trials; a.huber_delta = prm->huber_delta;
     a.chi2_outlier = prm->chi2_outlier; a.tau = prm->tau;
     const int dimp = 6 * std::max(max_free, 1);
-    const size_t smem = sizeof(double) * ((size_t)dimp * dimp + (size_t)std::max(max_free, 1) * 36 + 2 * (size_t)dimp);
+    const size_t smem = sizeof(double) * ((size_t)dimp * dimp + (size_t)dimp);
+    ClusterWs* d_ws = static_cast<ClusterWs*>(dev_scratch(ctx, 5, sizeof(ClusterWs) * P));
+    if (!d_ws) return YGZB_ERR_CUDA;
     YGZB_CUDA(ctx, cudaFuncSetAttribute(local_ba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
+        // one cluster of kClusterSize CTAs (= SMs) per problem
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(n_problems * kClusterSize));
+        cfg.blockDim = dim3(kBAThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kClusterSize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
         ProfScope ps(ctx, kStageLocalBA);
-        local_ba_kernel<<<n_problems, kBAThreads, smem, ctx->stream>>>(a);
+        YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, local_ba_kernel, a, d_ws));
     }
     YGZB_LAUNCHED(ctx);
     TRY(d2h(ctx, poses, d_poses, 6 * NK));
