@@ -271,7 +271,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the bounded cpu_baseline sample")
-    ap.add_argument("--e2e-contexts", type=int, default=2,
+    ap.add_argument("--e2e-contexts", type=int, default=4,
                     help="host threads (one ygzb context = one stream each) used by the e2e leg so that the H2D copy "
                          "of one batch overlaps the kernels of another")
     args = ap.parse_args()

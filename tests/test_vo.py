@@ -1,0 +1,47 @@
+"""The tracking loop of BASELINE config C5 (ygz_slam_b200/vo.py): on the CPU oracle it follows the synthetic
+ground truth; on the GPU it reproduces the oracle's trajectory (end-to-end pose parity through sparse alignment,
+direct projection, pose-only refinement, detection at keyframes and local BA)."""
+import numpy as np
+import pytest
+
+from ygz_slam_b200 import se3, synth, vo
+from vo_oracle_backend import OracleBackend
+
+
+def _run(backend, n_streams, n_frames, step=2):
+    V = vo.VisualOdometry(backend, n_streams, kf_min_frames=5, kf_min_rot=0.03, kf_min_trans=0.03)
+    T0 = [None] * n_streams
+    errs = np.zeros((n_streams, n_frames))
+    for k in range(n_frames):
+        frames = [synth.stream_frame(step * k, stream=s) for s in range(n_streams)]
+        V.add_frames([f[0] for f in frames], [f[1] for f in frames], k)
+        for s in range(n_streams):
+            if T0[s] is None:
+                T0[s] = frames[s][2]
+            gt = se3.mul(frames[s][2], se3.inv(T0[s]))
+            errs[s, k] = np.linalg.norm(se3.se3_log(se3.mul(V.streams[s].T_cw, se3.inv(gt))))
+    return V, errs
+
+
+def test_vo_on_oracle_follows_ground_truth(oracle):
+    V, errs = _run(OracleBackend(oracle), 1, 24)
+    st = V.streams[0]
+    assert not st.lost
+    assert st.stats["keyframes"] >= 3 and st.stats["ba"] >= 2
+    assert errs.max() < 3e-3                       # metres / radians on a 2 m scene, pixel noise sigma = 2 grey levels
+    assert st.stats["projected"] > 0.9 * st.stats["candidates"]
+
+
+@pytest.mark.gpu
+def test_vo_gpu_matches_oracle_trajectory(ctx3, oracle):
+    n_streams, n_frames = 2, 20
+    Vo, _ = _run(OracleBackend(oracle), n_streams, n_frames)
+    be = vo.GpuBackend(ctx3, n_streams * vo.VisualOdometry.SLOTS_PER_STREAM)
+    Vg, errs = _run(be, n_streams, n_frames)
+    for s in range(n_streams):
+        assert not Vg.streams[s].lost
+        assert Vg.streams[s].stats == Vo.streams[s].stats           # same candidates / projections / inliers / keyframes
+        for Tg, Tw in zip(Vg.streams[s].trajectory, Vo.streams[s].trajectory):
+            assert np.linalg.norm(se3.se3_log(se3.mul(Tg, se3.inv(Tw)))) < 1e-4   # BASELINE: pose error < 1e-4 vs reference
+    assert errs.max() < 3e-3
+    be.fr.close()

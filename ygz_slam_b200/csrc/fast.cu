@@ -62,22 +62,14 @@ template <int PITCH>
 __device__ __forceinline__ bool fast_quick_test(const uint8_t* __restrict__ c, int b) {
     const int p = *c;
     const int cb = p + b, c_b = p - b;
-    int v0 = c[3 * PITCH], v1 = c[-3 * PITCH];
-    bool pb = (v0 > cb) | (v1 > cb), pd = (v0 < c_b) | (v1 < c_b);
+    // pairs (0,8) and (4,12) evaluated together (five independent loads, one branch)
+    const int v0 = c[3 * PITCH], v8 = c[-3 * PITCH], v4 = c[3], v12 = c[-3];
+    bool pb = ((v0 > cb) | (v8 > cb)) & ((v4 > cb) | (v12 > cb));
+    bool pd = ((v0 < c_b) | (v8 < c_b)) & ((v4 < c_b) | (v12 < c_b));
     if (!(pb | pd)) return false;
-    v0 = c[3];
-    v1 = c[-3];
-    pb &= (v0 > cb) | (v1 > cb);
-    pd &= (v0 < c_b) | (v1 < c_b);
-    if (!(pb | pd)) return false;
-    v0 = c[2 * PITCH + 2];
-    v1 = c[-2 * PITCH - 2];
-    pb &= (v0 > cb) | (v1 > cb);
-    pd &= (v0 < c_b) | (v1 < c_b);
-    v0 = c[-2 * PITCH + 2];
-    v1 = c[2 * PITCH - 2];
-    pb &= (v0 > cb) | (v1 > cb);
-    pd &= (v0 < c_b) | (v1 < c_b);
+    const int v2 = c[2 * PITCH + 2], v10 = c[-2 * PITCH - 2], v6 = c[-2 * PITCH + 2], v14 = c[2 * PITCH - 2];
+    pb &= ((v2 > cb) | (v10 > cb)) & ((v6 > cb) | (v14 > cb));
+    pd &= ((v2 < c_b) | (v10 < c_b)) & ((v6 < c_b) | (v14 < c_b));
     return pb | pd;
 }
 
@@ -240,11 +232,26 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
             }
         }
     } else {
-        for (int idx = tid; idx < kScH * kScW; idx += 256) {
-            const int ry = idx / kScW, rx = idx - ry * kScW;
-            const int x = x0 - 1 + rx, y = y0 - 1 + ry;
-            if (x < 3 || x >= lv.w - 3 || y < 3 || y >= lv.h - 3) continue;
-            if (fast_quick_test<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_quick[atomicAdd(&s_nquick, 1)] = (uint16_t)idx;
+        // exact opposite-pair test: one warp per region row (no index divisions), lanes over the 82 columns in three
+        // passes, survivors appended with one shared-memory atomic per warp and pass
+        const int lane_ = tid & 31, warp_ = tid >> 5;
+        const int rx_lo = max(0, 4 - x0), rx_hi = min(kScW, lv.w - 2 - x0);   // x = x0 - 1 + rx in [3, w - 3)
+        const int ry_lo = max(0, 4 - y0), ry_hi = min(kScH, lv.h - 2 - y0);
+        for (int ry = ry_lo + warp_; ry < ry_hi; ry += 8) {
+            const uint8_t* row = s_img + (ry + 4) * kSmW + 7;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const int rx = pass * 32 + lane_;
+                bool cand = false;
+                if (rx >= rx_lo && rx < rx_hi) cand = fast_quick_test<kSmW>(row + rx, g.threshold);
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
+                if (m) {
+                    int base = 0;
+                    if (lane_ == 0) base = atomicAdd(&s_nquick, __popc(m));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (cand) s_quick[base + __popc(m & ((1u << lane_) - 1u))] = (uint16_t)(ry * kScW + rx);
+                }
+            }
         }
     }
     // grid-cell lookup tables of this tile (local cell column / row of every tile pixel)
