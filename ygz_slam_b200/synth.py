@@ -162,3 +162,29 @@ def ba_scene(n_kf: int = 10, n_pt: int = 2000, target_obs: int = 8000, seed: int
     return dict(poses_true=poses_true, poses_noisy=poses_noisy, pts_true=pts_true, pts_noisy=pts_noisy,
                 kf_idx=np.array(kf_idx, np.int32), pt_idx=np.array(pt_idx, np.int32),
                 px=np.array(px, np.float64))
+
+
+def shift_stream(stream: int, n_frames: int, noise_sigma: float = 2.0, plane_z: float = 2.0):
+    """Cheap exact-ground-truth VO stream: a fronto-parallel textured plane seen by a camera that only translates
+    parallel to it, i.e. integer-pixel sliding crops of one render.  Returns (frames u8 (n,H,W), depth (H,W) constant,
+    T_cw list) -- the pose of frame k relative to frame 0 is a pure translation known exactly."""
+    tex = texture(0x59475A00 + stream, 2048)
+    bw, bh = W + 256, H + 128
+    base, _ = render_plane(tex, np.eye(4)[:3], plane_z=plane_z, w=bw, h=bh, cx=bw / 2, cy=bh / 2)
+    rng = np.random.default_rng(1000 + stream)
+    frames = np.empty((n_frames, H, W), np.uint8)
+    poses = []
+    ox0 = oy0 = None
+    for k in range(n_frames):
+        ox = int(round(128 + 110 * np.sin(2 * np.pi * k / 240 + 0.3 * stream)))
+        oy = int(round(64 + 50 * np.sin(2 * np.pi * k / 170 + 0.5 * stream)))
+        if ox0 is None:
+            ox0, oy0 = ox, oy
+        crop = base[oy:oy + H, ox:ox + W].astype(np.int16) + np.rint(rng.normal(0, noise_sigma, (H, W))).astype(np.int16)
+        frames[k] = np.clip(crop, 0, 255).astype(np.uint8)
+        T = np.eye(4)[:3].copy()
+        T[0, 3] = -(ox - ox0) * plane_z / FX
+        T[1, 3] = -(oy - oy0) * plane_z / FY
+        poses.append(T)
+    depth = np.full((H, W), plane_z, np.float64)
+    return frames, depth, poses
