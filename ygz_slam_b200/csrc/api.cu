@@ -320,6 +320,7 @@ int ygzb_frames_create(ygzb_ctx* ctx, int capacity, ygzb_frames** out) {
     A(dalloc(ctx, &f->d_offsets, cap + 1));
     if (rc == YGZB_OK) rc = check_cuda(ctx, cudaMemsetAsync(f->d_count, 0, cap * sizeof(int32_t), ctx->stream), "memset");
     if (rc == YGZB_OK) rc = check_cuda(ctx, cudaMemsetAsync(f->d_pyr, 0, cap * ctx->slot_stride, ctx->stream), "memset");
+    if (rc == YGZB_OK) rc = build_tile_maps(f);
     if (rc != YGZB_OK) {
         ygzb_frames_destroy(f);
         return rc;
@@ -336,6 +337,7 @@ void ygzb_frames_destroy(ygzb_frames* f) {
                     f->d_fdesc, f->d_best_key, f->d_first_key, f->d_stats, f->d_slots,  f->d_occupied, f->d_offsets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (f->d_tile_maps) cudaFree(f->d_tile_maps);
     delete f;
 }
 

@@ -75,6 +75,11 @@ struct ygzb_frames {
     int32_t* d_stats;                 // [capacity][n_levels][2]
     int32_t* d_slots;                 // [capacity] slot list of the current call
     uint8_t* d_occupied;              // [capacity][n_cells]
+    // TMA descriptors (CUtensorMap, 128 B each) of the first pyramid levels: 3-D tensors (x, y, slot) of u8 with a
+    // 112 x 50 x 1 box = one FAST tile + halo; tma_levels == 0 disables the TMA path
+    alignas(64) unsigned char tile_maps[3][128];
+    void* d_tile_maps;                // device copy of tile_maps
+    int tma_levels;
     int32_t* d_offsets;               // [capacity+1]
     int last_n;
 };
@@ -123,6 +128,7 @@ int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr /*
 int launch_pyrdown_ptrs(ygzb_ctx* ctx, const uint8_t* const* d_src_ptr, uint8_t* const* d_dst_ptr, int sw, int sh, int spitch,
                         int dw, int dh, int dpitch, int count);
 int launch_detect(ygzb_frames* f, int n, bool have_occupied);
+int build_tile_maps(ygzb_frames* f);
 int launch_describe_store(ygzb_frames* f, int n);
 int launch_describe_list(ygzb_frames* f, int n, const int32_t* d_slot_of, int total, const double* d_x, const double* d_y,
                          const uint8_t* d_level, float* d_angle, uint8_t* d_desc);

@@ -21,19 +21,27 @@
 //     first = min (raster << 32 | score bits)          -> the earliest candidate and its score
 //     best  = max (orderable(score) << 32 | ~raster)   -> the best non-NaN score, earliest on ties
 // and merge_cells_kernel replays the level order.  All f32 maths is unfused (-fmad=false).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace ygzb {
 
 namespace {
 
-constexpr int kSmW = 96;            // smem tile pitch : x in [x0-8, x0+88)
+constexpr int kSmW = 112;           // smem tile pitch : x in [x0-16, x0+96); the TMA needs a 16-byte aligned start column
+constexpr int kSmX = 15;            // byte offset of region column rx = 0 (pixel x0 - 1) inside a smem row
 constexpr int kSmH = kTileH + 10;   // 50 rows         : y in [y0-5, y0+45)
 constexpr int kScW = kTileW + 2;    // score region 82 x 42 : tile + 1 px ring
 constexpr int kScH = kTileH + 2;
 constexpr int kScPitch = 84;
 constexpr int kMaxTileCells = 512;
 constexpr unsigned long long kEmptyFirst = ~0ull;
+
+// TMA descriptors of the levels whose tiles are fetched with cp.async.bulk.tensor (kernel parameter space)
+struct TileMaps {
+    CUtensorMap m[3];
+};
 
 struct DetectArgs {
     const uint8_t* pyr;
@@ -44,6 +52,7 @@ struct DetectArgs {
     unsigned long long* first_key;
     int32_t* stats;
     Geometry g;
+    int tma_levels;  // levels [0, tma_levels) stage their tile through the TMA
 };
 
 __device__ __forceinline__ bool has_run10(unsigned m16) {
@@ -139,8 +148,11 @@ __device__ __forceinline__ float shi_tomasi_from_sums(int sxx, int syy, int sxy)
     return __fmul_rn(0.5f, __fsub_rn(s, __fsqrt_rn(disc)));
 }
 
-__global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
-    __shared__ __align__(16) uint8_t s_img[kSmH * kSmW];
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a, const CUtensorMap* __restrict__ tmaps) {
+    __shared__ __align__(128) uint8_t s_img[kSmH * kSmW];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ __align__(16) uint8_t s_score[kScH * kScPitch];
     __shared__ uint16_t s_list[kScH * kScW];
     __shared__ unsigned long long s_best[kMaxTileCells];
@@ -168,23 +180,50 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
         s_best[i] = 0ull;
         s_first[i] = kEmptyFirst;
     }
-    // stage tile + halo, zero outside the image (never used: FAST stays 3 px inside, Shi-Tomasi
-    // returns 0 when its window touches the border)
-    for (int i = tid; i < kSmH * (kSmW / 4); i += 256) {
-        const int r = i / (kSmW / 4), k = i - r * (kSmW / 4);
-        const int y = y0 - 5 + r, x = x0 - 8 + 4 * k;
-        uint32_t v = 0;
-        if (y >= 0 && y < lv.h) {
-            const uint8_t* row = img + (size_t)y * lv.pitch;
-            if (x >= 0 && x + 3 < lv.w) {
-                v = *reinterpret_cast<const uint32_t*>(row + x);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x + j >= 0 && x + j < lv.w) v |= (uint32_t)row[x + j] << (8 * j);
-            }
+    // stage tile + halo, zero outside the image (never used: FAST stays 3 px inside, Shi-Tomasi returns 0 when its
+    // window touches the border).  Levels with a TMA descriptor fetch the whole 112 x 50 box with ONE
+    // cp.async.bulk.tensor issued by one thread (out-of-bounds elements are zero-filled by the hardware); the
+    // other levels (narrower than the box) use plain word loads.
+    if (L < a.tma_levels) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        reinterpret_cast<uint32_t*>(s_img)[i] = v;
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bar = smem_u32(&s_bar), dst = smem_u32(s_img);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kSmH * kSmW)) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmaps + L)), "r"(x0 - 16), "r"(y0 - 5), "r"(a.slots[item]), "r"(bar)
+                : "memory");
+        }
+        // every thread waits for the transaction bytes to land (phase 0 of the barrier)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done) : "r"(smem_u32(&s_bar)) : "memory");
+        }
+    } else {
+        for (int i = tid; i < kSmH * (kSmW / 4); i += 256) {
+            const int r = i / (kSmW / 4), k = i - r * (kSmW / 4);
+            const int y = y0 - 5 + r, x = x0 - 16 + 4 * k;
+            uint32_t v = 0;
+            if (y >= 0 && y < lv.h) {
+                const uint8_t* row = img + (size_t)y * lv.pitch;
+                if (x >= 0 && x + 3 < lv.w) {
+                    v = *reinterpret_cast<const uint32_t*>(row + x);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j >= 0 && x + j < lv.w) v |= (uint32_t)row[x + j] << (8 * j);
+                }
+            }
+            reinterpret_cast<uint32_t*>(s_img)[i] = v;
+        }
     }
     __syncthreads();
 
@@ -203,8 +242,8 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
         constexpr int kGroups = (kScW + 3) / 4;  // 21 groups of 4 pixels per region row
         for (int gi = tid; gi < kScH * kGroups; gi += 256) {
             const int ry = gi / kGroups, rx0 = (gi - ry * kGroups) * 4;
-            // word-aligned base of the centre row: pixel rx0 sits at byte offset rx0 + 7 = (rx0 + 4) + 3
-            const uint32_t* rowc = reinterpret_cast<const uint32_t*>(s_img + (ry + 4) * kSmW + rx0 + 4);
+            // word-aligned base of the centre row: pixel rx0 sits at byte offset rx0 + 15 = (rx0 + 12) + 3
+            const uint32_t* rowc = reinterpret_cast<const uint32_t*>(s_img + (ry + 4) * kSmW + rx0 + 12);
             constexpr int W = kSmW / 4;  // words per smem row
             const uint32_t c0 = rowc[0], c1 = rowc[1], c2 = rowc[2];
             const uint32_t ctr = __funnelshift_r(c0, c1, 24);
@@ -238,7 +277,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
         const int rx_lo = max(0, 4 - x0), rx_hi = min(kScW, lv.w - 2 - x0);   // x = x0 - 1 + rx in [3, w - 3)
         const int ry_lo = max(0, 4 - y0), ry_hi = min(kScH, lv.h - 2 - y0);
         for (int ry = ry_lo + warp_; ry < ry_hi; ry += 8) {
-            const uint8_t* row = s_img + (ry + 4) * kSmW + 7;
+            const uint8_t* row = s_img + (ry + 4) * kSmW + kSmX;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
                 const int rx = pass * 32 + lane_;
@@ -265,7 +304,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     for (int i = tid; i < n_quick; i += 256) {
         const int idx = s_quick[i];
         const int ry = idx / kScW, rx = idx - ry * kScW;
-        if (fast_is_corner<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7), g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
+        if (fast_is_corner<kSmW>(s_img + (ry + 4) * kSmW + (rx + kSmX), g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
     }
     __syncthreads();
     const int n_corner = s_n;
@@ -274,7 +313,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
     for (int i = tid; i < n_corner; i += 256) {
         const int idx = s_list[i];
         const int ry = idx / kScW, rx = idx - ry * kScW;
-        s_score[ry * kScPitch + rx] = (uint8_t)fast_score<kSmW>(s_img + (ry + 4) * kSmW + (rx + 7));
+        s_score[ry * kScPitch + rx] = (uint8_t)fast_score<kSmW>(s_img + (ry + 4) * kSmW + (rx + kSmX));
     }
     __syncthreads();
 
@@ -318,7 +357,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a) {
             const int x = x0 - 1 + rx, y = y0 - 1 + ry;
             float score = 0.f;
             if (!(x - 4 < 1 || x + 4 >= lv.w - 1 || y - 4 < 1 || y + 4 >= lv.h - 1)) {  // warp-uniform
-                const uint8_t* q = s_img + (ry + 4 + (lane >> 2) - 4) * kSmW + (rx + 7 + (lane & 3) * 2 - 4);
+                const uint8_t* q = s_img + (ry + 4 + (lane >> 2) - 4) * kSmW + (rx + kSmX + (lane & 3) * 2 - 4);
                 const int dx0 = (int)q[1] - (int)q[-1], dy0 = (int)q[kSmW] - (int)q[-kSmW];
                 const int dx1 = (int)q[2] - (int)q[0], dy1 = (int)q[kSmW + 1] - (int)q[-kSmW + 1];
                 const int sxx = __reduce_add_sync(0xFFFFFFFFu, dx0 * dx0 + dx1 * dx1);
@@ -496,13 +535,61 @@ int launch_detect(ygzb_frames* f, int n, bool have_occupied) {
     dim3 grid(g.tile_begin[g.n_levels], n);
     {
         ProfScope ps(ctx, kStageFastCells);
-        fast_cells_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+        a.tma_levels = f->tma_levels;
+        fast_cells_kernel<<<grid, 256, 0, ctx->stream>>>(a, reinterpret_cast<const CUtensorMap*>(f->d_tile_maps));
     }
     YGZB_LAUNCHED(ctx);
     ProfScope ps(ctx, kStageMergeCells);
     merge_cells_kernel<<<n, 1024, 0, ctx->stream>>>(f->d_best_key, f->d_first_key, f->d_slots, g, f->d_count, f->d_fx,
                                                     f->d_fy, f->d_flevel, f->d_fscore, f->d_fcell);
     YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+// CUtensorMap descriptors for the FAST tile fetch.  cuTensorMapEncodeTiled is a driver-API entry point; it is resolved
+// through the runtime (cudaGetDriverEntryPoint), so the library does not link against libcuda.
+int build_tile_maps(ygzb_frames* f) {
+    ygzb_ctx* ctx = f->ctx;
+    const Geometry& g = ctx->geo;
+    f->tma_levels = 0;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return YGZB_OK;  // no descriptor support: the kernel keeps its plain-load staging
+    }
+    const EncodeTiled encode = reinterpret_cast<EncodeTiled>(fn);
+    int n = 0;
+    for (int L = 0; L < g.n_levels && L < 3; ++L) {
+        if (g.lv[L].w < kSmW || g.lv[L].h < kSmH) break;  // the box must fit the level
+        const cuuint64_t dims[3] = {(cuuint64_t)g.lv[L].w, (cuuint64_t)g.lv[L].h, (cuuint64_t)f->capacity};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.lv[L].pitch, (cuuint64_t)ctx->slot_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)kSmW, (cuuint32_t)kSmH, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUtensorMap m;
+        const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, f->d_pyr + g.lv[L].off, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) break;
+        memcpy(f->tile_maps[L], &m, sizeof(m));
+        n = L + 1;
+    }
+    if (n > 0) {
+        // the descriptors live in global memory (written once by the host, read-only afterwards)
+        if (!f->d_tile_maps && cudaMalloc(&f->d_tile_maps, sizeof(f->tile_maps)) != cudaSuccess) {
+            cudaGetLastError();
+            return YGZB_OK;
+        }
+        if (cudaMemcpy(f->d_tile_maps, f->tile_maps, sizeof(f->tile_maps), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            return YGZB_OK;
+        }
+    }
+    f->tma_levels = n;
     return YGZB_OK;
 }
 
