@@ -63,7 +63,7 @@ constexpr int kPatchPitch = 48;            // 12 words: a 4-byte aligned span of
 // one warp: stage the (2*19+1)^2 neighbourhood of the centre in shared memory -- every entry is the
 // LINEAR-address tap c + dy*w + dx, so row wrap / outside-buffer semantics are preserved -- then
 // compute the angle (returned by all lanes) and descriptor byte `lane` from shared memory only.
-__device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy, const int8_t* __restrict__ s_pat,
+__device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy, const float* __restrict__ s_pat,
                                              uint8_t* __restrict__ s_patch, int lane, float* angle_out,
                                              uint8_t* byte_out) {
     const int c = cy * v.w + cx;
@@ -77,13 +77,16 @@ __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy,
         lin_first - align + (kPatchW - 1) * v.w + 44 <= n_px) {
         const uint8_t* src = v.img + (lin_first - align);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_patch);
+        // lanes 0-10 fetch the 11 words of an even row, lanes 11-21 those of the next row: 20 passes, one
+        // address increment per pass
+        if (lane < 22) {
+            const int half = lane >= 11, k = lane - 11 * half;
+            const uint8_t* p = src + (size_t)half * v.w + 4 * k;
+            uint32_t* d = dst + half * (kPatchPitch / 4) + k;
+            const size_t step = 2 * (size_t)v.w;
 #pragma unroll
-        for (int t = 0; t < 14; ++t) {
-            const int f = lane + 32 * t;
-            if (f < kPatchW * 11) {
-                const int r = f / 11, k = f - r * 11;
-                dst[r * (kPatchPitch / 4) + k] = *reinterpret_cast<const uint32_t*>(src + (size_t)r * v.w + 4 * k);
-            }
+            for (int t = 0; t < 19; ++t, p += step, d += 2 * (kPatchPitch / 4)) *d = *reinterpret_cast<const uint32_t*>(p);
+            if (!half) *d = *reinterpret_cast<const uint32_t*>(p);  // row 38
         }
         ctr_off += align;
     } else {
@@ -128,11 +131,12 @@ __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy,
     if (lane == 0) cs = (float)cos((double)rad);
     if (lane == 1) cs = (float)sin((double)rad);
     const float a = __shfl_sync(0xFFFFFFFFu, cs, 0), b = __shfl_sync(0xFFFFFFFFu, cs, 1);
-    const int8_t* pat = s_pat + lane * 32;
+    const float4* pat = reinterpret_cast<const float4*>(s_pat) + lane;   // [test k][lane]: conflict-free 128-bit reads
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+        const float4 pp = pat[32 * k];  // pattern converted to f32 once per CTA (I2F is an XU op)
+        const float x0 = pp.x, y0 = pp.y, x1 = pp.z, y1 = pp.w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
@@ -152,11 +156,16 @@ __global__ void __launch_bounds__(256) describe_store_kernel(const uint8_t* __re
                                                              const int16_t* __restrict__ fx, const int16_t* __restrict__ fy,
                                                              const uint8_t* __restrict__ flevel, float* __restrict__ fangle,
                                                              uint8_t* __restrict__ fdesc) {
-    __shared__ __align__(16) int8_t s_pat[1024];
+    __shared__ __align__(16) float s_pat[1024];
     __shared__ __align__(16) uint8_t s_patch[8][kPatchW * kPatchPitch];
-    reinterpret_cast<uint32_t*>(s_pat)[threadIdx.x] = reinterpret_cast<const uint32_t*>(g_orb_pattern)[threadIdx.x];
-    __syncthreads();
     const int slot = slots[blockIdx.y];
+    if (blockIdx.x * 8 >= count[slot]) return;  // most CTAs of the capacity-sized grid have no feature
+    // descriptor byte `lane` uses tests 8*lane .. 8*lane+7: store test (8*lane + k) at float4 index k*32 + lane
+    for (int t = threadIdx.x; t < 1024; t += 256) {
+        const int test = t >> 2, comp = t & 3;
+        s_pat[(((test & 7) * 32 + (test >> 3)) << 2) + comp] = (float)g_orb_pattern[t];
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= count[slot]) return;
@@ -176,9 +185,13 @@ __global__ void __launch_bounds__(256) describe_list_kernel(const uint8_t* __res
                                                             const double* __restrict__ px, const double* __restrict__ py,
                                                             const uint8_t* __restrict__ level, float* __restrict__ angle_out,
                                                             uint8_t* __restrict__ desc_out) {
-    __shared__ __align__(16) int8_t s_pat[1024];
+    __shared__ __align__(16) float s_pat[1024];
     __shared__ __align__(16) uint8_t s_patch[8][kPatchW * kPatchPitch];
-    reinterpret_cast<uint32_t*>(s_pat)[threadIdx.x] = reinterpret_cast<const uint32_t*>(g_orb_pattern)[threadIdx.x];
+    // descriptor byte `lane` uses tests 8*lane .. 8*lane+7: store test (8*lane + k) at float4 index k*32 + lane
+    for (int t = threadIdx.x; t < 1024; t += 256) {
+        const int test = t >> 2, comp = t & 3;
+        s_pat[(((test & 7) * 32 + (test >> 3)) << 2) + comp] = (float)g_orb_pattern[t];
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);

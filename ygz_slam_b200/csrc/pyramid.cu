@@ -95,6 +95,50 @@ __global__ void __launch_bounds__(256) pyrdown_ptr_kernel(const uint8_t* const* 
     pyrdown_tile(src_ptr[blockIdx.z], dst_ptr[blockIdx.z], src, dst);
 }
 
+// all remaining small levels of one frame in ONE CTA: level `first-1` (<= kTailBytes) is staged in shared memory and
+// every further level is produced from the previous one there (no launch or HBM round trip per level)
+constexpr int kTailBytes = 20480;
+
+__global__ void __launch_bounds__(256) pyrdown_tail_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot, Geometry g,
+                                                           int first) {
+    __shared__ uint8_t s_a[kTailBytes];
+    __shared__ uint8_t s_b[kTailBytes / 4 + 64];
+    uint8_t* slot = pyr + (size_t)(first_slot + blockIdx.x) * slot_stride;
+    const int tid = threadIdx.x;
+    uint8_t* cur = s_a;
+    uint8_t* nxt = s_b;
+    {
+        const LevelGeom s0 = g.lv[first - 1];
+        for (int i = tid; i < s0.w * s0.h; i += 256) {
+            const int y = i / s0.w, x = i - y * s0.w;
+            cur[i] = slot[s0.off + (size_t)y * s0.pitch + x];
+        }
+    }
+    __syncthreads();
+    for (int L = first; L < g.n_levels; ++L) {
+        const LevelGeom src = g.lv[L - 1], dst = g.lv[L];
+        for (int i = tid; i < dst.w * dst.h; i += 256) {
+            const int dy = i / dst.w, dx = i - dy * dst.w;
+            int acc = 0;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+                const uint8_t* row = cur + reflect101(2 * dy + ky - 2, src.h) * src.w;
+                const int wy = (ky == 0 || ky == 4) ? 1 : (ky == 2 ? 6 : 4);
+                const int hsum = row[reflect101(2 * dx - 2, src.w)] + 4 * row[reflect101(2 * dx - 1, src.w)] + 6 * row[2 * dx] +
+                                 4 * row[reflect101(2 * dx + 1, src.w)] + row[reflect101(2 * dx + 2, src.w)];
+                acc += wy * hsum;
+            }
+            const uint8_t v = (uint8_t)((acc + 128) >> 8);
+            nxt[i] = v;
+            slot[dst.off + (size_t)dy * dst.pitch + dx] = v;
+        }
+        __syncthreads();
+        uint8_t* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+}
+
 // cv::cvtColor(BGR2GRAY), 4 pixels per thread
 __global__ void __launch_bounds__(256) bgr2gray_kernel(const uint8_t* __restrict__ bgr, size_t bgr_frame_stride,
                                                        uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
@@ -125,10 +169,22 @@ int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr) {
                                                        ctx->slot_stride, first, g.lv[0]);
         YGZB_LAUNCHED(ctx);
     }
-    for (int L = 1; L < g.n_levels; ++L) {
+    // big levels: one tiled launch each; the small tail (source level <= kTailBytes): one CTA per frame for all of them
+    int tail = g.n_levels;
+    for (int L = 1; L < g.n_levels; ++L)
+        if (g.lv[L - 1].w * g.lv[L - 1].h <= kTailBytes) {
+            tail = L;
+            break;
+        }
+    for (int L = 1; L < tail; ++L) {
         dim3 grid((g.lv[L].w + kDW - 1) / kDW, (g.lv[L].h + kDH - 1) / kDH, count);
         ProfScope ps(ctx, kStagePyrDown);
         pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g.lv[L - 1], g.lv[L]);
+        YGZB_LAUNCHED(ctx);
+    }
+    if (tail < g.n_levels) {
+        ProfScope ps(ctx, kStagePyrDown);
+        pyrdown_tail_kernel<<<count, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g, tail);
         YGZB_LAUNCHED(ctx);
     }
     return YGZB_OK;
