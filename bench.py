@@ -496,13 +496,23 @@ def main() -> None:
             "pyrdown": None, "describe": B * kpf * (961 + 32), "merge_cells": None,
         }
         dom = max(shares, key=lambda k: shares[k]["share"])
+        # measured DRAM bytes per frame of each kernel from the committed `ncu --set full` captures (profiles/), scaled
+        # to this launch's frame count (null when the capture is missing)
+        try:
+            ncu_traffic = json.loads((ROOT / "profiles" / "r1_dram_traffic.json").read_text())
+        except Exception:  # noqa: BLE001
+            ncu_traffic = {}
+        ncu_key = {"match": "match_kernel", "fast_cells": "fast_cells", "describe": "describe_store"}
         roof = []
         for k in ("match", "fast_cells", "describe"):
             if k in shares and alg_bytes.get(k):
                 dur = shares[k]["ms_per_launch"] * 1e-3
                 ach = alg_bytes[k] / dur / 1e9
+                tr = ncu_traffic.get(ncu_key[k], {}).get("dram_bytes_per_frame")
                 roof.append({"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "traffic": None, "share_of_step": shares[k]["share"],
+                             "frac": ach / peak, "traffic": (tr * B if tr else None),
+                             "traffic_source": "profiles/r1_dram_traffic.json (dram__bytes_read+write per frame from ncu --set full at 128 frames) x frames per launch" if tr else None,
+                             "share_of_step": shares[k]["share"],
                              "us_per_launch": dur * 1e6, "algorithmic_bytes_per_launch": alg_bytes[k]})
         main_roof = next((r for r in roof if r["kernel"] == dom), roof[0] if roof else None)
         if main_roof is not None:
