@@ -149,6 +149,11 @@ int ygzb_hamming_pairs(ygzb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B
 int ygzb_align2d(ygzb_frames* f, int n, const int32_t* slot, const uint8_t* level, const uint8_t* ref_border,
                  const uint8_t* ref, int n_iter, double* uv, uint8_t* ok);
 
+/* replaces cvutils::Align1D (src/Algorithm/CVUtils.cpp:64-184; CVUtils.h:146-153): the same alignment restricted to
+ * the direction dir = (dx, dy) per patch (epipolar search); h_inv = the function's double& output.     */
+int ygzb_align1d(ygzb_frames* f, int n, const int32_t* slot, const uint8_t* level, const float* dir,
+                 const uint8_t* ref_border, const uint8_t* ref, int n_iter, double* uv, uint8_t* ok, double* h_inv);
+
 /* replaces Matcher::FindDirectProjection (src/Algorithm/Matcher.cpp:356-417, both overloads: the caller
  * supplies the reference depth) incl. GetWarpAffineMatrix / GetBestSearchLevel / WarpAffine
  * (:420-466, Matcher.h:123-134).  poses = n_poses x 12 (T_cw); candidate i uses frames ref_slot[i] /

@@ -60,5 +60,13 @@ int main(int argc, char** argv) {
         n_ok += m.FindDirectProjection(&f1, &f2, f, px, level);
     }
     printf("direct_projection ok %d\n", n_ok);
+    // Tracker: KLT from frame 1 to frame 2 (test_LK_tracking.cpp shape)
+    Tracker trk;
+    trk.SetReference(&f1);
+    trk.Track(&f2);
+    std::vector<Feature*> tf;
+    std::vector<Vector2d> tp;
+    trk.GetTrackedPixel(tf, tp);
+    printf("klt status %d tracked %zu mean_disparity %.4f\n", (int)trk.Status(), tp.size(), trk.MeanDisparity());
     return 0;
 }

@@ -47,3 +47,12 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     ok, err = lines[1].split()[2], float(lines[1].split()[-1])
     assert ok == "1" and err < 2e-3
     assert int(lines[2].split()[-1]) > 0.8 * len(range(0, f1["n"], 4))
+    # Tracker (KLT) against the oracle: same survivors (status && InFrame(pt, 20)) and mean disparity
+    ref = np.stack([f1["px"], f1["py"]], 1).astype(np.float32)
+    cur, st, _ = oracle.klt(g1, g2, ref, ref.copy())
+    inside = (cur[:, 0] >= 20) & (cur[:, 0] < 620) & (cur[:, 1] >= 20) & (cur[:, 1] < 460)
+    keep = st.astype(bool) & inside
+    parts = lines[3].split()
+    assert parts[2] == "1" and abs(int(parts[4]) - keep.sum()) <= 3
+    want_disp = np.linalg.norm(ref[keep] - cur[keep], axis=1).mean()
+    assert abs(float(parts[6]) - want_disp) < 0.02

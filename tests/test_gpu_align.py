@@ -115,3 +115,32 @@ def test_sparse_align_pose_tolerance(levels, max_level, ctx3, ctx8, oracle):
     T0, nm0, _ = fr.sparse_align([0], [1], [0, 0], np.zeros((0, 2)), np.zeros(0), np.zeros(0, np.uint8), T_ref[:1], T_ref[:1])
     assert nm0[0] == 0 and np.allclose(T0[0].reshape(-1), T_ref[0])
     fr.close()
+
+
+def test_align1d_bit_exact(ctx3, oracle):
+    """cvutils::Align1D (epipolar 1-D search): u, v, converged flag and h_inv against the oracle."""
+    s = _scene(oracle)
+    fr = ctx3.frames(2)
+    fr.upload(np.stack([s["g1"], s["g2"]]))
+    rng = np.random.default_rng(13)
+    n = 600
+    level = rng.integers(0, 3, n).astype(np.uint8)
+    ref_border = np.empty((n, 100), np.uint8)
+    uv = np.empty((n, 2))
+    ang = rng.uniform(0, 2 * np.pi, n)
+    direction = np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32)
+    for i in range(n):
+        img = oracle.level_view(s["p1"], 640, 480, 3, int(level[i]))
+        h, w = img.shape
+        x, y = int(rng.integers(6, w - 6)), int(rng.integers(6, h - 6))
+        ref_border[i] = img[y - 5:y + 5, x - 5:x + 5].reshape(-1)
+        t = rng.uniform(-2.5, 2.5)
+        uv[i] = (x + t * direction[i, 0], y + t * direction[i, 1])
+    got_uv, got_ok, got_h = fr.align1d(np.ones(n, np.int32), level, direction, ref_border, None, uv, 10)
+    for i in range(n):
+        img = oracle.level_view(s["p2"], 640, 480, 3, int(level[i]))
+        rb = ref_border[i].reshape(10, 10)
+        ok, u, v, hinv = oracle.align1d(img, float(direction[i, 0]), float(direction[i, 1]), rb, rb[1:9, 1:9], uv[i, 0], uv[i, 1], 10)
+        assert ok == got_ok[i] and u == got_uv[i, 0] and v == got_uv[i, 1], i
+        assert hinv == got_h[i] or (np.isinf(hinv) and np.isinf(got_h[i]))
+    fr.close()

@@ -37,7 +37,7 @@ EXPORTS = [
     "ygzb_profile_stage_name", "ygzb_host_alloc", "ygzb_host_free", "ygzb_frames_create", "ygzb_frames_destroy",
     "ygzb_frames_upload", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
-    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d",
+    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d", "ygzb_align1d",
     "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_pose_only",
     "ygzb_default_klt_params", "ygzb_klt",
 ]
@@ -408,7 +408,22 @@ def _sparse_align(self, ref_slot, cur_slot, offsets, px, depth, has_mp, T_ref, T
     return T.reshape(P, 3, 4), nm, iters
 
 
+def _align1d(self, slot, level, direction, ref_border, ref, uv, n_iter=10):
+    slot = np.ascontiguousarray(slot, np.int32)
+    n = len(slot)
+    rb = np.ascontiguousarray(ref_border, np.uint8).reshape(n, 100)
+    rf = None if ref is None else np.ascontiguousarray(ref, np.uint8).reshape(n, 64)
+    uv = np.ascontiguousarray(uv, np.float64).reshape(n, 2).copy()
+    ok = np.zeros(n, np.uint8)
+    hinv = np.zeros(n, np.float64)
+    self.ctx.check(self.lib.ygzb_align1d(self.h, n, _p(slot), _p(np.ascontiguousarray(level, np.uint8)),
+                                         _p(np.ascontiguousarray(direction, np.float32).reshape(n, 2)), _p(rb), _p(rf), n_iter, _p(uv),
+                                         _p(ok), _p(hinv)), "ygzb_align1d")
+    return uv, ok.astype(bool), hinv
+
+
 Frames.align2d = _align2d
+Frames.align1d = _align1d
 Frames.project_align = _project_align
 Frames.sparse_align = _sparse_align
 

@@ -141,6 +141,97 @@ __global__ void __launch_bounds__(128) align2d_kernel(const uint8_t* __restrict_
     ok[i] = s ? 1 : 0;
 }
 
+// cvutils::Align1D (reference src/Algorithm/CVUtils.cpp:64-184): 1-D search along `dir` (epipolar direction)
+__device__ bool align1d_dev(const LevelImg& im, float dirx, float diry, const uint8_t* __restrict__ pwb, const uint8_t* __restrict__ ref,
+                            int n_iter, double* pu, double* pv, double* h_inv) {
+    const int halfpatch = 4, patch = 8, ref_step = 10;
+    bool converged = false;
+    float H00 = 0.f, H01 = 0.f, H10 = 0.f, H11 = 0.f;
+    for (int y = 0; y < patch; ++y) {
+        const uint8_t* it = pwb + (y + 1) * ref_step + 1;
+        for (int x = 0; x < patch; ++x, ++it) {
+            const float J0 = (float)(0.5 * (dirx * (float)((int)it[1] - (int)it[-1]) + diry * (float)((int)it[ref_step] - (int)it[-ref_step])));
+            H00 += J0 * J0;
+            H01 += J0 * 1.f;
+            H10 += 1.f * J0;
+            H11 += 1.f;
+        }
+    }
+    *h_inv = 1.0 / H00 * patch * patch;
+    const float invdet = 1.0f / (H00 * H11 - H10 * H01);
+    const float I00 = H11 * invdet, I01 = -H01 * invdet, I10 = -H10 * invdet, I11 = H00 * invdet;
+    float mean_diff = 0.f;
+    float u = (float)*pu, v = (float)*pv;
+    const float min_update_squared = (float)(0.03 * 0.03);
+    float chi2 = 0.f, up0 = 0.f, up1 = 0.f;
+    for (int iter = 0; iter < n_iter; ++iter) {
+        const int u_r = (int)floorf(u), v_r = (int)floorf(v);
+        if (u_r < halfpatch || v_r < halfpatch || u_r >= im.w - halfpatch || v_r >= im.h - halfpatch) break;
+        if (isnan(u) || isnan(v)) return false;
+        const float sx = u - (float)u_r, sy = v - (float)v_r;
+        const float wTL = (float)((1.0 - sx) * (1.0 - sy));
+        const float wTR = (float)(sx * (1.0 - sy));
+        const float wBL = (float)((1.0 - sx) * sy);
+        const float wBR = sx * sy;
+        float new_chi2 = 0.f, J0 = 0.f, J1 = 0.f;
+        for (int y = 0; y < patch; ++y) {
+            const uint8_t* it = im.d + (size_t)(v_r + y - halfpatch) * im.pitch + (u_r - halfpatch);
+            const uint8_t* tb = pwb + (y + 1) * ref_step + 1;
+            for (int x = 0; x < patch; ++x) {
+                const float search_pixel = wTL * (float)it[x] + wTR * (float)it[x + 1] + wBL * (float)it[x + im.pitch] +
+                                           wBR * (float)it[x + im.pitch + 1];
+                const float res = search_pixel - (float)ref[y * patch + x] + mean_diff;
+                const float dv = (float)(0.5 * (dirx * (float)((int)tb[x + 1] - (int)tb[x - 1]) + diry * (float)((int)tb[x + ref_step] - (int)tb[x - ref_step])));
+                J0 -= res * dv;
+                J1 -= res;
+                new_chi2 += res * res;
+            }
+        }
+        if (iter > 0 && new_chi2 > chi2) {
+            u -= up0;
+            v -= up1;
+            break;
+        }
+        chi2 = new_chi2;
+        up0 = I00 * J0 + I01 * J1;
+        up1 = I10 * J0 + I11 * J1;
+        u += up0 * dirx;
+        v += up0 * diry;
+        mean_diff += up1;
+        if (up0 * up0 + up1 * up1 < min_update_squared) {
+            converged = true;
+            break;
+        }
+    }
+    *pu = (double)u;
+    *pv = (double)v;
+    return converged;
+}
+
+__global__ void __launch_bounds__(128) align1d_kernel(const uint8_t* __restrict__ pyr, size_t slot_stride, Geometry g, int n,
+                                                      const int32_t* __restrict__ slot, const uint8_t* __restrict__ level,
+                                                      const float* __restrict__ dir, const uint8_t* __restrict__ ref_border,
+                                                      const uint8_t* __restrict__ ref, int n_iter, double* __restrict__ uv,
+                                                      uint8_t* __restrict__ ok, double* __restrict__ h_inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t pwb[100], rp[64];
+    for (int k = 0; k < 100; ++k) pwb[k] = ref_border[(size_t)i * 100 + k];
+    if (ref) {
+        for (int k = 0; k < 64; ++k) rp[k] = ref[(size_t)i * 64 + k];
+    } else {
+        for (int y = 1; y < 9; ++y)
+            for (int x = 0; x < 8; ++x) rp[(y - 1) * 8 + x] = pwb[y * 10 + 1 + x];
+    }
+    const LevelImg im = level_img(pyr, slot_stride, slot[i], g, level[i]);
+    double u = uv[2 * i], v = uv[2 * i + 1], hi = 0;
+    const bool s = align1d_dev(im, dir[2 * i], dir[2 * i + 1], pwb, rp, n_iter, &u, &v, &hi);
+    uv[2 * i] = u;
+    uv[2 * i + 1] = v;
+    ok[i] = s ? 1 : 0;
+    h_inv[i] = hi;
+}
+
 struct CamF {
     float fx, fy, cx, cy;
 };
@@ -461,6 +552,17 @@ int launch_align2d(ygzb_frames* f, int n, const int32_t* d_slot, const uint8_t* 
     ProfScope ps(ctx, kStageAlign2D);
     align2d_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, ctx->geo, n, d_slot, d_level, d_ref_border,
                                                              d_ref, n_iter, d_uv, d_ok);
+    YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+int launch_align1d(ygzb_frames* f, int n, const int32_t* d_slot, const uint8_t* d_level, const float* d_dir, const uint8_t* d_ref_border,
+                   const uint8_t* d_ref, int n_iter, double* d_uv, uint8_t* d_ok, double* d_hinv) {
+    ygzb_ctx* ctx = f->ctx;
+    if (n <= 0) return YGZB_OK;
+    ProfScope ps(ctx, kStageAlign2D);
+    align1d_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, ctx->geo, n, d_slot, d_level, d_dir, d_ref_border,
+                                                             d_ref, n_iter, d_uv, d_ok, d_hinv);
     YGZB_LAUNCHED(ctx);
     return YGZB_OK;
 }

@@ -66,6 +66,44 @@ int ygzb_align2d(ygzb_frames* f, int n, const int32_t* slot, const uint8_t* leve
     return YGZB_OK;
 }
 
+int ygzb_align1d(ygzb_frames* f, int n, const int32_t* slot, const uint8_t* level, const float* dir, const uint8_t* ref_border,
+                 const uint8_t* ref, int n_iter, double* uv, uint8_t* ok, double* h_inv) {
+    if (!f || n < 0 || (n && (!slot || !level || !dir || !ref_border || !uv || !ok || !h_inv))) return YGZB_ERR_INVALID;
+    if (n == 0) return YGZB_OK;
+    ygzb_ctx* ctx = f->ctx;
+    cudaSetDevice(ctx->device);
+    TRY(check_slots(f, slot, n, "slot"));
+    for (int i = 0; i < n; ++i)
+        if (level[i] >= ctx->geo.n_levels) return set_error(ctx, YGZB_ERR_INVALID, "level[%d] out of range", i);
+    const size_t N = (size_t)n;
+    Carver sz(nullptr);
+    sz.take<int32_t>(N); sz.take<uint8_t>(N); sz.take<float>(2 * N); sz.take<uint8_t>(N * 100); sz.take<uint8_t>(N * 64); sz.take<double>(2 * N);
+    sz.take<uint8_t>(N); sz.take<double>(N);
+    void* buf = dev_scratch(ctx, 6, sz.bytes());
+    if (!buf) return YGZB_ERR_CUDA;
+    Carver c(buf);
+    int32_t* d_slot = c.take<int32_t>(N);
+    uint8_t* d_level = c.take<uint8_t>(N);
+    float* d_dir = c.take<float>(2 * N);
+    uint8_t* d_rb = c.take<uint8_t>(N * 100);
+    uint8_t* d_ref = c.take<uint8_t>(N * 64);
+    double* d_uv = c.take<double>(2 * N);
+    uint8_t* d_ok = c.take<uint8_t>(N);
+    double* d_h = c.take<double>(N);
+    TRY(h2d(ctx, d_slot, slot, N));
+    TRY(h2d(ctx, d_level, level, N));
+    TRY(h2d(ctx, d_dir, dir, 2 * N));
+    TRY(h2d(ctx, d_rb, ref_border, N * 100));
+    if (ref) TRY(h2d(ctx, d_ref, ref, N * 64));
+    TRY(h2d(ctx, d_uv, uv, 2 * N));
+    TRY(launch_align1d(f, n, d_slot, d_level, d_dir, d_rb, ref ? d_ref : nullptr, n_iter, d_uv, d_ok, d_h));
+    TRY(d2h(ctx, uv, d_uv, 2 * N));
+    TRY(d2h(ctx, ok, d_ok, N));
+    TRY(d2h(ctx, h_inv, d_h, N));
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return YGZB_OK;
+}
+
 int ygzb_project_align(ygzb_frames* f, int n, const int32_t* ref_slot, const int32_t* cur_slot, int n_poses, const double* poses,
                        const int32_t* ref_pose, const int32_t* cur_pose, const double* ref_px, const double* ref_depth,
                        const uint8_t* ref_level, double* cur_px, uint8_t* search_level, uint8_t* ok) {

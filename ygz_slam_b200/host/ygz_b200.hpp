@@ -4,6 +4,7 @@
 //
 //   ygz::FeatureDetector   include/ygz/Algorithm/FeatureDetector.h:43-101
 //   ygz::Matcher           include/ygz/Algorithm/Matcher.h:15-155
+//   ygz::Tracker           include/ygz/Algorithm/Tracker.h:11-76
 //   ygz::cvutils::Align2D  include/ygz/Algorithm/CVUtils.h:163-169
 //   ygz::SparseImgAlign    include/ygz/Algorithm/SparseImageAlign.h:12-58
 //   ygz::ba::*             include/ygz/Algorithm/BA.h:23-66
@@ -423,6 +424,95 @@ class Matcher {  // include/ygz/Algorithm/Matcher.h
     }
     std::unique_ptr<SparseImgAlign> _align;
     SE3 _TCR_esti;
+};
+
+class Tracker {  // include/ygz/Algorithm/Tracker.h:11-76
+  public:
+    enum TrackerStatusType { TRACK_NOT_READY, TRACK_GOOD, TRACK_LOST };
+    struct Option {
+        int _min_feature_tracking = 50;  // tracker.min_features (config/default.yaml:42)
+        double klt_win_size = 21.0;
+        int klt_max_iter = 30;
+        double klt_eps = 0.001;
+    } _option;
+    // Tracker.cpp:13-32
+    void SetReference(Frame* ref) {
+        if ((int)ref->_features.size() < _option._min_feature_tracking) {
+            _status = TRACK_NOT_READY;
+            return;
+        }
+        _ref = ref;
+        _curr = ref;
+        _status = TRACK_GOOD;
+        for (Feature* fea : ref->_features) {
+            _tracked_features.push_back(fea);
+            _px_curr.push_back({(float)fea->_pixel[0], (float)fea->_pixel[1]});
+        }
+    }
+    // Tracker.cpp:34-53
+    void Track(Frame* curr) {
+        if (_status != TRACK_GOOD) return;
+        _curr = curr;
+        TrackKLT();
+        if ((int)_px_curr.size() < _option._min_feature_tracking) _status = TRACK_LOST;
+    }
+    // Tracker.cpp:115-127
+    float MeanDisparity() const {
+        float mean = 0;
+        size_t i = 0;
+        for (auto it = _tracked_features.begin(); it != _tracked_features.end(); ++it, ++i) {
+            const double dx = (*it)->_pixel[0] - _px_curr[i].x, dy = (*it)->_pixel[1] - _px_curr[i].y;
+            mean += (float)std::sqrt(dx * dx + dy * dy);
+        }
+        return mean / _tracked_features.size();
+    }
+    // Tracker.cpp:55-63
+    void GetTrackedPixel(std::vector<Feature*>& feature1, std::vector<Vector2d>& pixels2) const {
+        for (Feature* f : _tracked_features) feature1.push_back(f);
+        for (auto& p : _px_curr) pixels2.push_back(Vector2d(p.x, p.y));
+    }
+    TrackerStatusType Status() const { return _status; }
+  private:
+    struct P2f { float x, y; };
+    // Tracker.cpp:65-113: cv::calcOpticalFlowPyrLK(ref.pyr[0], cur.pyr[0], ..., 21x21, 4, (COUNT+EPS, 30, 0.001), USE_INITIAL_FLOW)
+    void TrackKLT() {
+        auto& rt = b200::Runtime::Get();
+        const int n = (int)_tracked_features.size();
+        if (!n) return;
+        std::vector<float> ref(2 * (size_t)n), cur(2 * (size_t)n), err(n);
+        std::vector<uint8_t> status(n);
+        int i = 0;
+        for (Feature* f : _tracked_features) {
+            ref[2 * i] = (float)f->_pixel[0];
+            ref[2 * i + 1] = (float)f->_pixel[1];
+            cur[2 * i] = _px_curr[i].x;
+            cur[2 * i + 1] = _px_curr[i].y;
+            ++i;
+        }
+        ygzb_klt_params prm;
+        ygzb_default_klt_params(&prm);
+        prm.win = (int)_option.klt_win_size;
+        prm.max_iter = _option.klt_max_iter;
+        prm.eps = _option.klt_eps;
+        const int32_t rs = b200::SlotOf(_ref), cs = b200::SlotOf(_curr), off[2] = {0, n};
+        rt.Check(ygzb_klt(rt.frames(), 1, &rs, &cs, off, ref.data(), cur.data(), status.data(), err.data(), &prm), "ygzb_klt");
+        _px_curr.clear();
+        i = 0;
+        for (auto it = _tracked_features.begin(); it != _tracked_features.end(); ++i) {
+            const Vector2d p(cur[2 * i], cur[2 * i + 1]);
+            if (!status[i] || !_curr->InFrame(p, 20)) {
+                it = _tracked_features.erase(it);
+            } else {
+                ++it;
+                _px_curr.push_back({cur[2 * i], cur[2 * i + 1]});
+            }
+        }
+    }
+    Frame* _ref = nullptr;
+    Frame* _curr = nullptr;
+    std::list<Feature*> _tracked_features;
+    std::vector<P2f> _px_curr;
+    TrackerStatusType _status = TRACK_NOT_READY;
 };
 
 namespace ba {  // include/ygz/Algorithm/BA.h:23-66
