@@ -58,12 +58,73 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 constexpr int kPatchR = 19;                 // EDGE_THRESHOLD: rotated pattern taps stay within +-19 px
 constexpr int kPatchW = 2 * kPatchR + 1;    // 39
-constexpr int kPatchPitch = 48;            // 12 words: a 4-byte aligned span of 44 B always covers the 39 B row
+constexpr int kPatchPitch = 44;            // 11 words: a 4-byte aligned span of 44 B always covers the 39 B row, and an
+                                           // odd word pitch spreads the rows of a column over all 32 banks
+constexpr int kFeatPerWarp = 4;            // features per warp and CTA visit (amortises the pattern staging)
+
+// IC_Angle weights.  Lane l < 31 owns row v = l - 15 of the radius-15 disc and reads it as the 8 words covering
+// columns -15 .. 16; word k, byte j is column c = 4k + j - 15.  Row |v| is limited to |c| <= umax[|v|], so the
+// column weights (c for m10, 1 for the row sum) are zeroed outside: tables [k][|v|] of packed s8x4 / u8x4.
+struct IcTables {
+    uint32_t wu[8 * 16];
+    uint32_t w1[8 * 16];
+};
+
+constexpr IcTables make_ic_tables() {
+    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    IcTables t{};
+    for (int k = 0; k < 8; ++k)
+        for (int av = 0; av < 16; ++av) {
+            uint32_t wu = 0, w1 = 0;
+            for (int j = 0; j < 4; ++j) {
+                const int c = 4 * k + j - 15;
+                const int ac = c < 0 ? -c : c;
+                if (ac <= kUmax[av]) {
+                    wu |= (uint32_t)(uint8_t)(int8_t)c << (8 * j);
+                    w1 |= 1u << (8 * j);
+                }
+            }
+            t.wu[k * 16 + av] = wu;
+            t.w1[k * 16 + av] = w1;
+        }
+    return t;
+}
+
+__device__ const IcTables g_ic_tables = make_ic_tables();
+
+struct DescribeSmem {
+    float pat[1024];   // [test k of the byte][lane] as float4 (x0, y0, x1, y1)
+    uint32_t ic_wu[8 * 16];
+    uint32_t ic_w1[8 * 16];
+    uint8_t patch[8][kPatchW * kPatchPitch];
+};
+
+__device__ __forceinline__ void stage_tables(DescribeSmem& sm) {
+    // descriptor byte `lane` uses tests 8*lane .. 8*lane+7: store test (8*lane + k) at float4 index k*32 + lane
+    for (int t = threadIdx.x; t < 1024; t += 256) {
+        const int test = t >> 2, comp = t & 3;
+        sm.pat[(((test & 7) * 32 + (test >> 3)) << 2) + comp] = (float)g_orb_pattern[t];
+    }
+    if (threadIdx.x < 128) {
+        sm.ic_wu[threadIdx.x] = g_ic_tables.wu[threadIdx.x];
+        sm.ic_w1[threadIdx.x] = g_ic_tables.w1[threadIdx.x];
+    }
+}
+
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+// cvRound of a small f32 (|x| < 2^22) without the quarter-rate F2I: adding 1.5 * 2^23 leaves the integer, rounded
+// to nearest-even, in the low mantissa bits
+__device__ __forceinline__ int round_small(float x) { return __float_as_int(__fadd_rn(x, 12582912.f)) - 0x4B400000; }
 
 // one warp: stage the (2*19+1)^2 neighbourhood of the centre in shared memory -- every entry is the
 // LINEAR-address tap c + dy*w + dx, so row wrap / outside-buffer semantics are preserved -- then
 // compute the angle (returned by all lanes) and descriptor byte `lane` from shared memory only.
-__device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy, const float* __restrict__ s_pat,
+__device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy, const DescribeSmem& sm,
                                              uint8_t* __restrict__ s_patch, int lane, float* angle_out,
                                              uint8_t* byte_out) {
     const int c = cy * v.w + cx;
@@ -102,45 +163,54 @@ __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy,
     __syncwarp();
     const uint8_t* ctr = s_patch + ctr_off;
 
-    // IC_Angle: lane <-> column u = lane - 15 of the radius-15 disc
-    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    const int u = lane - 15;
+    // IC_Angle: m10 = sum u * I(u, v), m01 = sum v * I(u, v) over the disc.  Lane <-> row v = lane - 15; the row is
+    // read as 9 aligned words, shifted to start at column -15, and reduced with two byte dot products per word
+    // (integer sums: any order gives the reference's result).
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        m10 = u * (int)ctr[u];
-        const int au = u < 0 ? -u : u;
+        const int vr = lane - 15, av = vr < 0 ? -vr : vr;
+        const int o = ctr_off + vr * kPatchPitch - 15;          // byte offset of column -15 of this row
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s_patch) + (o >> 2);
+        const int sh = (o & 3) * 8;
+        int rowsum = 0;
+        uint32_t lo = w[0];
 #pragma unroll
-        for (int vv = 1; vv <= 15; ++vv) {
-            if (au <= kUmax[vv]) {
-                const int plus = ctr[vv * kPatchPitch + u], minus = ctr[-vv * kPatchPitch + u];
-                m01 += vv * (plus - minus);
-                m10 += u * (plus + minus);
-            }
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t hi = w[k + 1];
+            const uint32_t px = __funnelshift_r(lo, hi, sh);
+            m10 = dp4a_us(px, sm.ic_wu[k * 16 + av], m10);
+            rowsum = dp4a_us(px, sm.ic_w1[k * 16 + av], rowsum);
+            lo = hi;
         }
+        m01 = vr * rowsum;
     }
     m10 = __reduce_add_sync(0xFFFFFFFFu, m10);
     m01 = __reduce_add_sync(0xFFFFFFFFu, m01);
     const float angle = fast_atan2_deg((float)m01, (float)m10);
     *angle_out = angle;
 
-    // ComputeOrbDescriptor: a = cos, b = sin of angle * (float)(CV_PI/180.f); f64 evaluation on two
-    // lanes only (the FP64 pipe is narrow), broadcast by shuffle
+    // ComputeOrbDescriptor: a = cos, b = sin of angle * (float)(CV_PI/180.f); one f64 sincos on one lane (the FP64
+    // pipe is narrow), broadcast by shuffle
     constexpr float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float rad = __fmul_rn(angle, factorPI);
-    float cs = 0.f;
-    if (lane == 0) cs = (float)cos((double)rad);
-    if (lane == 1) cs = (float)sin((double)rad);
-    const float a = __shfl_sync(0xFFFFFFFFu, cs, 0), b = __shfl_sync(0xFFFFFFFFu, cs, 1);
-    const float4* pat = reinterpret_cast<const float4*>(s_pat) + lane;   // [test k][lane]: conflict-free 128-bit reads
+    float cs_c = 0.f, cs_s = 0.f;
+    if (lane == 0) {
+        double sd, cd;
+        sincos((double)rad, &sd, &cd);
+        cs_c = (float)cd;
+        cs_s = (float)sd;
+    }
+    const float a = __shfl_sync(0xFFFFFFFFu, cs_c, 0), b = __shfl_sync(0xFFFFFFFFu, cs_s, 0);
+    const float4* pat = reinterpret_cast<const float4*>(sm.pat) + lane;   // [test k][lane]: conflict-free 128-bit reads
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float4 pp = pat[32 * k];  // pattern converted to f32 once per CTA (I2F is an XU op)
+        const float4 pp = pat[32 * k];  // pattern converted to f32 once per CTA
         const float x0 = pp.x, y0 = pp.y, x1 = pp.z, y1 = pp.w;
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int r0 = round_small(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = round_small(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = round_small(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = round_small(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
         // |r|, |c| <= 19 for every pattern point (|p| <= 13*sqrt(2) < 19), so the staged window covers it
         const int t0 = ctr[r0 * kPatchPitch + c0], t1 = ctr[r1 * kPatchPitch + c1];
         val |= (t0 < t1) << k;
@@ -156,27 +226,25 @@ __global__ void __launch_bounds__(256) describe_store_kernel(const uint8_t* __re
                                                              const int16_t* __restrict__ fx, const int16_t* __restrict__ fy,
                                                              const uint8_t* __restrict__ flevel, float* __restrict__ fangle,
                                                              uint8_t* __restrict__ fdesc) {
-    __shared__ __align__(16) float s_pat[1024];
-    __shared__ __align__(16) uint8_t s_patch[8][kPatchW * kPatchPitch];
+    __shared__ __align__(16) DescribeSmem sm;
     const int slot = slots[blockIdx.y];
-    if (blockIdx.x * 8 >= count[slot]) return;  // most CTAs of the capacity-sized grid have no feature
-    // descriptor byte `lane` uses tests 8*lane .. 8*lane+7: store test (8*lane + k) at float4 index k*32 + lane
-    for (int t = threadIdx.x; t < 1024; t += 256) {
-        const int test = t >> 2, comp = t & 3;
-        s_pat[(((test & 7) * 32 + (test >> 3)) << 2) + comp] = (float)g_orb_pattern[t];
-    }
+    const int n = count[slot];
+    if (blockIdx.x * (8 * kFeatPerWarp) >= n) return;  // most CTAs of the capacity-sized grid have no feature
+    stage_tables(sm);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= count[slot]) return;
-    const size_t o = (size_t)slot * g.n_cells + i;
-    const int L = flevel[o];
-    LevelView v{pyr + (size_t)slot * slot_stride + g.lv[L].off, g.lv[L].w, g.lv[L].h, g.lv[L].pitch};
-    float angle;
-    uint8_t byte;
-    describe_one(v, fx[o], fy[o], s_pat, s_patch[threadIdx.x >> 5], lane, &angle, &byte);
-    fdesc[o * 32 + lane] = byte;
-    if (lane == 0) fangle[o] = angle;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = 0; r < kFeatPerWarp; ++r) {
+        const int i = blockIdx.x * (8 * kFeatPerWarp) + r * 8 + warp;
+        if (i >= n) return;
+        const size_t o = (size_t)slot * g.n_cells + i;
+        const int L = flevel[o];
+        LevelView v{pyr + (size_t)slot * slot_stride + g.lv[L].off, g.lv[L].w, g.lv[L].h, g.lv[L].pitch};
+        float angle;
+        uint8_t byte;
+        describe_one(v, fx[o], fy[o], sm, sm.patch[warp], lane, &angle, &byte);
+        fdesc[o * 32 + lane] = byte;
+        if (lane == 0) fangle[o] = angle;
+    }
 }
 
 // caller-supplied features (ComputeAngleAndDescriptor): full-res double pixels, centre = cvRound(px / 2^L)
@@ -185,27 +253,24 @@ __global__ void __launch_bounds__(256) describe_list_kernel(const uint8_t* __res
                                                             const double* __restrict__ px, const double* __restrict__ py,
                                                             const uint8_t* __restrict__ level, float* __restrict__ angle_out,
                                                             uint8_t* __restrict__ desc_out) {
-    __shared__ __align__(16) float s_pat[1024];
-    __shared__ __align__(16) uint8_t s_patch[8][kPatchW * kPatchPitch];
-    // descriptor byte `lane` uses tests 8*lane .. 8*lane+7: store test (8*lane + k) at float4 index k*32 + lane
-    for (int t = threadIdx.x; t < 1024; t += 256) {
-        const int test = t >> 2, comp = t & 3;
-        s_pat[(((test & 7) * 32 + (test >> 3)) << 2) + comp] = (float)g_orb_pattern[t];
-    }
+    __shared__ __align__(16) DescribeSmem sm;
+    stage_tables(sm);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= total) return;
-    const int L = level[i];
-    const int slot = slot_of[i];
-    LevelView v{pyr + (size_t)slot * slot_stride + g.lv[L].off, g.lv[L].w, g.lv[L].h, g.lv[L].pitch};
-    const double scale = (double)(1 << L);
-    const int cx = __double2int_rn(px[i] / scale), cy = __double2int_rn(py[i] / scale);
-    float angle;
-    uint8_t byte;
-    describe_one(v, cx, cy, s_pat, s_patch[threadIdx.x >> 5], lane, &angle, &byte);
-    desc_out[(size_t)i * 32 + lane] = byte;
-    if (lane == 0) angle_out[i] = angle;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = 0; r < kFeatPerWarp; ++r) {
+        const int i = blockIdx.x * (8 * kFeatPerWarp) + r * 8 + warp;
+        if (i >= total) return;
+        const int L = level[i];
+        const int slot = slot_of[i];
+        LevelView v{pyr + (size_t)slot * slot_stride + g.lv[L].off, g.lv[L].w, g.lv[L].h, g.lv[L].pitch};
+        const double scale = (double)(1 << L);
+        const int cx = __double2int_rn(px[i] / scale), cy = __double2int_rn(py[i] / scale);
+        float angle;
+        uint8_t byte;
+        describe_one(v, cx, cy, sm, sm.patch[warp], lane, &angle, &byte);
+        desc_out[(size_t)i * 32 + lane] = byte;
+        if (lane == 0) angle_out[i] = angle;
+    }
 }
 
 }  // namespace
@@ -213,7 +278,7 @@ __global__ void __launch_bounds__(256) describe_list_kernel(const uint8_t* __res
 int launch_describe_store(ygzb_frames* f, int n) {
     ygzb_ctx* ctx = f->ctx;
     const Geometry& g = ctx->geo;
-    dim3 grid((g.n_cells + 7) / 8, n);
+    dim3 grid((g.n_cells + 8 * kFeatPerWarp - 1) / (8 * kFeatPerWarp), n);
     ProfScope ps(ctx, kStageDescribe);
     describe_store_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, f->d_slots, g, f->d_count, f->d_fx,
                                                          f->d_fy, f->d_flevel, f->d_fangle, f->d_fdesc);
@@ -227,7 +292,7 @@ int launch_describe_list(ygzb_frames* f, int n, const int32_t* d_slot_of, int to
     ygzb_ctx* ctx = f->ctx;
     if (total <= 0) return YGZB_OK;
     ProfScope ps(ctx, kStageDescribe);
-    describe_list_kernel<<<(total + 7) / 8, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, ctx->geo, d_slot_of, total,
+    describe_list_kernel<<<(total + 8 * kFeatPerWarp - 1) / (8 * kFeatPerWarp), 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, ctx->geo, d_slot_of, total,
                                                                    d_x, d_y, d_level, d_angle, d_desc);
     YGZB_LAUNCHED(ctx);
     return YGZB_OK;

@@ -137,6 +137,35 @@ __device__ __forceinline__ int fast_score(const uint8_t* __restrict__ c) {
     return max(best_bright, -best_dark) - 1;
 }
 
+// The same closed form on packed halves: every ring pixel v becomes the word (255 - v) << 16 | v, so ONE
+// VIMNMX.U16x2 takes the running minimum of v (low half) and of 255 - v, i.e. the running maximum of v (high
+// half), at once: 16 IMAD to pack + 56 packed min/max instead of 112 scalar ones.  Values stay <= 255, so the
+// 16-bit lanes never interact.  Returns the score for ANY pixel (below the threshold = not a corner).
+template <int PITCH>
+__device__ __forceinline__ int fast_score_packed(const uint8_t* __restrict__ c) {
+    constexpr int RDX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr int RDY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    const int p = *c;
+    uint32_t P[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) P[i] = (uint32_t)c[RDY[i] * PITCH + RDX[i]] * 0xFFFF0001u + 0x00FF0000u;
+    uint32_t m2[16], m4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m2[i] = __vminu2(P[i], P[(i + 1) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m4[i] = __vminu2(m2[i], m2[(i + 2) & 15]);
+    uint32_t best = 0;  // (max over arcs of min v) | (max over arcs of min (255 - v)) << 16
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const uint32_t a0 = __vimin3_u16x2(m4[i], m4[(i + 4) & 15], m2[(i + 8) & 15]);          // arc i .. i+9
+        const uint32_t a1 = __vimin3_u16x2(m4[i + 1], m4[(i + 5) & 15], m2[(i + 9) & 15]);
+        best = __vimax3_u16x2(best, a0, a1);
+    }
+    const int bright = (int)(best & 0xFFFFu) - p;       // largest arc minimum of v - p
+    const int dark = p + (int)(best >> 16) - 255;       // p - smallest arc maximum of v
+    return max(bright, dark) - 1;
+}
+
 // FeatureDetector::ShiTomasiScore tail: the three sums over the 8x8 box are integers < 2^24, so their
 // f32 values are exact whatever the summation order; the rest follows the reference operation by operation.
 __device__ __forceinline__ float shi_tomasi_from_sums(int sxx, int syy, int sxy) {
@@ -150,20 +179,22 @@ __device__ __forceinline__ float shi_tomasi_from_sums(int sxx, int syy, int sxy)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a, const CUtensorMap* __restrict__ tmaps) {
+__global__ void __launch_bounds__(256, 5) fast_cells_kernel(const DetectArgs a, const CUtensorMap* __restrict__ tmaps) {
     __shared__ __align__(128) uint8_t s_img[kSmH * kSmW];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ __align__(16) uint8_t s_score[kScH * kScPitch];
     __shared__ uint16_t s_list[kScH * kScW];
     __shared__ unsigned long long s_best[kMaxTileCells];
     __shared__ unsigned long long s_first[kMaxTileCells];
-    __shared__ uint16_t s_cand[kTileW * kTileH / 4];
     __shared__ uint16_t s_quick[kScH * kScW];
     __shared__ uint8_t s_lutx[kTileW], s_luty[kTileH];
     __shared__ int s_n, s_ncorner, s_nnonmax, s_ncand, s_nquick;
+    uint16_t* const s_cand = s_quick;  // the prefilter list is dead once the scores are written (<= 800 candidates)
 
     const Geometry& g = a.g;
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     int L = 0;
     while (L + 1 < g.n_levels && (int)blockIdx.x >= g.tile_begin[L + 1]) ++L;
     const int t = blockIdx.x - g.tile_begin[L];
@@ -173,10 +204,14 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a, con
     const int item = blockIdx.y;
     const uint8_t* __restrict__ img = a.pyr + (size_t)a.slots[item] * a.slot_stride + lv.off;
     const bool selectable = L < g.n_sel_levels;
+    const int scale = 1 << L;
+    const int cpt_x = kTileW * scale / g.cell_size;          // grid cells per tile row / column at this level
+    const int cpt_y = kTileH * scale / g.cell_size;
+    const int n_tile_cells = selectable ? cpt_x * cpt_y : 0;  // <= kMaxTileCells (checked by build_geometry)
 
     if (tid == 0) s_n = s_ncorner = s_nnonmax = s_ncand = s_nquick = 0;
     for (int i = tid; i < kScH * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(s_score)[i] = 0;
-    for (int i = tid; i < kMaxTileCells; i += 256) {
+    for (int i = tid; i < n_tile_cells; i += 256) {
         s_best[i] = 0ull;
         s_first[i] = kEmptyFirst;
     }
@@ -227,145 +262,195 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a, con
     }
     __syncthreads();
 
-    // pass A0/A1: cheap necessary condition on tile + 1 px ring; survivors (a few %) are compacted so that the
-    // exact segment test (pass A2) runs on dense warps.
-    // Measured (profiles/r1_fast_cells_v3.txt): the sign-blind SWAR prefilter passes ~30 % more pixels than the exact
-    // pair test and its per-pixel append loop eats the saving (1.67 ms vs 1.57 ms per 512 frames), so the exact
-    // per-pixel test below stays the default until the append is warp-aggregated.
-    constexpr bool kUseSwarPrefilter = false;
-    if (kUseSwarPrefilter && g.threshold <= 126) {
+    // pass A: cheap necessary condition on tile + 1 px ring; the survivors (10-20 % on textured frames) are
+    // compacted so that the exact score (pass B) runs on dense warps.
+    // region pixel (rx, ry) = image pixel (x0 - 1 + rx, y0 - 1 + ry); FAST is defined for x in [3, w-3), y in [3, h-3)
+    const int rx_lo = max(0, 4 - x0), rx_hi = min(kScW, lv.w - 2 - x0);
+    const int ry_lo = max(0, 4 - y0), ry_hi = min(kScH, lv.h - 2 - y0);
+    if (g.threshold <= 126) {
         // SIMD-within-a-register prefilter, 4 horizontally adjacent pixels per thread: for each of the four opposite
         // ring pairs at least one pixel must differ from the centre by more than the threshold (|v - p| > b, sign
-        // ignored: a superset of the exact pair test).  VABSDIFF4 gives the four byte differences in one instruction,
-        // ((x & 0x7f7f7f7f) + (127-b)*0x01010101 | x) & 0x80808080 flags the bytes > b without inter-byte carries.
+        // ignored: a superset of "a 10-arc holds a pixel of every opposite pair").  VABSDIFF4 gives the four byte
+        // differences in one instruction, ((x & 0x7f7f7f7f) + (127-b)*0x01010101 | x) & 0x80808080 flags the bytes > b
+        // without inter-byte carries.  Survivors are appended with one shared-memory atomic per warp and iteration
+        // (four ballots give every flagged byte its slot).
         const uint32_t kadd = 0x01010101u * (uint32_t)(127 - g.threshold);
         constexpr int kGroups = (kScW + 3) / 4;  // 21 groups of 4 pixels per region row
-        for (int gi = tid; gi < kScH * kGroups; gi += 256) {
+        constexpr int W = kSmW / 4;              // words per smem row
+        for (int g0 = 0; g0 < kScH * kGroups; g0 += 256) {  // block-uniform trip count
+            const int gi = g0 + tid;
             const int ry = gi / kGroups, rx0 = (gi - ry * kGroups) * 4;
-            // word-aligned base of the centre row: pixel rx0 sits at byte offset rx0 + 15 = (rx0 + 12) + 3
-            const uint32_t* rowc = reinterpret_cast<const uint32_t*>(s_img + (ry + 4) * kSmW + rx0 + 12);
-            constexpr int W = kSmW / 4;  // words per smem row
-            const uint32_t c0 = rowc[0], c1 = rowc[1], c2 = rowc[2];
-            const uint32_t ctr = __funnelshift_r(c0, c1, 24);
+            uint32_t m = 0;
+            if (ry >= ry_lo && ry < ry_hi) {
+                // word-aligned base of the centre row: pixel rx0 sits at byte offset rx0 + 15 = (rx0 + 12) + 3
+                const uint32_t* rowc = reinterpret_cast<const uint32_t*>(s_img + (ry + 4) * kSmW + rx0 + 12);
+                const uint32_t c0 = rowc[0], c1 = rowc[1], c2 = rowc[2];
+                const uint32_t ctr = __funnelshift_r(c0, c1, 24);
 #define FLAG(v) ((((__vabsdiffu4((v), ctr) & 0x7f7f7f7fu) + kadd) | __vabsdiffu4((v), ctr)) & 0x80808080u)
-            uint32_t m = FLAG(c0) | FLAG(__funnelshift_r(c1, c2, 16));                               // ring 12 (-3,0) | 4 (+3,0)
-            if (m) {
-                const uint32_t* ru = rowc - 3 * W;
-                const uint32_t* rd = rowc + 3 * W;
-                m &= FLAG(__funnelshift_r(ru[0], ru[1], 24)) | FLAG(__funnelshift_r(rd[0], rd[1], 24));  // ring 8 | 0
-            }
-            if (m) {
-                const uint32_t* ru = rowc - 2 * W;
-                const uint32_t* rd = rowc + 2 * W;
-                const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
-                m &= FLAG(__funnelshift_r(u0, u1, 8)) | FLAG(__funnelshift_r(d1, d2, 8));   // ring 10 (-2,-2) | 2 (+2,+2)
-                m &= FLAG(__funnelshift_r(u1, u2, 8)) | FLAG(__funnelshift_r(d0, d1, 8));   // ring 6 (+2,-2) | 14 (-2,+2)
-            }
+                m = FLAG(c0) | FLAG(__funnelshift_r(c1, c2, 16));                                   // ring 12 (-3,0) | 4 (+3,0)
+                {
+                    const uint32_t* ru = rowc - 3 * W;
+                    const uint32_t* rd = rowc + 3 * W;
+                    m &= FLAG(__funnelshift_r(ru[0], ru[1], 24)) | FLAG(__funnelshift_r(rd[0], rd[1], 24));  // ring 8 | 0
+                }
+                {
+                    const uint32_t* ru = rowc - 2 * W;
+                    const uint32_t* rd = rowc + 2 * W;
+                    const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
+                    m &= FLAG(__funnelshift_r(u0, u1, 8)) | FLAG(__funnelshift_r(d1, d2, 8));   // ring 10 (-2,-2) | 2 (+2,+2)
+                    m &= FLAG(__funnelshift_r(u1, u2, 8)) | FLAG(__funnelshift_r(d0, d1, 8));   // ring 6 (+2,-2) | 14 (-2,+2)
+                }
 #undef FLAG
-            while (m) {
-                const int j = (__ffs(m) - 1) >> 3;  // byte index = pixel within the group
-                m &= m - 1;
-                const int rx = rx0 + j;
-                const int x = x0 - 1 + rx, y = y0 - 1 + ry;
-                if (rx < kScW && x >= 3 && x < lv.w - 3 && y >= 3 && y < lv.h - 3) s_quick[atomicAdd(&s_nquick, 1)] = (uint16_t)(ry * kScW + rx);
+                if (rx0 < rx_lo || rx0 + 4 > rx_hi) {  // group straddles the valid column range: keep bytes [lo, hi)
+                    const int lo = min(max(rx_lo - rx0, 0), 4), hi = min(max(rx_hi - rx0, 0), 4);
+                    const unsigned long long keep = ((1ull << (8 * hi)) - 1ull) & ~((1ull << (8 * lo)) - 1ull);
+                    m &= hi > lo ? (uint32_t)keep : 0u;
+                }
+            }
+            const unsigned b0 = __ballot_sync(0xFFFFFFFFu, m & 0x80u), b1 = __ballot_sync(0xFFFFFFFFu, m & 0x8000u);
+            const unsigned b2 = __ballot_sync(0xFFFFFFFFu, m & 0x800000u), b3 = __ballot_sync(0xFFFFFFFFu, m & 0x80000000u);
+            if (b0 | b1 | b2 | b3) {
+                const int n0 = __popc(b0), n1 = n0 + __popc(b1), n2 = n1 + __popc(b2), tot = n2 + __popc(b3);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nquick, tot);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                const int idx0 = ry * kScW + rx0;
+                if (m & 0x80u) s_quick[base + __popc(b0 & lt_mask)] = (uint16_t)idx0;
+                if (m & 0x8000u) s_quick[base + n0 + __popc(b1 & lt_mask)] = (uint16_t)(idx0 + 1);
+                if (m & 0x800000u) s_quick[base + n1 + __popc(b2 & lt_mask)] = (uint16_t)(idx0 + 2);
+                if (m & 0x80000000u) s_quick[base + n2 + __popc(b3 & lt_mask)] = (uint16_t)(idx0 + 3);
             }
         }
     } else {
-        // exact opposite-pair test: one warp per region row (no index divisions), lanes over the 82 columns in three
-        // passes, survivors appended with one shared-memory atomic per warp and pass
-        const int lane_ = tid & 31, warp_ = tid >> 5;
-        const int rx_lo = max(0, 4 - x0), rx_hi = min(kScW, lv.w - 2 - x0);   // x = x0 - 1 + rx in [3, w - 3)
-        const int ry_lo = max(0, 4 - y0), ry_hi = min(kScH, lv.h - 2 - y0);
+        // thresholds the byte trick cannot express: exact opposite-pair test, one warp per region row, lanes over the
+        // 82 columns in three passes, survivors appended with one shared-memory atomic per warp and pass
+        const int warp_ = tid >> 5;
         for (int ry = ry_lo + warp_; ry < ry_hi; ry += 8) {
             const uint8_t* row = s_img + (ry + 4) * kSmW + kSmX;
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
-                const int rx = pass * 32 + lane_;
+                const int rx = pass * 32 + lane;
                 bool cand = false;
                 if (rx >= rx_lo && rx < rx_hi) cand = fast_quick_test<kSmW>(row + rx, g.threshold);
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
                 if (m) {
                     int base = 0;
-                    if (lane_ == 0) base = atomicAdd(&s_nquick, __popc(m));
+                    if (lane == 0) base = atomicAdd(&s_nquick, __popc(m));
                     base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (cand) s_quick[base + __popc(m & ((1u << lane_) - 1u))] = (uint16_t)(ry * kScW + rx);
+                    if (cand) s_quick[base + __popc(m & lt_mask)] = (uint16_t)(ry * kScW + rx);
                 }
             }
         }
     }
     // grid-cell lookup tables of this tile (local cell column / row of every tile pixel)
     if (selectable) {
-        const int sc_ = 1 << L;
-        if (tid < kTileW) s_lutx[tid] = (uint8_t)(((x0 + tid) * sc_) / g.cell_size - (x0 * sc_) / g.cell_size);
-        else if (tid < kTileW + kTileH) s_luty[tid - kTileW] = (uint8_t)(((y0 + tid - kTileW) * sc_) / g.cell_size - (y0 * sc_) / g.cell_size);
+        if (tid < kTileW) s_lutx[tid] = (uint8_t)(((x0 + tid) * scale) / g.cell_size - (x0 * scale) / g.cell_size);
+        else if (tid < kTileW + kTileH) s_luty[tid - kTileW] = (uint8_t)(((y0 + tid - kTileW) * scale) / g.cell_size - (y0 * scale) / g.cell_size);
     }
     __syncthreads();
+
+    // pass B: exact score of every survivor; a pixel is a corner iff its score reaches the threshold (the score is the
+    // largest threshold at which the segment test still holds).  Corners go into the dense score tile (0 = not a
+    // corner; scores are >= threshold > 0) and into the corner list.
     const int n_quick = s_nquick;
-    for (int i = tid; i < n_quick; i += 256) {
-        const int idx = s_quick[i];
-        const int ry = idx / kScW, rx = idx - ry * kScW;
-        if (fast_is_corner<kSmW>(s_img + (ry + 4) * kSmW + (rx + kSmX), g.threshold)) s_list[atomicAdd(&s_n, 1)] = (uint16_t)idx;
+    for (int i0 = 0; i0 < n_quick; i0 += 256) {  // block-uniform trip count
+        const int i = i0 + tid;
+        bool corner = false;
+        int idx = 0;
+        if (i < n_quick) {
+            idx = s_quick[i];
+            const int ry = idx / kScW, rx = idx - ry * kScW;
+            const int s = fast_score_packed<kSmW>(s_img + (ry + 4) * kSmW + (rx + kSmX));
+            if (s >= g.threshold) {
+                corner = true;
+                s_score[ry * kScPitch + rx] = (uint8_t)s;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, corner);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (corner) s_list[base + __popc(bal & lt_mask)] = (uint16_t)idx;
+        }
     }
     __syncthreads();
     const int n_corner = s_n;
 
-    // pass B: score of every corner into the dense score tile (0 = not a corner; scores are >= threshold > 0)
-    for (int i = tid; i < n_corner; i += 256) {
-        const int idx = s_list[i];
-        const int ry = idx / kScW, rx = idx - ry * kScW;
-        s_score[ry * kScPitch + rx] = (uint8_t)fast_score<kSmW>(s_img + (ry + 4) * kSmW + (rx + kSmX));
-    }
-    __syncthreads();
-
     // pass C1: 3x3 non-max on the tile interior; survivors that pass InFrame / grid / occupancy become
     // cell candidates (at most one per 2x2 block: neighbours with equal or larger score kill each other)
-    const int scale = 1 << L;
-    const int cpt_x = kTileW * scale / g.cell_size;          // cells per tile row at this level
     const int cx0 = x0 * scale / g.cell_size, cy0 = y0 * scale / g.cell_size;
-    for (int i = tid; i < n_corner; i += 256) {
-        const int idx = s_list[i];
-        const int ry = idx / kScW, rx = idx - ry * kScW;
-        if (rx < 1 || rx > kTileW || ry < 1 || ry > kTileH) continue;  // ring pixels belong to a neighbour tile
-        atomicAdd(&s_ncorner, 1);
-        const uint8_t* sc = s_score + ry * kScPitch + rx;
-        const int s = *sc;
-        // fast_nonmax_3x3: dropped if any 8-neighbour corner scores >= s
-        if (sc[-1] >= s || sc[1] >= s || sc[-kScPitch - 1] >= s || sc[-kScPitch] >= s || sc[-kScPitch + 1] >= s ||
-            sc[kScPitch - 1] >= s || sc[kScPitch] >= s || sc[kScPitch + 1] >= s)
-            continue;
-        atomicAdd(&s_nnonmax, 1);
-        if (!selectable) continue;
-        const int x = x0 - 1 + rx, y = y0 - 1 + ry;
-        // Frame::InFrame(Vector2d(x,y), 20, L): x/2^L >= 20 && x/2^L < W-20 (exact in integers)
-        if (x < 20 * scale || x >= (g.W - 20) * scale || y < 20 * scale || y >= (g.H - 20) * scale) continue;
-        const int gy = cy0 + s_luty[ry - 1], gx = cx0 + s_lutx[rx - 1];
-        const int k = gy * g.grid_cols + gx;
-        if (k >= g.n_cells) continue;
-        if (a.occupied && a.occupied[(size_t)item * g.n_cells + k]) continue;
-        s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)idx;
+    {
+        int my_corner = 0, my_nonmax = 0;
+        for (int i = tid; i < n_corner; i += 256) {
+            const int idx = s_list[i];
+            const int ry = idx / kScW, rx = idx - ry * kScW;
+            if (rx < 1 || rx > kTileW || ry < 1 || ry > kTileH) continue;  // ring pixels belong to a neighbour tile
+            ++my_corner;
+            const uint8_t* sc = s_score + ry * kScPitch + rx;
+            const int s = *sc;
+            // fast_nonmax_3x3: dropped if any 8-neighbour corner scores >= s
+            if (sc[-1] >= s || sc[1] >= s || sc[-kScPitch - 1] >= s || sc[-kScPitch] >= s || sc[-kScPitch + 1] >= s ||
+                sc[kScPitch - 1] >= s || sc[kScPitch] >= s || sc[kScPitch + 1] >= s)
+                continue;
+            ++my_nonmax;
+            if (!selectable) continue;
+            const int x = x0 - 1 + rx, y = y0 - 1 + ry;
+            // Frame::InFrame(Vector2d(x,y), 20, L): x/2^L >= 20 && x/2^L < W-20 (exact in integers)
+            if (x < 20 * scale || x >= (g.W - 20) * scale || y < 20 * scale || y >= (g.H - 20) * scale) continue;
+            const int gy = cy0 + s_luty[ry - 1], gx = cx0 + s_lutx[rx - 1];
+            const int k = gy * g.grid_cols + gx;
+            if (k >= g.n_cells) continue;
+            if (a.occupied && a.occupied[(size_t)item * g.n_cells + k]) continue;
+            s_cand[atomicAdd(&s_ncand, 1)] = (uint16_t)idx;
+        }
+        // the per-level statistics need one shared-memory atomic per warp, not per corner
+        my_corner = __reduce_add_sync(0xFFFFFFFFu, my_corner);
+        my_nonmax = __reduce_add_sync(0xFFFFFFFFu, my_nonmax);
+        if (lane == 0 && my_corner) {
+            atomicAdd(&s_ncorner, my_corner);
+            atomicAdd(&s_nnonmax, my_nonmax);
+        }
     }
     __syncthreads();
 
-    // pass C2: one warp per candidate: Shi-Tomasi on the staged tile (2 pixels per lane, integer sums are
-    // exact so the f32 result equals the reference's sequential accumulation), then the two cell keys
+    // pass C2: eight lanes per candidate (four candidates per warp): Shi-Tomasi on the staged tile, one row of the
+    // 8x8 window per lane (the integer sums are exact, so the f32 result equals the reference's sequential
+    // accumulation whatever the order), then the two cell keys
     {
-        const int lane = tid & 31, warp = tid >> 5;
+        const int sub = lane & 7;
         const int n_cand = s_ncand;
-        for (int i = warp; i < n_cand; i += 8) {
-            const int idx = s_cand[i];
+        for (int i0 = (tid >> 5) * 4; i0 < n_cand; i0 += 32) {  // warp-uniform trip count
+            const int i = i0 + (lane >> 3);
+            const bool active = i < n_cand;
+            const int idx = active ? s_cand[i] : 0;
             const int ry = idx / kScW, rx = idx - ry * kScW;
             const int x = x0 - 1 + rx, y = y0 - 1 + ry;
-            float score = 0.f;
-            if (!(x - 4 < 1 || x + 4 >= lv.w - 1 || y - 4 < 1 || y + 4 >= lv.h - 1)) {  // warp-uniform
-                const uint8_t* q = s_img + (ry + 4 + (lane >> 2) - 4) * kSmW + (rx + kSmX + (lane & 3) * 2 - 4);
-                const int dx0 = (int)q[1] - (int)q[-1], dy0 = (int)q[kSmW] - (int)q[-kSmW];
-                const int dx1 = (int)q[2] - (int)q[0], dy1 = (int)q[kSmW + 1] - (int)q[-kSmW + 1];
-                const int sxx = __reduce_add_sync(0xFFFFFFFFu, dx0 * dx0 + dx1 * dx1);
-                const int syy = __reduce_add_sync(0xFFFFFFFFu, dy0 * dy0 + dy1 * dy1);
-                const int sxy = __reduce_add_sync(0xFFFFFFFFu, dx0 * dy0 + dx1 * dy1);
-                score = shi_tomasi_from_sums(sxx, syy, sxy);
+            const bool inside = active && !(x - 4 < 1 || x + 4 >= lv.w - 1 || y - 4 < 1 || y + 4 >= lv.h - 1);
+            int sxx = 0, syy = 0, sxy = 0;
+            if (inside) {
+                // window row y - 4 + sub, columns x - 4 .. x + 3
+                const uint8_t* q = s_img + (ry + 4 + sub - 4) * kSmW + (rx + kSmX - 4);
+                int left = q[-1], mid = q[0];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int right = q[c + 1];
+                    const int dx = right - left, dy = (int)q[c + kSmW] - (int)q[c - kSmW];
+                    sxx += dx * dx;
+                    syy += dy * dy;
+                    sxy += dx * dy;
+                    left = mid;
+                    mid = right;
+                }
             }
-            if (lane == 0) {
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) {
+                sxx += __shfl_xor_sync(0xFFFFFFFFu, sxx, o);
+                syy += __shfl_xor_sync(0xFFFFFFFFu, syy, o);
+                sxy += __shfl_xor_sync(0xFFFFFFFFu, sxy, o);
+            }
+            if (active && sub == 0) {
+                const float score = inside ? shi_tomasi_from_sums(sxx, syy, sxy) : 0.f;
                 const int li = (int)s_luty[ry - 1] * cpt_x + (int)s_lutx[rx - 1];
                 const unsigned raster = (unsigned)(y * lv.w + x);
                 atomicMin(&s_first[li], ((unsigned long long)raster << 32) | __float_as_uint(score));
@@ -382,9 +467,8 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const DetectArgs a, con
         if (s_nnonmax) atomicAdd(st + 1, s_nnonmax);
     }
     if (selectable) {
-        const int cpt_y = kTileH * scale / g.cell_size;
         const size_t base = ((size_t)item * g.n_sel_levels + L) * g.n_cells;
-        for (int li = tid; li < cpt_x * cpt_y; li += 256) {
+        for (int li = tid; li < n_tile_cells; li += 256) {
             const int gy = cy0 + li / cpt_x, gx = cx0 + li % cpt_x;
             if (gy >= g.grid_rows || gx >= g.grid_cols) continue;
             a.best_key[base + gy * g.grid_cols + gx] = s_best[li];
@@ -536,6 +620,12 @@ int launch_detect(ygzb_frames* f, int n, bool have_occupied) {
     {
         ProfScope ps(ctx, kStageFastCells);
         a.tma_levels = f->tma_levels;
+        // 5 CTAs x 31 KB per SM: ask for the large shared-memory carve-out (the tiles live in smem, L1 is barely used)
+        static bool carveout_set = false;
+        if (!carveout_set) {
+            cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+        }
         fast_cells_kernel<<<grid, 256, 0, ctx->stream>>>(a, reinterpret_cast<const CUtensorMap*>(f->d_tile_maps));
     }
     YGZB_LAUNCHED(ctx);

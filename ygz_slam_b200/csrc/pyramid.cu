@@ -82,6 +82,72 @@ __device__ __forceinline__ void pyrdown_tile(const uint8_t* __restrict__ sp, uin
     }
 }
 
+// ---- streaming variant for the large levels (source width a multiple of 8) ------------------------------------
+// No shared memory: a thread owns 4 adjacent destination pixels (one 32-bit store) of a strip of kStripRows
+// destination rows and walks down the source rows with a rolling window of five horizontally filtered rows in
+// registers.  All arithmetic is packed u16x2: the horizontal sums are <= 16*255 and the vertical ones <= 256*255,
+// so two pixels share one 32-bit register without carries between the halves.  Source bytes come in as one
+// aligned 8-byte load (the thread's own 8 source columns) plus the 4-byte words left and right of it (L1 hits:
+// they are the neighbours' columns); reflect-101 at the left / right image border is a byte permute of the
+// thread's own columns instead of a load, at the top / bottom it is a row index.
+// HBM traffic = source read once + destination written once; neighbouring strips share 3 source rows through L1/L2.
+constexpr int kStripRows = 8;
+
+struct HRow {
+    uint32_t lo, hi;  // (h0, h1) and (h2, h3): horizontal [1 4 6 4 1] sums of the thread's 4 destination columns
+};
+
+__device__ __forceinline__ HRow hfilter_row(const uint8_t* __restrict__ row, int k, bool first, bool last) {
+    const uint2 m = *reinterpret_cast<const uint2*>(row + 8 * k);                       // columns 8k .. 8k+7
+    // a: bytes 2,3 = columns 8k-2, 8k-1 (reflected to columns 2, 1 at the left border)
+    const uint32_t a = first ? __byte_perm(m.x, 0, 0x1200) : *reinterpret_cast<const uint32_t*>(row + 8 * k - 4);
+    // r: byte 0 = column 8k+8 (reflected to column 8k+6 at the right border)
+    const uint32_t r = last ? (m.y >> 16) : *reinterpret_cast<const uint32_t*>(row + 8 * k + 8);
+    const uint32_t e_lo = __byte_perm(m.x, 0, 0x4240), e_hi = __byte_perm(m.y, 0, 0x4240);  // even columns (e0,e1) (e2,e3)
+    const uint32_t o_lo = __byte_perm(m.x, 0, 0x4341), o_hi = __byte_perm(m.y, 0, 0x4341);  // odd columns  (o0,o1) (o2,o3)
+    const uint32_t em_lo = __byte_perm(e_lo, a, 0x1016);          // (e-1, e0)
+    const uint32_t e12 = __funnelshift_r(e_lo, e_hi, 16);         // (e1, e2) = left neighbours of hi = right neighbours of lo
+    const uint32_t ep_hi = __byte_perm(e_hi, r, 0x3432);          // (e3, e4)
+    const uint32_t om_lo = __byte_perm(o_lo, a, 0x1017);          // (o-1, o0)
+    const uint32_t om_hi = __funnelshift_r(o_lo, o_hi, 16);       // (o1, o2)
+    HRow h;
+    h.lo = em_lo + e12 + 6u * e_lo + 4u * (om_lo + o_lo);
+    h.hi = e12 + ep_hi + 6u * e_hi + 4u * (om_hi + o_hi);
+    return h;
+}
+
+__device__ __forceinline__ uint32_t vfilter_pack(const HRow& h0, const HRow& h1, const HRow& h2, const HRow& h3, const HRow& h4) {
+    const uint32_t lo = h0.lo + h4.lo + 4u * (h1.lo + h3.lo) + 6u * h2.lo + 0x00800080u;
+    const uint32_t hi = h0.hi + h4.hi + 4u * (h1.hi + h3.hi) + 6u * h2.hi + 0x00800080u;
+    return __byte_perm(lo, hi, 0x7531);  // byte 1 of every 16-bit half = (v + 128) >> 8
+}
+
+__global__ void __launch_bounds__(256) pyrdown_stream_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
+                                                             LevelGeom src, LevelGeom dst, int strips) {
+    const int tpr = src.w >> 3;  // threads per row
+    const int id = blockIdx.x * 256 + threadIdx.x;
+    const int strip = id / tpr, k = id - strip * tpr;
+    if (strip >= strips) return;
+    uint8_t* slot = pyr + (size_t)(first_slot + blockIdx.y) * slot_stride;
+    const uint8_t* __restrict__ sp = slot + src.off;
+    uint8_t* __restrict__ dp = slot + dst.off + 4 * k;
+    const bool first = k == 0, last = k == tpr - 1;
+    const int dy0 = strip * kStripRows;
+    const int sh = src.h;
+    auto hrow = [&](int sy) { return hfilter_row(sp + (size_t)reflect101(sy, sh) * src.pitch, k, first, last); };
+    HRow h0 = hrow(2 * dy0 - 2), h1 = hrow(2 * dy0 - 1), h2 = hrow(2 * dy0);
+#pragma unroll
+    for (int j = 0; j < kStripRows; ++j) {
+        const int dy = dy0 + j;
+        if (dy >= dst.h) break;
+        const HRow h3 = hrow(2 * dy + 1), h4 = hrow(2 * dy + 2);
+        *reinterpret_cast<uint32_t*>(dp + (size_t)dy * dst.pitch) = vfilter_pack(h0, h1, h2, h3, h4);
+        h0 = h2;
+        h1 = h3;
+        h2 = h4;
+    }
+}
+
 // one level of `count` consecutive slots
 __global__ void __launch_bounds__(256) pyrdown_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot,
                                                       LevelGeom src, LevelGeom dst) {
@@ -177,9 +243,15 @@ int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr) {
             break;
         }
     for (int L = 1; L < tail; ++L) {
-        dim3 grid((g.lv[L].w + kDW - 1) / kDW, (g.lv[L].h + kDH - 1) / kDH, count);
         ProfScope ps(ctx, kStagePyrDown);
-        pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g.lv[L - 1], g.lv[L]);
+        if (g.lv[L - 1].w % 8 == 0 && g.lv[L - 1].w >= 16 && g.lv[L - 1].h >= 2) {
+            const int strips = (g.lv[L].h + kStripRows - 1) / kStripRows;
+            dim3 grid((strips * (g.lv[L - 1].w / 8) + 255) / 256, count);
+            pyrdown_stream_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g.lv[L - 1], g.lv[L], strips);
+        } else {
+            dim3 grid((g.lv[L].w + kDW - 1) / kDW, (g.lv[L].h + kDH - 1) / kDH, count);
+            pyrdown_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g.lv[L - 1], g.lv[L]);
+        }
         YGZB_LAUNCHED(ctx);
     }
     if (tail < g.n_levels) {
