@@ -154,6 +154,18 @@ int build_geometry(ygzb_ctx* ctx) {
                              p.cell_size, kTileW, kTileH, L);
     }
     if (g.n_cells > 8 * 1024) return set_error(ctx, YGZB_ERR_INVALID, "grid has too many cells");
+    // magic multipliers for the divisions of the FAST kernel (see common.cuh)
+    g.cell_magic = (unsigned)(((1ull << 24) + p.cell_size - 1) / p.cell_size);
+    for (int L = 0; L < p.n_levels; ++L) {
+        g.tiles_x_magic[L] = (unsigned)(((1ull << 24) + g.tiles_x[L] - 1) / g.tiles_x[L]);
+        const long long n_tiles = g.tile_begin[L + 1] - g.tile_begin[L];
+        if (n_tiles * g.tiles_x[L] >= (1ll << 24)) return set_error(ctx, YGZB_ERR_INVALID, "image too large for the tile index arithmetic");
+        if (L < g.n_sel_levels) {
+            g.cpt_x[L] = (kTileW << L) / p.cell_size;
+            g.cpt_y[L] = (kTileH << L) / p.cell_size;
+            if ((long long)(kTileW << L) * p.cell_size >= (1ll << 24)) return set_error(ctx, YGZB_ERR_INVALID, "cell arithmetic out of range");
+        }
+    }
     return YGZB_OK;
 }
 

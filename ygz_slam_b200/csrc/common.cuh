@@ -33,7 +33,16 @@ struct Geometry {
     int threshold;
     int tile_begin[kMaxLevels + 1];  // prefix sums of tiles per level
     int tiles_x[kMaxLevels];
+    // exact division by small runtime constants without the ~20-instruction integer divide: n / d == (n * magic) >> 24
+    // with magic = ceil(2^24 / d), valid while n * d < 2^24 (checked by build_geometry)
+    unsigned tiles_x_magic[kMaxLevels];
+    unsigned cell_magic;
+    int cpt_x[kMaxLevels], cpt_y[kMaxLevels];  // grid cells per FAST tile row / column on the selectable levels
 };
+
+__host__ __device__ __forceinline__ unsigned div_magic(unsigned n, unsigned magic) {
+    return (unsigned)(((unsigned long long)n * magic) >> 24);
+}
 
 }  // namespace ygzb
 

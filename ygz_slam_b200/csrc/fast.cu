@@ -198,16 +198,15 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const DetectArgs a, 
     int L = 0;
     while (L + 1 < g.n_levels && (int)blockIdx.x >= g.tile_begin[L + 1]) ++L;
     const int t = blockIdx.x - g.tile_begin[L];
-    const int ty = t / g.tiles_x[L], tx = t - ty * g.tiles_x[L];
+    const int ty = (int)div_magic((unsigned)t, g.tiles_x_magic[L]), tx = t - ty * g.tiles_x[L];
     const int x0 = tx * kTileW, y0 = ty * kTileH;
     const LevelGeom lv = g.lv[L];
     const int item = blockIdx.y;
     const uint8_t* __restrict__ img = a.pyr + (size_t)a.slots[item] * a.slot_stride + lv.off;
     const bool selectable = L < g.n_sel_levels;
     const int scale = 1 << L;
-    const int cpt_x = kTileW * scale / g.cell_size;          // grid cells per tile row / column at this level
-    const int cpt_y = kTileH * scale / g.cell_size;
-    const int n_tile_cells = selectable ? cpt_x * cpt_y : 0;  // <= kMaxTileCells (checked by build_geometry)
+    const int cpt_x = g.cpt_x[L], cpt_y = g.cpt_y[L];        // grid cells per tile row / column at this level (0: not selectable)
+    const int n_tile_cells = cpt_x * cpt_y;                   // <= kMaxTileCells (checked by build_geometry)
 
     if (tid == 0) s_n = s_ncorner = s_nnonmax = s_ncand = s_nquick = 0;
     for (int i = tid; i < kScH * kScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(s_score)[i] = 0;
@@ -268,57 +267,97 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const DetectArgs a, 
     const int rx_lo = max(0, 4 - x0), rx_hi = min(kScW, lv.w - 2 - x0);
     const int ry_lo = max(0, 4 - y0), ry_hi = min(kScH, lv.h - 2 - y0);
     if (g.threshold <= 126) {
-        // SIMD-within-a-register prefilter, 4 horizontally adjacent pixels per thread: for each of the four opposite
-        // ring pairs at least one pixel must differ from the centre by more than the threshold (|v - p| > b, sign
-        // ignored: a superset of "a 10-arc holds a pixel of every opposite pair").  VABSDIFF4 gives the four byte
-        // differences in one instruction, ((x & 0x7f7f7f7f) + (127-b)*0x01010101 | x) & 0x80808080 flags the bytes > b
-        // without inter-byte carries.  Survivors are appended with one shared-memory atomic per warp and iteration
-        // (four ballots give every flagged byte its slot).
+        // SIMD-within-a-register prefilter, 4 horizontally adjacent pixels per thread, on the eight EVEN ring positions:
+        // a position is flagged when it differs from the centre by more than the threshold (|v - p| > b, sign ignored,
+        // so the filter is a superset of the bright and of the dark test).  VABSDIFF4 gives the four byte differences
+        // in one instruction, ((x & 0x7f7f7f7f) + (127-b)*0x01010101 | x) & 0x80808080 flags the bytes > b without
+        // inter-byte carries.  Survivors are appended with one shared-memory atomic per warp and iteration (four
+        // ballots give every flagged byte its slot).
+        // A thread tests 8 adjacent pixels (two words) per item, two items per thread cover the 42 x 88 padded region;
+        // the 16 result flags stay in a register and are compacted ONCE: warp scan of the per-thread counts, one
+        // shared-memory atomic per warp, then each thread writes its (few) survivors.
         const uint32_t kadd = 0x01010101u * (uint32_t)(127 - g.threshold);
-        constexpr int kGroups = (kScW + 3) / 4;  // 21 groups of 4 pixels per region row
+        constexpr int kPairs = 11;               // items of 8 pixels per region row (88 >= 82 columns)
         constexpr int W = kSmW / 4;              // words per smem row
-        for (int g0 = 0; g0 < kScH * kGroups; g0 += 256) {  // block-uniform trip count
-            const int gi = g0 + tid;
-            const int ry = gi / kGroups, rx0 = (gi - ry * kGroups) * 4;
-            uint32_t m = 0;
+#define FLAG(v, ctr) ((((__vabsdiffu4((v), (ctr)) & 0x7f7f7f7fu) + kadd) | __vabsdiffu4((v), (ctr))) & 0x80808080u)
+        // five consecutive (circular) flags among the eight even ring positions f0..f7 = ring 0, 2, .. 14: a 10-arc
+        // contains five consecutive even positions, so this is necessary for a corner (and implies the classic
+        // "one pixel of every opposite pair" test)
+#define RUN5(f0, f1, f2, f3, f4, f5, f6, f7, out)                                                         \
+    {                                                                                                    \
+        const uint32_t t0 = f0 & f1 & f2, t1 = f1 & f2 & f3, t2 = f2 & f3 & f4, t3 = f3 & f4 & f5;       \
+        const uint32_t t4 = f4 & f5 & f6, t5 = f5 & f6 & f7, t6 = f6 & f7 & f0, t7 = f7 & f0 & f1;       \
+        out = (t0 & t2) | (t1 & t3) | (t2 & t4) | (t3 & t5) | (t4 & t6) | (t5 & t7) | (t6 & t0) | (t7 & t1); \
+    }
+        unsigned flags16 = 0;   // bit 8*it + j: pixel j of item `it` of this thread survives
+        int idx_of[2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int item_id = it * 256 + tid;
+            const int ry = item_id / kPairs, rx0 = (item_id - ry * kPairs) * 8;
+            idx_of[it] = ry * kScW + rx0;
             if (ry >= ry_lo && ry < ry_hi) {
                 // word-aligned base of the centre row: pixel rx0 sits at byte offset rx0 + 15 = (rx0 + 12) + 3
                 const uint32_t* rowc = reinterpret_cast<const uint32_t*>(s_img + (ry + 4) * kSmW + rx0 + 12);
-                const uint32_t c0 = rowc[0], c1 = rowc[1], c2 = rowc[2];
-                const uint32_t ctr = __funnelshift_r(c0, c1, 24);
-#define FLAG(v) ((((__vabsdiffu4((v), ctr) & 0x7f7f7f7fu) + kadd) | __vabsdiffu4((v), ctr)) & 0x80808080u)
-                m = FLAG(c0) | FLAG(__funnelshift_r(c1, c2, 16));                                   // ring 12 (-3,0) | 4 (+3,0)
+                const uint32_t* ru3 = rowc - 3 * W;
+                const uint32_t* rd3 = rowc + 3 * W;
+                const uint32_t* ru2 = rowc - 2 * W;
+                const uint32_t* rd2 = rowc + 2 * W;
+                const uint32_t c0 = rowc[0], c1 = rowc[1], c2 = rowc[2], c3 = rowc[3];
+                const uint32_t a0 = ru3[0], a1 = ru3[1], a2 = ru3[2], b0 = rd3[0], b1 = rd3[1], b2 = rd3[2];
+                const uint32_t u0 = ru2[0], u1 = ru2[1], u2 = ru2[2], u3 = ru2[3];
+                const uint32_t d0 = rd2[0], d1 = rd2[1], d2 = rd2[2], d3 = rd2[3];
+                const uint32_t ctrA = __funnelshift_r(c0, c1, 24), ctrB = __funnelshift_r(c1, c2, 24);
+                const uint32_t um1 = __funnelshift_r(u1, u2, 8), dm1 = __funnelshift_r(d1, d2, 8);  // column +2 of A = -2 of B
+                uint32_t mA, mB;
                 {
-                    const uint32_t* ru = rowc - 3 * W;
-                    const uint32_t* rd = rowc + 3 * W;
-                    m &= FLAG(__funnelshift_r(ru[0], ru[1], 24)) | FLAG(__funnelshift_r(rd[0], rd[1], 24));  // ring 8 | 0
+                    const uint32_t f0 = FLAG(__funnelshift_r(b0, b1, 24), ctrA);   // ring 0  ( 0,+3)
+                    const uint32_t f1 = FLAG(dm1, ctrA);                           // ring 2  (+2,+2)
+                    const uint32_t f2 = FLAG(__funnelshift_r(c1, c2, 16), ctrA);   // ring 4  (+3, 0)
+                    const uint32_t f3 = FLAG(um1, ctrA);                           // ring 6  (+2,-2)
+                    const uint32_t f4 = FLAG(__funnelshift_r(a0, a1, 24), ctrA);   // ring 8  ( 0,-3)
+                    const uint32_t f5 = FLAG(__funnelshift_r(u0, u1, 8), ctrA);    // ring 10 (-2,-2)
+                    const uint32_t f6 = FLAG(c0, ctrA);                            // ring 12 (-3, 0)
+                    const uint32_t f7 = FLAG(__funnelshift_r(d0, d1, 8), ctrA);    // ring 14 (-2,+2)
+                    RUN5(f0, f1, f2, f3, f4, f5, f6, f7, mA)
                 }
                 {
-                    const uint32_t* ru = rowc - 2 * W;
-                    const uint32_t* rd = rowc + 2 * W;
-                    const uint32_t u0 = ru[0], u1 = ru[1], u2 = ru[2], d0 = rd[0], d1 = rd[1], d2 = rd[2];
-                    m &= FLAG(__funnelshift_r(u0, u1, 8)) | FLAG(__funnelshift_r(d1, d2, 8));   // ring 10 (-2,-2) | 2 (+2,+2)
-                    m &= FLAG(__funnelshift_r(u1, u2, 8)) | FLAG(__funnelshift_r(d0, d1, 8));   // ring 6 (+2,-2) | 14 (-2,+2)
+                    const uint32_t f0 = FLAG(__funnelshift_r(b1, b2, 24), ctrB);
+                    const uint32_t f1 = FLAG(__funnelshift_r(d2, d3, 8), ctrB);
+                    const uint32_t f2 = FLAG(__funnelshift_r(c2, c3, 16), ctrB);
+                    const uint32_t f3 = FLAG(__funnelshift_r(u2, u3, 8), ctrB);
+                    const uint32_t f4 = FLAG(__funnelshift_r(a1, a2, 24), ctrB);
+                    const uint32_t f5 = FLAG(um1, ctrB);
+                    const uint32_t f6 = FLAG(c1, ctrB);
+                    const uint32_t f7 = FLAG(dm1, ctrB);
+                    RUN5(f0, f1, f2, f3, f4, f5, f6, f7, mB)
                 }
-#undef FLAG
-                if (rx0 < rx_lo || rx0 + 4 > rx_hi) {  // group straddles the valid column range: keep bytes [lo, hi)
-                    const int lo = min(max(rx_lo - rx0, 0), 4), hi = min(max(rx_hi - rx0, 0), 4);
-                    const unsigned long long keep = ((1ull << (8 * hi)) - 1ull) & ~((1ull << (8 * lo)) - 1ull);
-                    m &= hi > lo ? (uint32_t)keep : 0u;
-                }
+                // bit 7 of every byte -> one bit per pixel, then drop the columns outside [rx_lo, rx_hi)
+                unsigned f8 = ((((mA >> 7) & 0x01010101u) * 0x01020408u) >> 24) | (((((mB >> 7) & 0x01010101u) * 0x01020408u) >> 24) << 4);
+                const int lo = min(max(rx_lo - rx0, 0), 8), hi = min(max(rx_hi - rx0, 0), 8);
+                f8 &= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+                flags16 |= f8 << (8 * it);
             }
-            const unsigned b0 = __ballot_sync(0xFFFFFFFFu, m & 0x80u), b1 = __ballot_sync(0xFFFFFFFFu, m & 0x8000u);
-            const unsigned b2 = __ballot_sync(0xFFFFFFFFu, m & 0x800000u), b3 = __ballot_sync(0xFFFFFFFFu, m & 0x80000000u);
-            if (b0 | b1 | b2 | b3) {
-                const int n0 = __popc(b0), n1 = n0 + __popc(b1), n2 = n1 + __popc(b2), tot = n2 + __popc(b3);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nquick, tot);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                const int idx0 = ry * kScW + rx0;
-                if (m & 0x80u) s_quick[base + __popc(b0 & lt_mask)] = (uint16_t)idx0;
-                if (m & 0x8000u) s_quick[base + n0 + __popc(b1 & lt_mask)] = (uint16_t)(idx0 + 1);
-                if (m & 0x800000u) s_quick[base + n1 + __popc(b2 & lt_mask)] = (uint16_t)(idx0 + 2);
-                if (m & 0x80000000u) s_quick[base + n2 + __popc(b3 & lt_mask)] = (uint16_t)(idx0 + 3);
+        }
+#undef FLAG
+#undef RUN5
+        const int cnt = __popc(flags16);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (tot) {  // warp-uniform
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&s_nquick, tot);
+            base = __shfl_sync(0xFFFFFFFFu, base, 31);
+            int pos = base + incl - cnt;
+            while (flags16) {
+                const int k = __ffs(flags16) - 1;
+                flags16 &= flags16 - 1;
+                s_quick[pos++] = (uint16_t)((k & 8 ? idx_of[1] : idx_of[0]) + (k & 7));
             }
         }
     } else {
@@ -344,8 +383,9 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const DetectArgs a, 
     }
     // grid-cell lookup tables of this tile (local cell column / row of every tile pixel)
     if (selectable) {
-        if (tid < kTileW) s_lutx[tid] = (uint8_t)(((x0 + tid) * scale) / g.cell_size - (x0 * scale) / g.cell_size);
-        else if (tid < kTileW + kTileH) s_luty[tid - kTileW] = (uint8_t)(((y0 + tid - kTileW) * scale) / g.cell_size - (y0 * scale) / g.cell_size);
+        // tiles start on cell boundaries (build_geometry), so the local cell of pixel i is (i * 2^L) / cell_size
+        if (tid < kTileW) s_lutx[tid] = (uint8_t)div_magic((unsigned)(tid << L), g.cell_magic);
+        else if (tid < kTileW + kTileH) s_luty[tid - kTileW] = (uint8_t)div_magic((unsigned)((tid - kTileW) << L), g.cell_magic);
     }
     __syncthreads();
 
@@ -379,7 +419,7 @@ __global__ void __launch_bounds__(256, 5) fast_cells_kernel(const DetectArgs a, 
 
     // pass C1: 3x3 non-max on the tile interior; survivors that pass InFrame / grid / occupancy become
     // cell candidates (at most one per 2x2 block: neighbours with equal or larger score kill each other)
-    const int cx0 = x0 * scale / g.cell_size, cy0 = y0 * scale / g.cell_size;
+    const int cx0 = tx * cpt_x, cy0 = ty * cpt_y;  // first grid cell of the tile (tiles start on cell boundaries)
     {
         int my_corner = 0, my_nonmax = 0;
         for (int i = tid; i < n_corner; i += 256) {
