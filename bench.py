@@ -389,14 +389,6 @@ def main() -> None:
 
     d2h_bytes = [0]
 
-    def e2e_step():
-        fr.upload_raw(pinned.data_ptr(), B, 1, FRAME_BYTES)
-        off, _ = fr.detect_packed(slots)
-        qoff, _, _ = fr.match_packed(slots, nxt, True)
-        nf = int(off[-1])
-        d2h_bytes[0] = nf * (4 + 4 + 1 + 4 + 4 + 32 + 4) + (B + 1) * 4 + int(qoff[-1]) * 8 + (B + 1) * 4
-        return nf
-
     # ---- resident leg (value) -------------------------------------------------------------------
     fr.upload_raw(pinned.data_ptr(), B, 1, FRAME_BYTES)   # level 0 resident before the timed region
     ctx.synchronize()
@@ -425,28 +417,46 @@ def main() -> None:
     # batch and run whole steps; the timed region covers all of them (wall clock bracketed by barriers,
     # because the work spans several streams).
     n_thr = max(1, args.e2e_contexts)
-    workers = [(ctx, fr, pinned)]
-    for t in range(1, n_thr):
-        c2 = Context(local_rank, n_levels=LEVELS)
-        f2 = c2.frames(B)
-        p2 = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
-        p2.copy_(pinned)
+    while B % n_thr:
+        n_thr -= 1
+    # every step's batch is split evenly over the contexts (sub-batch i = frames [i*Bs, (i+1)*Bs), each frame matched
+    # against its successor, cyclic inside the sub-batch), so all K steps flow through all contexts and the copies of
+    # one sub-batch overlap the kernels of the others in steady state
+    Bs = B // n_thr
+    slots_s = np.arange(Bs, dtype=np.int32)
+    nxt_s = (slots_s + 1) % Bs
+    workers = []
+    for t in range(n_thr):
+        c2, f2 = (ctx, fr) if t == 0 else (None, None)
+        if c2 is None:
+            c2 = Context(local_rank, n_levels=LEVELS)
+            f2 = c2.frames(Bs)
+        p2 = torch.empty((Bs, H, W), dtype=torch.uint8).pin_memory()
+        p2.copy_(pinned[t * Bs:(t + 1) * Bs])
         workers.append((c2, f2, p2))
+
+    call_s = [0.0, 0.0, 0.0, 0]   # worker 0: seconds inside upload / detect / match, calls (diagnostic)
 
     def e2e_step_on(w):
         c_, f_, p_ = w
-        f_.upload_raw(p_.data_ptr(), B, 1, FRAME_BYTES)
-        off, _ = f_.detect_packed(slots)
-        qoff, _, _ = f_.match_packed(slots, nxt, True)
+        t_a = time.perf_counter()
+        f_.upload_raw(p_.data_ptr(), Bs, 1, FRAME_BYTES)
+        t_b = time.perf_counter()
+        off, _ = f_.detect_packed(slots_s)
+        t_c = time.perf_counter()
+        qoff, _, _ = f_.match_packed(slots_s, nxt_s, True)
+        if w is workers[0]:
+            t_d = time.perf_counter()
+            call_s[0] += t_b - t_a; call_s[1] += t_c - t_b; call_s[2] += t_d - t_c; call_s[3] += 1
         nf = int(off[-1])
-        return nf, nf * (4 + 4 + 1 + 4 + 4 + 32 + 4) + (B + 1) * 4 + int(qoff[-1]) * 8 + (B + 1) * 4
+        return nf, nf * (4 + 4 + 1 + 4 + 4 + 32 + 4) + (Bs + 1) * 4 + int(qoff[-1]) * 8 + (Bs + 1) * 4
 
     def e2e_run(n_steps):
         res = [None] * n_thr
 
         def work(t):
             out = None
-            for _ in range(t, n_steps, n_thr):
+            for _ in range(n_steps):
                 out = e2e_step_on(workers[t])
             res[t] = out
 
@@ -455,9 +465,9 @@ def main() -> None:
             th.start()
         for th in ths:
             th.join()
-        return next(r for r in res if r is not None)
+        return sum(r[0] for r in res), sum(r[1] for r in res)
 
-    e2e_run(2 * n_thr)
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
     nfeat, d2h = e2e_run(args.steps)
@@ -466,6 +476,31 @@ def main() -> None:
     barrier()
     d2h_bytes[0] = d2h
     clocks = sampler.stop()
+    # diagnostics (untimed): what the PCIe link gives this process, and where worker 0 spent its wall time
+    e2e_diag = {"worker0_ms_per_call": {k: 1e3 * call_s[i] / max(call_s[3], 1) for i, k in enumerate(("upload", "detect_packed", "match_packed"))}}
+    try:
+        dev_buf = torch.empty_like(pinned, device="cuda")
+        back = torch.empty_like(pinned).pin_memory()
+        for name, dst, src in (("h2d_gbs", dev_buf, pinned), ("d2h_gbs", back, dev_buf)):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            e2e_diag[name] = 4 * pinned.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        ctx.synchronize()
+        t_u = time.perf_counter()
+        for _ in range(4):
+            fr.upload_raw(pinned.data_ptr(), B, 1, FRAME_BYTES)
+        ctx.synchronize()
+        e2e_diag["upload_api_gbs"] = 4 * pinned.numel() / (time.perf_counter() - t_u) / 1e9
+        e2e_diag["e2e_cap_frames_per_s_from_h2d"] = e2e_diag["h2d_gbs"] * 1e9 / FRAME_BYTES * world
+        del dev_buf, back
+    except Exception as e:  # noqa: BLE001
+        e2e_diag["error"] = repr(e)
 
     # ---- per-kernel shares (CUDA events around every launch; separate pass so the timed legs stay clean)
     ctx.profile(True)
@@ -556,7 +591,7 @@ def main() -> None:
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(B, "one batch of independent frames per GPU per step"),
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES, "d2h_bytes_per_step": d2h_bytes[0],
-                    "ms_per_step": ms_e2e / args.steps, "host_threads": n_thr,
+                    "ms_per_step": ms_e2e / args.steps, "host_threads": n_thr, "frames_per_context_per_step": Bs, "diag": e2e_diag,
                     "timing": "wall clock between device synchronisations (the leg spans several streams)"},
             "gpu_launches": int(launches),
             "clocks": clocks,

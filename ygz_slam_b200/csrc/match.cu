@@ -14,6 +14,8 @@
 //              -> first minimum over the query rows, which is what crossCheck compares against.
 // Roofline: 32*(nA+nB) + 8*nA algorithmic bytes per pair against nA*nB*8 POPC -- the kernel is bound
 // by the integer POPC pipe, not by HBM; bench.py reports both fractions.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ygzb {
@@ -43,17 +45,24 @@ __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t
     carry = (a & b) | (a & c) | (b & c);
 }
 
-__device__ __forceinline__ int hamming256(const uint32_t (&q)[8], const uint4 lo, const uint4 hi) {
+template <int kPopc = 5>
+__device__ __forceinline__ unsigned hamming256(const uint32_t (&q)[8], const uint4 lo, const uint4 hi) {
     const uint32_t x0 = q[0] ^ lo.x, x1 = q[1] ^ lo.y, x2 = q[2] ^ lo.z, x3 = q[3] ^ lo.w;
     const uint32_t x4 = q[4] ^ hi.x, x5 = q[5] ^ hi.y, x6 = q[6] ^ hi.z, x7 = q[7] ^ hi.w;
     uint32_t s0, c0, s1, c1, s2, c2;
     csa(x0, x1, x2, s0, c0);
     csa(x3, x4, x5, s1, c1);
     csa(s0, s1, x6, s2, c2);
+    if (kPopc == 4) {
+        // one more adder level folds the three weight-2 words into a weight-2 and a weight-4 word: 4 POPC + 16 LOP3
+        uint32_t t, f;
+        csa(c0, c1, c2, t, f);
+        return __popc(s2) + __popc(x7) + 2 * __popc(t) + 4 * __popc(f);
+    }
     return __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
 }
 
-template <bool kCross>
+template <bool kCross, int kPopc>
 __global__ void __launch_bounds__(kQueriesPerCta) match_kernel(const MatchArgs a) {
     __shared__ __align__(16) uint4 s_train[kChunk * 2];
     __shared__ unsigned s_col[kCross ? kWarps * kChunk : 1];
@@ -76,6 +85,9 @@ __global__ void __launch_bounds__(kQueriesPerCta) match_kernel(const MatchArgs a
     }
     const uint4* train = reinterpret_cast<const uint4*>(a.base + (size_t)sb * a.set_stride);
     unsigned best = 0xFFFFFFFFu;
+    // lanes past the last query shadow query q0 under the largest index: their column keys tie with q0's own lane
+    // and lose on the index, so the inner loop needs no select (set sizes stay below 65535)
+    const unsigned qkey = active ? (unsigned)qi : 0xFFFFu;
 
     for (int j0 = 0; j0 < nB; j0 += kChunk) {
         const int nj = min(kChunk, nB - j0);
@@ -84,11 +96,10 @@ __global__ void __launch_bounds__(kQueriesPerCta) match_kernel(const MatchArgs a
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < nj; ++j) {
-            const int d = hamming256(q, s_train[2 * j], s_train[2 * j + 1]);
-            best = min(best, ((unsigned)d << 16) | (unsigned)(j0 + j));
+            const unsigned d = hamming256<kPopc>(q, s_train[2 * j], s_train[2 * j + 1]);
+            best = min(best, d * 65536u + (unsigned)(j0 + j));
             if (kCross) {
-                const unsigned ck = active ? (((unsigned)d << 16) | (unsigned)qi) : 0xFFFFFFFFu;
-                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, ck);
+                const unsigned m = __reduce_min_sync(0xFFFFFFFFu, d * 65536u + qkey);
                 if (lane == 0) s_col[warp * kChunk + j] = m;
             }
         }
@@ -133,7 +144,7 @@ __global__ void hamming_pairs_kernel(const uint8_t* __restrict__ A, const uint8_
     const uint4* pb = reinterpret_cast<const uint4*>(B) + (size_t)ib[k] * 2;
     const uint4 a0 = pa[0], a1 = pa[1];
     uint32_t q[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    dist[k] = hamming256(q, pb[0], pb[1]);
+    dist[k] = (int32_t)hamming256<5>(q, pb[0], pb[1]);
 }
 
 // exclusive scan of counts[sets[i]] over the pairs/items of a call (n <= a few thousand): offsets[n] = total
@@ -195,10 +206,18 @@ int launch_match(ygzb_ctx* ctx, const uint8_t* d_base, size_t set_stride, const 
     dim3 grid((cap + kQueriesPerCta - 1) / kQueriesPerCta, n_pairs);
     {
         ProfScope ps(ctx, kStageMatch);
-        if (cross_check)
-            match_kernel<true><<<grid, kQueriesPerCta, 0, ctx->stream>>>(a);
-        else
-            match_kernel<false><<<grid, kQueriesPerCta, 0, ctx->stream>>>(a);
+        // YGZB_MATCH_POPC=4|5 picks the adder-tree depth of the distance (tuning knob, identical results)
+        static const int popc_variant = [] {
+            const char* e = getenv("YGZB_MATCH_POPC");
+            return e && e[0] == '4' ? 4 : 5;
+        }();
+        if (cross_check) {
+            if (popc_variant == 4) match_kernel<true, 4><<<grid, kQueriesPerCta, 0, ctx->stream>>>(a);
+            else match_kernel<true, 5><<<grid, kQueriesPerCta, 0, ctx->stream>>>(a);
+        } else {
+            if (popc_variant == 4) match_kernel<false, 4><<<grid, kQueriesPerCta, 0, ctx->stream>>>(a);
+            else match_kernel<false, 5><<<grid, kQueriesPerCta, 0, ctx->stream>>>(a);
+        }
     }
     YGZB_LAUNCHED(ctx);
     ProfScope ps(ctx, kStageMatchFinalize);
