@@ -244,6 +244,26 @@ def secondary_workloads(ctx) -> dict:
     ctx.profile(False)
     t_cpu, (wP, wX, wout, wst) = timed(lambda: ora.local_ba(g2o, fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"]), 3)
     k_ms = prof["local_ba"][0] / max(prof["local_ba"][1], 1)
+    # the Ceres flavour (ba::LocalBA, "vs CPU Ceres" of BASELINE.json): same scene, poses as [t; angle-axis]
+    t_aa = []
+    for v in sc["poses_noisy"]:
+        Tm = se3.se3_exp(v)
+        t_aa.append(np.r_[Tm[:, 3], se3.so3_log(Tm[:, :3])])
+    t_aa = np.array(t_aa)
+    ctx.profile(True)
+    t_gpu_c, (cP, cX, cst) = timed(lambda: ctx.local_ba_ceres([0, 10], [0, 2000], [0, n_obs], t_aa, fixed, sc["pts_noisy"], sc["kf_idx"],
+                                                              sc["pt_idx"], sc["px"]), 10)
+    prof_c = ctx.profile_read()
+    ctx.profile(False)
+    t_cpu_c, (wcP, wcX, wcst) = timed(lambda: ora.local_ba_ceres(t_aa, fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"]), 3)
+    kc_ms = prof_c["local_ba"][0] / max(prof_c["local_ba"][1], 1)
+    out["c4_local_ba_ceres_twin"] = {
+        "gpu_ms_total_e2e": t_gpu_c * 1e3, "gpu_kernel_ms_total": kc_ms, "gpu_iters": cst[0]["iters"],
+        "gpu_ms_per_iter": kc_ms / max(cst[0]["iters"], 1), "cpu_ms_total": t_cpu_c * 1e3, "cpu_iters": wcst["iters"],
+        "cpu_ms_per_iter": t_cpu_c * 1e3 / max(wcst["iters"], 1),
+        "cpu_kind": "oracle restatement of Ceres trust-region LM (forward jets, Schur + dense Cholesky), 1 thread; Ceres itself is not installable here",
+        "cost_final_gpu": cst[0]["cost_final"], "cost_final_cpu": wcst["cost_final"], "termination": cst[0]["termination"],
+        "max_pose_diff_vs_oracle": float(np.abs(cP - wcP).max()), "max_landmark_diff_vs_oracle_m": float(np.abs(cX - wcX).max())}
     trials = st[0]["lm_trials"]
     kbar = n_obs / 2000.0
     flop_per_trial = 300.0 * n_obs + 2000 * (216 * kbar**2 + 108 * kbar + 50) + 54**3 / 3.0
@@ -315,7 +335,7 @@ def main() -> None:
                     help="extract_match = BASELINE configs[1] (default, the headline); vo = configs[4] shape: 8 synthetic streams "
                          "per GPU through the full tracking loop")
     ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the bounded cpu_baseline sample")
-    ap.add_argument("--e2e-contexts", type=int, default=4,
+    ap.add_argument("--e2e-contexts", type=int, default=8,
                     help="host threads (one ygzb context = one stream each) used by the e2e leg so that the H2D copy "
                          "of one batch overlaps the kernels of another")
     args = ap.parse_args()

@@ -199,6 +199,24 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
                   double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
                   const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, ygzb_ba_stats* stats);
 
+/* replaces ba::LocalBA, the Ceres twin of the local BA (src/Algorithm/BA.cpp:324-384; BA.h:52-58) with
+ * CeresReprojectionError / CeresReprojectionErrorPointOnly (include/ygz/Ceres/CeresReprojectionError.h:33-69,
+ * CeresReprojectionErrorPointOnly.h:14-67): residual pt_cam - p / p.z in normalised image coordinates, no loss,
+ * default ceres::Solver::Options (trust-region LM with Jacobi scaling; max_iters = 50 there).  Same batching and index
+ * conventions as ygzb_local_ba, except that a pose is 6 doubles [t(3); angle-axis(3)] (the Vector6d of BA.cpp:353-357)
+ * and fixed[k] != 0 marks the key-frame with _keyframe_id == 0, whose observations become point-only residual blocks
+ * (BA.cpp:340-349).  Observations in frames outside the local set are not part of the problem (BA.cpp:338): the
+ * caller leaves them out.  obs_px are pixels; Pixel2Camera2D (float intrinsics of the context) is applied inside.
+ * termination: 0 max_iters reached, 1 gradient, 2 parameter, 3 function tolerance, 4 trust region collapsed.    */
+typedef struct {
+    int iters, successful_steps;
+    double cost_initial, cost_final, radius_final;
+    int termination;
+} ygzb_ceres_stats;
+int ygzb_local_ba_ceres(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
+                        double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
+                        const double* obs_px, int max_iters, ygzb_ceres_stats* stats);
+
 /* replaces ba::OptimizeCurrentPoseOnly (src/Algorithm/BA.cpp:188-264; BA.h:44-46) with
  * CeresReprojectionErrorPoseOnly (include/ygz/Ceres/CeresReprojectionErrorPoseOnly.h): four rounds of
  * trust-region LM on [t; angle-axis] with re-classification of the observations between rounds.

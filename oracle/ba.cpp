@@ -570,3 +570,326 @@ extern "C" int ora_pose_only(const ora_camera* camp, int n, const double* pt_wor
     T.to_mat(T_cw);
     return cntInlier;
 }
+
+// ---- ba::LocalBA, the Ceres twin of the local BA (reference src/Algorithm/BA.cpp:324-384) ---------------------
+//   CeresReprojectionError           reference include/ygz/Ceres/CeresReprojectionError.h:33-69
+//       pose = [t; angle-axis], residual = pt_cam - p / p.z in NORMALISED image coordinates, AutoDiff<2, 6, 3>
+//   CeresReprojectionErrorPointOnly  reference include/ygz/Ceres/CeresReprojectionErrorPointOnly.h:14-67
+//       the same residual with the pose held constant: used for the key-frame with _keyframe_id == 0 (BA.cpp:340-349)
+//       = `fixed[k] != 0` here; observations in frames outside the local set are not added at all (BA.cpp:338).
+// Solver: default ceres::Solver::Options -- trust-region Levenberg-Marquardt, Jacobi scaling, no loss function, <= 50
+// iterations, function / gradient / parameter tolerances 1e-6 / 1e-10 / 1e-8, initial radius 1e4.  The sparse normal
+// Cholesky of the full system is restated as its exact equivalent, the Schur complement onto the free poses.
+namespace {
+
+struct Jet9 {
+    double a;
+    double v[9];
+};
+inline Jet9 j9c(double c) {
+    Jet9 r{c, {}};
+    return r;
+}
+inline Jet9 operator+(const Jet9& x, const Jet9& y) {
+    Jet9 r{x.a + y.a, {}};
+    for (int i = 0; i < 9; ++i) r.v[i] = x.v[i] + y.v[i];
+    return r;
+}
+inline Jet9 operator-(const Jet9& x, const Jet9& y) {
+    Jet9 r{x.a - y.a, {}};
+    for (int i = 0; i < 9; ++i) r.v[i] = x.v[i] - y.v[i];
+    return r;
+}
+inline Jet9 operator*(const Jet9& x, const Jet9& y) {
+    Jet9 r{x.a * y.a, {}};
+    for (int i = 0; i < 9; ++i) r.v[i] = x.a * y.v[i] + x.v[i] * y.a;
+    return r;
+}
+inline Jet9 operator/(const Jet9& x, const Jet9& y) {
+    const double inv = 1.0 / y.a, q = x.a * inv;
+    Jet9 r{q, {}};
+    for (int i = 0; i < 9; ++i) r.v[i] = (x.v[i] - q * y.v[i]) * inv;
+    return r;
+}
+
+// ceres::AngleAxisRotatePoint on 9-partial jets
+void angle_axis_rotate9(const Jet9 aa[3], const Jet9 pt[3], Jet9 out[3]) {
+    const Jet9 theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+    if (theta2.a > 2.2204460492503131e-16) {
+        const double th = std::sqrt(theta2.a), dth = 1.0 / (2.0 * th);
+        Jet9 theta{th, {}}, costheta{std::cos(th), {}}, sintheta{std::sin(th), {}};
+        for (int i = 0; i < 9; ++i) {
+            theta.v[i] = theta2.v[i] * dth;
+            costheta.v[i] = -sintheta.a * theta.v[i];
+            sintheta.v[i] = costheta.a * theta.v[i];
+        }
+        const Jet9 inv = j9c(1.0) / theta;
+        const Jet9 w[3] = {aa[0] * inv, aa[1] * inv, aa[2] * inv};
+        const Jet9 wxp[3] = {w[1] * pt[2] - w[2] * pt[1], w[2] * pt[0] - w[0] * pt[2], w[0] * pt[1] - w[1] * pt[0]};
+        const Jet9 tmp = (w[0] * pt[0] + w[1] * pt[1] + w[2] * pt[2]) * (j9c(1.0) - costheta);
+        for (int i = 0; i < 3; ++i) out[i] = pt[i] * costheta + wxp[i] * sintheta + w[i] * tmp;
+    } else {
+        const Jet9 wxp[3] = {aa[1] * pt[2] - aa[2] * pt[1], aa[2] * pt[0] - aa[0] * pt[2], aa[0] * pt[1] - aa[1] * pt[0]};
+        for (int i = 0; i < 3; ++i) out[i] = pt[i] + wxp[i];
+    }
+}
+
+struct CeresBA {
+    int n_kf, n_pt, n_obs, np;
+    const int32_t *kf_idx, *pt_idx;
+    std::vector<int> free_index;
+    std::vector<double> ptcam;
+    std::vector<std::vector<int>> obs_of_pt;
+
+    // residuals (2 per observation) and, optionally, the Jacobian blocks Jp (2x6) / Jl (2x3) per observation
+    void evaluate(const std::vector<double>& P, const std::vector<double>& X, std::vector<double>& r, std::vector<double>* Jp,
+                  std::vector<double>* Jl) const {
+        for (int o = 0; o < n_obs; ++o) {
+            const double* pose = &P[6 * (size_t)kf_idx[o]];
+            const double* x = &X[3 * (size_t)pt_idx[o]];
+            Jet9 T[6], Xj[3];
+            for (int i = 0; i < 6; ++i) {
+                T[i] = j9c(pose[i]);
+                T[i].v[i] = 1.0;
+            }
+            for (int i = 0; i < 3; ++i) {
+                Xj[i] = j9c(x[i]);
+                Xj[i].v[6 + i] = 1.0;
+            }
+            const Jet9 rot[3] = {T[3], T[4], T[5]};
+            Jet9 p[3];
+            angle_axis_rotate9(rot, Xj, p);
+            p[0] = p[0] + T[0];
+            p[1] = p[1] + T[1];
+            p[2] = p[2] + T[2];
+            const Jet9 r0 = j9c(ptcam[2 * (size_t)o]) - p[0] / p[2], r1 = j9c(ptcam[2 * (size_t)o + 1]) - p[1] / p[2];
+            r[2 * (size_t)o] = r0.a;
+            r[2 * (size_t)o + 1] = r1.a;
+            if (Jp)
+                for (int k = 0; k < 6; ++k) {
+                    (*Jp)[12 * (size_t)o + k] = r0.v[k];
+                    (*Jp)[12 * (size_t)o + 6 + k] = r1.v[k];
+                }
+            if (Jl)
+                for (int k = 0; k < 3; ++k) {
+                    (*Jl)[6 * (size_t)o + k] = r0.v[6 + k];
+                    (*Jl)[6 * (size_t)o + 3 + k] = r1.v[6 + k];
+                }
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* poses, const uint8_t* fixed, int n_pt, double* pts,
+                                  int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px, int max_iters,
+                                  ora_ceres_stats* stats) {
+    const float fx = camp->fx, fy = camp->fy, cx = camp->cx, cy = camp->cy;
+    CeresBA pb;
+    pb.n_kf = n_kf; pb.n_pt = n_pt; pb.n_obs = n_obs;
+    pb.kf_idx = kf_idx; pb.pt_idx = pt_idx;
+    pb.free_index.assign(n_kf, -1);
+    pb.np = 0;
+    for (int k = 0; k < n_kf; ++k)
+        if (!fixed[k]) pb.free_index[k] = pb.np++;
+    const int np = pb.np, dimp = 6 * np;
+    pb.ptcam.resize(2 * (size_t)n_obs);
+    for (int o = 0; o < n_obs; ++o) {  // PinholeCamera::Pixel2Camera2D (float intrinsics, double maths)
+        pb.ptcam[2 * (size_t)o] = (obs_px[2 * (size_t)o] - cx) / fx;
+        pb.ptcam[2 * (size_t)o + 1] = (obs_px[2 * (size_t)o + 1] - cy) / fy;
+    }
+    pb.obs_of_pt.assign(n_pt, {});
+    for (int o = 0; o < n_obs; ++o) pb.obs_of_pt[pt_idx[o]].push_back(o);
+
+    std::vector<double> P(poses, poses + 6 * (size_t)n_kf), X(pts, pts + 3 * (size_t)n_pt);
+    std::vector<double> r(2 * (size_t)n_obs), rn(2 * (size_t)n_obs), Jp(12 * (size_t)n_obs), Jl(6 * (size_t)n_obs);
+    std::vector<double> Hpp((size_t)np * 36), gp(dimp), Hll((size_t)n_pt * 9), gl(3 * (size_t)n_pt), Hpl(18 * (size_t)n_obs);
+    double cost = 0;
+
+    auto build = [&]() {  // normal-equation blocks of the UNSCALED Jacobian and the gradient g = J^T r
+        pb.evaluate(P, X, r, &Jp, &Jl);
+        cost = 0;
+        for (double v : r) cost += v * v;
+        cost *= 0.5;
+        std::fill(Hpp.begin(), Hpp.end(), 0.0); std::fill(gp.begin(), gp.end(), 0.0);
+        std::fill(Hll.begin(), Hll.end(), 0.0); std::fill(gl.begin(), gl.end(), 0.0);
+        for (int o = 0; o < n_obs; ++o) {
+            const int j = pt_idx[o], fi = pb.free_index[kf_idx[o]];
+            const double* J0 = &Jl[6 * (size_t)o];
+            const double* J1 = J0 + 3;
+            const double e0 = r[2 * (size_t)o], e1 = r[2 * (size_t)o + 1];
+            for (int a = 0; a < 3; ++a) {
+                for (int b = 0; b < 3; ++b) Hll[9 * (size_t)j + 3 * a + b] += J0[a] * J0[b] + J1[a] * J1[b];
+                gl[3 * (size_t)j + a] += J0[a] * e0 + J1[a] * e1;
+            }
+            if (fi >= 0) {
+                const double* Q0 = &Jp[12 * (size_t)o];
+                const double* Q1 = Q0 + 6;
+                for (int a = 0; a < 6; ++a) {
+                    for (int b = 0; b < 6; ++b) Hpp[36 * (size_t)fi + 6 * a + b] += Q0[a] * Q0[b] + Q1[a] * Q1[b];
+                    gp[6 * fi + a] += Q0[a] * e0 + Q1[a] * e1;
+                    for (int b = 0; b < 3; ++b) Hpl[18 * (size_t)o + 3 * a + b] = Q0[a] * J0[b] + Q1[a] * J1[b];
+                }
+            }
+        }
+    };
+    auto gradient_max = [&]() {
+        double g = 0;
+        for (double v : gp) g = std::max(g, std::fabs(v));
+        for (double v : gl) g = std::max(g, std::fabs(v));
+        return g;
+    };
+
+    build();
+    const double cost_initial = cost;
+    // Jacobi scaling, computed once from the initial Jacobian: 1 / (1 + ||column||)
+    std::vector<double> sp(dimp), sl(3 * (size_t)n_pt);
+    for (int i = 0; i < np; ++i)
+        for (int a = 0; a < 6; ++a) sp[6 * i + a] = 1.0 / (1.0 + std::sqrt(Hpp[36 * (size_t)i + 7 * a]));
+    for (int j = 0; j < n_pt; ++j)
+        for (int a = 0; a < 3; ++a) sl[3 * (size_t)j + a] = 1.0 / (1.0 + std::sqrt(Hll[9 * (size_t)j + 4 * a]));
+
+    int iters = 0, n_success = 0, termination = 0;  // 0 = max iterations, 1 = gradient, 2 = parameter, 3 = function, 4 = radius
+    double radius = 1e4, decrease_factor = 2.0;
+    if (gradient_max() <= 1e-10) termination = 1;
+    std::vector<double> xp(dimp), xl(3 * (size_t)n_pt), Pc, Xc;
+    for (int iter = 0; termination == 0 && iter < max_iters; ++iter) {
+        ++iters;
+        // (Js^T Js + D / radius) y = -Js^T r with D = clamp(diag(Js^T Js), 1e-6, 1e32), delta = S y
+        //   <=>  (H + diag(d)) delta = -g,  d_k = clamp(s_k^2 H_kk) / (radius s_k^2)
+        auto damp = [&](double hkk, double s) { return std::min(std::max(s * s * hkk, 1e-6), 1e32) / radius / (s * s); };
+        std::vector<double> S((size_t)dimp * dimp, 0.0), bs(dimp);
+        for (int i = 0; i < np; ++i)
+            for (int a = 0; a < 6; ++a) {
+                for (int b = 0; b < 6; ++b) S[(size_t)(6 * i + a) * dimp + 6 * i + b] = Hpp[36 * (size_t)i + 6 * a + b];
+                S[(size_t)(6 * i + a) * dimp + 6 * i + a] += damp(Hpp[36 * (size_t)i + 7 * a], sp[6 * i + a]);
+                bs[6 * i + a] = -gp[6 * i + a];
+            }
+        std::vector<double> Dinv_all(9 * (size_t)n_pt);
+        for (int j = 0; j < n_pt; ++j) {
+            double D[3][3], Di[3][3];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) D[a][b] = Hll[9 * (size_t)j + 3 * a + b];
+            for (int a = 0; a < 3; ++a) D[a][a] += damp(Hll[9 * (size_t)j + 4 * a], sl[3 * (size_t)j + a]);
+            inverse3d(D, Di);
+            std::memcpy(&Dinv_all[9 * (size_t)j], Di, sizeof(Di));
+            for (int o1 : pb.obs_of_pt[j]) {
+                const int f1 = pb.free_index[kf_idx[o1]];
+                if (f1 < 0) continue;
+                double BD[6][3];
+                for (int a = 0; a < 6; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        BD[a][b] = Hpl[18 * (size_t)o1 + 3 * a] * Di[0][b] + Hpl[18 * (size_t)o1 + 3 * a + 1] * Di[1][b] +
+                                   Hpl[18 * (size_t)o1 + 3 * a + 2] * Di[2][b];
+                for (int a = 0; a < 6; ++a)
+                    bs[6 * f1 + a] -= BD[a][0] * -gl[3 * (size_t)j] + BD[a][1] * -gl[3 * (size_t)j + 1] + BD[a][2] * -gl[3 * (size_t)j + 2];
+                for (int o2 : pb.obs_of_pt[j]) {
+                    const int f2 = pb.free_index[kf_idx[o2]];
+                    if (f2 < 0) continue;
+                    for (int a = 0; a < 6; ++a)
+                        for (int b = 0; b < 6; ++b)
+                            S[(size_t)(6 * f1 + a) * dimp + 6 * f2 + b] -= BD[a][0] * Hpl[18 * (size_t)o2 + 3 * b] +
+                                                                          BD[a][1] * Hpl[18 * (size_t)o2 + 3 * b + 1] +
+                                                                          BD[a][2] * Hpl[18 * (size_t)o2 + 3 * b + 2];
+                }
+            }
+        }
+        std::vector<double> sol(bs);
+        bool step_ok = dimp == 0 || cholesky_solve(S, sol, dimp);
+        xp = sol;
+        for (int j = 0; j < n_pt; ++j) {
+            double rr[3] = {-gl[3 * (size_t)j], -gl[3 * (size_t)j + 1], -gl[3 * (size_t)j + 2]};
+            for (int o1 : pb.obs_of_pt[j]) {
+                const int f1 = pb.free_index[kf_idx[o1]];
+                if (f1 < 0) continue;
+                for (int b = 0; b < 3; ++b)
+                    for (int a = 0; a < 6; ++a) rr[b] -= Hpl[18 * (size_t)o1 + 3 * a + b] * xp[6 * f1 + a];
+            }
+            const double* Di = &Dinv_all[9 * (size_t)j];
+            for (int a = 0; a < 3; ++a) xl[3 * (size_t)j + a] = Di[3 * a] * rr[0] + Di[3 * a + 1] * rr[1] + Di[3 * a + 2] * rr[2];
+        }
+        double model_cost_change = 0;
+        if (step_ok) {  // -(J delta)^T (r + J delta / 2)
+            for (int o = 0; o < n_obs; ++o) {
+                const int fi = pb.free_index[kf_idx[o]];
+                for (int row = 0; row < 2; ++row) {
+                    double jy = 0;
+                    if (fi >= 0)
+                        for (int k = 0; k < 6; ++k) jy += Jp[12 * (size_t)o + 6 * row + k] * xp[6 * fi + k];
+                    for (int k = 0; k < 3; ++k) jy += Jl[6 * (size_t)o + 3 * row + k] * xl[3 * (size_t)pt_idx[o] + k];
+                    model_cost_change -= jy * (r[2 * (size_t)o + row] + jy / 2);
+                }
+            }
+            step_ok = model_cost_change > 0;
+        }
+        bool accepted = false;
+        if (step_ok) {
+            Pc = P;
+            Xc = X;
+            double step_norm = 0, x_norm = 0;
+            for (int k = 0; k < n_kf; ++k) {
+                const int fi = pb.free_index[k];
+                if (fi < 0) continue;
+                for (int a = 0; a < 6; ++a) {
+                    Pc[6 * (size_t)k + a] += xp[6 * fi + a];
+                    step_norm += xp[6 * fi + a] * xp[6 * fi + a];
+                    x_norm += P[6 * (size_t)k + a] * P[6 * (size_t)k + a];
+                }
+            }
+            for (size_t i = 0; i < 3 * (size_t)n_pt; ++i) {
+                Xc[i] += xl[i];
+                step_norm += xl[i] * xl[i];
+                x_norm += X[i] * X[i];
+            }
+            step_norm = std::sqrt(step_norm);
+            x_norm = std::sqrt(x_norm);
+            pb.evaluate(Pc, Xc, rn, nullptr, nullptr);
+            double new_cost = 0;
+            for (double v : rn) new_cost += v * v;
+            new_cost *= 0.5;
+            const double relative_decrease = (cost - new_cost) / model_cost_change;
+            if (relative_decrease > 1e-3) {
+                accepted = true;
+                if (step_norm <= 1e-8 * (x_norm + 1e-8)) {  // parameter tolerance (checked before the step is taken)
+                    termination = 2;
+                    break;
+                }
+                const double old_cost = cost;
+                P = Pc;
+                X = Xc;
+                build();
+                ++n_success;
+                if (std::fabs(old_cost - cost) <= 1e-6 * old_cost) {  // function tolerance
+                    termination = 3;
+                    break;
+                }
+                if (gradient_max() <= 1e-10) {
+                    termination = 1;
+                    break;
+                }
+                radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3));
+                radius = std::min(1e16, radius);
+                decrease_factor = 2.0;
+            }
+        }
+        if (!accepted) {
+            radius = radius / decrease_factor;
+            decrease_factor *= 2.0;
+            if (radius < 1e-32) {
+                termination = 4;
+                break;
+            }
+        }
+    }
+    std::memcpy(poses, P.data(), sizeof(double) * 6 * n_kf);
+    std::memcpy(pts, X.data(), sizeof(double) * 3 * n_pt);
+    if (stats) {
+        stats->iters = iters;
+        stats->successful_steps = n_success;
+        stats->cost_initial = cost_initial;
+        stats->cost_final = cost;
+        stats->radius_final = radius;
+        stats->termination = termination;
+    }
+    return iters;
+}

@@ -51,6 +51,11 @@ class BAStats(C.Structure):
                 ("chi2_final", C.c_double), ("lambda_final", C.c_double), ("n_outliers", C.c_int)]
 
 
+class CeresStats(C.Structure):
+    _fields_ = [("iters", C.c_int), ("successful_steps", C.c_int), ("cost_initial", C.c_double),
+                ("cost_final", C.c_double), ("radius_final", C.c_double), ("termination", C.c_int)]
+
+
 class KLTParams(C.Structure):
     _fields_ = [("win", C.c_int), ("max_level", C.c_int), ("max_iter", C.c_int), ("eps", C.c_double),
                 ("min_eig", C.c_double)]
@@ -277,6 +282,18 @@ class Oracle:
                                   _p(np.ascontiguousarray(px, np.float64)), C.byref(prm), _p(outl), C.byref(st))
         stats = {k: getattr(st, k) for k, _ in BAStats._fields_}
         return poses, pts, outl.astype(bool), stats
+
+    def local_ba_ceres(self, poses_t_aa, fixed, pts, kf_idx, pt_idx, px, max_iters=50, cam=None):
+        """ba::LocalBA (Ceres twin): poses as [t; angle-axis]."""
+        cam = cam or default_camera()
+        poses = np.ascontiguousarray(poses_t_aa, np.float64).copy()
+        pts = np.ascontiguousarray(pts, np.float64).copy()
+        st = CeresStats()
+        self.lib.ora_local_ba_ceres(C.byref(cam), len(poses), _p(poses), _p(np.ascontiguousarray(fixed, np.uint8)),
+                                    len(pts), _p(pts), len(kf_idx), _p(np.ascontiguousarray(kf_idx, np.int32)),
+                                    _p(np.ascontiguousarray(pt_idx, np.int32)), _p(np.ascontiguousarray(px, np.float64)),
+                                    max_iters, C.byref(st))
+        return poses, pts, {k: getattr(st, k) for k, _ in CeresStats._fields_}
 
     def pose_only(self, pt_world, px, T_cw, cam=None):
         cam = cam or default_camera()

@@ -4,6 +4,8 @@
 // by the Python test; prints a few summary numbers that the Python side compares with the oracle.
 #include <cmath>
 #include <cstdio>
+#include <map>
+#include <set>
 #include <vector>
 
 #include "../ygz_slam_b200/host/ygz_b200.hpp"
@@ -68,5 +70,63 @@ int main(int argc, char** argv) {
     std::vector<Vector2d> tp;
     trk.GetTrackedPixel(tf, tp);
     printf("klt status %d tracked %zu mean_disparity %.4f\n", (int)trk.Status(), tp.size(), trk.MeanDisparity());
+
+    // test_local_ba.cpp shape: 8 key-frames x 16 points, perturbed poses / points, both BA flavours
+    for (int flavour = 0; flavour < 2; ++flavour) {
+        const double rot[8][3] = {{0, 0, 0}, {0.1, 0, 0}, {0, 0.1, 0}, {0, 0, 0.1}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        const double tr[8][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0.1, 0, 0}, {0, 0.1, 0}, {0, 0, 0.1}, {0.1, 0.1, 0.1}};
+        std::vector<Frame> kfs(8);
+        std::vector<MapPoint> pts(16);
+        std::vector<Vector3d> truth(16);
+        std::map<unsigned long, Frame*> keyframe_of;
+        unsigned lcg = 12345u;
+        auto noise = [&](double s) { lcg = lcg * 1664525u + 1013904223u; return s * (((lcg >> 8) & 0xFFFF) / 32768.0 - 1.0); };
+        std::vector<SE3> T_true(8);
+        for (int k = 0; k < 8; ++k) {
+            const double v[6] = {tr[k][0], tr[k][1], tr[k][2], rot[k][0], rot[k][1], rot[k][2]};
+            T_true[k] = SE3::exp(v);
+            kfs[k]._keyframe_id = k;
+            kfs[k]._is_keyframe = true;
+            keyframe_of[k] = &kfs[k];
+        }
+        std::vector<std::vector<Feature*>> feats(8);
+        for (int j = 0; j < 16; ++j) {
+            truth[j] = Vector3d(j % 2, (j / 2) % 2, 2 + j / 4);
+            pts[j]._id = j;
+            for (int k = 0; k < 8; ++k) {
+                Feature* f = new Feature(cam.World2Pixel(truth[j], T_true[k]));
+                kfs[k]._features.push_back(f);
+                pts[j]._obs[k] = f;
+            }
+            pts[j]._pos_world = Vector3d(truth[j][0] + noise(0.05), truth[j][1] + noise(0.05), truth[j][2] + noise(0.05));
+        }
+        for (int k = 0; k < 8; ++k) {
+            double v[6] = {tr[k][0], tr[k][1], tr[k][2], rot[k][0], rot[k][1], rot[k][2]};
+            if (k > 0)
+                for (int c = 0; c < 6; ++c) v[c] += noise(0.03);
+            kfs[k]._TCW = SE3::exp(v);
+        }
+        auto rms = [&]() {
+            double s2 = 0;
+            for (int j = 0; j < 16; ++j)
+                for (int k = 0; k < 8; ++k) {
+                    const Vector2d px = cam.World2Pixel(pts[j]._pos_world, kfs[k]._TCW);
+                    const Feature* f = pts[j]._obs[k];
+                    s2 += (px[0] - f->_pixel[0]) * (px[0] - f->_pixel[0]) + (px[1] - f->_pixel[1]) * (px[1] - f->_pixel[1]);
+                }
+            return std::sqrt(s2 / (16 * 8));
+        };
+        std::set<Frame*> lk;
+        std::set<MapPoint*> lm;
+        for (auto& f : kfs) lk.insert(&f);
+        for (auto& m_ : pts) lm.insert(&m_);
+        const double before = rms();
+        if (flavour == 0) ba::LocalBAG2O(lk, lm, keyframe_of);
+        else ba::LocalBA(lk, lm, keyframe_of);
+        double T0[12];
+        kfs[0]._TCW.matrix3x4(T0);
+        printf("local_ba %s rms_px_before %.4f after %.6f kf0_moved %d\n", flavour == 0 ? "g2o" : "ceres", before, rms(),
+               (int)(std::fabs(T0[3]) + std::fabs(T0[7]) + std::fabs(T0[11]) > 1e-12));
+    }
     return 0;
 }

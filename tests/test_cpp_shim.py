@@ -56,3 +56,8 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     assert parts[2] == "1" and abs(int(parts[4]) - keep.sum()) <= 3
     want_disp = np.linalg.norm(ref[keep] - cur[keep], axis=1).mean()
     assert abs(float(parts[6]) - want_disp) < 0.02
+    # both bundle-adjustment flavours (ba::LocalBAG2O, ba::LocalBA) on the test_local_ba.cpp fixture: noise-free
+    # observations, so the reprojection error must collapse; key-frame 0 keeps its pose
+    for line, name in ((lines[4], "g2o"), (lines[5], "ceres")):
+        parts = line.split()
+        assert parts[1] == name and float(parts[3]) > 1.0 and float(parts[5]) < 1e-3 and parts[7] == "0"

@@ -85,3 +85,34 @@ def test_pose_only_matches_oracle(ctx3, oracle):
         assert cnt[p] == wcnt
         assert np.array_equal(inl[s], winl)
         assert np.allclose(depth[s], wdepth, atol=1e-6)
+
+
+def _t_aa(v):  # se3 log [upsilon; omega] -> [t; angle-axis] (the pose block of CeresReprojectionError)
+    out = []
+    for x in np.atleast_2d(v):
+        T = se3.se3_exp(x)
+        out.append(np.r_[T[:, 3], se3.so3_log(T[:, :3])])
+    return np.array(out)
+
+
+def test_local_ba_ceres_twin_matches_oracle(ctx3, oracle):
+    """ba::LocalBA (BA.cpp:324-384): two problems in one launch, the second with a different size."""
+    a = synth.ba_scene()
+    b = synth.ba_scene(n_kf=6, n_pt=300, target_obs=1500, seed=12)
+    fa = np.zeros(10, np.uint8); fa[0] = 1
+    fb = np.zeros(6, np.uint8); fb[0] = 1
+    na, nb = len(a["kf_idx"]), len(b["kf_idx"])
+    Pa, Pb = _t_aa(a["poses_noisy"]), _t_aa(b["poses_noisy"])
+    P, X, st = ctx3.local_ba_ceres([0, 10, 16], [0, 2000, 2300], [0, na, na + nb], np.concatenate([Pa, Pb]), np.concatenate([fa, fb]),
+                                   np.concatenate([a["pts_noisy"], b["pts_noisy"]]), np.concatenate([a["kf_idx"], b["kf_idx"]]),
+                                   np.concatenate([a["pt_idx"], b["pt_idx"]]), np.concatenate([a["px"], b["px"]]))
+    for i, (sc, f, P0, ps, xs) in enumerate(((a, fa, Pa, slice(0, 10), slice(0, 2000)), (b, fb, Pb, slice(10, 16), slice(2000, 2300)))):
+        wP, wX, wst = oracle.local_ba_ceres(P0, f, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"])
+        assert np.abs(P[ps] - wP).max() < 1e-6, i          # [t; angle-axis] within 1e-6 (tolerance of the float path: 1e-4)
+        assert np.abs(X[xs] - wX).max() < 1e-6, i
+        assert st[i]["iters"] == wst["iters"] and st[i]["successful_steps"] == wst["successful_steps"], (st[i], wst)
+        assert st[i]["termination"] == wst["termination"]
+        assert abs(st[i]["cost_final"] - wst["cost_final"]) < 1e-9 * max(wst["cost_final"], 1e-12)
+        assert abs(st[i]["cost_initial"] - wst["cost_initial"]) < 1e-12 * wst["cost_initial"]
+        assert np.array_equal(P[ps][0], P0[0])               # key-frame 0: point-only residual blocks
+        assert np.abs(P[ps] - _t_aa(sc["poses_true"])).max() < 0.01

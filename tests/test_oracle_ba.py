@@ -77,3 +77,31 @@ def test_pose_only_rejects_outliers(oracle):
     # fewer than 10 inliers: the loop breaks and the pose is left at the input (BA.cpp:248-249)
     T2, inl2, _, cnt2 = oracle.pose_only(pw[:8], px[:8] + 100, Tn)
     assert cnt2 == 0 and np.allclose(T2, Tn, atol=1e-12)
+
+
+def _t_aa(v):  # [upsilon; omega] (se3 log) -> [t; angle-axis] of the same transform (CeresReprojectionError's pose)
+    out = []
+    for x in np.atleast_2d(v):
+        T = se3.se3_exp(x)
+        out.append(np.r_[T[:, 3], se3.so3_log(T[:, :3])])
+    return np.array(out)
+
+
+def test_local_ba_ceres_twin_c4_scene(oracle):
+    """ba::LocalBA (Ceres flavour, BA.cpp:324-384): normalised residuals, no loss, [t; angle-axis] poses."""
+    sc = synth.ba_scene()
+    fixed = np.zeros(10, np.uint8)
+    fixed[0] = 1
+    P0 = _t_aa(sc["poses_noisy"])
+    P, X, st = oracle.local_ba_ceres(P0, fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"])
+    assert st["cost_final"] < 2e-3 * st["cost_initial"]
+    assert st["termination"] in (1, 2, 3) and 3 <= st["iters"] <= 50
+    assert np.allclose(P[0], P0[0])                                      # the first key-frame only has point-only blocks
+    assert np.abs(P - _t_aa(sc["poses_true"])).max() < 0.01
+    assert np.median(np.abs(X - sc["pts_true"])) < 0.05
+    # same minimum as the g2o flavour without its robust kernel (both are exact Gauss-Newton-type solvers of the same
+    # least-squares problem up to the residual scaling 1/f): compare the optimised poses as transforms
+    Pg, Xg, _, _ = oracle.local_ba(_g2o(sc["poses_noisy"]), fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"], huber=0.0,
+                                   max_iters=50)
+    est_g = _t_aa(np.concatenate([Pg[:, 3:], Pg[:, :3]], 1))
+    assert np.abs(P - est_g).max() < 2e-3

@@ -38,7 +38,7 @@ EXPORTS = [
     "ygzb_frames_upload", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
     "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d", "ygzb_align1d",
-    "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_pose_only",
+    "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_pose_only",
     "ygzb_default_klt_params", "ygzb_klt",
 ]
 
@@ -460,6 +460,26 @@ def _local_ba(self, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, 
     return poses, pts, outl.astype(bool), stats
 
 
+class CeresStats(C.Structure):
+    _fields_ = [("iters", C.c_int), ("successful_steps", C.c_int), ("cost_initial", C.c_double), ("cost_final", C.c_double),
+                ("radius_final", C.c_double), ("termination", C.c_int)]
+
+
+def _local_ba_ceres(self, kf_off, pt_off, obs_off, poses_t_aa, fixed, pts, kf_idx, pt_idx, px, max_iters=50):
+    """Batched ba::LocalBA (Ceres twin).  poses: (n_kf, 6) as [t; angle-axis]."""
+    kf_off = np.ascontiguousarray(kf_off, np.int32)
+    P = len(kf_off) - 1
+    poses = np.ascontiguousarray(poses_t_aa, np.float64).copy()
+    pts = np.ascontiguousarray(pts, np.float64).copy()
+    st = (CeresStats * P)()
+    self.check(self.lib.ygzb_local_ba_ceres(self.h, P, _p(kf_off), _p(np.ascontiguousarray(pt_off, np.int32)),
+                                            _p(np.ascontiguousarray(obs_off, np.int32)), _p(poses),
+                                            _p(np.ascontiguousarray(fixed, np.uint8)), _p(pts),
+                                            _p(np.ascontiguousarray(kf_idx, np.int32)), _p(np.ascontiguousarray(pt_idx, np.int32)),
+                                            _p(np.ascontiguousarray(px, np.float64)), max_iters, st), "ygzb_local_ba_ceres")
+    return poses, pts, [{k: getattr(s_, k) for k, _ in CeresStats._fields_} for s_ in st]
+
+
 def _pose_only(self, offsets, pt_world, px, T_cw):
     offsets = np.ascontiguousarray(offsets, np.int32)
     P = len(offsets) - 1
@@ -475,6 +495,7 @@ def _pose_only(self, offsets, pt_world, px, T_cw):
 
 
 Context.local_ba = _local_ba
+Context.local_ba_ceres = _local_ba_ceres
 Context.pose_only = _pose_only
 
 

@@ -63,6 +63,7 @@ struct BAArgs {
     double* Dinv;             // [n_pt][9]
     double* xl;               // [n_pt][3]
     double* pts_backup;       // [n_pt][3]
+    double* scale_l;          // [n_pt][3]  Ceres twin: Jacobi scaling of the landmark columns
     uint8_t* outlier;         // [n_obs]
     double* stats;            // [n_problems][8]: iters, trials, chi_first, chi_last, lambda, n_outliers
     float fx, fy, cx, cy;
@@ -136,6 +137,126 @@ __device__ __forceinline__ void make_hpl(const double* __restrict__ rec, double 
         for (int b = 0; b < 3; ++b) Hpl[a][b] = w * (Jp[a] * Jl[b] + Jp[6 + a] * Jl[3 + b]);
 }
 
+// ---- ba::LocalBA (Ceres twin): residual of CeresReprojectionError with forward-mode jets ---------------------------
+// pose = [t; angle-axis], X = world point, (c0, c1) = normalised observation.  9 partials: 0..5 pose, 6..8 point --
+// what ceres::AutoDiffCostFunction<CeresReprojectionError, 2, 6, 3> evaluates (reference
+// include/ygz/Ceres/CeresReprojectionError.h:33-69, ceres/rotation.h AngleAxisRotatePoint).  The operation order
+// follows oracle/ba.cpp so that the two agree to rounding.
+struct Jet9 {
+    double a;
+    double v[9];
+};
+__device__ __forceinline__ Jet9 j9c(double c) {
+    Jet9 r;
+    r.a = c;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.v[i] = 0.0;
+    return r;
+}
+__device__ __forceinline__ Jet9 operator+(const Jet9& x, const Jet9& y) {
+    Jet9 r;
+    r.a = x.a + y.a;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.v[i] = x.v[i] + y.v[i];
+    return r;
+}
+__device__ __forceinline__ Jet9 operator-(const Jet9& x, const Jet9& y) {
+    Jet9 r;
+    r.a = x.a - y.a;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.v[i] = x.v[i] - y.v[i];
+    return r;
+}
+__device__ __forceinline__ Jet9 operator*(const Jet9& x, const Jet9& y) {
+    Jet9 r;
+    r.a = x.a * y.a;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.v[i] = x.a * y.v[i] + x.v[i] * y.a;
+    return r;
+}
+__device__ __forceinline__ Jet9 operator/(const Jet9& x, const Jet9& y) {
+    const double inv = 1.0 / y.a, q = x.a * inv;
+    Jet9 r;
+    r.a = q;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.v[i] = (x.v[i] - q * y.v[i]) * inv;
+    return r;
+}
+
+// value only: p = AngleAxisRotatePoint(aa, X) + t
+__device__ __forceinline__ void ceres_project(const double* __restrict__ pose, double X0, double X1, double X2, double p[3]) {
+    const double a0 = pose[3], a1 = pose[4], a2 = pose[5];
+    const double theta2 = a0 * a0 + a1 * a1 + a2 * a2;
+    if (theta2 > 2.2204460492503131e-16) {
+        const double theta = sqrt(theta2), costheta = cos(theta), sintheta = sin(theta), inv = 1.0 / theta;
+        const double w0 = a0 * inv, w1 = a1 * inv, w2 = a2 * inv;
+        const double c0 = w1 * X2 - w2 * X1, c1 = w2 * X0 - w0 * X2, c2 = w0 * X1 - w1 * X0;
+        const double tmp = (w0 * X0 + w1 * X1 + w2 * X2) * (1.0 - costheta);
+        p[0] = X0 * costheta + c0 * sintheta + w0 * tmp;
+        p[1] = X1 * costheta + c1 * sintheta + w1 * tmp;
+        p[2] = X2 * costheta + c2 * sintheta + w2 * tmp;
+    } else {
+        p[0] = X0 + (a1 * X2 - a2 * X1);
+        p[1] = X1 + (a2 * X0 - a0 * X2);
+        p[2] = X2 + (a0 * X1 - a1 * X0);
+    }
+    p[0] += pose[0];
+    p[1] += pose[1];
+    p[2] += pose[2];
+}
+
+// residual + Jacobians into a linearisation record: rec = e(2) w(=1) Jl(2x3) Jp(2x6)
+__device__ __noinline__ void ceres_linearise(const double* __restrict__ pose, double X0, double X1, double X2, double c0, double c1,
+                                             double* __restrict__ rec) {
+    Jet9 T[6], Xj[3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        T[i] = j9c(pose[i]);
+        T[i].v[i] = 1.0;
+    }
+    Xj[0] = j9c(X0); Xj[1] = j9c(X1); Xj[2] = j9c(X2);
+    Xj[0].v[6] = 1.0; Xj[1].v[7] = 1.0; Xj[2].v[8] = 1.0;
+    Jet9 p[3];
+    const Jet9 theta2 = T[3] * T[3] + T[4] * T[4] + T[5] * T[5];
+    if (theta2.a > 2.2204460492503131e-16) {
+        const double th = sqrt(theta2.a), dth = 1.0 / (2.0 * th);
+        Jet9 theta, costheta, sintheta;
+        theta.a = th; costheta.a = cos(th); sintheta.a = sin(th);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            theta.v[i] = theta2.v[i] * dth;
+            costheta.v[i] = -sintheta.a * theta.v[i];
+            sintheta.v[i] = costheta.a * theta.v[i];
+        }
+        const Jet9 inv = j9c(1.0) / theta;
+        const Jet9 w0 = T[3] * inv, w1 = T[4] * inv, w2 = T[5] * inv;
+        const Jet9 x0 = w1 * Xj[2] - w2 * Xj[1], x1 = w2 * Xj[0] - w0 * Xj[2], x2 = w0 * Xj[1] - w1 * Xj[0];
+        const Jet9 tmp = (w0 * Xj[0] + w1 * Xj[1] + w2 * Xj[2]) * (j9c(1.0) - costheta);
+        p[0] = Xj[0] * costheta + x0 * sintheta + w0 * tmp;
+        p[1] = Xj[1] * costheta + x1 * sintheta + w1 * tmp;
+        p[2] = Xj[2] * costheta + x2 * sintheta + w2 * tmp;
+    } else {
+        p[0] = Xj[0] + (T[4] * Xj[2] - T[5] * Xj[1]);
+        p[1] = Xj[1] + (T[5] * Xj[0] - T[3] * Xj[2]);
+        p[2] = Xj[2] + (T[3] * Xj[1] - T[4] * Xj[0]);
+    }
+    p[0] = p[0] + T[0];
+    p[1] = p[1] + T[1];
+    p[2] = p[2] + T[2];
+    const Jet9 r0 = j9c(c0) - p[0] / p[2], r1 = j9c(c1) - p[1] / p[2];
+    rec[0] = r0.a; rec[1] = r1.a; rec[2] = 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        rec[3 + k] = r0.v[6 + k];
+        rec[6 + k] = r1.v[6 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        rec[9 + k] = r0.v[k];
+        rec[15 + k] = r1.v[k];
+    }
+}
+
 // ---- local BA: one thread-block CLUSTER (kClusterSize CTAs on kClusterSize SMs) per problem ---------------------
 // The observation / landmark / pair-entry loops stride over the whole cluster, the per-pose and per-block-pair sums
 // are warp-reduced and combined with f64 global atomics (RED.ADD.F64) into a small L2-resident workspace, scalar
@@ -153,6 +274,11 @@ struct ClusterWs {            // per problem, in global memory
     int ok;
 };
 
+// kCeres = false: ba::LocalBAG2O (g2o Levenberg, Huber kernel, pixel residuals, exp-map pose update)
+// kCeres = true : ba::LocalBA   (Ceres trust-region LM with Jacobi scaling, no loss, normalised residuals, poses as
+//                 [t; angle-axis] with additive updates) -- the same reduction / Schur / Cholesky machinery with
+//                 per-parameter damping d_k = clamp(s_k^2 H_kk, 1e-6, 1e32) / (radius s_k^2) instead of lambda
+template <bool kCeres>
 __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, ClusterWs* __restrict__ ws_all) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -162,6 +288,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
     __shared__ double s_pose[kMaxPoses][6];    // replica of the pose estimates (g2o order)
     __shared__ double s_backup[kMaxPoses][6];
     __shared__ double s_xp[kMaxFreePoses * 6];
+    __shared__ double s_sp[kMaxFreePoses * 6];   // Ceres twin: Jacobi scaling of the pose columns
     __shared__ int s_free[kMaxPoses];
     __shared__ int s_np;
 
@@ -191,7 +318,9 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
     int red_slot = 0;
 
     auto refresh_poses = [&]() {
-        if (tid < n_kf) se3_to_mat(pose_from_g2o(s_pose[tid]), s_R[tid]);
+        if constexpr (!kCeres) {
+            if (tid < n_kf) se3_to_mat(pose_from_g2o(s_pose[tid]), s_R[tid]);
+        }
         __syncthreads();
     };
     // cluster-wide sum of up to 2 values (identical result in every thread of every CTA); contains a cluster barrier
@@ -214,16 +343,30 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
         *out1 = s1;
     };
     auto reproject = [&](int o, double* e0, double* e1, double* px, double* py, double* pz) {
-        const double* Tm = s_R[a.kf_idx[o0 + o]];
         const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
         const double X0 = __ldcg(X), X1 = __ldcg(X + 1), X2 = __ldcg(X + 2);
-        const double x = Tm[0] * X0 + Tm[1] * X1 + Tm[2] * X2 + Tm[3];
-        const double y = Tm[4] * X0 + Tm[5] * X1 + Tm[6] * X2 + Tm[7];
-        const double z = Tm[8] * X0 + Tm[9] * X1 + Tm[10] * X2 + Tm[11];
-        *e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx);
-        *e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
-        *px = x; *py = y; *pz = z;
+        if constexpr (kCeres) {
+            double p[3];
+            ceres_project(s_pose[a.kf_idx[o0 + o]], X0, X1, X2, p);
+            const double iz = 1.0 / p[2];
+            // PinholeCamera::Pixel2Camera2D: float intrinsics, double maths
+            *e0 = (a.obs[2 * (size_t)(o0 + o)] - cx) / fx - p[0] * iz;
+            *e1 = (a.obs[2 * (size_t)(o0 + o) + 1] - cy) / fy - p[1] * iz;
+            *px = p[0]; *py = p[1]; *pz = p[2];
+        } else {
+            const double* Tm = s_R[a.kf_idx[o0 + o]];
+            const double x = Tm[0] * X0 + Tm[1] * X1 + Tm[2] * X2 + Tm[3];
+            const double y = Tm[4] * X0 + Tm[5] * X1 + Tm[6] * X2 + Tm[7];
+            const double z = Tm[8] * X0 + Tm[9] * X1 + Tm[10] * X2 + Tm[11];
+            *e0 = a.obs[2 * (size_t)(o0 + o)] - (x / z * fx + cx);
+            *e1 = a.obs[2 * (size_t)(o0 + o) + 1] - (y / z * fy + cy);
+            *px = x; *py = y; *pz = z;
+        }
     };
+    // Ceres twin: LM damping of one parameter from its Hessian diagonal and Jacobi scale
+    double radius = 1e4, decrease_factor = 2.0;
+    auto damp = [&](double hkk, double sk) { return fmin(fmax(sk * sk * hkk, 1e-6), 1e32) / radius / (sk * sk); };
+    int term = 0, n_success = 0;   // Ceres twin: termination code (see ygz_b200.h), accepted steps
 
     refresh_poses();
     int iters = 0, trials_total = 0;
@@ -234,31 +377,41 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
         for (int i = ct; i < np * 36; i += CT) ws.Hpp[i] = 0.0;
         for (int i = ct; i < dimp; i += CT) ws.bp[i] = 0.0;
         double acc = 0;
-        for (int o = ct; o < n_obs; o += CT) {
-            double e0, e1, x, y, z;
-            reproject(o, &e0, &e1, &x, &y, &z);
-            const double e2 = e0 * e0 + e1 * e1;
-            double w = 1.0;
-            if (a.huber_delta > 0 && e2 > dsqr) {
-                w = a.huber_delta / sqrt(e2);
-                acc += 2 * sqrt(e2) * a.huber_delta - dsqr;
-            } else {
-                acc += e2;
+        if constexpr (kCeres) {
+            for (int o = ct; o < n_obs; o += CT) {
+                const double* X = a.pts + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
+                double* rec = a.lin + 21 * (size_t)(o0 + o);
+                ceres_linearise(s_pose[a.kf_idx[o0 + o]], __ldcg(X), __ldcg(X + 1), __ldcg(X + 2),
+                                (a.obs[2 * (size_t)(o0 + o)] - cx) / fx, (a.obs[2 * (size_t)(o0 + o) + 1] - cy) / fy, rec);
+                acc += rec[0] * rec[0] + rec[1] * rec[1];
             }
-            const double* Tm = s_R[a.kf_idx[o0 + o]];
-            double* rec = a.lin + 21 * (size_t)(o0 + o);
-            rec[0] = e0; rec[1] = e1; rec[2] = w;
-            const double z_2 = z * z, iz = -1. / z;
-            const double t02 = -x / z * fx, t12 = -y / z * fy;
+        } else {
+            for (int o = ct; o < n_obs; o += CT) {
+                double e0, e1, x, y, z;
+                reproject(o, &e0, &e1, &x, &y, &z);
+                const double e2 = e0 * e0 + e1 * e1;
+                double w = 1.0;
+                if (a.huber_delta > 0 && e2 > dsqr) {
+                    w = a.huber_delta / sqrt(e2);
+                    acc += 2 * sqrt(e2) * a.huber_delta - dsqr;
+                } else {
+                    acc += e2;
+                }
+                const double* Tm = s_R[a.kf_idx[o0 + o]];
+                double* rec = a.lin + 21 * (size_t)(o0 + o);
+                rec[0] = e0; rec[1] = e1; rec[2] = w;
+                const double z_2 = z * z, iz = -1. / z;
+                const double t02 = -x / z * fx, t12 = -y / z * fy;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                rec[3 + c] = iz * (fx * Tm[c] + t02 * Tm[8 + c]);
-                rec[6 + c] = iz * (fy * Tm[4 + c] + t12 * Tm[8 + c]);
+                for (int c = 0; c < 3; ++c) {
+                    rec[3 + c] = iz * (fx * Tm[c] + t02 * Tm[8 + c]);
+                    rec[6 + c] = iz * (fy * Tm[4 + c] + t12 * Tm[8 + c]);
+                }
+                rec[9] = x * y / z_2 * fx; rec[10] = -(1 + (x * x / z_2)) * fx; rec[11] = y / z * fx;
+                rec[12] = -1. / z * fx; rec[13] = 0; rec[14] = x / z_2 * fx;
+                rec[15] = (1 + y * y / z_2) * fy; rec[16] = -x * y / z_2 * fy; rec[17] = -x / z * fy;
+                rec[18] = 0; rec[19] = -1. / z * fy; rec[20] = y / z_2 * fy;
             }
-            rec[9] = x * y / z_2 * fx; rec[10] = -(1 + (x * x / z_2)) * fx; rec[11] = y / z * fx;
-            rec[12] = -1. / z * fx; rec[13] = 0; rec[14] = x / z_2 * fx;
-            rec[15] = (1 + y * y / z_2) * fy; rec[16] = -x * y / z_2 * fy; rec[17] = -x / z * fy;
-            rec[18] = 0; rec[19] = -1. / z * fy; rec[20] = y / z_2 * fy;
         }
         double dummy;
         cluster_sum2(acc, 0.0, &currentChi, &dummy);   // (barrier: lin[] and the zeroed Hpp/bp are visible cluster-wide)
@@ -282,7 +435,15 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
             Hj[0] = H[0]; Hj[1] = H[1]; Hj[2] = H[2]; Hj[3] = H[1]; Hj[4] = H[3]; Hj[5] = H[4]; Hj[6] = H[2]; Hj[7] = H[4]; Hj[8] = H[5];
             double* bj = a.bl + 3 * (size_t)(p0 + j);
             bj[0] = b[0]; bj[1] = b[1]; bj[2] = b[2];
-            mx = fmax(mx, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
+            if constexpr (kCeres) {
+                mx = fmax(mx, fmax(fabs(b[0]), fmax(fabs(b[1]), fabs(b[2]))));   // gradient max norm
+                if (iteration == 0) {  // Jacobi scaling from the initial Jacobian: 1 / (1 + ||column||)
+                    double* sj = a.scale_l + 3 * (size_t)(p0 + j);
+                    sj[0] = 1.0 / (1.0 + sqrt(H[0])); sj[1] = 1.0 / (1.0 + sqrt(H[3])); sj[2] = 1.0 / (1.0 + sqrt(H[5]));
+                }
+            } else {
+                mx = fmax(mx, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
+            }
         }
         // Hpp, bp : (free pose, chunk) tasks over all warps of the cluster, f64 atomics into the workspace
         if (np > 0) {
@@ -335,13 +496,21 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
             cluster.sync();                                   // also publishes Hll/bl and the Hpp/bp atomics
             m0 = 0;
             for (int r = 0; r < C; ++r) m0 = fmax(m0, __ldcg(&ws.red[slot][r][0]));
-            if (iteration == 0) {  // computeLambdaInit = tau * max |diag H|
+            if constexpr (kCeres) {
+                for (int i = 0; i < dimp; ++i) m0 = fmax(m0, fabs(__ldcg(&ws.bp[i])));
+                if (iteration == 0) {
+                    if (tid < dimp) s_sp[tid] = 1.0 / (1.0 + sqrt(__ldcg(&ws.Hpp[(tid / 6) * 36 + (tid % 6) * 7])));
+                    __syncthreads();
+                }
+                if (m0 <= 1e-10) term = 1;   // gradient tolerance
+            } else if (iteration == 0) {  // computeLambdaInit = tau * max |diag H|
                 for (int i = 0; i < dimp; ++i) m0 = fmax(m0, fabs(__ldcg(&ws.Hpp[(i / 6) * 36 + (i % 6) * 7])));
                 lambda = a.tau * m0;
                 ni = 2;
             }
             (void)m1;
         }
+        if (kCeres && term) break;
 
         int qmax = 0;
         do {
@@ -353,7 +522,12 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                 const double* Hj = a.Hll + 9 * (size_t)(p0 + j);
 #pragma unroll
                 for (int t = 0; t < 9; ++t) D[t] = Hj[t];
-                D[0] += lambda; D[4] += lambda; D[8] += lambda;
+                if constexpr (kCeres) {
+                    const double* sj = a.scale_l + 3 * (size_t)(p0 + j);
+                    D[0] += damp(Hj[0], sj[0]); D[4] += damp(Hj[4], sj[1]); D[8] += damp(Hj[8], sj[2]);
+                } else {
+                    D[0] += lambda; D[4] += lambda; D[8] += lambda;
+                }
                 inverse3d(D, a.Dinv + 9 * (size_t)(p0 + j));
 #pragma unroll
                 for (int c = 0; c < 3; ++c) a.pts_backup[3 * (size_t)(p0 + j) + c] = a.pts[3 * (size_t)(p0 + j) + c];
@@ -428,7 +602,10 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                 for (int i = tid; i < dimp * dimp; i += T) {
                     const int r = i / dimp, c = i - r * dimp;
                     double v = __ldcg(&ws.S[i]);
-                    if (r / 6 == c / 6) v += __ldcg(&ws.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)]) + (r == c ? lambda : 0.0);
+                    if (r / 6 == c / 6) {
+                        const double h = __ldcg(&ws.Hpp[(r / 6) * 36 + (r % 6) * 6 + (c % 6)]);
+                        v += h + (r == c ? (kCeres ? damp(h, s_sp[r]) : lambda) : 0.0);
+                    }
                     s_S[i] = v;
                 }
                 if (tid < dimp) s_bs[tid] = __ldcg(&ws.bs[tid]) + __ldcg(&ws.bp[tid]);
@@ -481,7 +658,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
             if (tid < dimp) s_xp[tid] = __ldcg(&ws.xp[tid]);
             __syncthreads();
             // landmark back-substitution + update (owner thread), pose update (replicated), scale term
-            double scale = 0;
+            double scale = 0, xnorm2 = 0;
             for (int j = ct; j < n_pt; j += CT) {
                 const double* bj = a.bl + 3 * (size_t)(p0 + j);
                 double r[3] = {bj[0], bj[1], bj[2]};
@@ -501,48 +678,130 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const double x = Di[3 * c] * r[0] + Di[3 * c + 1] * r[1] + Di[3 * c + 2] * r[2];
-                    scale += x * (lambda * x + bj[c]);
+                    if constexpr (kCeres) {
+                        a.xl[3 * (size_t)(p0 + j) + c] = x;   // the model cost change needs J delta per observation
+                        scale += x * x;                      // |step|^2
+                        xnorm2 += X[c] * X[c];
+                    } else {
+                        scale += x * (lambda * x + bj[c]);
+                    }
                     X[c] += x;
                 }
             }
-            if (rank == 0 && tid < dimp) scale += s_xp[tid] * (lambda * s_xp[tid] + __ldcg(&ws.bp[tid]));
-            if (tid < n_kf && s_free[tid] >= 0) {  // VertexSE3Sophus::oplusImpl on the replica
-                const double* u = s_xp + 6 * s_free[tid];
-                const double v[6] = {u[3], u[4], u[5], u[0], u[1], u[2]};
-                const SE3d Tn = se3_mul(se3_exp(v), pose_from_g2o(s_pose[tid]));
-                double lg[6];
-                se3_log(Tn, lg);
-                s_pose[tid][0] = lg[3]; s_pose[tid][1] = lg[4]; s_pose[tid][2] = lg[5];
-                s_pose[tid][3] = lg[0]; s_pose[tid][4] = lg[1]; s_pose[tid][5] = lg[2];
+            if constexpr (kCeres) {
+                if (rank == 0 && tid < n_kf && s_free[tid] >= 0) {
+                    const double* u = s_xp + 6 * s_free[tid];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) {
+                        scale += u[c] * u[c];
+                        xnorm2 += s_pose[tid][c] * s_pose[tid][c];
+                    }
+                }
+                if (tid < n_kf && s_free[tid] >= 0) {  // plain Euclidean parameter block: x + delta
+                    const double* u = s_xp + 6 * s_free[tid];
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) s_pose[tid][c] += u[c];
+                }
+            } else {
+                if (rank == 0 && tid < dimp) scale += s_xp[tid] * (lambda * s_xp[tid] + __ldcg(&ws.bp[tid]));
+                if (tid < n_kf && s_free[tid] >= 0) {  // VertexSE3Sophus::oplusImpl on the replica
+                    const double* u = s_xp + 6 * s_free[tid];
+                    const double v[6] = {u[3], u[4], u[5], u[0], u[1], u[2]};
+                    const SE3d Tn = se3_mul(se3_exp(v), pose_from_g2o(s_pose[tid]));
+                    double lg[6];
+                    se3_log(Tn, lg);
+                    s_pose[tid][0] = lg[3]; s_pose[tid][1] = lg[4]; s_pose[tid][2] = lg[5];
+                    s_pose[tid][3] = lg[0]; s_pose[tid][4] = lg[1]; s_pose[tid][5] = lg[2];
+                }
             }
             __syncthreads();
             refresh_poses();
             double scale_tot, dummy2;
-            cluster_sum2(scale, 0.0, &scale_tot, &dummy2);    // (barrier: updated landmarks visible cluster-wide)
-            scale_tot += 1e-3;
-            double chi_part = 0;
-            for (int o = ct; o < n_obs; o += CT) {
-                double e0, e1, x, y, z;
-                reproject(o, &e0, &e1, &x, &y, &z);
-                const double e2 = e0 * e0 + e1 * e1;
-                chi_part += (a.huber_delta > 0 && e2 > dsqr) ? 2 * sqrt(e2) * a.huber_delta - dsqr : e2;
-            }
-            double tempChi;
-            cluster_sum2(chi_part, 0.0, &tempChi, &dummy2);
-            if (!ok2) tempChi = 1.7976931348623157e308;
-            rho = (currentChi - tempChi) / scale_tot;
             bool accept;
-            if (rho > 0 && isfinite(tempChi)) {
-                double alpha = 1. - pow((2 * rho - 1), 3);
-                alpha = fmin(alpha, 2. / 3.);
-                lambda *= fmax(1. / 3., alpha);
-                ni = 2;
-                currentChi = tempChi;
-                accept = true;
+            if constexpr (kCeres) {
+                double step2, x2;
+                cluster_sum2(scale, xnorm2, &step2, &x2);   // (barrier: updated landmarks and xl visible cluster-wide)
+                // candidate cost and model cost change -(J delta)^T (r + J delta / 2), one pass over the observations
+                double newc = 0, model = 0;
+                for (int o = ct; o < n_obs; o += CT) {
+                    double e0, e1, x, y, z;
+                    reproject(o, &e0, &e1, &x, &y, &z);
+                    newc += e0 * e0 + e1 * e1;
+                    const double* rec = a.lin + 21 * (size_t)(o0 + o);
+                    const int fi = s_free[a.kf_idx[o0 + o]];
+                    const double* dl = a.xl + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
+                    const double d0 = __ldcg(dl), d1 = __ldcg(dl + 1), d2 = __ldcg(dl + 2);
+#pragma unroll
+                    for (int row = 0; row < 2; ++row) {
+                        double jy = 0;
+                        if (fi >= 0) {
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) jy += rec[9 + 6 * row + k] * s_xp[6 * fi + k];
+                        }
+                        jy += rec[3 + 3 * row] * d0;
+                        jy += rec[4 + 3 * row] * d1;
+                        jy += rec[5 + 3 * row] * d2;
+                        model -= jy * (rec[row] + jy / 2);
+                    }
+                }
+                double newc_tot, model_tot;
+                cluster_sum2(newc, model, &newc_tot, &model_tot);
+                const double cost = 0.5 * currentChi, new_cost = 0.5 * newc_tot;
+                bool accepted = false;
+                double relative_decrease = 0;
+                if (ok2 && model_tot > 0) {
+                    relative_decrease = (cost - new_cost) / model_tot;
+                    accepted = relative_decrease > 1e-3;
+                }
+                accept = accepted;
+                if (accepted) {
+                    if (sqrt(step2) <= 1e-8 * (sqrt(x2) + 1e-8)) {  // parameter tolerance: checked before the step is taken
+                        term = 2;
+                        accept = false;
+                    } else {
+                        ++n_success;
+                        currentChi = newc_tot;
+                        if (fabs(cost - new_cost) <= 1e-6 * cost) {
+                            term = 3;   // function tolerance
+                        } else {
+                            radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3));
+                            radius = fmin(1e16, radius);
+                            decrease_factor = 2.0;
+                        }
+                    }
+                } else {
+                    radius = radius / decrease_factor;
+                    decrease_factor *= 2.0;
+                    if (radius < 1e-32) term = 4;
+                }
+                rho = accepted ? 1.0 : -1.0;
+                (void)scale_tot; (void)dummy2;
             } else {
-                lambda *= ni;
-                ni *= 2;
-                accept = false;
+                cluster_sum2(scale, 0.0, &scale_tot, &dummy2);    // (barrier: updated landmarks visible cluster-wide)
+                scale_tot += 1e-3;
+                double chi_part = 0;
+                for (int o = ct; o < n_obs; o += CT) {
+                    double e0, e1, x, y, z;
+                    reproject(o, &e0, &e1, &x, &y, &z);
+                    const double e2 = e0 * e0 + e1 * e1;
+                    chi_part += (a.huber_delta > 0 && e2 > dsqr) ? 2 * sqrt(e2) * a.huber_delta - dsqr : e2;
+                }
+                double tempChi;
+                cluster_sum2(chi_part, 0.0, &tempChi, &dummy2);
+                if (!ok2) tempChi = 1.7976931348623157e308;
+                rho = (currentChi - tempChi) / scale_tot;
+                if (rho > 0 && isfinite(tempChi)) {
+                    double alpha = 1. - pow((2 * rho - 1), 3);
+                    alpha = fmin(alpha, 2. / 3.);
+                    lambda *= fmax(1. / 3., alpha);
+                    ni = 2;
+                    currentChi = tempChi;
+                    accept = true;
+                } else {
+                    lambda *= ni;
+                    ni *= 2;
+                    accept = false;
+                }
             }
             if (!accept) {  // _optimizer->pop()
                 if (tid < n_kf)
@@ -555,10 +814,14 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
             }
             ++qmax;
             ++trials_total;
-        } while (rho < 0 && qmax < a.max_trials);
+        } while (kCeres ? (rho < 0 && !term && trials_total < a.max_iters) : (rho < 0 && qmax < a.max_trials));
         ++iters;
         chi_last = currentChi;
-        if (qmax == a.max_trials || rho == 0) break;
+        if constexpr (kCeres) {
+            if (term || trials_total >= a.max_iters) break;
+        } else {
+            if (qmax == a.max_trials || rho == 0) break;
+        }
     }
     cluster.sync();  // a rejected last trial restored landmarks owned by other CTAs
     // outlier flags (BA.cpp:505-515): plain chi2 > 5.991
@@ -566,7 +829,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
     for (int o = ct; o < n_obs; o += CT) {
         double e0, e1, x, y, z;
         reproject(o, &e0, &e1, &x, &y, &z);
-        const int out = (e0 * e0 + e1 * e1 > a.chi2_outlier) ? 1 : 0;
+        const int out = (!kCeres && e0 * e0 + e1 * e1 > a.chi2_outlier) ? 1 : 0;   // ba::LocalBA marks nothing
         a.outlier[o0 + o] = (uint8_t)out;
         n_out += out;
     }
@@ -577,7 +840,11 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
             for (int c = 0; c < 6; ++c) a.poses[6 * (size_t)(k0 + tid) + c] = s_pose[tid][c];
         if (tid == 0) {
             double* st = a.stats + 8 * (size_t)prob;
-            st[0] = iters; st[1] = trials_total; st[2] = chi_first; st[3] = chi_last; st[4] = lambda; st[5] = n_out_tot;
+            if constexpr (kCeres) {
+                st[0] = trials_total; st[1] = n_success; st[2] = 0.5 * chi_first; st[3] = 0.5 * chi_last; st[4] = radius; st[5] = term;
+            } else {
+                st[0] = iters; st[1] = trials_total; st[2] = chi_first; st[3] = chi_last; st[4] = lambda; st[5] = n_out_tot;
+            }
         }
     }
 }
@@ -962,12 +1229,14 @@ void ygzb_default_ba_params(ygzb_ba_params* p) {
     p->max_trials = 10;
 }
 
-int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
-                  double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
-                  const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, ygzb_ba_stats* stats) {
-    if (!ctx || n_problems < 1 || !kf_off || !pt_off || !obs_off || !poses || !fixed || !pts || !kf_idx || !pt_idx || !obs_px ||
-        !prm || !outlier)
-        return YGZB_ERR_INVALID;
+}  // extern "C"
+
+namespace {
+// shared body of ygzb_local_ba (ceres = false) and ygzb_local_ba_ceres (ceres = true): index bookkeeping on the host,
+// one cluster launch, results back.  hst receives the 8 raw statistics of every problem.
+int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
+                 double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
+                 const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, std::vector<double>& hst) {
     cudaSetDevice(ctx->device);
     const size_t P = (size_t)n_problems, NK = (size_t)kf_off[n_problems], NP = (size_t)pt_off[n_problems], NO = (size_t)obs_off[n_problems];
     // ---- structure: observations grouped by landmark, by pose, and landmark-sharing observation pairs per block pair
@@ -1036,7 +1305,7 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
     sz.take<int32_t>(3 * (P + 1)); sz.take<double>(6 * NK); sz.take<uint8_t>(NK); sz.take<double>(3 * NP); sz.take<int32_t>(2 * NO);
     sz.take<double>(2 * NO); sz.take<int32_t>(NP + 1 + NO + NK + 1 + NO); sz.take<int32_t>(P + 1 + NPS + 2 * NPAIR);
     sz.take<double>(21 * NO); sz.take<double>(9 * NP); sz.take<double>(3 * NP); sz.take<double>(9 * NP); sz.take<double>(3 * NP);
-    sz.take<double>(3 * NP); sz.take<uint8_t>(NO); sz.take<double>(8 * P);
+    sz.take<double>(3 * NP); sz.take<double>(3 * NP); sz.take<uint8_t>(NO); sz.take<double>(8 * P);
     void* buf = dev_scratch(ctx, 7, sz.bytes());
     if (!buf) return YGZB_ERR_CUDA;
     Carver c(buf);
@@ -1055,6 +1324,7 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
     a.Dinv = c.take<double>(9 * NP);
     a.xl = c.take<double>(3 * NP);
     a.pts_backup = c.take<double>(3 * NP);
+    a.scale_l = c.take<double>(3 * NP);
     a.outlier = c.take<uint8_t>(NO);
     a.stats = c.take<double>(8 * P);
     // kf_idx / pt_idx stay LOCAL to the problem; lm_obs / ps_obs / pair entries are GLOBAL observation ids
@@ -1087,7 +1357,8 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
     const size_t smem = sizeof(double) * ((size_t)dimp * dimp + (size_t)dimp);
     ClusterWs* d_ws = static_cast<ClusterWs*>(dev_scratch(ctx, 5, sizeof(ClusterWs) * P));
     if (!d_ws) return YGZB_ERR_CUDA;
-    YGZB_CUDA(ctx, cudaFuncSetAttribute(local_ba_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kernel = ceres ? local_ba_kernel<true> : local_ba_kernel<false>;
+    YGZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         // one cluster of kClusterSize CTAs (= SMs) per problem
         cudaLaunchConfig_t cfg{};
@@ -1103,23 +1374,61 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         ProfScope ps(ctx, kStageLocalBA);
-        YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, local_ba_kernel, a, d_ws));
+        YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, a, d_ws));
     }
     YGZB_LAUNCHED(ctx);
     TRY(d2h(ctx, poses, d_poses, 6 * NK));
     TRY(d2h(ctx, pts, d_pts, 3 * NP));
-    TRY(d2h(ctx, outlier, a.outlier, NO));
-    std::vector<double> hst(8 * P);
+    if (outlier) TRY(d2h(ctx, outlier, a.outlier, NO));
+    hst.resize(8 * P);
     TRY(d2h(ctx, hst.data(), a.stats, 8 * P));
     YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return YGZB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
+                  double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
+                  const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, ygzb_ba_stats* stats) {
+    if (!ctx || n_problems < 1 || !kf_off || !pt_off || !obs_off || !poses || !fixed || !pts || !kf_idx || !pt_idx || !obs_px ||
+        !prm || !outlier)
+        return YGZB_ERR_INVALID;
+    std::vector<double> hst;
+    TRY(run_local_ba(ctx, false, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, prm, outlier, hst));
     if (stats)
-        for (size_t p = 0; p < P; ++p) {
+        for (size_t p = 0; p < (size_t)n_problems; ++p) {
             stats[p].iters = (int)hst[8 * p];
             stats[p].lm_trials = (int)hst[8 * p + 1];
             stats[p].chi2_initial = hst[8 * p + 2];
             stats[p].chi2_final = hst[8 * p + 3];
             stats[p].lambda_final = hst[8 * p + 4];
             stats[p].n_outliers = (int)hst[8 * p + 5];
+        }
+    return YGZB_OK;
+}
+
+int ygzb_local_ba_ceres(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
+                        double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
+                        const double* obs_px, int max_iters, ygzb_ceres_stats* stats) {
+    if (!ctx || n_problems < 1 || !kf_off || !pt_off || !obs_off || !poses || !fixed || !pts || !kf_idx || !pt_idx || !obs_px ||
+        max_iters < 0)
+        return YGZB_ERR_INVALID;
+    ygzb_ba_params prm;
+    ygzb_default_ba_params(&prm);
+    prm.max_iters = max_iters;   // ceres::Solver::Options::max_num_iterations (50 by default)
+    prm.huber_delta = 0;         // no loss function (nullptr in AddResidualBlock, BA.cpp:346,364)
+    std::vector<double> hst;
+    TRY(run_local_ba(ctx, true, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, &prm, nullptr, hst));
+    if (stats)
+        for (size_t p = 0; p < (size_t)n_problems; ++p) {
+            stats[p].iters = (int)hst[8 * p];
+            stats[p].successful_steps = (int)hst[8 * p + 1];
+            stats[p].cost_initial = hst[8 * p + 2];
+            stats[p].cost_final = hst[8 * p + 3];
+            stats[p].radius_final = hst[8 * p + 4];
+            stats[p].termination = (int)hst[8 * p + 5];
         }
     return YGZB_OK;
 }

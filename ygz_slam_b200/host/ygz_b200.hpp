@@ -605,6 +605,60 @@ inline void LocalBAG2O(std::set<Frame*>& local_keyframes, std::set<MapPoint*>& l
     }
     for (int j = 0; j < np; ++j) pts[j]->_pos_world = Vector3d(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
 }
+
+// BA.cpp:324-384: the Ceres flavour.  Only observations in local key-frames enter (:338); the key-frame with
+// _keyframe_id == 0 keeps its pose (point-only residual blocks, :340-349); poses travel as [t; so3.log()] (:353-357)
+// and come back through SE3(SO3::exp(r), t) (:378-382).
+inline void LocalBA(std::set<Frame*>& local_keyframes, std::set<MapPoint*>& local_map_points,
+                    const std::map<unsigned long, Frame*>& keyframe_of) {
+    auto& rt = b200::Runtime::Get();
+    std::vector<Frame*> kfs(local_keyframes.begin(), local_keyframes.end());
+    std::map<Frame*, int> index;
+    std::vector<uint8_t> fixed;
+    for (size_t k = 0; k < kfs.size(); ++k) {
+        index[kfs[k]] = (int)k;
+        fixed.push_back(kfs[k]->_keyframe_id == 0);
+    }
+    std::vector<MapPoint*> pts;
+    std::vector<int32_t> kf_idx, pt_idx;
+    std::vector<double> obs;
+    for (MapPoint* mp : local_map_points) {
+        const int j = (int)pts.size();
+        pts.push_back(mp);
+        for (auto& o : mp->_obs) {
+            auto it = index.find(keyframe_of.at(o.first));
+            if (it == index.end()) continue;
+            kf_idx.push_back(it->second);
+            pt_idx.push_back(j);
+            obs.push_back(o.second->_pixel[0]);
+            obs.push_back(o.second->_pixel[1]);
+        }
+    }
+    const int nk = (int)kfs.size(), np = (int)pts.size(), no = (int)kf_idx.size();
+    if (!nk || !np || !no) return;
+    std::vector<double> poses(6 * (size_t)nk), X(3 * (size_t)np);
+    for (int k = 0; k < nk; ++k) {
+        double th;
+        const ygzb::V3d r = ygzb::so3_log(kfs[k]->_TCW.T.q, &th);
+        const ygzb::V3d t = kfs[k]->_TCW.T.t;
+        poses[6 * k] = t.x; poses[6 * k + 1] = t.y; poses[6 * k + 2] = t.z;
+        poses[6 * k + 3] = r.x; poses[6 * k + 4] = r.y; poses[6 * k + 5] = r.z;
+    }
+    for (int j = 0; j < np; ++j)
+        for (int c = 0; c < 3; ++c) X[3 * j + c] = pts[j]->_pos_world[c];
+    const int32_t ko[2] = {0, nk}, po[2] = {0, np}, oo[2] = {0, no};
+    rt.Check(ygzb_local_ba_ceres(rt.ctx(), 1, ko, po, oo, poses.data(), fixed.data(), X.data(), kf_idx.data(), pt_idx.data(), obs.data(),
+                                 50, nullptr), "ygzb_local_ba_ceres");
+    for (int k = 0; k < nk; ++k) {
+        if (fixed[k]) continue;   // the map `poses` of the reference only holds the key-frames with pose blocks
+        ygzb::SE3d T;
+        double th;
+        T.q = ygzb::so3_exp(ygzb::V3d{poses[6 * k + 3], poses[6 * k + 4], poses[6 * k + 5]}, &th);
+        T.t = ygzb::V3d{poses[6 * k], poses[6 * k + 1], poses[6 * k + 2]};
+        kfs[k]->_TCW = SE3(T);
+    }
+    for (int j = 0; j < np; ++j) pts[j]->_pos_world = Vector3d(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
+}
 }  // namespace ba
 
 // facade for the vocabulary of the north star ("ygz::Optimizer"); the reference's live API is namespace ygz::ba
