@@ -283,6 +283,26 @@ def secondary_workloads(ctx) -> dict:
         out["c5_vo_8_streams_1_gpu"] = run_vo(c3, 8, 40)
     finally:
         c3.close()
+    # CPU baseline of the same loop: the identical caller code (ygz_slam_b200/vo.py) on the oracle backend, one stream,
+    # bounded sample (the reference's VisualOdometry is single threaded)
+    try:
+        from oracle.vo_backend import OracleBackend
+        from ygz_slam_b200 import vo
+        n_cpu = 12
+        imgs, depth, _ = synth.shift_stream(0, n_cpu)
+        Vc = vo.VisualOdometry(OracleBackend(ora, 3), 1, kf_min_frames=5, kf_min_rot=0.03, kf_min_trans=0.03)
+        Vc.add_frames([imgs[0]], [depth], 0)
+        t0 = time.perf_counter()
+        for k in range(1, n_cpu):
+            Vc.add_frames([imgs[k]], [depth], k)
+        dt = time.perf_counter() - t0
+        cpu_fps = (n_cpu - 1) / dt
+        c5 = out["c5_vo_8_streams_1_gpu"]
+        c5["cpu_tracked_frames_per_s_1_thread"] = cpu_fps
+        c5["cpu_sample"] = f"{n_cpu - 1} frames of stream 0 through the same loop on the oracle (-O3 build), 1 thread"
+        c5["gpu_over_cpu_1_thread"] = c5["tracked_frames_per_s"] / cpu_fps
+    except Exception as e:  # noqa: BLE001
+        out["c5_vo_8_streams_1_gpu"]["cpu_error"] = repr(e)
     return out
 
 

@@ -1,5 +1,6 @@
-"""CPU-oracle implementation of the backend interface of ygz_slam_b200.vo (tests only): the same tracking loop
-can run on the oracle and on the GPU, which turns trajectory agreement into an end-to-end parity statement."""
+"""CPU-oracle implementation of the backend interface of ygz_slam_b200.vo (TEST INFRASTRUCTURE ONLY, like the rest of
+oracle/): the same tracking loop can run on the oracle and on the GPU, which turns trajectory agreement into an
+end-to-end parity statement; bench.py times it as the CPU baseline of BASELINE config C5."""
 import numpy as np
 
 from ygz_slam_b200 import se3

@@ -3,6 +3,8 @@ C ABI (ctypes) and is compared bit-exactly with the CPU oracle on the same seede
 import numpy as np
 import pytest
 
+from ygz_slam_b200 import synth
+
 pytestmark = pytest.mark.gpu
 
 
@@ -165,3 +167,43 @@ def test_match_frames_device_resident(ctx3, oracle, synth_frames):
         keep, n_good = oracle.good_matches(idx, dist)
         assert n_good > 300  # the synthetic pair really overlaps
     fr.close()
+
+
+@pytest.mark.parametrize("w,h,levels,cell", [(752, 480, 4, 10), (324, 246, 3, 8), (1281, 721, 5, 20)])
+def test_other_geometries_bit_exact(oracle, w, h, levels, cell):
+    """Image sizes other than 640x480: widths that are not multiples of 8 / 16 (tiled pyrDown fallback, word-load FAST
+    staging), ragged FAST tiles, odd level sizes, other grid cell sizes -- pyramid, corner statistics, features and
+    matches must still be bit-exact."""
+    from ygz_slam_b200 import Context
+    rng = np.random.default_rng(w * 7 + h)
+    tex = synth.texture(0x59475A00, 2048)
+    imgs = []
+    for k in range(2):
+        y0, x0 = 100 + 37 * k, 60 + 11 * k
+        g = tex[y0:y0 + h, x0:x0 + w].astype(np.int16) + rng.integers(-3, 4, (h, w))
+        imgs.append(np.clip(g, 0, 255).astype(np.uint8))
+    ctx = Context(0, image_width=w, image_height=h, n_levels=levels, cell_size=cell)
+    try:
+        fr = ctx.frames(2)
+        fr.upload(np.stack(imgs))
+        got = fr.detect([0, 1])
+        stats = fr.detect_stats(2)
+        wants = []
+        for s, g in enumerate(imgs):
+            pyr = oracle.build_pyramid(g, levels)
+            for L in range(levels):
+                lv = oracle.level_view(pyr, w, h, levels, L)
+                assert np.array_equal(fr.download_level(s, L), lv), (s, L)
+                xy = oracle.fast_detect(lv, 15)
+                nm = oracle.fast_nonmax(xy, oracle.fast_score(lv, xy))
+                assert stats[s, L, 0] == len(xy) and stats[s, L, 1] == len(nm), (s, L)
+            want = oracle.detect(pyr, w=w, h=h, n_levels=levels, cell=cell)
+            _assert_features_equal(got[s], want)
+            assert want["n"] > 50
+            wants.append(want)
+        idx, dist = fr.match([0], [1], True)[0]
+        widx, wdist = oracle.match_bf(wants[0]["desc"], wants[1]["desc"], True)
+        assert np.array_equal(idx, widx) and np.array_equal(dist, wdist)
+        fr.close()
+    finally:
+        ctx.close()

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from ygz_slam_b200 import se3, synth, vo
-from vo_oracle_backend import OracleBackend
+from oracle.vo_backend import OracleBackend
 
 
 def _run(backend, n_streams, n_frames, step=2):

@@ -240,16 +240,20 @@ class VisualOdometry:
             ids2, pt_idx = np.unique(o_id[multi], return_inverse=True)
             owner = np.searchsorted(hi, ids2, side="right")
             local = ids2 - lo[owner]
-            pts = np.stack([kfs[k].pw[n] for k, n in zip(owner, local)]) if len(ids2) else np.zeros((0, 3))
+            base = np.concatenate([[0], np.cumsum([len(kf.pw) for kf in kfs])])
+            flat = base[owner] + local                     # position of every BA point in the concatenated local map
+            pts = np.concatenate([kf.pw for kf in kfs])[flat].reshape(-1, 3)
             problems.append((poses, fixed, pts, o_kf[multi], pt_idx.astype(np.int32), o_px[multi]))
-            layouts.append((kfs, owner, local))
+            layouts.append((kfs, base, flat))
         results = self.be.local_ba(problems)
-        for i, (P, X), (kfs, owner, local) in zip(idx, results, layouts):
+        for i, (P, X), (kfs, base, flat) in zip(idx, results, layouts):
             st = self.streams[i]
             for k, kf in enumerate(kfs):
                 kf.T_cw = se3.se3_exp(P[k])
-            for k, n, x in zip(owner, local, X):
-                kfs[k].pw[n] = x
+            pw_all = np.concatenate([kf.pw for kf in kfs])
+            pw_all[flat] = X
+            for k, kf in enumerate(kfs):
+                kf.pw[:] = pw_all[base[k]:base[k + 1]]
             st.T_cw = kfs[-1].T_cw.copy()
             st.stats["ba"] += 1
 
