@@ -445,7 +445,8 @@ int ygzb_detect(ygzb_frames* f, const int32_t* slots, int n, const uint8_t* occu
 
     // packed copy-back: offsets first (one sync), then exactly `total` features per array
     if ((rc = launch_offsets(ctx, f->d_count, f->d_slots, n, f->d_offsets)) != YGZB_OK) return rc;
-    const size_t cap = (size_t)n * g.n_cells;
+    // array stride rounded up to 4 elements: the descriptor rows behind the five 4-byte arrays are moved as uint4
+    const size_t cap = ((size_t)n * g.n_cells + 3) & ~(size_t)3;
     uint8_t* pk = (uint8_t*)dev_scratch(ctx, 1, cap * 56);
     if (!pk) return YGZB_ERR_CUDA;
     float* ox = (float*)pk;
