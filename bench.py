@@ -281,6 +281,7 @@ def secondary_workloads(ctx) -> dict:
     c3 = _Ctx(ctx.device_index)
     try:
         out["c5_vo_8_streams_1_gpu"] = run_vo(c3, 8, 40)
+        out["c5_vo_8_streams_1_gpu"]["python_host_loop"] = run_vo(c3, 8, 40, native=False)["tracked_frames_per_s"]
     finally:
         c3.close()
     # CPU baseline of the same loop: the identical caller code (ygz_slam_b200/vo.py) on the oracle backend, one stream,
@@ -306,34 +307,45 @@ def secondary_workloads(ctx) -> dict:
     return out
 
 
-def run_vo(ctx, n_streams: int, n_frames: int, stream_offset: int = 0) -> dict:
-    """BASELINE config C5 shape: `n_streams` independent synthetic 640x480 streams tracked in lock step through the
-    caller loop of ygz_slam_b200/vo.py (sparse alignment -> direct projection -> pose-only -> keyframes: detect + BA),
-    every numeric step one batched C-ABI call with host buffers (uploads inside the timed region)."""
+def run_vo(ctx, n_streams: int, n_frames: int, stream_offset: int = 0, native: bool = True, threads: int = 2) -> dict:
+    """BASELINE config C5 shape: `n_streams` independent synthetic 640x480 streams tracked in lock step (sparse alignment ->
+    direct projection -> pose-only -> keyframes: detect + BA), every numeric step one batched C-ABI call with host buffers
+    (uploads inside the timed region).  native = the C++ host loop (ygz_slam_b200/host/vo_driver.cpp); otherwise the same
+    loop in Python (ygz_slam_b200/vo.py, the one the parity tests run against the oracle)."""
     from ygz_slam_b200 import se3, synth, vo
     data = [synth.shift_stream(stream_offset + s, n_frames) for s in range(n_streams)]
-    be = vo.GpuBackend(ctx, n_streams * vo.VisualOdometry.SLOTS_PER_STREAM)
-    V = vo.VisualOdometry(be, n_streams, kf_min_frames=5, kf_min_rot=0.03, kf_min_trans=0.03)
     warm = 3
-    t0 = None
-    for k in range(n_frames):
-        if k == warm:
-            ctx.synchronize()
-            t0 = time.perf_counter()
-        V.add_frames([data[s][0][k] for s in range(n_streams)], [data[s][1] for s in range(n_streams)], k)
-    ctx.synchronize()
-    dt = time.perf_counter() - t0
-    errs, lost = [], 0
-    for s in range(n_streams):
-        st = V.streams[s]
-        lost += int(st.lost)
-        errs.append(float(np.linalg.norm(se3.se3_log(se3.mul(st.T_cw, se3.inv(data[s][2][-1]))))))
-    be.fr.close()
+    if native:
+        from ygz_slam_b200 import vo_native
+        traj, stats, dt = vo_native.run(ctx, [d[0] for d in data], [d[1] for d in data], 5, 0.03, 0.03, warm=warm, threads=threads)
+        lost = sum(s["lost"] for s in stats)
+        errs = [float(np.linalg.norm(se3.se3_log(se3.mul(traj[s, -1], se3.inv(data[s][2][-1]))))) for s in range(n_streams)]
+        kfs, bas = sum(s["keyframes"] for s in stats), sum(s["ba"] for s in stats)
+        note = (f"host loop in C++ (host/vo_driver.cpp) on {min(threads, n_streams)} host threads with one context each; one batched "
+                "C-ABI call per stage, thread and lock-step frame")
+    else:
+        be = vo.GpuBackend(ctx, n_streams * vo.VisualOdometry.SLOTS_PER_STREAM)
+        V = vo.VisualOdometry(be, n_streams, kf_min_frames=5, kf_min_rot=0.03, kf_min_trans=0.03)
+        t0 = None
+        for k in range(n_frames):
+            if k == warm:
+                ctx.synchronize()
+                t0 = time.perf_counter()
+            V.add_frames([data[s][0][k] for s in range(n_streams)], [data[s][1] for s in range(n_streams)], k)
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        errs, lost = [], 0
+        for s in range(n_streams):
+            st = V.streams[s]
+            lost += int(st.lost)
+            errs.append(float(np.linalg.norm(se3.se3_log(se3.mul(st.T_cw, se3.inv(data[s][2][-1]))))))
+        be.fr.close()
+        kfs = int(sum(V.streams[s].stats["keyframes"] for s in range(n_streams)))
+        bas = int(sum(V.streams[s].stats["ba"] for s in range(n_streams)))
+        note = "host loop in Python (ygz_slam_b200/vo.py); one batched C-ABI call per stage and lock-step frame"
     return {"streams": n_streams, "frames_per_stream": n_frames, "tracked_frames_per_s": n_streams * (n_frames - warm) / dt,
             "ms_per_lockstep_frame": 1e3 * dt / (n_frames - warm), "streams_lost": lost, "final_pose_error_vs_gt_max": max(errs),
-            "keyframes": int(sum(V.streams[s].stats["keyframes"] for s in range(n_streams))),
-            "local_bas": int(sum(V.streams[s].stats["ba"] for s in range(n_streams))),
-            "note": "host loop in Python (caller code); one batched C-ABI call per stage and lock-step frame"}
+            "keyframes": kfs, "local_bas": bas, "note": note}
 
 
 def workload_config(batch: int, how: str) -> dict:

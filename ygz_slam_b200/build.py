@@ -45,6 +45,8 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
+        if not VO_LIB.exists() or VO_LIB.stat().st_mtime < (HERE / "host" / "vo_driver.cpp").stat().st_mtime:
+            build_vo_driver()
         return LIB
     objdir = HERE / "build"
     objdir.mkdir(exist_ok=True)
@@ -67,7 +69,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         print("\n".join(log))
     cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
     subprocess.run(cmd, check=True)
+    build_vo_driver()
     return LIB
+
+
+VO_LIB = HERE / "libygz_vo.so"
+
+
+def build_vo_driver() -> Path:
+    """Host-only C++ (g++): the native lock-step tracking loop over the C ABI (host/vo_driver.cpp)."""
+    src = HERE / "host" / "vo_driver.cpp"
+    gxx = shutil.which("g++") or "g++"
+    cmd = [gxx, "-std=c++20", "-O3", "-fPIC", "-shared", "-Wall", "-pthread", "-o", str(VO_LIB), str(src), f"-L{HERE}", "-lygz_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return VO_LIB
 
 
 if __name__ == "__main__":

@@ -1,0 +1,558 @@
+// vo_driver.cpp -- native (C++) lock-step tracking loop over the C ABI: the host side of BASELINE config C5.
+//
+// CALLER code in the shape of the reference's src/Module/VisualOdometry.cpp:38-107 (AddFrame), :281-302
+// (TrackRefFrame), src/Module/LocalMapping.cpp:24-140 (TrackLocalMap: FindCandidates / ProjectMapPoints /
+// OptimizeCurrent), VisualOdometry.cpp:182-218 + :304-321 (SetKeyframe / NeedNewKeyFrame) and LocalMapping.cpp:149-172
+// (LocalBA -> ba::LocalBAG2O).  It is the same loop as ygz_slam_b200/vo.py (which the tests run against the CPU oracle
+// backend for end-to-end parity); this file is that loop without the Python interpreter in the way, so that the
+// measured tracked-frames/s reflect the device path and not numpy call overhead.  No image or optimisation
+// arithmetic happens here: every numeric step is ONE batched C-ABI call over all streams (ygzb_frames_upload,
+// ygzb_sparse_align, ygzb_project_align, ygzb_pose_only, ygzb_detect, ygzb_local_ba).
+//
+// Input-side simplifications are those of vo.py: ground-truth depth initialises the map points of a key-frame
+// (test/test_feature_alignment.cpp:72-85 does the same with TUM depth), no BoW / loop closing.
+//
+// Build: host C++ only (g++), links libygz_b200.so; see ygz_slam_b200/build.py (libygz_vo.so).
+#include <algorithm>
+#include <barrier>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ygz_b200.h"
+#include "../csrc/se3.cuh"
+
+namespace {
+
+constexpr double FX = 520.9, FY = 521.0, CX = 325.1, CY = 249.7;   // config/default.yaml:32-35 (as Python floats in vo.py)
+constexpr int W = 640, H = 480;
+constexpr int kLocalKeyframes = 3;                                 // LocalMapping.local_keyframes (default.yaml:68)
+constexpr int kSlotsPerStream = kLocalKeyframes + 2;
+constexpr int kMinInliers = 30;                                    // vo.keyframe.min_features (default.yaml:66)
+
+struct Mat34 {
+    double m[12];
+};
+Mat34 identity() { return Mat34{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}}; }
+ygzb::SE3d to_se3(const Mat34& T) { return ygzb::se3_from_mat(T.m); }
+Mat34 from_se3(const ygzb::SE3d& s) {
+    Mat34 T;
+    ygzb::se3_to_mat(s, T.m);
+    return T;
+}
+Mat34 mul(const Mat34& A, const Mat34& B) {  // plain matrix product of [R|t] transforms
+    Mat34 C;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) C.m[4 * r + c] = A.m[4 * r] * B.m[c] + A.m[4 * r + 1] * B.m[4 + c] + A.m[4 * r + 2] * B.m[8 + c];
+        C.m[4 * r + 3] = A.m[4 * r] * B.m[3] + A.m[4 * r + 1] * B.m[7] + A.m[4 * r + 2] * B.m[11] + A.m[4 * r + 3];
+    }
+    return C;
+}
+Mat34 inv(const Mat34& A) {
+    Mat34 C;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) C.m[4 * r + c] = A.m[4 * c + r];
+        C.m[4 * r + 3] = -(A.m[r] * A.m[3] + A.m[4 + r] * A.m[7] + A.m[8 + r] * A.m[11]);
+    }
+    return C;
+}
+void se3_log(const Mat34& T, double out[6]) { ygzb::se3_log(to_se3(T), out); }  // [upsilon; omega]
+
+struct Keyframe {
+    int slot = 0, frame_id = 0;
+    Mat34 T;
+    std::vector<double> px;      // 2n full-res pixels of its features
+    std::vector<int> level;
+    std::vector<double> depth;   // n
+    std::vector<double> pw;      // 3n world points
+    long mp0 = 0;                // map point ids are [mp0, mp0 + n)
+    std::vector<long> obs_id;    // older map points tracked into this frame ...
+    std::vector<double> obs_px;  // ... and their measured pixels
+    int n() const { return (int)depth.size(); }
+};
+
+struct Stream {
+    int slot0 = 0;
+    std::deque<Keyframe> keyframes;   // at most kLocalKeyframes + 1, the newest is the reference key-frame
+    Mat34 T = identity();
+    bool has_pose = false, lost = false, has_ref = false, has_last = false;
+    int frames_since_kf = 0;
+    long next_mp = 0;
+    std::vector<long> last_id;
+    std::vector<double> last_px;
+    long n_keyframes = 0, n_ba = 0, n_candidates = 0, n_projected = 0, n_inliers = 0;
+    int first_local() const { return std::max(0, (int)keyframes.size() - kLocalKeyframes); }
+};
+
+struct Params {
+    int kf_min_frames;
+    double kf_min_rot, kf_min_trans;
+};
+
+#define CHK(call)                                     \
+    do {                                              \
+        int _rc = (call);                             \
+        if (_rc != YGZB_OK) return _rc;               \
+    } while (0)
+
+// wall time per C-ABI stage (printed when YGZ_VO_TIMING is set): where a lock-step frame goes
+enum { kTUpload, kTSparse, kTProject, kTPoseOnly, kTDetect, kTLocalBA, kTStages };
+double g_stage_s[kTStages];   // diagnostic only: threads add without synchronisation
+struct StageTimer {
+    int stage;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit StageTimer(int s) : stage(s) {}
+    ~StageTimer() { g_stage_s[stage] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+#define TIMED(stage, call)        \
+    do {                          \
+        StageTimer _t(stage);     \
+        CHK(call);                \
+    } while (0)
+
+class Driver {
+  public:
+    Driver(ygzb_ctx* ctx, ygzb_frames* fr, int n_streams, const Params& p) : ctx_(ctx), fr_(fr), S_(n_streams), prm_(p), st_(n_streams) {
+        for (int i = 0; i < S_; ++i) st_[i].slot0 = i * kSlotsPerStream;
+        int rows = 0, cols = 0;
+        ygzb_grid_dims(ctx, &rows, &cols);
+        n_cells_ = rows * cols;
+    }
+    std::vector<Stream>& streams() { return st_; }
+
+    // one lock-step frame: images[i] = grey frame of stream i, depth[i] = its (static) ground-truth depth map
+    int add_frames(const uint8_t* const* images, const double* const* depth, int frame_id) {
+        cur_slot_.assign(S_, 0);
+        for (int i = 0; i < S_; ++i) {
+            cur_slot_[i] = next_slot(i);
+            TIMED(kTUpload, ygzb_frames_upload(fr_, cur_slot_[i], 1, images[i], 1, (size_t)W * H));
+        }
+        std::vector<int> boot, track;
+        for (int i = 0; i < S_; ++i) {
+            if (st_[i].lost) continue;
+            if (!st_[i].has_ref) boot.push_back(i);
+            else track.push_back(i);
+        }
+        if (!boot.empty()) {
+            for (int i : boot) {
+                st_[i].T = identity();
+                st_[i].has_pose = true;
+            }
+            CHK(make_keyframes(boot, depth, frame_id, true));
+        }
+        if (!track.empty()) CHK(track_frames(track, depth, frame_id));
+        return YGZB_OK;
+    }
+
+  private:
+    int next_slot(int i) const {
+        const Stream& s = st_[i];
+        for (int c = 0; c < kSlotsPerStream; ++c) {
+            const int slot = s.slot0 + c;
+            bool used = false;
+            for (int k = s.first_local(); k < (int)s.keyframes.size(); ++k) used |= s.keyframes[k].slot == slot;
+            if (!used) return slot;
+        }
+        return s.slot0;  // cannot happen: the ring has kLocalKeyframes + 2 slots
+    }
+
+    // TrackRefFrame + TrackLocalMap + key-frame decision for the streams in idx
+    int track_frames(std::vector<int> idx, const double* const* depth, int frame_id) {
+        const int n = (int)idx.size();
+        // -- Matcher::SparseImageAlignment(ref, cur) with cur._TCW = ref._TCW (VisualOdometry.cpp:281-302)
+        std::vector<int32_t> ref_slot(n), cur_slot(n), offs(n + 1, 0), n_meas(n);
+        std::vector<double> px, dep, T_ref(12 * (size_t)n), T_cur(12 * (size_t)n);
+        for (int j = 0; j < n; ++j) {
+            const Keyframe& kf = st_[idx[j]].keyframes.back();
+            ref_slot[j] = kf.slot;
+            cur_slot[j] = cur_slot_[idx[j]];
+            offs[j + 1] = offs[j] + kf.n();
+            px.insert(px.end(), kf.px.begin(), kf.px.end());
+            dep.insert(dep.end(), kf.depth.begin(), kf.depth.end());
+            std::memcpy(&T_ref[12 * (size_t)j], kf.T.m, sizeof(kf.T.m));
+        }
+        T_cur = T_ref;
+        std::vector<uint8_t> has(px.size() / 2, 1);
+        TIMED(kTSparse, ygzb_sparse_align(fr_, n, ref_slot.data(), cur_slot.data(), offs.data(), px.data(), dep.data(), has.data(), T_ref.data(),
+                              T_cur.data(), 2, 0, 30, 1e-6, n_meas.data(), nullptr));
+        std::vector<int> alive;
+        std::vector<Mat34> T_of(S_);
+        for (int j = 0; j < n; ++j) {
+            Mat34 Tc, Tr;
+            std::memcpy(Tc.m, &T_cur[12 * (size_t)j], sizeof(Tc.m));
+            std::memcpy(Tr.m, &T_ref[12 * (size_t)j], sizeof(Tr.m));
+            double lg[6];
+            se3_log(mul(Tc, inv(Tr)), lg);   // Matcher.cpp:482-488: motion norm check
+            double nrm = 0;
+            for (double v : lg) nrm += v * v;
+            if (std::sqrt(nrm) <= 0.2) {
+                T_of[idx[j]] = Tc;
+                alive.push_back(idx[j]);
+            } else {
+                st_[idx[j]].lost = true;   // the reference keeps the last pose and reports VO_LOST
+            }
+        }
+        idx = alive;
+        if (idx.empty()) return YGZB_OK;
+
+        // -- FindCandidates: project the points of the local key-frames, border 20 (LocalMapping.cpp:47-80), then
+        //    ProjectMapPoints: Matcher::FindDirectProjection per candidate (:82-111) as ONE batch.  Poses go in relative
+        //    to the reference key-frame (I, T_cur * T_ref^-1): GetWarpAffineMatrix is only correct for an identity
+        //    reference pose (Matcher.cpp:425-430, quirk kept in the kernel).
+        struct Cand { int stream, kf, n; };
+        size_t bound = 0;   // every point of every local key-frame can become a candidate
+        for (int i : idx)
+            for (int k = st_[i].first_local(); k < (int)st_[i].keyframes.size(); ++k) bound += (size_t)st_[i].keyframes[k].n();
+        std::vector<Cand> cand(bound);
+        std::vector<int32_t> c_ref_slot(bound), c_cur_slot(bound), c_ref_pose(bound), c_cur_pose(bound);
+        const Mat34 eye = identity();
+        std::vector<double> poses(eye.m, eye.m + 12), c_ref_px(2 * bound), c_ref_depth(bound), c_cur_px(2 * bound);
+        std::vector<uint8_t> c_level(bound);
+        std::vector<int> job_begin;
+        size_t nc_sz = 0;
+        for (int i : idx) {
+            Stream& s = st_[i];
+            const Mat34& T = T_of[i];
+            job_begin.push_back((int)nc_sz);
+            const int pose_base = (int)(poses.size() / 12);
+            for (int k = s.first_local(); k < (int)s.keyframes.size(); ++k) {
+                const Mat34 rel = mul(T, inv(s.keyframes[k].T));
+                poses.insert(poses.end(), rel.m, rel.m + 12);
+            }
+            for (int k = s.first_local(); k < (int)s.keyframes.size(); ++k) {
+                const Keyframe& kf = s.keyframes[k];
+                const int32_t cur = cur_slot_[i], pose_id = pose_base + (k - s.first_local());
+                for (int g = 0; g < kf.n(); ++g) {
+                    const double* X = &kf.pw[3 * (size_t)g];
+                    const double x = T.m[0] * X[0] + T.m[1] * X[1] + T.m[2] * X[2] + T.m[3];
+                    const double y = T.m[4] * X[0] + T.m[5] * X[1] + T.m[6] * X[2] + T.m[7];
+                    const double z = T.m[8] * X[0] + T.m[9] * X[1] + T.m[10] * X[2] + T.m[11];
+                    const double u = FX * x / z + CX, v = FY * y / z + CY;
+                    if (!(z > 0 && u >= 20 && u < W - 20 && v >= 20 && v < H - 20)) continue;
+                    const size_t c = nc_sz++;
+                    cand[c] = {i, k, g};
+                    c_ref_slot[c] = kf.slot;
+                    c_cur_slot[c] = cur;
+                    c_ref_pose[c] = 0;
+                    c_cur_pose[c] = pose_id;
+                    c_ref_px[2 * c] = kf.px[2 * (size_t)g];
+                    c_ref_px[2 * c + 1] = kf.px[2 * (size_t)g + 1];
+                    c_ref_depth[c] = kf.depth[g];
+                    c_level[c] = (uint8_t)kf.level[g];
+                    c_cur_px[2 * c] = u;
+                    c_cur_px[2 * c + 1] = v;
+                }
+            }
+            s.n_candidates += (long)nc_sz - job_begin.back();
+        }
+        job_begin.push_back((int)nc_sz);
+        const int nc = (int)nc_sz;
+        std::vector<uint8_t> search_level(nc ? nc : 1), ok(nc ? nc : 1);
+        if (nc)
+            TIMED(kTProject, ygzb_project_align(fr_, nc, c_ref_slot.data(), c_cur_slot.data(), (int)(poses.size() / 12), poses.data(), c_ref_pose.data(),
+                                   c_cur_pose.data(), c_ref_px.data(), c_ref_depth.data(), c_level.data(), c_cur_px.data(),
+                                   search_level.data(), ok.data()));
+
+        // -- ba::OptimizeCurrentPoseOnly on the successfully projected points (LocalMapping.cpp:126; BA.cpp:188-264)
+        const int m = (int)idx.size();
+        std::vector<int32_t> po(m + 1, 0), n_inl(m);
+        std::vector<double> pw(3 * (size_t)nc + 3), obs(2 * (size_t)nc + 2), Tp(12 * (size_t)m);
+        std::vector<long> obs_id((size_t)nc + 1);
+        size_t q_out = 0;
+        for (int j = 0; j < m; ++j) {
+            Stream& s = st_[idx[j]];
+            int cnt = 0;
+            for (int c = job_begin[j]; c < job_begin[j + 1]; ++c) {
+                if (!ok[c]) continue;
+                const Keyframe& kf = s.keyframes[cand[c].kf];
+                std::memcpy(&pw[3 * q_out], &kf.pw[3 * (size_t)cand[c].n], 3 * sizeof(double));
+                obs[2 * q_out] = c_cur_px[2 * (size_t)c];
+                obs[2 * q_out + 1] = c_cur_px[2 * (size_t)c + 1];
+                obs_id[q_out] = kf.mp0 + cand[c].n;
+                ++q_out;
+                ++cnt;
+            }
+            po[j + 1] = po[j] + cnt;
+            s.n_projected += cnt;
+            std::memcpy(&Tp[12 * (size_t)j], T_of[idx[j]].m, sizeof(Mat34));
+        }
+        const size_t tot = (size_t)po[m];
+        std::vector<uint8_t> inl(tot ? tot : 1);
+        std::vector<double> dep_out(tot ? tot : 1);
+        TIMED(kTPoseOnly, ygzb_pose_only(ctx_, m, po.data(), pw.data(), obs.data(), Tp.data(), inl.data(), dep_out.data(),
+                           n_inl.data()));
+        std::vector<int> need;
+        for (int j = 0; j < m; ++j) {
+            Stream& s = st_[idx[j]];
+            if (n_inl[j] < kMinInliers) {
+                s.lost = true;
+                continue;
+            }
+            s.last_id.clear();
+            s.last_px.clear();
+            for (int q = po[j]; q < po[j + 1]; ++q)
+                if (inl[q]) {
+                    s.last_id.push_back(obs_id[q]);
+                    s.last_px.push_back(obs[2 * (size_t)q]);
+                    s.last_px.push_back(obs[2 * (size_t)q + 1]);
+                }
+            s.has_last = true;
+            std::memcpy(s.T.m, &Tp[12 * (size_t)j], sizeof(Mat34));
+            s.frames_since_kf += 1;
+            s.n_inliers += n_inl[j];
+            // NeedNewKeyFrame (VisualOdometry.cpp:304-321)
+            if (s.frames_since_kf < prm_.kf_min_frames) continue;
+            double d[6];
+            se3_log(mul(s.T, inv(s.keyframes.back().T)), d);
+            const double rot = std::sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]), tr = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            if (rot > prm_.kf_min_rot || tr > prm_.kf_min_trans) need.push_back(idx[j]);
+        }
+        if (!need.empty()) CHK(make_keyframes(need, depth, frame_id, false));
+        return YGZB_OK;
+    }
+
+    // SetKeyframe: Detect (grid FAST + ORB), depth-initialised map points, local BA (VisualOdometry.cpp:182-218)
+    int make_keyframes(const std::vector<int>& idx, const double* const* depth, int frame_id, bool fresh) {
+        const int n = (int)idx.size();
+        std::vector<int32_t> slots(n), off(n + 1);
+        for (int j = 0; j < n; ++j) slots[j] = cur_slot_[idx[j]];
+        const size_t cap = (size_t)n * n_cells_;
+        kx_.resize(cap); ky_.resize(cap); klevel_.resize(cap); kscore_.resize(cap); kangle_.resize(cap); kdesc_.resize(cap * 32);
+        ygzb_keypoints kp{off.data(), kx_.data(), ky_.data(), klevel_.data(), kscore_.data(), kangle_.data(), kdesc_.data(), nullptr, (int)cap};
+        TIMED(kTDetect, ygzb_detect(fr_, slots.data(), n, nullptr, &kp));
+        std::vector<int> ba_jobs;
+        for (int j = 0; j < n; ++j) {
+            Stream& s = st_[idx[j]];
+            Keyframe kf;
+            kf.slot = slots[j];
+            kf.frame_id = frame_id;
+            kf.T = s.T;
+            const Mat34 Tin = inv(s.T);
+            const int cnt = off[j + 1] - off[j];
+            kf.px.resize(2 * (size_t)cnt); kf.level.resize(cnt); kf.depth.resize(cnt); kf.pw.resize(3 * (size_t)cnt);
+            for (int g = 0; g < cnt; ++g) {
+                const double x = kx_[off[j] + g], y = ky_[off[j] + g];
+                const double d = depth[idx[j]][(size_t)(int)y * W + (int)x];
+                kf.px[2 * (size_t)g] = x;
+                kf.px[2 * (size_t)g + 1] = y;
+                kf.level[g] = klevel_[off[j] + g];
+                kf.depth[g] = d;
+                const double pc[3] = {(x - CX) * d / FX, (y - CY) * d / FY, d};
+                for (int r = 0; r < 3; ++r)
+                    kf.pw[3 * (size_t)g + r] = Tin.m[4 * r] * pc[0] + Tin.m[4 * r + 1] * pc[1] + Tin.m[4 * r + 2] * pc[2] + Tin.m[4 * r + 3];
+            }
+            kf.mp0 = s.next_mp;
+            s.next_mp += cnt;
+            if (!fresh && s.has_last) {
+                kf.obs_id = s.last_id;
+                kf.obs_px = s.last_px;
+            }
+            s.keyframes.push_back(std::move(kf));
+            while ((int)s.keyframes.size() > kLocalKeyframes + 1) s.keyframes.pop_front();
+            s.has_ref = true;
+            s.frames_since_kf = 0;
+            s.n_keyframes += 1;
+            if (!fresh && s.keyframes.size() >= 2) ba_jobs.push_back(idx[j]);
+        }
+        if (!ba_jobs.empty()) CHK(local_ba(ba_jobs));
+        return YGZB_OK;
+    }
+
+    // LocalMapping::LocalBA -> ba::LocalBAG2O over the local key-frames and the points at least two of them observe
+    int local_ba(const std::vector<int>& idx) {
+        const int P = (int)idx.size();
+        std::vector<int32_t> kf_off(P + 1, 0), pt_off(P + 1, 0), ob_off(P + 1, 0), kf_idx, pt_idx;
+        std::vector<double> poses, pts, obs;
+        std::vector<uint8_t> fixed;
+        struct Ref { int kf, n; };
+        std::vector<std::vector<Ref>> owners(P);
+        for (int p = 0; p < P; ++p) {
+            Stream& s = st_[idx[p]];
+            const int k0 = s.first_local(), nk = (int)s.keyframes.size() - k0;
+            for (int k = 0; k < nk; ++k) {
+                double lg[6];
+                se3_log(s.keyframes[k0 + k].T, lg);
+                const double g2o[6] = {lg[3], lg[4], lg[5], lg[0], lg[1], lg[2]};   // VertexSE3Sophus: [omega; upsilon]
+                poses.insert(poses.end(), g2o, g2o + 6);
+                fixed.push_back(k == 0);   // the oldest local key-frame fixes the gauge (key-frame 0 in the reference)
+            }
+            // observations: a key-frame observes its own points (detected pixel) and the older points tracked into it
+            struct Ob { long id; int kf; double u, v; };
+            std::vector<Ob> all;
+            auto in_local = [&](long id) {
+                for (int k = 0; k < nk; ++k) {
+                    const Keyframe& kf = s.keyframes[k0 + k];
+                    if (id >= kf.mp0 && id < kf.mp0 + kf.n()) return true;
+                }
+                return false;
+            };
+            for (int k = 0; k < nk; ++k) {
+                const Keyframe& kf = s.keyframes[k0 + k];
+                for (int g = 0; g < kf.n(); ++g) all.push_back({kf.mp0 + g, k, kf.px[2 * (size_t)g], kf.px[2 * (size_t)g + 1]});
+                for (size_t q = 0; q < kf.obs_id.size(); ++q)
+                    if (in_local(kf.obs_id[q])) all.push_back({kf.obs_id[q], k, kf.obs_px[2 * q], kf.obs_px[2 * q + 1]});
+            }
+            // points seen by a single key-frame do not constrain anything: keep ids with >= 2 observations, numbered in
+            // ascending id order (np.unique in vo.py)
+            std::vector<long> ids;
+            ids.reserve(all.size());
+            for (const Ob& o : all) ids.push_back(o.id);
+            std::sort(ids.begin(), ids.end());
+            std::vector<long> multi;
+            for (size_t a = 0; a < ids.size();) {
+                size_t b = a;
+                while (b < ids.size() && ids[b] == ids[a]) ++b;
+                if (b - a >= 2) multi.push_back(ids[a]);
+                a = b;
+            }
+            for (long id : multi) {
+                for (int k = 0; k < nk; ++k) {
+                    const Keyframe& kf = s.keyframes[k0 + k];
+                    if (id >= kf.mp0 && id < kf.mp0 + kf.n()) {
+                        const int g = (int)(id - kf.mp0);
+                        owners[p].push_back({k0 + k, g});
+                        pts.insert(pts.end(), &kf.pw[3 * (size_t)g], &kf.pw[3 * (size_t)g] + 3);
+                        break;
+                    }
+                }
+            }
+            int n_ob = 0;
+            for (const Ob& o : all) {
+                const auto it = std::lower_bound(multi.begin(), multi.end(), o.id);
+                if (it == multi.end() || *it != o.id) continue;
+                kf_idx.push_back(o.kf);
+                pt_idx.push_back((int32_t)(it - multi.begin()));
+                obs.push_back(o.u);
+                obs.push_back(o.v);
+                ++n_ob;
+            }
+            kf_off[p + 1] = kf_off[p] + nk;
+            pt_off[p + 1] = pt_off[p] + (int)multi.size();
+            ob_off[p + 1] = ob_off[p] + n_ob;
+        }
+        ygzb_ba_params bp;
+        ygzb_default_ba_params(&bp);
+        std::vector<uint8_t> outl(obs.size() / 2 + 1);
+        static const double zero3[3] = {0, 0, 0};
+        static const int32_t zero_i = 0;
+        TIMED(kTLocalBA, ygzb_local_ba(ctx_, P, kf_off.data(), pt_off.data(), ob_off.data(), poses.data(), fixed.data(), pts.empty() ? const_cast<double*>(zero3) : pts.data(),
+                          kf_idx.empty() ? &zero_i : kf_idx.data(), pt_idx.empty() ? &zero_i : pt_idx.data(), obs.empty() ? zero3 : obs.data(), &bp,
+                          outl.data(), nullptr));
+        for (int p = 0; p < P; ++p) {
+            Stream& s = st_[idx[p]];
+            const int k0 = s.first_local(), nk = (int)s.keyframes.size() - k0;
+            for (int k = 0; k < nk; ++k) {
+                const double* g = &poses[6 * (size_t)(kf_off[p] + k)];
+                const double v[6] = {g[3], g[4], g[5], g[0], g[1], g[2]};
+                s.keyframes[k0 + k].T = from_se3(ygzb::se3_exp(v));
+            }
+            for (size_t q = 0; q < owners[p].size(); ++q) {
+                Keyframe& kf = s.keyframes[owners[p][q].kf];
+                std::memcpy(&kf.pw[3 * (size_t)owners[p][q].n], &pts[3 * ((size_t)pt_off[p] + q)], 3 * sizeof(double));
+            }
+            s.T = s.keyframes.back().T;
+            s.n_ba += 1;
+        }
+        return YGZB_OK;
+    }
+
+    ygzb_ctx* ctx_;
+    ygzb_frames* fr_;
+    int S_, n_cells_ = 0;
+    Params prm_;
+    std::vector<Stream> st_;
+    std::vector<int> cur_slot_;
+    std::vector<float> kx_, ky_, kscore_, kangle_;
+    std::vector<uint8_t> klevel_, kdesc_;
+};
+
+}  // namespace
+
+extern "C" {
+
+// Tracks n_streams independent 640x480 grey streams in lock step for n_frames frames.  The streams are split over
+// n_threads host threads; thread 0 drives the caller's context, every further thread creates its own context (= its
+// own CUDA stream) on the same device with the same parameters, so the kernels of one group overlap the host work and
+// the kernels of the others.  The contexts must use the 3-level pyramid of the reference default.
+//   images[s] : n_frames * 480 * 640 bytes, depth[s] : 480 * 640 doubles (static ground-truth depth of stream s)
+//   traj      : n_streams * n_frames * 12 doubles out (T_cw after every frame; NaN while a stream has no pose)
+//   stats     : n_streams * 8 out: lost, keyframes, local BAs, candidates, projected, inliers, 0, 0
+//   seconds   : wall time of frames [warm, n_frames) including the final device synchronisation (all threads meet at a
+//               barrier before frame `warm` and after the last frame)
+int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threads, int n_streams, int n_frames,
+               const uint8_t* const* images, const double* const* depth, int kf_min_frames, double kf_min_rot, double kf_min_trans,
+               int warm, double* traj, int64_t* stats, double* seconds) {
+    if (!ctx || !params || n_streams < 1 || n_frames < 1 || !images || !depth || !traj || !stats || !seconds) return YGZB_ERR_INVALID;
+    n_threads = std::max(1, std::min(n_threads, n_streams));
+    warm = std::max(0, std::min(warm, n_frames - 1));
+    for (double& v : g_stage_s) v = 0;
+    std::vector<int> rcs(n_threads, YGZB_OK);
+    std::barrier sync_point(n_threads);
+    std::chrono::steady_clock::time_point t_begin, t_end;
+    auto worker = [&](int t) {
+        const int s0 = (int)((long)n_streams * t / n_threads), s1 = (int)((long)n_streams * (t + 1) / n_threads), ns = s1 - s0;
+        ygzb_ctx* my = ctx;
+        int rc = YGZB_OK;
+        if (t > 0) rc = ygzb_create(device, params, &my);
+        ygzb_frames* fr = nullptr;
+        if (rc == YGZB_OK) rc = ygzb_frames_create(my, ns * kSlotsPerStream, &fr);
+        Driver drv(my, fr, ns, Params{kf_min_frames, kf_min_rot, kf_min_trans});
+        std::vector<const uint8_t*> img(ns);
+        for (int k = 0; k < n_frames; ++k) {
+            if (k == warm) {
+                if (rc == YGZB_OK) ygzb_synchronize(my);
+                sync_point.arrive_and_wait();
+                if (t == 0) {
+                    t_begin = std::chrono::steady_clock::now();
+                    for (double& v : g_stage_s) v = 0;
+                }
+            }
+            if (rc != YGZB_OK) continue;   // keep meeting the barriers
+            for (int s = 0; s < ns; ++s) img[s] = images[s0 + s] + (size_t)k * W * H;
+            rc = drv.add_frames(img.data(), depth + s0, k);
+            for (int s = 0; s < ns; ++s) {
+                double* out = traj + ((size_t)(s0 + s) * n_frames + k) * 12;
+                const Stream& st = drv.streams()[s];
+                for (int c = 0; c < 12; ++c) out[c] = st.has_pose ? st.T.m[c] : NAN;
+            }
+        }
+        if (rc == YGZB_OK) ygzb_synchronize(my);
+        sync_point.arrive_and_wait();
+        if (t == 0) t_end = std::chrono::steady_clock::now();
+        for (int s = 0; s < ns; ++s) {
+            const Stream& st = drv.streams()[s];
+            int64_t* o = stats + 8 * (size_t)(s0 + s);
+            o[0] = st.lost; o[1] = st.n_keyframes; o[2] = st.n_ba; o[3] = st.n_candidates; o[4] = st.n_projected; o[5] = st.n_inliers;
+            o[6] = o[7] = 0;
+        }
+        if (fr) ygzb_frames_destroy(fr);
+        if (t > 0 && my) ygzb_destroy(my);
+        rcs[t] = rc;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
+    *seconds = std::chrono::duration<double>(t_end - t_begin).count();
+    if (getenv("YGZ_VO_TIMING")) {
+        static const char* names[kTStages] = {"upload", "sparse_align", "project_align", "pose_only", "detect", "local_ba"};
+        double sum = 0;
+        for (int i = 0; i < kTStages; ++i) sum += g_stage_s[i];
+        const int timed = n_frames - warm;
+        fprintf(stderr, "[ygz_vo] %d streams on %d host threads x %d timed frames: %.3f ms per lock-step frame; C-ABI time summed over threads %.3f ms\n",
+                n_streams, n_threads, timed, 1e3 * *seconds / timed, 1e3 * sum / timed);
+        for (int i = 0; i < kTStages; ++i) fprintf(stderr, "[ygz_vo]   %-14s %.3f ms/frame\n", names[i], 1e3 * g_stage_s[i] / timed);
+    }
+    for (int rc : rcs)
+        if (rc != YGZB_OK) return rc;
+    return YGZB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+"""ctypes harness for the native lock-step tracking loop (host/vo_driver.cpp -> libygz_vo.so): the C++ twin of
+vo.VisualOdometry with the GPU backend, used by bench.py for BASELINE config C5 and by the tests to compare both loops."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import build
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = Path(build.VO_LIB)
+        if not path.exists():
+            build.build()          # builds libygz_b200.so first if needed, then the driver
+        _LIB = C.CDLL(str(path))
+        _LIB.ygz_vo_run.restype = C.c_int
+        _LIB.ygz_vo_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return _LIB
+
+
+def run(ctx, frames, depths, kf_min_frames=10, kf_min_rot=0.1, kf_min_trans=0.1, warm=0, threads=1):
+    """frames[s]: (n_frames, 480, 640) uint8, depths[s]: (480, 640) float64.  The context must use the 3-level pyramid.
+    threads > 1 splits the streams over that many host threads, each with its own context (CUDA stream) on the device.
+    Returns (trajectory (S, n_frames, 3, 4), stats list of dicts, seconds of frames [warm, n_frames))."""
+    S = len(frames)
+    n = len(frames[0])
+    imgs = [np.ascontiguousarray(f, np.uint8) for f in frames]
+    deps = [np.ascontiguousarray(d, np.float64) for d in depths]
+    ip = (C.c_void_p * S)(*[a.ctypes.data for a in imgs])
+    dp = (C.c_void_p * S)(*[a.ctypes.data for a in deps])
+    traj = np.zeros((S, n, 12), np.float64)
+    stats = np.zeros((S, 8), np.int64)
+    sec = C.c_double(0.0)
+    rc = _lib().ygz_vo_run(ctx.h, ctx.device_index, C.byref(ctx.params), threads, S, n, C.cast(ip, C.c_void_p), C.cast(dp, C.c_void_p),
+                           kf_min_frames, kf_min_rot, kf_min_trans, warm, traj.ctypes.data, stats.ctypes.data, C.byref(sec))
+    ctx.check(rc, "ygz_vo_run")
+    keys = ("lost", "keyframes", "ba", "candidates", "projected", "inliers")
+    return traj.reshape(S, n, 3, 4), [dict(zip(keys, map(int, row[:6]))) for row in stats], sec.value
