@@ -282,6 +282,9 @@ def secondary_workloads(ctx) -> dict:
     try:
         out["c5_vo_8_streams_1_gpu"] = run_vo(c3, 8, 40)
         out["c5_vo_8_streams_1_gpu"]["python_host_loop"] = run_vo(c3, 8, 40, native=False)["tracked_frames_per_s"]
+        # the kernels of the tracking loop are latency-bound (one CTA / one cluster per stream), so throughput grows with the
+        # number of streams a GPU carries: same loop, 32 streams, 4 host threads
+        out["c5_vo_32_streams_1_gpu"] = run_vo(c3, 32, 40, threads=4)
     finally:
         c3.close()
     # CPU baseline of the same loop: the identical caller code (ygz_slam_b200/vo.py) on the oracle backend, one stream,
@@ -302,6 +305,8 @@ def secondary_workloads(ctx) -> dict:
         c5["cpu_tracked_frames_per_s_1_thread"] = cpu_fps
         c5["cpu_sample"] = f"{n_cpu - 1} frames of stream 0 through the same loop on the oracle (-O3 build), 1 thread"
         c5["gpu_over_cpu_1_thread"] = c5["tracked_frames_per_s"] / cpu_fps
+        if "c5_vo_32_streams_1_gpu" in out:
+            out["c5_vo_32_streams_1_gpu"]["gpu_over_cpu_1_thread"] = out["c5_vo_32_streams_1_gpu"]["tracked_frames_per_s"] / cpu_fps
     except Exception as e:  # noqa: BLE001
         out["c5_vo_8_streams_1_gpu"]["cpu_error"] = repr(e)
     return out
@@ -602,9 +607,18 @@ def main() -> None:
                 tr = ncu_traffic.get(ncu_key[k], {}).get("dram_bytes_per_frame")
                 roof.append({"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                              "frac": ach / peak, "traffic": (tr * B if tr else None),
-                             "traffic_source": "profiles/r1_dram_traffic.json (dram__bytes_read+write per frame from ncu --set full at 128 frames) x frames per launch" if tr else None,
+                             "traffic_source": "profiles/r1_dram_traffic.json (dram__bytes_read+write per frame from ncu --set full) x frames per launch" if tr else None,
                              "share_of_step": shares[k]["share"],
                              "us_per_launch": dur * 1e6, "algorithmic_bytes_per_launch": alg_bytes[k]})
+        if "pyrdown" in shares:   # the one kernel family of the step that is HBM-bound by nature: all its launches together
+            dur = shares["pyrdown"]["ms_per_launch"] * shares["pyrdown"]["launches_per_step"] * 1e-3
+            tr = ncu_traffic.get("pyrdown_stream", {}).get("dram_bytes_per_frame")
+            roof.append({"kernel": "pyrdown (all launches of a step)", "bound": "hbm", "achieved": 409600.0 * B / dur / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": 409600.0 * B / dur / 1e9 / peak,
+                         "traffic": (tr * B if tr else None),
+                         "traffic_source": "largest launch only (level 0 -> 1), profiles/r1_dram_traffic.json" if tr else None,
+                         "share_of_step": shares["pyrdown"]["share"], "us_per_launch": dur * 1e6 / shares["pyrdown"]["launches_per_step"],
+                         "algorithmic_bytes_per_launch": 409600.0 * B / shares["pyrdown"]["launches_per_step"]})
         main_roof = next((r for r in roof if r["kernel"] == dom), roof[0] if roof else None)
         if main_roof is not None:
             main_roof = dict(main_roof)
@@ -613,10 +627,13 @@ def main() -> None:
                 # the matcher is bound by the integer POPC pipe, not by HBM: report that roofline beside it
                 sm_mhz = clocks.get("sm_mhz") or 1965.0
                 popc_peak = 148 * 16 * sm_mhz * 1e6               # POPC lanes/clk/SM x SMs x clock
-                popc = B * kpf * kpf * 8 / (shares["match"]["ms_per_launch"] * 1e-3)
-                main_roof["popc_pipe"] = {"achieved_gpopc_s": popc / 1e9, "peak_gpopc_s": popc_peak / 1e9,
-                                          "frac": popc / popc_peak,
-                                          "note": "peak = 148 SMs x 16 POPC/clk/SM x sampled SM clock"}
+                pairs_per_s = B * kpf * kpf / (shares["match"]["ms_per_launch"] * 1e-3)
+                main_roof["popc_pipe"] = {
+                    "algorithmic_gpopc_s": 8 * pairs_per_s / 1e9,     # SURVEY 8d counts 8 POPC per descriptor pair
+                    "executed_popc_per_pair": 5,                      # carry-save adders fold the 8 words into 5 POPC
+                    "executed_gpopc_s": 5 * pairs_per_s / 1e9, "peak_gpopc_s": popc_peak / 1e9,
+                    "pipe_utilisation": 5 * pairs_per_s / popc_peak,
+                    "note": "peak = 148 SMs x 16 POPC/clk/SM (measured, profiles/r1_microbench_int_pipes.txt) x sampled SM clock"}
 
         # ---- bounded CPU baseline (rank 0, N=1 only) ----------------------------------------------
         cpu = None

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) pyrdown_ptr_kernel(const uint8_t* const* 
 
 // all remaining small levels of one frame in ONE CTA: level `first-1` (<= kTailBytes) is staged in shared memory and
 // every further level is produced from the previous one there (no launch or HBM round trip per level)
-constexpr int kTailBytes = 20480;
+constexpr int kTailBytes = 5120;   // 80 x 60 at 640 x 480: larger sources go through the streaming kernel (measured faster)
 
 __global__ void __launch_bounds__(256) pyrdown_tail_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot, Geometry g,
                                                            int first) {
