@@ -1,0 +1,47 @@
+"""CPU suite: the oracle against the committed golden vectors of tests/golden/cv2_pins.npz (OpenCV outputs generated once
+by tools/make_golden.py).  Unlike tests/test_oracle_cv2.py this needs no cv2 at run time, so the pin of the
+OpenCV-owned arithmetic (cvtColor, pyrDown, fastAtan2, BFMatcher cross-check, calcOpticalFlowPyrLK) always runs."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden" / "cv2_pins.npz"
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_bgr2gray_golden(oracle, gold):
+    assert np.array_equal(oracle.bgr2gray(gold["bgr"]), gold["bgr_gray"])
+
+
+def test_pyrdown_golden(oracle, gold):
+    for i in range(5):
+        assert np.array_equal(oracle.pyrdown(gold[f"pyr_in_{i}"]), gold[f"pyr_out_{i}"]), i
+
+
+def test_fast_atan2_golden(oracle, gold):
+    got = np.array([oracle.fast_atan2(y, x) for y, x in gold["atan2_yx"]], np.float32)
+    assert np.array_equal(got.view(np.uint32), gold["atan2_deg"].view(np.uint32))
+
+
+def test_bf_match_cross_check_golden(oracle, gold):
+    idx, dist = oracle.match_bf(gold["bf_A"], gold["bf_B"], True)
+    assert np.array_equal(idx, gold["bf_idx"]) and np.array_equal(dist, gold["bf_dist"])
+    assert (gold["bf_idx"] >= 0).sum() > 20 and (gold["bf_idx"] < 0).sum() > 20   # both outcomes occur, ties included
+
+
+def test_klt_golden(oracle, gold):
+    got, st, err = oracle.klt(gold["lk_g1"], gold["lk_g2"], gold["lk_pts"], gold["lk_init"])
+    wst = gold["lk_status"].astype(bool)
+    st = st.astype(bool)
+    assert (st != wst).sum() <= 1
+    both = st & wst
+    d = np.abs(got[both] - gold["lk_next"][both]).max(1)
+    # OpenCV's SIMD build accumulates the f32 normal equations in another order: tolerance, not bit-exactness
+    assert np.percentile(d, 99) < 0.01 and np.median(d) < 1e-3
+    assert np.abs(err[both] - gold["lk_err"][both]).max() < 0.05
+    assert both.sum() > 0.9 * len(wst) - 3
