@@ -150,6 +150,18 @@ __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy,
             if (!half) *d = *reinterpret_cast<const uint32_t*>(p);  // row 38
         }
         ctr_off += align;
+    } else if (v.pitch == v.w) {
+        // window reaches past the first / last byte of the level buffer (corners of the upper levels that InFrame lets
+        // through, SURVEY 8a hazard 4): the level is contiguous, so a linear address is a memory offset -- byte loads
+        // with a range check, no division
+        for (int r = 0; r < kPatchW; ++r) {
+            const int lin0 = lin_first + r * v.w;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc = lane + 32 * h, lin = lin0 + cc;
+                if (cc < kPatchW) s_patch[r * kPatchPitch + cc] = (lin >= 0 && lin < n_px) ? v.img[lin] : (uint8_t)0;
+            }
+        }
     } else {
         for (int r = 0; r < kPatchW; ++r) {
             const int lin0 = lin_first + r * v.w;
