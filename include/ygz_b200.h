@@ -207,6 +207,10 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
  * and fixed[k] != 0 marks the key-frame with _keyframe_id == 0, whose observations become point-only residual blocks
  * (BA.cpp:340-349).  Observations in frames outside the local set are not part of the problem (BA.cpp:338): the
  * caller leaves them out.  obs_px are pixels; Pixel2Camera2D (float intrinsics of the context) is applied inside.
+ * huber_a > 0 puts ceres::HuberLoss(huber_a) on every residual block (normalised image units): with it and the right
+ * choice of free / fixed poses the same entry point is ba::OptimizeCurrent (BA.cpp:91-186: the current frame free, its
+ * map points free, their other observers fixed, HuberLoss(0.1)) and ba::OptimizeCurrentPointOnly (:266-322: every pose
+ * fixed, no loss); a problem without free poses is a pure point refinement.
  * termination: 0 max_iters reached, 1 gradient, 2 parameter, 3 function tolerance, 4 trust region collapsed.    */
 typedef struct {
     int iters, successful_steps;
@@ -215,7 +219,7 @@ typedef struct {
 } ygzb_ceres_stats;
 int ygzb_local_ba_ceres(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
                         double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
-                        const double* obs_px, int max_iters, ygzb_ceres_stats* stats);
+                        const double* obs_px, int max_iters, double huber_a, ygzb_ceres_stats* stats);
 
 /* replaces ba::OptimizeCurrentPoseOnly (src/Algorithm/BA.cpp:188-264; BA.h:44-46) with
  * CeresReprojectionErrorPoseOnly (include/ygz/Ceres/CeresReprojectionErrorPoseOnly.h): four rounds of

@@ -683,7 +683,7 @@ struct CeresBA {
 
 extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* poses, const uint8_t* fixed, int n_pt, double* pts,
                                   int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px, int max_iters,
-                                  ora_ceres_stats* stats) {
+                                  double huber_a, ora_ceres_stats* stats) {
     const float fx = camp->fx, fy = camp->fy, cx = camp->cx, cy = camp->cy;
     CeresBA pb;
     pb.n_kf = n_kf; pb.n_pt = n_pt; pb.n_obs = n_obs;
@@ -706,29 +706,46 @@ extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* pose
     std::vector<double> Hpp((size_t)np * 36), gp(dimp), Hll((size_t)n_pt * 9), gl(3 * (size_t)n_pt), Hpl(18 * (size_t)n_obs);
     double cost = 0;
 
-    auto build = [&]() {  // normal-equation blocks of the UNSCALED Jacobian and the gradient g = J^T r
+    // ceres::HuberLoss(a) through the Corrector (ceres/corrector.cc): rho'' <= 0 for Huber, so residuals and Jacobians of
+    // a block are both scaled by sqrt(rho') -- i.e. the block enters the normal equations with the weight w = rho' --
+    // and the cost is 1/2 sum rho(s), s = |r|^2: rho = s, w = 1 for s <= a^2, else rho = 2 a sqrt(s) - a^2, w = a / sqrt(s)
+    std::vector<double> wgt(n_obs, 1.0);
+    auto robust_cost = [&](const std::vector<double>& res, std::vector<double>* w) {
+        double c = 0;
+        for (int o = 0; o < n_obs; ++o) {
+            const double s2 = res[2 * (size_t)o] * res[2 * (size_t)o] + res[2 * (size_t)o + 1] * res[2 * (size_t)o + 1];
+            if (huber_a > 0 && s2 > huber_a * huber_a) {
+                const double rt = std::sqrt(s2);
+                c += 2 * huber_a * rt - huber_a * huber_a;
+                if (w) (*w)[o] = huber_a / rt;
+            } else {
+                c += s2;
+                if (w) (*w)[o] = 1.0;
+            }
+        }
+        return 0.5 * c;
+    };
+    auto build = [&]() {  // normal-equation blocks of the UNSCALED (loss-corrected) Jacobian and the gradient g = J^T r
         pb.evaluate(P, X, r, &Jp, &Jl);
-        cost = 0;
-        for (double v : r) cost += v * v;
-        cost *= 0.5;
+        cost = robust_cost(r, &wgt);
         std::fill(Hpp.begin(), Hpp.end(), 0.0); std::fill(gp.begin(), gp.end(), 0.0);
         std::fill(Hll.begin(), Hll.end(), 0.0); std::fill(gl.begin(), gl.end(), 0.0);
         for (int o = 0; o < n_obs; ++o) {
             const int j = pt_idx[o], fi = pb.free_index[kf_idx[o]];
             const double* J0 = &Jl[6 * (size_t)o];
             const double* J1 = J0 + 3;
-            const double e0 = r[2 * (size_t)o], e1 = r[2 * (size_t)o + 1];
+            const double e0 = r[2 * (size_t)o], e1 = r[2 * (size_t)o + 1], w = wgt[o];
             for (int a = 0; a < 3; ++a) {
-                for (int b = 0; b < 3; ++b) Hll[9 * (size_t)j + 3 * a + b] += J0[a] * J0[b] + J1[a] * J1[b];
-                gl[3 * (size_t)j + a] += J0[a] * e0 + J1[a] * e1;
+                for (int b = 0; b < 3; ++b) Hll[9 * (size_t)j + 3 * a + b] += w * (J0[a] * J0[b] + J1[a] * J1[b]);
+                gl[3 * (size_t)j + a] += w * (J0[a] * e0 + J1[a] * e1);
             }
             if (fi >= 0) {
                 const double* Q0 = &Jp[12 * (size_t)o];
                 const double* Q1 = Q0 + 6;
                 for (int a = 0; a < 6; ++a) {
-                    for (int b = 0; b < 6; ++b) Hpp[36 * (size_t)fi + 6 * a + b] += Q0[a] * Q0[b] + Q1[a] * Q1[b];
-                    gp[6 * fi + a] += Q0[a] * e0 + Q1[a] * e1;
-                    for (int b = 0; b < 3; ++b) Hpl[18 * (size_t)o + 3 * a + b] = Q0[a] * J0[b] + Q1[a] * J1[b];
+                    for (int b = 0; b < 6; ++b) Hpp[36 * (size_t)fi + 6 * a + b] += w * (Q0[a] * Q0[b] + Q1[a] * Q1[b]);
+                    gp[6 * fi + a] += w * (Q0[a] * e0 + Q1[a] * e1);
+                    for (int b = 0; b < 3; ++b) Hpl[18 * (size_t)o + 3 * a + b] = w * (Q0[a] * J0[b] + Q1[a] * J1[b]);
                 }
             }
         }
@@ -817,7 +834,7 @@ extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* pose
                     if (fi >= 0)
                         for (int k = 0; k < 6; ++k) jy += Jp[12 * (size_t)o + 6 * row + k] * xp[6 * fi + k];
                     for (int k = 0; k < 3; ++k) jy += Jl[6 * (size_t)o + 3 * row + k] * xl[3 * (size_t)pt_idx[o] + k];
-                    model_cost_change -= jy * (r[2 * (size_t)o + row] + jy / 2);
+                    model_cost_change -= wgt[o] * jy * (r[2 * (size_t)o + row] + jy / 2);
                 }
             }
             step_ok = model_cost_change > 0;
@@ -844,9 +861,7 @@ extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* pose
             step_norm = std::sqrt(step_norm);
             x_norm = std::sqrt(x_norm);
             pb.evaluate(Pc, Xc, rn, nullptr, nullptr);
-            double new_cost = 0;
-            for (double v : rn) new_cost += v * v;
-            new_cost *= 0.5;
+            const double new_cost = robust_cost(rn, nullptr);
             const double relative_decrease = (cost - new_cost) / model_cost_change;
             if (relative_decrease > 1e-3) {
                 accepted = true;

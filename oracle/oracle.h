@@ -140,7 +140,8 @@ int ora_local_ba_g2o(const ora_camera* cam, int n_kf, double* poses, const uint8
 
 /* ba::LocalBA, the Ceres twin (BA.cpp:324-384).  poses: n_kf x 6 as [t; angle-axis] (CeresReprojectionError.h:33-69),
  * in/out; fixed[k] != 0 : the key-frame with _keyframe_id == 0 (point-only residual blocks, BA.cpp:340-349).
- * Default ceres::Solver::Options (trust-region LM, Jacobi scaling, no loss); max_iters = 50 in the reference.
+ * Default ceres::Solver::Options (trust-region LM, Jacobi scaling); max_iters = 50 in the reference.  huber_a > 0 adds the
+ * ceres::HuberLoss(a) of ba::OptimizeCurrent (BA.cpp:91-186, a = 0.1 in normalised image coordinates).
  * termination: 0 max iterations, 1 gradient, 2 parameter, 3 function tolerance, 4 trust region collapsed. */
 typedef struct {
     int iters, successful_steps;
@@ -149,7 +150,7 @@ typedef struct {
 } ora_ceres_stats;
 int ora_local_ba_ceres(const ora_camera* cam, int n_kf, double* poses, const uint8_t* fixed, int n_pt, double* pts,
                        int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px, int max_iters,
-                       ora_ceres_stats* stats);
+                       double huber_a /* ceres::HuberLoss(a) on every block, 0 = no loss */, ora_ceres_stats* stats);
 
 /* ba::OptimizeCurrentPoseOnly (BA.cpp:188-264).  T_cw in/out, inlier[] out (1 = !_bad), depth[] out */
 int ora_pose_only(const ora_camera* cam, int n, const double* pt_world /*3n*/, const double* px /*2n*/,

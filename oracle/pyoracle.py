@@ -283,7 +283,7 @@ class Oracle:
         stats = {k: getattr(st, k) for k, _ in BAStats._fields_}
         return poses, pts, outl.astype(bool), stats
 
-    def local_ba_ceres(self, poses_t_aa, fixed, pts, kf_idx, pt_idx, px, max_iters=50, cam=None):
+    def local_ba_ceres(self, poses_t_aa, fixed, pts, kf_idx, pt_idx, px, max_iters=50, huber=0.0, cam=None):
         """ba::LocalBA (Ceres twin): poses as [t; angle-axis]."""
         cam = cam or default_camera()
         poses = np.ascontiguousarray(poses_t_aa, np.float64).copy()
@@ -292,7 +292,7 @@ class Oracle:
         self.lib.ora_local_ba_ceres(C.byref(cam), len(poses), _p(poses), _p(np.ascontiguousarray(fixed, np.uint8)),
                                     len(pts), _p(pts), len(kf_idx), _p(np.ascontiguousarray(kf_idx, np.int32)),
                                     _p(np.ascontiguousarray(pt_idx, np.int32)), _p(np.ascontiguousarray(px, np.float64)),
-                                    max_iters, C.byref(st))
+                                    max_iters, C.c_double(huber), C.byref(st))
         return poses, pts, {k: getattr(st, k) for k, _ in CeresStats._fields_}
 
     def pose_only(self, pt_world, px, T_cw, cam=None):

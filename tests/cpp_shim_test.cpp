@@ -89,7 +89,7 @@ int main(int argc, char** argv) {
             kfs[k]._is_keyframe = true;
             keyframe_of[k] = &kfs[k];
         }
-        std::vector<std::vector<Feature*>> feats(8);
+        std::vector<std::vector<Feature*>> feats(16, std::vector<Feature*>(8, nullptr));   // [point][key-frame]
         for (int j = 0; j < 16; ++j) {
             truth[j] = Vector3d(j % 2, (j / 2) % 2, 2 + j / 4);
             pts[j]._id = j;
@@ -97,6 +97,7 @@ int main(int argc, char** argv) {
                 Feature* f = new Feature(cam.World2Pixel(truth[j], T_true[k]));
                 kfs[k]._features.push_back(f);
                 pts[j]._obs[k] = f;
+                feats[j][k] = f;
             }
             pts[j]._pos_world = Vector3d(truth[j][0] + noise(0.05), truth[j][1] + noise(0.05), truth[j][2] + noise(0.05));
         }
@@ -111,7 +112,7 @@ int main(int argc, char** argv) {
             for (int j = 0; j < 16; ++j)
                 for (int k = 0; k < 8; ++k) {
                     const Vector2d px = cam.World2Pixel(pts[j]._pos_world, kfs[k]._TCW);
-                    const Feature* f = pts[j]._obs[k];
+                    const Feature* f = feats[j][k];
                     s2 += (px[0] - f->_pixel[0]) * (px[0] - f->_pixel[0]) + (px[1] - f->_pixel[1]) * (px[1] - f->_pixel[1]);
                 }
             return std::sqrt(s2 / (16 * 8));
@@ -123,6 +124,28 @@ int main(int argc, char** argv) {
         const double before = rms();
         if (flavour == 0) ba::LocalBAG2O(lk, lm, keyframe_of);
         else ba::LocalBA(lk, lm, keyframe_of);
+        if (flavour == 1) {
+            // ba::OptimizeCurrent / OptimizeCurrentPointOnly on top of the converged map: perturb the last frame's pose and
+            // a few points, the refinement must bring the reprojection error back down
+            Frame& cur = kfs[7];
+            for (int j = 0; j < 16; ++j) {   // the current frame is not (yet) an observer key-frame of its points
+                feats[j][7]->_mappoint = &pts[j];
+                pts[j]._obs.erase(7);
+            }
+            double v[6];
+            cur._TCW.log(v);
+            for (int c = 0; c < 6; ++c) v[c] += noise(0.01);
+            cur._TCW = SE3::exp(v);
+            const double b2 = rms();
+            ba::OptimizeCurrent(&cur, keyframe_of);
+            int n_bad = 0;
+            for (Feature* f : cur._features) n_bad += f->_bad;
+            printf("optimize_current rms_px_before %.4f after %.6f bad %d\n", b2, rms(), n_bad);
+            for (int j = 0; j < 16; j += 3) pts[j]._pos_world = Vector3d(pts[j]._pos_world[0] + 0.02, pts[j]._pos_world[1] - 0.02, pts[j]._pos_world[2] + 0.03);
+            const double b3 = rms();
+            ba::OptimizeCurrentPointOnly(&cur, keyframe_of);
+            printf("optimize_point_only rms_px_before %.4f after %.6f\n", b3, rms());
+        }
         double T0[12];
         kfs[0]._TCW.matrix3x4(T0);
         printf("local_ba %s rms_px_before %.4f after %.6f kf0_moved %d\n", flavour == 0 ? "g2o" : "ceres", before, rms(),

@@ -58,6 +58,10 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     assert abs(float(parts[6]) - want_disp) < 0.02
     # both bundle-adjustment flavours (ba::LocalBAG2O, ba::LocalBA) on the test_local_ba.cpp fixture: noise-free
     # observations, so the reprojection error must collapse; key-frame 0 keeps its pose
-    for line, name in ((lines[4], "g2o"), (lines[5], "ceres")):
+    for line, name in ((lines[4], "g2o"), (lines[7], "ceres")):
         parts = line.split()
         assert parts[1] == name and float(parts[3]) > 1.0 and float(parts[5]) < 1e-3 and parts[7] == "0"
+    # ba::OptimizeCurrent (pose + points, Huber 0.1) and ba::OptimizeCurrentPointOnly after perturbing the converged map
+    oc, op = lines[5].split(), lines[6].split()
+    assert oc[0] == "optimize_current" and float(oc[2]) > 0.5 and float(oc[4]) < 1e-3 and oc[6] == "0"
+    assert op[0] == "optimize_point_only" and float(op[2]) > 0.5 and float(op[4]) < 1e-3

@@ -465,7 +465,7 @@ class CeresStats(C.Structure):
                 ("radius_final", C.c_double), ("termination", C.c_int)]
 
 
-def _local_ba_ceres(self, kf_off, pt_off, obs_off, poses_t_aa, fixed, pts, kf_idx, pt_idx, px, max_iters=50):
+def _local_ba_ceres(self, kf_off, pt_off, obs_off, poses_t_aa, fixed, pts, kf_idx, pt_idx, px, max_iters=50, huber=0.0):
     """Batched ba::LocalBA (Ceres twin).  poses: (n_kf, 6) as [t; angle-axis]."""
     kf_off = np.ascontiguousarray(kf_off, np.int32)
     P = len(kf_off) - 1
@@ -476,7 +476,8 @@ def _local_ba_ceres(self, kf_off, pt_off, obs_off, poses_t_aa, fixed, pts, kf_id
                                             _p(np.ascontiguousarray(obs_off, np.int32)), _p(poses),
                                             _p(np.ascontiguousarray(fixed, np.uint8)), _p(pts),
                                             _p(np.ascontiguousarray(kf_idx, np.int32)), _p(np.ascontiguousarray(pt_idx, np.int32)),
-                                            _p(np.ascontiguousarray(px, np.float64)), max_iters, st), "ygzb_local_ba_ceres")
+                                            _p(np.ascontiguousarray(px, np.float64)), max_iters, C.c_double(huber), st),
+               "ygzb_local_ba_ceres")
     return poses, pts, [{k: getattr(s_, k) for k, _ in CeresStats._fields_} for s_ in st]
 
 

@@ -383,7 +383,15 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                 double* rec = a.lin + 21 * (size_t)(o0 + o);
                 ceres_linearise(s_pose[a.kf_idx[o0 + o]], __ldcg(X), __ldcg(X + 1), __ldcg(X + 2),
                                 (a.obs[2 * (size_t)(o0 + o)] - cx) / fx, (a.obs[2 * (size_t)(o0 + o) + 1] - cy) / fy, rec);
-                acc += rec[0] * rec[0] + rec[1] * rec[1];
+                // ceres::HuberLoss through the Corrector: rho'' <= 0, so the block is weighted by rho' = a / |r| beyond a
+                const double e2 = rec[0] * rec[0] + rec[1] * rec[1];
+                if (a.huber_delta > 0 && e2 > dsqr) {
+                    const double rt = sqrt(e2);
+                    rec[2] = a.huber_delta / rt;
+                    acc += 2 * a.huber_delta * rt - dsqr;
+                } else {
+                    acc += e2;
+                }
             }
         } else {
             for (int o = ct; o < n_obs; o += CT) {
@@ -726,7 +734,8 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                 for (int o = ct; o < n_obs; o += CT) {
                     double e0, e1, x, y, z;
                     reproject(o, &e0, &e1, &x, &y, &z);
-                    newc += e0 * e0 + e1 * e1;
+                    const double e2n = e0 * e0 + e1 * e1;
+                    newc += (a.huber_delta > 0 && e2n > dsqr) ? 2 * a.huber_delta * sqrt(e2n) - dsqr : e2n;
                     const double* rec = a.lin + 21 * (size_t)(o0 + o);
                     const int fi = s_free[a.kf_idx[o0 + o]];
                     const double* dl = a.xl + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
@@ -741,7 +750,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                         jy += rec[3 + 3 * row] * d0;
                         jy += rec[4 + 3 * row] * d1;
                         jy += rec[5 + 3 * row] * d2;
-                        model -= jy * (rec[row] + jy / 2);
+                        model -= rec[2] * jy * (rec[row] + jy / 2);
                     }
                 }
                 double newc_tot, model_tot;
@@ -1411,14 +1420,14 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
 
 int ygzb_local_ba_ceres(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
                         double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
-                        const double* obs_px, int max_iters, ygzb_ceres_stats* stats) {
+                        const double* obs_px, int max_iters, double huber_a, ygzb_ceres_stats* stats) {
     if (!ctx || n_problems < 1 || !kf_off || !pt_off || !obs_off || !poses || !fixed || !pts || !kf_idx || !pt_idx || !obs_px ||
-        max_iters < 0)
+        max_iters < 0 || !(huber_a >= 0))
         return YGZB_ERR_INVALID;
     ygzb_ba_params prm;
     ygzb_default_ba_params(&prm);
     prm.max_iters = max_iters;   // ceres::Solver::Options::max_num_iterations (50 by default)
-    prm.huber_delta = 0;         // no loss function (nullptr in AddResidualBlock, BA.cpp:346,364)
+    prm.huber_delta = huber_a;   // 0: no loss function (nullptr in AddResidualBlock, BA.cpp:346,364); 0.1: BA.cpp:108-135
     std::vector<double> hst;
     TRY(run_local_ba(ctx, true, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, &prm, nullptr, hst));
     if (stats)

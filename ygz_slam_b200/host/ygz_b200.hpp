@@ -648,7 +648,7 @@ inline void LocalBA(std::set<Frame*>& local_keyframes, std::set<MapPoint*>& loca
         for (int c = 0; c < 3; ++c) X[3 * j + c] = pts[j]->_pos_world[c];
     const int32_t ko[2] = {0, nk}, po[2] = {0, np}, oo[2] = {0, no};
     rt.Check(ygzb_local_ba_ceres(rt.ctx(), 1, ko, po, oo, poses.data(), fixed.data(), X.data(), kf_idx.data(), pt_idx.data(), obs.data(),
-                                 50, nullptr), "ygzb_local_ba_ceres");
+                                 50, 0.0, nullptr), "ygzb_local_ba_ceres");
     for (int k = 0; k < nk; ++k) {
         if (fixed[k]) continue;   // the map `poses` of the reference only holds the key-frames with pose blocks
         ygzb::SE3d T;
@@ -658,6 +658,85 @@ inline void LocalBA(std::set<Frame*>& local_keyframes, std::set<MapPoint*>& loca
         kfs[k]->_TCW = SE3(T);
     }
     for (int j = 0; j < np; ++j) pts[j]->_pos_world = Vector3d(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
+}
+
+namespace detail {
+// shared body of OptimizeCurrent / OptimizeCurrentPointOnly: the current frame (free or fixed) observes the map points of
+// its usable features; every other observer of those points enters as a constant pose (CeresReprojectionErrorPointOnly)
+inline void OptimizeCurrentImpl(Frame* current, const std::map<unsigned long, Frame*>& keyframe_of, bool pose_free, double huber_a,
+                                bool skip_bad) {
+    auto& rt = b200::Runtime::Get();
+    std::vector<const Frame*> frames{current};
+    std::vector<uint8_t> fixed{(uint8_t)!pose_free};
+    std::map<const Frame*, int> fixed_index;
+    std::vector<MapPoint*> pts;
+    std::map<MapPoint*, int> pt_index;
+    std::vector<int32_t> kf_idx, pt_idx;
+    std::vector<double> obs;
+    for (Feature* fea : current->_features) {
+        if (!fea->_mappoint || (skip_bad && fea->_bad)) continue;
+        auto it = pt_index.find(fea->_mappoint);
+        if (it == pt_index.end()) {
+            it = pt_index.emplace(fea->_mappoint, (int)pts.size()).first;
+            pts.push_back(fea->_mappoint);
+        }
+        const int j = it->second;
+        kf_idx.push_back(0); pt_idx.push_back(j);
+        obs.push_back(fea->_pixel[0]); obs.push_back(fea->_pixel[1]);
+        for (auto& o : fea->_mappoint->_obs) {   // the covisible key-frames, poses held constant
+            const Frame* f = keyframe_of.at(o.first);
+            auto fi = fixed_index.find(f);
+            if (fi == fixed_index.end()) {
+                fi = fixed_index.emplace(f, (int)frames.size()).first;
+                frames.push_back(f);
+                fixed.push_back(1);
+            }
+            kf_idx.push_back(fi->second); pt_idx.push_back(j);
+            obs.push_back(o.second->_pixel[0]); obs.push_back(o.second->_pixel[1]);
+        }
+    }
+    const int nk = (int)frames.size(), np = (int)pts.size(), no = (int)kf_idx.size();
+    if (!np || !no) return;
+    std::vector<double> poses(6 * (size_t)nk), X(3 * (size_t)np);
+    for (int k = 0; k < nk; ++k) {
+        double th;
+        const ygzb::V3d r = ygzb::so3_log(frames[k]->_TCW.T.q, &th);
+        const ygzb::V3d t = frames[k]->_TCW.T.t;
+        poses[6 * k] = t.x; poses[6 * k + 1] = t.y; poses[6 * k + 2] = t.z;
+        poses[6 * k + 3] = r.x; poses[6 * k + 4] = r.y; poses[6 * k + 5] = r.z;
+    }
+    for (int j = 0; j < np; ++j)
+        for (int c = 0; c < 3; ++c) X[3 * j + c] = pts[j]->_pos_world[c];
+    const int32_t ko[2] = {0, nk}, po[2] = {0, np}, oo[2] = {0, no};
+    rt.Check(ygzb_local_ba_ceres(rt.ctx(), 1, ko, po, oo, poses.data(), fixed.data(), X.data(), kf_idx.data(), pt_idx.data(), obs.data(),
+                                 50, huber_a, nullptr), "ygzb_local_ba_ceres");
+    if (pose_free) {
+        ygzb::SE3d T;
+        double th;
+        T.q = ygzb::so3_exp(ygzb::V3d{poses[3], poses[4], poses[5]}, &th);
+        T.t = ygzb::V3d{poses[0], poses[1], poses[2]};
+        current->_TCW = SE3(T);
+    }
+    for (int j = 0; j < np; ++j) pts[j]->_pos_world = Vector3d(X[3 * j], X[3 * j + 1], X[3 * j + 2]);
+}
+}  // namespace detail
+
+// BA.cpp:91-186: pose of the current frame + its map points, HuberLoss(0.1) on every block, then the 4 * 5.991 px^2 test
+inline void OptimizeCurrent(Frame* current, const std::map<unsigned long, Frame*>& keyframe_of) {
+    detail::OptimizeCurrentImpl(current, keyframe_of, true, 0.1, false);
+    const float chi2Mono = 5.991 * 4;
+    for (Feature* fea : current->_features) {
+        if (!fea->_mappoint) continue;
+        const Vector2d px = current->_camera->World2Pixel(fea->_mappoint->_pos_world, current->_TCW);
+        const double dx = px[0] - fea->_pixel[0], dy = px[1] - fea->_pixel[1];
+        if (dx * dx + dy * dy > chi2Mono) fea->_bad = true;
+        else fea->_depth = current->_camera->World2Camera(fea->_mappoint->_pos_world, current->_TCW)[2];
+    }
+}
+
+// BA.cpp:266-322: only the map points move; every pose (the current frame's too) is a constant of its residual block
+inline void OptimizeCurrentPointOnly(Frame* current, const std::map<unsigned long, Frame*>& keyframe_of) {
+    detail::OptimizeCurrentImpl(current, keyframe_of, false, 0.0, true);
 }
 }  // namespace ba
 
