@@ -150,7 +150,16 @@ def run_reference(args, rank: int, world: int) -> None:
         return
     from oracle.pyoracle import Oracle
     ora = Oracle(native=True)
-    threads = os.cpu_count() or 1
+    # all the host threads the process may use: the scheduler affinity mask, capped by a cgroup CPU quota if there is one
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:  # noqa: BLE001
+        pass
+    threads = max(1, usable)
     per_thread = 8                      # frames per thread per step -> bounded sample
     n = threads * per_thread
     frames = make_frames(min(n, 512), 0)
@@ -167,7 +176,8 @@ def run_reference(args, rank: int, world: int) -> None:
         "config": workload_config(n, "C++ host threads, frame-parallel (oracle/bench_driver.cpp)"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": f"{n} frames/step ({per_thread} per thread) x {args.steps} steps; CPU restatement of the reference "
-                                   f"path (the reference cannot be built here), -O3 AVX2/FMA, {threads} std::threads"},
+                                   f"path (the reference cannot be built here), -O3 AVX2/FMA, {threads} std::threads",
+                         "logical_cpus": os.cpu_count(), "affinity_cpus": usable, "cgroup_cpu_quota": quota},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
