@@ -23,6 +23,8 @@
 //     device (no host round trip per iteration): threads stride over features, 16 residuals each; the
 //     6x6 normal equations (21 + 6 doubles) are reduced with warp shuffles + shared memory; thread 0
 //     solves LDL^T and applies T <- T * exp(-x).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "se3.cuh"
 
@@ -336,9 +338,15 @@ struct SparseArgs {
     float* gdy;                 // [total][16]
     double* frame_jac;          // [total][12]
     uint8_t* visible;           // [total]
+    double* ws;                 // [n_problems][2][kSparseCluster][kNormalTerms + 1]: per-CTA partial sums of an iteration
 };
 
-constexpr int kSparseThreads = 512;
+// One thread-block CLUSTER per (ref, cur) pair: the normal equations are FP64 (as in the reference) and one SM's FP64
+// pipe bounded the single-CTA version (33 us per Gauss-Newton iteration at 2000 features); the features are strided
+// over the cluster, every CTA publishes its partial sums, one barrier.cluster per iteration, and every CTA then adds the
+// partials in rank order and takes the same solver step on its own replica of the pose.
+constexpr int kSparseCluster = 8;
+constexpr int kSparseThreads = 256;
 constexpr int kNormalTerms = 21 + 6 + 1;  // upper triangle of H, Jres, chi2
 
 __device__ bool ldlt_solve6(const double H[6][6], const double b[6], double x[6]) {
@@ -373,6 +381,8 @@ __device__ bool ldlt_solve6(const double H[6][6], const double b[6], double x[6]
 }
 
 __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const SparseArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ double s_red[kSparseThreads / 32][kNormalTerms];
     __shared__ unsigned long long s_nmeas[kSparseThreads / 32];
     __shared__ SE3d s_T, s_old;
@@ -380,12 +390,16 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
     __shared__ double s_chi2;     // chi2_ of the solver (persists across levels, NLSSolver_impl.hpp:288-299)
     __shared__ unsigned long long s_last_nmeas;
 
-    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+    const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CT = C * kSparseThreads, ct = rank * kSparseThreads + tid;   // cluster-wide thread id
     const int f0 = a.offsets[prob], f1 = a.offsets[prob + 1];
     const int nf = f1 - f0;
     const Geometry& g = a.g;
+    double* ws = a.ws + (size_t)prob * 2 * kSparseCluster * (kNormalTerms + 1);
+    int slot = 0;
     if (nf == 0) {  // run(): no features -> returns 0, pose untouched
-        if (tid == 0) a.n_meas_out[prob] = 0;
+        if (rank == 0 && tid == 0) a.n_meas_out[prob] = 0;
         return;
     }
     if (tid == 0) {
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
         s_chi2 = 1e10;
         s_last_nmeas = 0;
     }
-    for (int i = f0 + tid; i < f1; i += kSparseThreads) a.visible[i] = 0;
+    for (int i = f0 + ct; i < f1; i += CT) a.visible[i] = 0;
     __syncthreads();
 
     for (int lvl = a.max_level; lvl >= a.min_level; --lvl) {
@@ -405,7 +419,7 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
         const double jscale = focal / (1 << lvl);
         // precomputeReferencePatches: features that are not cached at this level keep their stale patch with a
         // zero Jacobian (jacobian_cache_.setZero(); visible_fts_ is never cleared -- kept faithfully)
-        for (int i = f0 + tid; i < f1; i += kSparseThreads) {
+        for (int i = f0 + ct; i < f1; i += CT) {   // (per-feature scratch is written and later read by the same thread)
             for (int k = 0; k < 16; ++k) a.gdx[(size_t)i * 16 + k] = a.gdy[(size_t)i * 16 + k] = 0.f;
             const float u_ref = (float)(a.px[2 * i] * scale), v_ref = (float)(a.px[2 * i + 1] * scale);
             const int ui = (int)floorf(u_ref), vi = (int)floorf(v_ref);
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
 #pragma unroll
             for (int k = 0; k < kNormalTerms; ++k) acc[k] = 0.0;
             unsigned long long nm = 0;
-            for (int i = f0 + tid; i < f1; i += kSparseThreads) {
+            for (int i = f0 + ct; i < f1; i += CT) {
                 if (!a.visible[i]) continue;
                 const V3d xyz_ref = pixel2camera(a.cam, a.px[2 * i], a.px[2 * i + 1], a.depth[i]);
                 const V3d xyz_cur = transform(T, xyz_ref);
@@ -496,13 +510,28 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
             for (int o = 16; o > 0; o >>= 1) nm += __shfl_down_sync(0xFFFFFFFFu, nm, o);
             if (lane == 0) s_nmeas[warp] = nm;
             __syncthreads();
+            // CTA partials -> workspace, barrier.cluster, then every CTA adds the partials of all ranks in rank order
+            double* my = ws + ((size_t)slot * kSparseCluster + rank) * (kNormalTerms + 1);
+            if (tid <= kNormalTerms) {
+                double v = 0;
+                if (tid < kNormalTerms) {
+                    for (int w = 0; w < kSparseThreads / 32; ++w) v += s_red[w][tid];
+                } else {
+                    unsigned long long n = 0;
+                    for (int w = 0; w < kSparseThreads / 32; ++w) n += s_nmeas[w];
+                    v = (double)n;   // < 2^53: exact
+                }
+                my[tid] = v;
+            }
+            cluster.sync();
             if (tid == 0) {
                 double tot[kNormalTerms];
                 unsigned long long n_meas = 0;
                 for (int k = 0; k < kNormalTerms; ++k) tot[k] = 0;
-                for (int w = 0; w < kSparseThreads / 32; ++w) {
-                    for (int k = 0; k < kNormalTerms; ++k) tot[k] += s_red[w][k];
-                    n_meas += s_nmeas[w];
+                for (int r = 0; r < C; ++r) {
+                    const double* pr = ws + ((size_t)slot * kSparseCluster + r) * (kNormalTerms + 1);
+                    for (int k = 0; k < kNormalTerms; ++k) tot[k] += __ldcg(pr + k);
+                    n_meas += (unsigned long long)__ldcg(pr + kNormalTerms);
                 }
                 s_last_nmeas = n_meas;
                 double H[6][6], b[6], x[6];
@@ -530,13 +559,15 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
                     if (nmx <= a.eps) s_flag = 1;
                 }
             }
+            slot ^= 1;
             __syncthreads();
             if (s_flag) break;
         }
-        if (tid == 0 && a.iters_out) a.iters_out[prob * kMaxLevels + lvl] = it;
+        if (rank == 0 && tid == 0 && a.iters_out) a.iters_out[prob * kMaxLevels + lvl] = it;
         __syncthreads();
     }
-    if (tid == 0) {
+    cluster.sync();   // no CTA may exit while another still reads its partials
+    if (rank == 0 && tid == 0) {
         const SE3d Tref = se3_from_mat(a.T_ref + 12 * (size_t)prob);
         se3_to_mat(se3_mul(s_T, Tref), a.T_cur + 12 * (size_t)prob);
         a.n_meas_out[prob] = (int32_t)(s_last_nmeas / 16);
@@ -544,6 +575,8 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
 }
 
 }  // namespace
+
+size_t sparse_align_ws_doubles(int n_problems) { return (size_t)n_problems * 2 * kSparseCluster * (kNormalTerms + 1); }
 
 int launch_align2d(ygzb_frames* f, int n, const int32_t* d_slot, const uint8_t* d_level, const uint8_t* d_ref_border,
                    const uint8_t* d_ref, int n_iter, double* d_uv, uint8_t* d_ok) {
@@ -585,7 +618,7 @@ int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slo
                         const int32_t* d_offsets, const double* d_px, const double* d_depth, const uint8_t* d_has_mp,
                         const double* d_T_ref, double* d_T_cur, int max_level, int min_level, int n_iter, double eps,
                         int32_t* d_n_meas, int32_t* d_iters, float* d_ref_patch, float* d_gdx, float* d_gdy, double* d_frame_jac,
-                        uint8_t* d_visible) {
+                        uint8_t* d_visible, double* d_ws) {
     ygzb_ctx* ctx = f->ctx;
     if (n_problems <= 0) return YGZB_OK;
     SparseArgs a;
@@ -612,8 +645,21 @@ int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slo
     a.gdy = d_gdy;
     a.frame_jac = d_frame_jac;
     a.visible = d_visible;
+    a.ws = d_ws;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_problems * kSparseCluster));
+    cfg.blockDim = dim3(kSparseThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kSparseCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     ProfScope ps(ctx, kStageSparseAlign);
-    sparse_align_kernel<<<n_problems, kSparseThreads, 0, ctx->stream>>>(a);
+    YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, sparse_align_kernel, a));
     YGZB_LAUNCHED(ctx);
     return YGZB_OK;
 }

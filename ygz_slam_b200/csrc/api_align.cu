@@ -169,6 +169,7 @@ int ygzb_sparse_align(ygzb_frames* f, int n_problems, const int32_t* ref_slot, c
     sz.take<int32_t>(2 * P); sz.take<int32_t>(P + 1); sz.take<double>(2 * T); sz.take<double>(T); sz.take<uint8_t>(T);
     sz.take<double>(12 * P); sz.take<double>(12 * P); sz.take<int32_t>(P); sz.take<int32_t>(P * kMaxLevels);
     sz.take<float>(16 * T); sz.take<float>(16 * T); sz.take<float>(16 * T); sz.take<double>(12 * T); sz.take<uint8_t>(T);
+    sz.take<double>(sparse_align_ws_doubles(n_problems));
     void* buf = dev_scratch(ctx, 6, sz.bytes());
     if (!buf) return YGZB_ERR_CUDA;
     Carver c(buf);
@@ -186,6 +187,7 @@ int ygzb_sparse_align(ygzb_frames* f, int n_problems, const int32_t* ref_slot, c
     float* d_gdy = c.take<float>(16 * T);
     double* d_fj = c.take<double>(12 * T);
     uint8_t* d_vis = c.take<uint8_t>(T);
+    double* d_ws = c.take<double>(sparse_align_ws_doubles(n_problems));
     TRY(h2d(ctx, d_slots, ref_slot, P));
     TRY(h2d(ctx, d_slots + P, cur_slot, P));
     TRY(h2d(ctx, d_off, offsets, P + 1));
@@ -197,7 +199,7 @@ int ygzb_sparse_align(ygzb_frames* f, int n_problems, const int32_t* ref_slot, c
     YGZB_CUDA(ctx, cudaMemsetAsync(d_iters, 0, P * kMaxLevels * sizeof(int32_t), ctx->stream));
     YGZB_CUDA(ctx, cudaMemsetAsync(d_patch, 0, 16 * T * sizeof(float), ctx->stream));
     TRY(launch_sparse_align(f, n_problems, d_slots, d_slots + P, d_off, d_px, d_depth, d_mp, d_Tref, d_Tcur, max_level, min_level,
-                            n_iter, eps, d_nmeas, d_iters, d_patch, d_gdx, d_gdy, d_fj, d_vis));
+                            n_iter, eps, d_nmeas, d_iters, d_patch, d_gdx, d_gdy, d_fj, d_vis, d_ws));
     TRY(d2h(ctx, T_cw_cur, d_Tcur, 12 * P));
     TRY(d2h(ctx, n_meas, d_nmeas, P));
     if (iters_per_level) TRY(d2h(ctx, iters_per_level, d_iters, P * kMaxLevels));

@@ -159,7 +159,8 @@ int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slo
                         const int32_t* d_offsets, const double* d_px, const double* d_depth, const uint8_t* d_has_mp,
                         const double* d_T_ref, double* d_T_cur, int max_level, int min_level, int n_iter, double eps,
                         int32_t* d_n_meas, int32_t* d_iters, float* d_ref_patch, float* d_gdx, float* d_gdy, double* d_frame_jac,
-                        uint8_t* d_visible);
+                        uint8_t* d_visible, double* d_ws);
+size_t sparse_align_ws_doubles(int n_problems);   // size of d_ws
 
 // bump allocator over one scratch buffer (all sub-buffers 256-byte aligned)
 struct Carver {
