@@ -952,10 +952,16 @@ struct PoseOnlyArgs {
     double* depth;            // [total]
     int32_t* n_inlier;        // [n_problems]
     uint8_t* enable;          // scratch [total]
+    double* ws;               // [n_problems][4][kPoseCluster][kPoseRed]: per-CTA partial sums of a reduction
     float fx, fy, cx, cy;
 };
 
+// One 8-CTA cluster per frame: the forward-mode jets are FP64 and a single SM's FP64 pipe bounded the one-CTA version.
+// The points are strided over the cluster; every reduction publishes per-CTA partials, meets at barrier.cluster and is
+// summed in rank order by every CTA, so all CTAs take identical trust-region decisions on their replica of the pose.
 constexpr int kPoseThreads = 256;
+constexpr int kPoseCluster = 8;
+constexpr int kPoseRed = 32;
 
 __device__ bool cholesky6(double A[36], double y[6]) {
     for (int j = 0; j < 6; ++j) {
@@ -984,16 +990,19 @@ __device__ bool cholesky6(double A[36], double y[6]) {
 }
 
 __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyArgs a) {
-    __shared__ double s_tmp[33];
-    __shared__ double s_red[kPoseThreads / 32][40];
-    __shared__ double s_pose[6], s_cand[6], s_scale[6], s_sum[40];
-    __shared__ int s_state;  // 0 continue, 1 terminate
-    __shared__ int s_fail;
-    const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double s_red[kPoseThreads / 32][kPoseRed];
+    __shared__ double s_pose[6], s_cand[6], s_scale[6], s_sum[kPoseRed];
+    const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+    const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CT = C * kPoseThreads, ct = rank * kPoseThreads + tid;   // cluster-wide thread id
     const int i0 = a.offsets[prob], n = a.offsets[prob + 1] - i0;
     const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
+    double* ws = a.ws + (size_t)prob * 4 * kPoseCluster * kPoseRed;
+    int slot = 0;
 
-    // reduce `cnt` per-thread partial sums into s_sum (valid for every thread afterwards)
+    // cluster-wide sum of `cnt` per-thread partial sums into s_sum (identical in every thread of every CTA afterwards)
     auto reduce = [&](const double* part, int cnt) {
         for (int t = 0; t < cnt; ++t) {
             const double v = warp_sum(part[t]);
@@ -1003,41 +1012,45 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
         if (tid < cnt) {
             double s = 0;
             for (int w = 0; w < kPoseThreads / 32; ++w) s += s_red[w][tid];
+            ws[((size_t)slot * kPoseCluster + rank) * kPoseRed + tid] = s;
+        }
+        cluster.sync();
+        if (tid < cnt) {
+            double s = 0;
+            for (int r = 0; r < C; ++r) s += __ldcg(&ws[((size_t)slot * kPoseCluster + r) * kPoseRed + tid]);
             s_sum[tid] = s;
         }
+        slot = (slot + 1) & 3;
         __syncthreads();
     };
-    // cost only at `pose`; sets s_fail when a residual block returns false (depth < 0)
+    // cost only at `pose` -> s_sum[0] = sum of squares, s_sum[1] > 0 when a residual block returned false (depth < 0)
     auto eval_cost = [&](const double* pose) -> double {
-        if (tid == 0) s_fail = 0;
-        __syncthreads();
-        double c = 0;
-        for (int i = tid; i < n; i += kPoseThreads) {
+        double part[2] = {0, 0};
+        for (int i = ct; i < n; i += CT) {
             if (!a.enable[i0 + i]) continue;
             Jet6 p0, p1, p2;
             project_jet(pose, a.pw + 3 * (size_t)(i0 + i), &p0, &p1, &p2);
             if (p2.a < 0) {
-                s_fail = 1;
+                part[1] += 1;
                 continue;
             }
             const double r0 = (a.px[2 * (size_t)(i0 + i)] - cx) / fx - p0.a / p2.a, r1 = (a.px[2 * (size_t)(i0 + i) + 1] - cy) / fy - p1.a / p2.a;
-            c += r0 * r0 + r1 * r1;
+            part[0] += r0 * r0 + r1 * r1;
         }
-        return 0.5 * block_sum(c, s_tmp);
+        reduce(part, 2);
+        return 0.5 * s_sum[0];
     };
-    // J^T J (21), J^T r (6), cost, column norms: scaled by s_scale when `scaled`
+    // J^T J (21), J^T r (6), cost (27), failed blocks (28): scaled by s_scale when `scaled`
     auto eval_normal = [&](const double* pose, bool scaled) {
-        if (tid == 0) s_fail = 0;
-        __syncthreads();
-        double part[34];
+        double part[29];
 #pragma unroll
-        for (int t = 0; t < 34; ++t) part[t] = 0;
-        for (int i = tid; i < n; i += kPoseThreads) {
+        for (int t = 0; t < 29; ++t) part[t] = 0;
+        for (int i = ct; i < n; i += CT) {
             if (!a.enable[i0 + i]) continue;
             Jet6 p0, p1, p2;
             project_jet(pose, a.pw + 3 * (size_t)(i0 + i), &p0, &p1, &p2);
             if (p2.a < 0) {
-                s_fail = 1;
+                part[28] += 1;
                 continue;
             }
             const Jet6 r0 = jc((a.px[2 * (size_t)(i0 + i)] - cx) / fx) - p0 / p2, r1 = jc((a.px[2 * (size_t)(i0 + i) + 1] - cy) / fy) - p1 / p2;
@@ -1058,7 +1071,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
             for (int k = 0; k < 6; ++k) part[21 + k] += j0[k] * r0.a + j1[k] * r1.a;
             part[27] += r0.a * r0.a + r1.a * r1.a;
         }
-        reduce(part, 28);
+        reduce(part, 29);
     };
 
     // initial pose = [t; so3.log()]
@@ -1069,7 +1082,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
         const V3d rl = so3_log(T.q, &th);
         backup[0] = T.t.x; backup[1] = T.t.y; backup[2] = T.t.z; backup[3] = rl.x; backup[4] = rl.y; backup[5] = rl.z;
     }
-    for (int i = tid; i < n; i += kPoseThreads) {
+    for (int i = ct; i < n; i += CT) {   // (per-point flags are written and later read by the same thread)
         a.enable[i0 + i] = 1;
         a.inlier[i0 + i] = 1;
         a.depth[i0 + i] = -1;
@@ -1081,7 +1094,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
         __syncthreads();
         // ---- Ceres trust-region LM (default options) ----
         eval_normal(s_pose, false);
-        bool run = !s_fail;
+        bool run = !(s_sum[28] > 0);
         double cost = 0.5 * s_sum[27];
         if (run) {
             if (tid < 6) {
@@ -1141,7 +1154,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
                 x_norm = sqrt(x_norm);
                 __syncthreads();
                 const double new_cost = eval_cost(s_cand);
-                if (!s_fail) {
+                if (!(s_sum[1] > 0)) {
                     const double relative_decrease = (cost - new_cost) / model_cost_change;
                     if (relative_decrease > 1e-3) {
                         accepted = true;
@@ -1174,7 +1187,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
         __syncthreads();
         // ---- classification with the pose of the PREVIOUS round (BA.cpp:231-251) ----
         double cnt = 0;
-        for (int i = tid; i < n; i += kPoseThreads) {
+        for (int i = ct; i < n; i += CT) {
             const double* X = a.pw + 3 * (size_t)(i0 + i);
             const V3d pc = transform(T, V3d{X[0], X[1], X[2]});
             const double u = fx * pc.x / pc.z + cx, v = fy * pc.y / pc.z + cy;
@@ -1190,14 +1203,16 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
                 cnt += 1;
             }
         }
-        cntInlier = (int)block_sum(cnt, s_tmp);
+        reduce(&cnt, 1);
+        cntInlier = (int)s_sum[0];
         if (cntInlier < 10) break;
         double th;
         T.q = so3_exp(V3d{s_pose[3], s_pose[4], s_pose[5]}, &th);
         T.t = V3d{s_pose[0], s_pose[1], s_pose[2]};
         __syncthreads();
     }
-    if (tid == 0) {
+    cluster.sync();   // no CTA may exit while another still reads its partials
+    if (rank == 0 && tid == 0) {
         se3_to_mat(T, a.T_cw + 12 * (size_t)prob);
         a.n_inlier[prob] = cntInlier;
     }
@@ -1450,7 +1465,7 @@ int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const 
     if (N && (!pt_world || !px || !inlier || !depth)) return YGZB_ERR_INVALID;
     Carver sz(nullptr);
     sz.take<int32_t>(P + 1); sz.take<double>(3 * N); sz.take<double>(2 * N); sz.take<double>(12 * P); sz.take<uint8_t>(N);
-    sz.take<double>(N); sz.take<int32_t>(P); sz.take<uint8_t>(N);
+    sz.take<double>(N); sz.take<int32_t>(P); sz.take<uint8_t>(N); sz.take<double>(P * 4 * kPoseCluster * kPoseRed);
     void* buf = dev_scratch(ctx, 7, sz.bytes());
     if (!buf) return YGZB_ERR_CUDA;
     Carver c(buf);
@@ -1463,6 +1478,7 @@ int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const 
     a.depth = c.take<double>(N);
     a.n_inlier = c.take<int32_t>(P);
     a.enable = c.take<uint8_t>(N);
+    a.ws = c.take<double>(P * 4 * kPoseCluster * kPoseRed);
     a.offsets = d_off; a.pw = d_pw; a.px = d_px;
     a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
     TRY(h2d(ctx, d_off, offsets, P + 1));
@@ -1470,8 +1486,20 @@ int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const 
     TRY(h2d(ctx, d_px, px, 2 * N));
     TRY(h2d(ctx, a.T_cw, (const double*)T_cw, 12 * P));
     {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(n_problems * kPoseCluster));
+        cfg.blockDim = dim3(kPoseThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kPoseCluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
         ProfScope ps(ctx, kStagePoseOnly);
-        pose_only_kernel<<<n_problems, kPoseThreads, 0, ctx->stream>>>(a);
+        YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, pose_only_kernel, a));
     }
     YGZB_LAUNCHED(ctx);
     TRY(d2h(ctx, T_cw, a.T_cw, 12 * P));
