@@ -1,6 +1,8 @@
 // api_align.cu -- extern "C" entry points for the photometric alignment stages (marshalling only).
 #include <algorithm>
 
+#include <cstring>
+
 #include "common.cuh"
 
 using namespace ygzb;
@@ -135,15 +137,23 @@ int ygzb_project_align(ygzb_frames* f, int n, const int32_t* ref_slot, const int
     uint8_t* d_rlevel = c.take<uint8_t>(N);
     uint8_t* d_slevel = c.take<uint8_t>(N);
     uint8_t* d_ok = c.take<uint8_t>(N);
-    TRY(h2d(ctx, d_idx, ref_slot, N));
-    TRY(h2d(ctx, d_idx + N, cur_slot, N));
-    TRY(h2d(ctx, d_idx + 2 * N, ref_pose, N));
-    TRY(h2d(ctx, d_idx + 3 * N, cur_pose, N));
-    TRY(h2d(ctx, d_poses, poses, 12 * P));
-    TRY(h2d(ctx, d_rpx, ref_px, 2 * N));
-    TRY(h2d(ctx, d_depth, ref_depth, N));
-    TRY(h2d(ctx, d_cpx, cur_px, 2 * N));
-    TRY(h2d(ctx, d_rlevel, ref_level, N));
+    // the inputs are the first six sub-buffers, contiguous on the device: assemble them in pinned memory with the same
+    // layout and move them with ONE copy (nine pageable copies cost more than the kernel itself)
+    const size_t in_bytes = (size_t)((uint8_t*)(d_rlevel + N) - (uint8_t*)buf);
+    uint8_t* stage = (uint8_t*)host_scratch(ctx, 1, in_bytes);
+    if (!stage) return YGZB_ERR_CUDA;
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    auto put = [&](const void* dev_ptr, const void* src, size_t bytes) { memcpy(stage + ((const uint8_t*)dev_ptr - (uint8_t*)buf), src, bytes); };
+    put(d_idx, ref_slot, N * 4);
+    put(d_idx + N, cur_slot, N * 4);
+    put(d_idx + 2 * N, ref_pose, N * 4);
+    put(d_idx + 3 * N, cur_pose, N * 4);
+    put(d_poses, poses, 12 * P * 8);
+    put(d_rpx, ref_px, 2 * N * 8);
+    put(d_depth, ref_depth, N * 8);
+    put(d_cpx, cur_px, 2 * N * 8);
+    put(d_rlevel, ref_level, N);
+    YGZB_CUDA(ctx, cudaMemcpyAsync(buf, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     TRY(launch_project_align(f, n, d_idx, d_idx + N, d_poses, d_idx + 2 * N, d_idx + 3 * N, d_rpx, d_depth, d_rlevel, d_cpx, d_slevel,
                              d_ok));
     TRY(d2h(ctx, cur_px, d_cpx, 2 * N));

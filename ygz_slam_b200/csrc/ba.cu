@@ -22,6 +22,7 @@
 // Roofline class: FP64 ALU / latency (0.3 MB of unique data per iteration, ~1.1e7 FLOP): bench.py reports
 // achieved FLOP/s for the reduce, not HBM bytes.
 #include <algorithm>
+#include <cstring>
 #include <utility>
 #include <vector>
 
@@ -1293,36 +1294,55 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
                 ps_obs[pc[kf_off[p] + kf_idx[o]]++] = o;
             }
     }
+    // landmark-sharing observation pairs per (free pose f1 <= f2) block pair, as CSR: two passes (count, fill), no
+    // per-problem allocations.  pair_start holds n_pairs + 1 entries per problem.
+    std::vector<int32_t> free_of(NK, -1), nfree(P, 0);
     for (size_t p = 0; p < P; ++p) {
-        const int k0 = kf_off[p], nk = kf_off[p + 1] - k0, p0 = pt_off[p], npt = pt_off[p + 1] - p0;
-        std::vector<int> free_index(nk, -1);
         int nf = 0;
-        for (int k = 0; k < nk; ++k)
-            if (!fixed[k0 + k]) free_index[k] = nf++;
-        const int n_pairs = nf * (nf + 1) / 2;
-        std::vector<std::vector<std::pair<int32_t, int32_t>>> buckets(n_pairs);
-        auto pair_id = [&](int f1, int f2) { return f1 * nf - f1 * (f1 - 1) / 2 + (f2 - f1); };
-        for (int j = 0; j < npt; ++j)
-            for (int q1 = lm_start[p0 + j]; q1 < lm_start[p0 + j + 1]; ++q1) {
-                const int f1 = free_index[kf_idx[lm_obs[q1]]];
-                if (f1 < 0) continue;
-                for (int q2 = lm_start[p0 + j]; q2 < lm_start[p0 + j + 1]; ++q2) {
-                    const int f2 = free_index[kf_idx[lm_obs[q2]]];
-                    if (f2 < f1 || (f2 == f1 && q2 != q1)) continue;
-                    buckets[pair_id(f1, f2)].push_back({lm_obs[q1], lm_obs[q2]});
+        for (int k = kf_off[p]; k < kf_off[p + 1]; ++k)
+            if (!fixed[k]) free_of[k] = nf++;
+        nfree[p] = nf;
+        pair_off[p + 1] = pair_off[p] + nf * (nf + 1) / 2 + 1;
+    }
+    pair_start.assign((size_t)pair_off[P], 0);
+    auto for_each_pair = [&](auto&& visit) {
+        for (size_t p = 0; p < P; ++p) {
+            const int k0 = kf_off[p], p0 = pt_off[p], npt = pt_off[p + 1] - p0, nf = nfree[p];
+            if (nf == 0) continue;
+            for (int j = 0; j < npt; ++j) {
+                const int qa = lm_start[p0 + j], qb = lm_start[p0 + j + 1];
+                for (int q1 = qa; q1 < qb; ++q1) {
+                    const int f1 = free_of[k0 + kf_idx[lm_obs[q1]]];
+                    if (f1 < 0) continue;
+                    for (int q2 = qa; q2 < qb; ++q2) {
+                        const int f2 = free_of[k0 + kf_idx[lm_obs[q2]]];
+                        if (f2 < f1 || (f2 == f1 && q2 != q1)) continue;
+                        visit(pair_off[p] + f1 * nf - f1 * (f1 - 1) / 2 + (f2 - f1), lm_obs[q1], lm_obs[q2]);
+                    }
                 }
             }
-        pair_off[p] = (int32_t)pair_start.size();
-        for (int b = 0; b < n_pairs; ++b) {
-            pair_start.push_back((int32_t)pair_o1.size());
-            for (auto& e : buckets[b]) {
-                pair_o1.push_back(e.first);
-                pair_o2.push_back(e.second);
-            }
         }
-        pair_start.push_back((int32_t)pair_o1.size());
+    };
+    for_each_pair([&](int slot, int32_t, int32_t) { pair_start[slot + 1]++; });   // every problem owns n_pairs + 1 entries
+    // the counts sit one entry to the right: a running sum over the whole array turns them into start offsets (the extra
+    // entry of every problem carries the total across the problem boundary)
+    {
+        int32_t run = 0;
+        for (size_t i = 0; i < pair_start.size(); ++i) {
+            run += pair_start[i];
+            pair_start[i] = run;
+        }
     }
-    pair_off[P] = (int32_t)pair_start.size();
+    pair_o1.assign((size_t)(pair_start.empty() ? 0 : pair_start.back()), 0);
+    pair_o2.assign(pair_o1.size(), 0);
+    {
+        std::vector<int32_t> cursor(pair_start);
+        for_each_pair([&](int slot, int32_t o1, int32_t o2) {
+            const int32_t at = cursor[slot]++;
+            pair_o1[at] = o1;
+            pair_o2[at] = o2;
+        });
+    }
     const size_t NPAIR = pair_o1.size(), NPS = pair_start.size();
 
     Carver sz(nullptr);
@@ -1351,25 +1371,34 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
     a.scale_l = c.take<double>(3 * NP);
     a.outlier = c.take<uint8_t>(NO);
     a.stats = c.take<double>(8 * P);
-    // kf_idx / pt_idx stay LOCAL to the problem; lm_obs / ps_obs / pair entries are GLOBAL observation ids
-    TRY(h2d(ctx, d_off, kf_off, P + 1));
-    TRY(h2d(ctx, d_off + (P + 1), pt_off, P + 1));
-    TRY(h2d(ctx, d_off + 2 * (P + 1), obs_off, P + 1));
-    TRY(h2d(ctx, d_poses, poses, 6 * NK));
-    TRY(h2d(ctx, d_fixed, fixed, NK));
-    TRY(h2d(ctx, d_pts, pts, 3 * NP));
-    TRY(h2d(ctx, d_idx, kf_idx, NO));
-    TRY(h2d(ctx, d_idx + NO, pt_idx, NO));
-    TRY(h2d(ctx, d_obs, obs_px, 2 * NO));
-    TRY(h2d(ctx, d_csr, lm_start.data(), NP + 1));
-    TRY(h2d(ctx, d_csr + NP + 1, lm_obs.data(), NO));
-    TRY(h2d(ctx, d_csr + NP + 1 + NO, ps_start.data(), NK + 1));
-    TRY(h2d(ctx, d_csr + NP + 1 + NO + NK + 1, ps_obs.data(), NO));
-    TRY(h2d(ctx, d_pairs, pair_off.data(), P + 1));
-    TRY(h2d(ctx, d_pairs + P + 1, pair_start.data(), NPS));
-    TRY(h2d(ctx, d_pairs + P + 1 + NPS, pair_o1.data(), NPAIR));
-    TRY(h2d(ctx, d_pairs + P + 1 + NPS + NPAIR, pair_o2.data(), NPAIR));
-    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope after the launch
+    // kf_idx / pt_idx stay LOCAL to the problem; lm_obs / ps_obs / pair entries are GLOBAL observation ids.
+    // All inputs sit at the front of the device buffer in one contiguous run: they are assembled in a pinned staging
+    // buffer with the same layout and travel as ONE host-to-device copy (instead of 17 pageable ones).
+    const size_t in_bytes = (size_t)(reinterpret_cast<uint8_t*>(d_pairs + P + 1 + NPS + 2 * NPAIR) - static_cast<uint8_t*>(buf));
+    uint8_t* stage = static_cast<uint8_t*>(host_scratch(ctx, 1, in_bytes));
+    if (!stage) return YGZB_ERR_CUDA;
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // an earlier copy may still read the staging buffer
+    auto put = [&](const void* dev_ptr, const void* src, size_t bytes) {
+        if (bytes) memcpy(stage + (static_cast<const uint8_t*>(dev_ptr) - static_cast<uint8_t*>(buf)), src, bytes);
+    };
+    put(d_off, kf_off, (P + 1) * 4);
+    put(d_off + (P + 1), pt_off, (P + 1) * 4);
+    put(d_off + 2 * (P + 1), obs_off, (P + 1) * 4);
+    put(d_poses, poses, 6 * NK * 8);
+    put(d_fixed, fixed, NK);
+    put(d_pts, pts, 3 * NP * 8);
+    put(d_idx, kf_idx, NO * 4);
+    put(d_idx + NO, pt_idx, NO * 4);
+    put(d_obs, obs_px, 2 * NO * 8);
+    put(d_csr, lm_start.data(), (NP + 1) * 4);
+    put(d_csr + NP + 1, lm_obs.data(), NO * 4);
+    put(d_csr + NP + 1 + NO, ps_start.data(), (NK + 1) * 4);
+    put(d_csr + NP + 1 + NO + NK + 1, ps_obs.data(), NO * 4);
+    put(d_pairs, pair_off.data(), (P + 1) * 4);
+    put(d_pairs + P + 1, pair_start.data(), NPS * 4);
+    put(d_pairs + P + 1 + NPS, pair_o1.data(), NPAIR * 4);
+    put(d_pairs + P + 1 + NPS + NPAIR, pair_o2.data(), NPAIR * 4);
+    YGZB_CUDA(ctx, cudaMemcpyAsync(buf, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     a.kf_off = d_off; a.pt_off = d_off + (P + 1); a.obs_off = d_off + 2 * (P + 1);
     a.poses = d_poses; a.fixed = d_fixed; a.pts = d_pts; a.kf_idx = d_idx; a.pt_idx = d_idx + NO; a.obs = d_obs;
     a.lm_start = d_csr; a.lm_obs = d_csr + NP + 1; a.ps_start = d_csr + NP + 1 + NO; a.ps_obs = d_csr + NP + 1 + NO + NK + 1;
