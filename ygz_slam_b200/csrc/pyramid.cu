@@ -97,12 +97,25 @@ struct HRow {
     uint32_t lo, hi;  // (h0, h1) and (h2, h3): horizontal [1 4 6 4 1] sums of the thread's 4 destination columns
 };
 
-__device__ __forceinline__ HRow hfilter_row(const uint8_t* __restrict__ row, int k, bool first, bool last) {
-    const uint2 m = *reinterpret_cast<const uint2*>(row + 8 * k);                       // columns 8k .. 8k+7
-    // a: bytes 2,3 = columns 8k-2, 8k-1 (reflected to columns 2, 1 at the left border)
-    const uint32_t a = first ? __byte_perm(m.x, 0, 0x1200) : *reinterpret_cast<const uint32_t*>(row + 8 * k - 4);
-    // r: byte 0 = column 8k+8 (reflected to column 8k+6 at the right border)
-    const uint32_t r = last ? (m.y >> 16) : *reinterpret_cast<const uint32_t*>(row + 8 * k + 8);
+struct RawRow {
+    uint2 m;       // columns 8k .. 8k+7
+    uint32_t a;    // bytes 2,3 = columns 8k-2, 8k-1
+    uint32_t r;    // byte 0 = column 8k+8
+};
+
+// the three loads of one source row (issued early, consumed by hfilter one iteration later)
+__device__ __forceinline__ RawRow load_row(const uint8_t* __restrict__ row, int k, bool first, bool last) {
+    RawRow w;
+    w.m = *reinterpret_cast<const uint2*>(row + 8 * k);
+    // reflect-101 at the image border is a byte permute of the thread's own columns instead of a load
+    w.a = first ? __byte_perm(w.m.x, 0, 0x1200) : *reinterpret_cast<const uint32_t*>(row + 8 * k - 4);   // columns 2, 1
+    w.r = last ? (w.m.y >> 16) : *reinterpret_cast<const uint32_t*>(row + 8 * k + 8);                   // column 8k+6
+    return w;
+}
+
+__device__ __forceinline__ HRow hfilter(const RawRow& w) {
+    const uint2 m = w.m;
+    const uint32_t a = w.a, r = w.r;
     const uint32_t e_lo = __byte_perm(m.x, 0, 0x4240), e_hi = __byte_perm(m.y, 0, 0x4240);  // even columns (e0,e1) (e2,e3)
     const uint32_t o_lo = __byte_perm(m.x, 0, 0x4341), o_hi = __byte_perm(m.y, 0, 0x4341);  // odd columns  (o0,o1) (o2,o3)
     const uint32_t em_lo = __byte_perm(e_lo, a, 0x1016);          // (e-1, e0)
@@ -134,13 +147,24 @@ __global__ void __launch_bounds__(256) pyrdown_stream_kernel(uint8_t* __restrict
     const bool first = k == 0, last = k == tpr - 1;
     const int dy0 = strip * kStripRows;
     const int sh = src.h;
-    auto hrow = [&](int sy) { return hfilter_row(sp + (size_t)reflect101(sy, sh) * src.pitch, k, first, last); };
-    HRow h0 = hrow(2 * dy0 - 2), h1 = hrow(2 * dy0 - 1), h2 = hrow(2 * dy0);
+    // rows -2 .. sh+1 only (sh >= 4 on this path): one reflection, branch-free
+    auto raw = [&](int sy) {
+        const int r = sy < 0 ? -sy : (sy >= sh ? 2 * (sh - 1) - sy : sy);
+        return load_row(sp + (size_t)r * src.pitch, k, first, last);
+    };
+    HRow h0 = hfilter(raw(2 * dy0 - 2)), h1 = hfilter(raw(2 * dy0 - 1)), h2 = hfilter(raw(2 * dy0));
+    // software pipeline: the two source rows of destination row j + 1 are in flight while row j is filtered and stored
+    RawRow n3 = raw(2 * dy0 + 1), n4 = raw(2 * dy0 + 2);
 #pragma unroll
     for (int j = 0; j < kStripRows; ++j) {
         const int dy = dy0 + j;
         if (dy >= dst.h) break;
-        const HRow h3 = hrow(2 * dy + 1), h4 = hrow(2 * dy + 2);
+        const RawRow c3 = n3, c4 = n4;
+        if (j + 1 < kStripRows && dy + 1 < dst.h) {
+            n3 = raw(2 * dy + 3);
+            n4 = raw(2 * dy + 4);
+        }
+        const HRow h3 = hfilter(c3), h4 = hfilter(c4);
         *reinterpret_cast<uint32_t*>(dp + (size_t)dy * dst.pitch) = vfilter_pack(h0, h1, h2, h3, h4);
         h0 = h2;
         h1 = h3;
@@ -244,7 +268,7 @@ int launch_pyramid(ygzb_frames* f, int first, int count, const uint8_t* d_bgr) {
         }
     for (int L = 1; L < tail; ++L) {
         ProfScope ps(ctx, kStagePyrDown);
-        if (g.lv[L - 1].w % 8 == 0 && g.lv[L - 1].w >= 16 && g.lv[L - 1].h >= 2) {
+        if (g.lv[L - 1].w % 8 == 0 && g.lv[L - 1].w >= 16 && g.lv[L - 1].h >= 4) {
             const int strips = (g.lv[L].h + kStripRows - 1) / kStripRows;
             dim3 grid((strips * (g.lv[L - 1].w / 8) + 255) / 256, count);
             pyrdown_stream_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, first, g.lv[L - 1], g.lv[L], strips);
