@@ -39,3 +39,20 @@ def test_product_does_not_touch_the_oracle():
         if p.suffix in {".py", ".cu", ".cuh", ".cpp", ".h", ".hpp"}:
             txt = p.read_text(errors="ignore")
             assert "pyoracle" not in txt and "liboracle" not in txt and "oracle.h" not in txt, p
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ygz_b200.h must be usable from C (no C++ / CUDA / torch types): compile a pedantic C99 translation unit
+    that takes the address of every declared entry point and link it against the library (no call is made: no GPU)."""
+    import subprocess
+    syms = declared_symbols()
+    src = tmp_path / "abi.c"
+    body = "\n".join(f"    p[{i}] = (fn)&{s_};" for i, s_ in enumerate(syms))
+    src.write_text('#include "ygz_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n    fn p[%d];\n%s\n'
+                   '    printf("%%d\\n", (int)(sizeof p / sizeof p[0]));\n    return p[0] == 0;\n}\n' % (len(syms), body))
+    exe = tmp_path / "abi"
+    libdir = ROOT / "ygz_slam_b200"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe), f"-L{libdir}",
+                    "-lygz_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert int(out) == len(syms) and len(syms) >= 35
