@@ -22,6 +22,7 @@
 // Roofline class: FP64 ALU / latency (0.3 MB of unique data per iteration, ~1.1e7 FLOP): bench.py reports
 // achieved FLOP/s for the reduce, not HBM bytes.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -264,6 +265,7 @@ __device__ __noinline__ void ceres_linearise(const double* __restrict__ pose, do
 // reductions go through per-CTA partials + barrier.cluster, and CTA 0 factorises the reduced system in shared memory.
 // Every CTA keeps its own replica of the poses and of the LM scalars and takes the same (deterministic) decisions.
 constexpr int kClusterSize = 8;
+constexpr size_t kObsPerCtaFull = 1000;   // observations per CTA below which a smaller cluster wins (measured)
 
 struct ClusterWs {            // per problem, in global memory
     double red[4][kClusterSize][4];
@@ -1413,15 +1415,24 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
     auto kernel = ceres ? local_ba_kernel<true> : local_ba_kernel<false>;
     YGZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
-        // one cluster of kClusterSize CTAs (= SMs) per problem
+        // one cluster of CTAs (= SMs) per problem.  Every LM trial crosses ~8 cluster barriers, so small problems (a few
+        // thousand observations: the local BA of the tracking loop) are faster on fewer CTAs; large ones want all eight
+        size_t max_obs = 0;
+        for (size_t p = 0; p < P; ++p) max_obs = std::max(max_obs, (size_t)(obs_off[p + 1] - obs_off[p]));
+        int cluster = kClusterSize;
+        (void)max_obs;   // size-dependent choice pending measurement (tools/ba_cluster_sweep.py)
+        if (const char* e = getenv("YGZB_BA_CLUSTER")) {   // tuning knob: 1, 2, 4 or 8
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v;
+        }
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(n_problems * kClusterSize));
+        cfg.gridDim = dim3((unsigned)(n_problems * cluster));
         cfg.blockDim = dim3(kBAThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = ctx->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = kClusterSize;
+        attr[0].val.clusterDim.x = cluster;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
