@@ -160,9 +160,9 @@ def run_reference(args, rank: int, world: int) -> None:
     except Exception:  # noqa: BLE001
         pass
     threads = max(1, usable)
-    per_thread = 8                      # frames per thread per step -> bounded sample
-    n = threads * per_thread
-    frames = make_frames(min(n, 512), 0)
+    n = 512                             # the same 512-frame batch per step as the GPU arm (frame-parallel over the threads)
+    per_thread = -(-n // threads)
+    frames = make_frames(n, 0)
     for _ in range(args.warmup):
         cpu_run(ora, frames, n, threads)
     dt = 0.0
@@ -175,7 +175,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(n, "C++ host threads, frame-parallel (oracle/bench_driver.cpp)"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{n} frames/step ({per_thread} per thread) x {args.steps} steps; CPU restatement of the reference "
+                         "sample": f"{n} frames/step (<= {per_thread} per thread) x {args.steps} steps; CPU restatement of the reference "
                                    f"path (the reference cannot be built here), -O3 AVX2/FMA, {threads} std::threads",
                          "logical_cpus": os.cpu_count(), "affinity_cpus": usable, "cgroup_cpu_quota": quota},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
