@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Kernel time of the local BA for one cluster size (YGZB_BA_CLUSTER in the environment): the 8 small problems of the
-tracking loop and the C4 problem.  for c in 1 2 4 8; do YGZB_BA_CLUSTER=$c python tools/ba_cluster_sweep.py; done"""
+tracking loop and the C4 problem.  for c in 1 2 4 8 16; do YGZB_BA_CLUSTER=$c python tools/ba_cluster_sweep.py; done"""
 import os
 import sys
 

@@ -265,10 +265,11 @@ __device__ __noinline__ void ceres_linearise(const double* __restrict__ pose, do
 // reductions go through per-CTA partials + barrier.cluster, and CTA 0 factorises the reduced system in shared memory.
 // Every CTA keeps its own replica of the poses and of the LM scalars and takes the same (deterministic) decisions.
 constexpr int kClusterSize = 8;
+constexpr int kMaxCluster = 16;           // non-portable cluster size (opt-in attribute)
 constexpr size_t kObsPerCtaFull = 1000;   // observations per CTA below which a smaller cluster wins (measured)
 
 struct ClusterWs {            // per problem, in global memory
-    double red[4][kClusterSize][4];
+    double red[4][kMaxCluster][4];
     double Hpp[kMaxFreePoses * 36];
     double bp[kMaxFreePoses * 6];
     double S[kMaxFreePoses * 6 * kMaxFreePoses * 6];
@@ -1423,8 +1424,9 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
         (void)max_obs;   // size-dependent choice pending measurement (tools/ba_cluster_sweep.py)
         if (const char* e = getenv("YGZB_BA_CLUSTER")) {   // tuning knob: 1, 2, 4 or 8
             const int v = atoi(e);
-            if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v;
+            if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cluster = v;
         }
+        if (cluster > 8) YGZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(n_problems * cluster));
         cfg.blockDim = dim3(kBAThreads);
