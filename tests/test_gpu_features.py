@@ -169,7 +169,8 @@ def test_match_frames_device_resident(ctx3, oracle, synth_frames):
     fr.close()
 
 
-@pytest.mark.parametrize("w,h,levels,cell", [(752, 480, 4, 10), (324, 246, 3, 8), (1281, 721, 5, 20)])
+@pytest.mark.parametrize("w,h,levels,cell", [(752, 480, 4, 10), (324, 246, 3, 8), (1281, 721, 5, 20), (640, 480, 1, 10), (640, 480, 2, 10),
+                                              (128, 96, 3, 8), (200, 150, 8, 10)])
 def test_other_geometries_bit_exact(oracle, w, h, levels, cell):
     """Image sizes other than 640x480: widths that are not multiples of 8 / 16 (tiled pyrDown fallback, word-load FAST
     staging), ragged FAST tiles, odd level sizes, other grid cell sizes -- pyramid, corner statistics, features and
@@ -199,7 +200,7 @@ def test_other_geometries_bit_exact(oracle, w, h, levels, cell):
                 assert stats[s, L, 0] == len(xy) and stats[s, L, 1] == len(nm), (s, L)
             want = oracle.detect(pyr, w=w, h=h, n_levels=levels, cell=cell)
             _assert_features_equal(got[s], want)
-            assert want["n"] > 50
+            assert want["n"] > (50 if w >= 300 else 0)
             wants.append(want)
         idx, dist = fr.match([0], [1], True)[0]
         widx, wdist = oracle.match_bf(wants[0]["desc"], wants[1]["desc"], True)
