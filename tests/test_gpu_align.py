@@ -144,3 +144,51 @@ def test_align1d_bit_exact(ctx3, oracle):
         assert ok == got_ok[i] and u == got_uv[i, 0] and v == got_uv[i, 1], i
         assert hinv == got_h[i] or (np.isinf(hinv) and np.isinf(got_h[i]))
     fr.close()
+
+
+def test_alignment_and_klt_on_another_geometry(oracle):
+    """752 x 480, 4 levels (not the 640 x 480 default): FindDirectProjection bit-exact, SparseImgAlign and KLT within
+    their tolerances -- the level geometry (pitches, offsets, borders) is a run-time parameter everywhere."""
+    from ygz_slam_b200 import Context
+    w, h, levels = 752, 480, 4
+    tex = synth.texture(0x59475A00, 2048)
+    T1, T2 = synth.trajectory(1), synth.trajectory(4)
+    g1, d1 = synth.render_plane(tex, T1, noise_sigma=2.0, seed=11, w=w, h=h)
+    g2, _ = synth.render_plane(tex, T2, noise_sigma=2.0, seed=12, w=w, h=h)
+    p1, p2 = oracle.build_pyramid(g1, levels), oracle.build_pyramid(g2, levels)
+    f = oracle.detect(p1, w=w, h=h, n_levels=levels)
+    px = np.stack([f["px"], f["py"]], 1)
+    depth = d1[f["py"].astype(int), f["px"].astype(int)]
+    n = len(depth)
+    assert n > 500
+    Trel = se3.mul(T2, se3.inv(T1))
+    Xc = np.stack([(px[:, 0] - synth.CX) * depth / synth.FX, (px[:, 1] - synth.CY) * depth / synth.FY, depth], 1)
+    Xc2 = (Trel[:, :3] @ Xc.T).T + Trel[:, 3]
+    gt = np.stack([synth.FX * Xc2[:, 0] / Xc2[:, 2] + synth.CX, synth.FY * Xc2[:, 1] / Xc2[:, 2] + synth.CY], 1)
+    init = gt + np.random.default_rng(5).uniform(-2, 2, gt.shape)
+    ctx = Context(0, image_width=w, image_height=h, n_levels=levels)
+    try:
+        fr = ctx.frames(2)
+        fr.upload(np.stack([g1, g2]))
+        eye = np.eye(4)[:3]
+        want_px, want_lvl, want_ok = oracle.find_direct_projection(p1, p2, w, h, levels, eye, Trel, px, depth, f["level"], init)
+        z, o = np.zeros(n, np.int32), np.ones(n, np.int32)
+        got_px, got_lvl, got_ok = fr.project_align(z, o, np.stack([eye.reshape(-1), Trel.reshape(-1)]), z, o, px, depth,
+                                                   f["level"].astype(np.uint8), init)
+        assert np.array_equal(got_ok, want_ok) and np.array_equal(got_lvl, want_lvl) and np.array_equal(got_px, want_px)
+        assert got_ok.mean() > 0.8
+        has = np.ones(n, np.uint8)
+        wT, wn, _ = oracle.sparse_align(p1, p2, w, h, levels, px, depth, has, T1, T1, max_level=3)
+        gT, gn, _ = fr.sparse_align([0], [1], [0, n], px, depth, has, T1.reshape(1, 12), T1.reshape(1, 12), max_level=3)
+        assert gn[0] == wn
+        assert np.linalg.norm(se3.se3_log(se3.mul(se3.inv(gT[0]), wT))) < 1e-4
+        assert np.linalg.norm(se3.se3_log(se3.mul(se3.inv(gT[0]), T2))) < 5e-3
+        ref = px.astype(np.float32)
+        want, wst, werr = oracle.klt(g1, g2, ref, ref.copy())
+        got, gst, gerr = fr.klt([0], [1], [0, n], ref, ref.copy())
+        assert (gst != wst.astype(bool)).mean() < 0.005
+        both = gst & wst.astype(bool)
+        assert np.abs(got[both] - want[both]).max() < 1e-3 and both.mean() > 0.9
+        fr.close()
+    finally:
+        ctx.close()
