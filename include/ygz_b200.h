@@ -80,6 +80,10 @@ void ygzb_frames_destroy(ygzb_frames* f);
  * channels 1 (grey) or 3 (BGR); frame_stride = bytes between consecutive host images.          */
 int ygzb_frames_upload(ygzb_frames* f, int first, int count, const uint8_t* host, int channels,
                        size_t frame_stride);
+/* device-to-device copy of the whole pyramid of one slot into another (asynchronous on the context stream): lets a
+ * caller keep a frame beyond its staging slot, e.g. when Frame becomes a key-frame (the reference keeps the cv::Mat
+ * pyramid alive through the Frame object, include/ygz/Basic/Frame.h:138).  The slot's feature store is not copied. */
+int ygzb_frames_copy(ygzb_frames* f, int src_slot, int dst_slot);
 /* pyramid build only, for level-0 images already resident in slot storage (bench "value" leg) */
 int ygzb_frames_build_pyramid(ygzb_frames* f, int first, int count);
 /* device pointer / geometry of slot storage, level 0 first, every level pitch-linear */

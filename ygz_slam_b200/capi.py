@@ -35,7 +35,7 @@ EXPORTS = [
     "ygzb_default_params", "ygzb_create", "ygzb_destroy", "ygzb_last_error", "ygzb_synchronize", "ygzb_stream",
     "ygzb_launch_count", "ygzb_profile_enable", "ygzb_profile_read", "ygzb_profile_stage_count",
     "ygzb_profile_stage_name", "ygzb_host_alloc", "ygzb_host_free", "ygzb_frames_create", "ygzb_frames_destroy",
-    "ygzb_frames_upload", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
+    "ygzb_frames_upload", "ygzb_frames_copy", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
     "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d", "ygzb_align1d",
     "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_pose_only",
@@ -248,6 +248,9 @@ class Frames:
     def upload_raw(self, ptr: int, n: int, channels: int, frame_stride: int, first: int = 0):
         self.ctx.check(self.lib.ygzb_frames_upload(self.h, first, n, C.c_void_p(ptr), channels, C.c_size_t(frame_stride)),
                        "ygzb_frames_upload")
+
+    def copy_slot(self, src: int, dst: int):
+        self.ctx.check(self.lib.ygzb_frames_copy(self.h, int(src), int(dst)), "ygzb_frames_copy")
 
     def build_pyramid(self, first: int, count: int):
         self.ctx.check(self.lib.ygzb_frames_build_pyramid(self.h, first, count), "ygzb_frames_build_pyramid")

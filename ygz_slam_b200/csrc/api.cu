@@ -374,6 +374,16 @@ int ygzb_frames_build_pyramid(ygzb_frames* f, int first, int count) {
     return launch_pyramid(f, first, count, nullptr);
 }
 
+int ygzb_frames_copy(ygzb_frames* f, int src_slot, int dst_slot) {
+    if (!f || src_slot < 0 || dst_slot < 0 || src_slot >= f->capacity || dst_slot >= f->capacity) return YGZB_ERR_INVALID;
+    if (src_slot == dst_slot) return YGZB_OK;
+    ygzb_ctx* ctx = f->ctx;
+    cudaSetDevice(ctx->device);
+    YGZB_CUDA(ctx, cudaMemcpyAsync(f->d_pyr + (size_t)dst_slot * ctx->slot_stride, f->d_pyr + (size_t)src_slot * ctx->slot_stride,
+                                   ctx->slot_stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    return YGZB_OK;
+}
+
 int ygzb_frames_upload(ygzb_frames* f, int first, int count, const uint8_t* host, int channels, size_t frame_stride) {
     if (!f || !host || first < 0 || count < 0 || first + count > f->capacity) return YGZB_ERR_INVALID;
     ygzb_ctx* ctx = f->ctx;

@@ -119,8 +119,10 @@ struct StageTimer {
 
 class Driver {
   public:
+    // slot layout: [0, S) = staging slots of the incoming frames (contiguous: one upload per lock-step frame), then a ring
+    // of kSlotsPerStream - 1 key-frame slots per stream; a frame that becomes a key-frame is copied device-to-device
     Driver(ygzb_ctx* ctx, ygzb_frames* fr, int n_streams, const Params& p) : ctx_(ctx), fr_(fr), S_(n_streams), prm_(p), st_(n_streams) {
-        for (int i = 0; i < S_; ++i) st_[i].slot0 = i * kSlotsPerStream;
+        for (int i = 0; i < S_; ++i) st_[i].slot0 = S_ + i * (kSlotsPerStream - 1);
         int rows = 0, cols = 0;
         ygzb_grid_dims(ctx, &rows, &cols);
         n_cells_ = rows * cols;
@@ -129,10 +131,16 @@ class Driver {
 
     // one lock-step frame: images[i] = grey frame of stream i, depth[i] = its (static) ground-truth depth map
     int add_frames(const uint8_t* const* images, const double* const* depth, int frame_id) {
-        cur_slot_.assign(S_, 0);
-        for (int i = 0; i < S_; ++i) {
-            cur_slot_[i] = next_slot(i);
-            TIMED(kTUpload, ygzb_frames_upload(fr_, cur_slot_[i], 1, images[i], 1, (size_t)W * H));
+        cur_slot_.resize(S_);
+        for (int i = 0; i < S_; ++i) cur_slot_[i] = i;
+        // one strided copy when the caller's frames are equally spaced in host memory (a stacked [stream][frame] array)
+        bool strided = S_ > 1;
+        const ptrdiff_t stride = S_ > 1 ? images[1] - images[0] : 0;
+        for (int i = 1; i + 1 < S_ && strided; ++i) strided = images[i + 1] - images[i] == stride;
+        if (strided && stride >= (ptrdiff_t)W * H) {
+            TIMED(kTUpload, ygzb_frames_upload(fr_, 0, S_, images[0], 1, (size_t)stride));
+        } else {
+            for (int i = 0; i < S_; ++i) TIMED(kTUpload, ygzb_frames_upload(fr_, i, 1, images[i], 1, (size_t)W * H));
         }
         std::vector<int> boot, track;
         for (int i = 0; i < S_; ++i) {
@@ -154,13 +162,13 @@ class Driver {
   private:
     int next_slot(int i) const {
         const Stream& s = st_[i];
-        for (int c = 0; c < kSlotsPerStream; ++c) {
+        for (int c = 0; c < kSlotsPerStream - 1; ++c) {
             const int slot = s.slot0 + c;
             bool used = false;
             for (int k = s.first_local(); k < (int)s.keyframes.size(); ++k) used |= s.keyframes[k].slot == slot;
             if (!used) return slot;
         }
-        return s.slot0;  // cannot happen: the ring has kLocalKeyframes + 2 slots
+        return s.slot0;  // cannot happen: the ring has kLocalKeyframes + 1 slots
     }
 
     // TrackRefFrame + TrackLocalMap + key-frame decision for the streams in idx
@@ -331,7 +339,8 @@ class Driver {
         for (int j = 0; j < n; ++j) {
             Stream& s = st_[idx[j]];
             Keyframe kf;
-            kf.slot = slots[j];
+            kf.slot = next_slot(idx[j]);   // the frame leaves its staging slot: keep its pyramid in the stream's key-frame ring
+            TIMED(kTDetect, ygzb_frames_copy(fr_, slots[j], kf.slot));
             kf.frame_id = frame_id;
             kf.T = s.T;
             const Mat34 Tin = inv(s.T);
