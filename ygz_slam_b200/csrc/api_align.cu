@@ -198,14 +198,24 @@ int ygzb_sparse_align(ygzb_frames* f, int n_problems, const int32_t* ref_slot, c
     double* d_fj = c.take<double>(12 * T);
     uint8_t* d_vis = c.take<uint8_t>(T);
     double* d_ws = c.take<double>(sparse_align_ws_doubles(n_problems));
-    TRY(h2d(ctx, d_slots, ref_slot, P));
-    TRY(h2d(ctx, d_slots + P, cur_slot, P));
-    TRY(h2d(ctx, d_off, offsets, P + 1));
-    TRY(h2d(ctx, d_px, px, 2 * T));
-    TRY(h2d(ctx, d_depth, depth, T));
-    TRY(h2d(ctx, d_mp, has_mappoint, T));
-    TRY(h2d(ctx, d_Tref, T_cw_ref, 12 * P));
-    TRY(h2d(ctx, d_Tcur, T_cw_cur, 12 * P));
+    {   // the inputs are the first seven sub-buffers of `buf`: one pinned staging copy instead of eight pageable ones
+        const size_t in_bytes = (size_t)((uint8_t*)(d_Tcur + 12 * P) - (uint8_t*)buf);
+        uint8_t* stage = (uint8_t*)host_scratch(ctx, 1, in_bytes);
+        if (!stage) return YGZB_ERR_CUDA;
+        YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        auto put = [&](const void* dev_ptr, const void* src, size_t bytes) {
+            if (bytes) memcpy(stage + ((const uint8_t*)dev_ptr - (uint8_t*)buf), src, bytes);
+        };
+        put(d_slots, ref_slot, P * 4);
+        put(d_slots + P, cur_slot, P * 4);
+        put(d_off, offsets, (P + 1) * 4);
+        put(d_px, px, 2 * T * 8);
+        put(d_depth, depth, T * 8);
+        put(d_mp, has_mappoint, T);
+        put(d_Tref, T_cw_ref, 12 * P * 8);
+        put(d_Tcur, T_cw_cur, 12 * P * 8);
+        YGZB_CUDA(ctx, cudaMemcpyAsync(buf, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     YGZB_CUDA(ctx, cudaMemsetAsync(d_iters, 0, P * kMaxLevels * sizeof(int32_t), ctx->stream));
     YGZB_CUDA(ctx, cudaMemsetAsync(d_patch, 0, 16 * T * sizeof(float), ctx->stream));
     TRY(launch_sparse_align(f, n_problems, d_slots, d_slots + P, d_off, d_px, d_depth, d_mp, d_Tref, d_Tcur, max_level, min_level,

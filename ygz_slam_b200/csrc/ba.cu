@@ -1523,10 +1523,20 @@ int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const 
     a.ws = c.take<double>(P * 4 * kPoseCluster * kPoseRed);
     a.offsets = d_off; a.pw = d_pw; a.px = d_px;
     a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
-    TRY(h2d(ctx, d_off, offsets, P + 1));
-    TRY(h2d(ctx, d_pw, pt_world, 3 * N));
-    TRY(h2d(ctx, d_px, px, 2 * N));
-    TRY(h2d(ctx, a.T_cw, (const double*)T_cw, 12 * P));
+    {   // the four inputs are the first sub-buffers of `buf`: one pinned staging copy instead of four pageable ones
+        const size_t in_bytes = (size_t)(reinterpret_cast<uint8_t*>(a.T_cw + 12 * P) - static_cast<uint8_t*>(buf));
+        uint8_t* stage = static_cast<uint8_t*>(host_scratch(ctx, 1, in_bytes));
+        if (!stage) return YGZB_ERR_CUDA;
+        YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        auto put = [&](const void* dev_ptr, const void* src, size_t bytes) {
+            if (bytes) memcpy(stage + (static_cast<const uint8_t*>(dev_ptr) - static_cast<uint8_t*>(buf)), src, bytes);
+        };
+        put(d_off, offsets, (P + 1) * 4);
+        put(d_pw, pt_world, 3 * N * 8);
+        put(d_px, px, 2 * N * 8);
+        put(a.T_cw, T_cw, 12 * P * 8);
+        YGZB_CUDA(ctx, cudaMemcpyAsync(buf, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(n_problems * kPoseCluster));
