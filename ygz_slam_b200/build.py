@@ -45,7 +45,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
-        if not VO_LIB.exists() or VO_LIB.stat().st_mtime < (HERE / "host" / "vo_driver.cpp").stat().st_mtime:
+        if not VO_LIB.exists() or VO_LIB.stat().st_mtime < max((HERE / "host" / n).stat().st_mtime for n in ("vo_driver.cpp", "e2e_driver.cpp")):
             build_vo_driver()
         return LIB
     objdir = HERE / "build"
@@ -77,10 +77,11 @@ VO_LIB = HERE / "libygz_vo.so"
 
 
 def build_vo_driver() -> Path:
-    """Host-only C++ (g++): the native lock-step tracking loop over the C ABI (host/vo_driver.cpp)."""
-    src = HERE / "host" / "vo_driver.cpp"
+    """Host-only C++ (g++): the native callers of the C ABI -- lock-step tracking loop (host/vo_driver.cpp) and the
+    end-to-end extract + match loop (host/e2e_driver.cpp)."""
+    srcs = [str(HERE / "host" / "vo_driver.cpp"), str(HERE / "host" / "e2e_driver.cpp")]
     gxx = shutil.which("g++") or "g++"
-    cmd = [gxx, "-std=c++20", "-O3", "-fPIC", "-shared", "-Wall", "-pthread", "-o", str(VO_LIB), str(src), f"-L{HERE}", "-lygz_b200",
+    cmd = [gxx, "-std=c++20", "-O3", "-fPIC", "-shared", "-Wall", "-pthread", "-o", str(VO_LIB), *srcs, f"-L{HERE}", "-lygz_b200",
            "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
     return VO_LIB
