@@ -56,3 +56,34 @@ def test_header_is_plain_c_and_links(tmp_path):
                     "-lygz_b200", f"-Wl,-rpath,{libdir}"], check=True, capture_output=True, text=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert int(out) == len(syms) and len(syms) >= 35
+
+
+def _build_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "extract_match"
+    libdir = ROOT / "ygz_slam_b200"
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "extract_match.c"),
+                    f"-L{libdir}", "-lygz_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True, capture_output=True, text=True)
+    return exe
+
+
+def test_c_example_builds_and_fails_loudly_without_gpu(tmp_path):
+    """examples/extract_match.c (the test_orb_match shape in plain C) builds against the header + library; without an
+    sm_100 device it must stop at ygzb_create with a message, not fall back to anything."""
+    import subprocess
+    import torch
+    exe = _build_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu-marked run of the example")
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 1 and "ygzb_create" in r.stderr and "sm_100" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_runs(tmp_path):
+    import subprocess
+    exe = _build_example(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, check=True)
+    words = r.stdout.replace(",", "").split()
+    n1, n2, matches, good = int(words[1]), int(words[3]), int(words[6]), int(words[9])
+    assert n1 > 200 and n2 > 200 and matches > 100 and 0 < good <= matches
