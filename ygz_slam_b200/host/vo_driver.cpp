@@ -14,6 +14,7 @@
 //
 // Build: host C++ only (g++), links libygz_b200.so; see ygz_slam_b200/build.py (libygz_vo.so).
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <chrono>
 #include <cmath>
@@ -104,12 +105,15 @@ struct Params {
 
 // wall time per C-ABI stage (printed when YGZ_VO_TIMING is set): where a lock-step frame goes
 enum { kTUpload, kTSparse, kTProject, kTPoseOnly, kTDetect, kTLocalBA, kTStages };
-double g_stage_s[kTStages];   // diagnostic only: threads add without synchronisation
+std::atomic<long long> g_stage_ns[kTStages];   // summed over the host threads
 struct StageTimer {
     int stage;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     explicit StageTimer(int s) : stage(s) {}
-    ~StageTimer() { g_stage_s[stage] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+    ~StageTimer() {
+        g_stage_ns[stage].fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+                                    std::memory_order_relaxed);
+    }
 };
 #define TIMED(stage, call)        \
     do {                          \
@@ -501,7 +505,7 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
     if (!ctx || !params || n_streams < 1 || n_frames < 1 || !images || !depth || !traj || !stats || !seconds) return YGZB_ERR_INVALID;
     n_threads = std::max(1, std::min(n_threads, n_streams));
     warm = std::max(0, std::min(warm, n_frames - 1));
-    for (double& v : g_stage_s) v = 0;
+    for (auto& v : g_stage_ns) v.store(0);
     std::vector<int> rcs(n_threads, YGZB_OK);
     std::barrier sync_point(n_threads);
     std::chrono::steady_clock::time_point t_begin, t_end;
@@ -520,7 +524,7 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
                 sync_point.arrive_and_wait();
                 if (t == 0) {
                     t_begin = std::chrono::steady_clock::now();
-                    for (double& v : g_stage_s) v = 0;
+                    for (auto& v : g_stage_ns) v.store(0);
                 }
             }
             if (rc != YGZB_OK) continue;   // keep meeting the barriers
@@ -553,11 +557,11 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
     if (getenv("YGZ_VO_TIMING")) {
         static const char* names[kTStages] = {"upload", "sparse_align", "project_align", "pose_only", "detect", "local_ba"};
         double sum = 0;
-        for (int i = 0; i < kTStages; ++i) sum += g_stage_s[i];
+        for (int i = 0; i < kTStages; ++i) sum += 1e-9 * g_stage_ns[i].load();
         const int timed = n_frames - warm;
         fprintf(stderr, "[ygz_vo] %d streams on %d host threads x %d timed frames: %.3f ms per lock-step frame; C-ABI time summed over threads %.3f ms\n",
                 n_streams, n_threads, timed, 1e3 * *seconds / timed, 1e3 * sum / timed);
-        for (int i = 0; i < kTStages; ++i) fprintf(stderr, "[ygz_vo]   %-14s %.3f ms/frame\n", names[i], 1e3 * g_stage_s[i] / timed);
+        for (int i = 0; i < kTStages; ++i) fprintf(stderr, "[ygz_vo]   %-14s %.3f ms/frame\n", names[i], 1e-6 * g_stage_ns[i].load() / timed);
     }
     for (int rc : rcs)
         if (rc != YGZB_OK) return rc;
