@@ -23,6 +23,8 @@
 // and merge_cells_kernel replays the level order.  All f32 maths is unfused (-fmad=false).
 #include <cuda.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ygzb {
@@ -661,11 +663,10 @@ int launch_detect(ygzb_frames* f, int n, bool have_occupied) {
         ProfScope ps(ctx, kStageFastCells);
         a.tma_levels = f->tma_levels;
         // 5 CTAs x 31 KB per SM: ask for the large shared-memory carve-out (the tiles live in smem, L1 is barely used)
-        static bool carveout_set = false;
-        if (!carveout_set) {
+        static std::once_flag carveout_once;   // contexts of several host threads share the kernel's attribute
+        std::call_once(carveout_once, [] {
             cudaFuncSetAttribute(fast_cells_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carveout_set = true;
-        }
+        });
         fast_cells_kernel<<<grid, 256, 0, ctx->stream>>>(a, reinterpret_cast<const CUtensorMap*>(f->d_tile_maps));
     }
     YGZB_LAUNCHED(ctx);
