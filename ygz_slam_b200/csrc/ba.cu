@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -1414,7 +1415,16 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
     ClusterWs* d_ws = static_cast<ClusterWs*>(dev_scratch(ctx, 5, sizeof(ClusterWs) * P));
     if (!d_ws) return YGZB_ERR_CUDA;
     auto kernel = ceres ? local_ba_kernel<true> : local_ba_kernel<false>;
-    YGZB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        // opt both instantiations in to the largest reduced system (16 free poses: 74.5 KB) once: a per-call value would race
+        // between the contexts of several host threads
+        static std::once_flag smem_once;
+        std::call_once(smem_once, [] {
+            const int max_smem = (int)(sizeof(double) * ((size_t)(6 * kMaxFreePoses) * (6 * kMaxFreePoses) + 6 * kMaxFreePoses));
+            cudaFuncSetAttribute(local_ba_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            cudaFuncSetAttribute(local_ba_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        });
+    }
     {
         // one cluster of CTAs (= SMs) per problem.  Every LM trial crosses ~8 cluster barriers, so small problems (a few
         // thousand observations: the local BA of the tracking loop) are faster on fewer CTAs; large ones want all eight
