@@ -1,24 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the ygz-slam hot path on B200 (contract: task statement, section 4).
 
-Workload (BASELINE.json configs[1], "C2"): FAST+ORB extract + brute-force Hamming match on a synthetic
-640x480 stream, 8-level pyramid, ~1000-1300 keypoints/frame.  One STEP = one batch of `--batch` frames:
-    pyramid (7 pyrDown levels) -> fused FAST-10/score/nonmax/grid-cell selection on all 8 levels
-    -> IC angle + ORB descriptors -> cross-checked brute-force match of frame i against frame i+1.
-metric = tracked frames/sec (whole job, all ranks).
+Workload (BASELINE.json metric "tracked frames/sec on 640x480 synthetic stream", configs[4] "C5"): `--streams` (8)
+independent synthetic 640x480 streams per GPU through the FULL tracking loop of the reference --
+    Frame::InitFrame (pyramid) -> Matcher::SparseImageAlignment against the reference key-frame
+    -> LocalMapping::TrackLocalMap: candidate projection + Matcher::FindDirectProjection (8x8 patch alignment) of the
+       local map -> ba::OptimizeCurrentPoseOnly -> key-frame decision
+    -> at key-frames FeatureDetector::Detect (grid FAST-10 + ORB), depth-initialised map points, ba::LocalBAG2O.
+One STEP = `--frames-per-step` (10) consecutive frames of every stream (80 tracked frames per GPU); every step consumes
+frames that were never touched before.  metric = tracked frames/sec (whole job, all ranks).
 
-  value : frames already resident in HBM (level 0 in the slot storage) when the timed region starts;
-          CUDA events on the library's stream, max over ranks.
-  e2e   : same metric through the public C ABI with HOST buffers: every step copies the batch from
-          pinned host memory (H2D) and reads keypoints + matches back (D2H) inside the timed region.
-  roofline      : dominant kernel (largest share of the step, timed live with CUDA events around each
-                  launch) -- algorithmic bytes / duration against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  : the CPU oracle (-O3 AVX2/FMA build of the reference restatement) on a bounded sample
-                  of the same frames, rank 0 only.
-  --impl reference : the reference's CPU path (oracle restatement: the reference itself cannot be built
-                  here) on all host threads, frame-parallel, same metric/config.
-Multi-GPU: independent frame batches (streams) per rank, no data-path collective ("weak" scaling);
-torch.distributed (NCCL) only for the barrier and the max-over-ranks of the device time.
+  value : frames already resident in HBM when the timed region starts; the region is timed with CUDA events on the
+          library's stream (first event after the warm-up barrier, second after every stream has drained), max over ranks.
+  e2e   : the same loop through the public C ABI with HOST buffers: every step's frames are copied from pinned host
+          memory (H2D) and the poses / features / BA results are read back (D2H) inside the timed region.
+  roofline      : dominant kernel of the step (largest share of the device time, CUDA events around each launch in a
+                  separate profiled pass) -- algorithmic bytes / duration against MEASURED_PEAKS.json hbm_gbs, plus the
+                  FP64 FLOP/s of the BA reduce.
+  cpu_baseline  : the CPU oracle (-O3 AVX2/FMA build of the reference restatement) through the same loop in C++
+                  (oracle/vo_cpu.cpp) on a bounded sample of the same streams, rank 0, N=1 only; 1 thread and
+                  one thread per stream, with a per-stage breakdown.
+  --impl reference : the reference's CPU path (oracle restatement: the reference itself cannot be built here) through
+                  the same loop on all usable host threads, one independent stream per thread, same metric/config.
+  --workload extract_match : BASELINE configs[1] (C2, the round-1 headline); at N=1 it is also run as a secondary record.
+Multi-GPU: independent streams per rank, no data-path collective ("weak" scaling: 8 streams per GPU); the BASELINE
+sentence "8 streams sharded across the GPUs" is measured as well (`sharded_8_streams`, 8/N streams per GPU).
+torch.distributed (NCCL) only for the barrier, the max-over-ranks of the device time and the gather of per-rank records.
 """
 from __future__ import annotations
 
@@ -151,15 +158,7 @@ def run_reference(args, rank: int, world: int) -> None:
     from oracle.pyoracle import Oracle
     ora = Oracle(native=True)
     # all the host threads the process may use: the scheduler affinity mask, capped by a cgroup CPU quota if there is one
-    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    quota = None
-    try:
-        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-        if q != "max":
-            quota = float(q) / float(p)
-    except Exception:  # noqa: BLE001
-        pass
-    threads = max(1, usable)
+    threads, usable, quota = usable_threads()
     n = 512                             # the same 512-frame batch per step as the GPU arm (frame-parallel over the threads)
     per_thread = -(-n // threads)
     frames = make_frames(n, 0)
@@ -286,81 +285,7 @@ def secondary_workloads(ctx) -> dict:
         "achieved_gflops_fp64": flop_per_trial * trials / (k_ms * 1e-3) / 1e9, "flop_per_lm_trial_model": flop_per_trial,
         "chi2_final_gpu": st[0]["chi2_final"], "chi2_final_cpu": wst["chi2_final"],
         "max_landmark_diff_vs_oracle_m": float(np.abs(X - wX).max())}
-    # ---- C5 shape on one GPU: 8 streams x 40 frames (needs the 3-level pyramid of the reference default) -------
-    from ygz_slam_b200 import Context as _Ctx
-    c3 = _Ctx(ctx.device_index)
-    try:
-        out["c5_vo_8_streams_1_gpu"] = run_vo(c3, 8, 40)
-        out["c5_vo_8_streams_1_gpu"]["python_host_loop"] = run_vo(c3, 8, 40, native=False)["tracked_frames_per_s"]
-        # the kernels of the tracking loop are latency-bound (one CTA / one cluster per stream), so throughput grows with the
-        # number of streams a GPU carries: same loop, 32 streams, 4 host threads
-        out["c5_vo_32_streams_1_gpu"] = run_vo(c3, 32, 40, threads=4)
-    finally:
-        c3.close()
-    # CPU baseline of the same loop: the identical caller code (ygz_slam_b200/vo.py) on the oracle backend, one stream,
-    # bounded sample (the reference's VisualOdometry is single threaded)
-    try:
-        from oracle.vo_backend import OracleBackend
-        from ygz_slam_b200 import vo
-        n_cpu = 12
-        imgs, depth, _ = synth.shift_stream(0, n_cpu)
-        Vc = vo.VisualOdometry(OracleBackend(ora, 3), 1, kf_min_frames=5, kf_min_rot=0.03, kf_min_trans=0.03)
-        Vc.add_frames([imgs[0]], [depth], 0)
-        t0 = time.perf_counter()
-        for k in range(1, n_cpu):
-            Vc.add_frames([imgs[k]], [depth], k)
-        dt = time.perf_counter() - t0
-        cpu_fps = (n_cpu - 1) / dt
-        c5 = out["c5_vo_8_streams_1_gpu"]
-        c5["cpu_tracked_frames_per_s_1_thread"] = cpu_fps
-        c5["cpu_sample"] = f"{n_cpu - 1} frames of stream 0 through the same loop on the oracle (-O3 build), 1 thread"
-        c5["gpu_over_cpu_1_thread"] = c5["tracked_frames_per_s"] / cpu_fps
-        if "c5_vo_32_streams_1_gpu" in out:
-            out["c5_vo_32_streams_1_gpu"]["gpu_over_cpu_1_thread"] = out["c5_vo_32_streams_1_gpu"]["tracked_frames_per_s"] / cpu_fps
-    except Exception as e:  # noqa: BLE001
-        out["c5_vo_8_streams_1_gpu"]["cpu_error"] = repr(e)
     return out
-
-
-def run_vo(ctx, n_streams: int, n_frames: int, stream_offset: int = 0, native: bool = True, threads: int = 2) -> dict:
-    """BASELINE config C5 shape: `n_streams` independent synthetic 640x480 streams tracked in lock step (sparse alignment ->
-    direct projection -> pose-only -> keyframes: detect + BA), every numeric step one batched C-ABI call with host buffers
-    (uploads inside the timed region).  native = the C++ host loop (ygz_slam_b200/host/vo_driver.cpp); otherwise the same
-    loop in Python (ygz_slam_b200/vo.py, the one the parity tests run against the oracle)."""
-    from ygz_slam_b200 import se3, synth, vo
-    data = [synth.shift_stream(stream_offset + s, n_frames) for s in range(n_streams)]
-    warm = 3
-    if native:
-        from ygz_slam_b200 import vo_native
-        traj, stats, dt = vo_native.run(ctx, [d[0] for d in data], [d[1] for d in data], 5, 0.03, 0.03, warm=warm, threads=threads)
-        lost = sum(s["lost"] for s in stats)
-        errs = [float(np.linalg.norm(se3.se3_log(se3.mul(traj[s, -1], se3.inv(data[s][2][-1]))))) for s in range(n_streams)]
-        kfs, bas = sum(s["keyframes"] for s in stats), sum(s["ba"] for s in stats)
-        note = (f"host loop in C++ (host/vo_driver.cpp) on {min(threads, n_streams)} host threads with one context each; one batched "
-                "C-ABI call per stage, thread and lock-step frame")
-    else:
-        be = vo.GpuBackend(ctx, n_streams * vo.VisualOdometry.SLOTS_PER_STREAM)
-        V = vo.VisualOdometry(be, n_streams, kf_min_frames=5, kf_min_rot=0.03, kf_min_trans=0.03)
-        t0 = None
-        for k in range(n_frames):
-            if k == warm:
-                ctx.synchronize()
-                t0 = time.perf_counter()
-            V.add_frames([data[s][0][k] for s in range(n_streams)], [data[s][1] for s in range(n_streams)], k)
-        ctx.synchronize()
-        dt = time.perf_counter() - t0
-        errs, lost = [], 0
-        for s in range(n_streams):
-            st = V.streams[s]
-            lost += int(st.lost)
-            errs.append(float(np.linalg.norm(se3.se3_log(se3.mul(st.T_cw, se3.inv(data[s][2][-1]))))))
-        be.fr.close()
-        kfs = int(sum(V.streams[s].stats["keyframes"] for s in range(n_streams)))
-        bas = int(sum(V.streams[s].stats["ba"] for s in range(n_streams)))
-        note = "host loop in Python (ygz_slam_b200/vo.py); one batched C-ABI call per stage and lock-step frame"
-    return {"streams": n_streams, "frames_per_stream": n_frames, "tracked_frames_per_s": n_streams * (n_frames - warm) / dt,
-            "ms_per_lockstep_frame": 1e3 * dt / (n_frames - warm), "streams_lost": lost, "final_pose_error_vs_gt_max": max(errs),
-            "keyframes": kfs, "local_bas": bas, "note": note}
 
 
 def workload_config(batch: int, how: str) -> dict:
@@ -371,69 +296,286 @@ def workload_config(batch: int, how: str) -> dict:
             "l2_policy": "inputs larger than L2: %.0f MB of level-0 pixels per step vs 126 MB L2" % (batch * FRAME_BYTES / 1e6)}
 
 
-def main() -> None:
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
-    ap.add_argument("--workload", default="extract_match", choices=["extract_match", "vo"],
-                    help="extract_match = BASELINE configs[1] (default, the headline); vo = configs[4] shape: 8 synthetic streams "
-                         "per GPU through the full tracking loop")
-    ap.add_argument("--cpu-sample", type=int, default=48, help="frames of the bounded cpu_baseline sample")
-    ap.add_argument("--e2e-contexts", type=int, default=8,
-                    help="host threads (one ygzb context = one stream each) used by the e2e leg so that the H2D copy "
-                         "of one batch overlaps the kernels of another")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+KF_POLICY = dict(kf_min_frames=5, kf_min_rot=0.03, kf_min_trans=0.03)   # as in tests/test_vo.py: a key-frame every >= 5 frames
 
-    if args.impl == "reference":
-        run_reference(args, rank, world)
+
+def usable_threads():
+    """Host threads this process may really use: the affinity mask capped by a cgroup CPU quota if there is one."""
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:  # noqa: BLE001
+        pass
+    capped = usable if quota is None else max(1, min(usable, int(np.ceil(quota))))
+    return capped, usable, quota
+
+
+def vo_config(streams: int, frames_per_step: int) -> dict:
+    """Identical for the GPU arm and the reference arm (the driver compares the two dicts)."""
+    return {"workload": "C5: full VO tracking loop on independent synthetic 640x480 u8 streams, 3-level pyramid (reference default): "
+                        "sparse image alignment -> direct projection of the local map (8x8 patch alignment) -> pose-only refinement "
+                        "-> key-frame decision; key-frames: grid FAST-10 + ORB detect, depth-initialised map points, local BA (g2o "
+                        "Levenberg + Schur, 3 local key-frames, 20 iterations)",
+            "streams_per_gpu": streams, "frames_per_step_per_stream": frames_per_step,
+            "keyframe_policy": "NeedNewKeyFrame: >= %d frames since the last key-frame and rotation > %.2f rad or translation > %.2f m"
+                               % (KF_POLICY["kf_min_frames"], KF_POLICY["kf_min_rot"], KF_POLICY["kf_min_trans"]),
+            "l2_policy": "every step consumes %d new frames per GPU (%.1f MB of pixels, never re-read); the resident leg keeps all "
+                         "(warmup + steps) x that many frames in HBM, larger than the 126 MB L2 for the default steps"
+                         % (streams * frames_per_step, streams * frames_per_step * FRAME_BYTES / 1e6)}
+
+
+def vo_streams(first_stream: int, count: int, n_frames: int):
+    from ygz_slam_b200 import synth
+    return [synth.shift_stream(first_stream + s, n_frames) for s in range(count)]
+
+
+def vo_cpu(ora, data, threads: int, warm: int):
+    """oracle/vo_cpu.cpp over the given streams; returns (frames/s, seconds, stats, per-stage seconds)."""
+    from oracle import pyoracle
+    n = len(data[0][0])
+    _, stats, sec, stage = pyoracle.vo_run(ora, [d[0] for d in data], [d[1] for d in data], KF_POLICY["kf_min_frames"],
+                                           KF_POLICY["kf_min_rot"], KF_POLICY["kf_min_trans"], warm=warm, threads=threads)
+    return len(data) * (n - warm) / sec, sec, stats, stage
+
+
+def run_reference_vo(args, rank: int, world: int) -> None:
+    """--impl reference on the VO workload: the C++ loop on the CPU oracle, ONE INDEPENDENT STREAM PER USABLE HOST THREAD (the
+    reference tracks one sequence on one thread, so streams are the only parallelism it offers).  The job of the GPU arm has
+    8 x n_gpus streams; a host with more threads than that is given more streams (copies of the same pixels, tracked
+    independently) so that every thread it can use is busy -- `value` is the box's CPU throughput on this workload.  The
+    same-size job (8 x n_gpus streams, one thread each) is reported in cpu_baseline.same_job.  A step = one key-frame cycle
+    (5 frames) of every stream: a bounded sample of the GPU arm's 10-frame step."""
+    if rank != 0:
         return
+    from oracle.pyoracle import Oracle
+    ora = Oracle(native=True)
+    threads, affinity, quota = usable_threads()
+    S, F = args.streams, args.frames_per_step
+    Fs = KF_POLICY["kf_min_frames"]                 # frames per stream of one reference-arm step
+    n = (args.warmup + args.steps) * Fs
+    warm = args.warmup * Fs
+    job_streams = S * max(1, args.gpus)
+    base = vo_streams(0, min(job_streams, 8), n)    # pixels of at most 8 distinct streams, shared by the copies
+    sat = [base[t % len(base)] for t in range(max(threads, 1))]
+    fps, sec, stats, stage = vo_cpu(ora, sat, threads, warm)
+    job = [base[t % len(base)] for t in range(job_streams)]
+    fps_job, sec_job, _, _ = vo_cpu(ora, job, min(threads, job_streams), warm)
+    fps1, sec1, _, stage1 = vo_cpu(ora, base[:1], 1, warm)
+    tot = sum(stage.values()) or 1.0
+    line = {
+        "impl": "reference", "metric": "tracked frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32+f64", "data": "synthetic",
+        "config": vo_config(S, F),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{len(sat)} independent streams (one per usable host thread) x {Fs} frames per step x {args.steps} steps "
+                                   f"after {args.warmup} warm-up steps; C++ loop on the CPU restatement of the reference (oracle/vo_cpu.cpp, "
+                                   f"-O3 AVX2/FMA; the reference itself cannot be built here)",
+                         "same_job": {"streams": job_streams, "threads": min(threads, job_streams), "frames_per_s": fps_job},
+                         "one_thread_frames_per_s": fps1,
+                         "stage_share": {k: v / tot for k, v in stage.items()},
+                         "logical_cpus": os.cpu_count(), "affinity_cpus": affinity, "cgroup_cpu_quota": quota,
+                         "streams_lost": int(sum(s["lost"] for s in stats))},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
 
+
+def vo_gpu_leg(ctx, stacked, depths, threads, warm, device_ptr=None):
+    from ygz_slam_b200 import vo_native
+    S, n = stacked.shape[:2]
+    kw = dict(warm=warm, threads=threads, details=True)
+    if device_ptr is not None:
+        return vo_native.run(ctx, None, depths, KF_POLICY["kf_min_frames"], KF_POLICY["kf_min_rot"], KF_POLICY["kf_min_trans"],
+                             device_frames=(device_ptr, S, n), **kw)
+    return vo_native.run(ctx, stacked, depths, KF_POLICY["kf_min_frames"], KF_POLICY["kf_min_rot"], KF_POLICY["kf_min_trans"], **kw)
+
+
+def vo_line(args, rank, world, local_rank):
+    """The default workload: C5.  Returns the JSON line dict on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from ygz_slam_b200 import Context, se3, vo_native
+
+    S, F = args.streams, args.frames_per_step
+    n = (args.warmup + args.steps) * F
+    warm = args.warmup * F
+    timed = n - warm
+    data = vo_streams(S * rank, S, n)
+    stacked = vo_native.stack_pinned([d[0] for d in data])
+    depths = [d[1] for d in data]
+    threads = max(1, min(args.vo_threads, S))
+    ctx = Context(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def check(traj, stats):
+        lost = sum(s["lost"] for s in stats)
+        errs = [float(np.linalg.norm(se3.se3_log(se3.mul(traj[s, -1], se3.inv(data[s][2][-1]))))) for s in range(S)]
+        return lost, max(errs)
+
+    # ---- resident leg (value): all frames in HBM before the timed region; device-timed --------------------------------
+    dev = torch.empty((S, n, H, W), dtype=torch.uint8, device="cuda")
+    dev.copy_(torch.from_numpy(stacked), non_blocking=True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    traj_r, stats_r, sec_r, det_r = vo_gpu_leg(ctx, stacked, depths, threads, warm, device_ptr=dev.data_ptr())
+    barrier()
+    # ---- e2e leg: host frames through the C ABI, H2D + D2H inside the timed region ------------------------------------
+    traj_e, stats_e, sec_e, det_e = vo_gpu_leg(ctx, stacked, depths, threads, warm)
+    barrier()
+    clocks = sampler.stop()
+    del dev
+    lost, err = check(traj_e, stats_e)
+    ms_resident, ms_e2e = det_r["device_ms"], sec_e * 1e3
+
+    # ---- per-kernel shares: a short profiled pass on one context (CUDA events around every launch) --------------------
+    n_prof = min(n, warm + 2 * F)
+    ctx.profile(True)
+    _, stats_p, _, _ = vo_gpu_leg(ctx, stacked[:, :n_prof], depths, 1, 0)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+
+    sharded = None
+    if world > 1 and S % world == 0:
+        # BASELINE's sentence "8 streams sharded across the GPUs": the same 8 streams of the whole job, 8 / N per GPU
+        Ss = S // world
+        sh_data = vo_streams(Ss * rank, Ss, n)
+        sh_stacked = vo_native.stack_pinned([d[0] for d in sh_data])
+        barrier()
+        _, st_s, sec_s, det_s = vo_gpu_leg(ctx, sh_stacked, [d[1] for d in sh_data], max(1, min(threads, Ss)), warm)
+        barrier()
+        t = torch.tensor([sec_s * 1e3, float(sum(s["lost"] for s in st_s))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sharded = {"streams_total": S, "streams_per_gpu": Ss, "tracked_frames_per_s_e2e": S * timed / (float(t[0]) * 1e-3),
+                   "ms_per_step": float(t[0]) / args.steps, "streams_lost_max": int(t[1]), "scaling": "strong"}
+
+    per_rank = None
+    if world > 1:
+        from ygz_slam_b200 import dist as ydist
+        rec = ydist.make_record(rank, S * timed, sum(s["inliers"] for s in stats_e), lost, [0, 0, 0, 1, 0, 0, 0], ms_resident)
+        table, _, _ = ydist.gather_records([rec], world, device=torch.device("cuda", local_rank))
+        per_rank = [{"rank": int(r[0]), "frames": int(r[1]), "device_ms": float(r[11])} for r in table]
+        t = torch.tensor([ms_resident, ms_e2e, float(lost), err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_resident, ms_e2e, lost, err = t.tolist()
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = world * S * timed / (ms_resident * 1e-3)
+        e2e = world * S * timed / (ms_e2e * 1e-3)
+        total_ms = sum(v[0] for v in prof.values()) or 1.0
+        shares = {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1], "share": v[0] / total_ms} for k, v in prof.items() if v[1]}
+        dom = max(shares, key=lambda k: shares[k]["share"]) if shares else None
+        # algorithmic (minimum unique HBM) bytes of the stages of the profiled pass -- DESIGN.md section 4 / SURVEY 8d
+        agg = {k: sum(s[k] for s in stats_p) for k in stats_p[0]}
+        prof_frames = S * n_prof
+        slot3 = sum(((W + (1 << L) - 1) >> L) * ((H + (1 << L) - 1) >> L) for L in range(3))   # 3-level pyramid bytes
+        alg = {
+            "local_ba": 24.0 * agg["ba_obs"] + 48.0 * agg["ba_pts"] + 96.0 * agg["ba_kfs"],          # obs in, landmarks in+out, poses in+out
+            "sparse_align": (prof_frames - S) * (2.0 * slot3) + 25.0 * (agg["candidates"] / 3.0),     # ref + cur pyramid once, ref features
+            "project_align": 25.0 * agg["candidates"] + agg["candidates"] * (100 + 81.0),            # candidate record + the two patches' pixels
+            "pose_only": 40.0 * agg["projected"],
+            "pyrdown": prof_frames * float(slot3), "fast_cells": agg["keyframes"] * float(slot3),
+            "describe": agg["keyframes"] * 1244 * (961 + 32.0),
+        }
+        roof = []
+        for k, sh in sorted(shares.items(), key=lambda kv: -kv[1]["share"]):
+            if not alg.get(k):
+                continue
+            dur = sh["ms_per_launch"] * sh["launches"] * 1e-3
+            ach = alg[k] / dur / 1e9
+            roof.append({"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "share_of_step": sh["share"], "us_per_launch": sh["ms_per_launch"] * 1e3, "launches_profiled": sh["launches"],
+                         "algorithmic_bytes_per_launch": alg[k] / sh["launches"]})
+        main_roof = next((dict(r) for r in roof if r["kernel"] == dom), dict(roof[0]) if roof else None)
+        if main_roof is not None:
+            main_roof["peak_source"] = peak_src
+            try:
+                tr = json.loads((ROOT / "profiles" / "r2_dram_traffic.json").read_text()).get(main_roof["kernel"], {})
+                if tr.get("dram_bytes_per_launch"):
+                    main_roof["traffic"] = tr["dram_bytes_per_launch"]
+                    main_roof["traffic_source"] = tr.get("source")
+            except Exception:  # noqa: BLE001
+                pass
+            if main_roof["kernel"] == "local_ba" and "local_ba" in shares:
+                dur = shares["local_ba"]["ms_per_launch"] * shares["local_ba"]["launches"] * 1e-3
+                main_roof["fp64"] = {
+                    "achieved_gflops": agg["ba_flops"] / dur / 1e9, "nominal_peak_gflops": 40000.0,
+                    "frac_of_nominal": agg["ba_flops"] / dur / 1e9 / 40000.0,
+                    "ms_per_lm_trial_per_launch": shares["local_ba"]["ms_per_launch"] / max(agg["ba_trials"] / max(agg["ba"], 1), 1),
+                    "note": "FLOP model of SURVEY 8d (per LM trial 300 n_obs + sum_j(216 k_j^2 + 108 k_j + 50) + dim^3/3); the BA reduce is FP64 "
+                            "ALU / latency bound, not HBM bound -- no FP64 peak is in MEASURED_PEAKS.json, 40 TFLOP/s is the nominal B200 figure"}
+
+        cpu = None
+        extra = None
+        if world == 1:
+            try:
+                from oracle.pyoracle import Oracle
+                ora = Oracle(native=True)
+                thr, affinity, quota = usable_threads()
+                ncpu = min(n, 3 + 30)
+                sample = [(d[0][:ncpu], d[1], d[2][:ncpu]) for d in data]
+                fps1, sec1, st1, stage1 = vo_cpu(ora, sample[:2], 1, 3)
+                fpsS, secS, _, _ = vo_cpu(ora, sample, min(thr, S), 3)
+                tot = sum(stage1.values()) or 1.0
+                cpu = {"value": fps1, "unit": "frames/s", "cores": 1, "kind": "port",
+                       "sample": f"frames 3..{ncpu - 1} of 2 of the {S} streams through the same loop in C++ on the CPU oracle (oracle/vo_cpu.cpp, "
+                                 f"-O3 AVX2/FMA), single thread like the reference's own code ({sec1:.1f} s of CPU work)",
+                       "one_thread_per_stream": {"threads": min(thr, S), "streams": S, "frames_per_s": fpsS, "seconds": secS},
+                       "stage_share_1_thread": {k: v / tot for k, v in stage1.items()},
+                       "logical_cpus": os.cpu_count(), "affinity_cpus": affinity, "cgroup_cpu_quota": quota}
+            except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
+                cpu = {"error": repr(e)}
+            if not args.no_secondary:
+                try:
+                    extra = secondary_workloads(ctx)
+                except Exception as e:  # noqa: BLE001
+                    extra = {"error": repr(e)}
+        line = {
+            "metric": "tracked frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8+f32+f64", "data": "synthetic",
+            "config": vo_config(S, F),
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": (det_e["h2d_image_bytes"] + det_e["h2d_other_bytes"]) / args.steps,
+                    "d2h_bytes_per_step": det_e["d2h_bytes"] / args.steps, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_image_bytes_per_step": det_e["h2d_image_bytes"] / args.steps,
+                    "timing": "wall clock between device synchronisations (host bookkeeping and several CUDA streams are part of the step)"},
+            "gpu_launches": int(det_r["gpu_launches"]),
+            "clocks": clocks,
+            "roofline": main_roof, "roofline_kernels": roof, "kernel_shares": shares,
+            "cpu_baseline": cpu,
+            "engine": {"host_threads_per_gpu": threads, "note": "host loop in C++ (ygz_slam_b200/host/vo_driver.cpp), one ygzb context (CUDA "
+                       "stream) per host thread; resident leg wall ms %.2f vs device ms %.2f" % (sec_r * 1e3, det_r["device_ms"])},
+            "tracking": {"streams_lost": int(lost), "final_pose_error_vs_gt_max": err,
+                         "keyframes": int(sum(s["keyframes"] for s in stats_e)), "local_bas": int(sum(s["ba"] for s in stats_e)),
+                         "candidates_per_frame": sum(s["candidates"] for s in stats_e) / (S * n),
+                         "inliers_per_frame": sum(s["inliers"] for s in stats_e) / (S * n)},
+            "sharded_8_streams": sharded,
+            "secondary_workloads": extra,
+            "per_rank": per_rank,
+        }
+    ctx.close()
+    return line
+
+def extract_match_line(args, rank, world, local_rank, with_secondary=True):
+    """BASELINE configs[1] (C2): FAST+ORB extract + brute-force Hamming match over a batch of frames (the round-1 headline,
+    now `--workload extract_match` and a secondary record of the default run).  Returns the JSON line dict on rank 0."""
     import torch
     import torch.distributed as dist
     from ygz_slam_b200 import Context
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    if args.workload == "vo":
-        ctx = Context(local_rank)
-        best = None
-        for _ in range(max(1, args.steps // 5)):
-            r = run_vo(ctx, 8, 40, stream_offset=8 * rank)
-            best = r if best is None or r["tracked_frames_per_s"] > best["tracked_frames_per_s"] else best
-        t = torch.tensor([best["ms_per_lockstep_frame"], float(best["streams_lost"]), best["final_pose_error_vs_gt_max"]],
-                         device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            ms = float(t[0])
-            print(json.dumps({
-                "metric": "tracked frames/sec", "value": world * 8 * 1e3 / ms, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8+f32+f64", "data": "synthetic",
-                "config": {"workload": "C5 shape: full tracking loop (sparse align, direct projection, pose-only, keyframes: detect + local BA), "
-                                       "8 independent 640x480 streams per GPU in lock step, 3-level pyramid", "streams_per_gpu": 8,
-                           "frames_per_stream": 40},
-                "e2e": {"value": world * 8 * 1e3 / ms, "unit": "frames/s", "h2d_bytes_per_step": 8 * FRAME_BYTES, "d2h_bytes_per_step": None},
-                "streams_lost_max": int(t[1]), "final_pose_error_vs_gt_max": float(t[2]), "detail": best}))
-        ctx.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
+    line = None
     B = args.batch
     ctx = Context(local_rank, n_levels=LEVELS)
     fr = ctx.frames(B)
@@ -686,7 +828,7 @@ def main() -> None:
                              f"build, single thread like the reference's own code; host has {os.cpu_count()} logical CPUs"}
 
         extra = None
-        if world == 1:
+        if world == 1 and with_secondary:
             try:
                 extra = secondary_workloads(ctx)
             except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
@@ -710,12 +852,79 @@ def main() -> None:
             "secondary_workloads": extra,
             "per_rank": per_rank,
         }
-        print(json.dumps(line))
     for c_, f_, _ in workers[1:]:
         f_.close()
         c_.close()
     fr.close()
     ctx.close()
+    return line if rank == 0 else None
+
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="vo", choices=["vo", "extract_match"],
+                    help="vo = BASELINE metric (tracked frames/sec, configs[4] C5: 8 streams per GPU through the full tracking loop; "
+                         "the headline); extract_match = configs[1] C2 (FAST+ORB extract + BF match)")
+    ap.add_argument("--streams", type=int, default=8, help="vo: independent streams per GPU")
+    ap.add_argument("--frames-per-step", type=int, default=10, help="vo: frames per stream and step")
+    ap.add_argument("--vo-threads", type=int, default=2, help="vo: host threads (= ygzb contexts = CUDA streams) per GPU")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (C2, C3, C4) of the N=1 run")
+    ap.add_argument("--batch", type=int, default=512, help="extract_match: frames per step per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="extract_match: frames of the bounded cpu_baseline sample")
+    ap.add_argument("--e2e-contexts", type=int, default=8,
+                    help="extract_match: host threads (one ygzb context = one stream each) used by the e2e leg so that the H2D "
+                         "copy of one batch overlaps the kernels of another")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if args.workload == "vo":
+            run_reference_vo(args, rank, world)
+        else:
+            run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload == "vo":
+        line = vo_line(args, rank, world, local_rank)
+        if rank == 0 and world == 1 and not args.no_secondary:
+            # BASELINE configs[1] (C2) as a secondary record: a short run of the round-1 headline
+            try:
+                a2 = argparse.Namespace(**vars(args))
+                a2.steps, a2.warmup = 5, 3
+                c2 = extract_match_line(a2, rank, world, local_rank, with_secondary=False)
+                keep = ("value", "unit", "ms_per_step", "e2e", "roofline", "cpu_baseline", "keypoints_per_frame", "config", "gpu_launches")
+                line.setdefault("secondary_workloads", {})
+                if not isinstance(line["secondary_workloads"], dict):
+                    line["secondary_workloads"] = {"note": line["secondary_workloads"]}
+                line["secondary_workloads"]["c2_extract_match_512_frames"] = {k: c2[k] for k in keep if k in c2}
+            except Exception as e:  # noqa: BLE001
+                line.setdefault("secondary_workloads", {})
+                if isinstance(line["secondary_workloads"], dict):
+                    line["secondary_workloads"]["c2_error"] = repr(e)
+    else:
+        line = extract_match_line(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -57,6 +57,10 @@ const char* ygzb_last_error(const ygzb_ctx* ctx);
 int ygzb_synchronize(ygzb_ctx* ctx);
 /* the context's cudaStream_t, for callers that time or order work themselves */
 void* ygzb_stream(ygzb_ctx* ctx);
+/* device time between two points of the context's stream (CUDA events): start records an event, stop records a second
+ * one, waits for it and returns the elapsed milliseconds -- what bench.py reports as the device-timed step */
+int ygzb_timer_start(ygzb_ctx* ctx);
+int ygzb_timer_stop(ygzb_ctx* ctx, double* ms);
 /* number of kernels this library launched on the context since creation (bench.py: gpu_launches) */
 long long ygzb_launch_count(const ygzb_ctx* ctx);
 
@@ -77,7 +81,8 @@ int ygzb_host_free(void* ptr);
 int ygzb_frames_create(ygzb_ctx* ctx, int capacity, ygzb_frames** out);
 void ygzb_frames_destroy(ygzb_frames* f);
 /* host -> device copy of `count` images into slots [first, first+count) and pyramid build.
- * channels 1 (grey) or 3 (BGR); frame_stride = bytes between consecutive host images.          */
+ * channels 1 (grey) or 3 (BGR); frame_stride = bytes between consecutive host images.  `host` may also be a
+ * device pointer (frames that are already resident in HBM): the copy uses unified addressing.  */
 int ygzb_frames_upload(ygzb_frames* f, int first, int count, const uint8_t* host, int channels,
                        size_t frame_stride);
 /* device-to-device copy of the whole pyramid of one slot into another (asynchronous on the context stream): lets a

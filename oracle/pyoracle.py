@@ -316,3 +316,30 @@ class Oracle:
         self.lib.ora_klt(_p(np.ascontiguousarray(ref)), _p(np.ascontiguousarray(cur)), w, h, n,
                          _p(np.ascontiguousarray(ref_xy, np.float32)), _p(out), _p(status), _p(err), C.byref(prm))
         return out, status, err
+
+
+def vo_run(oracle: "Oracle", frames, depths, kf_min_frames=10, kf_min_rot=0.1, kf_min_trans=0.1, warm=0, threads=1):
+    """The C5 tracking loop on the CPU oracle in C++ (oracle/vo_cpu.cpp), one stream per host thread.
+    frames[s]: (n_frames, 480, 640) uint8, depths[s]: (480, 640) float64.
+    Returns (trajectory (S, n, 3, 4), stats list of dicts, seconds of frames [warm, n), per-stage seconds dict)."""
+    S, n = len(frames), len(frames[0])
+    imgs = [np.ascontiguousarray(f, np.uint8) for f in frames]
+    deps = [np.ascontiguousarray(d, np.float64) for d in depths]
+    ip = (C.c_void_p * S)(*[a.ctypes.data for a in imgs])
+    dp = (C.c_void_p * S)(*[a.ctypes.data for a in deps])
+    traj = np.zeros((S, n, 12), np.float64)
+    stats = np.zeros((S, 8), np.int64)
+    stage = np.zeros(7, np.float64)
+    sec = C.c_double(0.0)
+    fn = oracle.lib.ora_vo_run
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
+                   C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = fn(S, n, C.cast(ip, C.c_void_p), C.cast(dp, C.c_void_p), kf_min_frames, kf_min_rot, kf_min_trans, warm, threads,
+            traj.ctypes.data, stats.ctypes.data, C.byref(sec), stage.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"ora_vo_run rc={rc}")
+    keys = ("lost", "keyframes", "ba", "candidates", "projected", "inliers")
+    names = ("pyramid", "sparse_align", "project_align", "pose_only", "detect", "local_ba", "host")
+    return (traj.reshape(S, n, 3, 4), [dict(zip(keys, map(int, row[:6]))) for row in stats], sec.value,
+            dict(zip(names, map(float, stage))))

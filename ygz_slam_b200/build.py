@@ -39,7 +39,9 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + [HERE.parent / "include" / "ygz_b200.h"]
+    # build.py itself is a dependency: a change of the compiler flags must rebuild the library
+    deps = (list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + [HERE.parent / "include" / "ygz_b200.h"]
+            + [Path(__file__).resolve()])
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -114,6 +114,8 @@ int build_geometry(ygzb_ctx* ctx) {
     if (p.image_width < 16 || p.image_height < 16 || p.image_width > 8192 || p.image_height > 8192)
         return set_error(ctx, YGZB_ERR_INVALID, "unsupported image size");
     if (p.cell_size < 1) return set_error(ctx, YGZB_ERR_INVALID, "cell_size must be positive");
+    // the FAST kernel keeps scores in u8 with 0 = "not a corner" and builds SWAR constants from 127 - threshold
+    if (p.fast_threshold < 1 || p.fast_threshold > 254) return set_error(ctx, YGZB_ERR_INVALID, "fast_threshold must be in [1, 254]");
     g.n_levels = p.n_levels;
     g.W = p.image_width;
     g.H = p.image_height;
@@ -237,6 +239,8 @@ void ygzb_destroy(ygzb_ctx* ctx) {
         }
         delete v;
     }
+    for (cudaEvent_t e : ctx->timer)
+        if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -287,6 +291,28 @@ const char* ygzb_profile_stage_name(int i) {
 }
 
 void* ygzb_stream(ygzb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ygzb_timer_start(ygzb_ctx* ctx) {
+    if (!ctx) return YGZB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!ctx->timer[0]) {
+        YGZB_CUDA(ctx, cudaEventCreate(&ctx->timer[0]));
+        YGZB_CUDA(ctx, cudaEventCreate(&ctx->timer[1]));
+    }
+    YGZB_CUDA(ctx, cudaEventRecord(ctx->timer[0], ctx->stream));
+    return YGZB_OK;
+}
+
+int ygzb_timer_stop(ygzb_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->timer[0]) return YGZB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    YGZB_CUDA(ctx, cudaEventRecord(ctx->timer[1], ctx->stream));
+    YGZB_CUDA(ctx, cudaEventSynchronize(ctx->timer[1]));
+    float t = 0.f;
+    YGZB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->timer[0], ctx->timer[1]));
+    *ms = t;
+    return YGZB_OK;
+}
 long long ygzb_launch_count(const ygzb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int ygzb_host_alloc(void** ptr, size_t bytes) {
@@ -393,23 +419,33 @@ int ygzb_frames_upload(ygzb_frames* f, int first, int count, const uint8_t* host
     if (channels != 1 && channels != 3) return set_error(ctx, YGZB_ERR_INVALID, "channels must be 1 or 3");
     if (frame_stride < row * g.lv[0].h) return set_error(ctx, YGZB_ERR_INVALID, "frame_stride smaller than one image");
     if (count == 0) return YGZB_OK;
+    // cudaMemcpyDefault: `host` may also be a device pointer (frames already resident in HBM, unified addressing).
+    // A strided batch copy treats one image as a "row", so its pitch is limited (cudaDeviceProp::memPitch, 2^31 - 1):
+    // longer strides (a stacked [stream][frame] array of thousands of frames) fall back to one copy per image.
+    const bool one_copy = frame_stride <= (size_t)0x7FFFFFFF;
     if (channels == 1) {
         uint8_t* dst = f->d_pyr + (size_t)first * ctx->slot_stride + g.lv[0].off;
-        if (g.lv[0].pitch == g.lv[0].w) {
+        if (g.lv[0].pitch == g.lv[0].w && one_copy) {
             // level 0 of a slot is one contiguous run: a single strided copy moves the whole batch
-            YGZB_CUDA(ctx, cudaMemcpy2DAsync(dst, ctx->slot_stride, host, frame_stride, row * g.lv[0].h, count,
-                                             cudaMemcpyHostToDevice, ctx->stream));
+            YGZB_CUDA(ctx, cudaMemcpy2DAsync(dst, ctx->slot_stride, host, frame_stride, row * g.lv[0].h, count, cudaMemcpyDefault,
+                                             ctx->stream));
         } else {
             for (int i = 0; i < count; ++i)
                 YGZB_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)i * ctx->slot_stride, g.lv[0].pitch, host + (size_t)i * frame_stride,
-                                                 row, row, g.lv[0].h, cudaMemcpyHostToDevice, ctx->stream));
+                                                 row, row, g.lv[0].h, cudaMemcpyDefault, ctx->stream));
         }
         return launch_pyramid(f, first, count, nullptr);
     }
     uint8_t* d_bgr = (uint8_t*)dev_scratch(ctx, 0, (size_t)count * row * g.lv[0].h);
     if (!d_bgr) return YGZB_ERR_CUDA;
-    YGZB_CUDA(ctx, cudaMemcpy2DAsync(d_bgr, row * g.lv[0].h, host, frame_stride, row * g.lv[0].h, count, cudaMemcpyHostToDevice,
-                                     ctx->stream));
+    if (one_copy) {
+        YGZB_CUDA(ctx, cudaMemcpy2DAsync(d_bgr, row * g.lv[0].h, host, frame_stride, row * g.lv[0].h, count, cudaMemcpyDefault,
+                                         ctx->stream));
+    } else {
+        for (int i = 0; i < count; ++i)
+            YGZB_CUDA(ctx, cudaMemcpyAsync(d_bgr + (size_t)i * row * g.lv[0].h, host + (size_t)i * frame_stride, row * g.lv[0].h,
+                                           cudaMemcpyDefault, ctx->stream));
+    }
     return launch_pyramid(f, first, count, d_bgr);
 }
 
@@ -506,6 +542,9 @@ int ygzb_describe(ygzb_frames* f, const int32_t* slots, int n, const int32_t* of
     ygzb_ctx* ctx = f->ctx;
     cudaSetDevice(ctx->device);
     int rc = upload_slots(f, slots, n);
+    if (rc != YGZB_OK) return rc;
+    if (n < 0) return YGZB_ERR_INVALID;
+    rc = check_offsets(ctx, offsets, n, "offsets");
     if (rc != YGZB_OK) return rc;
     const int total = offsets[n];
     if (total <= 0) return YGZB_OK;

@@ -173,6 +173,7 @@ int ygzb_sparse_align(ygzb_frames* f, int n_problems, const int32_t* ref_slot, c
     TRY(check_slots(f, cur_slot, n_problems, "cur_slot"));
     if (max_level >= ctx->geo.n_levels || min_level < 0 || min_level > max_level)
         return set_error(ctx, YGZB_ERR_INVALID, "levels [%d, %d] outside the %d-level pyramid", min_level, max_level, ctx->geo.n_levels);
+    TRY(check_offsets(ctx, offsets, n_problems, "offsets"));
     const size_t P = (size_t)n_problems, T = (size_t)offsets[n_problems];
     if (T && (!px || !depth || !has_mappoint)) return YGZB_ERR_INVALID;
     Carver sz(nullptr);

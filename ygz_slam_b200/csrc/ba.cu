@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -1267,6 +1268,10 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
                  double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
                  const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, std::vector<double>& hst) {
     cudaSetDevice(ctx->device);
+    for (const auto& oc : {std::make_pair(kf_off, "kf_off"), std::make_pair(pt_off, "pt_off"), std::make_pair(obs_off, "obs_off")}) {
+        const int rc = check_offsets(ctx, oc.first, n_problems, oc.second);
+        if (rc != YGZB_OK) return rc;
+    }
     const size_t P = (size_t)n_problems, NK = (size_t)kf_off[n_problems], NP = (size_t)pt_off[n_problems], NO = (size_t)obs_off[n_problems];
     // ---- structure: observations grouped by landmark, by pose, and landmark-sharing observation pairs per block pair
     std::vector<int32_t> lm_start(NP + 1, 0), lm_obs(NO), ps_start(NK + 1, 0), ps_obs(NO), pair_off(P + 1, 0), pair_start, pair_o1, pair_o2;
@@ -1472,7 +1477,11 @@ int ygzb_local_ba(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
         !prm || !outlier)
         return YGZB_ERR_INVALID;
     std::vector<double> hst;
-    TRY(run_local_ba(ctx, false, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, prm, outlier, hst));
+    try {   // the header promises that calls never throw: allocation failures of the host-side bookkeeping become an error code
+        TRY(run_local_ba(ctx, false, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, prm, outlier, hst));
+    } catch (const std::exception& e) {
+        return set_error(ctx, YGZB_ERR_INVALID, "ygzb_local_ba: %s", e.what());
+    }
     if (stats)
         for (size_t p = 0; p < (size_t)n_problems; ++p) {
             stats[p].iters = (int)hst[8 * p];
@@ -1496,7 +1505,11 @@ int ygzb_local_ba_ceres(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, co
     prm.max_iters = max_iters;   // ceres::Solver::Options::max_num_iterations (50 by default)
     prm.huber_delta = huber_a;   // 0: no loss function (nullptr in AddResidualBlock, BA.cpp:346,364); 0.1: BA.cpp:108-135
     std::vector<double> hst;
-    TRY(run_local_ba(ctx, true, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, &prm, nullptr, hst));
+    try {
+        TRY(run_local_ba(ctx, true, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, &prm, nullptr, hst));
+    } catch (const std::exception& e) {
+        return set_error(ctx, YGZB_ERR_INVALID, "ygzb_local_ba_ceres: %s", e.what());
+    }
     if (stats)
         for (size_t p = 0; p < (size_t)n_problems; ++p) {
             stats[p].iters = (int)hst[8 * p];
@@ -1513,6 +1526,10 @@ int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const 
                    uint8_t* inlier, double* depth, int32_t* n_inlier) {
     if (!ctx || n_problems < 1 || !offsets || !T_cw || !n_inlier) return YGZB_ERR_INVALID;
     cudaSetDevice(ctx->device);
+    {
+        const int rc = check_offsets(ctx, offsets, n_problems, "offsets");
+        if (rc != YGZB_OK) return rc;
+    }
     const size_t P = (size_t)n_problems, N = (size_t)offsets[n_problems];
     if (N && (!pt_world || !px || !inlier || !depth)) return YGZB_ERR_INVALID;
     Carver sz(nullptr);

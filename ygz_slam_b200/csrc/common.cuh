@@ -63,6 +63,7 @@ struct ygzb_ctx {
     // optional per-stage CUDA-event timing (ygzb_profile_*): events bracket each kernel on ctx->stream
     int prof_on;
     void* prof;  // std::vector<ygzb::ProfRec>*
+    cudaEvent_t timer[2];   // ygzb_timer_start / ygzb_timer_stop
 };
 
 struct ygzb_frames {
@@ -97,6 +98,15 @@ namespace ygzb {
 
 int set_error(ygzb_ctx* ctx, int code, const char* fmt, ...);
 int check_cuda(ygzb_ctx* ctx, cudaError_t e, const char* what);
+// offsets arrays of the batched entry points: off[0] == 0, non-decreasing, int-range total (returns YGZB_ERR_INVALID before
+// anything is allocated or indexed)
+inline int check_offsets(ygzb_ctx* ctx, const int32_t* off, int n, const char* what) {
+    if (!off || n < 0) return set_error(ctx, YGZB_ERR_INVALID, "%s: null offsets", what);
+    if (off[0] != 0) return set_error(ctx, YGZB_ERR_INVALID, "%s[0] must be 0", what);
+    for (int i = 0; i < n; ++i)
+        if (off[i + 1] < off[i]) return set_error(ctx, YGZB_ERR_INVALID, "%s must be non-decreasing (entry %d)", what, i + 1);
+    return YGZB_OK;
+}
 // grow-only scratch buffers
 void* dev_scratch(ygzb_ctx* ctx, int which, size_t bytes);
 void* host_scratch(ygzb_ctx* ctx, int which, size_t bytes);

@@ -14,6 +14,7 @@
 // the same integer products in f32; its SIMD and scalar builds already differ in the last bits), reduced with warp
 // shuffles.  Roofline class: L1/L2-resident gather, latency bound (2.6 kB first touch per point and level).
 #include <algorithm>
+#include <exception>
 #include <vector>
 
 #include "common.cuh"
@@ -259,13 +260,29 @@ void ygzb_default_klt_params(ygzb_klt_params* p) {
     p->min_eig = 1e-4;   // cv::calcOpticalFlowPyrLK default minEigThreshold
 }
 
+static int klt_impl(ygzb_frames* f, int n_pairs, const int32_t* ref_slot, const int32_t* cur_slot, const int32_t* offsets,
+                    const float* ref_xy, float* cur_xy, uint8_t* status, float* err, const ygzb_klt_params* prm);
+
 int ygzb_klt(ygzb_frames* f, int n_pairs, const int32_t* ref_slot, const int32_t* cur_slot, const int32_t* offsets,
              const float* ref_xy, float* cur_xy, uint8_t* status, float* err, const ygzb_klt_params* prm) {
+    try {   // never throws (header): host-side bookkeeping failures become an error code
+        return klt_impl(f, n_pairs, ref_slot, cur_slot, offsets, ref_xy, cur_xy, status, err, prm);
+    } catch (const std::exception& e) {
+        return f ? set_error(f->ctx, YGZB_ERR_INVALID, "ygzb_klt: %s", e.what()) : YGZB_ERR_INVALID;
+    }
+}
+
+static int klt_impl(ygzb_frames* f, int n_pairs, const int32_t* ref_slot, const int32_t* cur_slot, const int32_t* offsets,
+                    const float* ref_xy, float* cur_xy, uint8_t* status, float* err, const ygzb_klt_params* prm) {
     if (!f || n_pairs < 1 || !ref_slot || !cur_slot || !offsets || !prm) return YGZB_ERR_INVALID;
     ygzb_ctx* ctx = f->ctx;
     const Geometry& g = ctx->geo;
     cudaSetDevice(ctx->device);
     if (prm->win != kWin) return set_error(ctx, YGZB_ERR_INVALID, "only the reference's 21x21 window is supported (got %d)", prm->win);
+    {
+        const int rc = check_offsets(ctx, offsets, n_pairs, "offsets");
+        if (rc != YGZB_OK) return rc;
+    }
     const int total = offsets[n_pairs];
     if (total <= 0) return YGZB_OK;
     if (!ref_xy || !cur_xy || !status || !err) return YGZB_ERR_INVALID;

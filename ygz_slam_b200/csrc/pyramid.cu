@@ -192,7 +192,9 @@ constexpr int kTailBytes = 5120;   // 80 x 60 at 640 x 480: larger sources go th
 __global__ void __launch_bounds__(256) pyrdown_tail_kernel(uint8_t* __restrict__ pyr, size_t slot_stride, int first_slot, Geometry g,
                                                            int first) {
     __shared__ uint8_t s_a[kTailBytes];
-    __shared__ uint8_t s_b[kTailBytes / 4 + 64];
+    // next level of a w x h source (w * h <= kTailBytes): ((w+1)/2) * ((h+1)/2) <= (w*h + w + h + 1) / 4 <= kTailBytes / 2 + 1
+    // (elongated levels such as 341 x 15 -> 171 x 8 = 1368 pixels exceed a quarter of the source)
+    __shared__ uint8_t s_b[kTailBytes / 2 + 64];
     uint8_t* slot = pyr + (size_t)(first_slot + blockIdx.x) * slot_stride;
     const int tid = threadIdx.x;
     uint8_t* cur = s_a;

@@ -89,6 +89,8 @@ struct Stream {
     std::vector<long> last_id;
     std::vector<double> last_px;
     long n_keyframes = 0, n_ba = 0, n_candidates = 0, n_projected = 0, n_inliers = 0;
+    long ba_obs = 0, ba_pts = 0, ba_kfs = 0, ba_trials = 0, ba_iters = 0;
+    double ba_flops = 0;   // SURVEY 8d model: per LM trial 300 n_obs + sum_j (216 k_j^2 + 108 k_j + 50) + dim^3 / 3
     int first_local() const { return std::max(0, (int)keyframes.size() - kLocalKeyframes); }
 };
 
@@ -132,6 +134,8 @@ class Driver {
         n_cells_ = rows * cols;
     }
     std::vector<Stream>& streams() { return st_; }
+    // bytes this driver hands to / reads back from the C ABI (host buffers), counted from the arrays of every call
+    long long h2d_image_bytes = 0, h2d_other_bytes = 0, d2h_bytes = 0;
 
     // one lock-step frame: images[i] = grey frame of stream i, depth[i] = its (static) ground-truth depth map
     int add_frames(const uint8_t* const* images, const double* const* depth, int frame_id) {
@@ -141,6 +145,7 @@ class Driver {
         bool strided = S_ > 1;
         const ptrdiff_t stride = S_ > 1 ? images[1] - images[0] : 0;
         for (int i = 1; i + 1 < S_ && strided; ++i) strided = images[i + 1] - images[i] == stride;
+        h2d_image_bytes += (long long)S_ * W * H;
         if (strided && stride >= (ptrdiff_t)W * H) {
             TIMED(kTUpload, ygzb_frames_upload(fr_, 0, S_, images[0], 1, (size_t)stride));
         } else {
@@ -192,6 +197,8 @@ class Driver {
         }
         T_cur = T_ref;
         std::vector<uint8_t> has(px.size() / 2, 1);
+        h2d_other_bytes += 8ll * n + 4ll * (n + 1) + 25ll * (long long)has.size() + 192ll * n;
+        d2h_bytes += 100ll * n;
         TIMED(kTSparse, ygzb_sparse_align(fr_, n, ref_slot.data(), cur_slot.data(), offs.data(), px.data(), dep.data(), has.data(), T_ref.data(),
                               T_cur.data(), 2, 0, 30, 1e-6, n_meas.data(), nullptr));
         std::vector<int> alive;
@@ -267,6 +274,8 @@ class Driver {
         job_begin.push_back((int)nc_sz);
         const int nc = (int)nc_sz;
         std::vector<uint8_t> search_level(nc ? nc : 1), ok(nc ? nc : 1);
+        h2d_other_bytes += 57ll * nc + 8ll * (long long)poses.size();
+        d2h_bytes += 18ll * nc;
         if (nc)
             TIMED(kTProject, ygzb_project_align(fr_, nc, c_ref_slot.data(), c_cur_slot.data(), (int)(poses.size() / 12), poses.data(), c_ref_pose.data(),
                                    c_cur_pose.data(), c_ref_px.data(), c_ref_depth.data(), c_level.data(), c_cur_px.data(),
@@ -298,6 +307,8 @@ class Driver {
         const size_t tot = (size_t)po[m];
         std::vector<uint8_t> inl(tot ? tot : 1);
         std::vector<double> dep_out(tot ? tot : 1);
+        h2d_other_bytes += 4ll * (m + 1) + 40ll * (long long)tot + 96ll * m;
+        d2h_bytes += 96ll * m + 9ll * (long long)tot + 4ll * m;
         TIMED(kTPoseOnly, ygzb_pose_only(ctx_, m, po.data(), pw.data(), obs.data(), Tp.data(), inl.data(), dep_out.data(),
                            n_inl.data()));
         std::vector<int> need;
@@ -339,6 +350,8 @@ class Driver {
         kx_.resize(cap); ky_.resize(cap); klevel_.resize(cap); kscore_.resize(cap); kangle_.resize(cap); kdesc_.resize(cap * 32);
         ygzb_keypoints kp{off.data(), kx_.data(), ky_.data(), klevel_.data(), kscore_.data(), kangle_.data(), kdesc_.data(), nullptr, (int)cap};
         TIMED(kTDetect, ygzb_detect(fr_, slots.data(), n, nullptr, &kp));
+        h2d_other_bytes += 4ll * n;
+        d2h_bytes += 4ll * (n + 1) + 49ll * off[n];
         std::vector<int> ba_jobs;
         for (int j = 0; j < n; ++j) {
             Stream& s = st_[idx[j]];
@@ -453,14 +466,28 @@ class Driver {
         ygzb_ba_params bp;
         ygzb_default_ba_params(&bp);
         std::vector<uint8_t> outl(obs.size() / 2 + 1);
+        std::vector<ygzb_ba_stats> bst(P);
+        h2d_other_bytes += 12ll * (P + 1) + 49ll * (long long)fixed.size() + 24ll * (long long)(pts.size() / 3) + 24ll * (long long)kf_idx.size();
+        d2h_bytes += 48ll * (long long)fixed.size() + 24ll * (long long)(pts.size() / 3) + (long long)kf_idx.size();
         static const double zero3[3] = {0, 0, 0};
         static const int32_t zero_i = 0;
         TIMED(kTLocalBA, ygzb_local_ba(ctx_, P, kf_off.data(), pt_off.data(), ob_off.data(), poses.data(), fixed.data(), pts.empty() ? const_cast<double*>(zero3) : pts.data(),
                           kf_idx.empty() ? &zero_i : kf_idx.data(), pt_idx.empty() ? &zero_i : pt_idx.data(), obs.empty() ? zero3 : obs.data(), &bp,
-                          outl.data(), nullptr));
+                          outl.data(), bst.data()));
         for (int p = 0; p < P; ++p) {
             Stream& s = st_[idx[p]];
             const int k0 = s.first_local(), nk = (int)s.keyframes.size() - k0;
+            {   // problem sizes and the FLOP model of SURVEY 8d (for the roofline of the BA kernel)
+                const int no = ob_off[p + 1] - ob_off[p], npt = pt_off[p + 1] - pt_off[p];
+                std::vector<int> deg(npt, 0);
+                for (int o = ob_off[p]; o < ob_off[p + 1]; ++o) deg[pt_idx[o]]++;
+                double per_trial = 300.0 * no;
+                for (int d : deg) per_trial += 216.0 * d * d + 108.0 * d + 50.0;
+                const double dim = 6.0 * (nk - 1);
+                per_trial += dim * dim * dim / 3.0;
+                s.ba_obs += no; s.ba_pts += npt; s.ba_kfs += nk; s.ba_trials += bst[p].lm_trials; s.ba_iters += bst[p].iters;
+                s.ba_flops += per_trial * bst[p].lm_trials;
+            }
             for (int k = 0; k < nk; ++k) {
                 const double* g = &poses[6 * (size_t)(kf_off[p] + k)];
                 const double v[6] = {g[3], g[4], g[5], g[0], g[1], g[2]};
@@ -496,17 +523,23 @@ extern "C" {
 // the kernels of the others.  The contexts must use the 3-level pyramid of the reference default.
 //   images[s] : n_frames * 480 * 640 bytes, depth[s] : 480 * 640 doubles (static ground-truth depth of stream s)
 //   traj      : n_streams * n_frames * 12 doubles out (T_cw after every frame; NaN while a stream has no pose)
-//   stats     : n_streams * 8 out: lost, keyframes, local BAs, candidates, projected, inliers, 0, 0
+//   stats     : n_streams * 16 out: lost, keyframes, local BAs, candidates, projected, inliers, BA observations, BA points,
+//               BA key-frames, BA LM trials, BA iterations, BA model FLOP, 0...
+//   totals    : (may be NULL) 8 out, timed region only, summed over the host threads: kernel launches, image H2D bytes,
+//               other H2D bytes, D2H bytes, 0...
 //   seconds   : wall time of frames [warm, n_frames) including the final device synchronisation (all threads meet at a
 //               barrier before frame `warm` and after the last frame)
+//   device_ms : (may be NULL) the same region timed with CUDA events on the caller's context stream: first event after
+//               the warm-up barrier, second one after every thread has synchronised its stream
 int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threads, int n_streams, int n_frames,
                const uint8_t* const* images, const double* const* depth, int kf_min_frames, double kf_min_rot, double kf_min_trans,
-               int warm, double* traj, int64_t* stats, double* seconds) {
+               int warm, double* traj, int64_t* stats, double* seconds, double* device_ms, int64_t* totals) {
     if (!ctx || !params || n_streams < 1 || n_frames < 1 || !images || !depth || !traj || !stats || !seconds) return YGZB_ERR_INVALID;
     n_threads = std::max(1, std::min(n_threads, n_streams));
     warm = std::max(0, std::min(warm, n_frames - 1));
     for (auto& v : g_stage_ns) v.store(0);
     std::vector<int> rcs(n_threads, YGZB_OK);
+    std::vector<std::vector<long long>> tot(n_threads, std::vector<long long>(4, 0));
     std::barrier sync_point(n_threads);
     std::chrono::steady_clock::time_point t_begin, t_end;
     auto worker = [&](int t) {
@@ -520,11 +553,14 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
         std::vector<const uint8_t*> img(ns);
         for (int k = 0; k < n_frames; ++k) {
             if (k == warm) {
+                tot[t][0] = -ygzb_launch_count(my);
+                drv.h2d_image_bytes = drv.h2d_other_bytes = drv.d2h_bytes = 0;
                 if (rc == YGZB_OK) ygzb_synchronize(my);
                 sync_point.arrive_and_wait();
                 if (t == 0) {
                     t_begin = std::chrono::steady_clock::now();
                     for (auto& v : g_stage_ns) v.store(0);
+                    ygzb_timer_start(ctx);   // device time of the timed region: CUDA events on the caller's context stream
                 }
             }
             if (rc != YGZB_OK) continue;   // keep meeting the barriers
@@ -537,13 +573,20 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
             }
         }
         if (rc == YGZB_OK) ygzb_synchronize(my);
+        tot[t][0] += ygzb_launch_count(my);
+        tot[t][1] = drv.h2d_image_bytes; tot[t][2] = drv.h2d_other_bytes; tot[t][3] = drv.d2h_bytes;
         sync_point.arrive_and_wait();
-        if (t == 0) t_end = std::chrono::steady_clock::now();
+        if (t == 0) {
+            double ms = 0;
+            if (ygzb_timer_stop(ctx, &ms) == YGZB_OK && device_ms) *device_ms = ms;   // every thread has synchronised its stream
+            t_end = std::chrono::steady_clock::now();
+        }
         for (int s = 0; s < ns; ++s) {
             const Stream& st = drv.streams()[s];
-            int64_t* o = stats + 8 * (size_t)(s0 + s);
+            int64_t* o = stats + 16 * (size_t)(s0 + s);
+            for (int c = 0; c < 16; ++c) o[c] = 0;
             o[0] = st.lost; o[1] = st.n_keyframes; o[2] = st.n_ba; o[3] = st.n_candidates; o[4] = st.n_projected; o[5] = st.n_inliers;
-            o[6] = o[7] = 0;
+            o[6] = st.ba_obs; o[7] = st.ba_pts; o[8] = st.ba_kfs; o[9] = st.ba_trials; o[10] = st.ba_iters; o[11] = (int64_t)st.ba_flops;
         }
         if (fr) ygzb_frames_destroy(fr);
         if (t > 0 && my) ygzb_destroy(my);
@@ -554,6 +597,11 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
     worker(0);
     for (auto& th : pool) th.join();
     *seconds = std::chrono::duration<double>(t_end - t_begin).count();
+    if (totals) {
+        for (int c = 0; c < 8; ++c) totals[c] = 0;
+        for (int t = 0; t < n_threads; ++t)
+            for (int c = 0; c < 4; ++c) totals[c] += tot[t][c];
+    }
     if (getenv("YGZ_VO_TIMING")) {
         static const char* names[kTStages] = {"upload", "sparse_align", "project_align", "pose_only", "detect", "local_ba"};
         double sum = 0;
