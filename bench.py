@@ -385,10 +385,10 @@ def run_reference_vo(args, rank: int, world: int) -> None:
     print(json.dumps(line))
 
 
-def vo_gpu_leg(ctx, stacked, depths, threads, warm, device_ptr=None):
+def vo_gpu_leg(ctx, stacked, depths, threads, warm, device_ptr=None, window=8, engine="resident"):
     from ygz_slam_b200 import vo_native
     S, n = stacked.shape[:2]
-    kw = dict(warm=warm, threads=threads, details=True)
+    kw = dict(warm=warm, threads=threads, details=True, window=window, engine=engine)
     if device_ptr is not None:
         return vo_native.run(ctx, None, depths, KF_POLICY["kf_min_frames"], KF_POLICY["kf_min_rot"], KF_POLICY["kf_min_trans"],
                              device_frames=(device_ptr, S, n), **kw)
@@ -428,11 +428,21 @@ def vo_line(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    traj_r, stats_r, sec_r, det_r = vo_gpu_leg(ctx, stacked, depths, threads, warm, device_ptr=dev.data_ptr())
+    traj_r, stats_r, sec_r, det_r = vo_gpu_leg(ctx, stacked, depths, threads, warm, device_ptr=dev.data_ptr(), window=args.vo_window)
     barrier()
     # ---- e2e leg: host frames through the C ABI, H2D + D2H inside the timed region ------------------------------------
-    traj_e, stats_e, sec_e, det_e = vo_gpu_leg(ctx, stacked, depths, threads, warm)
+    traj_e, stats_e, sec_e, det_e = vo_gpu_leg(ctx, stacked, depths, threads, warm, window=args.vo_window)
     barrier()
+    # diagnostics (untimed legs of the same streams): one frame per stream in flight (the latency mode of the engine) and
+    # the per-stage C-ABI path of round 1 (one blocking call per stage and lock-step frame)
+    diag = {}
+    if world == 1 and not args.no_secondary:
+        for name, kw in (("window_1", dict(window=1)), ("per_stage_calls", dict(engine="stages"))):
+            try:
+                _, st_d, sec_d, _ = vo_gpu_leg(ctx, stacked, depths, threads, warm, **kw)
+                diag[name] = {"tracked_frames_per_s_e2e": S * timed / sec_d, "streams_lost": int(sum(s_["lost"] for s_ in st_d))}
+            except Exception as e:  # noqa: BLE001
+                diag[name] = {"error": repr(e)}
     clocks = sampler.stop()
     del dev
     lost, err = check(traj_e, stats_e)
@@ -441,7 +451,7 @@ def vo_line(args, rank, world, local_rank):
     # ---- per-kernel shares: a short profiled pass on one context (CUDA events around every launch) --------------------
     n_prof = min(n, warm + 2 * F)
     ctx.profile(True)
-    _, stats_p, _, _ = vo_gpu_leg(ctx, stacked[:, :n_prof], depths, 1, 0)
+    _, stats_p, _, _ = vo_gpu_leg(ctx, stacked[:, :n_prof], depths, 1, 0, window=args.vo_window)
     prof = ctx.profile_read()
     ctx.profile(False)
 
@@ -452,7 +462,7 @@ def vo_line(args, rank, world, local_rank):
         sh_data = vo_streams(Ss * rank, Ss, n)
         sh_stacked = vo_native.stack_pinned([d[0] for d in sh_data])
         barrier()
-        _, st_s, sec_s, det_s = vo_gpu_leg(ctx, sh_stacked, [d[1] for d in sh_data], max(1, min(threads, Ss)), warm)
+        _, st_s, sec_s, det_s = vo_gpu_leg(ctx, sh_stacked, [d[1] for d in sh_data], max(1, min(threads, Ss)), warm, window=args.vo_window)
         barrier()
         t = torch.tensor([sec_s * 1e3, float(sum(s["lost"] for s in st_s))], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -538,10 +548,15 @@ def vo_line(args, rank, world, local_rank):
             except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
                 cpu = {"error": repr(e)}
             if not args.no_secondary:
+                c8 = None
                 try:
-                    extra = secondary_workloads(ctx)
+                    c8 = Context(local_rank, n_levels=LEVELS)   # C3 runs the 4-level alignment of BASELINE configs[2]
+                    extra = secondary_workloads(c8)
                 except Exception as e:  # noqa: BLE001
                     extra = {"error": repr(e)}
+                finally:
+                    if c8 is not None:
+                        c8.close()
         line = {
             "metric": "tracked frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -555,8 +570,12 @@ def vo_line(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": main_roof, "roofline_kernels": roof, "kernel_shares": shares,
             "cpu_baseline": cpu,
-            "engine": {"host_threads_per_gpu": threads, "note": "host loop in C++ (ygz_slam_b200/host/vo_driver.cpp), one ygzb context (CUDA "
-                       "stream) per host thread; resident leg wall ms %.2f vs device ms %.2f" % (sec_r * 1e3, det_r["device_ms"])},
+            "engine": {"host_threads_per_gpu": threads, "frames_in_flight_per_stream": args.vo_window,
+                       "note": "device-resident engine (ygzb_tracker_*: local map, candidate projection, key-frame insertion, BA assembly on "
+                               "the device), host loop in C++ (ygz_slam_b200/host/vo_driver.cpp), one ygzb context (CUDA stream) per host "
+                               "thread; a round enqueues for every stream the frames up to the first possible key-frame; resident leg wall "
+                               "ms %.2f vs device ms %.2f" % (sec_r * 1e3, det_r["device_ms"]),
+                       "other_modes": diag},
             "tracking": {"streams_lost": int(lost), "final_pose_error_vs_gt_max": err,
                          "keyframes": int(sum(s["keyframes"] for s in stats_e)), "local_bas": int(sum(s["ba"] for s in stats_e)),
                          "candidates_per_frame": sum(s["candidates"] for s in stats_e) / (S * n),
@@ -873,6 +892,7 @@ def main() -> None:
     ap.add_argument("--streams", type=int, default=8, help="vo: independent streams per GPU")
     ap.add_argument("--frames-per-step", type=int, default=10, help="vo: frames per stream and step")
     ap.add_argument("--vo-threads", type=int, default=2, help="vo: host threads (= ygzb contexts = CUDA streams) per GPU")
+    ap.add_argument("--vo-window", type=int, default=8, help="vo: frames of one stream that may be in flight per round (1 = latency mode)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (C2, C3, C4) of the N=1 run")
     ap.add_argument("--batch", type=int, default=512, help="extract_match: frames per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=48, help="extract_match: frames of the bounded cpu_baseline sample")

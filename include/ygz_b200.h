@@ -256,6 +256,73 @@ void ygzb_default_klt_params(ygzb_klt_params* p);
 int ygzb_klt(ygzb_frames* f, int n_pairs, const int32_t* ref_slot, const int32_t* cur_slot, const int32_t* offsets,
              const float* ref_xy, float* cur_xy, uint8_t* status, float* err, const ygzb_klt_params* prm);
 
+
+/* ---- device-resident tracking (VisualOdometry::TrackRefFrame + LocalMapping::TrackLocalMap + SetKeyframe) -----------
+ * The per-stage calls above move every intermediate through host memory.  A tracker keeps the LOCAL MAP of `n_streams`
+ * independent sequences on the device -- per stream a ring of YGZB_TRACK_RING key-frame entries (pose, features, depth,
+ * map points, tracked observations; the reference keeps them in Memory / Frame / MapPoint objects, src/Basic) -- and runs
+ * the whole per-frame chain as ONE asynchronous enqueue:
+ *   Matcher::SparseImageAlignment against the reference key-frame (Matcher.cpp:468-492, VisualOdometry.cpp:281-302)
+ *   -> LocalMapping::FindCandidates (LocalMapping.cpp:47-80: project the map points of the local key-frames, border 20)
+ *   -> Matcher::FindDirectProjection per candidate (LocalMapping.cpp:82-111)
+ *   -> ba::OptimizeCurrentPoseOnly on the projected points (LocalMapping.cpp:126, BA.cpp:188-264)
+ * for a batch of (stream, frame) jobs; one small record per job comes back.  Frames of ONE stream may be batched as
+ * long as none of them can become a key-frame before the last one (a frame is tracked against the reference key-frame,
+ * never against its predecessor: VisualOdometry.cpp:66), which is how a caller keeps several frames per stream in
+ * flight without changing any result.
+ * ygzb_tracker_make_keyframes is VisualOdometry::SetKeyframe (:182-218) for a batch of streams: FeatureDetector::Detect
+ * on the frame, map points from the depth image, insertion into the ring, and ba::LocalBAG2O over the local key-frames
+ * and the points at least two of them observe (LocalMapping::LocalBA, LocalMapping.cpp:149-172) -- problem assembly,
+ * optimisation and write-back all on the device.                                                                    */
+#define YGZB_TRACK_RING 4
+typedef struct ygzb_tracker ygzb_tracker;
+typedef struct {
+    int32_t stream;        /* sequence index                                                              */
+    int32_t cur_slot;      /* frame slot with the current frame's pyramid (ygzb_frames_upload)             */
+    int32_t n_local;       /* local key-frames, oldest first; the last one is the reference key-frame      */
+    int32_t entry[YGZB_TRACK_RING]; /* their ring entries                                                  */
+    int32_t pad;
+} ygzb_track_job;
+typedef struct {
+    double T_cw[12];       /* pose after OptimizeCurrentPoseOnly (after the alignment if that failed)      */
+    int32_t n_meas;        /* SparseImgAlign::run return value                                             */
+    int32_t aligned;       /* Matcher::SparseImageAlignment's bool (motion norm <= 0.2)                    */
+    int32_t n_candidates, n_projected, n_inliers;
+    int32_t pad[3];
+} ygzb_track_result;
+typedef struct {
+    int32_t stream;
+    int32_t frame_slot;    /* slot of the frame that becomes a key-frame                                    */
+    int32_t kf_slot;       /* slot that keeps its pyramid from now on (copied device-to-device)             */
+    int32_t entry;         /* ring entry to (over)write                                                     */
+    int32_t track_job;     /* job index in the LAST ygzb_tracker_track batch whose pose and inlier observations
+                              the key-frame takes over, or -1: first key-frame (identity pose, nothing tracked) */
+    int32_t n_local;       /* local key-frames AFTER the insertion, oldest first (the last one is `entry`)  */
+    int32_t local_entry[YGZB_TRACK_RING];
+    int32_t run_ba;        /* non-zero: LocalBAG2O over the local key-frames                                */
+    int32_t pad;
+    int64_t mp0;           /* id of the first map point the key-frame creates                               */
+} ygzb_keyframe_job;
+typedef struct {
+    int32_t n_features;
+    int32_t ba_points, ba_observations, ba_iters, ba_trials, pad;
+    double chi2_initial, chi2_final;
+    double T_cw[YGZB_TRACK_RING][12];   /* poses of the local key-frames after the BA, order of local_entry  */
+} ygzb_keyframe_result;
+
+/* K = {fx, fy, cx, cy} of the caller (doubles: the reference's callers project with PinholeCamera in double). */
+int ygzb_tracker_create(ygzb_frames* f, int n_streams, int max_jobs, const double K[4], ygzb_tracker** out);
+void ygzb_tracker_destroy(ygzb_tracker* t);
+/* depth image (image_width * image_height doubles, host or device) that initialises the map points of the next key-frame
+ * of `stream` (the reference's drivers read it from the TUM depth frame, test/test_feature_alignment.cpp:72-85)   */
+int ygzb_tracker_set_depth(ygzb_tracker* t, int stream, const double* depth);
+/* asynchronous: enqueues the chain on the context's stream and a copy of the n_jobs result records into `results`
+ * (host memory, page-locked for a truly asynchronous copy); valid after ygzb_synchronize(ctx).                    */
+int ygzb_tracker_track(ygzb_tracker* t, int n_jobs, const ygzb_track_job* jobs, ygzb_track_result* results);
+/* asynchronous like ygzb_tracker_track; local BA problems of a batch run as one cluster launch.                   */
+int ygzb_tracker_make_keyframes(ygzb_tracker* t, int n, const ygzb_keyframe_job* jobs, const ygzb_ba_params* ba,
+                                ygzb_keyframe_result* results);
+
 #ifdef __cplusplus
 }
 #endif

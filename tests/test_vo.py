@@ -53,9 +53,11 @@ def test_vo_gpu_matches_oracle_trajectory(ctx3, oracle):
 
 @pytest.mark.gpu
 def test_native_driver_matches_python_loop(ctx3):
-    """host/vo_driver.cpp (C++ lock-step loop over the C ABI) against vo.VisualOdometry on the same GPU backend: same
-    key-frames and BAs, every pose within the stated 1e-4 (the two loops differ in the host-side rounding of SE3 products,
-    which can flip a borderline candidate at the 20 px border or a pose-only inlier on the threshold; measured 1.5e-5)."""
+    """host/vo_driver.cpp against vo.VisualOdometry on the same GPU backend -- the per-stage C++ loop (one blocking C-ABI call
+    per stage) and the device-resident engine (ygzb_tracker_*: local map, candidate projection, key-frame insertion and BA
+    assembly on the device; one and several frames per stream in flight): same key-frames and BAs, every pose within the
+    stated 1e-4 (the loops differ in the rounding of SE3 products and in the summation order of the BA, which can flip a
+    borderline candidate at the 20 px border or a pose-only inlier on the threshold; measured 1.5e-5)."""
     from ygz_slam_b200 import vo_native
     n_streams, n_frames = 3, 26
     data = [synth.shift_stream(s, n_frames) for s in range(n_streams)]
@@ -64,16 +66,25 @@ def test_native_driver_matches_python_loop(ctx3):
     for k in range(n_frames):
         V.add_frames([data[s][0][k] for s in range(n_streams)], [data[s][1] for s in range(n_streams)], k)
     be.fr.close()
-    traj, stats, sec = vo_native.run(ctx3, [d[0] for d in data], [d[1] for d in data], 5, 0.03, 0.03)
-    assert sec > 0
+    runs = {"stages": vo_native.run(ctx3, [d[0] for d in data], [d[1] for d in data], 5, 0.03, 0.03, engine="stages"),
+            "resident_w1": vo_native.run(ctx3, [d[0] for d in data], [d[1] for d in data], 5, 0.03, 0.03, window=1),
+            "resident_w5_2threads": vo_native.run(ctx3, [d[0] for d in data], [d[1] for d in data], 5, 0.03, 0.03, window=8, threads=2)}
+    for name, (traj, stats, sec) in runs.items():
+        _check_native(name, traj, stats, sec, V, data, n_streams, n_frames)
+    # a window only changes how many frames are in flight, never a result: bit-identical trajectories
+    assert np.array_equal(runs["resident_w1"][0], runs["resident_w5_2threads"][0])
+
+
+def _check_native(name, traj, stats, sec, V, data, n_streams, n_frames):
+    assert sec > 0, name
     for s in range(n_streams):
         st = V.streams[s]
-        assert not st.lost and stats[s]["lost"] == 0
-        assert stats[s]["keyframes"] == st.stats["keyframes"] and stats[s]["ba"] == st.stats["ba"]
-        assert stats[s]["keyframes"] >= 3 and stats[s]["ba"] >= 2
+        assert not st.lost and stats[s]["lost"] == 0, name
+        assert stats[s]["keyframes"] == st.stats["keyframes"] and stats[s]["ba"] == st.stats["ba"], name
+        assert stats[s]["keyframes"] >= 3 and stats[s]["ba"] >= 2, name
         for key in ("candidates", "projected", "inliers"):
-            assert abs(stats[s][key] - st.stats[key]) <= 1e-3 * st.stats[key], key
+            assert abs(stats[s][key] - st.stats[key]) <= 1e-3 * st.stats[key], (name, key)
         for k in range(n_frames):
-            assert np.linalg.norm(se3.se3_log(se3.mul(traj[s, k], se3.inv(st.trajectory[k])))) < 1e-4, (s, k)
+            assert np.linalg.norm(se3.se3_log(se3.mul(traj[s, k], se3.inv(st.trajectory[k])))) < 1e-4, (name, s, k)
         # and both follow the exact ground truth of the sliding-crop stream
         assert np.linalg.norm(se3.se3_log(se3.mul(traj[s, -1], se3.inv(data[s][2][-1])))) < 3e-3

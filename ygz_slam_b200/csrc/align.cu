@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "se3.cuh"
+#include "track.cuh"
 
 namespace ygzb {
 
@@ -252,26 +253,19 @@ __device__ __forceinline__ uint8_t interp_uchar(double x, double y, const LevelI
     return (uint8_t)((1 - xx) * (1 - yy) * d[0] + xx * (1 - yy) * d[1] + (1 - xx) * yy * d[im.pitch] + xx * yy * d[im.pitch + 1]);
 }
 
-// Matcher::FindDirectProjection(ref, curr, Feature*, px, level) for candidate i
-__global__ void __launch_bounds__(128) project_align_kernel(const uint8_t* __restrict__ pyr, size_t slot_stride, Geometry g, CamF cam,
-                                                            int n, const int32_t* __restrict__ ref_slot,
-                                                            const int32_t* __restrict__ cur_slot, const double* __restrict__ poses,
-                                                            const int32_t* __restrict__ ref_pose, const int32_t* __restrict__ cur_pose,
-                                                            const double* __restrict__ ref_px, const double* __restrict__ ref_depth,
-                                                            const uint8_t* __restrict__ ref_level, double* __restrict__ cur_px,
-                                                            uint8_t* __restrict__ search_level, uint8_t* __restrict__ ok) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    ok[i] = 0;
-    search_level[i] = 0;
-    if (ref_depth[i] < 0) return;
+// Matcher::FindDirectProjection(ref, curr, Feature*, px, level) for one candidate: poses as 3x4 matrices, (cu, cv) = predicted
+// full-resolution pixel in, aligned pixel out.  Returns the function's bool.
+__device__ bool find_direct_projection_dev(const uint8_t* __restrict__ pyr, size_t slot_stride, const Geometry& g, const CamF& cam,
+                                           int ref_slot, int cur_slot, const double* __restrict__ Tr_mat, const double* __restrict__ Tc_mat,
+                                           double pxr, double pyr_, double ref_depth, int lvl, double* cu_io, double* cv_io,
+                                           uint8_t* search_level) {
+    *search_level = 0;
+    if (ref_depth < 0) return false;
     const int half = 4;
-    const double pxr = ref_px[2 * i], pyr_ = ref_px[2 * i + 1];
-    const int lvl = ref_level[i];
-    const SE3d Tr = se3_from_mat(poses + 12 * (size_t)ref_pose[i]), Tc = se3_from_mat(poses + 12 * (size_t)cur_pose[i]);
+    const SE3d Tr = se3_from_mat(Tr_mat), Tc = se3_from_mat(Tc_mat);
     const SE3d Tr_inv = se3_inverse(Tr);
     const SE3d TCR = se3_mul(Tc, Tr_inv);
-    const V3d pt_ref = pixel2camera(cam, pxr, pyr_, ref_depth[i]);
+    const V3d pt_ref = pixel2camera(cam, pxr, pyr_, ref_depth);
     const V3d pt_ref_world = transform(Tr_inv, pt_ref);
     const V3d pt_du = pixel2camera(cam, pxr + (double)half * (1 << lvl), pyr_, pt_ref.z);
     const V3d pt_dv = pixel2camera(cam, pxr, pyr_ + (double)half * (1 << lvl), pt_ref.z);
@@ -286,11 +280,11 @@ __global__ void __launch_bounds__(128) project_align_kernel(const uint8_t* __res
         sl += 1;
         D *= 0.25;
     }
-    search_level[i] = (uint8_t)sl;
+    *search_level = (uint8_t)sl;
     const double det = A00 * A11 - A10 * A01;
     const double invdet = 1.0 / det;
     const double R00 = A11 * invdet, R01 = -A01 * invdet, R10 = -A10 * invdet, R11 = A00 * invdet;
-    const LevelImg rim = level_img(pyr, slot_stride, ref_slot[i], g, lvl);
+    const LevelImg rim = level_img(pyr, slot_stride, ref_slot, g, lvl);
     uint8_t pwb[100], patch[64];
     const double rx = pxr / (1 << lvl), ry = pyr_ / (1 << lvl);
     for (int y = 0, k = 0; y < 10; ++y)
@@ -304,14 +298,35 @@ __global__ void __launch_bounds__(128) project_align_kernel(const uint8_t* __res
         }
     for (int y = 1; y < 9; ++y)
         for (int x = 0; x < 8; ++x) patch[(y - 1) * 8 + x] = pwb[y * 10 + 1 + x];
-    double su = cur_px[2 * i] / (1 << sl), sv = cur_px[2 * i + 1] / (1 << sl);
-    const LevelImg cim = level_img(pyr, slot_stride, cur_slot[i], g, sl);
+    double su = *cu_io / (1 << sl), sv = *cv_io / (1 << sl);
+    const LevelImg cim = level_img(pyr, slot_stride, cur_slot, g, sl);
     const bool success = align2d_dev(cim, pwb, patch, 10, &su, &sv);
     const double ou = su * (1 << sl), ov = sv * (1 << sl);
-    cur_px[2 * i] = ou;
-    cur_px[2 * i + 1] = ov;
+    *cu_io = ou;
+    *cv_io = ov;
     const bool in = ou >= 10 && ou < g.W - 10 && ov >= 10 && ov < g.H - 10;  // curr->InFrame(px_curr), border 10
-    ok[i] = (in && success) ? 1 : 0;
+    return in && success;
+}
+
+__global__ void __launch_bounds__(128) project_align_kernel(const uint8_t* __restrict__ pyr, size_t slot_stride, Geometry g, CamF cam,
+                                                            int n, const int32_t* __restrict__ ref_slot,
+                                                            const int32_t* __restrict__ cur_slot, const double* __restrict__ poses,
+                                                            const int32_t* __restrict__ ref_pose, const int32_t* __restrict__ cur_pose,
+                                                            const double* __restrict__ ref_px, const double* __restrict__ ref_depth,
+                                                            const uint8_t* __restrict__ ref_level, double* __restrict__ cur_px,
+                                                            uint8_t* __restrict__ search_level, uint8_t* __restrict__ ok) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double cu = cur_px[2 * i], cv = cur_px[2 * i + 1];
+    uint8_t sl = 0;
+    const bool good = find_direct_projection_dev(pyr, slot_stride, g, cam, ref_slot[i], cur_slot[i], poses + 12 * (size_t)ref_pose[i],
+                                                 poses + 12 * (size_t)cur_pose[i], ref_px[2 * i], ref_px[2 * i + 1], ref_depth[i],
+                                                 ref_level[i], &cu, &cv, &sl);
+    search_level[i] = sl;
+    ok[i] = good ? 1 : 0;
+    if (ref_depth[i] < 0) return;   // (the reference returns before touching px_curr)
+    cur_px[2 * i] = cu;
+    cur_px[2 * i + 1] = cv;
 }
 
 // ---- SparseImgAlign -----------------------------------------------------------------------------------
@@ -323,6 +338,8 @@ struct SparseArgs {
     const int32_t* ref_slot;
     const int32_t* cur_slot;
     const int32_t* offsets;     // [n_problems + 1] into the per-feature arrays
+    const int32_t* in_off;      // optional: px / depth / has_mp of problem p start at in_off[p] (default: offsets[p])
+    const int32_t* n_feat;      // optional: feature count of problem p (default: offsets[p + 1] - offsets[p])
     const double* px;           // [2 total]
     const double* depth;
     const uint8_t* has_mp;
@@ -393,8 +410,10 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
     const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
     const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int CT = C * kSparseThreads, ct = rank * kSparseThreads + tid;   // cluster-wide thread id
-    const int f0 = a.offsets[prob], f1 = a.offsets[prob + 1];
-    const int nf = f1 - f0;
+    const int f0 = a.offsets[prob];
+    const int nf = a.n_feat ? a.n_feat[prob] : a.offsets[prob + 1] - f0;
+    const int f1 = f0 + nf;
+    const long din = a.in_off ? (long)a.in_off[prob] - f0 : 0;   // input index = scratch index + din
     const Geometry& g = a.g;
     double* ws = a.ws + (size_t)prob * 2 * kSparseCluster * (kNormalTerms + 1);
     int slot = 0;
@@ -421,11 +440,11 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
         // zero Jacobian (jacobian_cache_.setZero(); visible_fts_ is never cleared -- kept faithfully)
         for (int i = f0 + ct; i < f1; i += CT) {   // (per-feature scratch is written and later read by the same thread)
             for (int k = 0; k < 16; ++k) a.gdx[(size_t)i * 16 + k] = a.gdy[(size_t)i * 16 + k] = 0.f;
-            const float u_ref = (float)(a.px[2 * i] * scale), v_ref = (float)(a.px[2 * i + 1] * scale);
+            const float u_ref = (float)(a.px[2 * (i + din)] * scale), v_ref = (float)(a.px[2 * (i + din) + 1] * scale);
             const int ui = (int)floorf(u_ref), vi = (int)floorf(v_ref);
-            if (!a.has_mp[i] || ui - 3 < 0 || vi - 3 < 0 || ui + 3 >= rim.w || vi + 3 >= rim.h) continue;
+            if ((a.has_mp && !a.has_mp[i + din]) || ui - 3 < 0 || vi - 3 < 0 || ui + 3 >= rim.w || vi + 3 >= rim.h) continue;
             a.visible[i] = 1;
-            const V3d xyz = pixel2camera(a.cam, a.px[2 * i], a.px[2 * i + 1], a.depth[i]);
+            const V3d xyz = pixel2camera(a.cam, a.px[2 * (i + din)], a.px[2 * (i + din) + 1], a.depth[i + din]);
             double* J = a.frame_jac + (size_t)i * 12;
             const double X = xyz.x, Y = xyz.y, zi = 1. / xyz.z, zi2 = zi * zi;
             J[0] = -zi; J[1] = 0; J[2] = X * zi2; J[3] = Y * J[2]; J[4] = -(1.0 + X * J[2]); J[5] = Y * zi;
@@ -463,7 +482,7 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
             unsigned long long nm = 0;
             for (int i = f0 + ct; i < f1; i += CT) {
                 if (!a.visible[i]) continue;
-                const V3d xyz_ref = pixel2camera(a.cam, a.px[2 * i], a.px[2 * i + 1], a.depth[i]);
+                const V3d xyz_ref = pixel2camera(a.cam, a.px[2 * (i + din)], a.px[2 * (i + din) + 1], a.depth[i + din]);
                 const V3d xyz_cur = transform(T, xyz_ref);
                 double pu, pv;
                 camera2pixel(a.cam, xyz_cur, &pu, &pv);
@@ -574,6 +593,133 @@ __global__ void __launch_bounds__(kSparseThreads) sparse_align_kernel(const Spar
     }
 }
 
+
+// ---- device-resident tracking chain (track.cuh): the caller-side steps between the kernels above -----------------------
+// plain 3x4 matrix products exactly as the host drivers write them (host/vo_driver.cpp: mul / inv of Mat34)
+__device__ __forceinline__ void mat34_mul(const double* A, const double* B, double* C) {
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) C[4 * r + c] = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
+        C[4 * r + 3] = A[4 * r] * B[3] + A[4 * r + 1] * B[7] + A[4 * r + 2] * B[11] + A[4 * r + 3];
+    }
+}
+__device__ __forceinline__ void mat34_inv(const double* A, double* C) {
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) C[4 * r + c] = A[4 * c + r];
+        C[4 * r + 3] = -(A[r] * A[3] + A[4 + r] * A[7] + A[8 + r] * A[11]);
+    }
+}
+
+// per job: problem description of the sparse alignment from the ring entry of the reference key-frame
+__global__ void track_prep_kernel(TrackStore st, TrackBatch b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b.J) return;
+    const ygzb_track_job job = b.jobs[j];
+    const int e = job.stream * st.R + job.entry[job.n_local - 1];
+    b.ref_slot[j] = st.kf_slot[e];
+    b.cur_slot[j] = job.cur_slot;
+    b.offsets[j] = j * st.cells;
+    if (j == 0) b.offsets[b.J] = b.J * st.cells;
+    b.in_off[j] = e * st.cells;
+    b.n_feat[j] = st.kf_n[e];
+    for (int c = 0; c < 12; ++c) b.T_ref[12 * (size_t)j + c] = b.T_cur[12 * (size_t)j + c] = st.kf_T[12 * (size_t)e + c];   // VisualOdometry.cpp:66
+    b.n_cand[j] = 0;
+    b.c_off[j] = j * b.cap;
+    if (j == 0) b.c_off[b.J] = b.J * b.cap;
+}
+
+// per job: Matcher::SparseImageAlignment's motion check (Matcher.cpp:482-488) and the current pose relative to every
+// local key-frame (GetWarpAffineMatrix is only correct for an identity reference pose, Matcher.cpp:425-430)
+__global__ void track_motion_kernel(TrackStore st, TrackBatch b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b.J) return;
+    const ygzb_track_job job = b.jobs[j];
+    const double* Tc = b.T_cur + 12 * (size_t)j;
+    double inv_ref[12], tcr[12], lg[6];
+    mat34_inv(b.T_ref + 12 * (size_t)j, inv_ref);
+    mat34_mul(Tc, inv_ref, tcr);
+    se3_log(se3_from_mat(tcr), lg);
+    double nrm = 0;
+    for (int k = 0; k < 6; ++k) nrm += lg[k] * lg[k];
+    b.aligned[j] = sqrt(nrm) <= 0.2 ? 1 : 0;
+    for (int k = 0; k < job.n_local; ++k) {
+        double inv_k[12];
+        mat34_inv(st.kf_T + 12 * (size_t)(job.stream * st.R + job.entry[k]), inv_k);
+        mat34_mul(Tc, inv_k, b.rel + 12 * ((size_t)j * kTrackMaxLocal + k));
+    }
+}
+
+// LocalMapping::FindCandidates (LocalMapping.cpp:47-80) + Matcher::FindDirectProjection (:82-111) for dense candidate
+// c = local key-frame k * cells + feature g of job blockIdx.y
+__global__ void __launch_bounds__(128) track_project_kernel(const uint8_t* __restrict__ pyr, size_t slot_stride, Geometry g, CamF cam,
+                                                            TrackStore st, TrackBatch b) {
+    const int j = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= b.cap) return;
+    const size_t at = (size_t)j * b.cap + c;
+    b.cand_ok[at] = 0;
+    if (!b.aligned[j]) return;
+    const ygzb_track_job job = b.jobs[j];
+    const int k = c / st.cells, f = c - k * st.cells;
+    if (k >= job.n_local) return;
+    const int e = job.stream * st.R + job.entry[k];
+    if (f >= st.kf_n[e]) return;
+    const double* X = st.kf_pw + 3 * ((size_t)e * st.cells + f);
+    const double* T = b.T_cur + 12 * (size_t)j;
+    const double x = T[0] * X[0] + T[1] * X[1] + T[2] * X[2] + T[3];
+    const double y = T[4] * X[0] + T[5] * X[1] + T[6] * X[2] + T[7];
+    const double z = T[8] * X[0] + T[9] * X[1] + T[10] * X[2] + T[11];
+    double u = st.fx * x / z + st.cx, v = st.fy * y / z + st.cy;
+    if (!(z > 0 && u >= 20 && u < st.W - 20 && v >= 20 && v < st.H - 20)) return;
+    atomicAdd(&b.n_cand[j], 1);
+    const double eye[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    uint8_t sl;
+    const size_t fe = (size_t)e * st.cells + f;
+    const bool ok = find_direct_projection_dev(pyr, slot_stride, g, cam, st.kf_slot[e], job.cur_slot, eye,
+                                               b.rel + 12 * ((size_t)j * kTrackMaxLocal + k), st.kf_px[2 * fe], st.kf_px[2 * fe + 1],
+                                               st.kf_depth[fe], st.kf_level[fe], &u, &v, &sl);
+    b.cand_px[2 * at] = u;
+    b.cand_px[2 * at + 1] = v;
+    b.cand_ok[at] = ok ? 1 : 0;
+}
+
+// ordered compaction of the successfully projected candidates of job blockIdx.x (candidate order = local key-frame, then
+// feature: the order in which the reference's caller loops hand them to OptimizeCurrentPoseOnly)
+__global__ void __launch_bounds__(1024) track_compact_kernel(TrackStore st, TrackBatch b) {
+    __shared__ int s_scan[1024];
+    __shared__ int s_carry;
+    const int j = blockIdx.x, tid = threadIdx.x;
+    const ygzb_track_job job = b.jobs[j];
+    const int total = job.n_local * st.cells;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += 1024) {
+        const int c = base + tid;
+        const int flag = (c < total && b.cand_ok[(size_t)j * b.cap + c]) ? 1 : 0;
+        s_scan[tid] = flag;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int v = tid >= o ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        if (flag) {
+            const size_t dst = (size_t)j * b.cap + s_carry + s_scan[tid] - 1;
+            const int k = c / st.cells, f = c - k * st.cells;
+            const size_t fe = (size_t)(job.stream * st.R + job.entry[k]) * st.cells + f;
+            b.c_src[dst] = c;
+            b.c_px[2 * dst] = b.cand_px[2 * ((size_t)j * b.cap + c)];
+            b.c_px[2 * dst + 1] = b.cand_px[2 * ((size_t)j * b.cap + c) + 1];
+            b.c_pw[3 * dst] = st.kf_pw[3 * fe];
+            b.c_pw[3 * dst + 1] = st.kf_pw[3 * fe + 1];
+            b.c_pw[3 * dst + 2] = st.kf_pw[3 * fe + 2];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry += s_scan[1023];
+        __syncthreads();
+    }
+    if (tid == 0) b.c_cnt[j] = s_carry;
+}
+
 }  // namespace
 
 size_t sparse_align_ws_doubles(int n_problems) { return (size_t)n_problems * 2 * kSparseCluster * (kNormalTerms + 1); }
@@ -629,6 +775,8 @@ int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slo
     a.ref_slot = d_ref_slot;
     a.cur_slot = d_cur_slot;
     a.offsets = d_offsets;
+    a.in_off = nullptr;
+    a.n_feat = nullptr;
     a.px = d_px;
     a.depth = d_depth;
     a.has_mp = d_has_mp;
@@ -661,6 +809,82 @@ int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slo
     ProfScope ps(ctx, kStageSparseAlign);
     YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, sparse_align_kernel, a));
     YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
+
+// front half of the tracking chain of a batch: prep -> sparse alignment -> motion check / relative poses -> candidate
+// projection + direct projection -> ordered compaction.  The pose-only refinement (ba.cu) follows on the same stream.
+int launch_track_chain_front(ygzb_frames* f, const TrackStore& st, const TrackBatch& b, int sparse_cluster) {
+    ygzb_ctx* ctx = f->ctx;
+    if (b.J <= 0) return YGZB_OK;
+    {
+        ProfScope ps(ctx, kStageOther);
+        track_prep_kernel<<<(b.J + 127) / 128, 128, 0, ctx->stream>>>(st, b);
+        YGZB_LAUNCHED(ctx);
+    }
+    YGZB_CUDA(ctx, cudaMemsetAsync(b.ref_patch, 0, (size_t)b.J * st.cells * 16 * sizeof(float), ctx->stream));
+    {
+        SparseArgs a;
+        a.pyr = f->d_pyr;
+        a.slot_stride = ctx->slot_stride;
+        a.g = ctx->geo;
+        a.cam = CamF{ctx->prm.fx, ctx->prm.fy, ctx->prm.cx, ctx->prm.cy};
+        a.ref_slot = b.ref_slot;
+        a.cur_slot = b.cur_slot;
+        a.offsets = b.offsets;
+        a.in_off = b.in_off;
+        a.n_feat = b.n_feat;
+        a.px = st.kf_px;
+        a.depth = st.kf_depth;
+        a.has_mp = nullptr;            // every feature of a key-frame has its map point (depth-initialised)
+        a.T_ref = b.T_ref;
+        a.T_cur = b.T_cur;
+        a.max_level = 2;               // Matcher's SparseImgAlign(2, 0, 30, GaussNewton) (Matcher.cpp:18)
+        a.min_level = 0;
+        a.n_iter = 30;
+        a.eps = 1e-6;
+        a.n_meas_out = b.n_meas;
+        a.iters_out = nullptr;
+        a.ref_patch = b.ref_patch;
+        a.gdx = b.gdx;
+        a.gdy = b.gdy;
+        a.frame_jac = b.frame_jac;
+        a.visible = b.visible;
+        a.ws = b.sparse_ws;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(b.J * sparse_cluster));
+        cfg.blockDim = dim3(kSparseThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = sparse_cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ProfScope ps(ctx, kStageSparseAlign);
+        YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, sparse_align_kernel, a));
+        YGZB_LAUNCHED(ctx);
+    }
+    {
+        ProfScope ps(ctx, kStageOther);
+        track_motion_kernel<<<(b.J + 63) / 64, 64, 0, ctx->stream>>>(st, b);
+        YGZB_LAUNCHED(ctx);
+    }
+    {
+        const CamF cam{ctx->prm.fx, ctx->prm.fy, ctx->prm.cx, ctx->prm.cy};
+        ProfScope ps(ctx, kStageProjectAlign);
+        track_project_kernel<<<dim3((unsigned)((b.cap + 127) / 128), (unsigned)b.J), 128, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, ctx->geo,
+                                                                                                          cam, st, b);
+        YGZB_LAUNCHED(ctx);
+    }
+    {
+        ProfScope ps(ctx, kStageOther);
+        track_compact_kernel<<<(unsigned)b.J, 1024, 0, ctx->stream>>>(st, b);
+        YGZB_LAUNCHED(ctx);
+    }
     return YGZB_OK;
 }
 

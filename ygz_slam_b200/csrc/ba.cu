@@ -31,8 +31,10 @@
 
 #include <cooperative_groups.h>
 
+#include "ba2.cuh"
 #include "common.cuh"
 #include "se3.cuh"
+#include "track.cuh"
 
 namespace ygzb {
 
@@ -951,6 +953,7 @@ __device__ void project_jet(const double pose[6], const double X[3], Jet6* p0, J
 
 struct PoseOnlyArgs {
     const int32_t* offsets;   // per problem range of points
+    const int32_t* counts;    // optional: points of problem p (default offsets[p + 1] - offsets[p])
     const double* pw;         // [total][3]
     const double* px;         // [total][2]
     double* T_cw;             // [n_problems][12] in/out
@@ -1003,7 +1006,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
     const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
     const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int CT = C * kPoseThreads, ct = rank * kPoseThreads + tid;   // cluster-wide thread id
-    const int i0 = a.offsets[prob], n = a.offsets[prob + 1] - i0;
+    const int i0 = a.offsets[prob], n = a.counts ? a.counts[prob] : a.offsets[prob + 1] - i0;
     const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
     double* ws = a.ws + (size_t)prob * 4 * kPoseCluster * kPoseRed;
     int slot = 0;
@@ -1226,6 +1229,37 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
 
 }  // namespace
 
+size_t pose_only_ws_doubles(int n_problems) { return (size_t)n_problems * 4 * kPoseCluster * kPoseRed; }
+
+// ba::OptimizeCurrentPoseOnly on device-resident problems (the tracking engine): problem p owns points
+// [d_offsets[p], d_offsets[p] + d_counts[p]); cluster = CTAs per problem (1, 2, 4 or 8)
+int launch_pose_only_dev(ygzb_ctx* ctx, int n_problems, const int32_t* d_offsets, const int32_t* d_counts, const double* d_pw,
+                         const double* d_px, double* d_T_cw, uint8_t* d_inlier, double* d_depth, int32_t* d_n_inlier, uint8_t* d_enable,
+                         double* d_ws, int cluster) {
+    if (n_problems <= 0) return YGZB_OK;
+    PoseOnlyArgs a;
+    a.offsets = d_offsets; a.counts = d_counts; a.pw = d_pw; a.px = d_px; a.T_cw = d_T_cw; a.inlier = d_inlier; a.depth = d_depth;
+    a.n_inlier = d_n_inlier; a.enable = d_enable; a.ws = d_ws;
+    a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
+    cluster = std::max(1, std::min(cluster, kPoseCluster));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_problems * cluster));
+    cfg.blockDim = dim3(kPoseThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope ps(ctx, kStagePoseOnly);
+    YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, pose_only_kernel, a));
+    YGZB_LAUNCHED(ctx);
+    return YGZB_OK;
+}
+
 }  // namespace ygzb
 
 // ---- extern "C" entry points (marshalling + index bookkeeping only) ---------------------------------------
@@ -1262,6 +1296,79 @@ void ygzb_default_ba_params(ygzb_ba_params* p) {
 }  // extern "C"
 
 namespace {
+// ba::LocalBAG2O through the second-generation kernel (ba2.cu): validation and ONE staged host-to-device copy here, the
+// landmark-major observation lists and everything else on the device
+int run_local_ba2(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off, double* poses,
+                  const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px,
+                  const ygzb_ba_params* prm, uint8_t* outlier, std::vector<double>& hst) {
+    const size_t P = (size_t)n_problems, NK = (size_t)kf_off[n_problems], NP = (size_t)pt_off[n_problems], NO = (size_t)obs_off[n_problems];
+    BA2Problem in{};
+    in.n_problems = n_problems;
+    for (size_t p = 0; p < P; ++p) {
+        const int k0 = kf_off[p], nk = kf_off[p + 1] - k0, npt = pt_off[p + 1] - pt_off[p], o0 = obs_off[p], no = obs_off[p + 1] - o0;
+        if (nk < 1 || nk > kBA2MaxPoses) return set_error(ctx, YGZB_ERR_INVALID, "problem %zu: %d poses (1..%d supported)", p, nk, kBA2MaxPoses);
+        int nf = 0;
+        for (int k = 0; k < nk; ++k) nf += fixed[k0 + k] ? 0 : 1;
+        if (nf > kBA2MaxFree) return set_error(ctx, YGZB_ERR_INVALID, "problem %zu: %d free poses (max %d)", p, nf, kBA2MaxFree);
+        for (int o = 0; o < no; ++o)
+            if (kf_idx[o0 + o] < 0 || kf_idx[o0 + o] >= nk || pt_idx[o0 + o] < 0 || pt_idx[o0 + o] >= npt)
+                return set_error(ctx, YGZB_ERR_INVALID, "observation %d: index out of range", o0 + o);
+        in.max_free = std::max(in.max_free, nf);
+        in.max_kf = std::max(in.max_kf, nk);
+        in.max_pts = std::max(in.max_pts, (size_t)npt);
+        in.max_obs = std::max(in.max_obs, (size_t)no);
+    }
+    in.total_pts = NP;
+    in.total_obs = NO;
+    Carver sz(nullptr);
+    sz.take<int32_t>(3 * (P + 1)); sz.take<double>(6 * NK); sz.take<uint8_t>(NK); sz.take<double>(3 * NP); sz.take<int32_t>(2 * NO);
+    sz.take<double>(2 * NO);
+    const size_t in_span = sz.bytes();
+    void* buf = dev_scratch(ctx, 7, in_span + ba2_scratch_bytes(NP, NO, P) + 256);
+    if (!buf) return YGZB_ERR_CUDA;
+    Carver c(buf);
+    int32_t* d_off = c.take<int32_t>(3 * (P + 1));
+    double* d_poses = c.take<double>(6 * NK);
+    uint8_t* d_fixed = c.take<uint8_t>(NK);
+    double* d_pts = c.take<double>(3 * NP);
+    int32_t* d_idx = c.take<int32_t>(2 * NO);
+    double* d_obs = c.take<double>(2 * NO);
+    const size_t in_bytes = (size_t)(reinterpret_cast<uint8_t*>(d_obs + 2 * NO) - static_cast<uint8_t*>(buf));
+    uint8_t* stage = static_cast<uint8_t*>(host_scratch(ctx, 1, in_bytes));
+    if (!stage) return YGZB_ERR_CUDA;
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // an earlier copy may still read the staging buffer
+    auto put = [&](const void* dev_ptr, const void* src, size_t bytes) {
+        if (bytes) memcpy(stage + (static_cast<const uint8_t*>(dev_ptr) - static_cast<uint8_t*>(buf)), src, bytes);
+    };
+    put(d_off, kf_off, (P + 1) * 4);
+    put(d_off + (P + 1), pt_off, (P + 1) * 4);
+    put(d_off + 2 * (P + 1), obs_off, (P + 1) * 4);
+    put(d_poses, poses, 6 * NK * 8);
+    put(d_fixed, fixed, NK);
+    put(d_pts, pts, 3 * NP * 8);
+    put(d_idx, kf_idx, NO * 4);
+    put(d_idx + NO, pt_idx, NO * 4);
+    put(d_obs, obs_px, 2 * NO * 8);
+    YGZB_CUDA(ctx, cudaMemcpyAsync(buf, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    in.kf_off = d_off; in.pt_off = d_off + (P + 1); in.obs_off = d_off + 2 * (P + 1);
+    in.poses = d_poses; in.fixed = d_fixed; in.pts = d_pts; in.kf_idx = d_idx; in.pt_idx = d_idx + NO; in.obs = d_obs;
+    in.lm_start = nullptr;
+    uint8_t* d_outl = nullptr;
+    double* d_stats = nullptr;
+    void* scratch = static_cast<uint8_t*>(buf) + ((in_span + 255) & ~(size_t)255);
+    TRY(launch_local_ba2(ctx, in, scratch, prm, &d_outl, &d_stats));
+    TRY(d2h(ctx, poses, d_poses, 6 * NK));
+    TRY(d2h(ctx, pts, d_pts, 3 * NP));
+    if (outlier) TRY(d2h(ctx, outlier, d_outl, NO));
+    hst.resize(8 * P);
+    TRY(d2h(ctx, hst.data(), d_stats, 8 * P));
+    YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t p = 0; p < P; ++p)
+        if (hst[8 * p + 6] != 0)
+            return set_error(ctx, YGZB_ERR_INVALID, "problem %zu: a point is observed twice by one key-frame (not a SLAM graph)", p);
+    return YGZB_OK;
+}
+
 // shared body of ygzb_local_ba (ceres = false) and ygzb_local_ba_ceres (ceres = true): index bookkeeping on the host,
 // one cluster launch, results back.  hst receives the 8 raw statistics of every problem.
 int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
@@ -1273,6 +1380,7 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
         if (rc != YGZB_OK) return rc;
     }
     const size_t P = (size_t)n_problems, NK = (size_t)kf_off[n_problems], NP = (size_t)pt_off[n_problems], NO = (size_t)obs_off[n_problems];
+    if (!ceres && !getenv("YGZB_BA_GEN1")) return run_local_ba2(ctx, n_problems, kf_off, pt_off, obs_off, poses, fixed, pts, kf_idx, pt_idx, obs_px, prm, outlier, hst);
     // ---- structure: observations grouped by landmark, by pose, and landmark-sharing observation pairs per block pair
     std::vector<int32_t> lm_start(NP + 1, 0), lm_obs(NO), ps_start(NK + 1, 0), ps_obs(NO), pair_off(P + 1, 0), pair_start, pair_o1, pair_o2;
     int max_free = 0;
@@ -1548,7 +1656,7 @@ int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const 
     a.n_inlier = c.take<int32_t>(P);
     a.enable = c.take<uint8_t>(N);
     a.ws = c.take<double>(P * 4 * kPoseCluster * kPoseRed);
-    a.offsets = d_off; a.pw = d_pw; a.px = d_px;
+    a.offsets = d_off; a.counts = nullptr; a.pw = d_pw; a.px = d_px;
     a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
     {   // the four inputs are the first sub-buffers of `buf`: one pinned staging copy instead of four pageable ones
         const size_t in_bytes = (size_t)(reinterpret_cast<uint8_t*>(a.T_cw + 12 * P) - static_cast<uint8_t*>(buf));

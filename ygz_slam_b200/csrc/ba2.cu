@@ -1,0 +1,857 @@
+// ba2.cu -- ba::LocalBAG2O, second generation: a landmark-partitioned thread-block cluster per problem.
+//
+// Replaces (same maths as the first-generation kernel in ba.cu, which stays in service for the Ceres twin):
+//   ba::LocalBAG2O                   reference src/Algorithm/BA.cpp:386-543
+//   VertexSE3Sophus::oplusImpl       reference include/ygz/G2oTypes.h:38-45
+//   EdgeSophusSE3ProjectXYZ          reference include/ygz/G2oTypes.h:84-132 (computeError, linearizeOplus)
+// g2o itself is outside the reference tree: the Levenberg schedule follows oracle/ba.cpp.
+//
+// Why a second generation: the first one strides observations over the cluster, keeps a 21-double linearisation record
+// per observation in global memory that every CTA reads through L2 (__ldcg), combines partial sums with f64 atomics and
+// crosses ~13 cluster barriers per LM trial; ncu showed 5 % issue-slot utilisation (profiles/r1_final2_local_ba.txt).
+// Here
+//   * the LANDMARKS are partitioned over the CTAs of the cluster (contiguous ranges of the landmark-major observation
+//     list), so everything a landmark needs -- its observations, Hll, bl, (Hll + lambda I)^-1, the 6-double
+//     linearisation record (x, y, z, e0, e1, w) of each observation from which the 2x3 / 2x6 Jacobians are rebuilt in
+//     ~30 flops -- is private to ONE CTA and staged in its shared memory (global scratch only when a problem is too big);
+//   * the reduced system is accumulated by warp tasks (block pair of free poses x stripe of landmarks) that keep their 36+6
+//     sums in registers across the whole stripe and shuffle-reduce once; no atomics anywhere: partial sums are combined
+//     in a fixed order inside the CTA and with a reduce-scatter / all-gather over distributed shared memory across the
+//     cluster, so the result is bit-reproducible run to run;
+//   * an LM trial crosses 3 cluster barriers (2 for the reduced system, 1 for chi2 / gain ratio) and 6 CTA barriers;
+//     a rejected trial re-uses the linearisation and only re-inverts (Hll + lambda I).
+// The observation lists arrive landmark-major (CSR): csr_* kernels below build that order on the device from the
+// (kf_idx, pt_idx) arrays of the C ABI, deterministic (observations of a landmark sorted by their original index).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include <cooperative_groups.h>
+
+#include "ba2.cuh"
+#include "common.cuh"
+#include "se3.cuh"
+
+namespace ygzb {
+
+namespace {
+
+namespace cg = cooperative_groups;
+
+constexpr int kT = kBA2Threads;
+constexpr int kW = kT / 32;
+constexpr int kPairW = 42;   // record of a block-pair task: 36 (Hpl D Hpl^T) + 6 (Hpl D bl, diagonal pairs only)
+constexpr int kPoseW = 27;   // record of a pose task: 21 (upper triangle of Hpp) + 6 (bp)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// block-wide sum of two values (result valid in every thread); s_tmp: 2 * (kW + 1) doubles
+__device__ void block_sum2(double& v0, double& v1, double* s_tmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v0 = warp_sum(v0);
+    v1 = warp_sum(v1);
+    __syncthreads();
+    if (lane == 0) {
+        s_tmp[warp] = v0;
+        s_tmp[kW + 1 + warp] = v1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double t0 = lane < kW ? s_tmp[lane] : 0.0, t1 = lane < kW ? s_tmp[kW + 1 + lane] : 0.0;
+        t0 = warp_sum(t0);
+        t1 = warp_sum(t1);
+        if (lane == 0) {
+            s_tmp[kW] = t0;
+            s_tmp[2 * kW + 1] = t1;
+        }
+    }
+    __syncthreads();
+    v0 = s_tmp[kW];
+    v1 = s_tmp[2 * kW + 1];
+}
+
+__device__ double block_max(double v, double* s_tmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xFFFFFFFFu, v, o));
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < kW ? s_tmp[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_down_sync(0xFFFFFFFFu, t, o));
+        if (lane == 0) s_tmp[kW] = t;
+    }
+    __syncthreads();
+    return s_tmp[kW];
+}
+
+__device__ __forceinline__ SE3d pose_from_g2o(const double* est) {
+    const double v[6] = {est[3], est[4], est[5], est[0], est[1], est[2]};
+    return se3_exp(v);
+}
+
+// Jacobians of EdgeSophusSE3ProjectXYZ::linearizeOplus (G2oTypes.h:108-131) rebuilt from the camera-frame point (x, y, z)
+// and the rotation rows of the pose at the linearisation point
+struct Jac {
+    double l0[3], l1[3];   // d e / d landmark, rows u and v
+    double p0[6], p1[6];   // d e / d pose ([omega; upsilon] order of VertexSE3Sophus)
+};
+__device__ __forceinline__ void pose_jac(double x, double y, double z, double fx, double fy, double* p0, double* p1) {
+    const double iz = 1.0 / z, iz2 = iz * iz;
+    p0[0] = x * y * iz2 * fx; p0[1] = -(1.0 + x * x * iz2) * fx; p0[2] = y * iz * fx;
+    p0[3] = -iz * fx; p0[4] = 0.0; p0[5] = x * iz2 * fx;
+    p1[0] = (1.0 + y * y * iz2) * fy; p1[1] = -x * y * iz2 * fy; p1[2] = -x * iz * fy;
+    p1[3] = 0.0; p1[4] = -iz * fy; p1[5] = y * iz2 * fy;
+}
+__device__ __forceinline__ void point_jac(double x, double y, double z, double fx, double fy, const double* R /* 12: [R|t] rows */,
+                                          double* l0, double* l1) {
+    const double iz = -1.0 / z;
+    const double t02 = x * iz * fx, t12 = y * iz * fy;   // -x/z fx, -y/z fy
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        l0[c] = iz * (fx * R[c] + t02 * R[8 + c]);
+        l1[c] = iz * (fy * R[4 + c] + t12 * R[8 + c]);
+    }
+}
+// Hpl = w Jp^T Jl (6 x 3)
+__device__ __forceinline__ void make_hpl(const double* rec /* x y z e0 e1 w */, const double* R, double fx, double fy, double H[6][3]) {
+    double p0[6], p1[6], l0[3], l1[3];
+    pose_jac(rec[0], rec[1], rec[2], fx, fy, p0, p1);
+    point_jac(rec[0], rec[1], rec[2], fx, fy, R, l0, l1);
+    const double w = rec[5];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) H[a][b] = w * (p0[a] * l0[b] + p1[a] * l1[b]);
+}
+
+// symmetric 3x3 stored as (00, 01, 02, 11, 12, 22)
+__device__ __forceinline__ void sym_inverse3(const double* h, double lambda, double* inv) {
+    const double h0 = h[0] + lambda, h1 = h[1], h2 = h[2], h3 = h[3] + lambda, h4 = h[4], h5 = h[5] + lambda;
+    const double c00 = h3 * h5 - h4 * h4, c01 = h2 * h4 - h1 * h5, c02 = h1 * h4 - h2 * h3;
+    const double det = (c00 * h0 + c01 * h1) + c02 * h2;
+    const double id = 1.0 / det;
+    inv[0] = c00 * id; inv[1] = c01 * id; inv[2] = c02 * id;
+    inv[3] = (h0 * h5 - h2 * h2) * id; inv[4] = (h1 * h2 - h0 * h4) * id; inv[5] = (h0 * h3 - h1 * h1) * id;
+}
+__device__ __forceinline__ void sym_mul3(const double* s, const double* v, double* out) {
+    out[0] = s[0] * v[0] + s[1] * v[1] + s[2] * v[2];
+    out[1] = s[1] * v[0] + s[3] * v[1] + s[4] * v[2];
+    out[2] = s[2] * v[0] + s[4] * v[1] + s[5] * v[2];
+}
+
+struct Stage {   // CTA-private per-landmark / per-observation state: shared memory when it fits, else global scratch
+    double* lin;     // [no][6]  x y z e0 e1 w
+    double* Hll;     // [nl][6]
+    double* bl;      // [nl][3]
+    double* Dinv;    // [nl][6]
+    double* Xb;      // [nl][3]  landmark positions at the linearisation point (push / pop)
+    uint8_t* slot;   // [nl][kBA2MaxFree]  position of the landmark's observation on free pose f inside its list, 0xFF = none
+};
+
+__global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double s_dyn[];
+    __shared__ double s_R[kBA2MaxPoses][12];      // current poses as [R|t]
+    __shared__ double s_Rlin[kBA2MaxPoses][12];   // poses at the linearisation point (the Jacobians are rebuilt from these)
+    __shared__ double s_pose[kBA2MaxPoses][6];    // estimates, g2o order [omega; upsilon]
+    __shared__ double s_backup[kBA2MaxPoses][6];
+    __shared__ double s_xp[6 * kBA2MaxFree];
+    __shared__ double s_tmp[2 * (kW + 1)];
+    __shared__ double s_small[4];                 // per-CTA scalars offered to the cluster: chi2, scale, max |diag|, outliers
+    __shared__ double s_bc[4];                    // cluster totals of the same
+    __shared__ int s_free[kBA2MaxPoses], s_kfof[kBA2MaxFree];
+    __shared__ int s_np, s_ok, s_dup;
+
+    const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+    const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0 = a.kf_off[prob], n_kf = a.n_kf ? a.n_kf[prob] : a.kf_off[prob + 1] - k0;
+    const int p0 = a.pt_off[prob], n_pt = a.n_pt ? a.n_pt[prob] : a.pt_off[prob + 1] - p0;
+    const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
+    const double dsqr = a.huber_delta * a.huber_delta;
+
+    if (tid == 0) {
+        int nf = 0;
+        for (int k = 0; k < n_kf; ++k) {
+            s_free[k] = a.fixed[k0 + k] ? -1 : nf;
+            if (!a.fixed[k0 + k]) s_kfof[nf++] = k;
+        }
+        s_np = nf;
+        s_dup = 0;
+    }
+    if (tid < n_kf)
+        for (int c = 0; c < 6; ++c) s_pose[tid][c] = a.poses[6 * (size_t)(k0 + tid) + c];
+    __syncthreads();
+    const int np = s_np, dimp = 6 * np, n_pairs = np * (np + 1) / 2;
+    const int V = kPairW * n_pairs + kPoseW * np, poseBase = kPairW * n_pairs;
+
+    // this CTA's landmarks [j_lo, j_hi) and their observations [q_lo, q_hi) of the landmark-major list
+    const int per_cta = (n_pt + C - 1) / C;
+    const int j_lo = min(n_pt, rank * per_cta), j_hi = min(n_pt, j_lo + per_cta), nl = j_hi - j_lo;
+    const int q_lo = a.lm_start[p0 + j_lo], q_hi = a.lm_start[p0 + j_hi], no = q_hi - q_lo;
+
+    // ---- dynamic shared memory: [S | bs] aliased with the task slots, the exchange vectors, then the staging area
+    const int n_tasks_all = n_pairs + np;
+    const int sysDoubles = max(dimp * dimp + dimp, (n_tasks_all + kW) * kPairW);
+    double* s_S = s_dyn;
+    double* s_bs = s_S + dimp * dimp;
+    double* s_part = s_dyn;                 // (task + warp) slots of kPairW doubles; consumed before S is assembled
+    double* s_x = s_dyn + sysDoubles;       // [V] CTA partial, after the exchange the cluster totals
+    double* s_tot = s_x + V;                // [V] totals of the slice this CTA owns
+    double* s_stage = s_tot + V;
+    Stage st;
+    {
+        const size_t need = (size_t)6 * no + (size_t)18 * nl + ((size_t)nl * kBA2MaxFree + 7) / 8;
+        const size_t have = (size_t)a.dyn_doubles - (size_t)(sysDoubles + 2 * V);
+        if (need <= have) {
+            st.lin = s_stage;
+            st.Hll = st.lin + (size_t)6 * no;
+            st.bl = st.Hll + (size_t)6 * nl;
+            st.Dinv = st.bl + (size_t)3 * nl;
+            st.Xb = st.Dinv + (size_t)6 * nl;
+            st.slot = reinterpret_cast<uint8_t*>(st.Xb + (size_t)3 * nl);
+        } else {
+            st.lin = a.lin + (size_t)6 * q_lo;
+            st.Hll = a.Hll + (size_t)6 * (p0 + j_lo);
+            st.bl = a.bl + (size_t)3 * (p0 + j_lo);
+            st.Dinv = a.Dinv + (size_t)6 * (p0 + j_lo);
+            st.Xb = a.pts_backup + (size_t)3 * (p0 + j_lo);
+            st.slot = a.slot + (size_t)kBA2MaxFree * (p0 + j_lo);
+        }
+    }
+    // slot table: which observation of a landmark sits on which free pose
+    for (int i = tid; i < nl * kBA2MaxFree; i += kT) st.slot[i] = 0xFF;
+    __syncthreads();
+    for (int jj = tid; jj < nl; jj += kT) {
+        const int qa = a.lm_start[p0 + j_lo + jj], qb = a.lm_start[p0 + j_lo + jj + 1];
+        for (int q = qa; q < qb; ++q) {
+            const int f = s_free[a.so_kf[q]];
+            if (f < 0) continue;
+            if (st.slot[jj * kBA2MaxFree + f] != 0xFF || q - qa >= 255) s_dup = 1;   // two observations of a point in one key-frame
+            st.slot[jj * kBA2MaxFree + f] = (uint8_t)(q - qa);
+        }
+    }
+
+    auto refresh_poses = [&]() {   // contains a CTA barrier
+        if (tid < n_kf) se3_to_mat(pose_from_g2o(s_pose[tid]), s_R[tid]);
+        __syncthreads();
+    };
+    // residual of one observation at the current poses / the given landmark
+    auto reproject = [&](int q, double X0, double X1, double X2, double* x, double* y, double* z, double* e0, double* e1) {
+        const double* Tm = s_R[a.so_kf[q]];
+        *x = Tm[0] * X0 + Tm[1] * X1 + Tm[2] * X2 + Tm[3];
+        *y = Tm[4] * X0 + Tm[5] * X1 + Tm[6] * X2 + Tm[7];
+        *z = Tm[8] * X0 + Tm[9] * X1 + Tm[10] * X2 + Tm[11];
+        *e0 = a.so_uv[2 * (size_t)q] - (*x / *z * fx + cx);
+        *e1 = a.so_uv[2 * (size_t)q + 1] - (*y / *z * fy + cy);
+    };
+    auto robust = [&](double e2, double* w) {   // RobustKernelHuber (delta in pixels, BA.cpp:450-452)
+        *w = 1.0;
+        if (a.huber_delta > 0 && e2 > dsqr) {
+            const double e = sqrt(e2);
+            *w = a.huber_delta / e;
+            return 2 * e * a.huber_delta - dsqr;
+        }
+        return e2;
+    };
+    // cluster totals of the per-CTA scalars in s_small (sum for [0], [1], [3]; max for [2]); contains a cluster barrier
+    auto exchange_small = [&]() {
+        cluster.sync();
+        if (tid == 0) {
+            double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+            for (int r = 0; r < C; ++r) {
+                const double* rs = cluster.map_shared_rank(s_small, r);
+                t0 += rs[0];
+                t1 += rs[1];
+                t2 = fmax(t2, rs[2]);
+                t3 += rs[3];
+            }
+            s_bc[0] = t0; s_bc[1] = t1; s_bc[2] = t2; s_bc[3] = t3;
+        }
+        __syncthreads();
+    };
+    // cluster totals of s_x[lo, hi): reduce-scatter (every CTA sums one slice over the ranks, in rank order) + all-gather
+    // over distributed shared memory; two cluster barriers; s_x holds the totals afterwards in every CTA
+    auto exchange_vector = [&](int lo, int hi) {
+        const int len = hi - lo, sl = (len + C - 1) / C;
+        cluster.sync();
+        for (int i = lo + rank * sl + tid; i < min(hi, lo + (rank + 1) * sl); i += kT) {
+            double t = 0;
+            for (int r = 0; r < C; ++r) t += cluster.map_shared_rank(s_x, r)[i];
+            s_tot[i] = t;
+        }
+        cluster.sync();
+        for (int i = lo + tid; i < hi; i += kT) s_x[i] = cluster.map_shared_rank(s_tot, (i - lo) / max(sl, 1))[i];
+        __syncthreads();
+    };
+
+    // ---- P1: linearise the landmarks of this CTA (relin) and invert Hll + lambda I (with_D) -------------------------
+    auto linearise = [&](bool relin, bool with_D, double lambda, double* chi_out, double* mx_out) {
+        double chi = 0, mx = 0;
+        for (int jj = tid; jj < nl; jj += kT) {
+            const int gj = p0 + j_lo + jj;
+            double H[6];
+            if (relin) {
+                const double X0 = a.pts[3 * (size_t)gj], X1 = a.pts[3 * (size_t)gj + 1], X2 = a.pts[3 * (size_t)gj + 2];
+                st.Xb[3 * jj] = X0; st.Xb[3 * jj + 1] = X1; st.Xb[3 * jj + 2] = X2;
+                double b[3] = {0, 0, 0};
+#pragma unroll
+                for (int t = 0; t < 6; ++t) H[t] = 0;
+                const int qa = a.lm_start[gj], qb = a.lm_start[gj + 1];
+                for (int q = qa; q < qb; ++q) {
+                    double x, y, z, e0, e1, w;
+                    reproject(q, X0, X1, X2, &x, &y, &z, &e0, &e1);
+                    chi += robust(e0 * e0 + e1 * e1, &w);
+                    double* rec = st.lin + 6 * (size_t)(q - q_lo);
+                    rec[0] = x; rec[1] = y; rec[2] = z; rec[3] = e0; rec[4] = e1; rec[5] = w;
+                    double l0[3], l1[3];
+                    point_jac(x, y, z, fx, fy, s_R[a.so_kf[q]], l0, l1);
+                    H[0] += w * (l0[0] * l0[0] + l1[0] * l1[0]); H[1] += w * (l0[0] * l0[1] + l1[0] * l1[1]);
+                    H[2] += w * (l0[0] * l0[2] + l1[0] * l1[2]); H[3] += w * (l0[1] * l0[1] + l1[1] * l1[1]);
+                    H[4] += w * (l0[1] * l0[2] + l1[1] * l1[2]); H[5] += w * (l0[2] * l0[2] + l1[2] * l1[2]);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) b[c] += -w * (l0[c] * e0 + l1[c] * e1);
+                }
+#pragma unroll
+                for (int t = 0; t < 6; ++t) st.Hll[6 * jj + t] = H[t];
+                st.bl[3 * jj] = b[0]; st.bl[3 * jj + 1] = b[1]; st.bl[3 * jj + 2] = b[2];
+                mx = fmax(mx, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
+            } else {
+#pragma unroll
+                for (int t = 0; t < 6; ++t) H[t] = st.Hll[6 * jj + t];
+            }
+            if (with_D) sym_inverse3(H, lambda, st.Dinv + 6 * jj);
+        }
+        *chi_out = chi;
+        *mx_out = mx;
+    };
+
+    // ---- P2: warp tasks.  Task t < n_pairs: block pair (f1 <= f2) of the reduced system; t >= n_pairs: Hpp / bp of free
+    // pose t - n_pairs.  The (task, 32-landmark chunk) items of [t_lo, t_hi) are dealt to the warps in contiguous runs, a
+    // warp keeps its sums in registers while the task stays the same and leaves them in slot (task + warp).
+    auto accumulate = [&](int t_lo, int t_hi) {
+        const int n_chunks = (nl + 31) / 32;
+        const int items = (t_hi - t_lo) * n_chunks, per = (items + kW - 1) / kW;
+        int it = warp * per;
+        const int end = min(items, it + per);
+        while (it < end) {
+            const int trel = it / n_chunks, task = t_lo + trel;
+            const int c_lo = it - trel * n_chunks, c_hi = min(n_chunks, c_lo + (end - it));
+            double* out = s_part + (size_t)(task + warp) * kPairW;
+            if (task < n_pairs) {
+                int f1 = 0, rem = task;
+                while (rem >= np - f1) {
+                    rem -= np - f1;
+                    ++f1;
+                }
+                const int f2 = f1 + rem;
+                const double* R1 = s_Rlin[s_kfof[f1]];
+                const double* R2 = s_Rlin[s_kfof[f2]];
+                double accS[36], accb[6];
+#pragma unroll
+                for (int t = 0; t < 36; ++t) accS[t] = 0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) accb[t] = 0;
+                for (int ch = c_lo; ch < c_hi; ++ch) {
+                    const int jj = ch * 32 + lane;
+                    if (jj >= nl) continue;
+                    const int s1 = st.slot[jj * kBA2MaxFree + f1], s2 = st.slot[jj * kBA2MaxFree + f2];
+                    if (s1 == 0xFF || s2 == 0xFF) continue;
+                    const int qa = a.lm_start[p0 + j_lo + jj] - q_lo;
+                    const double* Di = st.Dinv + 6 * jj;
+                    double H1[6][3], BD[6][3];
+                    make_hpl(st.lin + 6 * (size_t)(qa + s1), R1, fx, fy, H1);
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) sym_mul3(Di, H1[r], BD[r]);   // (Hpl D)_r = D Hpl_r (D symmetric)
+                    if (f1 == f2) {
+                        const double* bj = st.bl + 3 * jj;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) accb[r] += BD[r][0] * bj[0] + BD[r][1] * bj[1] + BD[r][2] * bj[2];
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H1[c][0] + BD[r][1] * H1[c][1] + BD[r][2] * H1[c][2];
+                    } else {
+                        double H2[6][3];
+                        make_hpl(st.lin + 6 * (size_t)(qa + s2), R2, fx, fy, H2);
+#pragma unroll
+                        for (int r = 0; r < 6; ++r)
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H2[c][0] + BD[r][1] * H2[c][1] + BD[r][2] * H2[c][2];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 36; ++t) {
+                    const double v = warp_sum(accS[t]);
+                    if (lane == 0) out[t] = v;
+                }
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const double v = warp_sum(accb[t]);
+                    if (lane == 0) out[36 + t] = v;
+                }
+            } else {
+                const int f = task - n_pairs;
+                double h[21], g[6];
+#pragma unroll
+                for (int t = 0; t < 21; ++t) h[t] = 0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) g[t] = 0;
+                for (int ch = c_lo; ch < c_hi; ++ch) {
+                    const int jj = ch * 32 + lane;
+                    if (jj >= nl) continue;
+                    const int s1 = st.slot[jj * kBA2MaxFree + f];
+                    if (s1 == 0xFF) continue;
+                    const double* rec = st.lin + 6 * (size_t)(a.lm_start[p0 + j_lo + jj] - q_lo + s1);
+                    double q0[6], q1[6];
+                    pose_jac(rec[0], rec[1], rec[2], fx, fy, q0, q1);
+                    const double w = rec[5];
+                    int t = 0;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int c = r; c < 6; ++c) h[t++] += w * (q0[r] * q0[c] + q1[r] * q1[c]);
+                        g[r] += -w * (q0[r] * rec[3] + q1[r] * rec[4]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 21; ++t) {
+                    const double v = warp_sum(h[t]);
+                    if (lane == 0) out[t] = v;
+                }
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                    const double v = warp_sum(g[t]);
+                    if (lane == 0) out[21 + t] = v;
+                }
+            }
+            it += c_hi - c_lo;
+        }
+        __syncthreads();
+        // slots -> CTA partial vector: the warps that worked on a task are a contiguous range, added in warp order
+        for (int i = tid; i < (t_hi - t_lo) * kPairW; i += kT) {
+            const int trel = i / kPairW, e = i - trel * kPairW, task = t_lo + trel;
+            const bool pose = task >= n_pairs;
+            if (pose && e >= kPoseW) continue;
+            double v = 0;
+            if (per > 0) {
+                const int w_lo = (trel * n_chunks) / per, w_hi = min(kW - 1, ((trel + 1) * n_chunks - 1) / per);
+                for (int w = w_lo; w <= w_hi && n_chunks > 0; ++w) v += s_part[(size_t)(task + w) * kPairW + e];
+            }
+            s_x[pose ? poseBase + (task - n_pairs) * kPoseW + e : task * kPairW + e] = v;
+        }
+        __syncthreads();
+    };
+
+    // ---- prologue: first linearisation, lambda_0 = tau * max |diag H| (computeLambdaInit) ------------------------------
+    refresh_poses();
+    if (tid < n_kf)
+        for (int c = 0; c < 12; ++c) s_Rlin[tid][c] = s_R[tid][c];
+    if (tid < n_kf)
+        for (int c = 0; c < 6; ++c) s_backup[tid][c] = s_pose[tid][c];
+    __syncthreads();
+    int iters = 0, trials_total = 0;
+    double chi_first = 0, chi_last = 0, lambda = 0, ni = 2, rho = 0, currentChi = 0;
+    {
+        double chi, mx;
+        linearise(true, false, 0.0, &chi, &mx);
+        double dummy = 0;
+        block_sum2(chi, dummy, s_tmp);
+        mx = block_max(mx, s_tmp);
+        accumulate(n_pairs, n_pairs + np);
+        exchange_vector(poseBase, V);
+        if (tid == 0) {
+            s_small[0] = chi;
+            s_small[1] = 0;
+            s_small[2] = mx;
+            s_small[3] = s_dup;
+        }
+        exchange_small();
+        currentChi = chi_first = chi_last = s_bc[0];
+        double m0 = s_bc[2];
+        for (int f = 0; f < np; ++f) {
+            const double* h = s_x + poseBase + f * kPoseW;
+            const int diag[6] = {0, 6, 11, 15, 18, 20};
+            for (int c = 0; c < 6; ++c) m0 = fmax(m0, fabs(h[diag[c]]));
+        }
+        lambda = a.tau * m0;
+    }
+    const bool dup = s_bc[3] > 0;   // unsupported input: reported through stats, nothing is optimised
+
+    bool relin = false;   // the prologue has linearised iteration 0
+    for (int iteration = 0; iteration < a.max_iters && !dup; ++iteration) {
+        int qmax = 0;
+        do {
+            // ---- P1 / P2: (re)linearise if the state moved, invert Hll + lambda I, accumulate the reduced system
+            if (relin) {
+                if (tid < n_kf) {
+                    for (int c = 0; c < 12; ++c) s_Rlin[tid][c] = s_R[tid][c];
+                    for (int c = 0; c < 6; ++c) s_backup[tid][c] = s_pose[tid][c];
+                }
+                __syncthreads();
+            }
+            {
+                double chi, mx;
+                linearise(relin, true, lambda, &chi, &mx);
+            }
+            __syncthreads();
+            accumulate(0, relin ? n_pairs + np : n_pairs);
+            exchange_vector(0, relin ? V : poseBase);
+            relin = false;
+            // ---- P3: S = Hpp + lambda I - sum Hpl D Hpl^T, b_s = bp - sum Hpl D bl; dense Cholesky in every CTA (same bits)
+            for (int i = tid; i < dimp * dimp; i += kT) {
+                const int r = i / dimp, c = i - r * dimp, fr = r / 6, fc = c / 6, rr = r - 6 * fr, cc = c - 6 * fc;
+                double v;
+                if (fr <= fc) v = -s_x[(fr * np - fr * (fr - 1) / 2 + (fc - fr)) * kPairW + rr * 6 + cc];
+                else v = -s_x[(fc * np - fc * (fc - 1) / 2 + (fr - fc)) * kPairW + cc * 6 + rr];
+                if (fr == fc) {
+                    const int lo = min(rr, cc), hi = max(rr, cc);
+                    v += s_x[poseBase + fr * kPoseW + (lo * 6 - lo * (lo - 1) / 2 + (hi - lo))] + (r == c ? lambda : 0.0);
+                }
+                s_S[i] = v;
+            }
+            // (s_part aliases s_S: accumulate() consumed the slots before its final barrier)
+            if (tid < dimp) {
+                const int f = tid / 6, r = tid - 6 * f;
+                s_bs[tid] = s_x[poseBase + f * kPoseW + 21 + r] - s_x[(f * np - f * (f - 1) / 2) * kPairW + 36 + r];
+            }
+            if (tid == 0) s_ok = 1;
+            __syncthreads();
+            for (int j = 0; j < dimp; ++j) {
+                if (tid == 0) {
+                    const double d = s_S[j * dimp + j];
+                    if (!(d > 0)) s_ok = 0;
+                    s_S[j * dimp + j] = sqrt(d);
+                }
+                __syncthreads();
+                if (!s_ok) break;
+                const double djj = s_S[j * dimp + j];
+                const int rem = dimp - j - 1;
+                for (int e = tid; e < rem * rem; e += kT) {
+                    const int r = j + 1 + e / rem, c = j + 1 + e % rem;
+                    if (c <= r) s_S[r * dimp + c] -= (s_S[r * dimp + j] / djj) * (s_S[c * dimp + j] / djj);
+                }
+                __syncthreads();
+                for (int i = j + 1 + tid; i < dimp; i += kT) s_S[i * dimp + j] /= djj;
+            }
+            __syncthreads();
+            if (s_ok && warp == 0) {
+                for (int i = 0; i < dimp; ++i) {
+                    double s = 0;
+                    for (int k = lane; k < i; k += 32) s += s_S[i * dimp + k] * s_bs[k];
+                    s = warp_sum(s);
+                    if (lane == 0) s_bs[i] = (s_bs[i] - s) / s_S[i * dimp + i];
+                    __syncwarp();
+                }
+                for (int i = dimp - 1; i >= 0; --i) {
+                    double s = 0;
+                    for (int k = i + 1 + lane; k < dimp; k += 32) s += s_S[k * dimp + i] * s_bs[k];
+                    s = warp_sum(s);
+                    if (lane == 0) s_bs[i] = (s_bs[i] - s) / s_S[i * dimp + i];
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            const bool ok2 = s_ok != 0;
+            if (tid < dimp) s_xp[tid] = s_bs[tid];
+            __syncthreads();
+            // ---- P4a: VertexSE3Sophus::oplusImpl on the pose replica
+            if (tid < n_kf && s_free[tid] >= 0) {
+                const double* u = s_xp + 6 * s_free[tid];
+                const double v[6] = {u[3], u[4], u[5], u[0], u[1], u[2]};
+                const SE3d Tn = se3_mul(se3_exp(v), pose_from_g2o(s_pose[tid]));
+                double lg[6];
+                se3_log(Tn, lg);
+                s_pose[tid][0] = lg[3]; s_pose[tid][1] = lg[4]; s_pose[tid][2] = lg[5];
+                s_pose[tid][3] = lg[0]; s_pose[tid][4] = lg[1]; s_pose[tid][5] = lg[2];
+            }
+            __syncthreads();
+            refresh_poses();
+            // ---- P4b: landmark back-substitution + update, chi2 at the trial point, gain-ratio denominator
+            double chi_part = 0, scale = 0;
+            for (int jj = tid; jj < nl; jj += kT) {
+                const int gj = p0 + j_lo + jj;
+                const int qa = a.lm_start[gj], qb = a.lm_start[gj + 1];
+                const double* bj = st.bl + 3 * jj;
+                double r[3] = {bj[0], bj[1], bj[2]};
+                for (int q = qa; q < qb; ++q) {
+                    const int kf = a.so_kf[q], fi = s_free[kf];
+                    if (fi < 0) continue;
+                    double H1[6][3];
+                    make_hpl(st.lin + 6 * (size_t)(q - q_lo), s_Rlin[kf], fx, fy, H1);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int rr = 0; rr < 6; ++rr) r[c] -= H1[rr][c] * s_xp[6 * fi + rr];
+                }
+                double xl[3];
+                sym_mul3(st.Dinv + 6 * jj, r, xl);
+                double X[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    scale += xl[c] * (lambda * xl[c] + bj[c]);
+                    X[c] = st.Xb[3 * jj + c] + xl[c];
+                    a.pts[3 * (size_t)gj + c] = X[c];
+                }
+                for (int q = qa; q < qb; ++q) {
+                    double x, y, z, e0, e1, w;
+                    reproject(q, X[0], X[1], X[2], &x, &y, &z, &e0, &e1);
+                    chi_part += robust(e0 * e0 + e1 * e1, &w);
+                }
+            }
+            if (rank == 0 && tid < dimp) {
+                const int f = tid / 6, rr = tid - 6 * f;
+                scale += s_xp[tid] * (lambda * s_xp[tid] + s_x[poseBase + f * kPoseW + 21 + rr]);
+            }
+            block_sum2(chi_part, scale, s_tmp);
+            if (tid == 0) {
+                s_small[0] = chi_part;
+                s_small[1] = scale;
+                s_small[2] = 0;
+                s_small[3] = 0;
+            }
+            exchange_small();
+            double tempChi = s_bc[0];
+            const double scale_tot = s_bc[1] + 1e-3;
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            rho = (currentChi - tempChi) / scale_tot;
+            bool accept;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+                accept = true;
+                relin = true;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                accept = false;
+            }
+            if (!accept) {  // _optimizer->pop(): back to the linearisation point
+                if (tid < n_kf)
+                    for (int c = 0; c < 6; ++c) s_pose[tid][c] = s_backup[tid][c];
+                for (int jj = tid; jj < nl; jj += kT)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a.pts[3 * (size_t)(p0 + j_lo + jj) + c] = st.Xb[3 * jj + c];
+                __syncthreads();
+                refresh_poses();
+            }
+            ++qmax;
+            ++trials_total;
+        } while (rho < 0 && qmax < a.max_trials);
+        ++iters;
+        chi_last = currentChi;
+        if (qmax == a.max_trials || rho == 0) break;
+    }
+    // ---- outlier flags (BA.cpp:505-515): plain chi2 > 5.991 at the final estimate
+    cluster.sync();   // the last exchange_small may still be read by a neighbour: s_small is rewritten below
+    double n_out = 0, zero = 0;
+    for (int jj = tid; jj < nl; jj += kT) {
+        const int gj = p0 + j_lo + jj;
+        const double X0 = a.pts[3 * (size_t)gj], X1 = a.pts[3 * (size_t)gj + 1], X2 = a.pts[3 * (size_t)gj + 2];
+        for (int q = a.lm_start[gj]; q < a.lm_start[gj + 1]; ++q) {
+            double x, y, z, e0, e1;
+            reproject(q, X0, X1, X2, &x, &y, &z, &e0, &e1);
+            const int out = (e0 * e0 + e1 * e1 > a.chi2_outlier) ? 1 : 0;
+            a.outlier[a.so_orig ? a.so_orig[q] : q] = (uint8_t)out;
+            n_out += out;
+        }
+    }
+    block_sum2(n_out, zero, s_tmp);
+    if (tid == 0) {
+        s_small[0] = n_out;
+        s_small[1] = s_small[2] = s_small[3] = 0;
+    }
+    exchange_small();
+    if (rank == 0) {
+        if (tid < n_kf)
+            for (int c = 0; c < 6; ++c) a.poses[6 * (size_t)(k0 + tid) + c] = s_pose[tid][c];
+        if (tid == 0) {
+            double* stt = a.stats + 8 * (size_t)prob;
+            stt[0] = iters; stt[1] = trials_total; stt[2] = chi_first; stt[3] = chi_last; stt[4] = lambda; stt[5] = s_bc[0];
+            stt[6] = dup ? 1.0 : 0.0; stt[7] = 0;
+        }
+    }
+    cluster.sync();   // no CTA may exit while another still reads its shared memory
+}
+
+// ---- landmark-major observation lists built on the device ---------------------------------------------------------
+__global__ void csr_count_kernel(int n_problems, const int32_t* __restrict__ obs_off, const int32_t* __restrict__ pt_off,
+                                 const int32_t* __restrict__ pt_idx, int32_t* __restrict__ cnt) {
+    const int p = blockIdx.y;
+    const int o0 = obs_off[p], no = obs_off[p + 1] - o0;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < no; o += gridDim.x * blockDim.x) atomicAdd(&cnt[pt_off[p] + pt_idx[o0 + o]], 1);
+}
+
+// one CTA per problem: exclusive scan of the counts -> lm_start, scatter of the observation ids, sort of every landmark's
+// short list by original id (deterministic order), gather of (pose index, pixel)
+__global__ void __launch_bounds__(1024) csr_build_kernel(const int32_t* __restrict__ obs_off, const int32_t* __restrict__ pt_off,
+                                                         const int32_t* __restrict__ kf_idx, const int32_t* __restrict__ pt_idx,
+                                                         const double* __restrict__ obs, int32_t* __restrict__ cnt,
+                                                         int32_t* __restrict__ lm_start, int32_t* __restrict__ so_orig,
+                                                         int32_t* __restrict__ so_kf, double* __restrict__ so_uv, int last) {
+    __shared__ int s_scan[1024];
+    __shared__ int s_carry;
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const int o0 = obs_off[p], no = obs_off[p + 1] - o0, p0 = pt_off[p], npt = pt_off[p + 1] - p0;
+    if (tid == 0) s_carry = o0;
+    __syncthreads();
+    for (int base = 0; base < npt; base += 1024) {
+        const int j = base + tid;
+        const int c = j < npt ? cnt[p0 + j] : 0;
+        s_scan[tid] = c;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+            const int v = tid >= o ? s_scan[tid - o] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const int start = s_carry + s_scan[tid] - c;
+        if (j < npt) {
+            lm_start[p0 + j] = start;
+            cnt[p0 + j] = start;   // becomes the fill cursor
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry += s_scan[1023];
+        __syncthreads();
+    }
+    // end of the problem's last list; for all but the last problem this is also the first start of the next problem (same
+    // value, written by both CTAs)
+    if (tid == 0) lm_start[p0 + npt] = o0 + no;
+    (void)last;
+    for (int o = tid; o < no; o += 1024) so_orig[atomicAdd(&cnt[p0 + pt_idx[o0 + o]], 1)] = o0 + o;
+    __syncthreads();
+    for (int j = tid; j < npt; j += 1024) {
+        const int qa = lm_start[p0 + j], qb = cnt[p0 + j];   // the cursor ended at the end of the list
+        for (int i = qa + 1; i < qb; ++i) {
+            const int v = so_orig[i];
+            int k = i - 1;
+            while (k >= qa && so_orig[k] > v) {
+                so_orig[k + 1] = so_orig[k];
+                --k;
+            }
+            so_orig[k + 1] = v;
+        }
+        for (int i = qa; i < qb; ++i) {
+            const int o = so_orig[i];
+            so_kf[i] = kf_idx[o];
+            so_uv[2 * (size_t)i] = obs[2 * (size_t)o];
+            so_uv[2 * (size_t)i + 1] = obs[2 * (size_t)o + 1];
+        }
+    }
+}
+
+}  // namespace
+
+size_t ba2_scratch_bytes(size_t NP, size_t NO, size_t P) {
+    Carver sz(nullptr);
+    sz.take<int32_t>(NP + 1); sz.take<int32_t>(NP + 1); sz.take<int32_t>(NO); sz.take<int32_t>(NO); sz.take<double>(2 * NO);
+    sz.take<double>(6 * NO); sz.take<double>(6 * NP); sz.take<double>(3 * NP); sz.take<double>(6 * NP); sz.take<double>(3 * NP);
+    sz.take<uint8_t>(NP * kBA2MaxFree); sz.take<uint8_t>(NO); sz.take<double>(8 * P);
+    return sz.bytes();
+}
+
+// Device-to-device entry: everything in `in` is a device pointer.  Builds the landmark-major lists, runs the cluster
+// kernel, leaves poses / pts / outlier / stats on the device.  max_pts / max_free bound the problems of the batch.
+int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const ygzb_ba_params* prm, uint8_t** d_outlier_out,
+                     double** d_stats_out) {
+    const size_t P = (size_t)in.n_problems, NP = in.total_pts, NO = in.total_obs;
+    Carver c(scratch);
+    int32_t* d_cnt = c.take<int32_t>(NP + 1);
+    int32_t* d_lm_start = c.take<int32_t>(NP + 1);
+    int32_t* d_so_orig = c.take<int32_t>(NO);
+    int32_t* d_so_kf = c.take<int32_t>(NO);
+    double* d_so_uv = c.take<double>(2 * NO);
+    BA2Args a;
+    a.lin = c.take<double>(6 * NO);
+    a.Hll = c.take<double>(6 * NP);
+    a.bl = c.take<double>(3 * NP);
+    a.Dinv = c.take<double>(6 * NP);
+    a.pts_backup = c.take<double>(3 * NP);
+    a.slot = c.take<uint8_t>(NP * kBA2MaxFree);
+    a.outlier = c.take<uint8_t>(NO);
+    a.stats = c.take<double>(8 * P);
+    if (in.lm_start) {   // the caller already has landmark-major lists (the tracking engine builds them itself)
+        a.lm_start = in.lm_start; a.so_kf = in.kf_idx; a.so_uv = in.obs; a.so_orig = nullptr;
+    } else {
+        YGZB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, (NP + 1) * sizeof(int32_t), ctx->stream));
+        if (NO) {
+            ProfScope ps(ctx, kStageOther);
+            const dim3 grid((unsigned)std::min<size_t>((in.max_obs + 255) / 256, 64), (unsigned)P);
+            csr_count_kernel<<<grid, 256, 0, ctx->stream>>>((int)P, in.obs_off, in.pt_off, in.pt_idx, d_cnt);
+            YGZB_LAUNCHED(ctx);
+        }
+        {
+            ProfScope ps(ctx, kStageOther);
+            csr_build_kernel<<<(unsigned)P, 1024, 0, ctx->stream>>>(in.obs_off, in.pt_off, in.kf_idx, in.pt_idx, in.obs, d_cnt, d_lm_start,
+                                                                    d_so_orig, d_so_kf, d_so_uv, (int)P - 1);
+            YGZB_LAUNCHED(ctx);
+        }
+        a.lm_start = d_lm_start; a.so_kf = d_so_kf; a.so_uv = d_so_uv; a.so_orig = d_so_orig;
+    }
+    a.kf_off = in.kf_off; a.pt_off = in.pt_off; a.obs_off = in.obs_off;
+    a.n_kf = in.n_kf; a.n_pt = in.n_pt;
+    a.poses = in.poses; a.fixed = in.fixed; a.pts = in.pts;
+    a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
+    a.max_iters = prm->max_iters; a.max_trials = prm->max_trials; a.huber_delta = prm->huber_delta;
+    a.chi2_outlier = prm->chi2_outlier; a.tau = prm->tau;
+
+    // cluster size: ~300 landmarks per CTA keep a problem's per-landmark state in shared memory and its FP64 work spread
+    int cluster = 1;
+    while (cluster < 8 && in.max_pts > (size_t)cluster * 320) cluster *= 2;
+    if (const char* e = getenv("YGZB_BA_CLUSTER")) {   // tuning knob: 1, 2, 4 or 8
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v;
+    }
+    const int np = std::max(in.max_free, 0), dimp = 6 * np, n_pairs = np * (np + 1) / 2;
+    const int V = kPairW * n_pairs + kPoseW * np;
+    const size_t sys = std::max<size_t>((size_t)dimp * dimp + dimp, (size_t)(n_pairs + np + kW) * kPairW);
+    const size_t nl = (in.max_pts + cluster - 1) / cluster;
+    const size_t no = std::min<size_t>(in.max_obs, nl * (size_t)std::max(in.max_kf, 1));
+    const size_t stage = 6 * no + 18 * nl + (nl * kBA2MaxFree + 7) / 8 + 2;
+    static int max_optin = 0;
+    static std::once_flag once;
+    std::call_once(once, [&] {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncSetAttribute(local_ba2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 24 * 1024);
+    });
+    const size_t cap = (size_t)std::max(0, max_optin - 24 * 1024) / sizeof(double);   // the kernel's static arrays use ~22 KB
+    if (sys + 2 * (size_t)V > cap) return set_error(ctx, YGZB_ERR_CAPACITY, "local BA: %d free poses do not fit shared memory", np);
+    const size_t dyn = std::min(cap, sys + 2 * (size_t)V + stage);
+    a.dyn_doubles = (long long)dyn;
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(P * cluster));
+    cfg.blockDim = dim3(kT);
+    cfg.dynamicSmemBytes = dyn * sizeof(double);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    {
+        ProfScope ps(ctx, kStageLocalBA);
+        YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, local_ba2_kernel, a));
+    }
+    YGZB_LAUNCHED(ctx);
+    if (d_outlier_out) *d_outlier_out = a.outlier;
+    if (d_stats_out) *d_stats_out = a.stats;
+    return YGZB_OK;
+}
+
+}  // namespace ygzb

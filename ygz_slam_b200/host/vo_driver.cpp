@@ -513,10 +513,232 @@ class Driver {
     std::vector<uint8_t> klevel_, kdesc_;
 };
 
+
+// ---- device-resident engine --------------------------------------------------------------------------------------------
+// The same caller logic on ygzb_tracker_*: the local map lives on the device, a ROUND enqueues for every stream a window of
+// consecutive frames -- up to and including the first frame that may become a key-frame (a frame is tracked against the
+// reference key-frame, never against its predecessor: VisualOdometry.cpp:66, so the frames of a window are independent) --
+// as ONE fused chain (upload + pyramid, sparse alignment, candidate projection, direct projection, pose-only), reads one
+// 128-byte record per frame back, takes the key-frame decisions, and inserts the key-frames of the round (Detect, map
+// points, local BA, all on the device) with one more enqueue.  Results are identical to frame-by-frame processing.
+struct KfInfo {
+    int entry = 0, n = 0, frame_id = 0;
+    Mat34 T;
+    long mp0 = 0;
+};
+struct EStream {
+    std::deque<KfInfo> kfs;   // at most YGZB_TRACK_RING, the newest is the reference key-frame; the last kLocalKeyframes are local
+    Mat34 T = identity();
+    bool has_pose = false, lost = false;
+    int frames_since_kf = 0, next_frame = 0;
+    long next_mp = 0;
+    long n_keyframes = 0, n_ba = 0, n_candidates = 0, n_projected = 0, n_inliers = 0;
+    long ba_obs = 0, ba_pts = 0, ba_kfs = 0, ba_trials = 0, ba_iters = 0;
+    double ba_flops = 0;
+};
+
+class Engine {
+  public:
+    Engine(ygzb_ctx* ctx, int n_streams, int window, const Params& p) : ctx_(ctx), S_(n_streams), F_(std::max(1, window)), prm_(p), st_(n_streams) {}
+    ~Engine() {
+        if (tr_) ygzb_tracker_destroy(tr_);
+        if (fr_) ygzb_frames_destroy(fr_);
+        if (h_res_) ygzb_host_free(h_res_);
+        if (h_kres_) ygzb_host_free(h_kres_);
+    }
+    int init(const double* const* depth) {
+        CHK(ygzb_frames_create(ctx_, S_ * F_ + S_ * YGZB_TRACK_RING, &fr_));
+        const double K[4] = {FX, FY, CX, CY};
+        CHK(ygzb_tracker_create(fr_, S_, S_ * F_, K, &tr_));
+        for (int i = 0; i < S_; ++i) CHK(ygzb_tracker_set_depth(tr_, i, depth[i]));
+        void* p = nullptr;
+        CHK(ygzb_host_alloc(&p, sizeof(ygzb_track_result) * (size_t)S_ * F_));
+        h_res_ = static_cast<ygzb_track_result*>(p);
+        CHK(ygzb_host_alloc(&p, sizeof(ygzb_keyframe_result) * (size_t)S_));
+        h_kres_ = static_cast<ygzb_keyframe_result*>(p);
+        ygzb_default_ba_params(&ba_);
+        return YGZB_OK;
+    }
+    std::vector<EStream>& streams() { return st_; }
+    bool all_reached(int frame) const {
+        for (const EStream& s : st_)
+            if (s.next_frame < frame) return false;
+        return true;
+    }
+    long long h2d_image_bytes = 0, h2d_other_bytes = 0, d2h_bytes = 0;
+
+    // one round; frames are taken from images[i] + frame * W * H; `limit` = no window crosses this frame index
+    int round(const uint8_t* const* images, int n_frames, int limit, double* traj /* this group's [S][n_frames][12] */) {
+        struct Win { int stream, first, count, job0; };
+        std::vector<Win> boot, track;
+        std::vector<ygzb_track_job> jobs;
+        for (int i = 0; i < S_; ++i) {
+            EStream& s = st_[i];
+            if (s.next_frame >= n_frames) continue;
+            const int stop = s.next_frame < limit ? limit : n_frames;
+            if (s.lost) {   // the reference keeps the last pose and reports VO_LOST
+                for (int k = s.next_frame; k < stop; ++k) put_pose(traj, i, n_frames, k, s);
+                s.next_frame = stop;
+                continue;
+            }
+            int w = 1;
+            if (!s.kfs.empty()) w = std::min(F_, std::max(1, prm_.kf_min_frames - s.frames_since_kf));
+            w = std::min(w, stop - s.next_frame);
+            CHK(ygzb_frames_upload(fr_, i * F_, w, images[i] + (size_t)s.next_frame * W * H, 1, (size_t)W * H));
+            h2d_image_bytes += (long long)w * W * H;
+            if (s.kfs.empty()) {
+                boot.push_back({i, s.next_frame, 1, -1});
+                continue;
+            }
+            track.push_back({i, s.next_frame, w, (int)jobs.size()});
+            const int nl = std::min(kLocalKeyframes, (int)s.kfs.size());
+            for (int t = 0; t < w; ++t) {
+                ygzb_track_job j{};
+                j.stream = i;
+                j.cur_slot = i * F_ + t;
+                j.n_local = nl;
+                for (int k = 0; k < nl; ++k) j.entry[k] = s.kfs[s.kfs.size() - nl + k].entry;
+                jobs.push_back(j);
+            }
+        }
+        std::vector<ygzb_keyframe_job> kjobs;
+        std::vector<int> kframe;   // frame index of every key-frame job
+        for (const Win& b : boot) {
+            EStream& s = st_[b.stream];
+            s.T = identity();
+            s.has_pose = true;
+            kjobs.push_back(make_kf_job(b.stream, b.stream * F_, -1));
+            kframe.push_back(b.first);
+        }
+        if (!jobs.empty()) {
+            StageTimer tm(kTSparse);
+            CHK(ygzb_tracker_track(tr_, (int)jobs.size(), jobs.data(), h_res_));
+            CHK(ygzb_synchronize(ctx_));
+            h2d_other_bytes += (long long)(jobs.size() * sizeof(ygzb_track_job));
+            d2h_bytes += (long long)(jobs.size() * sizeof(ygzb_track_result));
+        }
+        for (const Win& b : track) {
+            EStream& s = st_[b.stream];
+            int t = 0;
+            for (; t < b.count; ++t) {
+                const ygzb_track_result& r = h_res_[b.job0 + t];
+                if (!r.aligned) {   // Matcher::SparseImageAlignment returned false (Matcher.cpp:482-488)
+                    s.lost = true;
+                    break;
+                }
+                s.n_candidates += r.n_candidates;
+                s.n_projected += r.n_projected;
+                if (r.n_inliers < kMinInliers) {
+                    s.lost = true;
+                    break;
+                }
+                std::memcpy(s.T.m, r.T_cw, sizeof(s.T.m));
+                s.frames_since_kf += 1;
+                s.n_inliers += r.n_inliers;
+                put_pose(traj, b.stream, n_frames, b.first + t, s);
+                // NeedNewKeyFrame (VisualOdometry.cpp:304-321)
+                if (s.frames_since_kf < prm_.kf_min_frames) continue;
+                double d[6];
+                se3_log(mul(s.T, inv(s.kfs.back().T)), d);
+                const double rot = std::sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]), tr = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                if (rot > prm_.kf_min_rot || tr > prm_.kf_min_trans) {
+                    kjobs.push_back(make_kf_job(b.stream, b.stream * F_ + t, b.job0 + t));
+                    kframe.push_back(b.first + t);
+                    ++t;
+                    break;   // (by construction the last frame of the window)
+                }
+            }
+            if (s.lost) {
+                put_pose(traj, b.stream, n_frames, b.first + t, s);
+                s.next_frame = b.first + t + 1;
+            } else {
+                s.next_frame = b.first + t;
+            }
+        }
+        for (const Win& b : boot) st_[b.stream].next_frame = b.first + 1;
+        if (!kjobs.empty()) {
+            StageTimer tm(kTLocalBA);
+            CHK(ygzb_tracker_make_keyframes(tr_, (int)kjobs.size(), kjobs.data(), &ba_, h_kres_));
+            CHK(ygzb_synchronize(ctx_));
+            h2d_other_bytes += (long long)(kjobs.size() * (sizeof(ygzb_keyframe_job) + 4));
+            d2h_bytes += (long long)(kjobs.size() * sizeof(ygzb_keyframe_result));
+            for (size_t q = 0; q < kjobs.size(); ++q) {
+                const ygzb_keyframe_job& kj = kjobs[q];
+                const ygzb_keyframe_result& r = h_kres_[q];
+                EStream& s = st_[kj.stream];
+                KfInfo kf;
+                kf.entry = kj.entry;
+                kf.n = r.n_features;
+                kf.frame_id = kframe[q];
+                kf.mp0 = kj.mp0;
+                s.next_mp = kj.mp0 + r.n_features;
+                s.kfs.push_back(kf);
+                while ((int)s.kfs.size() > YGZB_TRACK_RING) s.kfs.pop_front();
+                for (int k = 0; k < kj.n_local; ++k) std::memcpy(s.kfs[s.kfs.size() - kj.n_local + k].T.m, r.T_cw[k], sizeof(Mat34));
+                s.T = s.kfs.back().T;
+                s.frames_since_kf = 0;
+                s.n_keyframes += 1;
+                if (kj.run_ba && kj.n_local >= 2) {
+                    s.n_ba += 1;
+                    s.ba_obs += r.ba_observations; s.ba_pts += r.ba_points; s.ba_kfs += kj.n_local; s.ba_trials += r.ba_trials; s.ba_iters += r.ba_iters;
+                    const double kbar = r.ba_points ? (double)r.ba_observations / r.ba_points : 0.0, dim = 6.0 * (kj.n_local - 1);
+                    s.ba_flops += r.ba_trials * (300.0 * r.ba_observations + r.ba_points * (216.0 * kbar * kbar + 108.0 * kbar + 50.0) + dim * dim * dim / 3.0);
+                }
+                put_pose(traj, kj.stream, n_frames, kframe[q], s);
+            }
+        }
+        return YGZB_OK;
+    }
+
+  private:
+    void put_pose(double* traj, int stream, int n_frames, int frame, const EStream& s) const {
+        if (!traj) return;
+        double* out = traj + ((size_t)stream * n_frames + frame) * 12;
+        for (int c = 0; c < 12; ++c) out[c] = s.has_pose ? s.T.m[c] : NAN;
+    }
+    ygzb_keyframe_job make_kf_job(int stream, int frame_slot, int track_job) const {
+        const EStream& s = st_[stream];
+        ygzb_keyframe_job kj{};
+        kj.stream = stream;
+        kj.frame_slot = frame_slot;
+        kj.track_job = track_job;
+        // ring entry: one that none of the key-frames that stay local uses (the oldest of a full ring leaves the map)
+        const int keep = std::min(kLocalKeyframes, (int)s.kfs.size());
+        for (int e = 0; e < YGZB_TRACK_RING; ++e) {
+            bool used = false;
+            for (int k = 0; k < keep; ++k) used |= s.kfs[s.kfs.size() - 1 - k].entry == e;
+            if (!used) {
+                kj.entry = e;
+                break;
+            }
+        }
+        kj.kf_slot = S_ * F_ + stream * YGZB_TRACK_RING + kj.entry;
+        const int nl = std::min(kLocalKeyframes, (int)s.kfs.size() + 1);
+        kj.n_local = nl;
+        for (int k = 0; k < nl - 1; ++k) kj.local_entry[k] = s.kfs[s.kfs.size() - (nl - 1) + k].entry;
+        kj.local_entry[nl - 1] = kj.entry;
+        kj.run_ba = (track_job >= 0 && nl >= 2) ? 1 : 0;
+        kj.mp0 = s.next_mp;
+        return kj;
+    }
+
+    ygzb_ctx* ctx_;
+    ygzb_frames* fr_ = nullptr;
+    ygzb_tracker* tr_ = nullptr;
+    int S_, F_;
+    Params prm_;
+    std::vector<EStream> st_;
+    ygzb_track_result* h_res_ = nullptr;
+    ygzb_keyframe_result* h_kres_ = nullptr;
+    ygzb_ba_params ba_;
+};
+
 }  // namespace
 
 extern "C" {
 
+// PER-STAGE PATH: every numeric step is one blocking C-ABI call with host buffers (the reference's call granularity);
+// kept as the cross-check of the device-resident engine below (tests/test_vo.py) and as a diagnostic of bench.py.
 // Tracks n_streams independent 640x480 grey streams in lock step for n_frames frames.  The streams are split over
 // n_threads host threads; thread 0 drives the caller's context, every further thread creates its own context (= its
 // own CUDA stream) on the same device with the same parameters, so the kernels of one group overlap the host work and
@@ -531,7 +753,7 @@ extern "C" {
 //               barrier before frame `warm` and after the last frame)
 //   device_ms : (may be NULL) the same region timed with CUDA events on the caller's context stream: first event after
 //               the warm-up barrier, second one after every thread has synchronised its stream
-int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threads, int n_streams, int n_frames,
+int ygz_vo_run_stages(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threads, int n_streams, int n_frames,
                const uint8_t* const* images, const double* const* depth, int kf_min_frames, double kf_min_rot, double kf_min_trans,
                int warm, double* traj, int64_t* stats, double* seconds, double* device_ms, int64_t* totals) {
     if (!ctx || !params || n_streams < 1 || n_frames < 1 || !images || !depth || !traj || !stats || !seconds) return YGZB_ERR_INVALID;
@@ -610,6 +832,82 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
         fprintf(stderr, "[ygz_vo] %d streams on %d host threads x %d timed frames: %.3f ms per lock-step frame; C-ABI time summed over threads %.3f ms\n",
                 n_streams, n_threads, timed, 1e3 * *seconds / timed, 1e3 * sum / timed);
         for (int i = 0; i < kTStages; ++i) fprintf(stderr, "[ygz_vo]   %-14s %.3f ms/frame\n", names[i], 1e-6 * g_stage_ns[i].load() / timed);
+    }
+    for (int rc : rcs)
+        if (rc != YGZB_OK) return rc;
+    return YGZB_OK;
+}
+
+
+// Device-resident engine (see Engine above).  Same arguments as ygz_vo_run_stages plus
+//   window : frames of one stream that may be in flight in one round (1 = one frame at a time, the latency mode);
+// frames [0, warm) are processed before the timed region starts (no window crosses frame `warm`).
+int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threads, int n_streams, int n_frames,
+               const uint8_t* const* images, const double* const* depth, int kf_min_frames, double kf_min_rot, double kf_min_trans,
+               int warm, int window, double* traj, int64_t* stats, double* seconds, double* device_ms, int64_t* totals) {
+    if (!ctx || !params || n_streams < 1 || n_frames < 1 || !images || !depth || !traj || !stats || !seconds) return YGZB_ERR_INVALID;
+    n_threads = std::max(1, std::min(n_threads, n_streams));
+    warm = std::max(0, std::min(warm, n_frames - 1));
+    for (auto& v : g_stage_ns) v.store(0);
+    std::vector<int> rcs(n_threads, YGZB_OK);
+    std::vector<std::vector<long long>> tot(n_threads, std::vector<long long>(4, 0));
+    std::barrier sync_point(n_threads);
+    std::chrono::steady_clock::time_point t_begin, t_end;
+    auto worker = [&](int t) {
+        const int s0 = (int)((long)n_streams * t / n_threads), s1 = (int)((long)n_streams * (t + 1) / n_threads), ns = s1 - s0;
+        ygzb_ctx* my = ctx;
+        int rc = YGZB_OK;
+        if (t > 0) rc = ygzb_create(device, params, &my);
+        {
+            Engine eng(my, ns, window, Params{kf_min_frames, kf_min_rot, kf_min_trans});
+            if (rc == YGZB_OK) rc = eng.init(depth + s0);
+            double* my_traj = traj + (size_t)s0 * n_frames * 12;
+            while (rc == YGZB_OK && !eng.all_reached(warm)) rc = eng.round(images + s0, n_frames, warm, my_traj);
+            if (rc == YGZB_OK) ygzb_synchronize(my);
+            tot[t][0] = -ygzb_launch_count(my);
+            eng.h2d_image_bytes = eng.h2d_other_bytes = eng.d2h_bytes = 0;
+            sync_point.arrive_and_wait();
+            if (t == 0) {
+                t_begin = std::chrono::steady_clock::now();
+                for (auto& v : g_stage_ns) v.store(0);
+                ygzb_timer_start(ctx);
+            }
+            while (rc == YGZB_OK && !eng.all_reached(n_frames)) rc = eng.round(images + s0, n_frames, n_frames, my_traj);
+            if (rc == YGZB_OK) ygzb_synchronize(my);
+            tot[t][0] += ygzb_launch_count(my);
+            tot[t][1] = eng.h2d_image_bytes; tot[t][2] = eng.h2d_other_bytes; tot[t][3] = eng.d2h_bytes;
+            sync_point.arrive_and_wait();
+            if (t == 0) {
+                double ms = 0;
+                if (ygzb_timer_stop(ctx, &ms) == YGZB_OK && device_ms) *device_ms = ms;
+                t_end = std::chrono::steady_clock::now();
+            }
+            for (int s = 0; s < ns; ++s) {
+                const EStream& st = eng.streams()[s];
+                int64_t* o = stats + 16 * (size_t)(s0 + s);
+                for (int c = 0; c < 16; ++c) o[c] = 0;
+                o[0] = st.lost; o[1] = st.n_keyframes; o[2] = st.n_ba; o[3] = st.n_candidates; o[4] = st.n_projected; o[5] = st.n_inliers;
+                o[6] = st.ba_obs; o[7] = st.ba_pts; o[8] = st.ba_kfs; o[9] = st.ba_trials; o[10] = st.ba_iters; o[11] = (int64_t)st.ba_flops;
+            }
+        }   // (the engine releases its tracker and frame slots before the context goes)
+        if (t > 0 && my) ygzb_destroy(my);
+        rcs[t] = rc;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
+    *seconds = std::chrono::duration<double>(t_end - t_begin).count();
+    if (totals) {
+        for (int c = 0; c < 8; ++c) totals[c] = 0;
+        for (int t = 0; t < n_threads; ++t)
+            for (int c = 0; c < 4; ++c) totals[c] += tot[t][c];
+    }
+    if (getenv("YGZ_VO_TIMING")) {
+        const int timed = n_frames - warm;
+        fprintf(stderr, "[ygz_vo engine] %d streams on %d host threads, window %d, %d timed frames: %.3f ms per frame index; track rounds %.3f ms, "
+                        "key-frame rounds %.3f ms (host wall, summed over threads)\n",
+                n_streams, n_threads, window, timed, 1e3 * *seconds / timed, 1e-6 * g_stage_ns[kTSparse].load(), 1e-6 * g_stage_ns[kTLocalBA].load());
     }
     for (int rc : rcs)
         if (rc != YGZB_OK) return rc;
