@@ -92,27 +92,37 @@ __device__ double block_max(double v, double* s_tmp) {
     return s_tmp[kW];
 }
 
+// 1 / x for positive, normal x: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps; within 1-2 ulp of the IEEE
+// quotient at a fraction of the latency of the division sequence (the serial solve of an LM trial is latency bound)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
 __device__ __forceinline__ SE3d pose_from_g2o(const double* est) {
     const double v[6] = {est[3], est[4], est[5], est[0], est[1], est[2]};
     return se3_exp(v);
 }
 
-// Jacobians of EdgeSophusSE3ProjectXYZ::linearizeOplus (G2oTypes.h:108-131) rebuilt from the camera-frame point (x, y, z)
-// and the rotation rows of the pose at the linearisation point
+// Jacobians of EdgeSophusSE3ProjectXYZ::linearizeOplus (G2oTypes.h:108-131) rebuilt from the camera-frame point (x, y, 1/z)
+// and the rotation rows of the pose at the linearisation point (the record keeps 1/z: no division when they are rebuilt)
 struct Jac {
     double l0[3], l1[3];   // d e / d landmark, rows u and v
     double p0[6], p1[6];   // d e / d pose ([omega; upsilon] order of VertexSE3Sophus)
 };
-__device__ __forceinline__ void pose_jac(double x, double y, double z, double fx, double fy, double* p0, double* p1) {
-    const double iz = 1.0 / z, iz2 = iz * iz;
+__device__ __forceinline__ void pose_jac(double x, double y, double iz, double fx, double fy, double* p0, double* p1) {
+    const double iz2 = iz * iz;
     p0[0] = x * y * iz2 * fx; p0[1] = -(1.0 + x * x * iz2) * fx; p0[2] = y * iz * fx;
     p0[3] = -iz * fx; p0[4] = 0.0; p0[5] = x * iz2 * fx;
     p1[0] = (1.0 + y * y * iz2) * fy; p1[1] = -x * y * iz2 * fy; p1[2] = -x * iz * fy;
     p1[3] = 0.0; p1[4] = -iz * fy; p1[5] = y * iz2 * fy;
 }
-__device__ __forceinline__ void point_jac(double x, double y, double z, double fx, double fy, const double* R /* 12: [R|t] rows */,
+__device__ __forceinline__ void point_jac(double x, double y, double iz_pos, double fx, double fy, const double* R /* 12: [R|t] rows */,
                                           double* l0, double* l1) {
-    const double iz = -1.0 / z;
+    const double iz = -iz_pos;
     const double t02 = x * iz * fx, t12 = y * iz * fy;   // -x/z fx, -y/z fy
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -121,7 +131,7 @@ __device__ __forceinline__ void point_jac(double x, double y, double z, double f
     }
 }
 // Hpl = w Jp^T Jl (6 x 3)
-__device__ __forceinline__ void make_hpl(const double* rec /* x y z e0 e1 w */, const double* R, double fx, double fy, double H[6][3]) {
+__device__ __forceinline__ void make_hpl(const double* rec /* x y 1/z e0 e1 w */, const double* R, double fx, double fy, double H[6][3]) {
     double p0[6], p1[6], l0[3], l1[3];
     pose_jac(rec[0], rec[1], rec[2], fx, fy, p0, p1);
     point_jac(rec[0], rec[1], rec[2], fx, fy, R, l0, l1);
@@ -147,25 +157,104 @@ __device__ __forceinline__ void sym_mul3(const double* s, const double* v, doubl
     out[2] = s[2] * v[0] + s[4] * v[1] + s[5] * v[2];
 }
 
+// doubles of the CTA-private staging area for nl landmarks with no observations (see Stage): 14 per observation (two
+// 6-double records + pixel) + 30 per landmark + the int / byte tables, rounded up
+__host__ __device__ inline size_t ba2_stage_doubles(size_t nl, size_t no) {
+    return 14 * no + 30 * nl + ((nl + 1) * 4 + ((no + 7) & ~(size_t)7) + nl * kBA2MaxFree + 7) / 8 + 1;
+}
+
 struct Stage {   // CTA-private per-landmark / per-observation state: shared memory when it fits, else global scratch
-    double* lin;     // [no][6]  x y z e0 e1 w
-    double* Hll;     // [nl][6]
-    double* bl;      // [nl][3]
-    double* Dinv;    // [nl][6]
-    double* Xb;      // [nl][3]  landmark positions at the linearisation point (push / pop)
+    double* lin[2];  // [no][6]  x y z e0 e1 w   (double buffered: accepted state / trial state)
+    double* Hll[2];  // [nl][6]
+    double* bl[2];   // [nl][3]
+    double* X[2];    // [nl][3]  landmark positions of the accepted state / of the trial
+    double* Dinv;    // [nl][6]  (Hll + lambda I)^-1 of the accepted state at the trial's lambda
+    double* uv;      // [no][2]  measured pixels (copy of so_uv: read every trial)
+    int32_t* qa;     // [nl + 1] first observation of every landmark, relative to the CTA's first observation
+    uint8_t* kf;     // [no]     pose index of every observation
     uint8_t* slot;   // [nl][kBA2MaxFree]  position of the landmark's observation on free pose f inside its list, 0xFF = none
 };
+
+// S x = b for a symmetric positive definite S by ONE warp: LDL^T in place (unit lower triangle below the diagonal, D on it),
+// lane i owns rows i, i + 32, i + 64 (left-looking: a row's dot products against the finished columns), shared memory +
+// __syncwarp only, one fast reciprocal per column and no square root.  rd = scratch of dimp doubles (1 / D).  b is
+// overwritten with x.  Returns false (uniformly) if a pivot is not positive -- the same condition under which the Cholesky
+// factorisation of g2o's dense solver fails.
+__device__ bool warp_ldlt_solve(double* S, double* b, double* rd, int dimp, int lane) {
+    for (int j = 0; j < dimp; ++j) {
+        double sj = 0, v[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int i = lane + 32 * m;
+            v[m] = 0;
+            if (i >= j && i < dimp) {
+                double t = S[i * dimp + j];
+                for (int k = 0; k < j; ++k) t -= S[i * dimp + k] * S[j * dimp + k] * S[k * dimp + k];
+                v[m] = t;
+                if (i == j) sj = t;
+            }
+        }
+        const double d = __shfl_sync(0xFFFFFFFFu, sj, j & 31);
+        if (!(d > 0)) return false;
+        const double r = fast_rcp(d);
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int i = lane + 32 * m;
+            if (i == j) {
+                S[i * dimp + j] = d;
+                rd[j] = r;
+            } else if (i > j && i < dimp) {
+                S[i * dimp + j] = v[m] * r;
+            }
+        }
+        __syncwarp();
+    }
+    // L z = b (unit diagonal), column oriented: the lane that owns row i publishes z_i, every lane updates its later rows
+    double r[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) r[m] = (lane + 32 * m < dimp) ? b[lane + 32 * m] : 0.0;
+    for (int i = 0; i < dimp; ++i) {
+        const int mi = i >> 5;
+        const double mine = mi == 0 ? r[0] : (mi == 1 ? r[1] : r[2]);
+        const double z = __shfl_sync(0xFFFFFFFFu, mine, i & 31);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int k = lane + 32 * m;
+            if (k > i && k < dimp) r[m] -= S[k * dimp + i] * z;
+        }
+    }
+    // D y = z, then L^T x = y
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+        if (lane + 32 * m < dimp) r[m] *= rd[lane + 32 * m];
+    for (int i = dimp - 1; i >= 0; --i) {
+        const int mi = i >> 5;
+        const double mine = mi == 0 ? r[0] : (mi == 1 ? r[1] : r[2]);
+        const double x = __shfl_sync(0xFFFFFFFFu, mine, i & 31);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const int k = lane + 32 * m;
+            if (k < i) r[m] -= S[i * dimp + k] * x;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+        if (lane + 32 * m < dimp) b[lane + 32 * m] = r[m];
+    __syncwarp();
+    return true;
+}
 
 __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double s_dyn[];
-    __shared__ double s_R[kBA2MaxPoses][12];      // current poses as [R|t]
-    __shared__ double s_Rlin[kBA2MaxPoses][12];   // poses at the linearisation point (the Jacobians are rebuilt from these)
-    __shared__ double s_pose[kBA2MaxPoses][6];    // estimates, g2o order [omega; upsilon]
-    __shared__ double s_backup[kBA2MaxPoses][6];
-    __shared__ double s_xp[6 * kBA2MaxFree];
+    __shared__ double s_Rlin[kBA2MaxPoses][12];   // poses of the accepted state as [R|t] (the Jacobians are rebuilt from these)
+    __shared__ double s_Rtry[kBA2MaxPoses][12];   // poses of the trial
+    __shared__ SE3d s_T[kBA2MaxPoses];            // accepted poses (the estimate of VertexSE3Sophus is their logarithm)
+    __shared__ SE3d s_Ttry[kBA2MaxPoses];         // trial poses
+    __shared__ double s_xp[6 * kBA2MaxFree], s_rd[6 * kBA2MaxFree];
     __shared__ double s_tmp[2 * (kW + 1)];
-    __shared__ double s_small[4];                 // per-CTA scalars offered to the cluster: chi2, scale, max |diag|, outliers
+    __shared__ double s_small[4];                 // per-CTA scalars offered to the cluster: chi2, scale, max |diag|, flag
     __shared__ double s_bc[4];                    // cluster totals of the same
     __shared__ int s_free[kBA2MaxPoses], s_kfof[kBA2MaxFree];
     __shared__ int s_np, s_ok, s_dup;
@@ -186,8 +275,10 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
         s_np = nf;
         s_dup = 0;
     }
-    if (tid < n_kf)
-        for (int c = 0; c < 6; ++c) s_pose[tid][c] = a.poses[6 * (size_t)(k0 + tid) + c];
+    if (tid < n_kf) {
+        s_T[tid] = pose_from_g2o(a.poses + 6 * (size_t)(k0 + tid));
+        se3_to_mat(s_T[tid], s_Rlin[tid]);
+    }
     __syncthreads();
     const int np = s_np, dimp = 6 * np, n_pairs = np * (np + 1) / 2;
     const int V = kPairW * n_pairs + kPoseW * np, poseBase = kPairW * n_pairs;
@@ -208,26 +299,30 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     double* s_stage = s_tot + V;
     Stage st;
     {
-        const size_t need = (size_t)6 * no + (size_t)18 * nl + ((size_t)nl * kBA2MaxFree + 7) / 8;
+        const size_t need = ba2_stage_doubles((size_t)nl, (size_t)no);
         const size_t have = (size_t)a.dyn_doubles - (size_t)(sysDoubles + 2 * V);
-        if (need <= have) {
-            st.lin = s_stage;
-            st.Hll = st.lin + (size_t)6 * no;
-            st.bl = st.Hll + (size_t)6 * nl;
-            st.Dinv = st.bl + (size_t)3 * nl;
-            st.Xb = st.Dinv + (size_t)6 * nl;
-            st.slot = reinterpret_cast<uint8_t*>(st.Xb + (size_t)3 * nl);
-        } else {
-            st.lin = a.lin + (size_t)6 * q_lo;
-            st.Hll = a.Hll + (size_t)6 * (p0 + j_lo);
-            st.bl = a.bl + (size_t)3 * (p0 + j_lo);
-            st.Dinv = a.Dinv + (size_t)6 * (p0 + j_lo);
-            st.Xb = a.pts_backup + (size_t)3 * (p0 + j_lo);
-            st.slot = a.slot + (size_t)kBA2MaxFree * (p0 + j_lo);
-        }
+        // global fall-back: disjoint regions because the size is monotone and 8 extra "landmarks" per preceding CTA cover its rounding
+        double* base = need <= have ? s_stage : a.lin + ba2_stage_doubles((size_t)(p0 + j_lo) + 8 * ((size_t)rank + 16 * (size_t)prob), (size_t)q_lo);
+        st.lin[0] = base;
+        st.lin[1] = st.lin[0] + (size_t)6 * no;
+        st.Hll[0] = st.lin[1] + (size_t)6 * no;
+        st.Hll[1] = st.Hll[0] + (size_t)6 * nl;
+        st.bl[0] = st.Hll[1] + (size_t)6 * nl;
+        st.bl[1] = st.bl[0] + (size_t)3 * nl;
+        st.X[0] = st.bl[1] + (size_t)3 * nl;
+        st.X[1] = st.X[0] + (size_t)3 * nl;
+        st.Dinv = st.X[1] + (size_t)3 * nl;
+        st.uv = st.Dinv + (size_t)6 * nl;
+        st.qa = reinterpret_cast<int32_t*>(st.uv + (size_t)2 * no);
+        st.kf = reinterpret_cast<uint8_t*>(st.qa + nl + 1);
+        st.slot = st.kf + ((no + 7) & ~7);
     }
-    // slot table: which observation of a landmark sits on which free pose
+    // slot table: which observation of a landmark sits on which free pose; landmark positions into the staging area
     for (int i = tid; i < nl * kBA2MaxFree; i += kT) st.slot[i] = 0xFF;
+    for (int i = tid; i < 3 * nl; i += kT) st.X[0][i] = a.pts[3 * (size_t)(p0 + j_lo) + i];
+    for (int i = tid; i < 2 * no; i += kT) st.uv[i] = a.so_uv[2 * (size_t)q_lo + i];
+    for (int i = tid; i < no; i += kT) st.kf[i] = (uint8_t)a.so_kf[q_lo + i];
+    for (int i = tid; i <= nl; i += kT) st.qa[i] = a.lm_start[p0 + j_lo + i] - q_lo;
     __syncthreads();
     for (int jj = tid; jj < nl; jj += kT) {
         const int qa = a.lm_start[p0 + j_lo + jj], qb = a.lm_start[p0 + j_lo + jj + 1];
@@ -238,20 +333,8 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
             st.slot[jj * kBA2MaxFree + f] = (uint8_t)(q - qa);
         }
     }
+    int cur = 0;   // index of the accepted state in the double buffers
 
-    auto refresh_poses = [&]() {   // contains a CTA barrier
-        if (tid < n_kf) se3_to_mat(pose_from_g2o(s_pose[tid]), s_R[tid]);
-        __syncthreads();
-    };
-    // residual of one observation at the current poses / the given landmark
-    auto reproject = [&](int q, double X0, double X1, double X2, double* x, double* y, double* z, double* e0, double* e1) {
-        const double* Tm = s_R[a.so_kf[q]];
-        *x = Tm[0] * X0 + Tm[1] * X1 + Tm[2] * X2 + Tm[3];
-        *y = Tm[4] * X0 + Tm[5] * X1 + Tm[6] * X2 + Tm[7];
-        *z = Tm[8] * X0 + Tm[9] * X1 + Tm[10] * X2 + Tm[11];
-        *e0 = a.so_uv[2 * (size_t)q] - (*x / *z * fx + cx);
-        *e1 = a.so_uv[2 * (size_t)q + 1] - (*y / *z * fy + cy);
-    };
     auto robust = [&](double e2, double* w) {   // RobustKernelHuber (delta in pixels, BA.cpp:450-452)
         *w = 1.0;
         if (a.huber_delta > 0 && e2 > dsqr) {
@@ -292,53 +375,48 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
         __syncthreads();
     };
 
-    // ---- P1: linearise the landmarks of this CTA (relin) and invert Hll + lambda I (with_D) -------------------------
-    auto linearise = [&](bool relin, bool with_D, double lambda, double* chi_out, double* mx_out) {
+    // ---- linearisation of this CTA's landmarks at (poses R, positions X) into buffer `buf`: the record (x, y, z, e, w) of every
+    // observation, Hll and bl of every landmark; returns the CTA-partial robust chi2 and max |diag Hll| per thread
+    auto linearise = [&](int buf, const double (*R)[12], const double* X, double* chi_out, double* mx_out) {
         double chi = 0, mx = 0;
         for (int jj = tid; jj < nl; jj += kT) {
-            const int gj = p0 + j_lo + jj;
-            double H[6];
-            if (relin) {
-                const double X0 = a.pts[3 * (size_t)gj], X1 = a.pts[3 * (size_t)gj + 1], X2 = a.pts[3 * (size_t)gj + 2];
-                st.Xb[3 * jj] = X0; st.Xb[3 * jj + 1] = X1; st.Xb[3 * jj + 2] = X2;
-                double b[3] = {0, 0, 0};
+            const double X0 = X[3 * jj], X1 = X[3 * jj + 1], X2 = X[3 * jj + 2];
+            double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+            for (int q = q_lo + st.qa[jj]; q < q_lo + st.qa[jj + 1]; ++q) {
+                const double* Tm = R[st.kf[q - q_lo]];
+                const double x = Tm[0] * X0 + Tm[1] * X1 + Tm[2] * X2 + Tm[3];
+                const double y = Tm[4] * X0 + Tm[5] * X1 + Tm[6] * X2 + Tm[7];
+                const double z = Tm[8] * X0 + Tm[9] * X1 + Tm[10] * X2 + Tm[11];
+                const double iz = 1.0 / z;
+                const double e0 = st.uv[2 * (size_t)(q - q_lo)] - (x * iz * fx + cx), e1 = st.uv[2 * (size_t)(q - q_lo) + 1] - (y * iz * fy + cy);
+                double w;
+                chi += robust(e0 * e0 + e1 * e1, &w);
+                double* rec = st.lin[buf] + 6 * (size_t)(q - q_lo);
+                rec[0] = x; rec[1] = y; rec[2] = iz; rec[3] = e0; rec[4] = e1; rec[5] = w;
+                double l0[3], l1[3];
+                point_jac(x, y, iz, fx, fy, Tm, l0, l1);
+                H[0] += w * (l0[0] * l0[0] + l1[0] * l1[0]); H[1] += w * (l0[0] * l0[1] + l1[0] * l1[1]);
+                H[2] += w * (l0[0] * l0[2] + l1[0] * l1[2]); H[3] += w * (l0[1] * l0[1] + l1[1] * l1[1]);
+                H[4] += w * (l0[1] * l0[2] + l1[1] * l1[2]); H[5] += w * (l0[2] * l0[2] + l1[2] * l1[2]);
 #pragma unroll
-                for (int t = 0; t < 6; ++t) H[t] = 0;
-                const int qa = a.lm_start[gj], qb = a.lm_start[gj + 1];
-                for (int q = qa; q < qb; ++q) {
-                    double x, y, z, e0, e1, w;
-                    reproject(q, X0, X1, X2, &x, &y, &z, &e0, &e1);
-                    chi += robust(e0 * e0 + e1 * e1, &w);
-                    double* rec = st.lin + 6 * (size_t)(q - q_lo);
-                    rec[0] = x; rec[1] = y; rec[2] = z; rec[3] = e0; rec[4] = e1; rec[5] = w;
-                    double l0[3], l1[3];
-                    point_jac(x, y, z, fx, fy, s_R[a.so_kf[q]], l0, l1);
-                    H[0] += w * (l0[0] * l0[0] + l1[0] * l1[0]); H[1] += w * (l0[0] * l0[1] + l1[0] * l1[1]);
-                    H[2] += w * (l0[0] * l0[2] + l1[0] * l1[2]); H[3] += w * (l0[1] * l0[1] + l1[1] * l1[1]);
-                    H[4] += w * (l0[1] * l0[2] + l1[1] * l1[2]); H[5] += w * (l0[2] * l0[2] + l1[2] * l1[2]);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) b[c] += -w * (l0[c] * e0 + l1[c] * e1);
-                }
-#pragma unroll
-                for (int t = 0; t < 6; ++t) st.Hll[6 * jj + t] = H[t];
-                st.bl[3 * jj] = b[0]; st.bl[3 * jj + 1] = b[1]; st.bl[3 * jj + 2] = b[2];
-                mx = fmax(mx, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
-            } else {
-#pragma unroll
-                for (int t = 0; t < 6; ++t) H[t] = st.Hll[6 * jj + t];
+                for (int c = 0; c < 3; ++c) b[c] += -w * (l0[c] * e0 + l1[c] * e1);
             }
-            if (with_D) sym_inverse3(H, lambda, st.Dinv + 6 * jj);
+#pragma unroll
+            for (int t = 0; t < 6; ++t) st.Hll[buf][6 * jj + t] = H[t];
+            st.bl[buf][3 * jj] = b[0]; st.bl[buf][3 * jj + 1] = b[1]; st.bl[buf][3 * jj + 2] = b[2];
+            mx = fmax(mx, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
         }
         *chi_out = chi;
         *mx_out = mx;
     };
 
-    // ---- P2: warp tasks.  Task t < n_pairs: block pair (f1 <= f2) of the reduced system; t >= n_pairs: Hpp / bp of free
+    // ---- warp tasks.  Task t < n_pairs: block pair (f1 <= f2) of the reduced system; t >= n_pairs: Hpp / bp of free
     // pose t - n_pairs.  The (task, 32-landmark chunk) items of [t_lo, t_hi) are dealt to the warps in contiguous runs, a
     // warp keeps its sums in registers while the task stays the same and leaves them in slot (task + warp).
-    auto accumulate = [&](int t_lo, int t_hi) {
+    auto accumulate = [&](int t_lo, int t_hi, double lambda) {
         const int n_chunks = (nl + 31) / 32;
         const int items = (t_hi - t_lo) * n_chunks, per = (items + kW - 1) / kW;
+        const double* lin = st.lin[cur];
         int it = warp * per;
         const int end = min(items, it + per);
         while (it < end) {
@@ -364,14 +442,14 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                     if (jj >= nl) continue;
                     const int s1 = st.slot[jj * kBA2MaxFree + f1], s2 = st.slot[jj * kBA2MaxFree + f2];
                     if (s1 == 0xFF || s2 == 0xFF) continue;
-                    const int qa = a.lm_start[p0 + j_lo + jj] - q_lo;
+                    const int qa = st.qa[jj];
                     const double* Di = st.Dinv + 6 * jj;
                     double H1[6][3], BD[6][3];
-                    make_hpl(st.lin + 6 * (size_t)(qa + s1), R1, fx, fy, H1);
+                    make_hpl(lin + 6 * (size_t)(qa + s1), R1, fx, fy, H1);
 #pragma unroll
                     for (int r = 0; r < 6; ++r) sym_mul3(Di, H1[r], BD[r]);   // (Hpl D)_r = D Hpl_r (D symmetric)
                     if (f1 == f2) {
-                        const double* bj = st.bl + 3 * jj;
+                        const double* bj = st.bl[cur] + 3 * jj;
 #pragma unroll
                         for (int r = 0; r < 6; ++r) accb[r] += BD[r][0] * bj[0] + BD[r][1] * bj[1] + BD[r][2] * bj[2];
 #pragma unroll
@@ -380,7 +458,7 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                             for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H1[c][0] + BD[r][1] * H1[c][1] + BD[r][2] * H1[c][2];
                     } else {
                         double H2[6][3];
-                        make_hpl(st.lin + 6 * (size_t)(qa + s2), R2, fx, fy, H2);
+                        make_hpl(lin + 6 * (size_t)(qa + s2), R2, fx, fy, H2);
 #pragma unroll
                         for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -409,7 +487,7 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                     if (jj >= nl) continue;
                     const int s1 = st.slot[jj * kBA2MaxFree + f];
                     if (s1 == 0xFF) continue;
-                    const double* rec = st.lin + 6 * (size_t)(a.lm_start[p0 + j_lo + jj] - q_lo + s1);
+                    const double* rec = lin + 6 * (size_t)(st.qa[jj] + s1);
                     double q0[6], q1[6];
                     pose_jac(rec[0], rec[1], rec[2], fx, fy, q0, q1);
                     const double w = rec[5];
@@ -451,21 +529,16 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     };
 
     // ---- prologue: first linearisation, lambda_0 = tau * max |diag H| (computeLambdaInit) ------------------------------
-    refresh_poses();
-    if (tid < n_kf)
-        for (int c = 0; c < 12; ++c) s_Rlin[tid][c] = s_R[tid][c];
-    if (tid < n_kf)
-        for (int c = 0; c < 6; ++c) s_backup[tid][c] = s_pose[tid][c];
     __syncthreads();
     int iters = 0, trials_total = 0;
     double chi_first = 0, chi_last = 0, lambda = 0, ni = 2, rho = 0, currentChi = 0;
     {
         double chi, mx;
-        linearise(true, false, 0.0, &chi, &mx);
+        linearise(0, s_Rlin, st.X[0], &chi, &mx);
         double dummy = 0;
         block_sum2(chi, dummy, s_tmp);
         mx = block_max(mx, s_tmp);
-        accumulate(n_pairs, n_pairs + np);
+        accumulate(n_pairs, n_pairs + np, 0.0);
         exchange_vector(poseBase, V);
         if (tid == 0) {
             s_small[0] = chi;
@@ -485,27 +558,29 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     }
     const bool dup = s_bc[3] > 0;   // unsupported input: reported through stats, nothing is optimised
 
-    bool relin = false;   // the prologue has linearised iteration 0
+    // optional phase timing (a.debug != null): cycles of CTA 0 / thread 0 per phase, summed over the trials
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    auto tick = [&](int ph) {
+        if (a.debug) {
+            const long long now = clock64();
+            tph[ph] += now - tlast;
+            tlast = now;
+        }
+    };
+    bool fresh = false;   // Hpp / bp of the accepted state are in s_x (the prologue computed them for iteration 0)
     for (int iteration = 0; iteration < a.max_iters && !dup; ++iteration) {
         int qmax = 0;
         do {
-            // ---- P1 / P2: (re)linearise if the state moved, invert Hll + lambda I, accumulate the reduced system
-            if (relin) {
-                if (tid < n_kf) {
-                    for (int c = 0; c < 12; ++c) s_Rlin[tid][c] = s_R[tid][c];
-                    for (int c = 0; c < 6; ++c) s_backup[tid][c] = s_pose[tid][c];
-                }
-                __syncthreads();
-            }
-            {
-                double chi, mx;
-                linearise(relin, true, lambda, &chi, &mx);
-            }
+            // ---- reduced system of the accepted state at the current lambda: (Hll + lambda I)^-1 is rebuilt per use
+            tick(7);
+            for (int jj = tid; jj < nl; jj += kT) sym_inverse3(st.Hll[cur] + 6 * jj, lambda, st.Dinv + 6 * jj);
             __syncthreads();
-            accumulate(0, relin ? n_pairs + np : n_pairs);
-            exchange_vector(0, relin ? V : poseBase);
-            relin = false;
-            // ---- P3: S = Hpp + lambda I - sum Hpl D Hpl^T, b_s = bp - sum Hpl D bl; dense Cholesky in every CTA (same bits)
+            accumulate(0, fresh ? n_pairs + np : n_pairs, lambda);
+            tick(0);
+            exchange_vector(0, fresh ? V : poseBase);
+            tick(1);
+            fresh = false;
+            // S = Hpp + lambda I - sum Hpl D Hpl^T, b_s = bp - sum Hpl D bl (every CTA: same bits)
             for (int i = tid; i < dimp * dimp; i += kT) {
                 const int r = i / dimp, c = i - r * dimp, fr = r / 6, fc = c / 6, rr = r - 6 * fr, cc = c - 6 * fc;
                 double v;
@@ -517,99 +592,73 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                 }
                 s_S[i] = v;
             }
-            // (s_part aliases s_S: accumulate() consumed the slots before its final barrier)
             if (tid < dimp) {
                 const int f = tid / 6, r = tid - 6 * f;
                 s_bs[tid] = s_x[poseBase + f * kPoseW + 21 + r] - s_x[(f * np - f * (f - 1) / 2) * kPairW + 36 + r];
             }
-            if (tid == 0) s_ok = 1;
             __syncthreads();
-            for (int j = 0; j < dimp; ++j) {
-                if (tid == 0) {
-                    const double d = s_S[j * dimp + j];
-                    if (!(d > 0)) s_ok = 0;
-                    s_S[j * dimp + j] = sqrt(d);
-                }
-                __syncthreads();
-                if (!s_ok) break;
-                const double djj = s_S[j * dimp + j];
-                const int rem = dimp - j - 1;
-                for (int e = tid; e < rem * rem; e += kT) {
-                    const int r = j + 1 + e / rem, c = j + 1 + e % rem;
-                    if (c <= r) s_S[r * dimp + c] -= (s_S[r * dimp + j] / djj) * (s_S[c * dimp + j] / djj);
-                }
-                __syncthreads();
-                for (int i = j + 1 + tid; i < dimp; i += kT) s_S[i * dimp + j] /= djj;
-            }
-            __syncthreads();
-            if (s_ok && warp == 0) {
-                for (int i = 0; i < dimp; ++i) {
-                    double s = 0;
-                    for (int k = lane; k < i; k += 32) s += s_S[i * dimp + k] * s_bs[k];
-                    s = warp_sum(s);
-                    if (lane == 0) s_bs[i] = (s_bs[i] - s) / s_S[i * dimp + i];
-                    __syncwarp();
-                }
-                for (int i = dimp - 1; i >= 0; --i) {
-                    double s = 0;
-                    for (int k = i + 1 + lane; k < dimp; k += 32) s += s_S[k * dimp + i] * s_bs[k];
-                    s = warp_sum(s);
-                    if (lane == 0) s_bs[i] = (s_bs[i] - s) / s_S[i * dimp + i];
-                    __syncwarp();
-                }
+            tick(2);
+            // ---- warp 0: dense Cholesky + triangular solves, then VertexSE3Sophus::oplusImpl for the trial poses
+            if (warp == 0) {
+                const bool ok = dimp == 0 || warp_ldlt_solve(s_S, s_bs, s_rd, dimp, lane);
+                if (lane == 0) s_ok = ok ? 1 : 0;
+                for (int i = lane; i < dimp; i += 32) s_xp[i] = ok ? s_bs[i] : 0.0;
             }
             __syncthreads();
             const bool ok2 = s_ok != 0;
-            if (tid < dimp) s_xp[tid] = s_bs[tid];
-            __syncthreads();
-            // ---- P4a: VertexSE3Sophus::oplusImpl on the pose replica
-            if (tid < n_kf && s_free[tid] >= 0) {
-                const double* u = s_xp + 6 * s_free[tid];
-                const double v[6] = {u[3], u[4], u[5], u[0], u[1], u[2]};
-                const SE3d Tn = se3_mul(se3_exp(v), pose_from_g2o(s_pose[tid]));
-                double lg[6];
-                se3_log(Tn, lg);
-                s_pose[tid][0] = lg[3]; s_pose[tid][1] = lg[4]; s_pose[tid][2] = lg[5];
-                s_pose[tid][3] = lg[0]; s_pose[tid][4] = lg[1]; s_pose[tid][5] = lg[2];
-            }
-            __syncthreads();
-            refresh_poses();
-            // ---- P4b: landmark back-substitution + update, chi2 at the trial point, gain-ratio denominator
+            tick(3);
             double chi_part = 0, scale = 0;
-            for (int jj = tid; jj < nl; jj += kT) {
-                const int gj = p0 + j_lo + jj;
-                const int qa = a.lm_start[gj], qb = a.lm_start[gj + 1];
-                const double* bj = st.bl + 3 * jj;
-                double r[3] = {bj[0], bj[1], bj[2]};
-                for (int q = qa; q < qb; ++q) {
-                    const int kf = a.so_kf[q], fi = s_free[kf];
-                    if (fi < 0) continue;
-                    double H1[6][3];
-                    make_hpl(st.lin + 6 * (size_t)(q - q_lo), s_Rlin[kf], fx, fy, H1);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int rr = 0; rr < 6; ++rr) r[c] -= H1[rr][c] * s_xp[6 * fi + rr];
+            if (warp == 0) {
+                for (int k = lane; k < n_kf; k += 32) {
+                    if (s_free[k] >= 0) {
+                        // VertexSE3Sophus::oplusImpl: estimate <- log(exp(update) * exp(estimate)); the replica keeps the group
+                        // element itself (the logarithm is taken once, for the result), which skips a log / exp round trip per trial
+                        const double* u = s_xp + 6 * s_free[k];
+                        const double v[6] = {u[3], u[4], u[5], u[0], u[1], u[2]};
+                        s_Ttry[k] = se3_mul(se3_exp(v), s_T[k]);
+                        se3_to_mat(s_Ttry[k], s_Rtry[k]);
+                    } else {
+                        s_Ttry[k] = s_T[k];
+                        for (int c = 0; c < 12; ++c) s_Rtry[k][c] = s_Rlin[k][c];
+                    }
                 }
-                double xl[3];
-                sym_mul3(st.Dinv + 6 * jj, r, xl);
-                double X[3];
+                if (rank == 0)
+                    for (int i = lane; i < dimp; i += 32) {
+                        const int f = i / 6, rr = i - 6 * f;
+                        scale += s_xp[i] * (lambda * s_xp[i] + s_x[poseBase + f * kPoseW + 21 + rr]);
+                    }
+            } else {
+                // ---- the other warps meanwhile: landmark back-substitution, trial positions, gain-ratio denominator
+                for (int jj = tid - 32; jj < nl; jj += kT - 32) {
+                    const double* bj = st.bl[cur] + 3 * jj;
+                    double r[3] = {bj[0], bj[1], bj[2]};
+                    for (int q = st.qa[jj]; q < st.qa[jj + 1]; ++q) {
+                        const int kf = st.kf[q], fi = s_free[kf];
+                        if (fi < 0) continue;
+                        double H1[6][3];
+                        make_hpl(st.lin[cur] + 6 * (size_t)q, s_Rlin[kf], fx, fy, H1);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    scale += xl[c] * (lambda * xl[c] + bj[c]);
-                    X[c] = st.Xb[3 * jj + c] + xl[c];
-                    a.pts[3 * (size_t)gj + c] = X[c];
-                }
-                for (int q = qa; q < qb; ++q) {
-                    double x, y, z, e0, e1, w;
-                    reproject(q, X[0], X[1], X[2], &x, &y, &z, &e0, &e1);
-                    chi_part += robust(e0 * e0 + e1 * e1, &w);
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int rr = 0; rr < 6; ++rr) r[c] -= H1[rr][c] * s_xp[6 * fi + rr];
+                    }
+                    double xl[3];
+                    sym_mul3(st.Dinv + 6 * jj, r, xl);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        scale += xl[c] * (lambda * xl[c] + bj[c]);
+                        st.X[cur ^ 1][3 * jj + c] = st.X[cur][3 * jj + c] + xl[c];
+                    }
                 }
             }
-            if (rank == 0 && tid < dimp) {
-                const int f = tid / 6, rr = tid - 6 * f;
-                scale += s_xp[tid] * (lambda * s_xp[tid] + s_x[poseBase + f * kPoseW + 21 + rr]);
+            __syncthreads();
+            tick(4);
+            // ---- chi2 at the trial point = linearisation of the next iteration if the step is accepted
+            {
+                double mx;
+                linearise(cur ^ 1, s_Rtry, st.X[cur ^ 1], &chi_part, &mx);
             }
+            tick(5);
             block_sum2(chi_part, scale, s_tmp);
             if (tid == 0) {
                 s_small[0] = chi_part;
@@ -618,32 +667,29 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                 s_small[3] = 0;
             }
             exchange_small();
+            tick(6);
             double tempChi = s_bc[0];
             const double scale_tot = s_bc[1] + 1e-3;
             if (!ok2) tempChi = 1.7976931348623157e308;
             rho = (currentChi - tempChi) / scale_tot;
-            bool accept;
             if (rho > 0 && isfinite(tempChi)) {
-                double alpha = 1. - pow((2 * rho - 1), 3);
+                const double t2 = 2 * rho - 1;
+                double alpha = 1. - t2 * t2 * t2;
                 alpha = fmin(alpha, 2. / 3.);
                 lambda *= fmax(1. / 3., alpha);
                 ni = 2;
                 currentChi = tempChi;
-                accept = true;
-                relin = true;
-            } else {
+                // the trial becomes the accepted state: swap the double buffers, take over the poses
+                cur ^= 1;
+                fresh = true;
+                if (tid < n_kf) {
+                    s_T[tid] = s_Ttry[tid];
+                    for (int c = 0; c < 12; ++c) s_Rlin[tid][c] = s_Rtry[tid][c];
+                }
+                __syncthreads();
+            } else {   // _optimizer->pop(): the accepted state was never touched
                 lambda *= ni;
                 ni *= 2;
-                accept = false;
-            }
-            if (!accept) {  // _optimizer->pop(): back to the linearisation point
-                if (tid < n_kf)
-                    for (int c = 0; c < 6; ++c) s_pose[tid][c] = s_backup[tid][c];
-                for (int jj = tid; jj < nl; jj += kT)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) a.pts[3 * (size_t)(p0 + j_lo + jj) + c] = st.Xb[3 * jj + c];
-                __syncthreads();
-                refresh_poses();
             }
             ++qmax;
             ++trials_total;
@@ -652,16 +698,15 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
         chi_last = currentChi;
         if (qmax == a.max_trials || rho == 0) break;
     }
-    // ---- outlier flags (BA.cpp:505-515): plain chi2 > 5.991 at the final estimate
+    // ---- results: landmark positions, outlier flags (BA.cpp:505-515: plain chi2 > 5.991 at the final estimate), poses
     cluster.sync();   // the last exchange_small may still be read by a neighbour: s_small is rewritten below
     double n_out = 0, zero = 0;
     for (int jj = tid; jj < nl; jj += kT) {
         const int gj = p0 + j_lo + jj;
-        const double X0 = a.pts[3 * (size_t)gj], X1 = a.pts[3 * (size_t)gj + 1], X2 = a.pts[3 * (size_t)gj + 2];
-        for (int q = a.lm_start[gj]; q < a.lm_start[gj + 1]; ++q) {
-            double x, y, z, e0, e1;
-            reproject(q, X0, X1, X2, &x, &y, &z, &e0, &e1);
-            const int out = (e0 * e0 + e1 * e1 > a.chi2_outlier) ? 1 : 0;
+        for (int c = 0; c < 3; ++c) a.pts[3 * (size_t)gj + c] = st.X[cur][3 * jj + c];
+        for (int q = q_lo + st.qa[jj]; q < q_lo + st.qa[jj + 1]; ++q) {
+            const double* rec = st.lin[cur] + 6 * (size_t)(q - q_lo);
+            const int out = (rec[3] * rec[3] + rec[4] * rec[4] > a.chi2_outlier) ? 1 : 0;
             a.outlier[a.so_orig ? a.so_orig[q] : q] = (uint8_t)out;
             n_out += out;
         }
@@ -673,12 +718,18 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     }
     exchange_small();
     if (rank == 0) {
-        if (tid < n_kf)
-            for (int c = 0; c < 6; ++c) a.poses[6 * (size_t)(k0 + tid) + c] = s_pose[tid][c];
+        if (tid < n_kf && s_free[tid] >= 0) {   // fixed vertices keep their input bits
+            double lg[6];
+            se3_log(s_T[tid], lg);
+            double* o = a.poses + 6 * (size_t)(k0 + tid);
+            o[0] = lg[3]; o[1] = lg[4]; o[2] = lg[5]; o[3] = lg[0]; o[4] = lg[1]; o[5] = lg[2];
+        }
         if (tid == 0) {
             double* stt = a.stats + 8 * (size_t)prob;
             stt[0] = iters; stt[1] = trials_total; stt[2] = chi_first; stt[3] = chi_last; stt[4] = lambda; stt[5] = s_bc[0];
             stt[6] = dup ? 1.0 : 0.0; stt[7] = 0;
+            if (a.debug)
+                for (int k = 0; k < 8; ++k) a.debug[8 * (size_t)prob + k] = (double)tph[k];
         }
     }
     cluster.sync();   // no CTA may exit while another still reads its shared memory
@@ -756,8 +807,8 @@ __global__ void __launch_bounds__(1024) csr_build_kernel(const int32_t* __restri
 size_t ba2_scratch_bytes(size_t NP, size_t NO, size_t P) {
     Carver sz(nullptr);
     sz.take<int32_t>(NP + 1); sz.take<int32_t>(NP + 1); sz.take<int32_t>(NO); sz.take<int32_t>(NO); sz.take<double>(2 * NO);
-    sz.take<double>(6 * NO); sz.take<double>(6 * NP); sz.take<double>(3 * NP); sz.take<double>(6 * NP); sz.take<double>(3 * NP);
-    sz.take<uint8_t>(NP * kBA2MaxFree); sz.take<uint8_t>(NO); sz.take<double>(8 * P);
+    sz.take<double>(ba2_stage_doubles(NP + 8 * 16 * P, NO));   // global fall-back of the staging areas (+ per-CTA rounding slack)
+    sz.take<uint8_t>(NP * kBA2MaxFree); sz.take<uint8_t>(NO); sz.take<double>(8 * P); sz.take<double>(8 * P);
     return sz.bytes();
 }
 
@@ -773,14 +824,11 @@ int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const y
     int32_t* d_so_kf = c.take<int32_t>(NO);
     double* d_so_uv = c.take<double>(2 * NO);
     BA2Args a;
-    a.lin = c.take<double>(6 * NO);
-    a.Hll = c.take<double>(6 * NP);
-    a.bl = c.take<double>(3 * NP);
-    a.Dinv = c.take<double>(6 * NP);
-    a.pts_backup = c.take<double>(3 * NP);
+    a.lin = c.take<double>(ba2_stage_doubles(NP + 8 * 16 * P, NO));   // global fall-back of the CTA-private staging areas
     a.slot = c.take<uint8_t>(NP * kBA2MaxFree);
     a.outlier = c.take<uint8_t>(NO);
     a.stats = c.take<double>(8 * P);
+    a.debug = getenv("YGZB_BA_DEBUG") ? c.take<double>(8 * P) : nullptr;
     if (in.lm_start) {   // the caller already has landmark-major lists (the tracking engine builds them itself)
         a.lm_start = in.lm_start; a.so_kf = in.kf_idx; a.so_uv = in.obs; a.so_orig = nullptr;
     } else {
@@ -811,14 +859,15 @@ int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const y
     while (cluster < 8 && in.max_pts > (size_t)cluster * 320) cluster *= 2;
     if (const char* e = getenv("YGZB_BA_CLUSTER")) {   // tuning knob: 1, 2, 4 or 8
         const int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) cluster = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cluster = v;
     }
+    if (cluster > 8) cudaFuncSetAttribute(local_ba2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     const int np = std::max(in.max_free, 0), dimp = 6 * np, n_pairs = np * (np + 1) / 2;
     const int V = kPairW * n_pairs + kPoseW * np;
     const size_t sys = std::max<size_t>((size_t)dimp * dimp + dimp, (size_t)(n_pairs + np + kW) * kPairW);
     const size_t nl = (in.max_pts + cluster - 1) / cluster;
     const size_t no = std::min<size_t>(in.max_obs, nl * (size_t)std::max(in.max_kf, 1));
-    const size_t stage = 6 * no + 18 * nl + (nl * kBA2MaxFree + 7) / 8 + 2;
+    const size_t stage = ba2_stage_doubles(nl, no) + 2;
     static int max_optin = 0;
     static std::once_flag once;
     std::call_once(once, [&] {
@@ -849,6 +898,17 @@ int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const y
         YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, local_ba2_kernel, a));
     }
     YGZB_LAUNCHED(ctx);
+    if (a.debug) {   // YGZB_BA_DEBUG: phase cycles of problem 0 (blocking; diagnostics only)
+        double h[16];
+        double hs[8];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h, a.debug, sizeof(double) * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hs, a.stats, sizeof(double) * 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ba2] P=%zu cluster=%d iters=%.0f trials=%.0f cycles/trial: accumulate %.0f exchange %.0f assemble %.0f solve %.0f "
+                        "pose+backsubst %.0f linearise %.0f reduce+exchange %.0f decide %.0f\n",
+                P, cluster, hs[0], hs[1], h[0] / hs[1], h[1] / hs[1], h[2] / hs[1], h[3] / hs[1], h[4] / hs[1], h[5] / hs[1], h[6] / hs[1],
+                h[7] / hs[1]);
+    }
     if (d_outlier_out) *d_outlier_out = a.outlier;
     if (d_stats_out) *d_stats_out = a.stats;
     return YGZB_OK;

@@ -25,11 +25,13 @@ struct BA2Args {
     const int32_t* so_kf;      // pose index LOCAL to the problem
     const double* so_uv;       // measured pixel
     const int32_t* so_orig;    // id of the observation in the caller's order (outlier[] is written there) or null = identity
-    // global fall-back of the CTA-private staging area (used only when a problem does not fit shared memory)
-    double *lin, *Hll, *bl, *Dinv, *pts_backup;
+    // global fall-back of the CTA-private staging area (used only when a problem does not fit shared memory): 12 doubles per
+    // observation + 24 per landmark, carved by the CTA from its observation / landmark offsets
+    double* lin;
     uint8_t* slot;
     uint8_t* outlier;          // [n_obs]
     double* stats;             // [n_problems][8]: iters, trials, chi2 first, chi2 last, lambda, outliers, duplicate flag, 0
+    double* debug;             // optional [n_problems][8]: cycles per phase (YGZB_BA_DEBUG)
     long long dyn_doubles;     // dynamic shared memory of the launch, in doubles
     float fx, fy, cx, cy;
     int max_iters, max_trials;
