@@ -1118,16 +1118,20 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
         }
         __syncthreads();
         double radius = 1e4, decrease_factor = 2.0;
+        // unscaled normal equations J^T J / J^T r at the current point (s_sum holds them after eval_normal(.., false)); the Jacobi
+        // scaled system Ceres solves is D J^T J D / D J^T r, formed here from the same sums instead of a second pass over the points
+        double U[27];
+        for (int t = 0; t < 27; ++t) U[t] = s_sum[t];
+        __syncthreads();
         for (int iter = 0; run && iter < 50; ++iter) {
-            eval_normal(s_pose, true);  // scaled normal equations at the current point
             double A[36], g[6], y[6];
             {
                 int t = 0;
                 for (int r = 0; r < 6; ++r)
                     for (int c = r; c < 6; ++c) {
-                        A[r * 6 + c] = A[c * 6 + r] = s_sum[t++];
+                        A[r * 6 + c] = A[c * 6 + r] = U[t++] * s_scale[r] * s_scale[c];
                     }
-                for (int k = 0; k < 6; ++k) g[k] = s_sum[21 + k];
+                for (int k = 0; k < 6; ++k) g[k] = U[21 + k] * s_scale[k];
             }
             double An[36];
             for (int t = 0; t < 36; ++t) An[t] = A[t];
@@ -1178,6 +1182,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
                         eval_normal(s_pose, false);
                         double gmax = 0;
                         for (int k = 0; k < 6; ++k) gmax = fmax(gmax, fabs(s_sum[21 + k]));
+                        for (int t = 0; t < 27; ++t) U[t] = s_sum[t];
                         __syncthreads();
                         if (gmax <= 1e-10) break;                         // gradient tolerance
                         radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3));

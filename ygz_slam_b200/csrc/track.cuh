@@ -42,6 +42,7 @@ struct TrackBatch {
     double* frame_jac;
     uint8_t* visible;
     double* sparse_ws;
+    void* sa2_scratch;          // global fall-back of the second-generation kernel's per-feature staging
     // Matcher::SparseImageAlignment's motion check, poses relative to the local key-frames
     int32_t* aligned;           // [J]
     double* rel;                // [J][kTrackMaxLocal][12]
@@ -66,5 +67,6 @@ int launch_pose_only_dev(ygzb_ctx* ctx, int n_problems, const int32_t* d_offsets
                          const double* d_px, double* d_T_cw, uint8_t* d_inlier, double* d_depth, int32_t* d_n_inlier, uint8_t* d_enable,
                          double* d_ws, int cluster);
 size_t pose_only_ws_doubles(int n_problems);
+size_t sparse_align2_scratch_bytes(int n_problems, int cells);
 
 }  // namespace ygzb
