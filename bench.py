@@ -128,6 +128,45 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa(gpu_index: int) -> dict:
+    """Pin this process (and the host threads it creates later: the C++ drivers' workers inherit the mask) to the CPUs that are
+    local to its GPU's PCIe root, so that pinned frame buffers are allocated on, and copied from, the GPU's own NUMA node.
+    8 ranks on one box otherwise share whatever node the scheduler picks (round 1: e2e scaling 0.59 at N=8)."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = gpu_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[gpu_index])
+            except (ValueError, IndexError):
+                pass
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{int(dom, 16):04x}:{rest.lower()}"
+        cpus = set()
+        for part in open(path + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        info["numa_node"] = int(open(path + "/numa_node").read().strip())
+        allowed = os.sched_getaffinity(0) & cpus
+        info["local_cpus"] = len(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+            info["cpus_bound"] = len(allowed)
+    except Exception as e:  # noqa: BLE001 -- binding is an optimisation, never a failure
+        info["error"] = repr(e)
+    return info
+
+
 def measured_peaks() -> tuple:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -405,6 +444,7 @@ def vo_line(args, rank, world, local_rank):
     n = (args.warmup + args.steps) * F
     warm = args.warmup * F
     timed = n - warm
+    numa = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else {"bound": False, "note": "--no-numa-bind"}
     data = vo_streams(S * rank, S, n)
     stacked = vo_native.stack_pinned([d[0] for d in data])
     depths = [d[1] for d in data]
@@ -472,9 +512,11 @@ def vo_line(args, rank, world, local_rank):
     per_rank = None
     if world > 1:
         from ygz_slam_b200 import dist as ydist
-        rec = ydist.make_record(rank, S * timed, sum(s["inliers"] for s in stats_e), lost, [0, 0, 0, 1, 0, 0, 0], ms_resident)
+        rec = ydist.make_record(rank, S * timed, sum(s["inliers"] for s in stats_e), lost,
+                                [ms_e2e, float(numa.get("numa_node", -1)), float(numa.get("cpus_bound", 0)), 1, 0, 0, 0], ms_resident)
         table, _, _ = ydist.gather_records([rec], world, device=torch.device("cuda", local_rank))
-        per_rank = [{"rank": int(r[0]), "frames": int(r[1]), "device_ms": float(r[11])} for r in table]
+        per_rank = [{"rank": int(r[0]), "frames": int(r[1]), "device_ms": float(r[11]), "e2e_ms": float(r[4]), "numa_node": int(r[5]),
+                     "cpus_bound": int(r[6])} for r in table]
         t = torch.tensor([ms_resident, ms_e2e, float(lost), err], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_resident, ms_e2e, lost, err = t.tolist()
@@ -581,6 +623,7 @@ def vo_line(args, rank, world, local_rank):
                          "candidates_per_frame": sum(s["candidates"] for s in stats_e) / (S * n),
                          "inliers_per_frame": sum(s["inliers"] for s in stats_e) / (S * n)},
             "sharded_8_streams": sharded,
+            "numa": numa,
             "secondary_workloads": extra,
             "per_rank": per_rank,
         }
@@ -595,6 +638,8 @@ def extract_match_line(args, rank, world, local_rank, with_secondary=True):
     from ygz_slam_b200 import Context
 
     line = None
+    if not getattr(args, "no_numa_bind", False):
+        bind_to_gpu_numa(local_rank)
     B = args.batch
     ctx = Context(local_rank, n_levels=LEVELS)
     fr = ctx.frames(B)
@@ -893,6 +938,7 @@ def main() -> None:
     ap.add_argument("--frames-per-step", type=int, default=10, help="vo: frames per stream and step")
     ap.add_argument("--vo-threads", type=int, default=2, help="vo: host threads (= ygzb contexts = CUDA streams) per GPU")
     ap.add_argument("--vo-window", type=int, default=8, help="vo: frames of one stream that may be in flight per round (1 = latency mode)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the CPUs local to its GPU")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (C2, C3, C4) of the N=1 run")
     ap.add_argument("--batch", type=int, default=512, help="extract_match: frames per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=48, help="extract_match: frames of the bounded cpu_baseline sample")

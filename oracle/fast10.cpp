@@ -12,7 +12,11 @@
 // closed-form score vs. bisection, nonmax vs. a dense 8-neighbour check; tests/test_oracle_fast.py).
 #include "oracle.h"
 
+#include <cstdlib>
 #include <vector>
+#if defined(__AVX2__)
+#include <immintrin.h>   // the timed CPU-baseline build (-march=x86-64-v3) gets a 32-pixel prefilter like the SSE2 path of the library
+#endif
 
 namespace {
 
@@ -57,15 +61,46 @@ extern "C" int ora_fastN_detect(const uint8_t* img, int w, int h, int stride, in
     int n = 0;
     // fast_corner_detect_10: for y in [3,h-3) for x in [3,w-3), raster order (the SSE2 variant walks
     // 16-pixel blocks plus a scalar tail and emits the same set in the same order)
-    for (int y = 3; y < h - 3; ++y)
-        for (int x = 3; x < w - 3; ++x)
-            if (is_corner(img + (size_t)y * stride + x, off, barrier, arc)) {
-                if (n < cap) {
-                    xy[2 * n] = (int16_t)x;
-                    xy[2 * n + 1] = (int16_t)y;
+    auto emit = [&](int x, int y) {
+        if (n < cap) {
+            xy[2 * n] = (int16_t)x;
+            xy[2 * n + 1] = (int16_t)y;
+        }
+        ++n;
+    };
+    for (int y = 3; y < h - 3; ++y) {
+        int x = 3;
+#if defined(__AVX2__)
+        // 32 pixels at a time (the reference calls fast_corner_detect_10_sse2, FeatureDetector.cpp:365-368, which filters 16
+        // pixels per step the same way): an arc of >= 9 ring pixels contains at least two of the four compass pixels, so a
+        // pixel with fewer than two brighter AND fewer than two darker compass pixels cannot be a corner; the survivors take
+        // the exact scalar test, in raster order -- same set, same order as the scalar loop
+        if (arc >= 9 && barrier >= 0 && barrier <= 255) {
+            const __m256i vb = _mm256_set1_epi8((char)barrier), zero = _mm256_setzero_si256(), one = _mm256_set1_epi8(1);
+            const int comp[4] = {off[0], off[4], off[8], off[12]};
+            for (; x + 32 <= w - 3; x += 32) {
+                const uint8_t* p = img + (size_t)y * stride + x;
+                const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+                const __m256i hi = _mm256_adds_epu8(c, vb), lo = _mm256_subs_epu8(c, vb);
+                __m256i nb = zero, nd = zero;   // number of brighter / darker compass pixels per lane
+                for (int k = 0; k < 4; ++k) {
+                    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + comp[k]));
+                    // v > hi  <=>  subs(v, hi) != 0 ; v < lo  <=>  subs(lo, v) != 0  (the saturation keeps p + b > 255 / p - b < 0 exact)
+                    nb = _mm256_add_epi8(nb, _mm256_andnot_si256(_mm256_cmpeq_epi8(_mm256_subs_epu8(v, hi), zero), one));
+                    nd = _mm256_add_epi8(nd, _mm256_andnot_si256(_mm256_cmpeq_epi8(_mm256_subs_epu8(lo, v), zero), one));
                 }
-                ++n;
+                unsigned m = (unsigned)_mm256_movemask_epi8(_mm256_or_si256(_mm256_cmpgt_epi8(nb, one), _mm256_cmpgt_epi8(nd, one)));
+                while (m) {
+                    const int k = __builtin_ctz(m);
+                    m &= m - 1;
+                    if (is_corner(p + k, off, barrier, arc)) emit(x + k, y);
+                }
             }
+        }
+#endif
+        for (; x < w - 3; ++x)
+            if (is_corner(img + (size_t)y * stride + x, off, barrier, arc)) emit(x, y);
+    }
     return n;
 }
 
@@ -98,6 +133,19 @@ extern "C" void ora_fast10_score(const uint8_t* img, int stride, const int16_t* 
 // indices into the corner list, ascending.  Walks the list with row-start pointers like the
 // library does (left / right neighbours are i-1 / i+1, rows above and below are scanned with
 // monotone cursors).
+// The neighbour rule of uzh-rpg/fast is restated from memory (its source is not in the reference tree): ">=" (a corner dies when
+// a neighbour scores at least as much) is the default; ora_set_fast_nonmax_strict(1) or YGZ_ORACLE_NONMAX_STRICT=1 switches the
+// oracle to ">" (only a strictly better neighbour kills), so that the choice is one flag once the library source can be read.
+static int g_nonmax_strict = -1;
+extern "C" void ora_set_fast_nonmax_strict(int strict) { g_nonmax_strict = strict ? 1 : 0; }
+static inline bool nonmax_beats(int other, int s) {
+    if (g_nonmax_strict < 0) {
+        const char* e = getenv("YGZ_ORACLE_NONMAX_STRICT");
+        g_nonmax_strict = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_nonmax_strict ? other > s : other >= s;
+}
+
 extern "C" int ora_fast_nonmax_3x3(const int16_t* xy, const int32_t* scores, int n, int32_t* keep_idx) {
     if (n < 1) return 0;
     const int last_row = xy[2 * (n - 1) + 1];
@@ -115,13 +163,13 @@ extern "C" int ora_fast_nonmax_3x3(const int16_t* xy, const int32_t* scores, int
     for (int i = 0; i < n; ++i) {
         const int s = scores[i], x = xy[2 * i], y = xy[2 * i + 1];
         bool dead = false;
-        if (i > 0 && xy[2 * (i - 1) + 1] == y && xy[2 * (i - 1)] == x - 1 && scores[i - 1] >= s) dead = true;
-        if (!dead && i < n - 1 && xy[2 * (i + 1) + 1] == y && xy[2 * (i + 1)] == x + 1 && scores[i + 1] >= s) dead = true;
+        if (i > 0 && xy[2 * (i - 1) + 1] == y && xy[2 * (i - 1)] == x - 1 && nonmax_beats(scores[i - 1], s)) dead = true;
+        if (!dead && i < n - 1 && xy[2 * (i + 1) + 1] == y && xy[2 * (i + 1)] == x + 1 && nonmax_beats(scores[i + 1], s)) dead = true;
         if (!dead && y > 0 && row_start[y - 1] != -1) {
             if (xy[2 * above + 1] < y - 1) above = row_start[y - 1];
             while (xy[2 * above + 1] < y && xy[2 * above] < x - 1) ++above;
             for (int j = above; xy[2 * j + 1] < y && xy[2 * j] <= x + 1; ++j)
-                if (scores[j] >= s) {  // x in {x-1, x, x+1} guaranteed by the two loop bounds
+                if (nonmax_beats(scores[j], s)) {  // x in {x-1, x, x+1} guaranteed by the two loop bounds
                     dead = true;
                     break;
                 }
@@ -130,7 +178,7 @@ extern "C" int ora_fast_nonmax_3x3(const int16_t* xy, const int32_t* scores, int
             if (xy[2 * below + 1] < y + 1) below = row_start[y + 1];
             while (below < n && xy[2 * below + 1] == y + 1 && xy[2 * below] < x - 1) ++below;
             for (int j = below; j < n && xy[2 * j + 1] == y + 1 && xy[2 * j] <= x + 1; ++j)
-                if (scores[j] >= s) {
+                if (nonmax_beats(scores[j], s)) {
                     dead = true;
                     break;
                 }

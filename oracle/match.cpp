@@ -27,13 +27,32 @@ extern "C" int ora_descriptor_distance(const uint8_t* a, const uint8_t* b) {
 
 // BFMatcher::match -> knnMatch(k=1): per query the FIRST minimum over the train rows.
 // crossCheck: (i,j) kept iff i is also the first minimum of train row j over the query rows.
+namespace {
+// Hamming distance of two 256-bit descriptors for the brute-force matcher: cv::BFMatcher uses OpenCV's normHamming (hardware
+// POPCNT where available), so the timed CPU-baseline build does too; the value is identical to DescriptorDistance
+inline int bf_distance(const uint8_t* a, const uint8_t* b) {
+#if defined(__POPCNT__)
+    int d = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t wa, wb;
+        std::memcpy(&wa, a + 8 * i, 8);
+        std::memcpy(&wb, b + 8 * i, 8);
+        d += __builtin_popcountll(wa ^ wb);
+    }
+    return d;
+#else
+    return ora_descriptor_distance(a, b);
+#endif
+}
+}  // namespace
+
 extern "C" void ora_match_bf(const uint8_t* A, int nA, const uint8_t* B, int nB, int cross_check, int32_t* train_idx,
                              int32_t* dist) {
     std::vector<int32_t> best_q(nB, -1), best_qd(nB, 1 << 30);
     for (int i = 0; i < nA; ++i) {
         int bj = -1, bd = 1 << 30;
         for (int j = 0; j < nB; ++j) {
-            const int d = ora_descriptor_distance(A + 32 * (size_t)i, B + 32 * (size_t)j);
+            const int d = bf_distance(A + 32 * (size_t)i, B + 32 * (size_t)j);
             if (d < bd) {
                 bd = d;
                 bj = j;

@@ -44,6 +44,8 @@ void ora_build_pyramid(const uint8_t* gray, int w, int h, int n_levels, uint8_t*
 int ora_fast10_detect(const uint8_t* img, int w, int h, int stride, int barrier, int16_t* xy, int cap);
 void ora_fast10_score(const uint8_t* img, int stride, const int16_t* xy, int n, int barrier, int32_t* scores);
 int ora_fast_nonmax_3x3(const int16_t* xy, const int32_t* scores, int n, int32_t* keep_idx);
+/* neighbour rule of fast_nonmax_3x3: 0 = ">=" (default, restated from memory of uzh-rpg/fast), 1 = ">" */
+void ora_set_fast_nonmax_strict(int strict);
 
 /* ---- FeatureDetector (src/Algorithm/FeatureDetector.cpp:299-596) ------------------------ */
 typedef struct {

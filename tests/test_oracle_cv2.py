@@ -145,3 +145,20 @@ def test_detect_semantics(oracle, synth_frames):
     # describe() on the detected pixels reproduces angle + descriptor
     ang, desc = oracle.describe(pyr, 640, 480, 3, f["px"], f["py"], f["level"])
     assert np.array_equal(ang, f["angle"]) and np.array_equal(desc, f["desc"])
+
+
+def test_fast_nonmax_rule_is_switchable(oracle, synth_frames):
+    """FAST-10 / fast_nonmax_3x3 stay PARITY UNPINNED (uzh-rpg/fast is not in the reference tree).  The one rule restated from
+    memory -- a corner dies when a neighbour scores ">=" -- is a flag of the oracle: with ">" the survivors are a superset
+    (ties keep both corners), everything else is unchanged."""
+    g = synth_frames[0][0]
+    xy = oracle.fast_detect(g)
+    sc = oracle.fast_score(g, xy)
+    keep_ge = oracle.fast_nonmax(xy, sc)
+    try:
+        oracle.lib.ora_set_fast_nonmax_strict(1)
+        keep_gt = oracle.fast_nonmax(xy, sc)
+    finally:
+        oracle.lib.ora_set_fast_nonmax_strict(0)
+    assert set(keep_ge.tolist()) <= set(keep_gt.tolist()) and len(keep_gt) >= len(keep_ge)
+    assert np.array_equal(oracle.fast_nonmax(xy, sc), keep_ge)

@@ -857,6 +857,12 @@ int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const y
     // cluster size: ~300 landmarks per CTA keep a problem's per-landmark state in shared memory and its FP64 work spread
     int cluster = 1;
     while (cluster < 8 && in.max_pts > (size_t)cluster * 320) cluster *= 2;
+    {   // many block pairs (free poses) per landmark chunk: the warp tasks of the reduced system dominate a trial, and their
+        // number per warp is (pairs + poses) * chunks / warps -- spread such problems over a 16-CTA cluster (non-portable size)
+        const size_t tasks = (size_t)std::max(in.max_free, 0) * (std::max(in.max_free, 0) + 1) / 2 + std::max(in.max_free, 0);
+        auto items_per_warp = [&](int c) { return tasks * (((in.max_pts + c - 1) / c + 31) / 32) / (kT / 32); };
+        while (cluster < 16 && items_per_warp(cluster) > 24) cluster *= 2;
+    }
     if (const char* e = getenv("YGZB_BA_CLUSTER")) {   // tuning knob: 1, 2, 4 or 8
         const int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) cluster = v;
