@@ -151,5 +151,46 @@ int main(int argc, char** argv) {
         printf("local_ba %s rms_px_before %.4f after %.6f kf0_moved %d\n", flavour == 0 ? "g2o" : "ceres", before, rms(),
                (int)(std::fabs(T0[3]) + std::fabs(T0[7]) + std::fabs(T0[11]) > 1e-12));
     }
+    {
+        // slot ownership: a live frame (e.g. a key-frame kept by Memory) keeps its device pyramid however many frames come
+        // and go; the pool reports exhaustion instead of recycling a live slot; the section-8b helpers are reachable
+        auto& rt = b200::Runtime::Get();
+        const int free0 = rt.FreeSlots();
+        Frame* keyframe = new Frame();
+        keyframe->_color.create(480, 640, 1);
+        std::memcpy(keyframe->_color.data, f1._color.data, 640 * 480);
+        keyframe->InitFrame();
+        const int kf_slot = keyframe->_slot;
+        for (int k = 0; k < 200; ++k) {   // 200 transient frames through a 64-slot pool
+            Frame tmp;
+            tmp._color.create(480, 640, 1);
+            std::memcpy(tmp._color.data, f2._color.data, 640 * 480);
+            tmp.InitFrame();
+            if (tmp._slot == kf_slot) return 10;
+        }
+        FeatureDetector det2;
+        det2.Detect(keyframe);   // its pyramid is still there
+        const size_t n_kf = keyframe->_features.size();
+        uint8_t before[32];
+        std::memcpy(before, keyframe->_features[0]->_desc, 32);
+        det2.ComputeDescriptor(keyframe->_features[0]);
+        const bool same_desc = std::memcmp(before, keyframe->_features[0]->_desc, 32) == 0;
+        bool exhausted = false;
+        std::vector<Frame*> hold;
+        try {
+            for (int k = 0; k < 100; ++k) {
+                hold.push_back(new Frame());
+                hold.back()->_color.create(480, 640, 1);
+                hold.back()->InitFrame();
+            }
+        } catch (const b200::Error&) {
+            exhausted = true;
+        }
+        for (Frame* f : hold) delete f;
+        delete keyframe;
+        const auto J = cvutils::JacobXYZ2Cam(Vector3d(0.1, -0.2, 2.0));
+        printf("slots keyframe_features %zu same_as_frame1 %d compute_descriptor_same %d exhausted %d free_restored %d jac %.6f\n", n_kf,
+               (int)(n_kf == f1._features.size()), (int)same_desc, (int)exhausted, (int)(rt.FreeSlots() == free0), J(0, 4));
+    }
     return 0;
 }

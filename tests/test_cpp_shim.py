@@ -65,3 +65,7 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     oc, op = lines[5].split(), lines[6].split()
     assert oc[0] == "optimize_current" and float(oc[2]) > 0.5 and float(oc[4]) < 1e-3 and oc[6] == "0"
     assert op[0] == "optimize_point_only" and float(op[2]) > 0.5 and float(op[4]) < 1e-3
+    # slot ownership (a live key-frame keeps its pyramid; exhaustion is reported, not silently recycled) and the 8b helpers
+    sl = lines[8].split()
+    assert sl[0] == "slots" and sl[4] == "1" and sl[6] == "1" and sl[8] == "1" and sl[10] == "1"
+    assert abs(float(sl[12]) - (-(1.0 + 0.1 * 0.1 / 4.0))) < 1e-9      # JacobXYZ2Cam(0.1, -0.2, 2)(0, 4) = -(1 + x^2/z^2)

@@ -27,6 +27,10 @@ def test_klt_matches_oracle_and_cv2(levels, ctx3, ctx8, oracle, synth_frames):
         both = wst & gst[s]
         d = np.abs(got[s][both] - want[both]).max(1)
         assert np.percentile(d, 99) < 0.01 and np.median(d) < 1e-3     # integer window sums vs f32 accumulation
+        # the tail is bounded too: measured max over ALL tracked points 6.1e-4 px, identical status flags (tools/klt_tail.py
+        # prints the worst points with their conditioning); the bound leaves a factor of ~8
+        worst = np.argsort(-d)[:5]
+        assert d.max() < 5e-3, [(float(d[i]), ref[np.nonzero(both)[0][i]].tolist()) for i in worst]
         assert np.abs(gerr[s][both] - werr[both]).max() < 0.05
         cvp, cvs, _ = cv2.calcOpticalFlowPyrLK(g1, cur, ref.copy(), init.copy(), winSize=(21, 21), maxLevel=4,
                                                criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.001),

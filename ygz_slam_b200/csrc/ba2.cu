@@ -245,6 +245,57 @@ __device__ bool warp_ldlt_solve(double* S, double* b, double* rd, int dimp, int 
     return true;
 }
 
+// The same solve for a small system of compile-time size N (6 or 12: one or two free poses, the local BA of the tracking
+// loop) by ONE thread with everything in registers and every loop unrolled: no shared-memory round trips, no shuffles, the
+// reciprocal of a pivot overlaps the dot products of the next column (the warp version spends ~1000 cycles per column on
+// dependent shared-memory / shuffle latency).
+template <int N>
+__device__ __noinline__ bool thread_ldlt_solve(const double* __restrict__ S, double* __restrict__ b) {
+    double L[N][N], D[N], rD[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L[i][j] = S[i * N + j];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double d = L[j][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+        D[j] = d;
+        ok = ok && (d > 0);
+        rD[j] = fast_rcp(d);
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            double t = L[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = t * rD[j];
+        }
+    }
+    if (!ok) return false;
+    double y[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double t = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) t -= L[i][k] * y[k];
+        y[i] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] *= rD[i];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        double t = y[i];
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) t -= L[k][i] * y[k];
+        y[i] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) b[i] = y[i];
+    return true;
+}
+
 __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double s_dyn[];
@@ -600,8 +651,19 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
             tick(2);
             // ---- warp 0: dense Cholesky + triangular solves, then VertexSE3Sophus::oplusImpl for the trial poses
             if (warp == 0) {
-                const bool ok = dimp == 0 || warp_ldlt_solve(s_S, s_bs, s_rd, dimp, lane);
-                if (lane == 0) s_ok = ok ? 1 : 0;
+                bool ok = true;
+                if (false && (dimp == 12 || dimp == 6)) {   // register-resident solve by one lane: measured SLOWER (23.9k vs 12.2k cycles
+                    // per trial at 12x12): a dependent FP64 operation costs ~40 cycles here, the warp version has shorter chains
+                    if (lane == 0) {
+                        ok = dimp == 12 ? thread_ldlt_solve<12>(s_S, s_bs) : thread_ldlt_solve<6>(s_S, s_bs);
+                        s_ok = ok ? 1 : 0;
+                    }
+                    __syncwarp();
+                    ok = s_ok != 0;
+                } else {
+                    ok = dimp == 0 || warp_ldlt_solve(s_S, s_bs, s_rd, dimp, lane);
+                    if (lane == 0) s_ok = ok ? 1 : 0;
+                }
                 for (int i = lane; i < dimp; i += 32) s_xp[i] = ok ? s_bs[i] : 0.0;
             }
             __syncthreads();

@@ -37,6 +37,7 @@ constexpr int W = 640, H = 480;
 constexpr int kLocalKeyframes = 3;                                 // LocalMapping.local_keyframes (default.yaml:68)
 constexpr int kSlotsPerStream = kLocalKeyframes + 2;
 constexpr int kMinInliers = 30;                                    // vo.keyframe.min_features (default.yaml:66)
+constexpr int kSpeculativeFrames = 3;                              // engine: frames tracked ahead once a key-frame may trigger any time
 
 struct Mat34 {
     double m[12];
@@ -581,8 +582,14 @@ class Engine {
                 s.next_frame = stop;
                 continue;
             }
+            // window: up to and including the first frame that may become a key-frame; past that point every frame may, and a
+            // few frames are tracked speculatively -- the ones behind a key-frame trigger are dropped and tracked again against
+            // the new key-frame next round (results stay those of frame-by-frame processing)
             int w = 1;
-            if (!s.kfs.empty()) w = std::min(F_, std::max(1, prm_.kf_min_frames - s.frames_since_kf));
+            if (!s.kfs.empty()) {
+                const int sure = prm_.kf_min_frames - s.frames_since_kf;
+                w = sure >= 1 ? std::min(F_, sure) : std::min(F_, kSpeculativeFrames);
+            }
             w = std::min(w, stop - s.next_frame);
             CHK(ygzb_frames_upload(fr_, i * F_, w, images[i] + (size_t)s.next_frame * W * H, 1, (size_t)W * H));
             h2d_image_bytes += (long long)w * W * H;
@@ -645,7 +652,7 @@ class Engine {
                     kjobs.push_back(make_kf_job(b.stream, b.stream * F_ + t, b.job0 + t));
                     kframe.push_back(b.first + t);
                     ++t;
-                    break;   // (by construction the last frame of the window)
+                    break;   // frames of the window behind the key-frame (speculative ones) are dropped: tracked again next round
                 }
             }
             if (s.lost) {

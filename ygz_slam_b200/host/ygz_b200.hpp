@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstring>
 #include <list>
+#include <cmath>
 #include <map>
 #include <memory>
 #include <set>
@@ -118,7 +119,7 @@ class PinholeCamera {  // include/ygz/Basic/Camera.h:10-112
 
 struct Frame {  // include/ygz/Basic/Frame.h:20-166 (fields used on the hot path)
     struct Option { int _pyramid_level = 3; } _option;
-    ~Frame() { CleanAllFeatures(); }
+    ~Frame();          // releases the device pyramid slot: a frame pins its slot for as long as it lives (key-frames in Memory: for good)
     void InitFrame();  // cvtColor + pyrDown chain (src/Basic/Frame.cpp:22-40) -> device pyramid
     bool InFrame(const Vector2d& px, const int& boarder = 10) const {
         return px[0] >= boarder && px[0] < _color.cols - boarder && px[1] >= boarder && px[1] < _color.rows - boarder;
@@ -161,20 +162,31 @@ class Runtime {
         Check(ygzb_frames_create(ctx_, slots, &frames_), "ygzb_frames_create");
         params_ = p;
         owner_.assign(slots, nullptr);
-        next_ = 0;
+        free_.clear();
+        for (int i = slots - 1; i >= 0; --i) free_.push_back(i);   // slot 0 is handed out first
     }
     ygzb_ctx* ctx() { Ensure(); return ctx_; }
     ygzb_frames* frames() { Ensure(); return frames_; }
     const ygzb_params& params() { Ensure(); return params_; }
-    // round-robin slot assignment; a frame whose slot was recycled must call InitFrame again
+    // explicit slot ownership: a Frame pins its slot from InitFrame until it is destroyed (the reference keeps the cv::Mat
+    // pyramid alive through the Frame object, Frame.h:138; Memory keeps key-frames forever, Memory.cpp:7-19), so a live
+    // key-frame can never lose its pyramid.  Running out of slots is an error the caller sees: Configure(.., slots) sizes the pool.
     int AcquireSlot(Frame* f) {
         Ensure();
-        const int s = next_;
-        next_ = (next_ + 1) % (int)owner_.size();
-        if (owner_[s]) owner_[s]->_slot = -1;
+        if (free_.empty()) throw Error("out of device frame slots: " + std::to_string(owner_.size()) +
+                                       " frames are alive; raise the `slots` argument of b200::Runtime::Configure");
+        const int s = free_.back();
+        free_.pop_back();
         owner_[s] = f;
         return s;
     }
+    void ReleaseSlot(Frame* f, int s) {
+        if (s >= 0 && s < (int)owner_.size() && owner_[s] == f) {
+            owner_[s] = nullptr;
+            free_.push_back(s);
+        }
+    }
+    int FreeSlots() const { return (int)free_.size(); }
     void Check(int rc, const char* what) {
         if (rc != YGZB_OK) throw Error(std::string(what) + ": " + (ctx_ ? ygzb_last_error(ctx_) : "?"));
     }
@@ -197,20 +209,25 @@ class Runtime {
     ygzb_frames* frames_ = nullptr;
     ygzb_params params_{};
     std::vector<Frame*> owner_;
-    int next_ = 0;
+    std::vector<int> free_;
 };
 
 inline int SlotOf(Frame* f) {
-    if (f->_slot < 0) throw Error("Frame::InitFrame() has not been called (or its device slot was recycled)");
+    if (f->_slot < 0) throw Error("Frame::InitFrame() has not been called");
     return f->_slot;
 }
 inline void PoseTo3x4(const SE3& T, double* out) { T.matrix3x4(out); }
 
 }  // namespace b200
 
+inline Frame::~Frame() {
+    CleanAllFeatures();
+    if (_slot >= 0) b200::Runtime::Get().ReleaseSlot(this, _slot);
+}
+
 inline void Frame::InitFrame() {
     auto& rt = b200::Runtime::Get();
-    _slot = rt.AcquireSlot(this);
+    if (_slot < 0) _slot = rt.AcquireSlot(this);   // (a second InitFrame of the same frame re-uses its slot)
     rt.Check(ygzb_frames_upload(rt.frames(), _slot, 1, _color.data, _color.channels, (size_t)_color.rows * _color.cols * _color.channels),
              "ygzb_frames_upload");
 }
@@ -282,9 +299,56 @@ class FeatureDetector {  // include/ygz/Algorithm/FeatureDetector.h
             std::memcpy(frame->_features[i]->_desc, &desc[(size_t)i * 32], 32);
         }
     }
+    // FeatureDetector.cpp:591-594 (no caller in the reference).  The reference rebuilds the descriptor with the angle the
+    // feature carries; a feature that came out of Detect / ComputeAngleAndDescriptor carries the IC angle of its pixel, which is
+    // what the device computes, so the descriptor is the same and the angle is left untouched.
+    void ComputeDescriptor(Feature* fea) {
+        auto& rt = b200::Runtime::Get();
+        const double x = fea->_pixel[0], y = fea->_pixel[1];
+        const uint8_t level = (uint8_t)fea->_level;
+        float angle = 0;
+        const int32_t slot = b200::SlotOf(fea->_frame), off[2] = {0, 1};
+        rt.Check(ygzb_describe(rt.frames(), &slot, 1, off, &x, &y, &level, &angle, fea->_desc), "ygzb_describe");
+    }
 };
 
 namespace cvutils {
+// Host-side helpers of include/ygz/Algorithm/CVUtils.h that the reference's callers use directly (pure arithmetic: the device
+// kernels carry their own copies).  Matrix<double,2,6> is a plain row-major array here.
+struct Matrix26d {
+    double m[2][6];
+    double operator()(int r, int c) const { return m[r][c]; }
+    double& operator()(int r, int c) { return m[r][c]; }
+};
+// CVUtils.h:77-99 (translation first, already negated)
+inline Matrix26d JacobXYZ2Cam(const Vector3d& xyz) {
+    Matrix26d J;
+    const double x = xyz[0], y = xyz[1], z_inv = 1. / xyz[2], z_inv_2 = z_inv * z_inv;
+    J(0, 0) = -z_inv; J(0, 1) = 0.0; J(0, 2) = x * z_inv_2; J(0, 3) = y * J(0, 2); J(0, 4) = -(1.0 + x * J(0, 2)); J(0, 5) = y * z_inv;
+    J(1, 0) = 0.0; J(1, 1) = -z_inv; J(1, 2) = y * z_inv_2; J(1, 3) = 1.0 + y * J(1, 2); J(1, 4) = -J(0, 3); J(1, 5) = -x * z_inv;
+    return J;
+}
+// CVUtils.h:101-126
+inline Matrix26d JacobXYZ2Pixel(const Vector3d& xyz, PinholeCamera* cam) {
+    Matrix26d J;
+    const double x = xyz[0], y = xyz[1], z_inv = 1. / xyz[2], z_inv_2 = z_inv * z_inv;
+    J(0, 0) = -z_inv * cam->fx(); J(0, 1) = 0.0; J(0, 2) = x * z_inv_2 * cam->fx(); J(0, 3) = cam->fx() * y * J(0, 2);
+    J(0, 4) = -cam->fx() * (1.0 + x * J(0, 2)); J(0, 5) = cam->fx() * y * z_inv;
+    J(1, 0) = 0.0; J(1, 1) = -cam->fy() * z_inv; J(1, 2) = cam->fy() * y * z_inv_2; J(1, 3) = cam->fy() * (1.0 + y * J(1, 2));
+    J(1, 4) = -cam->fy() * x * J(1, 2); J(1, 5) = -cam->fy() * x * z_inv;
+    return J;
+}
+// CVUtils.h:59-71 / :41-57 on a host-resident single-channel image (row pitch = cols)
+inline uint8_t GetBilateralInterpUchar(const double& x, const double& y, const Mat& gray) {
+    const double xx = x - std::floor(x), yy = y - std::floor(y);
+    const uint8_t* d = &gray.data[(size_t)int(y) * gray.cols + int(x)];
+    return uint8_t((1 - xx) * (1 - yy) * d[0] + xx * (1 - yy) * d[1] + (1 - xx) * yy * d[gray.cols] + xx * yy * d[gray.cols + 1]);
+}
+inline float GetBilateralInterp(const double& x, const double& y, const Mat& gray) {
+    const double xx = x - std::floor(x), yy = y - std::floor(y);
+    const uint8_t* d = &gray.data[(size_t)int(y) * gray.cols + int(x)];
+    return float((1 - xx) * (1 - yy) * d[0] + xx * (1 - yy) * d[1] + (1 - xx) * yy * d[gray.cols] + xx * yy * d[gray.cols + 1]);
+}
 // include/ygz/Algorithm/CVUtils.h:163-169 -- cur_img is identified by (frame, level) instead of a cv::Mat
 inline bool Align2D(Frame* cur, int level, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter, Vector2d& cur_px_estimate) {
     auto& rt = b200::Runtime::Get();
