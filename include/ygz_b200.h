@@ -230,6 +230,16 @@ int ygzb_local_ba_ceres(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, co
                         double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
                         const double* obs_px, int max_iters, double huber_a, ygzb_ceres_stats* stats);
 
+/* replaces ba::TwoViewBACeres (src/Algorithm/BA.cpp:11-89; BA.h:23-30), the two-view bundle adjustment after the monocular
+ * initialisation, for n_problems independent frame pairs: pair p owns points [offsets[p], offsets[p+1]) of px_ref / px_cur
+ * (pixels), inlier (in/out) and pts (world points, in/out); T_cw_ref stays fixed (point-only residual blocks), T_cw_cur and
+ * the points are refined; points that come in as non-inliers restart from (0,0,1) with ceres::HuberLoss(0.1) on their two
+ * blocks (:31-56); afterwards inlier[i] = both squared pixel errors <= 5.991 and both depths positive (:70-84).
+ * Solver: the trust-region Levenberg-Marquardt of ygzb_local_ba_ceres on the identical cost (the reference selects
+ * ceres::DOGLEG; both strategies converge to the same minimum within the function tolerance).                   */
+int ygzb_two_view_ba(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const double* T_cw_ref, double* T_cw_cur,
+                     const double* px_ref, const double* px_cur, uint8_t* inlier, double* pts, ygzb_ceres_stats* stats);
+
 /* replaces ba::OptimizeCurrentPoseOnly (src/Algorithm/BA.cpp:188-264; BA.h:44-46) with
  * CeresReprojectionErrorPoseOnly (include/ygz/Ceres/CeresReprojectionErrorPoseOnly.h): four rounds of
  * trust-region LM on [t; angle-axis] with re-classification of the observations between rounds.

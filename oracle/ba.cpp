@@ -681,9 +681,21 @@ struct CeresBA {
 
 }  // namespace
 
+static int ceres_ba_impl(const ora_camera* camp, int n_kf, double* poses, const uint8_t* fixed, int n_pt, double* pts,
+                         int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px, int max_iters,
+                         double huber_a, const uint8_t* loss_mask, ora_ceres_stats* stats);
+
 extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* poses, const uint8_t* fixed, int n_pt, double* pts,
                                   int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px, int max_iters,
                                   double huber_a, ora_ceres_stats* stats) {
+    return ceres_ba_impl(camp, n_kf, poses, fixed, n_pt, pts, n_obs, kf_idx, pt_idx, obs_px, max_iters, huber_a, nullptr, stats);
+}
+
+// loss_mask (may be NULL = every block): the residual blocks that carry ceres::HuberLoss(huber_a); the others have no loss
+// (AddResidualBlock(cost, inlier ? nullptr : new HuberLoss(0.1), ...), BA.cpp:38-56)
+static int ceres_ba_impl(const ora_camera* camp, int n_kf, double* poses, const uint8_t* fixed, int n_pt, double* pts,
+                         int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px, int max_iters,
+                         double huber_a, const uint8_t* loss_mask, ora_ceres_stats* stats) {
     const float fx = camp->fx, fy = camp->fy, cx = camp->cx, cy = camp->cy;
     CeresBA pb;
     pb.n_kf = n_kf; pb.n_pt = n_pt; pb.n_obs = n_obs;
@@ -714,7 +726,7 @@ extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* pose
         double c = 0;
         for (int o = 0; o < n_obs; ++o) {
             const double s2 = res[2 * (size_t)o] * res[2 * (size_t)o] + res[2 * (size_t)o + 1] * res[2 * (size_t)o + 1];
-            if (huber_a > 0 && s2 > huber_a * huber_a) {
+            if (huber_a > 0 && (!loss_mask || loss_mask[o]) && s2 > huber_a * huber_a) {
                 const double rt = std::sqrt(s2);
                 c += 2 * huber_a * rt - huber_a * huber_a;
                 if (w) (*w)[o] = huber_a / rt;
@@ -907,4 +919,51 @@ extern "C" int ora_local_ba_ceres(const ora_camera* camp, int n_kf, double* pose
         stats->termination = termination;
     }
     return iters;
+}
+
+// ba::TwoViewBACeres (src/Algorithm/BA.cpp:11-89): two-view bundle adjustment after the monocular initialisation.  The
+// reference frame is fixed (CeresReprojectionErrorPointOnly blocks), the current pose [t; angle-axis] and every point are
+// free; points that are not inliers are reset to (0, 0, 1) and their two blocks carry HuberLoss(0.1) (:31-56); afterwards a
+// point is an inlier iff both pixel errors are <= 5.991 (squared) and both depths are positive (:70-84).
+// The reference solves with DENSE_SCHUR + DOGLEG; Ceres is not in the reference tree, and this restatement (like the CUDA
+// path) runs the same trust-region LEVENBERG-MARQUARDT as ba::LocalBA on the identical cost -- both strategies stop at the
+// same local minimum up to the solver's function tolerance (1e-6), which the tests bound.
+extern "C" int ora_two_view_ba(const ora_camera* cam, int n, const double* T_cw_ref, double* T_cw_cur, const double* px_ref,
+                               const double* px_cur, uint8_t* inlier, double* pts, ora_ceres_stats* stats) {
+    const SE3 Tr = SE3::from_mat(T_cw_ref), Tc = SE3::from_mat(T_cw_cur);
+    double poses[12];
+    const V3 lr = Tr.so3.log(), lc = Tc.so3.log();
+    poses[0] = Tr.t.x; poses[1] = Tr.t.y; poses[2] = Tr.t.z; poses[3] = lr.x; poses[4] = lr.y; poses[5] = lr.z;
+    poses[6] = Tc.t.x; poses[7] = Tc.t.y; poses[8] = Tc.t.z; poses[9] = lc.x; poses[10] = lc.y; poses[11] = lc.z;
+    const uint8_t fixed[2] = {1, 0};
+    std::vector<int32_t> kf(2 * (size_t)n), pt(2 * (size_t)n);
+    std::vector<double> obs(4 * (size_t)n);
+    std::vector<uint8_t> mask(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        if (!inlier[i]) {
+            pts[3 * i] = 0; pts[3 * i + 1] = 0; pts[3 * i + 2] = 1;
+        }
+        kf[2 * i] = 0; kf[2 * i + 1] = 1;
+        pt[2 * i] = pt[2 * i + 1] = i;
+        obs[4 * i] = px_ref[2 * i]; obs[4 * i + 1] = px_ref[2 * i + 1]; obs[4 * i + 2] = px_cur[2 * i]; obs[4 * i + 3] = px_cur[2 * i + 1];
+        mask[2 * i] = mask[2 * i + 1] = inlier[i] ? 0 : 1;
+    }
+    ceres_ba_impl(cam, 2, poses, fixed, n, pts, 2 * n, kf.data(), pt.data(), obs.data(), 50, 0.1, mask.data(), stats);
+    SE3 Tn;
+    Tn.so3 = SO3::exp(V3{poses[9], poses[10], poses[11]});
+    Tn.t = V3{poses[6], poses[7], poses[8]};
+    Tn.to_mat(T_cw_cur);
+    const float fx = cam->fx, fy = cam->fy, cx = cam->cx, cy = cam->cy;
+    int n_in = 0;
+    for (int i = 0; i < n; ++i) {
+        const V3 X{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        const V3 p1 = Tr * X, p2 = Tn * X;
+        const double e1x = px_ref[2 * i] - (fx * p1.x / p1.z + cx), e1y = px_ref[2 * i + 1] - (fy * p1.y / p1.z + cy);
+        const double e2x = px_cur[2 * i] - (fx * p2.x / p2.z + cx), e2y = px_cur[2 * i + 1] - (fy * p2.y / p2.z + cy);
+        if (e1x * e1x + e1y * e1y > 5.991 || e2x * e2x + e2y * e2y > 5.991) inlier[i] = 0;
+        else if (p1.z < 0 || p2.z < 0) inlier[i] = 0;
+        else inlier[i] = 1;
+        n_in += inlier[i];
+    }
+    return n_in;
 }

@@ -154,6 +154,12 @@ int ora_local_ba_ceres(const ora_camera* cam, int n_kf, double* poses, const uin
                        int n_obs, const int32_t* kf_idx, const int32_t* pt_idx, const double* obs_px, int max_iters,
                        double huber_a /* ceres::HuberLoss(a) on every block, 0 = no loss */, ora_ceres_stats* stats);
 
+/* ba::TwoViewBACeres (BA.cpp:11-89): ref pose fixed, current pose and points free, HuberLoss(0.1) on the blocks of the
+ * non-inlier points (which restart from (0,0,1)); inlier[] in/out, returns the inlier count.  Trust-region LM instead of the
+ * reference's DOGLEG strategy (same cost, same minimum up to the function tolerance). */
+int ora_two_view_ba(const ora_camera* cam, int n, const double* T_cw_ref, double* T_cw_cur, const double* px_ref,
+                    const double* px_cur, uint8_t* inlier, double* pts, ora_ceres_stats* stats);
+
 /* ba::OptimizeCurrentPoseOnly (BA.cpp:188-264).  T_cw in/out, inlier[] out (1 = !_bad), depth[] out */
 int ora_pose_only(const ora_camera* cam, int n, const double* pt_world /*3n*/, const double* px /*2n*/,
                   double* T_cw, uint8_t* inlier, double* depth);

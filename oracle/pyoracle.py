@@ -295,6 +295,19 @@ class Oracle:
                                     max_iters, C.c_double(huber), C.byref(st))
         return poses, pts, {k: getattr(st, k) for k, _ in CeresStats._fields_}
 
+    def two_view_ba(self, T_ref, T_cur, px_ref, px_cur, inlier, pts, cam=None):
+        """ba::TwoViewBACeres: returns (T_cur 3x4, inlier bool, pts, stats, inlier count)."""
+        cam = cam or default_camera()
+        n = len(px_ref)
+        Tr = np.ascontiguousarray(T_ref, np.float64).reshape(12)
+        Tc = np.ascontiguousarray(T_cur, np.float64).reshape(12).copy()
+        inl = np.ascontiguousarray(inlier, np.uint8).copy()
+        X = np.ascontiguousarray(pts, np.float64).reshape(n, 3).copy()
+        st = CeresStats()
+        cnt = self.lib.ora_two_view_ba(C.byref(cam), n, _p(Tr), _p(Tc), _p(np.ascontiguousarray(px_ref, np.float64)),
+                                       _p(np.ascontiguousarray(px_cur, np.float64)), _p(inl), _p(X), C.byref(st))
+        return Tc.reshape(3, 4), inl.astype(bool), X, {k: getattr(st, k) for k, _ in CeresStats._fields_}, int(cnt)
+
     def pose_only(self, pt_world, px, T_cw, cam=None):
         cam = cam or default_camera()
         n = len(pt_world)

@@ -151,3 +151,22 @@ def test_local_ba_ceres_huber_and_point_only(ctx3, oracle):
     assert np.array_equal(P2, Pt)
     assert np.abs(X2 - wX2).max() < 1e-6 and st2[0]["iters"] == wst2["iters"]
     assert np.median(np.abs(X2 - sc["pts_true"])) < 0.02
+
+
+def test_two_view_ba_matches_oracle(ctx3, oracle):
+    """ba::TwoViewBACeres (BA.cpp:11-89) on the Ceres-flavoured kernel with a per-block loss mask: two problems in one call
+    against the oracle -- pose < 1e-4, points < 1e-4 m (scene scale 2-5 m), identical inlier flags and termination."""
+    from tests.test_oracle_ba import two_view_scene
+    scs = [two_view_scene(21, 120, 12), two_view_scene(22, 75, 5)]
+    offs = np.cumsum([0] + [len(s["X"]) for s in scs]).astype(np.int32)
+    T, inl, X, st = ctx3.two_view_ba(offs, np.stack([s["T_ref"] for s in scs]), np.stack([s["T_cur0"] for s in scs]),
+                                     np.concatenate([s["px_ref"] for s in scs]), np.concatenate([s["px_cur"] for s in scs]),
+                                     np.concatenate([s["inlier"] for s in scs]), np.concatenate([s["X0"] for s in scs]))
+    for p, s in enumerate(scs):
+        wT, winl, wX, wst, cnt = oracle.two_view_ba(s["T_ref"], s["T_cur0"], s["px_ref"], s["px_cur"], s["inlier"], s["X0"])
+        sl = slice(offs[p], offs[p + 1])
+        assert np.linalg.norm(se3.se3_log(se3.mul(se3.inv(T[p]), wT))) < 1e-4
+        assert np.abs(X[sl] - wX).max() < 1e-4
+        assert np.array_equal(inl[sl], winl)
+        assert st[p]["iters"] == wst["iters"] and st[p]["termination"] == wst["termination"]
+        assert abs(st[p]["cost_final"] - wst["cost_final"]) < 1e-9 * max(wst["cost_final"], 1e-12) + 1e-15

@@ -38,7 +38,7 @@ EXPORTS = [
     "ygzb_frames_upload", "ygzb_frames_copy", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
     "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d", "ygzb_align1d",
-    "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_pose_only",
+    "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_two_view_ba", "ygzb_pose_only",
     "ygzb_default_klt_params", "ygzb_klt",
     "ygzb_tracker_create", "ygzb_tracker_destroy", "ygzb_tracker_set_depth", "ygzb_tracker_track", "ygzb_tracker_make_keyframes",
 ]
@@ -499,9 +499,25 @@ def _pose_only(self, offsets, pt_world, px, T_cw):
     return T.reshape(P, 3, 4), inl.astype(bool), depth, cnt
 
 
+def _two_view_ba(self, offsets, T_ref, T_cur, px_ref, px_cur, inlier, pts):
+    """Batched ba::TwoViewBACeres.  Returns (T_cur (P,3,4), inlier bool, pts, stats)."""
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    P = len(offsets) - 1
+    n = int(offsets[-1])
+    Tr = np.ascontiguousarray(T_ref, np.float64).reshape(P, 12)
+    Tc = np.ascontiguousarray(T_cur, np.float64).reshape(P, 12).copy()
+    inl = np.ascontiguousarray(inlier, np.uint8).copy()
+    X = np.ascontiguousarray(pts, np.float64).reshape(n, 3).copy()
+    st = (CeresStats * P)()
+    self.check(self.lib.ygzb_two_view_ba(self.h, P, _p(offsets), _p(Tr), _p(Tc), _p(np.ascontiguousarray(px_ref, np.float64)),
+                                         _p(np.ascontiguousarray(px_cur, np.float64)), _p(inl), _p(X), st), "ygzb_two_view_ba")
+    return Tc.reshape(P, 3, 4), inl.astype(bool), X, [{k: getattr(s_, k) for k, _ in CeresStats._fields_} for s_ in st]
+
+
 Context.local_ba = _local_ba
 Context.local_ba_ceres = _local_ba_ceres
 Context.pose_only = _pose_only
+Context.two_view_ba = _two_view_ba
 
 
 # ---- KLT (method attached to Frames) -------------------------------------------------------------------

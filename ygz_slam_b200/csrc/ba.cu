@@ -75,6 +75,7 @@ struct BAArgs {
     float fx, fy, cx, cy;
     int max_iters, max_trials;
     double huber_delta, chi2_outlier, tau;
+    const uint8_t* loss_mask;   // Ceres twin: residual blocks that carry the HuberLoss (null = all of them)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                                 (a.obs[2 * (size_t)(o0 + o)] - cx) / fx, (a.obs[2 * (size_t)(o0 + o) + 1] - cy) / fy, rec);
                 // ceres::HuberLoss through the Corrector: rho'' <= 0, so the block is weighted by rho' = a / |r| beyond a
                 const double e2 = rec[0] * rec[0] + rec[1] * rec[1];
-                if (a.huber_delta > 0 && e2 > dsqr) {
+                if (a.huber_delta > 0 && e2 > dsqr && (!a.loss_mask || a.loss_mask[o0 + o])) {
                     const double rt = sqrt(e2);
                     rec[2] = a.huber_delta / rt;
                     acc += 2 * a.huber_delta * rt - dsqr;
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                     double e0, e1, x, y, z;
                     reproject(o, &e0, &e1, &x, &y, &z);
                     const double e2n = e0 * e0 + e1 * e1;
-                    newc += (a.huber_delta > 0 && e2n > dsqr) ? 2 * a.huber_delta * sqrt(e2n) - dsqr : e2n;
+                    newc += (a.huber_delta > 0 && e2n > dsqr && (!a.loss_mask || a.loss_mask[o0 + o])) ? 2 * a.huber_delta * sqrt(e2n) - dsqr : e2n;
                     const double* rec = a.lin + 21 * (size_t)(o0 + o);
                     const int fi = s_free[a.kf_idx[o0 + o]];
                     const double* dl = a.xl + 3 * (size_t)(p0 + a.pt_idx[o0 + o]);
@@ -1378,7 +1379,8 @@ int run_local_ba2(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, const in
 // one cluster launch, results back.  hst receives the 8 raw statistics of every problem.
 int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_off, const int32_t* pt_off, const int32_t* obs_off,
                  double* poses, const uint8_t* fixed, double* pts, const int32_t* kf_idx, const int32_t* pt_idx,
-                 const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, std::vector<double>& hst) {
+                 const double* obs_px, const ygzb_ba_params* prm, uint8_t* outlier, std::vector<double>& hst,
+                 const uint8_t* loss_mask = nullptr) {
     cudaSetDevice(ctx->device);
     for (const auto& oc : {std::make_pair(kf_off, "kf_off"), std::make_pair(pt_off, "pt_off"), std::make_pair(obs_off, "obs_off")}) {
         const int rc = check_offsets(ctx, oc.first, n_problems, oc.second);
@@ -1528,6 +1530,13 @@ int run_local_ba(ygzb_ctx* ctx, bool ceres, int n_problems, const int32_t* kf_of
     a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
     a.max_iters = prm->max_iters; a.max_trials = prm->max_trials; a.huber_delta = prm->huber_delta;
     a.chi2_outlier = prm->chi2_outlier; a.tau = prm->tau;
+    a.loss_mask = nullptr;
+    if (loss_mask && NO) {
+        uint8_t* d_mask = static_cast<uint8_t*>(dev_scratch(ctx, 4, NO));
+        if (!d_mask) return YGZB_ERR_CUDA;
+        YGZB_CUDA(ctx, cudaMemcpyAsync(d_mask, loss_mask, NO, cudaMemcpyHostToDevice, ctx->stream));
+        a.loss_mask = d_mask;
+    }
     const int dimp = 6 * std::max(max_free, 1);
     const size_t smem = sizeof(double) * ((size_t)dimp * dimp + (size_t)dimp);
     ClusterWs* d_ws = static_cast<ClusterWs*>(dev_scratch(ctx, 5, sizeof(ClusterWs) * P));
@@ -1632,6 +1641,126 @@ int ygzb_local_ba_ceres(ygzb_ctx* ctx, int n_problems, const int32_t* kf_off, co
             stats[p].radius_final = hst[8 * p + 4];
             stats[p].termination = (int)hst[8 * p + 5];
         }
+    return YGZB_OK;
+}
+
+// ba::TwoViewBACeres (reference src/Algorithm/BA.cpp:11-89) for a batch of two-view problems, on the Ceres-flavoured
+// cluster kernel: reference pose fixed (point-only blocks), current pose and points free, HuberLoss(0.1) on the blocks of the
+// non-inlier points, then the reference's inlier test (classification kernel below)
+__global__ void two_view_classify_kernel(int n, const int32_t* __restrict__ prob_of, const double* __restrict__ T_ref,
+                                         const double* __restrict__ poses, const double* __restrict__ pts, const double* __restrict__ px_ref,
+                                         const double* __restrict__ px_cur, float fx, float fy, float cx, float cy, uint8_t* __restrict__ inlier,
+                                         double* __restrict__ T_cur_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = prob_of[i];
+    const double* Tr = T_ref + 12 * (size_t)p;
+    const double* pc = poses + 12 * (size_t)p + 6;   // [t; angle-axis] of the current frame
+    double th;
+    SE3d Tc;
+    Tc.q = so3_exp(V3d{pc[3], pc[4], pc[5]}, &th);
+    Tc.t = V3d{pc[0], pc[1], pc[2]};
+    double Tm[12];
+    se3_to_mat(Tc, Tm);
+    if (i == 0 || prob_of[i - 1] != p)
+        for (int c = 0; c < 12; ++c) T_cur_out[12 * (size_t)p + c] = Tm[c];
+    const double X = pts[3 * (size_t)i], Y = pts[3 * (size_t)i + 1], Z = pts[3 * (size_t)i + 2];
+    const double x1 = Tr[0] * X + Tr[1] * Y + Tr[2] * Z + Tr[3], y1 = Tr[4] * X + Tr[5] * Y + Tr[6] * Z + Tr[7], z1 = Tr[8] * X + Tr[9] * Y + Tr[10] * Z + Tr[11];
+    const double x2 = Tm[0] * X + Tm[1] * Y + Tm[2] * Z + Tm[3], y2 = Tm[4] * X + Tm[5] * Y + Tm[6] * Z + Tm[7], z2 = Tm[8] * X + Tm[9] * Y + Tm[10] * Z + Tm[11];
+    const double e1x = px_ref[2 * (size_t)i] - (fx * x1 / z1 + cx), e1y = px_ref[2 * (size_t)i + 1] - (fy * y1 / z1 + cy);
+    const double e2x = px_cur[2 * (size_t)i] - (fx * x2 / z2 + cx), e2y = px_cur[2 * (size_t)i + 1] - (fy * y2 / z2 + cy);
+    uint8_t in = 1;
+    if (e1x * e1x + e1y * e1y > 5.991 || e2x * e2x + e2y * e2y > 5.991) in = 0;   // BA.cpp:70-77
+    else if (z1 < 0 || z2 < 0) in = 0;                                            // :78-81
+    inlier[i] = in;
+}
+
+int ygzb_two_view_ba(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const double* T_cw_ref, double* T_cw_cur, const double* px_ref,
+                     const double* px_cur, uint8_t* inlier, double* pts, ygzb_ceres_stats* stats) {
+    if (!ctx || n_problems < 1 || !offsets || !T_cw_ref || !T_cw_cur) return YGZB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    {
+        const int rc = check_offsets(ctx, offsets, n_problems, "offsets");
+        if (rc != YGZB_OK) return rc;
+    }
+    const size_t P = (size_t)n_problems, N = (size_t)offsets[n_problems];
+    if (N && (!px_ref || !px_cur || !inlier || !pts)) return YGZB_ERR_INVALID;
+    try {
+        std::vector<int32_t> kf_off(P + 1), pt_off(offsets, offsets + P + 1), obs_off(P + 1), kf_idx(2 * N), pt_idx(2 * N), prob_of(N);
+        std::vector<double> poses(12 * P), obs(4 * N), X(pts, pts + 3 * N);
+        std::vector<uint8_t> fixed(2 * P), mask(2 * N);
+        for (size_t p = 0; p < P; ++p) {
+            kf_off[p] = (int32_t)(2 * p);
+            obs_off[p] = 2 * offsets[p];
+            fixed[2 * p] = 1;   // the reference frame: CeresReprojectionErrorPointOnly blocks (BA.cpp:33-43)
+            fixed[2 * p + 1] = 0;
+            for (int k = 0; k < 2; ++k) {   // pose = [translation; so3 log] (BA.cpp:24-26)
+                const SE3d T = se3_from_mat((k ? T_cw_cur : T_cw_ref) + 12 * p);
+                double th;
+                const V3d l = so3_log(T.q, &th);
+                double* o = &poses[12 * p + 6 * k];
+                o[0] = T.t.x; o[1] = T.t.y; o[2] = T.t.z; o[3] = l.x; o[4] = l.y; o[5] = l.z;
+            }
+            for (int i = offsets[p]; i < offsets[p + 1]; ++i) {
+                const int li = i - offsets[p];
+                prob_of[i] = (int32_t)p;
+                if (!inlier[i]) {   // BA.cpp:35-37
+                    X[3 * (size_t)i] = 0; X[3 * (size_t)i + 1] = 0; X[3 * (size_t)i + 2] = 1;
+                }
+                kf_idx[2 * (size_t)i] = 0; kf_idx[2 * (size_t)i + 1] = 1;
+                pt_idx[2 * (size_t)i] = pt_idx[2 * (size_t)i + 1] = li;
+                obs[4 * (size_t)i] = px_ref[2 * (size_t)i]; obs[4 * (size_t)i + 1] = px_ref[2 * (size_t)i + 1];
+                obs[4 * (size_t)i + 2] = px_cur[2 * (size_t)i]; obs[4 * (size_t)i + 3] = px_cur[2 * (size_t)i + 1];
+                mask[2 * (size_t)i] = mask[2 * (size_t)i + 1] = inlier[i] ? 0 : 1;
+            }
+        }
+        kf_off[P] = (int32_t)(2 * P);
+        obs_off[P] = 2 * offsets[P];
+        ygzb_ba_params prm;
+        ygzb_default_ba_params(&prm);
+        prm.max_iters = 50;
+        prm.huber_delta = 0.1;
+        std::vector<double> hst;
+        TRY(run_local_ba(ctx, true, n_problems, kf_off.data(), pt_off.data(), obs_off.data(), poses.data(), fixed.data(), X.data(),
+                         kf_idx.data(), pt_idx.data(), obs.data(), &prm, nullptr, hst, mask.data()));
+        if (stats)
+            for (size_t p = 0; p < P; ++p) {
+                stats[p].iters = (int)hst[8 * p]; stats[p].successful_steps = (int)hst[8 * p + 1]; stats[p].cost_initial = hst[8 * p + 2];
+                stats[p].cost_final = hst[8 * p + 3]; stats[p].radius_final = hst[8 * p + 4]; stats[p].termination = (int)hst[8 * p + 5];
+            }
+        std::memcpy(pts, X.data(), 3 * N * sizeof(double));
+        // inlier classification + pose conversion on the device
+        Carver sz(nullptr);
+        sz.take<int32_t>(N); sz.take<double>(12 * P); sz.take<double>(12 * P); sz.take<double>(3 * N); sz.take<double>(2 * N); sz.take<double>(2 * N);
+        sz.take<uint8_t>(N); sz.take<double>(12 * P);
+        void* buf = dev_scratch(ctx, 6, sz.bytes());
+        if (!buf) return YGZB_ERR_CUDA;
+        Carver c(buf);
+        int32_t* d_prob = c.take<int32_t>(N);
+        double* d_Tref = c.take<double>(12 * P);
+        double* d_poses = c.take<double>(12 * P);
+        double* d_pts = c.take<double>(3 * N);
+        double* d_pr = c.take<double>(2 * N);
+        double* d_pc = c.take<double>(2 * N);
+        uint8_t* d_in = c.take<uint8_t>(N);
+        double* d_Tcur = c.take<double>(12 * P);
+        TRY(h2d(ctx, d_prob, prob_of.data(), N));
+        TRY(h2d(ctx, d_Tref, T_cw_ref, 12 * P));
+        TRY(h2d(ctx, d_poses, poses.data(), 12 * P));
+        TRY(h2d(ctx, d_pts, X.data(), 3 * N));
+        TRY(h2d(ctx, d_pr, px_ref, 2 * N));
+        TRY(h2d(ctx, d_pc, px_cur, 2 * N));
+        if (N) {
+            two_view_classify_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((int)N, d_prob, d_Tref, d_poses, d_pts, d_pr, d_pc, ctx->prm.fx,
+                                                                                       ctx->prm.fy, ctx->prm.cx, ctx->prm.cy, d_in, d_Tcur);
+            YGZB_LAUNCHED(ctx);
+            TRY(d2h(ctx, inlier, d_in, N));
+            TRY(d2h(ctx, T_cw_cur, d_Tcur, 12 * P));
+        }
+        YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } catch (const std::exception& e) {
+        return set_error(ctx, YGZB_ERR_INVALID, "ygzb_two_view_ba: %s", e.what());
+    }
     return YGZB_OK;
 }
 

@@ -580,6 +580,31 @@ class Tracker {  // include/ygz/Algorithm/Tracker.h:11-76
 };
 
 namespace ba {  // include/ygz/Algorithm/BA.h:23-66
+
+// BA.h:23-30 / BA.cpp:11-89: two-view bundle adjustment after the monocular initialisation (VisualOdometry.cpp:148)
+inline void TwoViewBACeres(const SE3& ref, SE3& curr, const std::vector<Vector2d> px_ref, const std::vector<Vector2d> px_curr,
+                           std::vector<bool>& inlier, std::vector<Vector3d>& pts_ref) {
+    auto& rt = b200::Runtime::Get();
+    const int n = (int)px_ref.size();
+    const int32_t off[2] = {0, n};
+    double Tr[12], Tc[12];
+    ref.matrix3x4(Tr);
+    curr.matrix3x4(Tc);
+    std::vector<double> pr(2 * (size_t)n), pc(2 * (size_t)n), X(3 * (size_t)n);
+    std::vector<uint8_t> in(n);
+    for (int i = 0; i < n; ++i) {
+        pr[2 * i] = px_ref[i][0]; pr[2 * i + 1] = px_ref[i][1];
+        pc[2 * i] = px_curr[i][0]; pc[2 * i + 1] = px_curr[i][1];
+        X[3 * i] = pts_ref[i][0]; X[3 * i + 1] = pts_ref[i][1]; X[3 * i + 2] = pts_ref[i][2];
+        in[i] = inlier[i] ? 1 : 0;
+    }
+    rt.Check(ygzb_two_view_ba(rt.ctx(), 1, off, Tr, Tc, pr.data(), pc.data(), in.data(), X.data(), nullptr), "ygzb_two_view_ba");
+    curr = SE3::from3x4(Tc);
+    for (int i = 0; i < n; ++i) {
+        pts_ref[i] = Vector3d(X[3 * i], X[3 * i + 1], X[3 * i + 2]);
+        inlier[i] = in[i] != 0;
+    }
+}
 // BA.cpp:188-264
 inline void OptimizeCurrentPoseOnly(Frame* current) {
     auto& rt = b200::Runtime::Get();
