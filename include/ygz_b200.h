@@ -149,6 +149,23 @@ int ygzb_match_frames(ygzb_frames* f, const int32_t* a_slots, const int32_t* b_s
 int ygzb_hamming_pairs(ygzb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B, int nB, const int32_t* ia,
                        const int32_t* ib, int n, int32_t* dist);
 
+/* replaces Matcher::SearchForTriangulation (src/Algorithm/Matcher.cpp:86-193; Matcher.h:61-67) with
+ * Matcher::CheckDistEpipolarLine (:338-354) for n_pairs key-frame pairs: pair p matches features [off1[p], off1[p+1]) of
+ * key-frame 1 against [off2[p], off2[p+1]) of key-frame 2.  node1 / node2 = the vocabulary node of every feature in the
+ * key-frame's DBoW3 feature vector (Frame::_feature_vec, levelsup = 4, Frame.cpp:199), -1 if the feature is in no node;
+ * only features of the same node are compared, candidates in ascending index like the vector's index lists.  E12 = 9
+ * doubles per pair (row major); th_low = matcher.th_low (65 in default.yaml, 50 in Matcher::Options), epipolar_dsqr =
+ * Options::_epipolar_dsqr (1e-4).  match12[i] = index of the match inside key-frame 2 of the pair, or -1.          */
+int ygzb_search_for_triangulation(ygzb_ctx* ctx, int n_pairs, const int32_t* off1, const int32_t* off2, const uint8_t* desc1,
+                                  const double* px1, const int32_t* node1, const uint8_t* desc2, const double* px2,
+                                  const int32_t* node2, const double* E12, int th_low, double epipolar_dsqr, int32_t* match12);
+/* replaces cvutils::DepthFromTriangulation (include/ygz/Algorithm/CVUtils.h:18-38) for n bearing pairs: T_search_ref =
+ * n_poses x 12 (3x4), pose_of[i] selects the pose of item i (NULL when n_poses == 1); f_ref / f_cur = unit-depth camera
+ * rays; ok[i] = the function's bool (determinant >= determinant_th, 1e-5 in the reference), depth1 / depth2 = |depth|.  */
+int ygzb_depth_from_triangulation(ygzb_ctx* ctx, int n, int n_poses, const double* T_search_ref, const int32_t* pose_of,
+                                  const double* f_ref, const double* f_cur, double determinant_th, double* depth1, double* depth2,
+                                  uint8_t* ok);
+
 /* ---- cvutils / Matcher: direct (photometric) alignment ---------------------------------------
  * replaces cvutils::Align2D (src/Algorithm/CVUtils.cpp:186-318; include/ygz/Algorithm/CVUtils.h:163-169):
  * inverse-compositional alignment of an 8x8 template.  Patch i is searched on pyramid level level[i] of

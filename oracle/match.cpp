@@ -8,6 +8,7 @@
 //                                    against cv2.BFMatcher in tests/test_oracle_cv2.py)
 #include "oracle.h"
 
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -105,4 +106,63 @@ extern "C" int ora_check_descriptors(const uint8_t* A, const uint8_t* B, const i
         good += keep[k];
     }
     return good;
+}
+
+// ---- matching for triangulation -------------------------------------------------------------
+//   Matcher::SearchForTriangulation   reference src/Algorithm/Matcher.cpp:86-193
+//   Matcher::CheckDistEpipolarLine    reference src/Algorithm/Matcher.cpp:338-354
+// The DBoW3 feature vectors arrive as one node id per feature (-1 = in no node); index lists of a node are ascending.
+namespace {
+inline bool check_dist_epipolar_line(double x1, double y1, double x2, double y2, const double* E, float dsqr_th) {
+    const float a = (float)(x1 * E[0] + y1 * E[3] + E[6]);
+    const float b = (float)(x1 * E[1] + y1 * E[4] + E[7]);
+    const float c = (float)(x1 * E[2] + y1 * E[5] + E[8]);
+    const float num = (float)(a * x2 + b * y2 + c);   // float * double -> double, one rounding on assignment
+    const float den = a * a + b * b;
+    if (den < 1e-6) return false;
+    const float dsqr = num * num / den;
+    return std::fabs(dsqr) < dsqr_th;
+}
+}  // namespace
+
+extern "C" void ora_search_for_triangulation(const ora_camera* cam, int n1, const uint8_t* desc1, const double* px1, const int32_t* node1,
+                                             int n2, const uint8_t* desc2, const double* px2, const int32_t* node2, const double* E12,
+                                             int th_low, double epipolar_dsqr, int32_t* match12) {
+    const float fx = cam->fx, fy = cam->fy, cx = cam->cx, cy = cam->cy;
+    for (int i = 0; i < n1; ++i) {
+        match12[i] = -1;
+        if (node1[i] < 0) continue;
+        const double x1 = (px1[2 * i] - cx) * 1.0 / fx, y1 = (px1[2 * i + 1] - cy) * 1.0 / fy;   // PinholeCamera::Pixel2Camera
+        int bestDist = 256, bestIdx2 = -1;
+        for (int j = 0; j < n2; ++j) {
+            if (node2[j] != node1[i]) continue;
+            const int dist = ora_descriptor_distance(desc1 + 32 * (size_t)i, desc2 + 32 * (size_t)j);
+            if (dist > th_low || dist > bestDist) continue;
+            const double x2 = (px2[2 * j] - cx) * 1.0 / fx, y2 = (px2[2 * j + 1] - cy) * 1.0 / fy;
+            if (check_dist_epipolar_line(x1, y1, x2, y2, E12, (float)epipolar_dsqr)) {
+                bestIdx2 = j;
+                bestDist = dist;
+            }
+        }
+        match12[i] = bestIdx2;
+    }
+}
+
+// cvutils::DepthFromTriangulation (include/ygz/Algorithm/CVUtils.h:18-38); T = 3x4 [R|t] of T_search_ref
+extern "C" int ora_depth_from_triangulation(const double* T, const double* f_ref, const double* f_cur, double determinant_th,
+                                            double* depth1, double* depth2) {
+    double a0[3], a1[3];
+    for (int r = 0; r < 3; ++r) {
+        a0[r] = T[4 * r] * f_ref[0] + T[4 * r + 1] * f_ref[1] + T[4 * r + 2] * f_ref[2];
+        a1[r] = -f_cur[r];
+    }
+    const double m00 = a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2], m01 = a0[0] * a1[0] + a0[1] * a1[1] + a0[2] * a1[2],
+                 m11 = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+    const double det = m00 * m11 - m01 * m01;
+    if (det < determinant_th) return 0;
+    const double b0 = a0[0] * T[3] + a0[1] * T[7] + a0[2] * T[11], b1 = a1[0] * T[3] + a1[1] * T[7] + a1[2] * T[11];
+    const double id = 1.0 / det;
+    *depth1 = std::fabs(-(m11 * id * b0 + -m01 * id * b1));
+    *depth2 = std::fabs(-(-m01 * id * b0 + m00 * id * b1));
+    return 1;
 }

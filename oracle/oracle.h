@@ -88,13 +88,23 @@ int ora_good_matches(const int32_t* train_idx, const int32_t* dist, int nA, uint
 int ora_check_descriptors(const uint8_t* A, const uint8_t* B, const int32_t* ia, const int32_t* ib, int n,
                           int init_low, int init_high, int32_t* dist, uint8_t* keep);
 
+typedef struct { float fx, fy, cx, cy; } ora_camera; /* Camera.h:14-22: stored as float */
+
+/* Matcher::SearchForTriangulation + CheckDistEpipolarLine (Matcher.cpp:86-193, 338-354): node1 / node2 = vocabulary node of
+ * every feature in the key-frame's DBoW3 feature vector (-1 = none); match12[i] = index in key-frame 2 or -1 */
+void ora_search_for_triangulation(const ora_camera* cam, int n1, const uint8_t* desc1, const double* px1, const int32_t* node1,
+                                  int n2, const uint8_t* desc2, const double* px2, const int32_t* node2, const double* E12,
+                                  int th_low, double epipolar_dsqr, int32_t* match12);
+/* cvutils::DepthFromTriangulation (CVUtils.h:18-38); returns the function's bool */
+int ora_depth_from_triangulation(const double* T_search_ref, const double* f_ref, const double* f_cur, double determinant_th,
+                                 double* depth1, double* depth2);
+
 /* ---- patch alignment (src/Algorithm/CVUtils.cpp:186-318; Matcher.cpp:356-466) ----------- */
 int ora_align2d(const uint8_t* img, int w, int h, const uint8_t* ref_with_border /*100*/,
                 const uint8_t* ref /*64*/, int n_iter, double* u, double* v);
 int ora_align1d(const uint8_t* img, int w, int h, float dirx, float diry, const uint8_t* ref_with_border,
                 const uint8_t* ref, int n_iter, double* u, double* v, double* h_inv);
 
-typedef struct { float fx, fy, cx, cy; } ora_camera; /* Camera.h:14-22: stored as float */
 
 /* pose = T_cw as 3x4 row-major [R|t] (12 doubles) at this boundary; quaternion inside like Sophus */
 /* Matcher::FindDirectProjection(ref,curr,Feature*,px,level) (Matcher.cpp:385-417) for a batch */

@@ -295,6 +295,30 @@ class Oracle:
                                     max_iters, C.c_double(huber), C.byref(st))
         return poses, pts, {k: getattr(st, k) for k, _ in CeresStats._fields_}
 
+    def search_for_triangulation(self, desc1, px1, node1, desc2, px2, node2, E12, th_low=65, epipolar_dsqr=1e-4, cam=None):
+        cam = cam or default_camera()
+        n1, n2 = len(node1), len(node2)
+        out = np.full(n1, -1, np.int32)
+        self.lib.ora_search_for_triangulation(C.byref(cam), n1, _p(np.ascontiguousarray(desc1, np.uint8)),
+                                              _p(np.ascontiguousarray(px1, np.float64)), _p(np.ascontiguousarray(node1, np.int32)), n2,
+                                              _p(np.ascontiguousarray(desc2, np.uint8)), _p(np.ascontiguousarray(px2, np.float64)),
+                                              _p(np.ascontiguousarray(node2, np.int32)), _p(np.ascontiguousarray(E12, np.float64)),
+                                              int(th_low), C.c_double(epipolar_dsqr), _p(out))
+        return out
+
+    def depth_from_triangulation(self, T, f_ref, f_cur, det_th=1e-5):
+        T = np.ascontiguousarray(T, np.float64).reshape(12)
+        f_ref = np.ascontiguousarray(f_ref, np.float64).reshape(-1, 3)
+        f_cur = np.ascontiguousarray(f_cur, np.float64).reshape(-1, 3)
+        n = len(f_ref)
+        d1, d2, ok = np.zeros(n), np.zeros(n), np.zeros(n, bool)
+        a, b = C.c_double(0), C.c_double(0)
+        for i in range(n):
+            ok[i] = bool(self.lib.ora_depth_from_triangulation(_p(T), _p(f_ref[i]), _p(f_cur[i]), C.c_double(det_th), C.byref(a), C.byref(b)))
+            if ok[i]:
+                d1[i], d2[i] = a.value, b.value
+        return d1, d2, ok
+
     def two_view_ba(self, T_ref, T_cur, px_ref, px_cur, inlier, pts, cam=None):
         """ba::TwoViewBACeres: returns (T_cur 3x4, inlier bool, pts, stats, inlier count)."""
         cam = cam or default_camera()

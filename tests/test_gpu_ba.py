@@ -156,8 +156,7 @@ def test_local_ba_ceres_huber_and_point_only(ctx3, oracle):
 def test_two_view_ba_matches_oracle(ctx3, oracle):
     """ba::TwoViewBACeres (BA.cpp:11-89) on the Ceres-flavoured kernel with a per-block loss mask: two problems in one call
     against the oracle -- pose < 1e-4, points < 1e-4 m (scene scale 2-5 m), identical inlier flags and termination."""
-    from tests.test_oracle_ba import two_view_scene
-    scs = [two_view_scene(21, 120, 12), two_view_scene(22, 75, 5)]
+    scs = [synth.two_view_scene(21, 120, 12), synth.two_view_scene(22, 75, 5)]
     offs = np.cumsum([0] + [len(s["X"]) for s in scs]).astype(np.int32)
     T, inl, X, st = ctx3.two_view_ba(offs, np.stack([s["T_ref"] for s in scs]), np.stack([s["T_cur0"] for s in scs]),
                                      np.concatenate([s["px_ref"] for s in scs]), np.concatenate([s["px_cur"] for s in scs]),

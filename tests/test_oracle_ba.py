@@ -107,31 +107,11 @@ def test_local_ba_ceres_twin_c4_scene(oracle):
     assert np.abs(P - est_g).max() < 2e-3
 
 
-def two_view_scene(seed=21, n=120, n_bad=12):
-    """Two views of points in front of both cameras (the situation after Initializer::TryInitialize): true relative pose,
-    noisy triangulated points, pixel noise, and a few points flagged as non-inliers (they restart from (0,0,1))."""
-    rng = np.random.default_rng(seed)
-    T_ref = np.eye(4)[:3]
-    T_cur = se3.se3_exp(np.array([-0.12, 0.03, 0.02, 0.01, -0.02, 0.015]))
-    X = np.stack([rng.uniform(-1.2, 1.2, n), rng.uniform(-0.9, 0.9, n), rng.uniform(2.0, 5.0, n)], 1)
-
-    def proj(T):
-        pc = (T[:, :3] @ X.T).T + T[:, 3]
-        return np.stack([520.9 * pc[:, 0] / pc[:, 2] + 325.1, 521.0 * pc[:, 1] / pc[:, 2] + 249.7], 1)
-
-    px_ref = proj(T_ref) + rng.normal(0, 0.5, (n, 2))
-    px_cur = proj(T_cur) + rng.normal(0, 0.5, (n, 2))
-    inlier = np.ones(n, np.uint8)
-    inlier[rng.choice(n, n_bad, replace=False)] = 0
-    T_cur0 = se3.se3_exp(se3.se3_log(T_cur) + rng.normal(0, 0.01, 6))
-    return dict(T_ref=T_ref, T_cur=T_cur, T_cur0=T_cur0, X=X, X0=X + rng.normal(0, 0.05, X.shape), px_ref=px_ref, px_cur=px_cur, inlier=inlier)
-
-
 def test_two_view_ba(oracle):
     """ba::TwoViewBACeres restatement (BA.cpp:11-89): the current pose comes back to the truth (up to the monocular scale,
     which the fixed reference frame does not pin: rotations are compared), the flagged points are re-triangulated from
     (0,0,1) and end up inliers, every point passes the reference's 5.991 px^2 test."""
-    sc = two_view_scene()
+    sc = synth.two_view_scene()
     T, inl, X, st, cnt = oracle.two_view_ba(sc["T_ref"], sc["T_cur0"], sc["px_ref"], sc["px_cur"], sc["inlier"], sc["X0"])
     assert st["cost_final"] < 0.05 * st["cost_initial"] and st["termination"] in (1, 2, 3)
     assert np.abs(T[:, :3] - sc["T_cur"][:, :3]).max() < 2e-3

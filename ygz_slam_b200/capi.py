@@ -37,7 +37,7 @@ EXPORTS = [
     "ygzb_profile_stage_name", "ygzb_host_alloc", "ygzb_host_free", "ygzb_frames_create", "ygzb_frames_destroy",
     "ygzb_frames_upload", "ygzb_frames_copy", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
-    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_align2d", "ygzb_align1d",
+    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_search_for_triangulation", "ygzb_depth_from_triangulation", "ygzb_align2d", "ygzb_align1d",
     "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_two_view_ba", "ygzb_pose_only",
     "ygzb_default_klt_params", "ygzb_klt",
     "ygzb_tracker_create", "ygzb_tracker_destroy", "ygzb_tracker_set_depth", "ygzb_tracker_track", "ygzb_tracker_make_keyframes",
@@ -514,6 +514,32 @@ def _two_view_ba(self, offsets, T_ref, T_cur, px_ref, px_cur, inlier, pts):
     return Tc.reshape(P, 3, 4), inl.astype(bool), X, [{k: getattr(s_, k) for k, _ in CeresStats._fields_} for s_ in st]
 
 
+def _search_for_triangulation(self, off1, off2, desc1, px1, node1, desc2, px2, node2, E12, th_low=65, epipolar_dsqr=1e-4):
+    """Batched Matcher::SearchForTriangulation: match12 per key-frame-1 feature (index local to key-frame 2 of its pair, or -1)."""
+    off1 = np.ascontiguousarray(off1, np.int32)
+    off2 = np.ascontiguousarray(off2, np.int32)
+    out = np.full(int(off1[-1]), -1, np.int32)
+    self.check(self.lib.ygzb_search_for_triangulation(self.h, len(off1) - 1, _p(off1), _p(off2), _p(np.ascontiguousarray(desc1, np.uint8)),
+                                                      _p(np.ascontiguousarray(px1, np.float64)), _p(np.ascontiguousarray(node1, np.int32)),
+                                                      _p(np.ascontiguousarray(desc2, np.uint8)), _p(np.ascontiguousarray(px2, np.float64)),
+                                                      _p(np.ascontiguousarray(node2, np.int32)), _p(np.ascontiguousarray(E12, np.float64)),
+                                                      int(th_low), C.c_double(epipolar_dsqr), _p(out)), "ygzb_search_for_triangulation")
+    return out
+
+
+def _depth_from_triangulation(self, T, pose_of, f_ref, f_cur, det_th=1e-5):
+    T = np.ascontiguousarray(T, np.float64).reshape(-1, 12)
+    f_ref = np.ascontiguousarray(f_ref, np.float64).reshape(-1, 3)
+    n = len(f_ref)
+    d1, d2, ok = np.zeros(n), np.zeros(n), np.zeros(n, np.uint8)
+    po = None if pose_of is None else np.ascontiguousarray(pose_of, np.int32)
+    self.check(self.lib.ygzb_depth_from_triangulation(self.h, n, len(T), _p(T), _p(po), _p(f_ref), _p(np.ascontiguousarray(f_cur, np.float64)),
+                                                      C.c_double(det_th), _p(d1), _p(d2), _p(ok)), "ygzb_depth_from_triangulation")
+    return d1, d2, ok.astype(bool)
+
+
+Context.search_for_triangulation = _search_for_triangulation
+Context.depth_from_triangulation = _depth_from_triangulation
 Context.local_ba = _local_ba
 Context.local_ba_ceres = _local_ba_ceres
 Context.pose_only = _pose_only

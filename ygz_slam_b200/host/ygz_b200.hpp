@@ -134,6 +134,7 @@ struct Frame {  // include/ygz/Basic/Frame.h:20-166 (fields used on the hot path
     bool _is_keyframe = false;
     std::vector<Feature*> _features;
     Mat _color;                 // BGR (3 channels) or grey (1 channel) input image
+    std::map<unsigned, std::vector<unsigned>> _feature_vec;   // DBoW3::FeatureVector of Frame::ComputeBoW (Frame.cpp:190-201): node -> feature indices
     int _slot = -1;             // device pyramid slot (set by InitFrame)
     static inline PinholeCamera* _camera = nullptr;
 };
@@ -349,6 +350,17 @@ inline float GetBilateralInterp(const double& x, const double& y, const Mat& gra
     const uint8_t* d = &gray.data[(size_t)int(y) * gray.cols + int(x)];
     return float((1 - xx) * (1 - yy) * d[0] + xx * (1 - yy) * d[1] + (1 - xx) * yy * d[gray.cols] + xx * yy * d[gray.cols + 1]);
 }
+// CVUtils.h:18-38
+inline bool DepthFromTriangulation(const SE3& T_search_ref, const Vector3d& f_ref, const Vector3d& f_cur, double& depth1, double& depth2,
+                                   const double& determinant_th = 1e-5) {
+    auto& rt = b200::Runtime::Get();
+    double T[12];
+    T_search_ref.matrix3x4(T);
+    const double fr[3] = {f_ref[0], f_ref[1], f_ref[2]}, fc[3] = {f_cur[0], f_cur[1], f_cur[2]};
+    uint8_t ok = 0;
+    rt.Check(ygzb_depth_from_triangulation(rt.ctx(), 1, 1, T, nullptr, fr, fc, determinant_th, &depth1, &depth2, &ok), "ygzb_depth_from_triangulation");
+    return ok != 0;
+}
 // include/ygz/Algorithm/CVUtils.h:163-169 -- cur_img is identified by (frame, level) instead of a cv::Mat
 inline bool Align2D(Frame* cur, int level, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter, Vector2d& cur_px_estimate) {
     auto& rt = b200::Runtime::Get();
@@ -400,6 +412,8 @@ class Matcher {  // include/ygz/Algorithm/Matcher.h
         float initMatchRatio = 3.0;
         int init_low = 30, init_high = 100;  // matcher.init_low / init_high (config/default.yaml:59-60)
         double _max_alignment_motion = 0.2;
+        int th_low = 65;                      // matcher.th_low (config/default.yaml:54)
+        double _epipolar_dsqr = 1e-4;         // Matcher.h:31
     } _options;
     Matcher() : _align(new SparseImgAlign(2, 0, 30, SparseImgAlign::GaussNewton, false, false)) {}
     // Matcher.cpp:30-43
@@ -433,6 +447,37 @@ class Matcher {  // include/ygz/Algorithm/Matcher.h
         return cnt_good;
     }
     // brute-force cross-checked matching of two frames (cv::BFMatcher in test/test_orb_match.cpp:87-92)
+    // Matcher.cpp:86-193 (+ CheckDistEpipolarLine :338-354): matches inside the common nodes of the two feature vectors
+    int SearchForTriangulation(Frame* kf1, Frame* kf2, const double E12[9] /* row major */, std::vector<std::pair<int, int>>& matched_points,
+                               const bool& onlyStereo = false) {
+        (void)onlyStereo;
+        auto& rt = b200::Runtime::Get();
+        auto flatten = [](Frame* f, std::vector<uint8_t>& desc, std::vector<double>& px, std::vector<int32_t>& node) {
+            const size_t n = f->_features.size();
+            desc.resize(32 * n); px.resize(2 * n); node.assign(n, -1);
+            for (size_t i = 0; i < n; ++i) {
+                std::memcpy(&desc[32 * i], f->_features[i]->_desc, 32);
+                px[2 * i] = f->_features[i]->_pixel[0];
+                px[2 * i + 1] = f->_features[i]->_pixel[1];
+            }
+            for (const auto& kv : f->_feature_vec)
+                for (unsigned idx : kv.second)
+                    if (idx < n) node[idx] = (int32_t)kv.first;
+        };
+        std::vector<uint8_t> d1, d2;
+        std::vector<double> p1, p2;
+        std::vector<int32_t> n1, n2;
+        flatten(kf1, d1, p1, n1);
+        flatten(kf2, d2, p2, n2);
+        const int32_t off1[2] = {0, (int32_t)n1.size()}, off2[2] = {0, (int32_t)n2.size()};
+        std::vector<int32_t> m12(n1.size(), -1);
+        rt.Check(ygzb_search_for_triangulation(rt.ctx(), 1, off1, off2, d1.data(), p1.data(), n1.data(), d2.data(), p2.data(), n2.data(), E12,
+                                               _options.th_low, _options._epipolar_dsqr, m12.data()), "ygzb_search_for_triangulation");
+        matched_points.clear();
+        for (size_t i = 0; i < m12.size(); ++i)
+            if (m12[i] >= 0) matched_points.push_back(std::make_pair((int)i, (int)m12[i]));
+        return (int)matched_points.size();
+    }
     static void BruteForceMatch(Frame* f1, Frame* f2, std::vector<int>& train_idx, std::vector<int>& dist, bool cross_check = true) {
         auto& rt = b200::Runtime::Get();
         const int n1 = (int)f1->_features.size(), n2 = (int)f2->_features.size();

@@ -164,6 +164,27 @@ def ba_scene(n_kf: int = 10, n_pt: int = 2000, target_obs: int = 8000, seed: int
                 px=np.array(px, np.float64))
 
 
+def two_view_scene(seed=21, n=120, n_bad=12):
+    """Two views of points in front of both cameras (the situation after Initializer::TryInitialize): true relative pose,
+    noisy triangulated points, pixel noise, and a few points flagged as non-inliers (they restart from (0,0,1))."""
+    from .se3 import se3_exp, se3_log
+    rng = np.random.default_rng(seed)
+    T_ref = np.eye(4)[:3]
+    T_cur = se3_exp(np.array([-0.12, 0.03, 0.02, 0.01, -0.02, 0.015]))
+    X = np.stack([rng.uniform(-1.2, 1.2, n), rng.uniform(-0.9, 0.9, n), rng.uniform(2.0, 5.0, n)], 1)
+
+    def proj(T):
+        pc = (T[:, :3] @ X.T).T + T[:, 3]
+        return np.stack([FX * pc[:, 0] / pc[:, 2] + CX, FY * pc[:, 1] / pc[:, 2] + CY], 1)
+
+    px_ref = proj(T_ref) + rng.normal(0, 0.5, (n, 2))
+    px_cur = proj(T_cur) + rng.normal(0, 0.5, (n, 2))
+    inlier = np.ones(n, np.uint8)
+    inlier[rng.choice(n, n_bad, replace=False)] = 0
+    T_cur0 = se3_exp(se3_log(T_cur) + rng.normal(0, 0.01, 6))
+    return dict(T_ref=T_ref, T_cur=T_cur, T_cur0=T_cur0, X=X, X0=X + rng.normal(0, 0.05, X.shape), px_ref=px_ref, px_cur=px_cur, inlier=inlier)
+
+
 def shift_stream(stream: int, n_frames: int, noise_sigma: float = 2.0, plane_z: float = 2.0):
     """Cheap exact-ground-truth VO stream: a fronto-parallel textured plane seen by a camera that only translates
     parallel to it, i.e. integer-pixel sliding crops of one render.  Returns (frames u8 (n,H,W), depth (H,W) constant,
