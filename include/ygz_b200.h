@@ -343,6 +343,10 @@ void ygzb_tracker_destroy(ygzb_tracker* t);
 /* depth image (image_width * image_height doubles, host or device) that initialises the map points of the next key-frame
  * of `stream` (the reference's drivers read it from the TUM depth frame, test/test_feature_alignment.cpp:72-85)   */
 int ygzb_tracker_set_depth(ygzb_tracker* t, int stream, const double* depth);
+/* host -> device copy of `count` grey frames into slots [first, first+count) and their pyramids, like ygzb_frames_upload,
+ * but on the tracker's second CUDA stream: behind the last key-frame insertion and tracking chain (which still read the
+ * slots), concurrent with a local BA in flight.  ygzb_tracker_track orders itself behind these uploads.              */
+int ygzb_tracker_upload(ygzb_tracker* t, int first, int count, const uint8_t* host, size_t frame_stride);
 /* asynchronous: enqueues the chain on the context's stream and a copy of the n_jobs result records into `results`
  * (host memory, page-locked for a truly asynchronous copy); valid after ygzb_synchronize(ctx).                    */
 int ygzb_tracker_track(ygzb_tracker* t, int n_jobs, const ygzb_track_job* jobs, ygzb_track_result* results);

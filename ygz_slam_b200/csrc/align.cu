@@ -912,10 +912,24 @@ __global__ void track_prep_kernel(TrackStore st, TrackBatch b) {
     if (j == 0) b.offsets[b.J] = b.J * st.cells;
     b.in_off[j] = e * st.cells;
     b.n_feat[j] = st.kf_n[e];
-    for (int c = 0; c < 12; ++c) b.T_ref[12 * (size_t)j + c] = b.T_cur[12 * (size_t)j + c] = st.kf_T[12 * (size_t)e + c];   // VisualOdometry.cpp:66
+    // the alignment runs RELATIVE to the reference key-frame (cur._TCW = ref._TCW, VisualOdometry.cpp:66: the start is the
+    // identity in the key-frame's frame); track_compose_kernel applies the key-frame's pose afterwards, so this part of the
+    // chain does not depend on a local BA that may still be refining that pose
+    for (int c = 0; c < 12; ++c) b.T_ref[12 * (size_t)j + c] = b.T_cur[12 * (size_t)j + c] = (c == 0 || c == 5 || c == 10) ? 1.0 : 0.0;
     b.n_cand[j] = 0;
     b.c_off[j] = j * b.cap;
     if (j == 0) b.c_off[b.J] = b.J * b.cap;
+}
+
+// per job: T_cw of the aligned frame = (pose relative to the reference key-frame) * (pose of the key-frame, after its BA)
+__global__ void track_compose_kernel(TrackStore st, TrackBatch b) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b.J) return;
+    const ygzb_track_job job = b.jobs[j];
+    const double* Tk = st.kf_T + 12 * (size_t)(job.stream * st.R + job.entry[job.n_local - 1]);
+    const SE3d Trel = se3_from_mat(b.T_cur + 12 * (size_t)j), Tref = se3_from_mat(Tk);
+    se3_to_mat(se3_mul(Trel, Tref), b.T_cur + 12 * (size_t)j);
+    for (int c = 0; c < 12; ++c) b.T_ref[12 * (size_t)j + c] = Tk[c];
 }
 
 // per job: Matcher::SparseImageAlignment's motion check (Matcher.cpp:482-488) and the current pose relative to every
@@ -1107,8 +1121,8 @@ int launch_sparse_align(ygzb_frames* f, int n_problems, const int32_t* d_ref_slo
 }
 
 
-// front half of the tracking chain of a batch: prep -> sparse alignment -> motion check / relative poses -> candidate
-// projection + direct projection -> ordered compaction.  The pose-only refinement (ba.cu) follows on the same stream.
+// Tracking chain of a batch, part 1 (on whatever stream ctx->stream currently is: the tracker points it at its second
+// stream): prep -> sparse alignment relative to the reference key-frame.  Needs the key-frame's features, not its pose.
 int launch_track_chain_front(ygzb_frames* f, const TrackStore& st, const TrackBatch& b, int sparse_cluster) {
     ygzb_ctx* ctx = f->ctx;
     if (b.J <= 0) return YGZB_OK;
@@ -1184,6 +1198,19 @@ int launch_track_chain_front(ygzb_frames* f, const TrackStore& st, const TrackBa
         } else {
             YGZB_CUDA(ctx, cudaLaunchKernelEx(&cfg, sparse_align2_kernel, a, feat_cap));
         }
+        YGZB_LAUNCHED(ctx);
+    }
+    return YGZB_OK;
+}
+
+// part 2 (main stream, behind a local BA in flight): key-frame pose applied -> motion check / relative poses -> candidate
+// projection + direct projection -> ordered compaction.  The pose-only refinement (ba.cu) follows on the same stream.
+int launch_track_chain_mid(ygzb_frames* f, const TrackStore& st, const TrackBatch& b) {
+    ygzb_ctx* ctx = f->ctx;
+    if (b.J <= 0) return YGZB_OK;
+    {
+        ProfScope ps(ctx, kStageOther);
+        track_compose_kernel<<<(b.J + 63) / 64, 64, 0, ctx->stream>>>(st, b);
         YGZB_LAUNCHED(ctx);
     }
     {

@@ -43,6 +43,12 @@ struct ygzb_tracker {
     void* d_ba;            // problem arrays + scratch of ba2
     size_t ba_bytes;
     int pcap, ocap;        // points / observations capacity per problem
+    cudaStream_t front;    // second stream: uploads + pyramid + sparse alignment of the next batch run here, concurrently with a
+                           // local BA on the context's stream (they need the new key-frame's features, not its refined pose)
+    cudaEvent_t e_fill;    // recorded on the main stream after the key-frame insertion kernel (features + ring entry written)
+    cudaEvent_t e_front;   // recorded on the front stream after the sparse alignment
+    cudaEvent_t e_up;      // recorded on the front stream after every upload: a key-frame insertion (Detect) waits for it
+    cudaEvent_t e_main;    // recorded on the main stream after a tracking chain: the front stream must not overwrite its arrays earlier
     int cluster;           // CTAs per tracking problem (sparse alignment, pose-only): fixed, so that a frame's result does not
                            // depend on how many other frames share its batch (the summation order follows the cluster size)
 };
@@ -390,6 +396,14 @@ int ygzb_tracker_create(ygzb_frames* f, int n_streams, int max_jobs, const doubl
     if (rc == YGZB_OK) rc = dalloc(ctx, &t->d_kfjobs, S);
     if (rc == YGZB_OK) rc = dalloc(ctx, &t->d_kfres, S);
     if (rc == YGZB_OK) rc = check_cuda(ctx, cudaEventCreateWithFlags(&t->staged, cudaEventDisableTiming), "cudaEventCreate");
+    if (rc == YGZB_OK) rc = check_cuda(ctx, cudaStreamCreateWithFlags(&t->front, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (cudaEvent_t* e : {&t->e_fill, &t->e_front, &t->e_main, &t->e_up})
+        if (rc == YGZB_OK) rc = check_cuda(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+    if (rc == YGZB_OK) {   // (events start out "completed": recorded once on an idle stream)
+        rc = check_cuda(ctx, cudaEventRecord(t->e_fill, ctx->stream), "cudaEventRecord");
+        if (rc == YGZB_OK) rc = check_cuda(ctx, cudaEventRecord(t->e_main, ctx->stream), "cudaEventRecord");
+        if (rc == YGZB_OK) rc = check_cuda(ctx, cudaEventRecord(t->e_up, ctx->stream), "cudaEventRecord");
+    }
     if (rc == YGZB_OK) {
         t->pcap = (int)(kTrackMaxLocal * cells + 1);
         t->ocap = (int)(kTrackMaxLocal * kTrackMaxLocal * cells);
@@ -422,6 +436,12 @@ void ygzb_tracker_destroy(ygzb_tracker* t) {
     if (t->d_kfres) cudaFree(t->d_kfres);
     if (t->d_ba) cudaFree(t->d_ba);
     if (t->staged) cudaEventDestroy(t->staged);
+    if (t->front) {
+        cudaStreamSynchronize(t->front);
+        cudaStreamDestroy(t->front);
+    }
+    for (cudaEvent_t e : {t->e_fill, t->e_front, t->e_main, t->e_up})
+        if (e) cudaEventDestroy(e);
     delete t;
 }
 
@@ -432,6 +452,22 @@ int ygzb_tracker_set_depth(ygzb_tracker* t, int stream, const double* depth) {
     const size_t n = (size_t)t->st.W * t->st.H;
     YGZB_CUDA(ctx, cudaMemcpyAsync(t->d_depth + (size_t)stream * n, depth, n * sizeof(double), cudaMemcpyDefault, ctx->stream));
     return YGZB_OK;
+}
+
+int ygzb_tracker_upload(ygzb_tracker* t, int first, int count, const uint8_t* host, size_t frame_stride) {
+    if (!t) return YGZB_ERR_INVALID;
+    ygzb_ctx* ctx = t->ctx;
+    cudaSetDevice(ctx->device);
+    // on the front stream, behind the last key-frame insertion (which still reads the frame slots of the previous window) and
+    // behind the last tracking chain (ditto); NOT behind a local BA in flight
+    YGZB_CUDA(ctx, cudaStreamWaitEvent(t->front, t->e_fill, 0));
+    YGZB_CUDA(ctx, cudaStreamWaitEvent(t->front, t->e_main, 0));
+    cudaStream_t main = ctx->stream;
+    ctx->stream = t->front;
+    int rc = ygzb_frames_upload(t->f, first, count, host, 1, frame_stride);
+    if (rc == YGZB_OK) rc = check_cuda(ctx, cudaEventRecord(t->e_up, ctx->stream), "cudaEventRecord");
+    ctx->stream = main;
+    return rc;
 }
 
 int ygzb_tracker_track(ygzb_tracker* t, int n_jobs, const ygzb_track_job* jobs, ygzb_track_result* results) {
@@ -449,14 +485,27 @@ int ygzb_tracker_track(ygzb_tracker* t, int n_jobs, const ygzb_track_job* jobs, 
     }
     YGZB_CUDA(ctx, cudaEventSynchronize(t->staged));   // the previous copy out of the staging buffer has finished
     memcpy(t->h_jobs, jobs, sizeof(ygzb_track_job) * (size_t)n_jobs);
-    YGZB_CUDA(ctx, cudaMemcpyAsync(const_cast<ygzb_track_job*>(t->b.jobs), t->h_jobs, sizeof(ygzb_track_job) * (size_t)n_jobs,
-                                   cudaMemcpyHostToDevice, ctx->stream));
-    YGZB_CUDA(ctx, cudaEventRecord(t->staged, ctx->stream));
     TrackBatch b = t->b;
     b.J = n_jobs;
     t->last_J = n_jobs;
     const int cl = t->cluster;
-    int rc = launch_track_chain_front(t->f, t->st, b, cl);
+    int rc;
+    {   // part 1 on the front stream: behind the key-frame insertion (new reference features, and the batch arrays it still
+        // reads) and the previous chain, concurrent with a local BA on the main stream
+        cudaStream_t main = ctx->stream;
+        YGZB_CUDA(ctx, cudaStreamWaitEvent(t->front, t->e_fill, 0));
+        YGZB_CUDA(ctx, cudaStreamWaitEvent(t->front, t->e_main, 0));
+        ctx->stream = t->front;
+        cudaError_t ce = cudaMemcpyAsync(const_cast<ygzb_track_job*>(t->b.jobs), t->h_jobs, sizeof(ygzb_track_job) * (size_t)n_jobs,
+                                         cudaMemcpyHostToDevice, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(t->staged, ctx->stream);
+        rc = ce == cudaSuccess ? launch_track_chain_front(t->f, t->st, b, cl) : check_cuda(ctx, ce, "H2D(track jobs)");
+        if (rc == YGZB_OK) rc = check_cuda(ctx, cudaEventRecord(t->e_front, ctx->stream), "cudaEventRecord");
+        ctx->stream = main;
+        if (rc != YGZB_OK) return rc;
+        YGZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, t->e_front, 0));
+    }
+    rc = launch_track_chain_mid(t->f, t->st, b);
     if (rc != YGZB_OK) return rc;
     rc = launch_pose_only_dev(ctx, n_jobs, b.c_off, b.c_cnt, b.c_pw, b.c_px, b.T_cur, b.inlier, b.c_depth, b.n_inl, b.enable, b.pose_ws, cl);
     if (rc != YGZB_OK) return rc;
@@ -466,6 +515,7 @@ int ygzb_tracker_track(ygzb_tracker* t, int n_jobs, const ygzb_track_job* jobs, 
         YGZB_LAUNCHED(ctx);
     }
     YGZB_CUDA(ctx, cudaMemcpyAsync(results, b.results, sizeof(ygzb_track_result) * (size_t)n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+    YGZB_CUDA(ctx, cudaEventRecord(t->e_main, ctx->stream));
     return YGZB_OK;
 }
 
@@ -492,7 +542,9 @@ int ygzb_tracker_make_keyframes(ygzb_tracker* t, int n, const ygzb_keyframe_job*
         slots[i] = q.frame_slot;
         prob_of[i] = (q.run_ba && q.n_local >= 2) ? P++ : -1;
     }
-    // FeatureDetector::Detect on the frames (results stay in the slots' feature store)
+    // FeatureDetector::Detect on the frames (results stay in the slots' feature store); the frames may have been uploaded on
+    // the front stream without a tracking chain behind them (first frame of a stream)
+    YGZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, t->e_up, 0));
     int rc = ygzb_detect(f, slots.data(), n, nullptr, nullptr);
     if (rc != YGZB_OK) return rc;
     for (int i = 0; i < n; ++i)
@@ -521,6 +573,7 @@ int ygzb_tracker_make_keyframes(ygzb_tracker* t, int n, const ygzb_keyframe_job*
                                                              t->d_kfres);
         YGZB_LAUNCHED(ctx);
     }
+    YGZB_CUDA(ctx, cudaEventRecord(t->e_fill, ctx->stream));   // from here on only the BA runs: the next batch's front part may start
     double* d_ba_stats = nullptr;
     if (P > 0) {
         {

@@ -62,6 +62,7 @@ struct TrackBatch {
 
 // align.cu
 int launch_track_chain_front(ygzb_frames* f, const TrackStore& st, const TrackBatch& b, int sparse_cluster);
+int launch_track_chain_mid(ygzb_frames* f, const TrackStore& st, const TrackBatch& b);
 // ba.cu
 int launch_pose_only_dev(ygzb_ctx* ctx, int n_problems, const int32_t* d_offsets, const int32_t* d_counts, const double* d_pw,
                          const double* d_px, double* d_T_cw, uint8_t* d_inlier, double* d_depth, int32_t* d_n_inlier, uint8_t* d_enable,

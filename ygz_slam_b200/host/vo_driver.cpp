@@ -539,6 +539,7 @@ struct EStream {
 };
 
 class Engine {
+    struct Win { int stream, first, count, job0; };   // a window in flight: frames [first, first + count) of a stream (job0 < 0: first frame)
   public:
     Engine(ygzb_ctx* ctx, int n_streams, int window, const Params& p) : ctx_(ctx), S_(n_streams), F_(std::max(1, window)), prm_(p), st_(n_streams) {}
     ~Engine() {
@@ -568,123 +569,141 @@ class Engine {
     }
     long long h2d_image_bytes = 0, h2d_other_bytes = 0, d2h_bytes = 0;
 
-    // one round; frames are taken from images[i] + frame * W * H; `limit` = no window crosses this frame index
-    int round(const uint8_t* const* images, int n_frames, int limit, double* traj /* this group's [S][n_frames][12] */) {
-        struct Win { int stream, first, count, job0; };
-        std::vector<Win> boot, track;
-        std::vector<ygzb_track_job> jobs;
-        for (int i = 0; i < S_; ++i) {
-            EStream& s = st_[i];
-            if (s.next_frame >= n_frames) continue;
-            const int stop = s.next_frame < limit ? limit : n_frames;
-            if (s.lost) {   // the reference keeps the last pose and reports VO_LOST
-                for (int k = s.next_frame; k < stop; ++k) put_pose(traj, i, n_frames, k, s);
-                s.next_frame = stop;
-                continue;
-            }
-            // window: up to and including the first frame that may become a key-frame; past that point every frame may, and a
-            // few frames are tracked speculatively -- the ones behind a key-frame trigger are dropped and tracked again against
-            // the new key-frame next round (results stay those of frame-by-frame processing)
-            int w = 1;
-            if (!s.kfs.empty()) {
-                const int sure = prm_.kf_min_frames - s.frames_since_kf;
-                w = sure >= 1 ? std::min(F_, sure) : std::min(F_, kSpeculativeFrames);
-            }
-            w = std::min(w, stop - s.next_frame);
-            CHK(ygzb_frames_upload(fr_, i * F_, w, images[i] + (size_t)s.next_frame * W * H, 1, (size_t)W * H));
-            h2d_image_bytes += (long long)w * W * H;
-            if (s.kfs.empty()) {
-                boot.push_back({i, s.next_frame, 1, -1});
-                continue;
-            }
-            track.push_back({i, s.next_frame, w, (int)jobs.size()});
-            const int nl = std::min(kLocalKeyframes, (int)s.kfs.size());
-            for (int t = 0; t < w; ++t) {
-                ygzb_track_job j{};
-                j.stream = i;
-                j.cur_slot = i * F_ + t;
-                j.n_local = nl;
-                for (int k = 0; k < nl; ++k) j.entry[k] = s.kfs[s.kfs.size() - nl + k].entry;
-                jobs.push_back(j);
-            }
-        }
-        std::vector<ygzb_keyframe_job> kjobs;
-        std::vector<int> kframe;   // frame index of every key-frame job
-        for (const Win& b : boot) {
-            EStream& s = st_[b.stream];
-            s.T = identity();
-            s.has_pose = true;
-            kjobs.push_back(make_kf_job(b.stream, b.stream * F_, -1));
-            kframe.push_back(b.first);
-        }
-        if (!jobs.empty()) {
-            StageTimer tm(kTSparse);
-            CHK(ygzb_tracker_track(tr_, (int)jobs.size(), jobs.data(), h_res_));
-            CHK(ygzb_synchronize(ctx_));
-            h2d_other_bytes += (long long)(jobs.size() * sizeof(ygzb_track_job));
-            d2h_bytes += (long long)(jobs.size() * sizeof(ygzb_track_result));
-        }
-        for (const Win& b : track) {
-            EStream& s = st_[b.stream];
-            int t = 0;
-            for (; t < b.count; ++t) {
-                const ygzb_track_result& r = h_res_[b.job0 + t];
-                if (!r.aligned) {   // Matcher::SparseImageAlignment returned false (Matcher.cpp:482-488)
-                    s.lost = true;
-                    break;
+    // Runs until every stream has reached frame `limit` (no window crosses it) and nothing is in flight.  The loop is
+    // software-pipelined around ONE host synchronisation per round:
+    //   1. take the decisions of the tracking batch that has just come back (lost streams, key-frame triggers),
+    //   2. enqueue the key-frame insertions of this round (Detect, map points, local BA) -- asynchronous,
+    //   3. plan the next window of every stream, upload its frames and enqueue its tracking chain right behind; the tracker
+    //      runs the uploads and the sparse alignment of that batch on a second CUDA stream, concurrently with the local BA
+    //      of step 2 (the alignment works relative to the reference key-frame and needs its features, not its refined pose),
+    //   4. synchronise, apply the key-frame results (poses after the BA, feature counts).
+    int run_until(const uint8_t* const* images, int n_frames, int limit, double* traj /* this group's [S][n_frames][12] */) {
+        for (;;) {
+            std::vector<ygzb_keyframe_job> kjobs;
+            std::vector<int> kframe;
+            // ---- 1. results of the batch in flight
+            for (const Win& b : wins_) {
+                EStream& s = st_[b.stream];
+                if (b.job0 < 0) {   // first frame of the stream: becomes the first key-frame (depth-initialised map)
+                    s.T = identity();
+                    s.has_pose = true;
+                    kjobs.push_back(make_kf_job(b.stream, b.stream * F_, -1));
+                    kframe.push_back(b.first);
+                    s.next_frame = b.first + 1;
+                    continue;
                 }
-                s.n_candidates += r.n_candidates;
-                s.n_projected += r.n_projected;
-                if (r.n_inliers < kMinInliers) {
-                    s.lost = true;
-                    break;
+                int t = 0;
+                for (; t < b.count; ++t) {
+                    const ygzb_track_result& r = h_res_[b.job0 + t];
+                    if (!r.aligned) {   // Matcher::SparseImageAlignment returned false (Matcher.cpp:482-488)
+                        s.lost = true;
+                        break;
+                    }
+                    s.n_candidates += r.n_candidates;
+                    s.n_projected += r.n_projected;
+                    if (r.n_inliers < kMinInliers) {
+                        s.lost = true;
+                        break;
+                    }
+                    std::memcpy(s.T.m, r.T_cw, sizeof(s.T.m));
+                    s.frames_since_kf += 1;
+                    s.n_inliers += r.n_inliers;
+                    put_pose(traj, b.stream, n_frames, b.first + t, s);
+                    // NeedNewKeyFrame (VisualOdometry.cpp:304-321)
+                    if (s.frames_since_kf < prm_.kf_min_frames) continue;
+                    double d[6];
+                    se3_log(mul(s.T, inv(s.kfs.back().T)), d);
+                    const double rot = std::sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]), tr = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                    if (rot > prm_.kf_min_rot || tr > prm_.kf_min_trans) {
+                        kjobs.push_back(make_kf_job(b.stream, b.stream * F_ + t, b.job0 + t));
+                        kframe.push_back(b.first + t);
+                        ++t;
+                        break;   // frames of the window behind the key-frame (speculative ones) are dropped: tracked again next round
+                    }
                 }
-                std::memcpy(s.T.m, r.T_cw, sizeof(s.T.m));
-                s.frames_since_kf += 1;
-                s.n_inliers += r.n_inliers;
-                put_pose(traj, b.stream, n_frames, b.first + t, s);
-                // NeedNewKeyFrame (VisualOdometry.cpp:304-321)
-                if (s.frames_since_kf < prm_.kf_min_frames) continue;
-                double d[6];
-                se3_log(mul(s.T, inv(s.kfs.back().T)), d);
-                const double rot = std::sqrt(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]), tr = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-                if (rot > prm_.kf_min_rot || tr > prm_.kf_min_trans) {
-                    kjobs.push_back(make_kf_job(b.stream, b.stream * F_ + t, b.job0 + t));
-                    kframe.push_back(b.first + t);
-                    ++t;
-                    break;   // frames of the window behind the key-frame (speculative ones) are dropped: tracked again next round
+                if (s.lost) {   // the reference keeps the last pose and reports VO_LOST
+                    put_pose(traj, b.stream, n_frames, b.first + t, s);
+                    s.next_frame = b.first + t + 1;
+                } else {
+                    s.next_frame = b.first + t;
                 }
             }
-            if (s.lost) {
-                put_pose(traj, b.stream, n_frames, b.first + t, s);
-                s.next_frame = b.first + t + 1;
-            } else {
-                s.next_frame = b.first + t;
+            wins_.clear();
+            // ---- 2. key-frame insertions of this round (asynchronous)
+            if (!kjobs.empty()) {
+                StageTimer tm(kTLocalBA);
+                for (size_t q = 0; q < kjobs.size(); ++q) {   // bookkeeping that does not need the device's answer
+                    EStream& s = st_[kjobs[q].stream];
+                    KfInfo kf;
+                    kf.entry = kjobs[q].entry;
+                    kf.frame_id = kframe[q];
+                    kf.mp0 = kjobs[q].mp0;
+                    kf.T = s.T;
+                    s.kfs.push_back(kf);
+                    while ((int)s.kfs.size() > YGZB_TRACK_RING) s.kfs.pop_front();
+                    s.frames_since_kf = 0;
+                    s.n_keyframes += 1;
+                }
+                CHK(ygzb_tracker_make_keyframes(tr_, (int)kjobs.size(), kjobs.data(), &ba_, h_kres_));
+                h2d_other_bytes += (long long)(kjobs.size() * (sizeof(ygzb_keyframe_job) + 4));
+                d2h_bytes += (long long)(kjobs.size() * sizeof(ygzb_keyframe_result));
             }
-        }
-        for (const Win& b : boot) st_[b.stream].next_frame = b.first + 1;
-        if (!kjobs.empty()) {
-            StageTimer tm(kTLocalBA);
-            CHK(ygzb_tracker_make_keyframes(tr_, (int)kjobs.size(), kjobs.data(), &ba_, h_kres_));
-            CHK(ygzb_synchronize(ctx_));
-            h2d_other_bytes += (long long)(kjobs.size() * (sizeof(ygzb_keyframe_job) + 4));
-            d2h_bytes += (long long)(kjobs.size() * sizeof(ygzb_keyframe_result));
+            // ---- 3. next window of every stream: uploads + tracking chain (asynchronous, right behind the key-frames)
+            std::vector<ygzb_track_job> jobs;
+            for (int i = 0; i < S_; ++i) {
+                EStream& s = st_[i];
+                if (s.next_frame >= limit) continue;
+                if (s.lost) {
+                    for (int k = s.next_frame; k < limit; ++k) put_pose(traj, i, n_frames, k, s);
+                    s.next_frame = limit;
+                    continue;
+                }
+                // window: up to and including the first frame that may become a key-frame; past that point every frame may, and a
+                // few frames are tracked speculatively -- the ones behind a key-frame trigger are dropped and tracked again against
+                // the new key-frame next round (results stay those of frame-by-frame processing)
+                int w = 1;
+                if (!s.kfs.empty()) {
+                    const int sure = prm_.kf_min_frames - s.frames_since_kf;
+                    w = sure >= 1 ? std::min(F_, sure) : std::min(F_, kSpeculativeFrames);
+                }
+                w = std::min(w, limit - s.next_frame);
+                CHK(ygzb_tracker_upload(tr_, i * F_, w, images[i] + (size_t)s.next_frame * W * H, (size_t)W * H));
+                h2d_image_bytes += (long long)w * W * H;
+                if (s.kfs.empty()) {
+                    wins_.push_back({i, s.next_frame, 1, -1});
+                    continue;
+                }
+                wins_.push_back({i, s.next_frame, w, (int)jobs.size()});
+                const int nl = std::min(kLocalKeyframes, (int)s.kfs.size());
+                for (int t = 0; t < w; ++t) {
+                    ygzb_track_job j{};
+                    j.stream = i;
+                    j.cur_slot = i * F_ + t;
+                    j.n_local = nl;
+                    for (int k = 0; k < nl; ++k) j.entry[k] = s.kfs[s.kfs.size() - nl + k].entry;
+                    jobs.push_back(j);
+                }
+            }
+            if (!jobs.empty()) {
+                StageTimer tm(kTSparse);
+                CHK(ygzb_tracker_track(tr_, (int)jobs.size(), jobs.data(), h_res_));
+                h2d_other_bytes += (long long)(jobs.size() * sizeof(ygzb_track_job));
+                d2h_bytes += (long long)(jobs.size() * sizeof(ygzb_track_result));
+            }
+            if (kjobs.empty() && wins_.empty()) return YGZB_OK;   // every stream is at `limit`, nothing in flight
+            // ---- 4. one synchronisation per round; key-frame results
+            {
+                StageTimer tm(kTPoseOnly);
+                CHK(ygzb_synchronize(ctx_));
+            }
             for (size_t q = 0; q < kjobs.size(); ++q) {
                 const ygzb_keyframe_job& kj = kjobs[q];
                 const ygzb_keyframe_result& r = h_kres_[q];
                 EStream& s = st_[kj.stream];
-                KfInfo kf;
-                kf.entry = kj.entry;
-                kf.n = r.n_features;
-                kf.frame_id = kframe[q];
-                kf.mp0 = kj.mp0;
+                s.kfs.back().n = r.n_features;
                 s.next_mp = kj.mp0 + r.n_features;
-                s.kfs.push_back(kf);
-                while ((int)s.kfs.size() > YGZB_TRACK_RING) s.kfs.pop_front();
                 for (int k = 0; k < kj.n_local; ++k) std::memcpy(s.kfs[s.kfs.size() - kj.n_local + k].T.m, r.T_cw[k], sizeof(Mat34));
                 s.T = s.kfs.back().T;
-                s.frames_since_kf = 0;
-                s.n_keyframes += 1;
                 if (kj.run_ba && kj.n_local >= 2) {
                     s.n_ba += 1;
                     s.ba_obs += r.ba_observations; s.ba_pts += r.ba_points; s.ba_kfs += kj.n_local; s.ba_trials += r.ba_trials; s.ba_iters += r.ba_iters;
@@ -694,7 +713,6 @@ class Engine {
                 put_pose(traj, kj.stream, n_frames, kframe[q], s);
             }
         }
-        return YGZB_OK;
     }
 
   private:
@@ -738,6 +756,7 @@ class Engine {
     ygzb_track_result* h_res_ = nullptr;
     ygzb_keyframe_result* h_kres_ = nullptr;
     ygzb_ba_params ba_;
+    std::vector<Win> wins_;
 };
 
 }  // namespace
@@ -869,7 +888,7 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
             Engine eng(my, ns, window, Params{kf_min_frames, kf_min_rot, kf_min_trans});
             if (rc == YGZB_OK) rc = eng.init(depth + s0);
             double* my_traj = traj + (size_t)s0 * n_frames * 12;
-            while (rc == YGZB_OK && !eng.all_reached(warm)) rc = eng.round(images + s0, n_frames, warm, my_traj);
+            if (rc == YGZB_OK) rc = eng.run_until(images + s0, n_frames, warm, my_traj);
             if (rc == YGZB_OK) ygzb_synchronize(my);
             tot[t][0] = -ygzb_launch_count(my);
             eng.h2d_image_bytes = eng.h2d_other_bytes = eng.d2h_bytes = 0;
@@ -879,7 +898,7 @@ int ygz_vo_run(ygzb_ctx* ctx, int device, const ygzb_params* params, int n_threa
                 for (auto& v : g_stage_ns) v.store(0);
                 ygzb_timer_start(ctx);
             }
-            while (rc == YGZB_OK && !eng.all_reached(n_frames)) rc = eng.round(images + s0, n_frames, n_frames, my_traj);
+            if (rc == YGZB_OK) rc = eng.run_until(images + s0, n_frames, n_frames, my_traj);
             if (rc == YGZB_OK) ygzb_synchronize(my);
             tot[t][0] += ygzb_launch_count(my);
             tot[t][1] = eng.h2d_image_bytes; tot[t][2] = eng.h2d_other_bytes; tot[t][3] = eng.d2h_bytes;
