@@ -327,6 +327,59 @@ def secondary_workloads(ctx) -> dict:
     return out
 
 
+def opencv_owned_stages(ora) -> dict:
+    """The stages the reference delegates to OpenCV (SURVEY 8a: cv::pyrDown Frame.cpp:127-141, cv::BFMatcher
+    test_orb_match.cpp:109-131, cv::calcOpticalFlowPyrLK Tracker.cpp:86-133), timed with cv2 itself beside the oracle's port
+    of the same arithmetic, on 1 thread and on cv2's default thread count.  cv2 is a timing witness only."""
+    try:
+        import cv2
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+    from ygz_slam_b200 import synth
+    g1, _, _ = synth.stream_frame(1)
+    g2, _, _ = synth.stream_frame(3)
+
+    def best(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return 1e3 * min(ts)
+
+    p1, p2 = ora.build_pyramid(g1, LEVELS), ora.build_pyramid(g2, LEVELS)
+    f1, f2 = ora.detect(p1, n_levels=LEVELS), ora.detect(p2, n_levels=LEVELS)
+    d1 = ora.describe(p1, W, H, LEVELS, f1["px"], f1["py"], f1["level"])[1]
+    d2 = ora.describe(p2, W, H, LEVELS, f2["px"], f2["py"], f2["level"])[1]
+    n_klt = min(1000, f1["n"])
+    pts = np.stack([f1["px"][:n_klt], f1["py"][:n_klt]], 1).astype(np.float32)
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING, True)
+
+    def cv_pyr3():
+        a = cv2.pyrDown(g1)
+        return cv2.pyrDown(a)
+
+    def cv_klt():
+        return cv2.calcOpticalFlowPyrLK(g1, g2, pts.reshape(-1, 1, 2), pts.reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=4,
+                                        criteria=(cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.001),
+                                        flags=cv2.OPTFLOW_USE_INITIAL_FLOW, minEigThreshold=1e-4)
+
+    out = {"inputs": {"image": "640x480 u8", "descriptors": [int(len(d1)), int(len(d2))], "klt_points": int(n_klt)}}
+    default_threads = cv2.getNumThreads()
+    for label, nt in (("cv2_1_thread_ms", 1), ("cv2_default_threads_ms", default_threads)):
+        cv2.setNumThreads(nt)
+        out[label] = {"threads": nt, "pyrDown_3_levels": best(cv_pyr3), "BFMatcher_hamming_crosscheck": best(lambda: bf.match(d1, d2)),
+                      "calcOpticalFlowPyrLK_21x21_5_levels": best(cv_klt)}
+    cv2.setNumThreads(default_threads)
+    out["port_1_thread_ms"] = {"threads": 1, "pyrDown_3_levels": best(lambda: ora.build_pyramid(g1, 3)),
+                               "BFMatcher_hamming_crosscheck": best(lambda: ora.match_bf(d1, d2)),
+                               "calcOpticalFlowPyrLK_21x21_5_levels": best(lambda: ora.klt(g1, g2, pts, pts.copy()), reps=2)}
+    out["note"] = ("in the C5 loop only the pyramid is OpenCV-owned (its share is cpu_baseline.stage_share_1_thread.pyramid); the "
+                   "matcher and the KLT belong to BASELINE configs C2 and C1")
+    return out
+
+
 def workload_config(batch: int, how: str) -> dict:
     return {"workload": "C2: FAST-10+ORB extract (grid 10px, thr 15) + cross-checked brute-force Hamming match, "
                         "640x480 u8, 8-level pyramid, frame i matched against frame i+1",
@@ -448,13 +501,15 @@ def vo_line(args, rank, world, local_rank):
     data = vo_streams(S * rank, S, n)
     stacked = vo_native.stack_pinned([d[0] for d in data])
     depths = [d[1] for d in data]
-    # host threads (= ygzb contexts = CUDA streams): every stream is its own latency-bound chain of kernels, so one thread per
-    # stream overlaps the most chains (measured: 1 / 2 / 4 / 8 threads -> 15.5k / 20.1k / 19.9k / 23.1k frames/s); capped by the
-    # CPUs this rank may use (the threads spin in cudaStreamSynchronize)
+    # host threads (= ygzb contexts = CUDA streams): every thread drives a latency-bound chain of kernels for its streams and the
+    # chains of different threads overlap on the GPU.  Measured on one B200, 8 streams: 2 / 3 / 4 / 8 threads -> 22.5k / 23.7k /
+    # 23.9k / 21.6k frames/s; 32 streams: 4 / 8 / 16 threads -> 31k / 33.6k / collapse (the threads spin in
+    # cudaStreamSynchronize: 16 spinning threads on a 16-CPU cgroup quota get throttled).  Default: one thread per two streams,
+    # at most half of the CPUs this rank may use.
     if args.vo_threads > 0:
         threads = max(1, min(args.vo_threads, S))
     else:
-        threads = max(1, min(S, max(2, usable_threads()[0] // max(world, 1))))
+        threads = max(1, min(max(1, S // 2), 8, max(2, usable_threads()[0] // (2 * max(world, 1)))))
     ctx = Context(local_rank)
 
     def barrier():
@@ -561,8 +616,9 @@ def vo_line(args, rank, world, local_rank):
             main_roof["peak_source"] = peak_src
             try:
                 tr = json.loads((ROOT / "profiles" / "r2_dram_traffic.json").read_text()).get(main_roof["kernel"], {})
-                if tr.get("dram_bytes_per_launch"):
-                    main_roof["traffic"] = tr["dram_bytes_per_launch"]
+                if tr.get("dram_bytes_per_problem") and main_roof["kernel"] == "local_ba":
+                    # captured per problem (= per cluster); a launch of the profiled pass carries agg["ba"] / launches problems
+                    main_roof["traffic"] = tr["dram_bytes_per_problem"] * agg["ba"] / max(shares["local_ba"]["launches"], 1)
                     main_roof["traffic_source"] = tr.get("source")
             except Exception:  # noqa: BLE001
                 pass
@@ -593,6 +649,10 @@ def vo_line(args, rank, world, local_rank):
                        "one_thread_per_stream": {"threads": min(thr, S), "streams": S, "frames_per_s": fpsS, "seconds": secS},
                        "stage_share_1_thread": {k: v / tot for k, v in stage1.items()},
                        "logical_cpus": os.cpu_count(), "affinity_cpus": affinity, "cgroup_cpu_quota": quota}
+                try:
+                    cpu["opencv_owned_stages"] = opencv_owned_stages(ora)
+                except Exception as e:  # noqa: BLE001
+                    cpu["opencv_owned_stages"] = {"error": repr(e)}
             except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
                 cpu = {"error": repr(e)}
             if not args.no_secondary:
@@ -615,6 +675,11 @@ def vo_line(args, rank, world, local_rank):
                     "h2d_image_bytes_per_step": det_e["h2d_image_bytes"] / args.steps,
                     "timing": "wall clock between device synchronisations (host bookkeeping and several CUDA streams are part of the step)"},
             "gpu_launches": int(det_r["gpu_launches"]),
+            # serialised kernel time of the profiled pass (CUDA events around every launch, one context) scaled to the timed region,
+            # over the timed wall: > 1 means kernels of several CUDA streams overlapped
+            "gpu_busy": {"kernel_ms_per_frame_serialised": total_ms / prof_frames,
+                         "kernel_time_over_wall_resident": (total_ms / prof_frames) * S * timed / ms_resident,
+                         "kernel_time_over_wall_e2e": (total_ms / prof_frames) * S * timed / ms_e2e},
             "clocks": clocks,
             "roofline": main_roof, "roofline_kernels": roof, "kernel_shares": shares,
             "cpu_baseline": cpu,

@@ -166,6 +166,35 @@ int ygzb_depth_from_triangulation(ygzb_ctx* ctx, int n, int n_poses, const doubl
                                   const double* f_ref, const double* f_cur, double determinant_th, double* depth1, double* depth2,
                                   uint8_t* ok);
 
+/* ---- DBoW3 vocabulary: Frame::ComputeBoW and BoW-guided matching ---------------------------------
+ * replaces DBoW3::Vocabulary::loadFromBinaryFile (thirdparty/DBoW3/src/Vocabulary.cpp:1180-1225; the call
+ * test/test_orb_match.cpp:74 `vocab.loadFromBinaryFile("./vocab/ORBvoc.bin")`): file_bytes = the whole file (u32 nb_nodes,
+ * u32 size_node, i32 k, i32 L, i32 scoring, i32 weighting, then {i32 parent, u8 descriptor[32], f32 weight, u8 is_leaf}
+ * records).  The tree is uploaded once and stays resident (39 MB for ORBvoc.bin).  Malformed data -> YGZB_ERR_INVALID.    */
+typedef struct ygzb_vocab ygzb_vocab;
+int ygzb_vocab_create(ygzb_ctx* ctx, const void* file_bytes, size_t n_bytes, ygzb_vocab** out);
+void ygzb_vocab_destroy(ygzb_vocab* v);
+/* info[6] = k, L, scoring (DBoW3::ScoringType), weighting (DBoW3::WeightingType), nodes, words -- like the reference, the
+ * counts include the copy of the last record its `while (!f.eof())` loop appends */
+int ygzb_vocab_info(const ygzb_vocab* v, int32_t* info);
+/* replaces DBoW3::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup) (Vocabulary.cpp:706-832) as called by
+ * Frame::ComputeBoW (src/Basic/Frame.cpp:190-201, levelsup = 4) for n_frames frames: frame f owns descriptors
+ * [offsets[f], offsets[f+1]) (32 bytes each, at most 16384 per frame).  Per descriptor: word[i], weight[i] (the word's
+ * weight) and node[i] = the id of its ancestor at level L - levelsup = the key of the FeatureVector entry the feature
+ * index is appended to (-1 when the word is stopped, weight <= 0: such a feature enters neither vector).  The BowVector
+ * of frame f = bow_count[f] pairs (bow_word ascending, bow_value) stored from index offsets[f] of bow_word / bow_value.
+ * Word, node and count outputs are exact; bow_value differs from the reference's map-order sum in the last bits only.    */
+int ygzb_bow_transform(ygzb_vocab* v, int n_frames, const int32_t* offsets, const uint8_t* desc, int levelsup, int32_t* word,
+                       int32_t* node, double* weight, int32_t* bow_count, int32_t* bow_word, double* bow_value);
+/* replaces Matcher::SearchByBoW (src/Algorithm/Matcher.cpp:196-292; Matcher.h:52-58) for n_pairs key-frame pairs, the
+ * feature vectors given as one node id per feature (ygzb_bow_transform's `node`).  th_low / knn_ratio / check_orientation =
+ * Matcher::Options (Matcher.h:21-24: 50, 0.9, false).  match12[i] = index inside key-frame 2 of the pair or -1; count[p] =
+ * the function's return value (with check_orientation the matches outside the three dominant rotation bins are counted
+ * out but -- as in the reference, Matcher.cpp:280-285 -- stay in match12); angle1 / angle2 may be NULL without it.       */
+int ygzb_search_by_bow(ygzb_ctx* ctx, int n_pairs, const int32_t* off1, const int32_t* off2, const uint8_t* desc1,
+                       const int32_t* node1, const float* angle1, const uint8_t* desc2, const int32_t* node2, const float* angle2,
+                       int th_low, float knn_ratio, int check_orientation, int32_t* match12, int32_t* count);
+
 /* ---- cvutils / Matcher: direct (photometric) alignment ---------------------------------------
  * replaces cvutils::Align2D (src/Algorithm/CVUtils.cpp:186-318; include/ygz/Algorithm/CVUtils.h:163-169):
  * inverse-compositional alignment of an 8x8 template.  Patch i is searched on pyramid level level[i] of

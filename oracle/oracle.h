@@ -99,6 +99,19 @@ void ora_search_for_triangulation(const ora_camera* cam, int n1, const uint8_t* 
 int ora_depth_from_triangulation(const double* T_search_ref, const double* f_ref, const double* f_cur, double determinant_th,
                                  double* depth1, double* depth2);
 
+/* ---- DBoW3 (thirdparty/DBoW3/src/Vocabulary.cpp; bow.cpp) --------------------------------------------------------------- */
+typedef struct ora_vocab ora_vocab;
+/* Vocabulary::loadFromBinaryFile (Vocabulary.cpp:1180-1225) from the file's bytes; NULL if malformed */
+ora_vocab* ora_vocab_load(const uint8_t* bytes, size_t n_bytes);
+void ora_vocab_free(ora_vocab* v);
+void ora_vocab_info(const ora_vocab* v, int32_t* info /* k, L, scoring, weighting, nodes, words */);
+/* Vocabulary::transform(features, bow, feature vector, levelsup) (Vocabulary.cpp:706-832), Frame::ComputeBoW (Frame.cpp:190-201) */
+int ora_bow_transform(const ora_vocab* v, int n, const uint8_t* desc, int levelsup, int32_t* word, int32_t* node, double* weight,
+                      int32_t* bow_word, double* bow_value);
+/* Matcher::SearchByBoW (Matcher.cpp:196-292) */
+int ora_search_by_bow(int n1, const uint8_t* desc1, const int32_t* node1, const float* angle1, int n2, const uint8_t* desc2,
+                      const int32_t* node2, const float* angle2, int th_low, float knn_ratio, int check_orientation, int32_t* match12);
+
 /* ---- patch alignment (src/Algorithm/CVUtils.cpp:186-318; Matcher.cpp:356-466) ----------- */
 int ora_align2d(const uint8_t* img, int w, int h, const uint8_t* ref_with_border /*100*/,
                 const uint8_t* ref /*64*/, int n_iter, double* u, double* v);

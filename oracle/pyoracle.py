@@ -306,6 +306,46 @@ class Oracle:
                                               int(th_low), C.c_double(epipolar_dsqr), _p(out))
         return out
 
+    # ---- DBoW3 (bow.cpp) ----------------------------------------------------------------------
+    def vocab_load(self, data: bytes):
+        """Vocabulary::loadFromBinaryFile from the file's bytes -> opaque handle (free with vocab_free)."""
+        self.lib.ora_vocab_load.restype = C.c_void_p
+        self.lib.ora_vocab_load.argtypes = [C.c_char_p, C.c_size_t]
+        h = self.lib.ora_vocab_load(data, len(data))
+        if not h:
+            raise ValueError("malformed vocabulary")
+        return C.c_void_p(h)
+
+    def vocab_free(self, v):
+        self.lib.ora_vocab_free.argtypes = [C.c_void_p]
+        self.lib.ora_vocab_free(v)
+
+    def vocab_info(self, v):
+        info = np.zeros(6, np.int32)
+        self.lib.ora_vocab_info.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.ora_vocab_info(v, _p(info))
+        return dict(zip(("k", "L", "scoring", "weighting", "nodes", "words"), info.tolist()))
+
+    def bow_transform(self, v, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word, node, weight = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n)
+        bw, bv = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1))
+        self.lib.ora_bow_transform.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        m = self.lib.ora_bow_transform(v, n, _p(desc), int(levelsup), _p(word), _p(node), _p(weight), _p(bw), _p(bv))
+        return word, node, weight, bw[:m].copy(), bv[:m].copy()
+
+    def search_by_bow(self, desc1, node1, angle1, desc2, node2, angle2, th_low=50, knn_ratio=0.9, check_orientation=False):
+        n1, n2 = len(node1), len(node2)
+        out = np.full(n1, -1, np.int32)
+        self.lib.ora_search_by_bow.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_float, C.c_int, C.c_void_p]
+        cnt = self.lib.ora_search_by_bow(n1, _p(np.ascontiguousarray(desc1, np.uint8)), _p(np.ascontiguousarray(node1, np.int32)),
+                                         _p(np.ascontiguousarray(angle1, np.float32)), n2, _p(np.ascontiguousarray(desc2, np.uint8)),
+                                         _p(np.ascontiguousarray(node2, np.int32)), _p(np.ascontiguousarray(angle2, np.float32)),
+                                         int(th_low), float(knn_ratio), int(check_orientation), _p(out))
+        return out, cnt
+
     def depth_from_triangulation(self, T, f_ref, f_cur, det_th=1e-5):
         T = np.ascontiguousarray(T, np.float64).reshape(12)
         f_ref = np.ascontiguousarray(f_ref, np.float64).reshape(-1, 3)

@@ -192,5 +192,24 @@ int main(int argc, char** argv) {
         printf("slots keyframe_features %zu same_as_frame1 %d compute_descriptor_same %d exhausted %d free_restored %d jac %.6f\n", n_kf,
                (int)(n_kf == f1._features.size()), (int)same_desc, (int)exhausted, (int)(rt.FreeSlots() == free0), J(0, 4));
     }
+    if (argc > 2) {
+        // test_orb_match.cpp:72-75 shape: vocabulary from a DBoW3 binary file, Frame::ComputeBoW, Matcher::SearchByBoW
+        ORBVocabulary vocab;
+        if (!vocab.loadFromBinaryFile(argv[2])) return 11;
+        Frame::SetORBVocabulary(&vocab);
+        f1.ComputeBoW();
+        f2.ComputeBoW();
+        double sum1 = 0;
+        for (auto& kv : f1._bow_vec) sum1 += kv.second;
+        size_t in_fv = 0;
+        for (auto& kv : f1._feature_vec) in_fv += kv.second.size();
+        std::map<int, int> bow_matches;
+        const int cnt = m.SearchByBoW(&f1, &f2, bow_matches);
+        long h = 0;
+        for (auto& kv : bow_matches) h = (h * 31 + kv.first * 7 + kv.second) % 1000003;
+        printf("bow words %u bow_vec %zu feature_vec_nodes %zu features_in_nodes %zu sum %.12f matches %d map %zu hash %ld\n", vocab.size(),
+               f1._bow_vec.size(), f1._feature_vec.size(), in_fv, sum1, cnt, bow_matches.size(), h);
+        Frame::SetORBVocabulary(nullptr);
+    }
     return 0;
 }

@@ -37,7 +37,10 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     blob = tmp_path / "in.bin"
     with open(blob, "wb") as f:
         f.write(g1.tobytes()); f.write(g2.tobytes()); f.write(d1.astype(np.float32).tobytes()); f.write(Trel.astype(np.float64).tobytes())
-    r = subprocess.run([str(EXE), str(blob)], capture_output=True, text=True, check=True)
+    voc_file = tmp_path / "voc.bin"
+    voc_data = synth.make_vocabulary(k=8, L=5, seed=21)
+    voc_file.write_bytes(voc_data)
+    r = subprocess.run([str(EXE), str(blob), str(voc_file)], capture_output=True, text=True, check=True)
     lines = r.stdout.strip().splitlines()
     f1 = oracle.detect(oracle.build_pyramid(g1, 3))
     f2 = oracle.detect(oracle.build_pyramid(g2, 3))
@@ -69,3 +72,16 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     sl = lines[8].split()
     assert sl[0] == "slots" and sl[4] == "1" and sl[6] == "1" and sl[8] == "1" and sl[10] == "1"
     assert abs(float(sl[12]) - (-(1.0 + 0.1 * 0.1 / 4.0))) < 1e-9      # JacobXYZ2Cam(0.1, -0.2, 2)(0, 4) = -(1 + x^2/z^2)
+    # DBoW3 front (ORBVocabulary::loadFromBinaryFile, Frame::ComputeBoW, Matcher::SearchByBoW with the shim's th_low = 65)
+    v = oracle.vocab_load(voc_data)
+    _, n1, _, bw1, bv1 = oracle.bow_transform(v, f1["desc"], 4)
+    _, n2, _, _, _ = oracle.bow_transform(v, f2["desc"], 4)
+    om, ocnt = oracle.search_by_bow(f1["desc"], n1, f1["angle"], f2["desc"], n2, f2["angle"], th_low=65, knn_ratio=0.9, check_orientation=False)
+    h = 0
+    for i in np.flatnonzero(om >= 0):
+        h = (h * 31 + int(i) * 7 + int(om[i])) % 1000003
+    bl = lines[9].split()
+    assert bl[0] == "bow" and int(bl[2]) == oracle.vocab_info(v)["words"] and int(bl[4]) == len(bw1)
+    assert int(bl[6]) == len(set(n1[n1 >= 0])) and int(bl[8]) == int((n1 >= 0).sum())
+    assert abs(float(bl[10]) - bv1.sum()) < 1e-10 and int(bl[12]) == ocnt and int(bl[14]) == int((om >= 0).sum()) and int(bl[16]) == h
+    oracle.vocab_free(v)

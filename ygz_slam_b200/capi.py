@@ -37,7 +37,8 @@ EXPORTS = [
     "ygzb_profile_stage_name", "ygzb_host_alloc", "ygzb_host_free", "ygzb_frames_create", "ygzb_frames_destroy",
     "ygzb_frames_upload", "ygzb_frames_copy", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
-    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_search_for_triangulation", "ygzb_depth_from_triangulation", "ygzb_align2d", "ygzb_align1d",
+    "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_search_for_triangulation", "ygzb_depth_from_triangulation",
+    "ygzb_vocab_create", "ygzb_vocab_destroy", "ygzb_vocab_info", "ygzb_bow_transform", "ygzb_search_by_bow", "ygzb_align2d", "ygzb_align1d",
     "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_two_view_ba", "ygzb_pose_only",
     "ygzb_default_klt_params", "ygzb_klt",
     "ygzb_tracker_create", "ygzb_tracker_destroy", "ygzb_tracker_set_depth", "ygzb_tracker_upload", "ygzb_tracker_track", "ygzb_tracker_make_keyframes",
@@ -538,6 +539,58 @@ def _depth_from_triangulation(self, T, pose_of, f_ref, f_cur, det_th=1e-5):
     return d1, d2, ok.astype(bool)
 
 
+class Vocabulary:
+    """DBoW3 vocabulary resident on the device (ygzb_vocab_*): Vocabulary::loadFromBinaryFile + transform."""
+
+    def __init__(self, ctx, data: bytes):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        ctx.lib.ygzb_vocab_create.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
+        ctx.check(ctx.lib.ygzb_vocab_create(ctx.h, data, len(data), C.byref(self.h)), "ygzb_vocab_create")
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ygzb_vocab_destroy.argtypes = [C.c_void_p]
+            self.ctx.lib.ygzb_vocab_destroy.restype = None
+            self.ctx.lib.ygzb_vocab_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def info(self):
+        out = np.zeros(6, np.int32)
+        self.ctx.check(self.ctx.lib.ygzb_vocab_info(self.h, _p(out)), "ygzb_vocab_info")
+        return dict(zip(("k", "L", "scoring", "weighting", "nodes", "words"), out.tolist()))
+
+    def transform(self, offsets, desc, levelsup=4):
+        """-> word, node, weight per descriptor and, per frame, the BowVector as (word ids ascending, values)."""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        n, F = int(offsets[-1]), len(offsets) - 1
+        word, node, weight = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n)
+        cnt, bw, bv = np.zeros(F, np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1))
+        self.ctx.check(self.ctx.lib.ygzb_bow_transform(self.h, F, _p(offsets), _p(np.ascontiguousarray(desc, np.uint8)), int(levelsup), _p(word),
+                                                       _p(node), _p(weight), _p(cnt), _p(bw), _p(bv)), "ygzb_bow_transform")
+        bows = [(bw[offsets[f]:offsets[f] + cnt[f]].copy(), bv[offsets[f]:offsets[f] + cnt[f]].copy()) for f in range(F)]
+        return word, node, weight, bows
+
+
+def _search_by_bow(self, off1, off2, desc1, node1, angle1, desc2, node2, angle2, th_low=50, knn_ratio=0.9, check_orientation=False):
+    """Batched Matcher::SearchByBoW -> (match12, count per pair)."""
+    off1 = np.ascontiguousarray(off1, np.int32)
+    off2 = np.ascontiguousarray(off2, np.int32)
+    P = len(off1) - 1
+    out = np.full(int(off1[-1]), -1, np.int32)
+    cnt = np.zeros(P, np.int32)
+    a1 = None if angle1 is None else np.ascontiguousarray(angle1, np.float32)
+    a2 = None if angle2 is None else np.ascontiguousarray(angle2, np.float32)
+    self.lib.ygzb_search_by_bow.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    self.check(self.lib.ygzb_search_by_bow(self.h, P, _p(off1), _p(off2), _p(np.ascontiguousarray(desc1, np.uint8)),
+                                           _p(np.ascontiguousarray(node1, np.int32)), _p(a1), _p(np.ascontiguousarray(desc2, np.uint8)),
+                                           _p(np.ascontiguousarray(node2, np.int32)), _p(a2), int(th_low), float(knn_ratio),
+                                           int(check_orientation), _p(out), _p(cnt)), "ygzb_search_by_bow")
+    return out, cnt
+
+
+Context.search_by_bow = _search_by_bow
+Context.vocabulary = lambda self, data: Vocabulary(self, data)
 Context.search_for_triangulation = _search_for_triangulation
 Context.depth_from_triangulation = _depth_from_triangulation
 Context.local_ba = _local_ba

@@ -18,6 +18,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <list>
 #include <cmath>
@@ -117,6 +118,8 @@ class PinholeCamera {  // include/ygz/Basic/Camera.h:10-112
     float _fx, _fy, _cx, _cy;
 };
 
+class ORBVocabulary;
+
 struct Frame {  // include/ygz/Basic/Frame.h:20-166 (fields used on the hot path)
     struct Option { int _pyramid_level = 3; } _option;
     ~Frame();          // releases the device pyramid slot: a frame pins its slot for as long as it lives (key-frames in Memory: for good)
@@ -129,14 +132,18 @@ struct Frame {  // include/ygz/Basic/Frame.h:20-166 (fields used on the hot path
         _features.clear();
     }
     static void SetCamera(PinholeCamera* c) { _camera = c; }
+    static void SetORBVocabulary(ORBVocabulary* v) { _vocab = v; }   // Frame.h:101
+    void ComputeBoW();   // Frame.cpp:190-201: _vocab->transform(all descriptors, _bow_vec, _feature_vec, 4)
     unsigned long _id = 0, _keyframe_id = 0;
     SE3 _TCW;
     bool _is_keyframe = false;
     std::vector<Feature*> _features;
     Mat _color;                 // BGR (3 channels) or grey (1 channel) input image
     std::map<unsigned, std::vector<unsigned>> _feature_vec;   // DBoW3::FeatureVector of Frame::ComputeBoW (Frame.cpp:190-201): node -> feature indices
+    std::map<unsigned, double> _bow_vec;                      // DBoW3::BowVector: word -> normalised tf-idf
     int _slot = -1;             // device pyramid slot (set by InitFrame)
     static inline PinholeCamera* _camera = nullptr;
+    static inline ORBVocabulary* _vocab = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -231,6 +238,79 @@ inline void Frame::InitFrame() {
     if (_slot < 0) _slot = rt.AcquireSlot(this);   // (a second InitFrame of the same frame re-uses its slot)
     rt.Check(ygzb_frames_upload(rt.frames(), _slot, 1, _color.data, _color.channels, (size_t)_color.rows * _color.cols * _color.channels),
              "ygzb_frames_upload");
+}
+
+// DBoW3::Vocabulary as the reference uses it (typedef DBoW3::Vocabulary ORBVocabulary, Common.h): the tree lives on the device
+class ORBVocabulary {
+  public:
+    typedef std::map<unsigned, double> BowVector;                        // DBoW3/BowVector.h:52
+    typedef std::map<unsigned, std::vector<unsigned>> FeatureVector;     // DBoW3/FeatureVector.h
+    ORBVocabulary() = default;
+    ORBVocabulary(const ORBVocabulary&) = delete;
+    ORBVocabulary& operator=(const ORBVocabulary&) = delete;
+    ~ORBVocabulary() { clear(); }
+    // Vocabulary.cpp:1180-1225; false if the file cannot be read or is malformed (the reference does not check)
+    bool loadFromBinaryFile(const std::string& filename) {
+        std::FILE* f = std::fopen(filename.c_str(), "rb");
+        if (!f) return false;
+        std::vector<uint8_t> bytes;
+        uint8_t buf[1 << 16];
+        size_t got;
+        while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) bytes.insert(bytes.end(), buf, buf + got);
+        std::fclose(f);
+        return loadFromMemory(bytes.data(), bytes.size());
+    }
+    bool loadFromMemory(const void* bytes, size_t n) {
+        clear();
+        auto& rt = b200::Runtime::Get();
+        if (ygzb_vocab_create(rt.ctx(), bytes, n, &v_) != YGZB_OK) {
+            v_ = nullptr;
+            return false;
+        }
+        return true;
+    }
+    bool empty() const { return v_ == nullptr; }
+    unsigned size() const { return (unsigned)info(5); }                   // number of words
+    int getBranchingFactor() const { return info(0); }
+    int getDepthLevels() const { return info(1); }
+    // Vocabulary.cpp:706-776; features = 32-byte descriptors
+    void transform(const std::vector<const uint8_t*>& features, BowVector& v, FeatureVector& fv, int levelsup) const {
+        v.clear();
+        fv.clear();
+        if (empty() || features.empty()) return;
+        auto& rt = b200::Runtime::Get();
+        const int n = (int)features.size();
+        std::vector<uint8_t> desc((size_t)n * 32);
+        for (int i = 0; i < n; ++i) std::memcpy(&desc[(size_t)i * 32], features[i], 32);
+        const int32_t off[2] = {0, n};
+        std::vector<int32_t> word(n), node(n), bw(n);
+        std::vector<double> weight(n), bv(n);
+        int32_t cnt = 0;
+        rt.Check(ygzb_bow_transform(v_, 1, off, desc.data(), levelsup, word.data(), node.data(), weight.data(), &cnt, bw.data(), bv.data()),
+                 "ygzb_bow_transform");
+        for (int q = 0; q < cnt; ++q) v.emplace_hint(v.end(), (unsigned)bw[q], bv[q]);
+        for (int i = 0; i < n; ++i)
+            if (node[i] >= 0) fv[(unsigned)node[i]].push_back((unsigned)i);
+    }
+    void clear() {
+        if (v_) ygzb_vocab_destroy(v_);
+        v_ = nullptr;
+    }
+  private:
+    int info(int i) const {
+        int32_t a[6] = {0, 0, 0, 0, 0, 0};
+        if (v_) ygzb_vocab_info(v_, a);
+        return a[i];
+    }
+    ygzb_vocab* v_ = nullptr;
+};
+
+inline void Frame::ComputeBoW() {
+    if (_vocab != nullptr && _bow_vec.empty()) {
+        std::vector<const uint8_t*> alldesp;
+        for (Feature* fea : _features) alldesp.push_back(fea->_desc);
+        _vocab->transform(alldesp, _bow_vec, _feature_vec, 4);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -414,6 +494,8 @@ class Matcher {  // include/ygz/Algorithm/Matcher.h
         double _max_alignment_motion = 0.2;
         int th_low = 65;                      // matcher.th_low (config/default.yaml:54)
         double _epipolar_dsqr = 1e-4;         // Matcher.h:31
+        float knnRatio = 0.9f;                // Matcher.h:22
+        bool checkOrientation = false;        // Matcher.h:24
     } _options;
     Matcher() : _align(new SparseImgAlign(2, 0, 30, SparseImgAlign::GaussNewton, false, false)) {}
     // Matcher.cpp:30-43
@@ -477,6 +559,34 @@ class Matcher {  // include/ygz/Algorithm/Matcher.h
         for (size_t i = 0; i < m12.size(); ++i)
             if (m12[i] >= 0) matched_points.push_back(std::make_pair((int)i, (int)m12[i]));
         return (int)matched_points.size();
+    }
+    // Matcher.cpp:196-292: best / second-best Hamming match inside the common vocabulary nodes of the two feature vectors
+    int SearchByBoW(Frame* kf1, Frame* kf2, std::map<int, int>& matches) {
+        auto& rt = b200::Runtime::Get();
+        auto flatten = [](Frame* f, std::vector<uint8_t>& desc, std::vector<float>& angle, std::vector<int32_t>& node) {
+            const size_t n = f->_features.size();
+            desc.resize(32 * n); angle.resize(n); node.assign(n, -1);
+            for (size_t i = 0; i < n; ++i) {
+                std::memcpy(&desc[32 * i], f->_features[i]->_desc, 32);
+                angle[i] = (float)f->_features[i]->_angle;
+            }
+            for (const auto& kv : f->_feature_vec)
+                for (unsigned idx : kv.second)
+                    if (idx < n) node[idx] = (int32_t)kv.first;
+        };
+        std::vector<uint8_t> d1, d2;
+        std::vector<float> a1, a2;
+        std::vector<int32_t> n1, n2;
+        flatten(kf1, d1, a1, n1);
+        flatten(kf2, d2, a2, n2);
+        const int32_t off1[2] = {0, (int32_t)n1.size()}, off2[2] = {0, (int32_t)n2.size()};
+        std::vector<int32_t> m12(n1.size(), -1);
+        int32_t cnt = 0;
+        rt.Check(ygzb_search_by_bow(rt.ctx(), 1, off1, off2, d1.data(), n1.data(), a1.data(), d2.data(), n2.data(), a2.data(), _options.th_low,
+                                    _options.knnRatio, _options.checkOrientation ? 1 : 0, m12.data(), &cnt), "ygzb_search_by_bow");
+        for (size_t i = 0; i < m12.size(); ++i)
+            if (m12[i] >= 0) matches[(int)i] = (int)m12[i];
+        return cnt;
     }
     static void BruteForceMatch(Frame* f1, Frame* f2, std::vector<int>& train_idx, std::vector<int>& dist, bool cross_check = true) {
         auto& rt = b200::Runtime::Get();

@@ -209,3 +209,41 @@ def shift_stream(stream: int, n_frames: int, noise_sigma: float = 2.0, plane_z: 
         poses.append(T)
     depth = np.full((H, W), plane_z, np.float64)
     return frames, depth, poses
+
+
+def make_vocabulary(k: int = 6, L: int = 4, seed: int = 0, scoring: int = 0, weighting: int = 0, stop_fraction: float = 0.1,
+                    early_leaf: float = 0.15, wide_node: bool = True) -> bytes:
+    """A random vocabulary tree in DBoW3's binary file format (Vocabulary.cpp:1180-1225): header {u32 nb_nodes (root
+    included), u32 size_node = 41, i32 k, i32 L, i32 scoring, i32 weighting}, then records {i32 parent, u8 descriptor[32],
+    f32 weight, u8 is_leaf} in depth-first creation order like DBoW3's HKmeansStep (a parent precedes its children, the
+    children of different parents interleave).  The tree is ragged like vocab/ORBvoc.bin: nodes with 2..k children, leaves
+    above level L, zero-weight (stopped) words and, optionally, one node with k + 1 children."""
+    rng = np.random.default_rng(seed)
+    recs = []   # (parent, desc, weight, leaf)
+
+    def grow(parent_id, parent_desc, level):
+        n_ch = int(rng.integers(2, k + 1))
+        if wide_node and level == 2 and not grow.widened:
+            n_ch = k + 1
+            grow.widened = True
+        kids = []
+        for _ in range(n_ch):
+            d = parent_desc.copy()
+            flips = rng.integers(0, 256, int(rng.integers(8, 48)))
+            for b in flips:
+                d[b >> 3] ^= np.uint8(1 << (b & 7))
+            leaf = level == L or (level >= 2 and rng.random() < early_leaf)
+            w = 0.0 if (leaf and rng.random() < stop_fraction) else float(np.float32(rng.uniform(0.5, 9.0)))
+            recs.append([parent_id, d, w if leaf else 0.0, leaf])
+            kids.append((len(recs), d, leaf))
+        for nid, d, leaf in kids:
+            if not leaf:
+                grow(nid, d, level + 1)
+
+    grow.widened = False
+    grow(0, rng.integers(0, 256, 32, dtype=np.uint8), 1)
+    import struct
+    out = bytearray(struct.pack("<IIiiii", len(recs) + 1, 41, k, L, scoring, weighting))
+    for parent, d, w, leaf in recs:
+        out += struct.pack("<i", parent) + d.tobytes() + struct.pack("<f", w) + bytes([1 if leaf else 0])
+    return bytes(out)
