@@ -201,6 +201,9 @@ def numpy_search_by_bow(desc1, node1, angle1, desc2, node2, angle2, th_low, rati
 
 def bow_pair(seed, n1=260, n2=300, n_nodes=12):
     rng = np.random.default_rng(seed)
+    if n2 == 0:   # a key-frame 2 without features: nothing can match
+        return (rng.integers(0, 256, (n1, 32), dtype=np.uint8), rng.integers(0, n_nodes, n1).astype(np.int32),
+                rng.uniform(0, 360, n1).astype(np.float32), np.zeros((0, 32), np.uint8), np.zeros(0, np.int32), np.zeros(0, np.float32))
     desc2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
     src = rng.integers(0, n2, n1)
     desc1 = desc2[src].copy()

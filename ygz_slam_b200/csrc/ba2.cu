@@ -51,6 +51,28 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // block-wide sum of two values (result valid in every thread); s_tmp: 2 * (kW + 1) doubles
+// Sums of N per-lane values over the warp, all at once (a "reduce-scatter" butterfly): at every step a lane keeps one half of
+// its values and hands the other half to its partner, so N values cost N - 1 (+ log2(32 / N)) shuffles instead of 5 N.
+// N = 32: lane l returns the total of v[l]; N = 16: lanes 2 i and 2 i + 1 return the total of v[i].  (A warp flushes 42
+// sums per block pair: 420 32-bit shuffles with one butterfly per value was a quarter of the accumulate phase.)
+template <int N>
+__device__ __forceinline__ double warp_reduce_scatter(double* v, int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N / 2; n >= 1; n >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const double keep = up ? v[i + n] : v[i];
+            const double send = up ? v[i] : v[i + n];
+            v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+        }
+    }
+#pragma unroll
+    for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xFFFFFFFFu, v[0], off);
+    return v[0];
+}
+
 __device__ void block_sum2(double& v0, double& v1, double* s_tmp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v0 = warp_sum(v0);
@@ -94,6 +116,8 @@ __device__ double block_max(double v, double* s_tmp) {
 
 // 1 / x for positive, normal x: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps; within 1-2 ulp of the IEEE
 // quotient at a fraction of the latency of the division sequence (the serial solve of an LM trial is latency bound)
+constexpr int kCtaSolveMinDim = 24;   // reduced systems above this size are factorised by the whole CTA
+
 __device__ __forceinline__ double fast_rcp(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -173,43 +197,18 @@ struct Stage {   // CTA-private per-landmark / per-observation state: shared mem
     int32_t* qa;     // [nl + 1] first observation of every landmark, relative to the CTA's first observation
     uint8_t* kf;     // [no]     pose index of every observation
     uint8_t* slot;   // [nl][kBA2MaxFree]  position of the landmark's observation on free pose f inside its list, 0xFF = none
+    uint32_t* ent;   // [ba2_entry_cap] dense (landmark, slot on f1, slot on f2) entries sorted by block pair, or null (see accumulate)
 };
 
-// S x = b for a symmetric positive definite S by ONE warp: LDL^T in place (unit lower triangle below the diagonal, D on it),
-// lane i owns rows i, i + 32, i + 64 (left-looking: a row's dot products against the finished columns), shared memory +
-// __syncwarp only, one fast reciprocal per column and no square root.  rd = scratch of dimp doubles (1 / D).  b is
-// overwritten with x.  Returns false (uniformly) if a pivot is not positive -- the same condition under which the Cholesky
-// factorisation of g2o's dense solver fails.
-__device__ bool warp_ldlt_solve(double* S, double* b, double* rd, int dimp, int lane) {
-    for (int j = 0; j < dimp; ++j) {
-        double sj = 0, v[3];
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            const int i = lane + 32 * m;
-            v[m] = 0;
-            if (i >= j && i < dimp) {
-                double t = S[i * dimp + j];
-                for (int k = 0; k < j; ++k) t -= S[i * dimp + k] * S[j * dimp + k] * S[k * dimp + k];
-                v[m] = t;
-                if (i == j) sj = t;
-            }
-        }
-        const double d = __shfl_sync(0xFFFFFFFFu, sj, j & 31);
-        if (!(d > 0)) return false;
-        const double r = fast_rcp(d);
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            const int i = lane + 32 * m;
-            if (i == j) {
-                S[i * dimp + j] = d;
-                rd[j] = r;
-            } else if (i > j && i < dimp) {
-                S[i * dimp + j] = v[m] * r;
-            }
-        }
-        __syncwarp();
-    }
+// upper bound of the block-pair entries of a CTA with nl landmarks and no observations on np free poses: a landmark seen by d
+// free poses contributes d (d + 1) / 2 <= d (np + 1) / 2 entries
+__host__ __device__ inline size_t ba2_entry_cap(size_t nl, size_t no, size_t np) {
+    const size_t a = (no * (np + 1) + 1) / 2, b = nl * (np * (np + 1) / 2);
+    return a < b ? a : b;
+}
+
+// L D L^T x = b by one warp with the factor of ldlt_factor_rl in S (unit lower triangle) and rd = 1 / D; b is overwritten with x
+__device__ void warp_ldlt_subst(const double* S, double* b, const double* rd, int dimp, int lane) {
     // L z = b (unit diagonal), column oriented: the lane that owns row i publishes z_i, every lane updates its later rows
     double r[3];
 #pragma unroll
@@ -242,57 +241,190 @@ __device__ bool warp_ldlt_solve(double* S, double* b, double* rd, int dimp, int 
     for (int m = 0; m < 3; ++m)
         if (lane + 32 * m < dimp) b[lane + 32 * m] = r[m];
     __syncwarp();
+}
+
+// Right-looking LDL^T by a group of TI x TK threads (one warp as 4 x 8 for the small systems of the tracking loop, the whole
+// CTA as 16 x 16 for the larger ones): per column the rank-1 update of the trailing triangle is one INDEPENDENT multiply-add
+// per element (operands loaded first, then the arithmetic, then the stores -- no dependent chain longer than one operation;
+// the left-looking version's dot product of length j per lane cost 88k cycles per LM trial at 54 x 54 and 12k at 12 x 12, a
+// dependent FP64 operation being ~40 cycles), the thread that updates the next pivot also publishes its reciprocal, and there is
+// ONE barrier per column.  Column j is scaled by 1 / D_j after the barrier (nothing reads it again before the substitution).
+// S keeps D on the diagonal and the unit lower factor below it, rd = 1 / D (0 marks a non-positive pivot: the condition under
+// which g2o's dense Cholesky fails).  Rows up to TI * A, i.e. n <= TI * A (+ the column itself).  Uniform return value.
+template <int TI, int TK, int A, int B, bool kCta>
+__device__ __forceinline__ bool ldlt_factor_rl(double* S, double* rd, int n, int t) {
+    const int ti = t / TK, tk = t % TK;
+    auto sync = [] {
+        if (kCta) __syncthreads();
+        else __syncwarp();
+    };
+    if (t == 0) {
+        const double d = S[0];
+        rd[0] = d > 0 ? fast_rcp(d) : 0.0;
+    }
+    sync();
+    for (int j = 0; j < n; ++j) {
+        const double r = rd[j];
+        if (r == 0.0) return false;
+        const int base = j + 1;
+        double li[A], cj[B], v[A][B];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int i = base + ti + TI * a;
+            li[a] = i < n ? S[i * n + j] * r : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int k = base + tk + TK * b;
+            cj[b] = k < n ? S[k * n + j] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int i = base + ti + TI * a, k = base + tk + TK * b;
+                v[a][b] = (i < n && k <= i) ? S[i * n + k] : 0.0;
+            }
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int i = base + ti + TI * a, k = base + tk + TK * b;
+                if (i < n && k <= i) {
+                    const double u = v[a][b] - li[a] * cj[b];
+                    S[i * n + k] = u;
+                    if (a == 0 && b == 0 && t == 0) rd[base] = u > 0 ? fast_rcp(u) : 0.0;   // the next pivot
+                }
+            }
+        sync();
+        for (int q = t; q < n - base; q += TI * TK) S[(base + q) * n + j] *= r;
+    }
+    sync();
     return true;
 }
 
-// The same solve for a small system of compile-time size N (6 or 12: one or two free poses, the local BA of the tracking
-// loop) by ONE thread with everything in registers and every loop unrolled: no shared-memory round trips, no shuffles, the
-// reciprocal of a pivot overlaps the dot products of the next column (the warp version spends ~1000 cycles per column on
-// dependent shared-memory / shuffle latency).
-template <int N>
-__device__ __noinline__ bool thread_ldlt_solve(const double* __restrict__ S, double* __restrict__ b) {
-    double L[N][N], D[N], rD[N];
+// ---- 6 x 6 BLOCK LDL^T (right-looking).  Measured on the scalar version: a column costs ~900 cycles, of which only ~200 are
+// the six dependent FP64 operations of the pivot chain -- the rest is the barrier and the shared-memory round trip around it.
+// The dimension of the reduced system is a multiple of 6 (one block per free pose), so a pivot BLOCK is factorised by every
+// thread itself in registers (same loads, same bits everywhere: nothing to publish), the rows of the block column are pushed
+// through that factor (W = C Lb^-T = L D, L = W D^-1), the trailing triangle gets its rank-6 update, and there is ONE barrier per
+// six columns.  The arithmetic is that of the scalar LDL^T (same pivots, no explicit inverse), the storage too: unit lower
+// factor below the diagonal, D on it, rd = 1 / D -- warp_ldlt_subst applies it.  A non-positive pivot (the condition under which
+// g2o's dense Cholesky fails) returns false, uniformly.  n <= TI * A + 6.
+template <int TI, int TK, int A, int B, bool kCta>
+__device__ __forceinline__ bool ldlt6_factor(double* S, double* rd, int n, int t) {
+    const int ti = t / TK, tk = t % TK;
+    auto sync = [] {
+        if (kCta) __syncthreads();
+        else __syncwarp();
+    };
+    sync();
+    for (int J = 0; J < n; J += 6) {
+        double P[6][6], rp[6];   // pivot block: lower triangle in, unit lower factor (below the diagonal) + D (diagonal) out
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+        for (int r = 0; r < 6; ++r)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) L[i][j] = S[i * N + j];
-    bool ok = true;
+            for (int c = 0; c <= r; ++c) P[r][c] = S[(J + r) * n + J + c];
+        bool pd = true;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-        double d = L[j][j];
+        for (int p = 0; p < 6; ++p) {
+            const double d = P[p][p];
+            pd = pd && d > 0;
+            rp[p] = fast_rcp(d);
+            double u[6];   // the unscaled column below the pivot
 #pragma unroll
-        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
-        D[j] = d;
-        ok = ok && (d > 0);
-        rD[j] = fast_rcp(d);
+            for (int r = p + 1; r < 6; ++r) u[r] = P[r][p];
 #pragma unroll
-        for (int i = j + 1; i < N; ++i) {
-            double t = L[i][j];
+            for (int r = p + 1; r < 6; ++r) {
+                const double l = u[r] * rp[p];
 #pragma unroll
-            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k] * D[k];
-            L[i][j] = t * rD[j];
+                for (int c = p + 1; c <= r; ++c) P[r][c] -= l * u[c];
+                P[r][p] = l;
+            }
+        }
+        if (!pd) return false;
+        const int base = J + 6;
+        double Wr[A][6], Lc[B][6], v[A][B];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int i = base + ti + TI * a;
+            if (i < n) {
+                double X[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) X[c] = S[i * n + J + c];
+                // S_iJ = L_i D Lb^T  ->  (L_i D)_c = X_c - sum_{q<c} (L_i D)_q Lb[c][q]
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    double w = X[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) w -= Wr[a][q] * P[c][q];
+                    Wr[a][c] = w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) Wr[a][c] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int k = base + tk + TK * b;
+            if (k < n) {
+                double X[6], W[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) X[c] = S[k * n + J + c];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    double w = X[c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) w -= W[q] * P[c][q];
+                    W[c] = w;
+                    Lc[b][c] = w * rp[c];
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) Lc[b][c] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int i = base + ti + TI * a, k = base + tk + TK * b;
+                v[a][b] = (i < n && k <= i) ? S[i * n + k] : 0.0;
+            }
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int i = base + ti + TI * a, k = base + tk + TK * b;
+                if (i < n && k <= i) {
+                    const double s0 = Wr[a][0] * Lc[b][0] + Wr[a][1] * Lc[b][1] + Wr[a][2] * Lc[b][2];
+                    const double s1 = Wr[a][3] * Lc[b][3] + Wr[a][4] * Lc[b][4] + Wr[a][5] * Lc[b][5];
+                    S[i * n + k] = v[a][b] - (s0 + s1);
+                }
+            }
+        sync();
+        // the factor replaces the block column (everybody has read the unscaled values before the barrier)
+        if (tk == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const int i = base + ti + TI * a;
+                if (i < n) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) S[i * n + J + c] = Wr[a][c] * rp[c];
+                }
+            }
+        }
+        if (t == 0) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                for (int c = 0; c <= r; ++c) S[(J + r) * n + J + c] = P[r][c];
+                rd[J + r] = rp[r];
+            }
         }
     }
-    if (!ok) return false;
-    double y[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        double t = b[i];
-#pragma unroll
-        for (int k = 0; k < i; ++k) t -= L[i][k] * y[k];
-        y[i] = t;
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] *= rD[i];
-#pragma unroll
-    for (int i = N - 1; i >= 0; --i) {
-        double t = y[i];
-#pragma unroll
-        for (int k = i + 1; k < N; ++k) t -= L[k][i] * y[k];
-        y[i] = t;
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) b[i] = y[i];
+    sync();
     return true;
 }
 
@@ -309,6 +441,8 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     __shared__ double s_bc[4];                    // cluster totals of the same
     __shared__ int s_free[kBA2MaxPoses], s_kfof[kBA2MaxFree];
     __shared__ int s_np, s_ok, s_dup;
+    __shared__ int s_estart[kBA2MaxFree * (kBA2MaxFree + 1) / 2 + 1];   // entry list: first entry of every block pair
+    __shared__ int s_gstart[kBA2MaxFree * (kBA2MaxFree + 1) / 2 + kBA2MaxFree + 1];   // first 32-lane work group of every task
 
     const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
     const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -367,6 +501,8 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
         st.qa = reinterpret_cast<int32_t*>(st.uv + (size_t)2 * no);
         st.kf = reinterpret_cast<uint8_t*>(st.qa + nl + 1);
         st.slot = st.kf + ((no + 7) & ~7);
+        const size_t ent_doubles = (ba2_entry_cap((size_t)nl, (size_t)no, (size_t)np) + 1) / 2;
+        st.ent = (need + ent_doubles <= have && nl < 65536) ? reinterpret_cast<uint32_t*>(s_stage + need) : nullptr;
     }
     // slot table: which observation of a landmark sits on which free pose; landmark positions into the staging area
     for (int i = tid; i < nl * kBA2MaxFree; i += kT) st.slot[i] = 0xFF;
@@ -384,6 +520,50 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
             st.slot[jj * kBA2MaxFree + f] = (uint8_t)(q - qa);
         }
     }
+    // ---- work list of the reduced system.  With few key-frames per landmark most (landmark, block pair) combinations are empty
+    // (C4: a landmark is seen by 4 of 10 key-frames -> 16 % of the lanes of a 32-landmark chunk had work): the non-empty ones are
+    // listed once, sorted by block pair (counting sort; inside a pair ascending landmark, so the order is deterministic), and a
+    // task's work groups are 32 consecutive entries.  Without room for the list a work group is a 32-landmark chunk.
+    __syncthreads();
+    const int n_chunks = (nl + 31) / 32;
+    auto pair_index = [&](int f1, int f2) { return f1 * np - f1 * (f1 - 1) / 2 + (f2 - f1); };
+    if (st.ent) {
+        for (int t = tid; t <= n_pairs; t += kT) s_estart[t] = 0;
+        __syncthreads();
+        for (int jj = tid; jj < nl; jj += kT)
+            for (int f1 = 0; f1 < np; ++f1) {
+                if (st.slot[jj * kBA2MaxFree + f1] == 0xFF) continue;
+                for (int f2 = f1; f2 < np; ++f2)
+                    if (st.slot[jj * kBA2MaxFree + f2] != 0xFF) atomicAdd(&s_estart[pair_index(f1, f2) + 1], 1);
+            }
+        __syncthreads();
+        if (tid == 0)
+            for (int t = 0; t < n_pairs; ++t) s_estart[t + 1] += s_estart[t];
+        __syncthreads();
+        for (int f1 = 0, t = 0; f1 < np; ++f1)
+            for (int f2 = f1; f2 < np; ++f2, ++t) {
+                if (t % kW != warp) continue;
+                int pos = s_estart[t];
+                for (int base = 0; base < nl; base += 32) {
+                    const int jj = base + lane;
+                    const int s1 = jj < nl ? st.slot[jj * kBA2MaxFree + f1] : 0xFF, s2 = jj < nl ? st.slot[jj * kBA2MaxFree + f2] : 0xFF;
+                    const bool has = s1 != 0xFF && s2 != 0xFF;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, has);
+                    if (has) st.ent[pos + __popc(m & ((1u << lane) - 1u))] = (unsigned)jj | ((unsigned)s1 << 16) | ((unsigned)s2 << 24);
+                    pos += __popc(m);
+                }
+            }
+    }
+    if (tid == 0) {
+        int g = 0;
+        for (int t = 0; t < n_pairs + np; ++t) {
+            s_gstart[t] = g;
+            const int tb = t < n_pairs ? t : pair_index(t - n_pairs, t - n_pairs);
+            g += st.ent ? (s_estart[tb + 1] - s_estart[tb] + 31) / 32 : n_chunks;
+        }
+        s_gstart[n_pairs + np] = g;
+    }
+    __syncthreads();
     int cur = 0;   // index of the accepted state in the double buffers
 
     auto robust = [&](double e2, double* w) {   // RobustKernelHuber (delta in pixels, BA.cpp:450-452)
@@ -465,14 +645,13 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
     // pose t - n_pairs.  The (task, 32-landmark chunk) items of [t_lo, t_hi) are dealt to the warps in contiguous runs, a
     // warp keeps its sums in registers while the task stays the same and leaves them in slot (task + warp).
     auto accumulate = [&](int t_lo, int t_hi, double lambda) {
-        const int n_chunks = (nl + 31) / 32;
-        const int items = (t_hi - t_lo) * n_chunks, per = (items + kW - 1) / kW;
+        const int g0 = s_gstart[t_lo], items = s_gstart[t_hi] - g0, per = (items + kW - 1) / kW;
         const double* lin = st.lin[cur];
-        int it = warp * per;
-        const int end = min(items, it + per);
+        int it = g0 + warp * per, task = t_lo;
+        const int end = min(g0 + items, it + per);
         while (it < end) {
-            const int trel = it / n_chunks, task = t_lo + trel;
-            const int c_lo = it - trel * n_chunks, c_hi = min(n_chunks, c_lo + (end - it));
+            while (s_gstart[task + 1] <= it) ++task;   // tasks without work groups are skipped (their slots are never read)
+            const int c_lo = it - s_gstart[task], c_hi = min(s_gstart[task + 1], end) - s_gstart[task];
             double* out = s_part + (size_t)(task + warp) * kPairW;
             if (task < n_pairs) {
                 int f1 = 0, rem = task;
@@ -483,16 +662,28 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                 const int f2 = f1 + rem;
                 const double* R1 = s_Rlin[s_kfof[f1]];
                 const double* R2 = s_Rlin[s_kfof[f2]];
-                double accS[36], accb[6];
+                const int e_lo = st.ent ? s_estart[task] : 0, e_hi = st.ent ? s_estart[task + 1] : 0;
+                double acc[48];   // [0, 36) the 6 x 6 block, [36, 42) the right-hand side (diagonal pairs), the rest stays zero
+                double* accS = acc;
+                double* accb = acc + 36;
 #pragma unroll
-                for (int t = 0; t < 36; ++t) accS[t] = 0;
-#pragma unroll
-                for (int t = 0; t < 6; ++t) accb[t] = 0;
+                for (int t = 0; t < 48; ++t) acc[t] = 0;
                 for (int ch = c_lo; ch < c_hi; ++ch) {
-                    const int jj = ch * 32 + lane;
-                    if (jj >= nl) continue;
-                    const int s1 = st.slot[jj * kBA2MaxFree + f1], s2 = st.slot[jj * kBA2MaxFree + f2];
-                    if (s1 == 0xFF || s2 == 0xFF) continue;
+                    int jj, s1, s2;
+                    if (st.ent) {
+                        const int idx = e_lo + ch * 32 + lane;
+                        if (idx >= e_hi) continue;
+                        const unsigned e = st.ent[idx];
+                        jj = (int)(e & 0xFFFFu);
+                        s1 = (int)((e >> 16) & 0xFFu);
+                        s2 = (int)(e >> 24);
+                    } else {
+                        jj = ch * 32 + lane;
+                        if (jj >= nl) continue;
+                        s1 = st.slot[jj * kBA2MaxFree + f1];
+                        s2 = st.slot[jj * kBA2MaxFree + f2];
+                        if (s1 == 0xFF || s2 == 0xFF) continue;
+                    }
                     const int qa = st.qa[jj];
                     const double* Di = st.Dinv + 6 * jj;
                     double H1[6][3], BD[6][3];
@@ -516,28 +707,33 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                             for (int c = 0; c < 6; ++c) accS[r * 6 + c] += BD[r][0] * H2[c][0] + BD[r][1] * H2[c][1] + BD[r][2] * H2[c][2];
                     }
                 }
-#pragma unroll
-                for (int t = 0; t < 36; ++t) {
-                    const double v = warp_sum(accS[t]);
-                    if (lane == 0) out[t] = v;
-                }
-#pragma unroll
-                for (int t = 0; t < 6; ++t) {
-                    const double v = warp_sum(accb[t]);
-                    if (lane == 0) out[36 + t] = v;
+                {
+                    const double lo = warp_reduce_scatter<32>(acc, lane), hi = warp_reduce_scatter<16>(acc + 32, lane);
+                    out[lane] = lo;
+                    if (!(lane & 1) && 32 + (lane >> 1) < kPairW) out[32 + (lane >> 1)] = hi;
                 }
             } else {
-                const int f = task - n_pairs;
-                double h[21], g[6];
+                const int f = task - n_pairs, td = pair_index(f, f);
+                const int e_lo = st.ent ? s_estart[td] : 0, e_hi = st.ent ? s_estart[td + 1] : 0;
+                double acc[32];   // [0, 21) upper triangle of Hpp, [21, 27) bp
+                double* h = acc;
+                double* g = acc + 21;
 #pragma unroll
-                for (int t = 0; t < 21; ++t) h[t] = 0;
-#pragma unroll
-                for (int t = 0; t < 6; ++t) g[t] = 0;
+                for (int t = 0; t < 32; ++t) acc[t] = 0;
                 for (int ch = c_lo; ch < c_hi; ++ch) {
-                    const int jj = ch * 32 + lane;
-                    if (jj >= nl) continue;
-                    const int s1 = st.slot[jj * kBA2MaxFree + f];
-                    if (s1 == 0xFF) continue;
+                    int jj, s1;
+                    if (st.ent) {
+                        const int idx = e_lo + ch * 32 + lane;
+                        if (idx >= e_hi) continue;
+                        const unsigned e = st.ent[idx];
+                        jj = (int)(e & 0xFFFFu);
+                        s1 = (int)((e >> 16) & 0xFFu);
+                    } else {
+                        jj = ch * 32 + lane;
+                        if (jj >= nl) continue;
+                        s1 = st.slot[jj * kBA2MaxFree + f];
+                        if (s1 == 0xFF) continue;
+                    }
                     const double* rec = lin + 6 * (size_t)(st.qa[jj] + s1);
                     double q0[6], q1[6];
                     pose_jac(rec[0], rec[1], rec[2], fx, fy, q0, q1);
@@ -550,15 +746,9 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
                         g[r] += -w * (q0[r] * rec[3] + q1[r] * rec[4]);
                     }
                 }
-#pragma unroll
-                for (int t = 0; t < 21; ++t) {
-                    const double v = warp_sum(h[t]);
-                    if (lane == 0) out[t] = v;
-                }
-#pragma unroll
-                for (int t = 0; t < 6; ++t) {
-                    const double v = warp_sum(g[t]);
-                    if (lane == 0) out[21 + t] = v;
+                {
+                    const double tot = warp_reduce_scatter<32>(acc, lane);
+                    if (lane < kPoseW) out[lane] = tot;
                 }
             }
             it += c_hi - c_lo;
@@ -566,15 +756,16 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
         __syncthreads();
         // slots -> CTA partial vector: the warps that worked on a task are a contiguous range, added in warp order
         for (int i = tid; i < (t_hi - t_lo) * kPairW; i += kT) {
-            const int trel = i / kPairW, e = i - trel * kPairW, task = t_lo + trel;
-            const bool pose = task >= n_pairs;
+            const int trel = i / kPairW, e = i - trel * kPairW, tk = t_lo + trel;
+            const bool pose = tk >= n_pairs;
             if (pose && e >= kPoseW) continue;
             double v = 0;
-            if (per > 0) {
-                const int w_lo = (trel * n_chunks) / per, w_hi = min(kW - 1, ((trel + 1) * n_chunks - 1) / per);
-                for (int w = w_lo; w <= w_hi && n_chunks > 0; ++w) v += s_part[(size_t)(task + w) * kPairW + e];
+            const int ga = s_gstart[tk] - g0, gb = s_gstart[tk + 1] - g0;
+            if (per > 0 && gb > ga) {
+                const int w_lo = ga / per, w_hi = min(kW - 1, (gb - 1) / per);
+                for (int w = w_lo; w <= w_hi; ++w) v += s_part[(size_t)(tk + w) * kPairW + e];
             }
-            s_x[pose ? poseBase + (task - n_pairs) * kPoseW + e : task * kPairW + e] = v;
+            s_x[pose ? poseBase + (tk - n_pairs) * kPoseW + e : tk * kPairW + e] = v;
         }
         __syncthreads();
     };
@@ -623,7 +814,7 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
         int qmax = 0;
         do {
             // ---- reduced system of the accepted state at the current lambda: (Hll + lambda I)^-1 is rebuilt per use
-            tick(7);
+            tick(6);
             for (int jj = tid; jj < nl; jj += kT) sym_inverse3(st.Hll[cur] + 6 * jj, lambda, st.Dinv + 6 * jj);
             __syncthreads();
             accumulate(0, fresh ? n_pairs + np : n_pairs, lambda);
@@ -649,22 +840,43 @@ __global__ void __launch_bounds__(kT) local_ba2_kernel(const BA2Args a) {
             }
             __syncthreads();
             tick(2);
-            // ---- warp 0: dense Cholesky + triangular solves, then VertexSE3Sophus::oplusImpl for the trial poses
-            if (warp == 0) {
-                bool ok = true;
-                if (false && (dimp == 12 || dimp == 6)) {   // register-resident solve by one lane: measured SLOWER (23.9k vs 12.2k cycles
-                    // per trial at 12x12): a dependent FP64 operation costs ~40 cycles here, the warp version has shorter chains
-                    if (lane == 0) {
-                        ok = dimp == 12 ? thread_ldlt_solve<12>(s_S, s_bs) : thread_ldlt_solve<6>(s_S, s_bs);
-                        s_ok = ok ? 1 : 0;
-                    }
-                    __syncwarp();
-                    ok = s_ok != 0;
-                } else {
-                    ok = dimp == 0 || warp_ldlt_solve(s_S, s_bs, s_rd, dimp, lane);
+            // ---- dense LDL^T + triangular solves (small systems: warp 0 alone; larger ones: factorisation by the whole CTA),
+            // then VertexSE3Sophus::oplusImpl for the trial poses
+            if (a.solver == 0 && dimp > kCtaSolveMinDim) {
+                // (more than 11 free poses: the scalar version; its 6 x 6 tile per thread would not fit the registers in block form)
+                const bool ok = dimp <= 70 ? ldlt6_factor<16, 16, 4, 4, true>(s_S, s_rd, dimp, tid)
+                                           : ldlt_factor_rl<16, 16, 6, 6, true>(s_S, s_rd, dimp, tid);
+                tick(7);
+                if (warp == 0) {
+                    if (ok) warp_ldlt_subst(s_S, s_bs, s_rd, dimp, lane);
                     if (lane == 0) s_ok = ok ? 1 : 0;
+                    for (int i = lane; i < dimp; i += 32) s_xp[i] = ok ? s_bs[i] : 0.0;
                 }
+            } else if (a.solver == 0 && warp == 0 && dimp > 0) {
+                const bool ok = ldlt6_factor<4, 8, 5, 3, false>(s_S, s_rd, dimp, lane);
+                tick(7);
+                if (ok) warp_ldlt_subst(s_S, s_bs, s_rd, dimp, lane);
+                if (lane == 0) s_ok = ok ? 1 : 0;
                 for (int i = lane; i < dimp; i += 32) s_xp[i] = ok ? s_bs[i] : 0.0;
+            } else if (a.solver == 0) {
+                if (warp == 0 && lane == 0) s_ok = 1;   // no free pose: nothing to solve
+            } else if (dimp > kCtaSolveMinDim) {
+                const bool ok = dimp <= 64 ? ldlt_factor_rl<16, 16, 4, 4, true>(s_S, s_rd, dimp, tid)
+                                           : ldlt_factor_rl<16, 16, 6, 6, true>(s_S, s_rd, dimp, tid);
+                tick(7);
+                if (warp == 0) {
+                    if (ok) warp_ldlt_subst(s_S, s_bs, s_rd, dimp, lane);
+                    if (lane == 0) s_ok = ok ? 1 : 0;
+                    for (int i = lane; i < dimp; i += 32) s_xp[i] = ok ? s_bs[i] : 0.0;
+                }
+            } else if (warp == 0 && dimp > 0) {
+                const bool ok = ldlt_factor_rl<4, 8, 6, 3, false>(s_S, s_rd, dimp, lane);
+                tick(7);
+                if (ok) warp_ldlt_subst(s_S, s_bs, s_rd, dimp, lane);
+                if (lane == 0) s_ok = ok ? 1 : 0;
+                for (int i = lane; i < dimp; i += 32) s_xp[i] = ok ? s_bs[i] : 0.0;
+            } else if (warp == 0) {   // no free pose: nothing to solve
+                if (lane == 0) s_ok = 1;
             }
             __syncthreads();
             const bool ok2 = s_ok != 0;
@@ -891,6 +1103,10 @@ int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const y
     a.outlier = c.take<uint8_t>(NO);
     a.stats = c.take<double>(8 * P);
     a.debug = getenv("YGZB_BA_DEBUG") ? c.take<double>(8 * P) : nullptr;
+    {
+        const char* e = getenv("YGZB_BA_SOLVER");
+        a.solver = e && atoi(e) == 1 ? 1 : 0;
+    }
     if (in.lm_start) {   // the caller already has landmark-major lists (the tracking engine builds them itself)
         a.lm_start = in.lm_start; a.so_kf = in.kf_idx; a.so_uv = in.obs; a.so_orig = nullptr;
     } else {
@@ -935,7 +1151,7 @@ int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const y
     const size_t sys = std::max<size_t>((size_t)dimp * dimp + dimp, (size_t)(n_pairs + np + kW) * kPairW);
     const size_t nl = (in.max_pts + cluster - 1) / cluster;
     const size_t no = std::min<size_t>(in.max_obs, nl * (size_t)std::max(in.max_kf, 1));
-    const size_t stage = ba2_stage_doubles(nl, no) + 2;
+    const size_t stage = ba2_stage_doubles(nl, no) + 2 + (ba2_entry_cap(nl, no, (size_t)np) + 1) / 2;   // + the block-pair entry list
     static int max_optin = 0;
     static std::once_flag once;
     std::call_once(once, [&] {
@@ -972,8 +1188,8 @@ int launch_local_ba2(ygzb_ctx* ctx, const BA2Problem& in, void* scratch, const y
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(h, a.debug, sizeof(double) * 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(hs, a.stats, sizeof(double) * 8, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[ba2] P=%zu cluster=%d iters=%.0f trials=%.0f cycles/trial: accumulate %.0f exchange %.0f assemble %.0f solve %.0f "
-                        "pose+backsubst %.0f linearise %.0f reduce+exchange %.0f decide %.0f\n",
+        fprintf(stderr, "[ba2] P=%zu cluster=%d iters=%.0f trials=%.0f cycles/trial: accumulate %.0f exchange %.0f assemble %.0f substitution %.0f "
+                        "pose+backsubst %.0f linearise %.0f reduce+exchange+decide %.0f factorisation %.0f\n",
                 P, cluster, hs[0], hs[1], h[0] / hs[1], h[1] / hs[1], h[2] / hs[1], h[3] / hs[1], h[4] / hs[1], h[5] / hs[1], h[6] / hs[1],
                 h[7] / hs[1]);
     }

@@ -32,6 +32,7 @@ struct BA2Args {
     uint8_t* outlier;          // [n_obs]
     double* stats;             // [n_problems][8]: iters, trials, chi2 first, chi2 last, lambda, outliers, duplicate flag, 0
     double* debug;             // optional [n_problems][8]: cycles per phase (YGZB_BA_DEBUG)
+    int solver;                // 0 = 6 x 6 block LDL^T (default), 1 = scalar LDL^T (YGZB_BA_SOLVER=1, kept for comparison)
     long long dyn_doubles;     // dynamic shared memory of the launch, in doubles
     float fx, fy, cx, cy;
     int max_iters, max_trials;
