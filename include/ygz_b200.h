@@ -195,6 +195,21 @@ int ygzb_search_by_bow(ygzb_ctx* ctx, int n_pairs, const int32_t* off1, const in
                        const int32_t* node1, const float* angle1, const uint8_t* desc2, const int32_t* node2, const float* angle2,
                        int th_low, float knn_ratio, int check_orientation, int32_t* match12, int32_t* count);
 
+/* ---- Initializer: the RANSAC half of the monocular initialisation -----------------------------
+ * replaces Initializer::FindHomography + FindFundamental (src/Algorithm/Initializer.cpp:89-138, 670-717; with Normalize
+ * :140-175, ComputeH21 :196-239, CheckHomography :251-318, ComputeF21 :730-762, CheckFundamental :772-853) as called from
+ * Initializer::TryInitialize (:52-60) for n_lists pairs of matched pixel lists: list l owns point pairs
+ * [offsets[l], offsets[l+1]) of px1 / px2 (x, y doubles; at least 8).  sets = n_lists x max_iter x 8 indices into the list:
+ * the minimal sets TryInitialize draws with cv::RNG (:25-49; ygz::Initializer in the shim restates the generator).
+ * sigma = Options::_sigma (2.0), max_iter = Options::_max_iter (200).  Per list: H21 / F21 (9 doubles, row major) = the
+ * model of the best-scoring iteration, score_* = the float scores sh / sf of TryInitialize (:66), best_* = that iteration
+ * or -1 when no model scored above 0 (the reference then leaves the matrix untouched; here it is zero), inlier_* = the
+ * flags of the best model.  all_models (may be NULL) = n_lists x max_iter x 18 doubles, every iteration's H21i then F21i.
+ * Every hypothesis is evaluated in parallel; scores are the reference's sequential float sums (same order of additions). */
+int ygzb_initializer_ransac(ygzb_ctx* ctx, int n_lists, const int32_t* offsets, const double* px1, const double* px2, int max_iter,
+                            const int32_t* sets, float sigma, double* H21, float* score_H, int32_t* best_H, uint8_t* inlier_H,
+                            double* F21, float* score_F, int32_t* best_F, uint8_t* inlier_F, double* all_models);
+
 /* ---- cvutils / Matcher: direct (photometric) alignment ---------------------------------------
  * replaces cvutils::Align2D (src/Algorithm/CVUtils.cpp:186-318; include/ygz/Algorithm/CVUtils.h:163-169):
  * inverse-compositional alignment of an 8x8 template.  Patch i is searched on pyramid level level[i] of

@@ -1,0 +1,288 @@
+// oracle/initializer.cpp -- CPU restatement of the RANSAC half of the monocular initialiser (TEST INFRASTRUCTURE ONLY, see
+// oracle.h):
+//   Initializer::TryInitialize, RANSAC sets   reference src/Algorithm/Initializer.cpp:9-87   (cv::RNG minimal sets :33-49, model choice :66-78)
+//   Initializer::FindHomography                reference src/Algorithm/Initializer.cpp:89-138
+//   Initializer::Normalize                     reference src/Algorithm/Initializer.cpp:140-175
+//   Initializer::ComputeH21                    reference src/Algorithm/Initializer.cpp:196-239
+//   Initializer::CheckHomography               reference src/Algorithm/Initializer.cpp:251-318
+//   Initializer::FindFundamental               reference src/Algorithm/Initializer.cpp:670-717
+//   Initializer::ComputeF21                    reference src/Algorithm/Initializer.cpp:730-762
+//   Initializer::CheckFundamental              reference src/Algorithm/Initializer.cpp:772-853
+// Third-party arithmetic that is not in the reference tree, restated:
+//   * cv::RNG (OpenCV core/operations.hpp): multiply-with-carry, state = (uint64)(unsigned)state * 4164903690 + (state >> 32),
+//     default state 0xffffffff, uniform(a, b) = a + next() % (b - a).  Not reachable through cv2's Python API: unpinned.
+//   * Eigen::JacobiSVD (ComputeH21 / ComputeF21 take the right singular vector of the smallest singular value; ComputeF21 zeroes
+//     the smallest singular value of the 3 x 3 matrix): restated as a one-sided (Hestenes) Jacobi SVD -- same singular
+//     subspaces to rounding.  A singular vector is defined up to sign; H and F are homogeneous and every use below is
+//     sign-invariant.  The null vector is canonicalised to a non-negative largest-magnitude component.
+//   * Eigen 3 x 3 inverse: cofactors / determinant.
+// Reference defects kept or resolved: Normalize() accumulates into uninitialised `Vector2d mean, meanDev` (:146, :153) --
+// zero-initialised here; CheckHomography scores only the transfer of image 2 into image 1 (:284-303) -- kept; a RANSAC run
+// whose best score stays 0 leaves H21 / F21 untouched in the reference -- reported as best = -1 and a zero matrix here.
+// The CUDA path (ygz_slam_b200/csrc/initializer.cu) performs the same operations in the same order without FMA contraction,
+// so the comparison in tests/test_initializer.py is bit for bit.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "oracle.h"
+
+namespace {
+
+// one-sided Jacobi SVD of the M x N matrix a (row major, overwritten: columns become U * sigma); v = N x N right vectors
+template <int M, int N>
+void jacobi_svd(double* a, double* v) {
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) v[i * N + j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int r = 0; r < M; ++r) {
+                    const double x = a[r * N + p], y = a[r * N + q];
+                    alpha += x * x;
+                    beta += y * y;
+                    gamma += x * y;
+                }
+                if (gamma == 0.0 || std::fabs(gamma) <= 1e-15 * std::sqrt(alpha * beta)) continue;
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+                for (int r = 0; r < M; ++r) {
+                    const double x = a[r * N + p], y = a[r * N + q];
+                    a[r * N + p] = c * x - s * y;
+                    a[r * N + q] = s * x + c * y;
+                }
+                for (int r = 0; r < N; ++r) {
+                    const double x = v[r * N + p], y = v[r * N + q];
+                    v[r * N + p] = c * x - s * y;
+                    v[r * N + q] = s * x + c * y;
+                }
+            }
+        if (!rotated) break;
+    }
+}
+
+template <int M, int N>
+int smallest_column(const double* a, double* norms2) {
+    int best = 0;
+    for (int c = 0; c < N; ++c) {
+        double n2 = 0;
+        for (int r = 0; r < M; ++r) n2 += a[r * N + c] * a[r * N + c];
+        norms2[c] = n2;
+        if (n2 < norms2[best]) best = c;
+    }
+    return best;
+}
+
+// right singular vector of the smallest singular value, largest-magnitude component made non-negative
+template <int M>
+void null_vector(double* a, double* out9) {
+    double v[81], n2[9];
+    jacobi_svd<M, 9>(a, v);
+    const int c = smallest_column<M, 9>(a, n2);
+    int big = 0;
+    for (int r = 1; r < 9; ++r)
+        if (std::fabs(v[r * 9 + c]) > std::fabs(v[big * 9 + c])) big = r;
+    const double sg = v[big * 9 + c] < 0 ? -1.0 : 1.0;
+    for (int r = 0; r < 9; ++r) out9[r] = sg * v[r * 9 + c];
+}
+
+void mul3(const double* A, const double* B, double* C) {
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+}
+
+void inverse3(const double* m, double* inv) {
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const double id = 1.0 / det;
+    inv[0] = c00 * id;
+    inv[1] = (m[2] * m[7] - m[1] * m[8]) * id;
+    inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    inv[3] = c01 * id;
+    inv[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+    inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    inv[6] = c02 * id;
+    inv[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+    inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+}
+
+// Initializer::Normalize (:140-175); T row major
+void normalize(int n, const double* px, std::vector<double>& pn, double* T) {
+    double mean[2] = {0, 0}, dev[2] = {0, 0};
+    for (int i = 0; i < n; ++i) {
+        mean[0] += px[2 * i];
+        mean[1] += px[2 * i + 1];
+    }
+    mean[0] = mean[0] / n;
+    mean[1] = mean[1] / n;
+    pn.resize(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        pn[2 * i] = px[2 * i] - mean[0];
+        pn[2 * i + 1] = px[2 * i + 1] - mean[1];
+        dev[0] += std::fabs(pn[2 * i]);
+        dev[1] += std::fabs(pn[2 * i + 1]);
+    }
+    dev[0] /= n;
+    dev[1] /= n;
+    const float sX = (float)(1.0 / dev[0]), sY = (float)(1.0 / dev[1]);
+    for (int i = 0; i < n; ++i) {
+        pn[2 * i] *= sX;
+        pn[2 * i + 1] *= sY;
+    }
+    const double t[9] = {sX, 0, -mean[0] * sX, 0, sY, -mean[1] * sY, 0, 0, 1};
+    std::memcpy(T, t, sizeof t);
+}
+
+// CheckHomography (:251-318): score, optionally the inlier flags
+float check_homography(int n, const double* px1, const double* px2, const double* H12, float sigma, uint8_t* inl) {
+    float score = 0;
+    const float th = 5.991f;
+    const float invSigmaSquare = (float)(1.0 / (sigma * sigma));
+    for (int i = 0; i < n; ++i) {
+        const double u1 = px1[2 * i], v1 = px1[2 * i + 1], u2 = px2[2 * i], v2 = px2[2 * i + 1];
+        const float w2in1inv = (float)(1.0 / (H12[6] * u2 + H12[7] * v2 + H12[8]));
+        const float u2in1 = (float)((H12[0] * u2 + H12[1] * v2 + H12[2]) * w2in1inv);
+        const float v2in1 = (float)((H12[3] * u2 + H12[4] * v2 + H12[5]) * w2in1inv);
+        const float squareDist1 = (float)((u1 - u2in1) * (u1 - u2in1) + (v1 - v2in1) * (v1 - v2in1));
+        const float chiSquare1 = squareDist1 * invSigmaSquare;
+        const bool in = !(chiSquare1 > th);
+        if (in) score += th - chiSquare1;
+        if (inl) inl[i] = in ? 1 : 0;
+    }
+    return score;
+}
+
+// CheckFundamental (:772-853)
+float check_fundamental(int n, const double* px1, const double* px2, const double* F21, float sigma, uint8_t* inl) {
+    const float f11 = (float)F21[0], f12 = (float)F21[1], f13 = (float)F21[2], f21 = (float)F21[3], f22 = (float)F21[4], f23 = (float)F21[5],
+                f31 = (float)F21[6], f32 = (float)F21[7], f33 = (float)F21[8];
+    float score = 0;
+    const float th = 3.841f, thScore = 5.991f;
+    const float invSigmaSquare = (float)(1.0 / (sigma * sigma));
+    for (int i = 0; i < n; ++i) {
+        bool bIn = true;
+        const float u1 = (float)px1[2 * i], v1 = (float)px1[2 * i + 1], u2 = (float)px2[2 * i], v2 = (float)px2[2 * i + 1];
+        const float a2 = f11 * u1 + f12 * v1 + f13, b2 = f21 * u1 + f22 * v1 + f23, c2 = f31 * u1 + f32 * v1 + f33;
+        const float num2 = a2 * u2 + b2 * v2 + c2;
+        const float squareDist1 = num2 * num2 / (a2 * a2 + b2 * b2);
+        const float chiSquare1 = squareDist1 * invSigmaSquare;
+        if (chiSquare1 > th) bIn = false;
+        else score += thScore - chiSquare1;
+        const float a1 = f11 * u2 + f21 * v2 + f31, b1 = f12 * u2 + f22 * v2 + f32, c1 = f13 * u2 + f23 * v2 + f33;
+        const float num1 = a1 * u1 + b1 * v1 + c1;
+        const float squareDist2 = num1 * num1 / (a1 * a1 + b1 * b1);
+        const float chiSquare2 = squareDist2 * invSigmaSquare;
+        if (chiSquare2 > th) bIn = false;
+        else score += thScore - chiSquare2;
+        if (inl) inl[i] = bIn ? 1 : 0;
+    }
+    return score;
+}
+
+}  // namespace
+
+// the RANSAC minimal sets of TryInitialize (:25-49): sets[it * 8 + j]; a fresh cv::RNG per call, like the reference
+extern "C" void ora_initializer_sets(int n_points, int max_iter, int32_t* sets) {
+    uint64_t state = 0xffffffffULL;
+    auto next = [&]() {
+        state = (uint64_t)(uint32_t)state * 4164903690ULL + (uint32_t)(state >> 32);
+        return (uint32_t)state;
+    };
+    std::vector<int32_t> avail;
+    for (int it = 0; it < max_iter; ++it) {
+        avail.resize(n_points);
+        for (int i = 0; i < n_points; ++i) avail[i] = i;
+        for (int j = 0; j < 8; ++j) {
+            const int b = (int)avail.size();
+            const int r = b == 0 ? 0 : (int)(next() % (uint32_t)b);
+            sets[it * 8 + j] = avail[r];
+            avail[r] = avail.back();
+            avail.pop_back();
+        }
+    }
+}
+
+// FindHomography + FindFundamental for one pair of point lists (n >= 8).  H21 / F21: 9 doubles row major, score_*: the
+// float scores (sh, sf of TryInitialize), best_*: the winning iteration or -1, inl_*: n flags, models (may be NULL):
+// max_iter x 18 doubles, every iteration's H21i then F21i (for the tests)
+extern "C" void ora_initializer_ransac(int n, const double* px1, const double* px2, int max_iter, const int32_t* sets, float sigma, double* H21,
+                                       float* score_H, int32_t* best_H, uint8_t* inl_H, double* F21, float* score_F, int32_t* best_F,
+                                       uint8_t* inl_F, double* models) {
+    std::vector<double> pn1, pn2;
+    double T1[9], T2[9], T2inv[9], T2t[9];
+    normalize(n, px1, pn1, T1);
+    normalize(n, px2, pn2, T2);
+    inverse3(T2, T2inv);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) T2t[r * 3 + c] = T2[c * 3 + r];
+    *score_H = 0;
+    *score_F = 0;
+    *best_H = -1;
+    *best_F = -1;
+    std::memset(H21, 0, 72);
+    std::memset(F21, 0, 72);
+    std::memset(inl_H, 0, n);
+    std::memset(inl_F, 0, n);
+    for (int it = 0; it < max_iter; ++it) {
+        // ---- homography: ComputeH21 (:196-239)
+        double A[16 * 9];
+        for (int j = 0; j < 8; ++j) {
+            const int idx = sets[it * 8 + j];
+            const double u1 = pn1[2 * idx], v1 = pn1[2 * idx + 1], u2 = pn2[2 * idx], v2 = pn2[2 * idx + 1];
+            double* r0 = A + (2 * j) * 9;
+            double* r1 = r0 + 9;
+            r0[0] = 0.0; r0[1] = 0.0; r0[2] = 0.0; r0[3] = -u1; r0[4] = -v1; r0[5] = -1; r0[6] = v2 * u1; r0[7] = v2 * v1; r0[8] = v2;
+            r1[0] = u1; r1[1] = v1; r1[2] = 1; r1[3] = 0.0; r1[4] = 0.0; r1[5] = 0.0; r1[6] = -u2 * u1; r1[7] = -u2 * v1; r1[8] = -u2;
+        }
+        double Hn[9], tmp[9], H21i[9], H12i[9];
+        null_vector<16>(A, Hn);
+        mul3(T2inv, Hn, tmp);
+        mul3(tmp, T1, H21i);
+        inverse3(H21i, H12i);
+        const float sh = check_homography(n, px1, px2, H12i, sigma, nullptr);
+        if (sh > *score_H) {
+            *score_H = sh;
+            *best_H = it;
+            std::memcpy(H21, H21i, 72);
+        }
+        // ---- fundamental matrix: ComputeF21 (:730-762)
+        double B[8 * 9];
+        for (int j = 0; j < 8; ++j) {
+            const int idx = sets[it * 8 + j];
+            const double u1 = pn1[2 * idx], v1 = pn1[2 * idx + 1], u2 = pn2[2 * idx], v2 = pn2[2 * idx + 1];
+            double* r = B + j * 9;
+            r[0] = u2 * u1; r[1] = u2 * v1; r[2] = u2; r[3] = v2 * u1; r[4] = v2 * v1; r[5] = v2; r[6] = u1; r[7] = v1; r[8] = 1;
+        }
+        double Fpre[9], Fa[9], Fv[9], n2[3], Fn[9], F21i[9];
+        null_vector<8>(B, Fpre);
+        std::memcpy(Fa, Fpre, 72);
+        jacobi_svd<3, 3>(Fa, Fv);
+        const int cz = smallest_column<3, 3>(Fa, n2);
+        // U diag(s0, s1, 0) V^T = Fpre - (column cz of U sigma) (column cz of V)^T
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Fn[r * 3 + c] = Fpre[r * 3 + c] - Fa[r * 3 + cz] * Fv[c * 3 + cz];
+        mul3(T2t, Fn, tmp);
+        mul3(tmp, T1, F21i);
+        const float sf = check_fundamental(n, px1, px2, F21i, sigma, nullptr);
+        if (sf > *score_F) {
+            *score_F = sf;
+            *best_F = it;
+            std::memcpy(F21, F21i, 72);
+        }
+        if (models) {
+            std::memcpy(models + 18 * (size_t)it, H21i, 72);
+            std::memcpy(models + 18 * (size_t)it + 9, F21i, 72);
+        }
+    }
+    if (*best_H >= 0) {
+        double H12[9];
+        inverse3(H21, H12);
+        check_homography(n, px1, px2, H12, sigma, inl_H);
+    }
+    if (*best_F >= 0) check_fundamental(n, px1, px2, F21, sigma, inl_F);
+}

@@ -112,6 +112,15 @@ int ora_bow_transform(const ora_vocab* v, int n, const uint8_t* desc, int levels
 int ora_search_by_bow(int n1, const uint8_t* desc1, const int32_t* node1, const float* angle1, int n2, const uint8_t* desc2,
                       const int32_t* node2, const float* angle2, int th_low, float knn_ratio, int check_orientation, int32_t* match12);
 
+/* ---- monocular initialiser, RANSAC half (src/Algorithm/Initializer.cpp:9-318, 670-853; initializer.cpp) ----------------- */
+/* the 8-point minimal sets TryInitialize draws from a default-constructed cv::RNG (:25-49): sets[it * 8 + j] */
+void ora_initializer_sets(int n_points, int max_iter, int32_t* sets);
+/* FindHomography + FindFundamental: best model, float score, winning iteration (-1: no model scored above 0) and inlier
+ * flags of each; models (may be NULL) = max_iter x 18 doubles, every iteration's H21i then F21i */
+void ora_initializer_ransac(int n, const double* px1, const double* px2, int max_iter, const int32_t* sets, float sigma, double* H21,
+                            float* score_H, int32_t* best_H, uint8_t* inl_H, double* F21, float* score_F, int32_t* best_F, uint8_t* inl_F,
+                            double* models);
+
 /* ---- patch alignment (src/Algorithm/CVUtils.cpp:186-318; Matcher.cpp:356-466) ----------- */
 int ora_align2d(const uint8_t* img, int w, int h, const uint8_t* ref_with_border /*100*/,
                 const uint8_t* ref /*64*/, int n_iter, double* u, double* v);

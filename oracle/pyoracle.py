@@ -346,6 +346,31 @@ class Oracle:
                                          int(th_low), float(knn_ratio), int(check_orientation), _p(out))
         return out, cnt
 
+    # ---- Initializer RANSAC (initializer.cpp) ----------------------------------------------------
+    def initializer_sets(self, n_points, max_iter=200):
+        sets = np.zeros((max_iter, 8), np.int32)
+        self.lib.ora_initializer_sets(int(n_points), int(max_iter), _p(sets))
+        return sets
+
+    def initializer_ransac(self, px1, px2, sets, sigma=2.0, models=False):
+        px1 = np.ascontiguousarray(px1, np.float64).reshape(-1, 2)
+        px2 = np.ascontiguousarray(px2, np.float64).reshape(-1, 2)
+        sets = np.ascontiguousarray(sets, np.int32).reshape(-1, 8)
+        n, iters = len(px1), len(sets)
+        H, F = np.zeros(9), np.zeros(9)
+        sh, sf = C.c_float(0), C.c_float(0)
+        bh, bf = C.c_int32(0), C.c_int32(0)
+        ih, jf = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        mod = np.zeros((iters, 18)) if models else None
+        self.lib.ora_initializer_ransac.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float] + [C.c_void_p] * 9
+        self.lib.ora_initializer_ransac(n, _p(px1), _p(px2), iters, _p(sets), C.c_float(sigma), _p(H), C.byref(sh), C.byref(bh), _p(ih), _p(F),
+                                        C.byref(sf), C.byref(bf), _p(jf), _p(mod))
+        out = dict(H21=H.reshape(3, 3), score_H=np.float32(sh.value), best_H=bh.value, inliers_H=ih.astype(bool), F21=F.reshape(3, 3),
+                   score_F=np.float32(sf.value), best_F=bf.value, inliers_F=jf.astype(bool))
+        if models:
+            out["models"] = mod
+        return out
+
     def depth_from_triangulation(self, T, f_ref, f_cur, det_th=1e-5):
         T = np.ascontiguousarray(T, np.float64).reshape(12)
         f_ref = np.ascontiguousarray(f_ref, np.float64).reshape(-1, 3)

@@ -211,5 +211,21 @@ int main(int argc, char** argv) {
                f1._bow_vec.size(), f1._feature_vec.size(), in_fv, sum1, cnt, bow_matches.size(), h);
         Frame::SetORBVocabulary(nullptr);
     }
+    {
+        // Initializer (RANSAC half) on the brute-force matches of the two frames
+        std::vector<Vector2d> q1, q2;
+        for (size_t i = 0; i < idx.size(); ++i)
+            if (idx[i] >= 0) {
+                q1.push_back(f1._features[i]->_pixel);
+                q2.push_back(f2._features[idx[i]]->_pixel);
+            }
+        Initializer init;
+        const bool use_h = init.FindModels(q1, q2);
+        int nh = 0, nf = 0;
+        for (bool v : init._inliers_H) nh += v;
+        for (bool v : init._inliers_F) nf += v;
+        printf("initializer pairs %zu use_h %d score_h %.3f score_f %.3f inl_h %d inl_f %d f22 %.9e\n", q1.size(), (int)use_h, init._score_H,
+               init._score_F, nh, nf, init._F21(2, 2));
+    }
     return 0;
 }

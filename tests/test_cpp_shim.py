@@ -85,3 +85,13 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     assert int(bl[6]) == len(set(n1[n1 >= 0])) and int(bl[8]) == int((n1 >= 0).sum())
     assert abs(float(bl[10]) - bv1.sum()) < 1e-10 and int(bl[12]) == ocnt and int(bl[14]) == int((om >= 0).sum()) and int(bl[16]) == h
     oracle.vocab_free(v)
+    # Initializer::FindModels on the same matches: scores, inlier counts and F21(2,2) are the oracle's, bit for bit
+    m1 = np.stack([f1["px"], f1["py"]], 1)[idx >= 0]
+    m2 = np.stack([f2["px"], f2["py"]], 1)[idx[idx >= 0]]
+    ro = oracle.initializer_ransac(m1, m2, oracle.initializer_sets(len(m1), 200))
+    il = lines[10].split()
+    assert il[0] == "initializer" and int(il[2]) == len(m1)
+    assert il[6] == "%.3f" % ro["score_H"] and il[8] == "%.3f" % ro["score_F"]
+    assert int(il[10]) == int(ro["inliers_H"].sum()) and int(il[12]) == int(ro["inliers_F"].sum())
+    assert il[14] == "%.9e" % ro["F21"][2, 2]
+    assert int(il[4]) == int(ro["score_H"] / (ro["score_H"] + ro["score_F"]) > 0.4)

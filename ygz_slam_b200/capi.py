@@ -38,7 +38,7 @@ EXPORTS = [
     "ygzb_frames_upload", "ygzb_frames_copy", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
     "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_search_for_triangulation", "ygzb_depth_from_triangulation",
-    "ygzb_vocab_create", "ygzb_vocab_destroy", "ygzb_vocab_info", "ygzb_bow_transform", "ygzb_search_by_bow", "ygzb_align2d", "ygzb_align1d",
+    "ygzb_vocab_create", "ygzb_vocab_destroy", "ygzb_vocab_info", "ygzb_bow_transform", "ygzb_search_by_bow", "ygzb_initializer_ransac", "ygzb_align2d", "ygzb_align1d",
     "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_two_view_ba", "ygzb_pose_only",
     "ygzb_default_klt_params", "ygzb_klt",
     "ygzb_tracker_create", "ygzb_tracker_destroy", "ygzb_tracker_set_depth", "ygzb_tracker_upload", "ygzb_tracker_track", "ygzb_tracker_make_keyframes",
@@ -589,6 +589,29 @@ def _search_by_bow(self, off1, off2, desc1, node1, angle1, desc2, node2, angle2,
     return out, cnt
 
 
+def _initializer_ransac(self, offsets, px1, px2, sets, sigma=2.0, models=False):
+    """Batched Initializer::FindHomography + FindFundamental; sets: [n_lists][max_iter][8] indices local to each list."""
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    P, N = len(offsets) - 1, int(offsets[-1])
+    sets = np.ascontiguousarray(sets, np.int32).reshape(P, -1, 8)
+    I = sets.shape[1]
+    H, F = np.zeros((P, 9)), np.zeros((P, 9))
+    sh, sf = np.zeros(P, np.float32), np.zeros(P, np.float32)
+    bh, bf = np.zeros(P, np.int32), np.zeros(P, np.int32)
+    ih, jf = np.zeros(max(N, 1), np.uint8), np.zeros(max(N, 1), np.uint8)
+    mod = np.zeros((P, I, 18)) if models else None
+    self.lib.ygzb_initializer_ransac.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float] + [C.c_void_p] * 9
+    self.check(self.lib.ygzb_initializer_ransac(self.h, P, _p(offsets), _p(np.ascontiguousarray(px1, np.float64)), _p(np.ascontiguousarray(px2, np.float64)),
+                                                I, _p(sets), C.c_float(sigma), _p(H), _p(sh), _p(bh), _p(ih), _p(F), _p(sf), _p(bf), _p(jf), _p(mod)),
+               "ygzb_initializer_ransac")
+    out = dict(H21=H.reshape(P, 3, 3), score_H=sh, best_H=bh, inliers_H=ih[:N].astype(bool), F21=F.reshape(P, 3, 3), score_F=sf, best_F=bf,
+               inliers_F=jf[:N].astype(bool))
+    if models:
+        out["models"] = mod
+    return out
+
+
+Context.initializer_ransac = _initializer_ransac
 Context.search_by_bow = _search_by_bow
 Context.vocabulary = lambda self, data: Vocabulary(self, data)
 Context.search_for_triangulation = _search_for_triangulation

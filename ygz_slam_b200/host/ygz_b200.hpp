@@ -734,6 +734,61 @@ class Tracker {  // include/ygz/Algorithm/Tracker.h:11-76
     TrackerStatusType _status = TRACK_NOT_READY;
 };
 
+// include/ygz/Algorithm/Initializer.h:27-145 -- the RANSAC half (FindHomography / FindFundamental and the model choice of
+// TryInitialize, src/Algorithm/Initializer.cpp:9-78); ReconstructH / ReconstructF (pose + structure from the chosen model) are
+// not part of the device path yet
+class Initializer {
+  public:
+    struct Option {
+        float _sigma = 2.0f;    // Initializer.h:45
+        float _sigma2 = 4.0f;
+        int _max_iter = 200;    // Initializer.h:47
+    } _options;
+    struct Matrix3 { double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; double operator()(int r, int c) const { return m[3 * r + c]; } };
+    // the minimal sets of TryInitialize (:25-49): a default-constructed cv::RNG (multiply-with-carry, state 0xffffffff,
+    // uniform(0, b) = next() % b), 8 draws without replacement per iteration by swap-with-last
+    static std::vector<int32_t> DrawSets(int num_points, int max_iter) {
+        std::vector<int32_t> sets((size_t)max_iter * 8), avail;
+        uint64_t state = 0xffffffffULL;
+        for (int it = 0; it < max_iter; ++it) {
+            avail.resize(num_points);
+            for (int i = 0; i < num_points; ++i) avail[i] = i;
+            for (int j = 0; j < 8; ++j) {
+                state = (uint64_t)(uint32_t)state * 4164903690ULL + (uint32_t)(state >> 32);
+                const int r = avail.empty() ? 0 : (int)((uint32_t)state % (uint32_t)avail.size());
+                sets[(size_t)it * 8 + j] = avail[r];
+                avail[r] = avail.back();
+                avail.pop_back();
+            }
+        }
+        return sets;
+    }
+    // TryInitialize up to the choice of the model (:9-78): returns true if the homography is preferred (rh > 0.4)
+    bool FindModels(const std::vector<Vector2d>& px1, const std::vector<Vector2d>& px2) {
+        if (px1.size() != px2.size() || px1.size() < 8) throw b200::Error("Initializer: at least 8 matched pixels are needed");
+        auto& rt = b200::Runtime::Get();
+        const int n = (int)px1.size();
+        std::vector<double> a(2 * (size_t)n), b(2 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            a[2 * i] = px1[i][0]; a[2 * i + 1] = px1[i][1];
+            b[2 * i] = px2[i][0]; b[2 * i + 1] = px2[i][1];
+        }
+        const std::vector<int32_t> sets = DrawSets(n, _options._max_iter);
+        const int32_t off[2] = {0, n};
+        std::vector<uint8_t> ih(n), jf(n);
+        int32_t bh = -1, bf = -1;
+        rt.Check(ygzb_initializer_ransac(rt.ctx(), 1, off, a.data(), b.data(), _options._max_iter, sets.data(), _options._sigma, _H21.m, &_score_H,
+                                         &bh, ih.data(), _F21.m, &_score_F, &bf, jf.data(), nullptr), "ygzb_initializer_ransac");
+        _inliers_H.assign(ih.begin(), ih.end());
+        _inliers_F.assign(jf.begin(), jf.end());
+        const float rh = _score_H / (_score_H + _score_F);   // :66
+        return rh > 0.4f;
+    }
+    Matrix3 _H21, _F21;
+    float _score_H = 0, _score_F = 0;
+    std::vector<bool> _inliers_H, _inliers_F;
+};
+
 namespace ba {  // include/ygz/Algorithm/BA.h:23-66
 
 // BA.h:23-30 / BA.cpp:11-89: two-view bundle adjustment after the monocular initialisation (VisualOdometry.cpp:148)
