@@ -782,7 +782,10 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
                         if (fabs(cost - new_cost) <= 1e-6 * cost) {
                             term = 3;   // function tolerance
                         } else {
-                            radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3));
+                            {
+                            const double t3 = 2.0 * relative_decrease - 1.0;
+                            radius = radius / fmax(1.0 / 3.0, 1.0 - t3 * t3 * t3);
+                        }
                             radius = fmin(1e16, radius);
                             decrease_factor = 2.0;
                         }
@@ -952,6 +955,66 @@ __device__ void project_jet(const double pose[6], const double X[3], Jet6* p0, J
     *p2 = out[2] + P[2];
 }
 
+// value + partials with respect to the angle-axis only: the rotation of the pose, differentiated ONCE per evaluation instead
+// of once per point (the jets of project_jet spent two thirds of the kernel's FP64 instructions re-deriving it per point)
+struct Jet3 {
+    double a;
+    double v[3];
+};
+__device__ __forceinline__ Jet3 j3c(double c) { return Jet3{c, {0, 0, 0}}; }
+__device__ __forceinline__ Jet3 operator+(const Jet3& x, const Jet3& y) { return Jet3{x.a + y.a, {x.v[0] + y.v[0], x.v[1] + y.v[1], x.v[2] + y.v[2]}}; }
+__device__ __forceinline__ Jet3 operator-(const Jet3& x, const Jet3& y) { return Jet3{x.a - y.a, {x.v[0] - y.v[0], x.v[1] - y.v[1], x.v[2] - y.v[2]}}; }
+__device__ __forceinline__ Jet3 operator*(const Jet3& x, const Jet3& y) {
+    return Jet3{x.a * y.a, {x.a * y.v[0] + x.v[0] * y.a, x.a * y.v[1] + x.v[1] * y.a, x.a * y.v[2] + x.v[2] * y.a}};
+}
+__device__ __forceinline__ Jet3 operator/(const Jet3& x, const Jet3& y) {
+    const double inv = 1.0 / y.a, q = x.a * inv;
+    return Jet3{q, {(x.v[0] - q * y.v[0]) * inv, (x.v[1] - q * y.v[1]) * inv, (x.v[2] - q * y.v[2]) * inv}};
+}
+
+// column k of R(angle-axis) and of dR/d(angle-axis): ceres::AngleAxisRotatePoint (both branches) applied to the basis vector e_k
+__device__ void rotate_basis(const double aa[3], int k, double col[3], double dcol[3][3]) {
+    Jet3 P[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        P[i] = j3c(aa[i]);
+        P[i].v[i] = 1.0;
+    }
+    const Jet3 pt[3] = {j3c(k == 0 ? 1.0 : 0.0), j3c(k == 1 ? 1.0 : 0.0), j3c(k == 2 ? 1.0 : 0.0)};
+    const Jet3 theta2 = P[0] * P[0] + P[1] * P[1] + P[2] * P[2];
+    Jet3 out[3];
+    if (theta2.a > 2.2204460492503131e-16) {
+        Jet3 theta, costheta, sintheta;
+        const double s = sqrt(theta2.a), d = 1.0 / (2.0 * s);
+        theta.a = s;
+        const double c = cos(s), sn = sin(s);
+        costheta.a = c;
+        sintheta.a = sn;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            theta.v[i] = theta2.v[i] * d;
+            costheta.v[i] = -sn * theta.v[i];
+            sintheta.v[i] = c * theta.v[i];
+        }
+        const Jet3 inv = j3c(1.0) / theta;
+        const Jet3 w[3] = {P[0] * inv, P[1] * inv, P[2] * inv};
+        const Jet3 wxp[3] = {w[1] * pt[2] - w[2] * pt[1], w[2] * pt[0] - w[0] * pt[2], w[0] * pt[1] - w[1] * pt[0]};
+        const Jet3 tmp = (w[0] * pt[0] + w[1] * pt[1] + w[2] * pt[2]) * (j3c(1.0) - costheta);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = pt[i] * costheta + wxp[i] * sintheta + w[i] * tmp;
+    } else {
+        const Jet3 wxp[3] = {P[1] * pt[2] - P[2] * pt[1], P[2] * pt[0] - P[0] * pt[2], P[0] * pt[1] - P[1] * pt[0]};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = pt[i] + wxp[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        col[i] = out[i].a;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) dcol[i][m] = out[i].v[m];
+    }
+}
+
 struct PoseOnlyArgs {
     const int32_t* offsets;   // per problem range of points
     const int32_t* counts;    // optional: points of problem p (default offsets[p + 1] - offsets[p])
@@ -962,8 +1025,9 @@ struct PoseOnlyArgs {
     double* depth;            // [total]
     int32_t* n_inlier;        // [n_problems]
     uint8_t* enable;          // scratch [total]
-    double* ws;               // [n_problems][4][kPoseCluster][kPoseRed]: per-CTA partial sums of a reduction
+    double* ws;               // (unused since the partial sums travel through distributed shared memory; kept for the scratch layout)
     float fx, fy, cx, cy;
+    int stage_k;              // points per thread the dynamic shared memory can stage (0: read the points from global memory)
 };
 
 // One 8-CTA cluster per frame: the forward-mode jets are FP64 and a single SM's FP64 pipe bounded the one-CTA version.
@@ -973,28 +1037,42 @@ constexpr int kPoseThreads = 256;
 constexpr int kPoseCluster = 8;
 constexpr int kPoseRed = 32;
 
+// A y = b for the 6 x 6 SPD system of a trust-region step (b in y on entry): LDL^T with one reciprocal per pivot instead of the
+// square roots and 33 divisions of a textbook Cholesky -- every thread runs this between two reductions, so its dependent chain
+// is on the critical path of every LM iteration.  false if a pivot is not positive (Ceres: the linear solver failed).
 __device__ bool cholesky6(double A[36], double y[6]) {
+    double rd[6];
+#pragma unroll
     for (int j = 0; j < 6; ++j) {
         double d = A[j * 6 + j];
-        for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k] * A[k * 6 + k];
         if (!(d > 0)) return false;
-        d = sqrt(d);
         A[j * 6 + j] = d;
+        rd[j] = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double s = A[i * 6 + j];
-            for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
-            A[i * 6 + j] = s / d;
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k] * A[k * 6 + k];
+            A[i * 6 + j] = s * rd[j];
         }
     }
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         double s = y[i];
+#pragma unroll
         for (int k = 0; k < i; ++k) s -= A[i * 6 + k] * y[k];
-        y[i] = s / A[i * 6 + i];
+        y[i] = s;
     }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] *= rd[i];
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         double s = y[i];
+#pragma unroll
         for (int k = i + 1; k < 6; ++k) s -= A[k * 6 + i] * y[k];
-        y[i] = s / A[i * 6 + i];
+        y[i] = s;
     }
     return true;
 }
@@ -1002,74 +1080,127 @@ __device__ bool cholesky6(double A[36], double y[6]) {
 __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyArgs a) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ double s_pts[];                        // staged points: [(k * 5 + c) * kPoseThreads + tid], c = X Y Z u_n v_n
     __shared__ double s_red[kPoseThreads / 32][kPoseRed];
+    __shared__ double s_pub[4][kPoseRed];                    // this CTA's partial sums of the last four reductions (read by the peers)
     __shared__ double s_pose[6], s_cand[6], s_scale[6], s_sum[kPoseRed];
+    __shared__ double s_R[9], s_dR[27], s_Rpose[6];          // rotation (row major), dR[3 * (3 j + k) + m] = d R_jk / d aa_m, and their pose
     const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
     const int prob = blockIdx.x / C, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int CT = C * kPoseThreads, ct = rank * kPoseThreads + tid;   // cluster-wide thread id
     const int i0 = a.offsets[prob], n = a.counts ? a.counts[prob] : a.offsets[prob + 1] - i0;
     const double fx = a.fx, fy = a.fy, cx = a.cx, cy = a.cy;
-    double* ws = a.ws + (size_t)prob * 4 * kPoseCluster * kPoseRed;
+    const int K = (n + CT - 1) / CT;                         // points per thread: i = ct + k * CT
+    const bool staged = K <= a.stage_k && K <= 32;
+    unsigned en_mask = 0;                                    // (staged) enable flag of this thread's k-th point
     int slot = 0;
 
-    // cluster-wide sum of `cnt` per-thread partial sums into s_sum (identical in every thread of every CTA afterwards)
-    auto reduce = [&](const double* part, int cnt) {
-        for (int t = 0; t < cnt; ++t) {
-            const double v = warp_sum(part[t]);
-            if (lane == 0) s_red[warp][t] = v;
-        }
+    // cluster-wide sums of the per-thread partials `part[0 .. cnt)` into s_sum (identical in every thread of every CTA afterwards):
+    // warp level, CTA level through shared memory, cluster level through distributed shared memory (one cluster barrier)
+    auto finish_reduce = [&](int cnt) {
         __syncthreads();
         if (tid < cnt) {
             double s = 0;
             for (int w = 0; w < kPoseThreads / 32; ++w) s += s_red[w][tid];
-            ws[((size_t)slot * kPoseCluster + rank) * kPoseRed + tid] = s;
+            s_pub[slot][tid] = s;
         }
         cluster.sync();
         if (tid < cnt) {
             double s = 0;
-            for (int r = 0; r < C; ++r) s += __ldcg(&ws[((size_t)slot * kPoseCluster + r) * kPoseRed + tid]);
+            for (int r = 0; r < C; ++r) s += cluster.map_shared_rank(&s_pub[slot][0], r)[tid];
             s_sum[tid] = s;
         }
         slot = (slot + 1) & 3;
         __syncthreads();
     };
-    // cost only at `pose` -> s_sum[0] = sum of squares, s_sum[1] > 0 when a residual block returned false (depth < 0)
-    auto eval_cost = [&](const double* pose) -> double {
-        double part[2] = {0, 0};
-        for (int i = ct; i < n; i += CT) {
-            if (!a.enable[i0 + i]) continue;
-            Jet6 p0, p1, p2;
-            project_jet(pose, a.pw + 3 * (size_t)(i0 + i), &p0, &p1, &p2);
-            if (p2.a < 0) {
-                part[1] += 1;
-                continue;
-            }
-            const double r0 = (a.px[2 * (size_t)(i0 + i)] - cx) / fx - p0.a / p2.a, r1 = (a.px[2 * (size_t)(i0 + i) + 1] - cy) / fy - p1.a / p2.a;
-            part[0] += r0 * r0 + r1 * r1;
+    auto reduce_few = [&](const double* part, int cnt) {
+        for (int t = 0; t < cnt; ++t) {
+            const double v = warp_sum(part[t]);
+            if (lane == 0) s_red[warp][t] = v;
         }
-        reduce(part, 2);
-        return 0.5 * s_sum[0];
+        finish_reduce(cnt);
     };
-    // J^T J (21), J^T r (6), cost (27), failed blocks (28): scaled by s_scale when `scaled`
-    auto eval_normal = [&](const double* pose, bool scaled) {
-        double part[29];
+    auto reduce32 = [&](double* part) {   // 32 values: a reduce-scatter butterfly, lane l ends with the warp total of part[l]
+        int off = 16;
 #pragma unroll
-        for (int t = 0; t < 29; ++t) part[t] = 0;
-        for (int i = ct; i < n; i += CT) {
-            if (!a.enable[i0 + i]) continue;
-            Jet6 p0, p1, p2;
-            project_jet(pose, a.pw + 3 * (size_t)(i0 + i), &p0, &p1, &p2);
-            if (p2.a < 0) {
+        for (int m = 16; m >= 1; m >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < m; ++i) {
+                const double keep = up ? part[i + m] : part[i];
+                const double send = up ? part[i] : part[i + m];
+                part[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, off);
+            }
+        }
+        s_red[warp][lane] = part[0];
+        finish_reduce(32);
+    };
+    // R(aa) and dR / d aa of `pose` into shared memory (three threads, a column each); skipped when they are already there
+    auto rotation_of = [&](const double* pose) {
+        bool same = true;
+        for (int k = 0; k < 6; ++k) same = same && s_Rpose[k] == pose[k];
+        if (same) return;   // (uniform: shared memory values)
+        __syncthreads();
+        if (tid < 3) {
+            double col[3], dcol[3][3];
+            const double aa[3] = {pose[3], pose[4], pose[5]};
+            rotate_basis(aa, tid, col, dcol);
+            for (int j = 0; j < 3; ++j) {
+                s_R[3 * j + tid] = col[j];
+                for (int m = 0; m < 3; ++m) s_dR[3 * (3 * j + tid) + m] = dcol[j][m];
+            }
+        }
+        if (tid >= 32 && tid < 38) s_Rpose[tid - 32] = pose[tid - 32];
+        __syncthreads();
+    };
+    auto point = [&](int k, double* X, double* o) {   // world point and normalised observation of this thread's k-th point
+        if (staged) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) X[c] = s_pts[(k * 5 + c) * kPoseThreads + tid];
+            o[0] = s_pts[(k * 5 + 3) * kPoseThreads + tid];
+            o[1] = s_pts[(k * 5 + 4) * kPoseThreads + tid];
+        } else {
+            const size_t i = (size_t)(i0 + ct + k * CT);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) X[c] = a.pw[3 * i + c];
+            o[0] = (a.px[2 * i] - cx) / fx;
+            o[1] = (a.px[2 * i + 1] - cy) / fy;
+        }
+    };
+    auto enabled = [&](int k) { return staged ? (en_mask >> k & 1u) != 0 : a.enable[i0 + ct + k * CT] != 0; };
+    // J^T J (21), J^T r (6), cost (27), failed blocks (28) at `pose`: the derivative of ceres' angle-axis residual, with the rotation
+    // differentiated once (rotation_of) and pushed through the projection analytically
+    auto eval_normal = [&](const double* pose) {
+        rotation_of(pose);
+        double part[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) part[t] = 0;
+        const double t0 = pose[0], t1 = pose[1], t2 = pose[2];
+        for (int k = 0; k < K; ++k) {
+            if (ct + k * CT >= n || !enabled(k)) continue;
+            double X[3], o[2];
+            point(k, X, o);
+            const double p2 = s_R[6] * X[0] + s_R[7] * X[1] + s_R[8] * X[2] + t2;
+            if (p2 < 0) {
                 part[28] += 1;
                 continue;
             }
-            const Jet6 r0 = jc((a.px[2 * (size_t)(i0 + i)] - cx) / fx) - p0 / p2, r1 = jc((a.px[2 * (size_t)(i0 + i) + 1] - cy) / fy) - p1 / p2;
-            double j0[6], j1[6];
+            const double p0 = s_R[0] * X[0] + s_R[1] * X[1] + s_R[2] * X[2] + t0, p1 = s_R[3] * X[0] + s_R[4] * X[1] + s_R[5] * X[2] + t1;
+            const double inv = 1.0 / p2, q0 = p0 * inv, q1 = p1 * inv, r0 = o[0] - q0, r1 = o[1] - q1;
+            double dp[3][3];   // d p_j / d aa_m
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const double s = scaled ? s_scale[k] : 1.0;
-                j0[k] = r0.v[k] * s;
-                j1[k] = r1.v[k] * s;
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+                    dp[j][m] = s_dR[3 * (3 * j) + m] * X[0] + s_dR[3 * (3 * j + 1) + m] * X[1] + s_dR[3 * (3 * j + 2) + m] * X[2];
+            // residual = observation - p / p_z: d r0 = -(d p0 - q0 d p2) / p_z
+            double j0[6], j1[6];
+            j0[0] = -inv; j0[1] = 0.0; j0[2] = q0 * inv;
+            j1[0] = 0.0; j1[1] = -inv; j1[2] = q1 * inv;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                j0[3 + m] = -(dp[0][m] - q0 * dp[2][m]) * inv;
+                j1[3 + m] = -(dp[1][m] - q1 * dp[2][m]) * inv;
             }
             int t = 0;
 #pragma unroll
@@ -1078,10 +1209,10 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
                 for (int c = r; c < 6; ++c) part[t++] += j0[r] * j0[c] + j1[r] * j1[c];
             }
 #pragma unroll
-            for (int k = 0; k < 6; ++k) part[21 + k] += j0[k] * r0.a + j1[k] * r1.a;
-            part[27] += r0.a * r0.a + r1.a * r1.a;
+            for (int q = 0; q < 6; ++q) part[21 + q] += j0[q] * r0 + j1[q] * r1;
+            part[27] += r0 * r0 + r1 * r1;
         }
-        reduce(part, 29);
+        reduce32(part);
     };
 
     // initial pose = [t; so3.log()]
@@ -1092,18 +1223,28 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
         const V3d rl = so3_log(T.q, &th);
         backup[0] = T.t.x; backup[1] = T.t.y; backup[2] = T.t.z; backup[3] = rl.x; backup[4] = rl.y; backup[5] = rl.z;
     }
-    for (int i = ct; i < n; i += CT) {   // (per-point flags are written and later read by the same thread)
+    for (int k = 0; k < K; ++k) {   // (per-point flags are written and later read by the same thread)
+        const int i = ct + k * CT;
+        if (i >= n) break;
         a.enable[i0 + i] = 1;
         a.inlier[i0 + i] = 1;
         a.depth[i0 + i] = -1;
+        if (staged) {
+            en_mask |= 1u << k;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s_pts[(k * 5 + c) * kPoseThreads + tid] = a.pw[3 * (size_t)(i0 + i) + c];
+            s_pts[(k * 5 + 3) * kPoseThreads + tid] = (a.px[2 * (size_t)(i0 + i)] - cx) / fx;
+            s_pts[(k * 5 + 4) * kPoseThreads + tid] = (a.px[2 * (size_t)(i0 + i) + 1] - cy) / fy;
+        }
     }
+    if (tid < 6) s_Rpose[tid] = __longlong_as_double(0x7FF8000000000000LL);   // NaN: no rotation cached yet
     __syncthreads();
     int cntInlier = 0;
     for (int round = 0; round < 4; ++round) {
         if (tid < 6) s_pose[tid] = backup[tid];
         __syncthreads();
         // ---- Ceres trust-region LM (default options) ----
-        eval_normal(s_pose, false);
+        eval_normal(s_pose);
         bool run = !(s_sum[28] > 0);
         double cost = 0.5 * s_sum[27];
         if (run) {
@@ -1167,8 +1308,11 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
                 step_norm = sqrt(step_norm);
                 x_norm = sqrt(x_norm);
                 __syncthreads();
-                const double new_cost = eval_cost(s_cand);
-                if (!(s_sum[1] > 0)) {
+                // ONE pass at the candidate: its cost decides the step, and if the step is accepted the same sums are the normal
+                // equations of the next iteration (a rejected step wastes the Jacobian part of the pass, not a second reduction)
+                eval_normal(s_cand);
+                const double new_cost = 0.5 * s_sum[27];
+                if (!(s_sum[28] > 0)) {
                     const double relative_decrease = (cost - new_cost) / model_cost_change;
                     if (relative_decrease > 1e-3) {
                         accepted = true;
@@ -1180,7 +1324,6 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
                         const double old_cost = cost;
                         cost = new_cost;
                         if (fabs(cost_change) <= 1e-6 * old_cost) break;  // function tolerance
-                        eval_normal(s_pose, false);
                         double gmax = 0;
                         for (int k = 0; k < 6; ++k) gmax = fmax(gmax, fabs(s_sum[21 + k]));
                         for (int t = 0; t < 27; ++t) U[t] = s_sum[t];
@@ -1202,7 +1345,9 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
         __syncthreads();
         // ---- classification with the pose of the PREVIOUS round (BA.cpp:231-251) ----
         double cnt = 0;
-        for (int i = ct; i < n; i += CT) {
+        for (int k = 0; k < K; ++k) {
+            const int i = ct + k * CT;
+            if (i >= n) break;
             const double* X = a.pw + 3 * (size_t)(i0 + i);
             const V3d pc = transform(T, V3d{X[0], X[1], X[2]});
             const double u = fx * pc.x / pc.z + cx, v = fy * pc.y / pc.z + cy;
@@ -1211,14 +1356,16 @@ __global__ void __launch_bounds__(kPoseThreads) pose_only_kernel(const PoseOnlyA
             if (error2 > (double)5.991f) {
                 a.inlier[i0 + i] = 0;
                 a.enable[i0 + i] = 0;
+                en_mask &= ~(1u << (k & 31));
             } else {
                 a.depth[i0 + i] = pc.z;
                 a.inlier[i0 + i] = 1;
                 a.enable[i0 + i] = 1;
+                en_mask |= 1u << (k & 31);
                 cnt += 1;
             }
         }
-        reduce(&cnt, 1);
+        reduce_few(&cnt, 1);
         cntInlier = (int)s_sum[0];
         if (cntInlier < 10) break;
         double th;
@@ -1239,19 +1386,37 @@ size_t pose_only_ws_doubles(int n_problems) { return (size_t)n_problems * 4 * kP
 
 // ba::OptimizeCurrentPoseOnly on device-resident problems (the tracking engine): problem p owns points
 // [d_offsets[p], d_offsets[p] + d_counts[p]); cluster = CTAs per problem (1, 2, 4 or 8)
+// points per thread the kernel may stage in shared memory for problems of at most max_points points on `cluster` CTAs
+// (0 = more than fits: the kernel then reads the points from global memory); sets the kernel's shared-memory opt-in once
+static int pose_only_stage_k(int max_points, int cluster) {
+    static std::once_flag once;
+    static int max_k = 0;
+    std::call_once(once, [] {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const int budget = std::max(0, optin - 8 * 1024);   // the kernel's static arrays use ~4 KB
+        cudaFuncSetAttribute(pose_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, budget);
+        max_k = std::min(32, budget / (int)(5 * kPoseThreads * sizeof(double)));
+    });
+    const int k = (std::max(max_points, 1) + cluster * kPoseThreads - 1) / (cluster * kPoseThreads);
+    return k <= max_k ? k : 0;
+}
+
 int launch_pose_only_dev(ygzb_ctx* ctx, int n_problems, const int32_t* d_offsets, const int32_t* d_counts, const double* d_pw,
                          const double* d_px, double* d_T_cw, uint8_t* d_inlier, double* d_depth, int32_t* d_n_inlier, uint8_t* d_enable,
-                         double* d_ws, int cluster) {
+                         double* d_ws, int cluster, int max_points) {
     if (n_problems <= 0) return YGZB_OK;
     PoseOnlyArgs a;
     a.offsets = d_offsets; a.counts = d_counts; a.pw = d_pw; a.px = d_px; a.T_cw = d_T_cw; a.inlier = d_inlier; a.depth = d_depth;
     a.n_inlier = d_n_inlier; a.enable = d_enable; a.ws = d_ws;
     a.fx = ctx->prm.fx; a.fy = ctx->prm.fy; a.cx = ctx->prm.cx; a.cy = ctx->prm.cy;
     cluster = std::max(1, std::min(cluster, kPoseCluster));
+    a.stage_k = pose_only_stage_k(max_points, cluster);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n_problems * cluster));
     cfg.blockDim = dim3(kPoseThreads);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)a.stage_k * 5 * kPoseThreads * sizeof(double);
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1807,10 +1972,13 @@ int ygzb_pose_only(ygzb_ctx* ctx, int n_problems, const int32_t* offsets, const 
         YGZB_CUDA(ctx, cudaMemcpyAsync(buf, stage, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     {
+        int max_points = 0;
+        for (size_t q = 0; q < P; ++q) max_points = std::max(max_points, offsets[q + 1] - offsets[q]);
+        a.stage_k = pose_only_stage_k(max_points, kPoseCluster);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(n_problems * kPoseCluster));
         cfg.blockDim = dim3(kPoseThreads);
-        cfg.dynamicSmemBytes = 0;
+        cfg.dynamicSmemBytes = (size_t)a.stage_k * 5 * kPoseThreads * sizeof(double);
         cfg.stream = ctx->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;

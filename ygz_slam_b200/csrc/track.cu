@@ -507,7 +507,7 @@ int ygzb_tracker_track(ygzb_tracker* t, int n_jobs, const ygzb_track_job* jobs, 
     }
     rc = launch_track_chain_mid(t->f, t->st, b);
     if (rc != YGZB_OK) return rc;
-    rc = launch_pose_only_dev(ctx, n_jobs, b.c_off, b.c_cnt, b.c_pw, b.c_px, b.T_cur, b.inlier, b.c_depth, b.n_inl, b.enable, b.pose_ws, cl);
+    rc = launch_pose_only_dev(ctx, n_jobs, b.c_off, b.c_cnt, b.c_pw, b.c_px, b.T_cur, b.inlier, b.c_depth, b.n_inl, b.enable, b.pose_ws, cl, b.cap);
     if (rc != YGZB_OK) return rc;
     {
         ProfScope ps(ctx, kStageOther);

@@ -66,7 +66,7 @@ int launch_track_chain_mid(ygzb_frames* f, const TrackStore& st, const TrackBatc
 // ba.cu
 int launch_pose_only_dev(ygzb_ctx* ctx, int n_problems, const int32_t* d_offsets, const int32_t* d_counts, const double* d_pw,
                          const double* d_px, double* d_T_cw, uint8_t* d_inlier, double* d_depth, int32_t* d_n_inlier, uint8_t* d_enable,
-                         double* d_ws, int cluster);
+                         double* d_ws, int cluster, int max_points);
 size_t pose_only_ws_doubles(int n_problems);
 size_t sparse_align2_scratch_bytes(int n_problems, int cells);
 
