@@ -502,8 +502,8 @@ def vo_line(args, rank, world, local_rank):
     stacked = vo_native.stack_pinned([d[0] for d in data])
     depths = [d[1] for d in data]
     # host threads (= ygzb contexts = CUDA streams): every thread drives a latency-bound chain of kernels for its streams and the
-    # chains of different threads overlap on the GPU.  Measured on one B200, 8 streams: 2 / 3 / 4 / 8 threads -> 22.5k / 23.7k /
-    # 23.9k / 21.6k frames/s; 32 streams: 4 / 8 / 16 threads -> 31k / 33.6k / collapse (the threads spin in
+    # chains of different threads overlap on the GPU.  Measured on one B200, 8 streams: 2 / 4 / 6 / 8 threads -> 25.8k / 27.7k /
+    # 27.7k / 24.0k frames/s; 32 streams: 8 / 12 / 16 threads -> 40.4k / 36.9k / collapse (the threads spin in
     # cudaStreamSynchronize: 16 spinning threads on a 16-CPU cgroup quota get throttled).  Default: one thread per two streams,
     # at most half of the CPUs this rank may use.
     if args.vo_threads > 0:
@@ -534,6 +534,23 @@ def vo_line(args, rank, world, local_rank):
     # ---- e2e leg: host frames through the C ABI, H2D + D2H inside the timed region ------------------------------------
     traj_e, stats_e, sec_e, det_e = vo_gpu_leg(ctx, stacked, depths, threads, warm, window=args.vo_window)
     barrier()
+    # Guard against a rare slow FIRST leg (seen in 2 of ~40 runs: the whole first leg of the process, warm-up included, ran ~5x
+    # slower than the e2e leg that follows it on the same frames; no throttle reason, clocks at max): the resident leg cannot be
+    # slower than the e2e leg, which does the same work plus the uploads.  Like a throttled run it is re-measured ONCE, and both
+    # figures are reported.
+    remeasured = None
+    redo = 1.0 if det_r["device_ms"] > 1.5 * sec_e * 1e3 else 0.0
+    if world > 1:
+        flag = torch.tensor([redo], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        redo = float(flag[0])
+    if redo:
+        first_ms = det_r["device_ms"]
+        barrier()
+        traj_r, stats_r, sec_r, det_r = vo_gpu_leg(ctx, stacked, depths, threads, warm, device_ptr=dev.data_ptr(), window=args.vo_window)
+        barrier()
+        remeasured = {"first_resident_ms": first_ms, "second_resident_ms": det_r["device_ms"], "e2e_ms": sec_e * 1e3,
+                      "reason": "resident leg slower than 1.5x the e2e leg of the same frames"}
     # diagnostics (untimed legs of the same streams): one frame per stream in flight (the latency mode of the engine) and
     # the per-stage C-ABI path of round 1 (one blocking call per stage and lock-step frame)
     diag = {}
@@ -675,6 +692,7 @@ def vo_line(args, rank, world, local_rank):
                     "h2d_image_bytes_per_step": det_e["h2d_image_bytes"] / args.steps,
                     "timing": "wall clock between device synchronisations (host bookkeeping and several CUDA streams are part of the step)"},
             "gpu_launches": int(det_r["gpu_launches"]),
+            "resident_remeasured": remeasured,
             # serialised kernel time of the profiled pass (CUDA events around every launch, one context) scaled to the timed region,
             # over the timed wall: > 1 means kernels of several CUDA streams overlapped
             "gpu_busy": {"kernel_ms_per_frame_serialised": total_ms / prof_frames,
