@@ -210,6 +210,20 @@ int ygzb_initializer_ransac(ygzb_ctx* ctx, int n_lists, const int32_t* offsets, 
                             const int32_t* sets, float sigma, double* H21, float* score_H, int32_t* best_H, uint8_t* inlier_H,
                             double* F21, float* score_F, int32_t* best_F, uint8_t* inlier_F, double* all_models);
 
+/* replaces Initializer::ReconstructH / ReconstructF with CheckRT, Triangulate and DecomposeE (src/Algorithm/Initializer.cpp:
+ * 330-675, 855-963) as called from TryInitialize (:74-78): per list the model TryInitialize chose (use_h[l] != 0: model[l] =
+ * H21 and ReconstructH, else F21 and ReconstructF), inliers = that model's flags (only their count enters, :861-864, 882).
+ * The camera is the context's (ygzb_params fx fy cx cy, float like Camera.h:14-22); sigma2 = Options::_sigma2 (4.0),
+ * min_parallax = _min_parallex (1.0), min_triangulated = _min_triangulated_pts (8), good_point_ratio_h (0.9).
+ * Out per list: ok = the function's bool; R21 (9, row major), t21 (3), zero unless ok; n_good[8] = CheckRT's count of every
+ * pose candidate (8 for H, 4 for F); parallax = the selected candidate's (degrees); per point pair: p3d (3 doubles, camera-1
+ * frame; zero where not reconstructed) and triangulated flags of the selected candidate; candidates (may be NULL) = n_lists x
+ * 8 x 12, every candidate's R then t.  All point pairs of all candidates are triangulated in parallel.                     */
+int ygzb_initializer_reconstruct(ygzb_ctx* ctx, int n_lists, const int32_t* offsets, const double* px1, const double* px2,
+                                 const int32_t* use_h, const double* model, const uint8_t* inliers, float sigma2, float min_parallax,
+                                 int min_triangulated, double good_point_ratio_h, int32_t* ok, double* R21, double* t21, double* p3d,
+                                 uint8_t* triangulated, int32_t* n_good, double* parallax, double* candidates);
+
 /* ---- cvutils / Matcher: direct (photometric) alignment ---------------------------------------
  * replaces cvutils::Align2D (src/Algorithm/CVUtils.cpp:186-318; include/ygz/Algorithm/CVUtils.h:163-169):
  * inverse-compositional alignment of an 8x8 template.  Patch i is searched on pyramid level level[i] of

@@ -21,6 +21,7 @@
 // whose best score stays 0 leaves H21 / F21 untouched in the reference -- reported as best = -1 and a zero matrix here.
 // The CUDA path (ygz_slam_b200/csrc/initializer.cu) performs the same operations in the same order without FMA contraction,
 // so the comparison in tests/test_initializer.py is bit for bit.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -285,4 +286,295 @@ extern "C" void ora_initializer_ransac(int n, const double* px1, const double* p
         check_homography(n, px1, px2, H12, sigma, inl_H);
     }
     if (*best_F >= 0) check_fundamental(n, px1, px2, F21, sigma, inl_F);
+}
+
+// =====================================================================================================================
+// Second half: pose and structure from the chosen model.
+//   Initializer::ReconstructH   reference src/Algorithm/Initializer.cpp:330-513  (Faugeras' eight hypotheses)
+//   Initializer::CheckRT        reference src/Algorithm/Initializer.cpp:515-630
+//   Initializer::Triangulate    reference src/Algorithm/Initializer.cpp:661-675
+//   Initializer::ReconstructF   reference src/Algorithm/Initializer.cpp:855-941
+//   Initializer::DecomposeE     reference src/Algorithm/Initializer.cpp:943-963
+// Eigen::JacobiSVD of the 3 x 3 / 4 x 4 matrices is again the one-sided Jacobi SVD above, singular values sorted descending,
+// U = A V / sigma (the left vector of a singular value below 1e-12 sigma_max -- the essential matrix' third -- is the cross
+// product of the other two, as an orthogonal U requires).  A singular pair is defined up to a common sign; the eight (H) / four
+// (F) pose hypotheses are closed under those sign changes, so the selected pose does not depend on them, only the order in which
+// equal candidates would be met does.  acos() of CheckRT runs in float like the reference's (std::acos(float) through
+// `using namespace std`); the CUDA path's acosf may differ in the last bit: parallax is compared with a tolerance.
+namespace {
+
+struct Svd3 {
+    double U[9], V[9], s[3];   // row major; columns sorted by descending singular value
+};
+
+Svd3 svd3_sorted(const double* A) {
+    double a[9], v[9], n2[3];
+    std::memcpy(a, A, 72);
+    jacobi_svd<3, 3>(a, v);
+    for (int c = 0; c < 3; ++c) n2[c] = a[c] * a[c] + a[3 + c] * a[3 + c] + a[6 + c] * a[6 + c];
+    int ord[3] = {0, 1, 2};
+    for (int i = 0; i < 2; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (n2[ord[j]] > n2[ord[i]]) {
+                const int t = ord[i];
+                ord[i] = ord[j];
+                ord[j] = t;
+            }
+    Svd3 r;
+    for (int c = 0; c < 3; ++c) {
+        const int o = ord[c];
+        r.s[c] = std::sqrt(n2[o]);
+        for (int k = 0; k < 3; ++k) r.V[k * 3 + c] = v[k * 3 + o];
+    }
+    for (int c = 0; c < 3; ++c) {
+        const int o = ord[c];
+        if (c < 2 || r.s[2] > 1e-12 * r.s[0]) {
+            for (int k = 0; k < 3; ++k) r.U[k * 3 + c] = a[k * 3 + o] / r.s[c];
+        } else {
+            r.U[2] = r.U[3] * r.U[7] - r.U[6] * r.U[4];
+            r.U[5] = r.U[6] * r.U[1] - r.U[0] * r.U[7];
+            r.U[8] = r.U[0] * r.U[4] - r.U[3] * r.U[1];
+        }
+    }
+    return r;
+}
+
+double det3(const double* m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+void transpose3(const double* A, double* T) {
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) T[r * 3 + c] = A[c * 3 + r];
+}
+
+// Initializer::Triangulate: the right singular vector of the smallest singular value of the 4 x 4 DLT matrix, dehomogenised
+void triangulate(const double* kp1, const double* kp2, const double* P1, const double* P2, double* x3D) {
+    double A[16], v[16], n2[4];
+    for (int c = 0; c < 4; ++c) {
+        A[c] = kp1[0] * P1[8 + c] - P1[c];
+        A[4 + c] = kp1[1] * P1[8 + c] - P1[4 + c];
+        A[8 + c] = kp2[0] * P2[8 + c] - P2[c];
+        A[12 + c] = kp2[1] * P2[8 + c] - P2[4 + c];
+    }
+    jacobi_svd<4, 4>(A, v);
+    const int c = smallest_column<4, 4>(A, n2);
+    for (int k = 0; k < 3; ++k) x3D[k] = v[k * 4 + c] / v[12 + c];
+}
+
+// Initializer::CheckRT: number of points in front of both cameras (and, optionally, with a small reprojection error);
+// good[i] additionally needs parallax; p3d of the counted points; parallax = the 51st smallest angle in degrees
+int check_rt(int n, const double* px1, const double* px2, const double* R, const double* t, const double* K /* fx fy cx cy */, float th2,
+             bool check_reprojection, uint8_t* good, double* p3d, double* parallax) {
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const double P1[12] = {fx, 0, cx, 0, 0, fy, cy, 0, 0, 0, 1, 0};
+    const double Rt[12] = {R[0], R[1], R[2], t[0], R[3], R[4], R[5], t[1], R[6], R[7], R[8], t[2]};
+    double P2[12];
+    for (int c = 0; c < 4; ++c) {   // K * [R | t]
+        P2[c] = fx * Rt[c] + 0.0 * Rt[4 + c] + cx * Rt[8 + c];
+        P2[4 + c] = 0.0 * Rt[c] + fy * Rt[4 + c] + cy * Rt[8 + c];
+        P2[8 + c] = 0.0 * Rt[c] + 0.0 * Rt[4 + c] + 1.0 * Rt[8 + c];
+    }
+    const double O2[3] = {-(R[0] * t[0] + R[3] * t[1] + R[6] * t[2]), -(R[1] * t[0] + R[4] * t[1] + R[7] * t[2]),
+                          -(R[2] * t[0] + R[5] * t[1] + R[8] * t[2])};
+    std::vector<float> cosv;
+    cosv.reserve(n);
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+        good[i] = 0;
+        p3d[3 * i] = p3d[3 * i + 1] = p3d[3 * i + 2] = 0;
+        double X[3];
+        triangulate(px1 + 2 * i, px2 + 2 * i, P1, P2, X);
+        if (!std::isfinite(X[0])) continue;
+        const double dist1 = std::sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]);
+        const double n2v[3] = {X[0] - O2[0], X[1] - O2[1], X[2] - O2[2]};
+        const double dist2 = std::sqrt(n2v[0] * n2v[0] + n2v[1] * n2v[1] + n2v[2] * n2v[2]);
+        const double cosParallax = (X[0] * n2v[0] + X[1] * n2v[1] + X[2] * n2v[2]) / (dist1 * dist2);
+        if (X[2] < 0 && cosParallax < 0.99998) continue;
+        const double Y[3] = {R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0], R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1],
+                             R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2]};
+        if (Y[2] < 0 && cosParallax < 0.99998) continue;
+        if (check_reprojection) {
+            const double invZ1 = 1.0 / X[2];
+            const double im1x = fx * X[0] * invZ1 + cx, im1y = fy * X[1] * invZ1 + cy;
+            const double e1 = (im1x - px1[2 * i]) * (im1x - px1[2 * i]) + (im1y - px1[2 * i + 1]) * (im1y - px1[2 * i + 1]);
+            if (e1 > th2) continue;
+            const double invZ2 = 1.0 / Y[2];
+            const double im2x = fx * Y[0] * invZ2 + cx, im2y = fy * Y[1] * invZ2 + cy;
+            const double e2 = (im2x - px2[2 * i]) * (im2x - px2[2 * i]) + (im2y - px2[2 * i + 1]) * (im2y - px2[2 * i + 1]);
+            if (e2 > th2) continue;
+        }
+        cosv.push_back((float)cosParallax);
+        p3d[3 * i] = X[0];
+        p3d[3 * i + 1] = X[1];
+        p3d[3 * i + 2] = X[2];
+        ++cnt;
+        if (cosParallax < 0.99998) good[i] = 1;
+    }
+    if (cnt > 0) {
+        std::sort(cosv.begin(), cosv.end());
+        const size_t idx = (size_t)std::min(50, (int)cosv.size() - 1);
+        *parallax = std::acos(cosv[idx]) * 180 / M_PI;   // float acos, like std::acos(float) in the reference
+    } else {
+        *parallax = 0;
+    }
+    return cnt;
+}
+
+void mat_R(const double* U, double s, const double* Rp, const double* V, double* R) {   // (s U) Rp V^T
+    double sU[9], t1[9], Vt[9];
+    for (int k = 0; k < 9; ++k) sU[k] = s * U[k];
+    mul3(sU, Rp, t1);
+    transpose3(V, Vt);
+    mul3(t1, Vt, R);
+}
+
+}  // namespace
+
+// ReconstructH (use_h != 0) or ReconstructF on the model chosen by TryInitialize.  K = {fx, fy, cx, cy}; inliers = the model's
+// flags (only their count enters, ReconstructF :861-864, 882).  Out: R21 (row major), t21, p3d (3 n, zero where not
+// triangulated), triangulated flags, info[8] = {candidates' good counts ...}; parallax of the selected candidate.  Returns the
+// function's bool.
+extern "C" int ora_initializer_reconstruct(int n, const double* px1, const double* px2, int use_h, const double* model, const uint8_t* inliers,
+                                           const double* K, float sigma2, float min_parallax, int min_triangulated, double ratio_h,
+                                           double* R21, double* t21, double* p3d, uint8_t* triangulated, int32_t* n_good, double* parallax_out,
+                                           double* candidates /* may be NULL: 8 x 12, every candidate's R (9) and t (3) */) {
+    int N = 0;
+    for (int i = 0; i < n; ++i) N += inliers[i] ? 1 : 0;
+    const double Km[9] = {K[0], 0, K[2], 0, K[1], K[3], 0, 0, 1};
+    std::memset(R21, 0, 72);
+    std::memset(t21, 0, 24);
+    std::memset(p3d, 0, 24 * (size_t)n);
+    std::memset(triangulated, 0, n);
+    for (int k = 0; k < 8; ++k) n_good[k] = 0;
+    *parallax_out = 0;
+    if (candidates) std::memset(candidates, 0, 96 * sizeof(double));
+    std::vector<uint8_t> good(n);
+    std::vector<double> pts(3 * (size_t)n);
+    if (use_h) {
+        double invK[9], t1[9], A[9];
+        inverse3(Km, invK);
+        mul3(invK, model, t1);
+        mul3(t1, Km, A);
+        const Svd3 sv = svd3_sorted(A);
+        const double d1 = sv.s[0], d2 = sv.s[1], d3 = sv.s[2];
+        const double s = det3(sv.U) * det3(sv.V);
+        if (d1 / d2 < 1.00001 || d2 / d3 < 1.00001) return 0;
+        double Rs[8][9], ts[8][3];
+        const float aux1 = (float)std::sqrt((d1 * d1 - d2 * d2) / (d1 * d1 - d3 * d3));
+        const float aux3 = (float)std::sqrt((d2 * d2 - d3 * d3) / (d1 * d1 - d3 * d3));
+        const float x1[4] = {aux1, aux1, -aux1, -aux1}, x3[4] = {aux3, -aux3, aux3, -aux3};
+        const float aux_stheta = (float)(std::sqrt((d1 * d1 - d2 * d2) * (d2 * d2 - d3 * d3)) / ((d1 + d3) * d2));
+        const float ctheta = (float)((d2 * d2 + d1 * d3) / ((d1 + d3) * d2));
+        const float stheta[4] = {aux_stheta, -aux_stheta, -aux_stheta, aux_stheta};
+        for (int i = 0; i < 4; ++i) {
+            const double Rp[9] = {ctheta, 0, -stheta[i], 0, 1, 0, stheta[i], 0, ctheta};
+            mat_R(sv.U, s, Rp, sv.V, Rs[i]);
+            const double tp[3] = {x1[i] * (d1 - d3), 0.0 * (d1 - d3), -x3[i] * (d1 - d3)};
+            double tt[3];
+            for (int r = 0; r < 3; ++r) tt[r] = sv.U[r * 3] * tp[0] + sv.U[r * 3 + 1] * tp[1] + sv.U[r * 3 + 2] * tp[2];
+            const double nn = std::sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
+            for (int r = 0; r < 3; ++r) ts[i][r] = tt[r] / nn;
+        }
+        const float aux_sphi = (float)(std::sqrt((d1 * d1 - d2 * d2) * (d2 * d2 - d3 * d3)) / ((d1 - d3) * d2));
+        const float cphi = (float)((d1 * d3 - d2 * d2) / ((d1 - d3) * d2));
+        const float sphi[4] = {aux_sphi, -aux_sphi, -aux_sphi, aux_sphi};
+        for (int i = 0; i < 4; ++i) {
+            const double Rp[9] = {cphi, 0, sphi[i], 0, -1, 0, sphi[i], 0, -cphi};
+            mat_R(sv.U, s, Rp, sv.V, Rs[4 + i]);
+            const double tp[3] = {x1[i] * (d1 + d3), 0.0 * (d1 + d3), x3[i] * (d1 + d3)};
+            double tt[3];
+            for (int r = 0; r < 3; ++r) tt[r] = sv.U[r * 3] * tp[0] + sv.U[r * 3 + 1] * tp[1] + sv.U[r * 3 + 2] * tp[2];
+            const double nn = std::sqrt(tt[0] * tt[0] + tt[1] * tt[1] + tt[2] * tt[2]);
+            for (int r = 0; r < 3; ++r) ts[4 + i][r] = tt[r] / nn;
+        }
+        if (candidates)
+            for (int i = 0; i < 8; ++i) {
+                std::memcpy(candidates + 12 * i, Rs[i], 72);
+                std::memcpy(candidates + 12 * i + 9, ts[i], 24);
+            }
+        int bestGood = 0, secondBestGood = 0, bestIdx = -1;
+        float bestParallax = -1;
+        for (int i = 0; i < 8; ++i) {
+            double par = 0;
+            const int nGood = check_rt(n, px1, px2, Rs[i], ts[i], K, 4.0f * sigma2, true, good.data(), pts.data(), &par);
+            n_good[i] = nGood;
+            if (nGood > bestGood) {
+                secondBestGood = bestGood;
+                bestGood = nGood;
+                bestIdx = i;
+                bestParallax = (float)par;
+                std::memcpy(p3d, pts.data(), 24 * (size_t)n);
+                std::memcpy(triangulated, good.data(), n);
+            } else if (nGood > secondBestGood) {
+                secondBestGood = nGood;
+            }
+        }
+        *parallax_out = bestParallax;
+        if (secondBestGood < 0.75 * bestGood && bestParallax >= min_parallax && bestGood > min_triangulated && bestGood > ratio_h * n) {
+            std::memcpy(R21, Rs[bestIdx], 72);
+            std::memcpy(t21, ts[bestIdx], 24);
+            return 1;
+        }
+        std::memset(p3d, 0, 24 * (size_t)n);
+        std::memset(triangulated, 0, n);
+        return 0;
+    }
+    // ---- ReconstructF
+    double Kt[9], t1[9], E[9];
+    transpose3(Km, Kt);
+    mul3(Kt, model, t1);
+    mul3(t1, Km, E);
+    const Svd3 sv = svd3_sorted(E);
+    double tv[3] = {sv.U[2], sv.U[5], sv.U[8]};
+    {
+        const double nn = std::sqrt(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]);
+        for (int r = 0; r < 3; ++r) tv[r] = tv[r] / nn;
+    }
+    const double W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1}, Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    double Vt[9], R1[9], R2[9];
+    transpose3(sv.V, Vt);
+    mul3(sv.U, W, t1);
+    mul3(t1, Vt, R1);
+    if (det3(R1) < 0)
+        for (int k = 0; k < 9; ++k) R1[k] = -R1[k];
+    mul3(sv.U, Wt, t1);
+    mul3(t1, Vt, R2);
+    if (det3(R2) < 0)
+        for (int k = 0; k < 9; ++k) R2[k] = -R2[k];
+    const double tneg[3] = {-tv[0], -tv[1], -tv[2]};
+    const double* Rc[4] = {R1, R2, R1, R2};
+    const double* tc[4] = {tv, tv, tneg, tneg};
+    if (candidates)
+        for (int i = 0; i < 4; ++i) {
+            std::memcpy(candidates + 12 * i, Rc[i], 72);
+            std::memcpy(candidates + 12 * i + 9, tc[i], 24);
+        }
+    std::vector<std::vector<uint8_t>> goods(4, std::vector<uint8_t>(n));
+    std::vector<std::vector<double>> ptss(4, std::vector<double>(3 * (size_t)n));
+    int g[4];
+    double par[4];
+    for (int i = 0; i < 4; ++i) {
+        g[i] = check_rt(n, px1, px2, Rc[i], tc[i], K, 24.0f * sigma2, false, goods[i].data(), ptss[i].data(), &par[i]);
+        n_good[i] = g[i];
+    }
+    const int maxGood = std::max(g[0], std::max(g[1], std::max(g[2], g[3])));
+    const int minGood = std::max((int)(0.9 * N), min_triangulated);
+    int similar = 0;
+    for (int i = 0; i < 4; ++i)
+        if (g[i] > 0.7 * maxGood) ++similar;
+    if (maxGood < minGood || similar > 1) return 0;
+    for (int i = 0; i < 4; ++i)
+        if (maxGood == g[i]) {   // the reference's if / else-if chain: the first candidate with the maximum decides
+            *parallax_out = par[i];
+            if (par[i] > min_parallax) {
+                std::memcpy(p3d, ptss[i].data(), 24 * (size_t)n);
+                std::memcpy(triangulated, goods[i].data(), n);
+                std::memcpy(R21, Rc[i], 72);
+                std::memcpy(t21, tc[i], 24);
+                return 1;
+            }
+            return 0;
+        }
+    return 0;
 }

@@ -121,6 +121,13 @@ void ora_initializer_ransac(int n, const double* px1, const double* px2, int max
                             float* score_H, int32_t* best_H, uint8_t* inl_H, double* F21, float* score_F, int32_t* best_F, uint8_t* inl_F,
                             double* models);
 
+/* Initializer::ReconstructH (use_h != 0) / ReconstructF with CheckRT, Triangulate, DecomposeE (Initializer.cpp:330-675, 855-963) on
+ * the model TryInitialize chose; K = {fx, fy, cx, cy}; returns the function's bool; n_good[8] = CheckRT's count per candidate */
+int ora_initializer_reconstruct(int n, const double* px1, const double* px2, int use_h, const double* model, const uint8_t* inliers,
+                                const double* K, float sigma2, float min_parallax, int min_triangulated, double ratio_h, double* R21,
+                                double* t21, double* p3d, uint8_t* triangulated, int32_t* n_good, double* parallax,
+                                double* candidates /* may be NULL: 8 x 12 */);
+
 /* ---- patch alignment (src/Algorithm/CVUtils.cpp:186-318; Matcher.cpp:356-466) ----------- */
 int ora_align2d(const uint8_t* img, int w, int h, const uint8_t* ref_with_border /*100*/,
                 const uint8_t* ref /*64*/, int n_iter, double* u, double* v);

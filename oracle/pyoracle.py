@@ -371,6 +371,24 @@ class Oracle:
             out["models"] = mod
         return out
 
+    def initializer_reconstruct(self, px1, px2, use_h, model, inliers, K=(520.9, 521.0, 325.1, 249.7), sigma2=4.0, min_parallax=1.0,
+                                min_triangulated=8, ratio_h=0.9):
+        px1 = np.ascontiguousarray(px1, np.float64).reshape(-1, 2)
+        px2 = np.ascontiguousarray(px2, np.float64).reshape(-1, 2)
+        n = len(px1)
+        # the reference's camera keeps float intrinsics (Camera.h:14-22)
+        Kd = np.asarray(K, np.float32).astype(np.float64)
+        R, t, p3d = np.zeros(9), np.zeros(3), np.zeros((n, 3))
+        tri, ng, par, cand = np.zeros(n, np.uint8), np.zeros(8, np.int32), C.c_double(0), np.zeros((8, 12))
+        self.lib.ora_initializer_reconstruct.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                                         C.c_float, C.c_int, C.c_double] + [C.c_void_p] * 7
+        ok = self.lib.ora_initializer_reconstruct(n, _p(px1), _p(px2), int(bool(use_h)), _p(np.ascontiguousarray(model, np.float64).reshape(9)),
+                                                  _p(np.ascontiguousarray(inliers, np.uint8)), _p(Kd), C.c_float(sigma2), C.c_float(min_parallax),
+                                                  int(min_triangulated), C.c_double(ratio_h), _p(R), _p(t), _p(p3d), _p(tri), _p(ng),
+                                                  C.byref(par), _p(cand))
+        return dict(ok=bool(ok), R21=R.reshape(3, 3), t21=t, p3d=p3d, triangulated=tri.astype(bool), n_good=ng, parallax=par.value,
+                    candidates=cand)
+
     def depth_from_triangulation(self, T, f_ref, f_cur, det_th=1e-5):
         T = np.ascontiguousarray(T, np.float64).reshape(12)
         f_ref = np.ascontiguousarray(f_ref, np.float64).reshape(-1, 3)

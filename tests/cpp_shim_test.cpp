@@ -226,6 +226,13 @@ int main(int argc, char** argv) {
         for (bool v : init._inliers_F) nf += v;
         printf("initializer pairs %zu use_h %d score_h %.3f score_f %.3f inl_h %d inl_f %d f22 %.9e\n", q1.size(), (int)use_h, init._score_H,
                init._score_F, nh, nf, init._F21(2, 2));
+        Initializer full;
+        const bool ok = full.TryInitialize(q1, q2, &f1, &f2);
+        double T21[12];
+        full._T21.matrix3x4(T21);
+        int n_tri = 0;
+        for (bool v : full._inliers) n_tri += v;
+        printf("try_initialize ok %d triangulated %d t21 %.9e %.9e %.9e r00 %.9e\n", (int)ok, ok ? n_tri : 0, T21[3], T21[7], T21[11], T21[0]);
     }
     return 0;
 }

@@ -95,3 +95,12 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     assert int(il[10]) == int(ro["inliers_H"].sum()) and int(il[12]) == int(ro["inliers_F"].sum())
     assert il[14] == "%.9e" % ro["F21"][2, 2]
     assert int(il[4]) == int(ro["score_H"] / (ro["score_H"] + ro["score_F"]) > 0.4)
+    # Initializer::TryInitialize end to end (model choice + ReconstructF / ReconstructH)
+    use_h = bool(ro["score_H"] / (ro["score_H"] + ro["score_F"]) > 0.4)
+    rq = oracle.initializer_reconstruct(m1, m2, use_h, ro["H21"] if use_h else ro["F21"], ro["inliers_H"] if use_h else ro["inliers_F"])
+    tl = lines[11].split()
+    assert tl[0] == "try_initialize" and int(tl[2]) == int(rq["ok"])
+    assert int(tl[4]) == (int(rq["triangulated"].sum()) if rq["ok"] else 0)
+    if rq["ok"]:
+        # quaternion round trip inside the shim's SE3: compare with a tolerance
+        assert np.allclose([float(tl[6]), float(tl[7]), float(tl[8])], rq["t21"], atol=1e-9) and abs(float(tl[10]) - rq["R21"][0, 0]) < 1e-9

@@ -129,6 +129,57 @@ def test_oracle_without_a_scoring_model(ora):
         assert not r["H21"].any() and not r["inliers_H"].any()
 
 
+def planar_scene(seed, n=300, noise=0.0):
+    rng = np.random.default_rng(seed)
+    X = np.c_[rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), np.zeros(n)]
+    X[:, 2] = 5.0 + 0.3 * X[:, 0]
+    th = 0.1
+    R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    t = np.array([1.5, 0.2, 0.3])
+
+    def proj(Rm, tv):
+        Y = (Rm @ X.T).T + tv
+        return (K @ (Y / Y[:, 2:]).T).T[:, :2]
+
+    return proj(np.eye(3), np.zeros(3)), proj(R, t) + rng.normal(0, noise, (n, 2)), R, t, X
+
+
+def test_oracle_reconstruct_f_recovers_pose_and_structure(ora):
+    """ReconstructF / DecomposeE / CheckRT / Triangulate (Initializer.cpp:515-675, 855-963) on a general scene."""
+    p1, p2, R, t, n_out = two_view(0, noise=0.2)
+    r = ora.initializer_ransac(p1, p2, ora.initializer_sets(len(p1), 200))
+    q = ora.initializer_reconstruct(p1, p2, 0, r["F21"], r["inliers_F"])
+    assert q["ok"]
+    assert np.linalg.norm(q["R21"] - R) < 0.01 and abs(np.linalg.det(q["R21"]) - 1) < 1e-12
+    assert np.linalg.norm(q["t21"] - t / np.linalg.norm(t)) < 0.1 and abs(np.linalg.norm(q["t21"]) - 1) < 1e-12
+    assert q["n_good"][:4].argmax() == int(np.flatnonzero(q["n_good"][:4] == q["n_good"][:4].max())[0])
+    assert sorted(q["n_good"][:4])[-2] < 0.7 * q["n_good"][:4].max()          # an unambiguous winner among the four candidates
+    tri = q["triangulated"]
+    assert tri[n_out:].mean() > 0.9
+    # the triangulated points reproject onto their pixels in both views (scale = |t| = 1)
+    X1 = q["p3d"][tri]
+    u1 = (K @ (X1 / X1[:, 2:]).T).T[:, :2]
+    Y = (q["R21"] @ X1.T).T + q["t21"]
+    u2 = (K @ (Y / Y[:, 2:]).T).T[:, :2]
+    assert np.median(np.linalg.norm(u1 - p1[tri], axis=1)) < 1.0 and np.median(np.linalg.norm(u2 - p2[tri], axis=1)) < 1.0
+    assert q["parallax"] > 1.0
+
+
+def test_oracle_reconstruct_h_candidates(ora):
+    """ReconstructH (Initializer.cpp:330-513): Faugeras' eight candidates contain the true motion exactly on a noise-free plane;
+    a plane seen entirely in front of both cameras leaves the classical two-fold ambiguity, which the reference's
+    `secondBestGood < 0.75 bestGood` test rejects."""
+    p1, p2, R, t, _ = planar_scene(0)
+    r = ora.initializer_ransac(p1, p2, ora.initializer_sets(len(p1), 200))
+    q = ora.initializer_reconstruct(p1, p2, 1, r["H21"], r["inliers_H"])
+    errs = [np.linalg.norm(c[:9].reshape(3, 3) - R) + np.linalg.norm(c[9:] - t / np.linalg.norm(t)) for c in q["candidates"]]
+    assert min(errs) < 1e-6
+    for c in q["candidates"]:
+        assert abs(np.linalg.det(c[:9].reshape(3, 3)) - 1) < 1e-6 and abs(np.linalg.norm(c[9:]) - 1) < 1e-9   # (float cos / sin in the reference)
+    assert sorted(q["n_good"])[-1] == len(p1) and sorted(q["n_good"])[-2] == len(p1) and not q["ok"]
+    assert not q["triangulated"].any() and not q["R21"].any()
+
+
 # ---- CUDA path -------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_gpu_ransac_is_bit_exact(ora):
@@ -162,4 +213,33 @@ def test_gpu_ransac_rejects_bad_input(ora):
     bad[0, 1, 2] = 20
     with pytest.raises(YgzbError):
         ctx.initializer_ransac([0, 20], p, p, bad)                                             # set index out of range
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reconstruct_is_bit_exact(ora):
+    from ygz_slam_b200 import Context
+    lists = []
+    for seed, planar, use_h in ((0, False, 0), (2, False, 0), (1, True, 1), (0, False, 1), (7, False, 0)):
+        p1, p2 = (planar_scene(seed, noise=0.2)[:2] if planar else two_view(seed, n=300 + 37 * seed, noise=0.2)[:2])
+        r = ora.initializer_ransac(p1, p2, ora.initializer_sets(len(p1), 200))
+        lists.append((p1, p2, use_h, r["H21"] if use_h else r["F21"], r["inliers_H"] if use_h else r["inliers_F"]))
+    lists.append(planar_scene(3)[:2] + (1, np.eye(3), np.ones(300, bool)))                       # degenerate H: d1/d2 < 1.00001 -> false
+    offsets = np.r_[0, np.cumsum([len(l[0]) for l in lists])].astype(np.int32)
+    ctx = Context(0)
+    g = ctx.initializer_reconstruct(offsets, np.concatenate([l[0] for l in lists]), np.concatenate([l[1] for l in lists]), [l[2] for l in lists],
+                                    np.stack([l[3] for l in lists]), np.concatenate([l[4] for l in lists]))
+    n_ok = 0
+    for q, l in enumerate(lists):
+        o = ora.initializer_reconstruct(*l)
+        a, b = offsets[q], offsets[q + 1]
+        assert bool(g["ok"][q]) == o["ok"], q
+        assert np.array_equal(g["n_good"][q], o["n_good"]), q
+        assert np.array_equal(g["candidates"][q].view(np.uint64), o["candidates"].view(np.uint64)), q
+        assert np.array_equal(g["R21"][q], o["R21"]) and np.array_equal(g["t21"][q], o["t21"]), q
+        assert np.array_equal(g["p3d"][a:b].view(np.uint64), o["p3d"].view(np.uint64)), q
+        assert np.array_equal(g["triangulated"][a:b], o["triangulated"]), q
+        assert abs(g["parallax"][q] - o["parallax"]) <= 1e-4 * max(1.0, abs(o["parallax"])), q      # acosf vs glibc acosf
+        n_ok += int(o["ok"])
+    assert n_ok >= 3
     ctx.close()

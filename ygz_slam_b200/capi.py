@@ -38,7 +38,7 @@ EXPORTS = [
     "ygzb_frames_upload", "ygzb_frames_copy", "ygzb_frames_build_pyramid", "ygzb_frames_layout", "ygzb_frames_device_ptr",
     "ygzb_frames_download_level", "ygzb_detect", "ygzb_grid_dims", "ygzb_describe", "ygzb_fast_debug",
     "ygzb_detect_stats", "ygzb_match_bf", "ygzb_match_frames", "ygzb_hamming_pairs", "ygzb_search_for_triangulation", "ygzb_depth_from_triangulation",
-    "ygzb_vocab_create", "ygzb_vocab_destroy", "ygzb_vocab_info", "ygzb_bow_transform", "ygzb_search_by_bow", "ygzb_initializer_ransac", "ygzb_align2d", "ygzb_align1d",
+    "ygzb_vocab_create", "ygzb_vocab_destroy", "ygzb_vocab_info", "ygzb_bow_transform", "ygzb_search_by_bow", "ygzb_initializer_ransac", "ygzb_initializer_reconstruct", "ygzb_align2d", "ygzb_align1d",
     "ygzb_project_align", "ygzb_sparse_align", "ygzb_default_ba_params", "ygzb_local_ba", "ygzb_local_ba_ceres", "ygzb_two_view_ba", "ygzb_pose_only",
     "ygzb_default_klt_params", "ygzb_klt",
     "ygzb_tracker_create", "ygzb_tracker_destroy", "ygzb_tracker_set_depth", "ygzb_tracker_upload", "ygzb_tracker_track", "ygzb_tracker_make_keyframes",
@@ -611,6 +611,25 @@ def _initializer_ransac(self, offsets, px1, px2, sets, sigma=2.0, models=False):
     return out
 
 
+def _initializer_reconstruct(self, offsets, px1, px2, use_h, model, inliers, sigma2=4.0, min_parallax=1.0, min_triangulated=8, ratio_h=0.9):
+    """Batched Initializer::ReconstructH / ReconstructF on the chosen models."""
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    P, N = len(offsets) - 1, int(offsets[-1])
+    ok, R, t = np.zeros(P, np.int32), np.zeros((P, 9)), np.zeros((P, 3))
+    p3d, tri, ng, par, cand = np.zeros((N, 3)), np.zeros(N, np.uint8), np.zeros((P, 8), np.int32), np.zeros(P), np.zeros((P, 8, 12))
+    self.lib.ygzb_initializer_reconstruct.argtypes = ([C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_int, C.c_double]
+                                                      + [C.c_void_p] * 8)
+    self.check(self.lib.ygzb_initializer_reconstruct(self.h, P, _p(offsets), _p(np.ascontiguousarray(px1, np.float64)),
+                                                     _p(np.ascontiguousarray(px2, np.float64)), _p(np.ascontiguousarray(use_h, np.int32)),
+                                                     _p(np.ascontiguousarray(model, np.float64).reshape(P, 9)),
+                                                     _p(np.ascontiguousarray(inliers, np.uint8)), C.c_float(sigma2), C.c_float(min_parallax),
+                                                     int(min_triangulated), C.c_double(ratio_h), _p(ok), _p(R), _p(t), _p(p3d), _p(tri), _p(ng),
+                                                     _p(par), _p(cand)), "ygzb_initializer_reconstruct")
+    return dict(ok=ok.astype(bool), R21=R.reshape(P, 3, 3), t21=t, p3d=p3d, triangulated=tri.astype(bool), n_good=ng, parallax=par,
+                candidates=cand)
+
+
+Context.initializer_reconstruct = _initializer_reconstruct
 Context.initializer_ransac = _initializer_ransac
 Context.search_by_bow = _search_by_bow
 Context.vocabulary = lambda self, data: Vocabulary(self, data)

@@ -734,15 +734,17 @@ class Tracker {  // include/ygz/Algorithm/Tracker.h:11-76
     TrackerStatusType _status = TRACK_NOT_READY;
 };
 
-// include/ygz/Algorithm/Initializer.h:27-145 -- the RANSAC half (FindHomography / FindFundamental and the model choice of
-// TryInitialize, src/Algorithm/Initializer.cpp:9-78); ReconstructH / ReconstructF (pose + structure from the chosen model) are
-// not part of the device path yet
+// include/ygz/Algorithm/Initializer.h:27-145: TryInitialize (src/Algorithm/Initializer.cpp:9-87) = the RANSAC over 200 minimal
+// sets for H and F, the model choice, and ReconstructH / ReconstructF (pose + structure), all on the device
 class Initializer {
   public:
     struct Option {
         float _sigma = 2.0f;    // Initializer.h:45
         float _sigma2 = 4.0f;
         int _max_iter = 200;    // Initializer.h:47
+        double _min_parallex = 1.0;
+        int _min_triangulated_pts = 8;
+        double good_point_ratio_H = 0.9;
     } _options;
     struct Matrix3 { double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; double operator()(int r, int c) const { return m[3 * r + c]; } };
     // the minimal sets of TryInitialize (:25-49): a default-constructed cv::RNG (multiply-with-carry, state 0xffffffff,
@@ -784,9 +786,45 @@ class Initializer {
         const float rh = _score_H / (_score_H + _score_F);   // :66
         return rh > 0.4f;
     }
+    // Initializer.cpp:9-87.  The camera is the runtime's (ygzb_params); `ref` / `curr` are kept like the reference does.
+    bool TryInitialize(std::vector<Vector2d>& px1, std::vector<Vector2d>& px2, Frame* ref, Frame* curr) {
+        _ref = ref;
+        _curr = curr;
+        const bool use_h = FindModels(px1, px2);
+        auto& rt = b200::Runtime::Get();
+        const int n = (int)px1.size();
+        std::vector<double> a(2 * (size_t)n), b(2 * (size_t)n), p3d(3 * (size_t)n);
+        std::vector<uint8_t> inl(n), tri(n);
+        for (int i = 0; i < n; ++i) {
+            a[2 * i] = px1[i][0]; a[2 * i + 1] = px1[i][1];
+            b[2 * i] = px2[i][0]; b[2 * i + 1] = px2[i][1];
+            inl[i] = (use_h ? _inliers_H[i] : _inliers_F[i]) ? 1 : 0;
+        }
+        const int32_t off[2] = {0, n}, uh = use_h ? 1 : 0;
+        int32_t ok = 0, n_good[8];
+        double R[9], t[3], parallax = 0;
+        rt.Check(ygzb_initializer_reconstruct(rt.ctx(), 1, off, a.data(), b.data(), &uh, use_h ? _H21.m : _F21.m, inl.data(), _options._sigma2,
+                                              (float)_options._min_parallex, _options._min_triangulated_pts, _options.good_point_ratio_H, &ok, R, t,
+                                              p3d.data(), tri.data(), n_good, &parallax, nullptr), "ygzb_initializer_reconstruct");
+        const double Rt[12] = {R[0], R[1], R[2], t[0], R[3], R[4], R[5], t[1], R[6], R[7], R[8], t[2]};
+        _T21 = ok ? SE3::from3x4(Rt) : SE3();
+        _inliers.assign(n, true);
+        if (!ok) return false;
+        _pts_triangulated.resize(n);
+        for (int i = 0; i < n; ++i) {
+            _inliers[i] = tri[i] != 0;
+            _pts_triangulated[i] = Vector3d(p3d[3 * i], p3d[3 * i + 1], p3d[3 * i + 2]);
+        }
+        return true;
+    }
     Matrix3 _H21, _F21;
     float _score_H = 0, _score_F = 0;
     std::vector<bool> _inliers_H, _inliers_F;
+    std::vector<bool> _inliers;                  // Initializer.h:118
+    std::vector<Vector3d> _pts_triangulated;     // Initializer.h:119
+    SE3 _T21;                                    // Initializer.h:120
+    Frame* _ref = nullptr;
+    Frame* _curr = nullptr;
 };
 
 namespace ba {  // include/ygz/Algorithm/BA.h:23-66
