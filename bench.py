@@ -29,6 +29,14 @@ torch.distributed (NCCL) only for the barrier, the max-over-ranks of the device 
 """
 from __future__ import annotations
 
+import os as _os
+
+# Every engine thread owns two CUDA streams (tracking chain + upload / alignment); with the default 8 hardware work queues
+# ("connections") the streams of several threads share a queue and falsely serialise behind each other -- measured: 8 host
+# threads 22k tracked frames/s with 8 connections, 28.6k with 32, and the rare 5x slow legs disappear.  Must be set before the
+# CUDA context exists, i.e. before torch / the library touch the device.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import argparse
 import json
 import os
@@ -502,14 +510,18 @@ def vo_line(args, rank, world, local_rank):
     stacked = vo_native.stack_pinned([d[0] for d in data])
     depths = [d[1] for d in data]
     # host threads (= ygzb contexts = CUDA streams): every thread drives a latency-bound chain of kernels for its streams and the
-    # chains of different threads overlap on the GPU.  Measured on one B200, 8 streams: 2 / 4 / 6 / 8 threads -> 25.8k / 27.7k /
-    # 27.7k / 24.0k frames/s; 32 streams: 8 / 12 / 16 threads -> 40.4k / 36.9k / collapse (the threads spin in
-    # cudaStreamSynchronize: 16 spinning threads on a 16-CPU cgroup quota get throttled).  Default: one thread per two streams,
-    # at most half of the CPUs this rank may use.
+    # chains of different threads overlap on the GPU.  Measured on one B200 with 32 hardware work queues (see the top of this
+    # file), 8 streams: 4 / 8 threads -> 27.4k / 29.9k frames/s; 16 streams: 8 / 16 threads -> 36.6k / 38.8k; 32 streams: 8 / 16
+    # threads -> 41.0k / 40.1k.  Default: one thread per stream, at most 8, and no more than the CPUs this rank may use.
     if args.vo_threads > 0:
         threads = max(1, min(args.vo_threads, S))
     else:
-        threads = max(1, min(max(1, S // 2), 8, max(2, usable_threads()[0] // (2 * max(world, 1)))))
+        threads = max(1, min(S, 8, max(2, usable_threads()[0] // max(world, 1))))
+    # the engine threads spin in their one synchronisation per round; when the threads of all ranks outnumber the CPUs this job
+    # may use (a small cgroup quota under an 8-GPU run), they sleep on a blocking event instead
+    cpus = usable_threads()[0]
+    blocking = {"on": True, "off": False}.get(args.vo_sync, world * (threads + 1) > cpus)
+    os.environ["YGZ_VO_BLOCKING_SYNC"] = "1" if blocking else "0"
     ctx = Context(local_rank)
 
     def barrier():
@@ -701,7 +713,8 @@ def vo_line(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": main_roof, "roofline_kernels": roof, "kernel_shares": shares,
             "cpu_baseline": cpu,
-            "engine": {"host_threads_per_gpu": threads, "frames_in_flight_per_stream": args.vo_window,
+            "engine": {"host_threads_per_gpu": threads, "frames_in_flight_per_stream": args.vo_window, "blocking_sync": bool(blocking),
+                       "usable_cpus": cpus,
                        "note": "device-resident engine (ygzb_tracker_*: local map, candidate projection, key-frame insertion, BA assembly on "
                                "the device), host loop in C++ (ygz_slam_b200/host/vo_driver.cpp), one ygzb context (CUDA stream) per host "
                                "thread; a round enqueues for every stream the frames up to the first possible key-frame; resident leg wall "
@@ -1028,6 +1041,8 @@ def main() -> None:
     ap.add_argument("--vo-threads", type=int, default=0,
                     help="vo: host threads (= ygzb contexts = CUDA streams) per GPU; 0 = one per stream, capped by the usable CPUs per rank")
     ap.add_argument("--vo-window", type=int, default=8, help="vo: frames of one stream that may be in flight per round (1 = latency mode)")
+    ap.add_argument("--vo-sync", default="auto", choices=["auto", "on", "off"],
+                    help="vo: blocking (sleeping) synchronisation of the engine threads; auto = only when they outnumber the usable CPUs")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the CPUs local to its GPU")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (C2, C3, C4) of the N=1 run")
     ap.add_argument("--batch", type=int, default=512, help="extract_match: frames per step per GPU")

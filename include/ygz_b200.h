@@ -55,6 +55,9 @@ int ygzb_create(int device, const ygzb_params* p, ygzb_ctx** out);
 void ygzb_destroy(ygzb_ctx* ctx);
 const char* ygzb_last_error(const ygzb_ctx* ctx);
 int ygzb_synchronize(ygzb_ctx* ctx);
+/* the same, but the calling thread sleeps on a blocking event instead of spinning: for hosts where more threads wait on
+ * the GPU than there are CPUs to spin on (a few tens of microseconds of extra wake-up latency per call) */
+int ygzb_synchronize_blocking(ygzb_ctx* ctx);
 /* the context's cudaStream_t, for callers that time or order work themselves */
 void* ygzb_stream(ygzb_ctx* ctx);
 /* device time between two points of the context's stream (CUDA events): start records an event, stop records a second

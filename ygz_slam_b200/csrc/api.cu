@@ -241,6 +241,7 @@ void ygzb_destroy(ygzb_ctx* ctx) {
     }
     for (cudaEvent_t e : ctx->timer)
         if (e) cudaEventDestroy(e);
+    if (ctx->block_ev) cudaEventDestroy(ctx->block_ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -250,6 +251,17 @@ const char* ygzb_last_error(const ygzb_ctx* ctx) { return ctx ? ctx->err : "null
 int ygzb_synchronize(ygzb_ctx* ctx) {
     if (!ctx) return YGZB_ERR_INVALID;
     YGZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return YGZB_OK;
+}
+
+// waits on a cudaEventBlockingSync event recorded behind everything enqueued so far: the calling thread sleeps instead of
+// spinning (cudaStreamSynchronize spins under the default scheduling flags) -- for hosts with fewer CPUs than waiting threads
+int ygzb_synchronize_blocking(ygzb_ctx* ctx) {
+    if (!ctx) return YGZB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!ctx->block_ev) YGZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->block_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    YGZB_CUDA(ctx, cudaEventRecord(ctx->block_ev, ctx->stream));
+    YGZB_CUDA(ctx, cudaEventSynchronize(ctx->block_ev));
     return YGZB_OK;
 }
 

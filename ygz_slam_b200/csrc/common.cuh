@@ -64,6 +64,7 @@ struct ygzb_ctx {
     int prof_on;
     void* prof;  // std::vector<ygzb::ProfRec>*
     cudaEvent_t timer[2];   // ygzb_timer_start / ygzb_timer_stop
+    cudaEvent_t block_ev;   // ygzb_synchronize_blocking (created on first use)
 };
 
 struct ygzb_frames {

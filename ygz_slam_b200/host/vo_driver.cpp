@@ -541,7 +541,12 @@ struct EStream {
 class Engine {
     struct Win { int stream, first, count, job0; };   // a window in flight: frames [first, first + count) of a stream (job0 < 0: first frame)
   public:
-    Engine(ygzb_ctx* ctx, int n_streams, int window, const Params& p) : ctx_(ctx), S_(n_streams), F_(std::max(1, window)), prm_(p), st_(n_streams) {}
+    Engine(ygzb_ctx* ctx, int n_streams, int window, const Params& p) : ctx_(ctx), S_(n_streams), F_(std::max(1, window)), prm_(p), st_(n_streams) {
+        // YGZ_VO_BLOCKING_SYNC=1: sleep instead of spinning in the one synchronisation per round (hosts with fewer CPUs than
+        // engine threads; bench.py sets it when the threads of all ranks outnumber the CPUs it may use)
+        const char* e = std::getenv("YGZ_VO_BLOCKING_SYNC");
+        blocking_sync_ = e && std::atoi(e) != 0;
+    }
     ~Engine() {
         if (tr_) ygzb_tracker_destroy(tr_);
         if (fr_) ygzb_frames_destroy(fr_);
@@ -694,7 +699,7 @@ class Engine {
             // ---- 4. one synchronisation per round; key-frame results
             {
                 StageTimer tm(kTPoseOnly);
-                CHK(ygzb_synchronize(ctx_));
+                CHK(blocking_sync_ ? ygzb_synchronize_blocking(ctx_) : ygzb_synchronize(ctx_));
             }
             for (size_t q = 0; q < kjobs.size(); ++q) {
                 const ygzb_keyframe_job& kj = kjobs[q];
@@ -757,6 +762,7 @@ class Engine {
     ygzb_keyframe_result* h_kres_ = nullptr;
     ygzb_ba_params ba_;
     std::vector<Win> wins_;
+    bool blocking_sync_ = false;
 };
 
 }  // namespace
