@@ -988,8 +988,36 @@ __global__ void __launch_bounds__(128) track_project_kernel(const uint8_t* __res
 
 // ordered compaction of the successfully projected candidates of job blockIdx.x (candidate order = local key-frame, then
 // feature: the order in which the reference's caller loops hand them to OptimizeCurrentPoseOnly)
+// inclusive scan of one int per thread over a 1024-thread CTA (shuffles + one pass over the 32 warp totals: two barriers
+// instead of the twenty of a shared-memory Hillis-Steele scan); s_w = 33 ints; *total = the CTA total
+__device__ __forceinline__ int block_scan_1024(int v, int* s_w, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += u;
+    }
+    if (lane == 31) s_w[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += u;
+        }
+        s_w[lane] = w;
+        if (lane == 31) s_w[32] = w;
+    }
+    __syncthreads();
+    const int out = v + (warp ? s_w[warp - 1] : 0);
+    *total = s_w[32];
+    __syncthreads();
+    return out;
+}
+
 __global__ void __launch_bounds__(1024) track_compact_kernel(TrackStore st, TrackBatch b) {
-    __shared__ int s_scan[1024];
+    __shared__ int s_scan[33];
     __shared__ int s_carry;
     const int j = blockIdx.x, tid = threadIdx.x;
     const ygzb_track_job job = b.jobs[j];
@@ -999,16 +1027,10 @@ __global__ void __launch_bounds__(1024) track_compact_kernel(TrackStore st, Trac
     for (int base = 0; base < total; base += 1024) {
         const int c = base + tid;
         const int flag = (c < total && b.cand_ok[(size_t)j * b.cap + c]) ? 1 : 0;
-        s_scan[tid] = flag;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int v = tid >= o ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
+        int chunk_total;
+        const int incl = block_scan_1024(flag, s_scan, &chunk_total);
         if (flag) {
-            const size_t dst = (size_t)j * b.cap + s_carry + s_scan[tid] - 1;
+            const size_t dst = (size_t)j * b.cap + s_carry + incl - 1;
             const int k = c / st.cells, f = c - k * st.cells;
             const size_t fe = (size_t)(job.stream * st.R + job.entry[k]) * st.cells + f;
             b.c_src[dst] = c;
@@ -1019,7 +1041,7 @@ __global__ void __launch_bounds__(1024) track_compact_kernel(TrackStore st, Trac
             b.c_pw[3 * dst + 2] = st.kf_pw[3 * fe + 2];
         }
         __syncthreads();
-        if (tid == 1023) s_carry += s_scan[1023];
+        if (tid == 0) s_carry += chunk_total;
         __syncthreads();
     }
     if (tid == 0) b.c_cnt[j] = s_carry;

@@ -81,6 +81,34 @@ __global__ void track_finish_kernel(TrackBatch b) {
     b.results[j] = r;
 }
 
+// inclusive scan of one int per thread over a 1024-thread CTA: shuffles inside the warps, the 32 warp totals scanned by warp 0
+// (two barriers instead of the twenty of a shared-memory Hillis-Steele scan); s_w = 33 ints; returns the CTA total in *total
+__device__ __forceinline__ int block_scan_1024(int v, int* s_w, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += u;
+    }
+    if (lane == 31) s_w[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += u;
+        }
+        s_w[lane] = w;
+        if (lane == 31) s_w[32] = w;
+    }
+    __syncthreads();
+    const int out = v + (warp ? s_w[warp - 1] : 0);
+    *total = s_w[32];
+    __syncthreads();   // s_w may be rewritten by the next call
+    return out;
+}
+
 // SetKeyframe for job blockIdx.x: the features Detect left in the frame slot's store become the key-frame's features and
 // map points (depth image -> camera point -> world, VisualOdometry.cpp:182-218 with the depth initialisation of
 // test/test_feature_alignment.cpp:72-85), the inlier observations of its tracking job become its observations of older points
@@ -130,23 +158,17 @@ __global__ void __launch_bounds__(1024) kf_fill_kernel(TrackStore st, TrackBatch
             const int q = base + tid;
             const size_t at = (size_t)tj * b.cap + q;
             const int flag = (q < cnt && b.inlier[at]) ? 1 : 0;
-            s_scan[tid] = flag;
-            __syncthreads();
-            for (int o = 1; o < 1024; o <<= 1) {
-                const int v = tid >= o ? s_scan[tid - o] : 0;
-                __syncthreads();
-                s_scan[tid] += v;
-                __syncthreads();
-            }
+            int chunk_total;
+            const int incl = block_scan_1024(flag, s_scan, &chunk_total);
             if (flag) {
-                const size_t dst = (size_t)e * b.cap + s_carry + s_scan[tid] - 1;
+                const size_t dst = (size_t)e * b.cap + s_carry + incl - 1;
                 const int c = b.c_src[at], k = c / st.cells, f = c - k * st.cells;
                 st.kf_obs_id[dst] = st.kf_mp0[job.stream * st.R + job.entry[k]] + f;
                 st.kf_obs_px[2 * dst] = b.c_px[2 * at];
                 st.kf_obs_px[2 * dst + 1] = b.c_px[2 * at + 1];
             }
             __syncthreads();
-            if (tid == 1023) s_carry += s_scan[1023];
+            if (tid == 0) s_carry += chunk_total;
             __syncthreads();
         }
         total = s_carry;
@@ -211,16 +233,10 @@ __global__ void __launch_bounds__(1024) ba_build_kernel(TrackStore st, const ygz
         }
         const int keep = deg >= 2 ? 1 : 0;
         const int packed = keep | ((keep ? deg : 0) << 14);
-        s_scan[tid] = packed;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int v = tid >= o ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
+        int chunk_total;
+        const int incl_all = block_scan_1024(packed, s_scan, &chunk_total);
         if (keep) {
-            const int incl = s_scan[tid];
+            const int incl = incl_all;
             const int pt = s_cpt + (incl & 0x3FFF) - 1, ob = s_cobs + (incl >> 14) - deg;
             const size_t P = (size_t)p0 + pt, fe = (size_t)e[k] * st.cells + g;
             B.pts[3 * P] = st.kf_pw[3 * fe];
@@ -243,9 +259,9 @@ __global__ void __launch_bounds__(1024) ba_build_kernel(TrackStore st, const ygz
             }
         }
         __syncthreads();
-        if (tid == 1023) {
-            s_cpt += s_scan[1023] & 0x3FFF;
-            s_cobs += s_scan[1023] >> 14;
+        if (tid == 0) {
+            s_cpt += chunk_total & 0x3FFF;
+            s_cobs += chunk_total >> 14;
         }
         __syncthreads();
     }
