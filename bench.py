@@ -519,7 +519,8 @@ def vo_line(args, rank, world, local_rank):
         threads = max(1, min(S, 8, max(2, usable_threads()[0] // max(world, 1))))
     # the engine threads spin in their one synchronisation per round; when the threads of all ranks outnumber the CPUs this job
     # may use (a small cgroup quota under an 8-GPU run), they sleep on a blocking event instead
-    cpus = usable_threads()[0]
+    _, _, quota = usable_threads()
+    cpus = int(min(os.cpu_count() or 1, quota if quota else 1e9))   # what the whole job (all ranks) may use: all CPUs or the cgroup quota
     blocking = {"on": True, "off": False}.get(args.vo_sync, world * (threads + 1) > cpus)
     os.environ["YGZ_VO_BLOCKING_SYNC"] = "1" if blocking else "0"
     ctx = Context(local_rank)
