@@ -87,3 +87,22 @@ def test_c_example_runs(tmp_path):
     words = r.stdout.replace(",", "").split()
     n1, n2, matches, good = int(words[1]), int(words[3]), int(words[6]), int(words[9])
     assert n1 > 200 and n2 > 200 and matches > 100 and 0 < good <= matches
+
+
+@pytest.mark.gpu
+def test_blocking_synchronize():
+    """ygzb_synchronize_blocking (sleeping wait on a blocking event) completes the same work as ygzb_synchronize."""
+    import ctypes as C
+    import numpy as np
+    from ygz_slam_b200 import Context, synth
+    ctx = Context(0)
+    fr = ctx.frames(1)
+    fr.upload(synth.stream_frame(1)[0][None])
+    ctx.lib.ygzb_synchronize_blocking.argtypes = [C.c_void_p]
+    for _ in range(3):
+        assert ctx.lib.ygzb_synchronize_blocking(ctx.h) == 0
+    feats = fr.detect([0])
+    assert ctx.lib.ygzb_synchronize_blocking(ctx.h) == 0 and feats[0]["n"] > 1000
+    assert ctx.lib.ygzb_synchronize_blocking(None) != 0
+    fr.close()
+    ctx.close()

@@ -43,6 +43,24 @@ def test_local_ba_c4_matches_oracle(ctx3, oracle, huber):
     assert np.abs(est - sc["poses_true"]).max() < 0.01   # and it is the right answer
 
 
+@pytest.mark.parametrize("n_kf", [2, 3, 4, 12])
+def test_local_ba_every_solver_path(ctx3, oracle, n_kf, monkeypatch):
+    """The reduced system is solved by one lane in registers (1 or 2 free poses), by one warp (up to 4), by the whole CTA in 6 x 6
+    blocks (up to 11) or by the scalar CTA factorisation (more); YGZB_BA_SOLVER=1 forces the scalar LDL^T everywhere."""
+    sc = synth.ba_scene(n_kf=n_kf, n_pt=400, target_obs=400 * min(n_kf, 4), seed=20 + n_kf)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[0] = 1
+    n_obs = len(sc["kf_idx"])
+    wP, wX, _, wst = oracle.local_ba(_g2o(sc["poses_noisy"]), fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"], sc["px"])
+    for solver in ("0", "1"):
+        monkeypatch.setenv("YGZB_BA_SOLVER", solver)
+        P, X, _, st = ctx3.local_ba([0, n_kf], [0, 400], [0, n_obs], _g2o(sc["poses_noisy"]), fixed, sc["pts_noisy"], sc["kf_idx"], sc["pt_idx"],
+                                    sc["px"])
+        assert abs(st[0]["chi2_final"] - wst["chi2_final"]) < 1e-6 * wst["chi2_final"], (n_kf, solver)
+        if n_kf > 2:   # (two views fix the scale only through the fixed pose's points: compare the cost there, not the gauge)
+            assert _pose_diff(P, wP) < 1e-4 and np.abs(X - wX).max() < 1e-4, (n_kf, solver)
+
+
 def test_local_ba_batched_and_fixed_observers(ctx3, oracle):
     """Two problems in one launch; the second has two fixed keyframes (non-local observers, BA.cpp:458-492)."""
     a = synth.ba_scene(n_kf=10, n_pt=2000, target_obs=8000, seed=11)
