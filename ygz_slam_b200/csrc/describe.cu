@@ -232,6 +232,8 @@ __device__ __forceinline__ void describe_one(const LevelView& v, int cx, int cy,
 }
 
 // features of the slot store (written by merge_cells_kernel): level coordinates are integers
+template <int kFPW>   // features per warp: 4 amortises the table staging over big batches, 1 keeps a small batch (the key-frames of
+                      // one tracking round) one feature deep
 __global__ void __launch_bounds__(256) describe_store_kernel(const uint8_t* __restrict__ pyr, size_t slot_stride,
                                                              const int32_t* __restrict__ slots, Geometry g,
                                                              const int32_t* __restrict__ count,
@@ -241,12 +243,12 @@ __global__ void __launch_bounds__(256) describe_store_kernel(const uint8_t* __re
     __shared__ __align__(16) DescribeSmem sm;
     const int slot = slots[blockIdx.y];
     const int n = count[slot];
-    if (blockIdx.x * (8 * kFeatPerWarp) >= n) return;  // most CTAs of the capacity-sized grid have no feature
+    if (blockIdx.x * (8 * kFPW) >= n) return;  // most CTAs of the capacity-sized grid have no feature
     stage_tables(sm);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int r = 0; r < kFeatPerWarp; ++r) {
-        const int i = blockIdx.x * (8 * kFeatPerWarp) + r * 8 + warp;
+    for (int r = 0; r < kFPW; ++r) {
+        const int i = blockIdx.x * (8 * kFPW) + r * 8 + warp;
         if (i >= n) return;
         const size_t o = (size_t)slot * g.n_cells + i;
         const int L = flevel[o];
@@ -290,10 +292,16 @@ __global__ void __launch_bounds__(256) describe_list_kernel(const uint8_t* __res
 int launch_describe_store(ygzb_frames* f, int n) {
     ygzb_ctx* ctx = f->ctx;
     const Geometry& g = ctx->geo;
-    dim3 grid((g.n_cells + 8 * kFeatPerWarp - 1) / (8 * kFeatPerWarp), n);
     ProfScope ps(ctx, kStageDescribe);
-    describe_store_kernel<<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, f->d_slots, g, f->d_count, f->d_fx,
-                                                         f->d_fy, f->d_flevel, f->d_fangle, f->d_fdesc);
+    if (n <= 16) {   // a few frames: the launch is one partial wave either way, so keep every warp one feature deep
+        dim3 grid((g.n_cells + 7) / 8, n);
+        describe_store_kernel<1><<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, f->d_slots, g, f->d_count, f->d_fx, f->d_fy, f->d_flevel,
+                                                                f->d_fangle, f->d_fdesc);
+    } else {
+        dim3 grid((g.n_cells + 8 * kFeatPerWarp - 1) / (8 * kFeatPerWarp), n);
+        describe_store_kernel<kFeatPerWarp><<<grid, 256, 0, ctx->stream>>>(f->d_pyr, ctx->slot_stride, f->d_slots, g, f->d_count, f->d_fx, f->d_fy,
+                                                                           f->d_flevel, f->d_fangle, f->d_fdesc);
+    }
     YGZB_LAUNCHED(ctx);
     return YGZB_OK;
 }

@@ -224,47 +224,64 @@ __global__ void __launch_bounds__(1024) ba_build_kernel(TrackStore st, const ygz
     }
     __syncthreads();
     const int p0 = p * B.pcap, o0 = p * B.ocap;
-    for (int base = 0; base < dense; base += 1024) {
-        const int i = base + tid, k = i / st.cells, g = i - k * st.cells;
-        int deg = 0;
-        if (i < dense && g < nf[k]) {
-            deg = 1;
-            for (int k2 = 0; k2 < nk; ++k2) deg += tab[(size_t)k2 * kTrackMaxLocal * st.cells + i] != 0;
-        }
-        const int keep = deg >= 2 ? 1 : 0;
-        const int packed = keep | ((keep ? deg : 0) << 14);
-        int chunk_total;
-        const int incl_all = block_scan_1024(packed, s_scan, &chunk_total);
-        if (keep) {
-            const int incl = incl_all;
-            const int pt = s_cpt + (incl & 0x3FFF) - 1, ob = s_cobs + (incl >> 14) - deg;
-            const size_t P = (size_t)p0 + pt, fe = (size_t)e[k] * st.cells + g;
-            B.pts[3 * P] = st.kf_pw[3 * fe];
-            B.pts[3 * P + 1] = st.kf_pw[3 * fe + 1];
-            B.pts[3 * P + 2] = st.kf_pw[3 * fe + 2];
-            B.lm_start[P] = o0 + ob;
-            B.owner[P] = i;
-            size_t o = (size_t)o0 + ob;
-            B.so_kf[o] = k;
-            B.so_uv[2 * o] = st.kf_px[2 * fe];
-            B.so_uv[2 * o + 1] = st.kf_px[2 * fe + 1];
-            ++o;
-            for (int k2 = 0; k2 < nk; ++k2) {
-                const int q = tab[(size_t)k2 * kTrackMaxLocal * st.cells + i];
-                if (!q) continue;
-                B.so_kf[o] = k2;
-                B.so_uv[2 * o] = st.kf_obs_px[2 * ((size_t)e[k2] * cap_obs + q - 1)];
-                B.so_uv[2 * o + 1] = st.kf_obs_px[2 * ((size_t)e[k2] * cap_obs + q - 1) + 1];
-                ++o;
+    // every thread takes `per` CONSECUTIVE dense indices (so the output order is the dense order), finds their degrees with all
+    // the table loads in flight at once, and ONE block scan of the per-thread (points, observations) totals places them
+    constexpr int kMaxPer = (kTrackMaxLocal * 4096 + 1023) / 1024;   // cells <= 4096
+    const int per = (dense + 1023) / 1024;
+    int degs[kMaxPer];
+    int my_pts = 0, my_obs = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxPer; ++r) {
+        degs[r] = 0;
+        const int i = tid * per + r;
+        if (r < per && i < dense) {
+            const int k = i / st.cells, g = i - k * st.cells;
+            if (g < nf[k]) {
+                int deg = 1;
+                for (int k2 = 0; k2 < nk; ++k2) deg += tab[(size_t)k2 * kTrackMaxLocal * st.cells + i] != 0;
+                if (deg >= 2) {
+                    degs[r] = deg;
+                    my_pts += 1;
+                    my_obs += deg;
+                }
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            s_cpt += chunk_total & 0x3FFF;
-            s_cobs += chunk_total >> 14;
-        }
-        __syncthreads();
     }
+    int total_packed;
+    const int incl = block_scan_1024(my_pts | (my_obs << 15), s_scan, &total_packed);   // 15 bits of points, 17 of observations
+    int pt = (incl & 0x7FFF) - my_pts, ob = (int)((unsigned)incl >> 15) - my_obs;   // exclusive prefix of this thread
+#pragma unroll
+    for (int r = 0; r < kMaxPer; ++r) {
+        const int deg = degs[r];
+        if (!deg) continue;
+        const int i = tid * per + r, k = i / st.cells, g = i - k * st.cells;
+        const size_t P = (size_t)p0 + pt, fe = (size_t)e[k] * st.cells + g;
+        B.pts[3 * P] = st.kf_pw[3 * fe];
+        B.pts[3 * P + 1] = st.kf_pw[3 * fe + 1];
+        B.pts[3 * P + 2] = st.kf_pw[3 * fe + 2];
+        B.lm_start[P] = o0 + ob;
+        B.owner[P] = i;
+        size_t o = (size_t)o0 + ob;
+        B.so_kf[o] = k;
+        B.so_uv[2 * o] = st.kf_px[2 * fe];
+        B.so_uv[2 * o + 1] = st.kf_px[2 * fe + 1];
+        ++o;
+        for (int k2 = 0; k2 < nk; ++k2) {
+            const int q = tab[(size_t)k2 * kTrackMaxLocal * st.cells + i];
+            if (!q) continue;
+            B.so_kf[o] = k2;
+            B.so_uv[2 * o] = st.kf_obs_px[2 * ((size_t)e[k2] * cap_obs + q - 1)];
+            B.so_uv[2 * o + 1] = st.kf_obs_px[2 * ((size_t)e[k2] * cap_obs + q - 1) + 1];
+            ++o;
+        }
+        pt += 1;
+        ob += deg;
+    }
+    if (tid == 0) {
+        s_cpt = total_packed & 0x7FFF;
+        s_cobs = (int)((unsigned)total_packed >> 15);
+    }
+    __syncthreads();
     if (tid == 0) {
         B.lm_start[(size_t)p0 + s_cpt] = o0 + s_cobs;
         B.n_kf[p] = nk;
@@ -342,6 +359,7 @@ int ygzb_tracker_create(ygzb_frames* f, int n_streams, int max_jobs, const doubl
     *out = nullptr;
     ygzb_ctx* ctx = f->ctx;
     cudaSetDevice(ctx->device);
+    if (ctx->geo.n_cells > 4096) return set_error(ctx, YGZB_ERR_CAPACITY, "tracker: %d grid cells (the BA assembly handles up to 4096)", ctx->geo.n_cells);
     ygzb_tracker* t = new (std::nothrow) ygzb_tracker();
     if (!t) return YGZB_ERR_INVALID;
     memset(t, 0, sizeof(*t));
