@@ -209,6 +209,50 @@ int main(int argc, char** argv) {
         for (auto& kv : bow_matches) h = (h * 31 + kv.first * 7 + kv.second) % 1000003;
         printf("bow words %u bow_vec %zu feature_vec_nodes %zu features_in_nodes %zu sum %.12f matches %d map %zu hash %ld\n", vocab.size(),
                f1._bow_vec.size(), f1._feature_vec.size(), in_fv, sum1, cnt, bow_matches.size(), h);
+        if (argc > 3) {
+            // LocalMapping::CreateNewMapPoints (LocalMapping.cpp:375-571): a third frame with a wider baseline is the new key-frame,
+            // frame 1 its neighbour with map points on every second feature (ground-truth depth); matches between two features
+            // without a map point are triangulated, matches with a mapped feature are associated
+            FILE* f3p = fopen(argv[3], "rb");
+            if (!f3p) return 12;
+            Frame f3;
+            f3._color.create(480, 640, 1);
+            double T3[12];
+            if (fread(f3._color.data, 1, 640 * 480, f3p) != 640 * 480 || fread(T3, 8, 12, f3p) != 12) return 13;
+            fclose(f3p);
+            f3.InitFrame();
+            det.Detect(&f3);
+            f3.ComputeBoW();
+            f1._keyframe_id = 1;
+            f3._keyframe_id = 3;
+            f1._TCW = SE3();
+            f3._TCW = SE3::from3x4(T3);
+            for (size_t i = 0; i < f1._features.size(); ++i) {
+                Feature* f = f1._features[i];
+                if (i % 2 == 0) {
+                    f->_mappoint = &mps[i];
+                    mps[i]._pos_world = cam.Pixel2Camera(f->_pixel, f->_depth);
+                    mps[i]._bad = false;
+                } else {
+                    f->_mappoint = nullptr;
+                }
+            }
+            std::vector<Vector2d> px_saved;   // CreateNewMapPoints refines the neighbour's matched pixels (LocalMapping.cpp:446)
+            for (Feature* f : f1._features) px_saved.push_back(f->_pixel);
+            LocalMapping lm;
+            lm.CreateNewMapPoints(&f3, {&f1});
+            double sx = 0, sy = 0, sz = 0;
+            for (auto& mp : lm._new_points) {
+                sx += mp->_pos_world[0];
+                sy += mp->_pos_world[1];
+                sz += mp->_pos_world[2];
+            }
+            printf("create_new_map_points new %d associated %d sum %.9f %.9f %.9f\n", lm._cnt_new_mappoints, lm._cnt_associate_mps, sx, sy, sz);
+            for (size_t i = 0; i < f1._features.size(); ++i) {   // (the points of `lm` die with it)
+                f1._features[i]->_mappoint = nullptr;
+                f1._features[i]->_pixel = px_saved[i];
+            }
+        }
         Frame::SetORBVocabulary(nullptr);
     }
     {

@@ -40,7 +40,12 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     voc_file = tmp_path / "voc.bin"
     voc_data = synth.make_vocabulary(k=8, L=5, seed=21)
     voc_file.write_bytes(voc_data)
-    r = subprocess.run([str(EXE), str(blob), str(voc_file)], capture_output=True, text=True, check=True)
+    g3, _, T3 = synth.stream_frame(16)
+    T31 = se3.mul(T3, se3.inv(T1))
+    blob3 = tmp_path / "third.bin"
+    with open(blob3, "wb") as f:
+        f.write(g3.tobytes()); f.write(T31.astype(np.float64).tobytes())
+    r = subprocess.run([str(EXE), str(blob), str(voc_file), str(blob3)], capture_output=True, text=True, check=True)
     lines = r.stdout.strip().splitlines()
     f1 = oracle.detect(oracle.build_pyramid(g1, 3))
     f2 = oracle.detect(oracle.build_pyramid(g2, 3))
@@ -85,11 +90,20 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     assert int(bl[6]) == len(set(n1[n1 >= 0])) and int(bl[8]) == int((n1 >= 0).sum())
     assert abs(float(bl[10]) - bv1.sum()) < 1e-10 and int(bl[12]) == ocnt and int(bl[14]) == int((om >= 0).sum()) and int(bl[16]) == h
     oracle.vocab_free(v)
+    # LocalMapping::CreateNewMapPoints: the same composition on the oracle's functions
+    v2 = oracle.vocab_load(voc_data)
+    cml = [l for l in lines if l.startswith("create_new_map_points")][0].split()
+    f3 = oracle.detect(oracle.build_pyramid(g3, 3))
+    _, n3, _, _, _ = oracle.bow_transform(v2, f3["desc"], 4)
+    want_new, want_assoc, want_sum = _create_new_map_points_on_oracle(oracle, g1, g3, d1, T31, f1, f3, n1, n3)
+    assert abs(int(cml[2]) - want_new) <= 2 and abs(int(cml[4]) - want_assoc) <= 2 and want_new >= 1 and want_assoc > 20
+    if int(cml[2]) == want_new:
+        assert np.allclose([float(cml[6]), float(cml[7]), float(cml[8])], want_sum, rtol=0, atol=1e-6)
     # Initializer::FindModels on the same matches: scores, inlier counts and F21(2,2) are the oracle's, bit for bit
     m1 = np.stack([f1["px"], f1["py"]], 1)[idx >= 0]
     m2 = np.stack([f2["px"], f2["py"]], 1)[idx[idx >= 0]]
     ro = oracle.initializer_ransac(m1, m2, oracle.initializer_sets(len(m1), 200))
-    il = lines[10].split()
+    il = [l for l in lines if l.startswith("initializer")][0].split()
     assert il[0] == "initializer" and int(il[2]) == len(m1)
     assert il[6] == "%.3f" % ro["score_H"] and il[8] == "%.3f" % ro["score_F"]
     assert int(il[10]) == int(ro["inliers_H"].sum()) and int(il[12]) == int(ro["inliers_F"].sum())
@@ -98,9 +112,88 @@ def test_shim_reproduces_oracle(oracle, tmp_path):
     # Initializer::TryInitialize end to end (model choice + ReconstructF / ReconstructH)
     use_h = bool(ro["score_H"] / (ro["score_H"] + ro["score_F"]) > 0.4)
     rq = oracle.initializer_reconstruct(m1, m2, use_h, ro["H21"] if use_h else ro["F21"], ro["inliers_H"] if use_h else ro["inliers_F"])
-    tl = lines[11].split()
+    tl = [l for l in lines if l.startswith("try_initialize")][0].split()
     assert tl[0] == "try_initialize" and int(tl[2]) == int(rq["ok"])
     assert int(tl[4]) == (int(rq["triangulated"].sum()) if rq["ok"] else 0)
     if rq["ok"]:
         # quaternion round trip inside the shim's SE3: compare with a tolerance
         assert np.allclose([float(tl[6]), float(tl[7]), float(tl[8])], rq["t21"], atol=1e-9) and abs(float(tl[10]) - rq["R21"][0, 0]) < 1e-9
+
+
+def _create_new_map_points_on_oracle(oracle, g1, g2, d1, Trel, f1, f2, node1, node2):
+    """LocalMapping.cpp:375-571 with frame 2 as the new key-frame and frame 1 as its only neighbour, on the oracle's
+    SearchForTriangulation / DepthFromTriangulation / FindDirectProjection (the twin of the shim's LocalMapping)."""
+    from ygz_slam_b200 import se3, synth
+    fx, fy, cx, cy = (float(np.float32(v)) for v in (synth.FX, synth.FY, synth.CX, synth.CY))
+    p_cur, p_nb = oracle.build_pyramid(g2, 3), oracle.build_pyramid(g1, 3)
+    I = np.eye(4)[:3]
+    T_cur, T_nb = Trel, I
+    T12 = se3.mul(T_cur, se3.inv(T_nb))
+    t = T12[:, 3]
+    hat = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    E12 = hat @ T12[:, :3]
+    px_cur = np.stack([f2["px"], f2["py"]], 1).astype(np.float64)
+    px_nb = np.stack([f1["px"], f1["py"]], 1).astype(np.float64)
+    depth_nb = d1[px_nb[:, 1].astype(int), px_nb[:, 0].astype(int)].astype(np.float32).astype(np.float64)
+    # neighbour map points on every second feature (camera 1 = world)
+    mp_nb = {i: np.array([(px_nb[i, 0] - cx) * depth_nb[i] / fx, (px_nb[i, 1] - cy) * depth_nb[i] / fy, depth_nb[i]]) for i in range(0, len(px_nb), 2)}
+    mp_cur = {}
+    # baseline against the neighbour's mean map-point depth (LocalMapping.cpp:394-399)
+    c_cur, c_nb = se3.inv(T_cur)[:, 3], se3.inv(T_nb)[:, 3]
+    mean_depth = np.mean([(T_nb[:, :3] @ pw + T_nb[:, 3])[2] for pw in mp_nb.values()])
+    if np.linalg.norm(c_cur - c_nb) / mean_depth < 0.01:
+        return 0, 0, np.zeros(3)
+    m = oracle.search_for_triangulation(f2["desc"], px_cur, node2, f1["desc"], px_nb, node1, E12, th_low=65, epipolar_dsqr=1e-4)
+    T21 = se3.inv(T12)
+
+    def p2c(px, depth=1.0):
+        return np.array([(px[0] - cx) * depth / fx, (px[1] - cy) * depth / fy, depth])
+
+    def c2p(p):
+        return np.array([fx * p[0] / p[2] + cx, fy * p[1] / p[2] + cy])
+
+    n_new = n_assoc = 0
+    total = np.zeros(3)
+    for i1 in range(len(px_cur)):
+        i2 = int(m[i1])
+        if i2 < 0:
+            continue
+        has1, has2 = i1 in mp_cur, i2 in mp_nb
+        if not has1 and not has2:
+            pt1, pt2 = p2c(px_cur[i1]), p2c(px_nb[i2])
+            if pt1 @ pt2 / (np.linalg.norm(pt1) * np.linalg.norm(pt2)) >= 0.9998:
+                continue
+            d1_, d2_, ok = oracle.depth_from_triangulation(T21, pt1, pt2)
+            if not ok[0] or d1_[0] < 0 or d2_[0] < 0:
+                continue
+            px, _, okp = oracle.find_direct_projection(p_cur, p_nb, 640, 480, 3, T_cur, T_nb, px_cur[i1:i1 + 1], np.array([d1_[0]]),
+                                                       f2["level"][i1:i1 + 1], px_nb[i2:i2 + 1].copy())
+            if not okp[0]:
+                continue
+            px_nb[i2] = px[0]
+            pt2 = p2c(px_nb[i2])
+            d1_, d2_, ok = oracle.depth_from_triangulation(T21, pt1, pt2)
+            if not ok[0] or d1_[0] < 0 or d2_[0] < 0:
+                continue
+            tri = pt1 * d1_[0]
+            if np.linalg.norm(c2p(T21[:, :3] @ tri + T21[:, 3]) - px_nb[i2]) > 5.991:
+                continue
+            Ti = se3.inv(T_cur)
+            world = Ti[:, :3] @ tri + Ti[:, 3]
+            mp_cur[i1] = world
+            mp_nb[i2] = world
+            total += world
+            n_new += 1
+        elif has2 and not has1:
+            pw = mp_nb[i2]
+            if np.linalg.norm(c2p(T_cur[:, :3] @ pw + T_cur[:, 3]) - px_cur[i1]) > 5.991:
+                continue
+            mp_cur[i1] = pw
+            n_assoc += 1
+        elif has1 and not has2:
+            pw = mp_cur[i1]
+            if np.linalg.norm(c2p(T_nb[:, :3] @ pw + T_nb[:, 3]) - px_nb[i2]) > 5.991:
+                continue
+            mp_nb[i2] = pw
+            n_assoc += 1
+    return n_new, n_assoc, total

@@ -100,7 +100,8 @@ struct MapPoint {  // include/ygz/Basic/MapPoint.h:17-46 (fields used on the hot
     unsigned long _id = 0;
     Vector3d _pos_world;
     bool _bad = false;
-    int _cnt_found = 0;
+    int _cnt_found = 0, _cnt_visible = 0;
+    unsigned long _first_seen = 0, _last_seen = 0;
     std::map<unsigned long, Feature*> _obs;  // keyframe id -> feature
 };
 
@@ -110,6 +111,10 @@ class PinholeCamera {  // include/ygz/Basic/Camera.h:10-112
     Vector3d World2Camera(const Vector3d& p_w, const SE3& T_c_w) const { return T_c_w * p_w; }
     Vector2d Camera2Pixel(const Vector3d& p) const { return Vector2d(_fx * p[0] / p[2] + _cx, _fy * p[1] / p[2] + _cy); }
     Vector2d World2Pixel(const Vector3d& p_w, const SE3& T) const { return Camera2Pixel(World2Camera(p_w, T)); }
+    Vector3d Camera2World(const Vector3d& p_c, const SE3& T_c_w) const { return T_c_w.inverse() * p_c; }             // Camera.h:45-47
+    Vector3d Pixel2Camera(const Vector2d& p, double depth = 1) const {                                                // Camera.h:56-62
+        return Vector3d((p[0] - _cx) * depth / _fx, (p[1] - _cy) * depth / _fy, depth);
+    }
     float fx() const { return _fx; }
     float fy() const { return _fy; }
     float cx() const { return _cx; }
@@ -133,6 +138,26 @@ struct Frame {  // include/ygz/Basic/Frame.h:20-166 (fields used on the hot path
     }
     static void SetCamera(PinholeCamera* c) { _camera = c; }
     static void SetORBVocabulary(ORBVocabulary* v) { _vocab = v; }   // Frame.h:101
+    Vector3d GetCamCenter() const { return _TCW.inverse().translation(); }                  // Frame.h:77-80
+    bool GetMeanAndMinDepth(double& mean_depth, double& min_depth) const {                   // Frame.cpp:42-71
+        mean_depth = 0;
+        min_depth = 9999;
+        int cnt = 0;
+        for (const Feature* f : _features) {
+            if (f->_mappoint == nullptr || f->_mappoint->_bad) continue;
+            const double depth = (_TCW * f->_mappoint->_pos_world)[2];
+            if (depth < 0) continue;
+            ++cnt;
+            mean_depth += depth;
+            if (depth < min_depth) min_depth = depth;
+        }
+        if (cnt == 0) {
+            mean_depth = min_depth = 0;
+            return false;
+        }
+        mean_depth /= cnt;
+        return true;
+    }
     void ComputeBoW();   // Frame.cpp:190-201: _vocab->transform(all descriptors, _bow_vec, _feature_vec, 4)
     unsigned long _id = 0, _keyframe_id = 0;
     SE3 _TCW;
@@ -732,6 +757,104 @@ class Tracker {  // include/ygz/Algorithm/Tracker.h:11-76
     std::list<Feature*> _tracked_features;
     std::vector<P2f> _px_curr;
     TrackerStatusType _status = TRACK_NOT_READY;
+};
+
+// LocalMapping::CreateNewMapPoints (src/Module/LocalMapping.cpp:375-571) as a caller of the device entry points:
+// SearchForTriangulation per neighbour key-frame, then per match DepthFromTriangulation -> FindDirectProjection ->
+// DepthFromTriangulation -> reprojection test, or the association with an already triangulated point.  The neighbours
+// (Frame::GetBestCovisibilityKeyframes in the reference) and the owner of new map points (Memory::CreateMapPoint) are the
+// caller's; E12 = hat(t12) R12.
+struct LocalMapping {
+    std::vector<std::unique_ptr<MapPoint>> _new_points;   // the map points this call created (stand-in for Memory)
+    int _cnt_new_mappoints = 0, _cnt_associate_mps = 0;
+    void CreateNewMapPoints(Frame* current_kf, const std::vector<Frame*>& neighbour_kf) {
+        PinholeCamera* cam = Frame::_camera;
+        const Vector3d cam_current = current_kf->GetCamCenter();
+        _cnt_new_mappoints = _cnt_associate_mps = 0;
+        for (Frame* f2 : neighbour_kf) {
+            const Vector3d c2 = f2->GetCamCenter();
+            const double bl = std::sqrt((cam_current[0] - c2[0]) * (cam_current[0] - c2[0]) + (cam_current[1] - c2[1]) * (cam_current[1] - c2[1]) +
+                                        (cam_current[2] - c2[2]) * (cam_current[2] - c2[2]));
+            double mean_depth, min_depth;
+            f2->GetMeanAndMinDepth(mean_depth, min_depth);
+            if (bl / mean_depth < 0.01) continue;
+            const SE3 T12 = current_kf->_TCW * f2->_TCW.inverse();
+            double M[12];
+            T12.matrix3x4(M);
+            const double t[3] = {M[3], M[7], M[11]};
+            const double hat[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+            double E12[9];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) E12[3 * r + c] = hat[3 * r] * M[c] + hat[3 * r + 1] * M[4 + c] + hat[3 * r + 2] * M[8 + c];
+            std::vector<std::pair<int, int>> matched_pairs;
+            Matcher matcher;
+            const int matches = matcher.SearchForTriangulation(current_kf, f2, E12, matched_pairs);
+            const SE3 T21 = T12.inverse();
+            for (int im = 0; im < matches; ++im) {
+                Feature* fea1 = current_kf->_features[matched_pairs[im].first];
+                Feature* fea2 = f2->_features[matched_pairs[im].second];
+                if (fea2->_mappoint == nullptr && fea1->_mappoint == nullptr) {
+                    const Vector3d pt1 = cam->Pixel2Camera(fea1->_pixel);
+                    Vector3d pt2 = cam->Pixel2Camera(fea2->_pixel);
+                    const double n1 = std::sqrt(pt1[0] * pt1[0] + pt1[1] * pt1[1] + pt1[2] * pt1[2]),
+                                 n2 = std::sqrt(pt2[0] * pt2[0] + pt2[1] * pt2[1] + pt2[2] * pt2[2]);
+                    const double cos_para_rays = (pt1[0] * pt2[0] + pt1[1] * pt2[1] + pt1[2] * pt2[2]) / (n1 * n2);
+                    if (cos_para_rays >= 0.9998) continue;
+                    double depth1 = 0, depth2 = 0;
+                    bool ret = cvutils::DepthFromTriangulation(T21, pt1, pt2, depth1, depth2);
+                    if (ret == false || depth1 < 0 || depth2 < 0) continue;
+                    fea1->_depth = depth1;
+                    Vector2d px_curr = fea2->_pixel;
+                    int level = 0;
+                    ret = matcher.FindDirectProjection(current_kf, f2, fea1, px_curr, level);
+                    if (ret == false) continue;
+                    fea2->_pixel = px_curr;
+                    pt2 = cam->Pixel2Camera(fea2->_pixel);
+                    ret = cvutils::DepthFromTriangulation(T21, pt1, pt2, depth1, depth2);
+                    if (ret == false || depth1 < 0 || depth2 < 0) continue;
+                    const Vector3d pt1_tri(pt1[0] * depth1, pt1[1] * depth1, pt1[2] * depth1);
+                    const Vector2d px2_reproj = cam->Camera2Pixel(T21 * pt1_tri);
+                    const double reproj_error = std::sqrt((px2_reproj[0] - fea2->_pixel[0]) * (px2_reproj[0] - fea2->_pixel[0]) +
+                                                          (px2_reproj[1] - fea2->_pixel[1]) * (px2_reproj[1] - fea2->_pixel[1]));
+                    if (reproj_error > 5.991) continue;
+                    _new_points.emplace_back(new MapPoint());
+                    MapPoint* mp = _new_points.back().get();
+                    mp->_id = _next_id++;
+                    mp->_first_seen = mp->_last_seen = current_kf->_keyframe_id;
+                    mp->_obs[current_kf->_keyframe_id] = fea1;
+                    mp->_obs[f2->_keyframe_id] = fea2;
+                    mp->_cnt_visible = 2;
+                    mp->_cnt_found = 2;
+                    mp->_pos_world = cam->Camera2World(pt1_tri, current_kf->_TCW);
+                    fea1->_mappoint = mp;
+                    fea2->_mappoint = mp;
+                    fea1->_depth = depth1;
+                    fea2->_depth = depth2;
+                    fea1->_bad = fea2->_bad = false;
+                    ++_cnt_new_mappoints;
+                } else if (fea2->_mappoint && fea1->_mappoint == nullptr) {
+                    const Vector2d px_reproj = cam->World2Pixel(fea2->_mappoint->_pos_world, current_kf->_TCW);
+                    const double e = std::sqrt((px_reproj[0] - fea1->_pixel[0]) * (px_reproj[0] - fea1->_pixel[0]) +
+                                               (px_reproj[1] - fea1->_pixel[1]) * (px_reproj[1] - fea1->_pixel[1]));
+                    if (e > 5.991) continue;
+                    fea1->_mappoint = fea2->_mappoint;
+                    fea1->_depth = cam->World2Camera(fea2->_mappoint->_pos_world, current_kf->_TCW)[2];
+                    fea1->_mappoint->_obs[current_kf->_keyframe_id] = fea1;
+                    ++_cnt_associate_mps;
+                } else if (fea1->_mappoint && fea2->_mappoint == nullptr) {
+                    const Vector2d px_reproj = cam->World2Pixel(fea1->_mappoint->_pos_world, f2->_TCW);
+                    const double e = std::sqrt((px_reproj[0] - fea2->_pixel[0]) * (px_reproj[0] - fea2->_pixel[0]) +
+                                               (px_reproj[1] - fea2->_pixel[1]) * (px_reproj[1] - fea2->_pixel[1]));
+                    if (e > 5.991) continue;
+                    fea2->_mappoint = fea1->_mappoint;
+                    fea2->_depth = cam->World2Camera(fea2->_mappoint->_pos_world, f2->_TCW)[2];
+                    fea2->_mappoint->_obs[f2->_keyframe_id] = fea2;
+                    ++_cnt_associate_mps;
+                }
+            }
+        }
+    }
+    unsigned long _next_id = 0;
 };
 
 // include/ygz/Algorithm/Initializer.h:27-145: TryInitialize (src/Algorithm/Initializer.cpp:9-87) = the RANSAC over 200 minimal
