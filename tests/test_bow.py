@@ -304,3 +304,42 @@ def test_gpu_transform_feeds_search_for_triangulation(ora):
     assert np.array_equal(d1[ok], d2[m[ok]])                                  # identical descriptors find each other
     voc.close()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_transform_properties_on_a_large_vocabulary():
+    """Size-independent properties on a ~100k-node vocabulary and a full frame load (no oracle in the loop): the reported node is
+    the word's ancestor at level L - levelsup, BowVectors are sorted, unique and L1-normalised, stopped words appear nowhere,
+    and the transform is a function of the descriptor alone (same descriptor -> same word in every frame)."""
+    from ygz_slam_b200 import Context
+    data = synth.make_vocabulary(k=10, L=6, seed=5, early_leaf=0.02)
+    rec = parse(data)[0]
+    n_rec = len(rec)
+    parent = np.r_[0, rec["parent"], rec["parent"][-1]]                       # node id -> parent (root = 0; the eof() repeat last)
+    leaf = np.r_[False, rec["leaf"].astype(bool), bool(rec["leaf"][-1])]
+    word_node = np.flatnonzero(leaf)                                             # word id -> node id
+    depth = np.zeros(n_rec + 2, np.int32)
+    for i in range(1, n_rec + 2):
+        depth[i] = depth[parent[i]] + 1
+    ctx = Context(0)
+    voc = ctx.vocabulary(data)
+    sizes = [3072, 2500, 3072]
+    offsets = np.r_[0, np.cumsum(sizes)].astype(np.int32)
+    desc = random_descriptors(data, int(offsets[-1]), 9)
+    desc[offsets[1]:offsets[1] + 500] = desc[:500]                             # the same descriptors in another frame
+    word, node, weight, bows = voc.transform(offsets, desc, 4)
+    assert np.array_equal(word[offsets[1]:offsets[1] + 500], word[:500]) and np.array_equal(node[offsets[1]:offsets[1] + 500], node[:500])
+    stopped = weight <= 0
+    assert np.array_equal(node < 0, stopped) and stopped.any() and (~stopped).any()
+    lvl = 6 - 4
+    for i in np.flatnonzero(~stopped)[::7]:
+        a = int(word_node[word[i]])
+        while depth[a] > lvl:
+            a = int(parent[a])
+        assert a == node[i], i                                                  # ancestor at level 2 (or the leaf itself if shallower)
+    for f, (bw, bv) in enumerate(bows):
+        seg = slice(offsets[f], offsets[f + 1])
+        assert np.all(np.diff(bw) > 0) and abs(bv.sum() - 1.0) < 1e-12 and np.all(bv > 0)
+        assert set(bw) == set(word[seg][~stopped[seg]])
+    voc.close()
+    ctx.close()

@@ -243,3 +243,37 @@ def test_gpu_reconstruct_is_bit_exact(ora):
         n_ok += int(o["ok"])
     assert n_ok >= 3
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_initializer_properties_at_full_size():
+    """3072 noise-free point pairs (a full grid of features), no oracle in the loop: every pair is an inlier of the recovered F,
+    the epipolar residual is at rounding level, ReconstructF returns the true rotation and translation direction, and the
+    triangulated structure is the true structure up to the scale |t|."""
+    from ygz_slam_b200 import Context
+    rng = np.random.default_rng(12)
+    n = 3072
+    X = np.c_[rng.uniform(-2, 2, n), rng.uniform(-1.5, 1.5, n), rng.uniform(3, 8, n)]
+    th = 0.08
+    R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    t = np.array([0.4, -0.05, 0.1])
+    Kf = np.array([[np.float32(520.9), 0, np.float32(325.1)], [0, np.float32(521.0), np.float32(249.7)], [0, 0, 1]], np.float64)
+
+    def proj(Rm, tv):
+        Y = (Rm @ X.T).T + tv
+        return (Kf @ (Y / Y[:, 2:]).T).T[:, :2]
+
+    p1, p2 = proj(np.eye(3), np.zeros(3)), proj(R, t)
+    sets = Oracle().initializer_sets(n, 200)[None]                              # (only the cv::RNG index draw comes from the oracle)
+    ctx = Context(0)
+    g = ctx.initializer_ransac([0, n], p1, p2, sets)
+    assert g["inliers_F"].all() and g["best_F"][0] >= 0
+    F = g["F21"][0]
+    x1, x2 = np.c_[p1, np.ones(n)], np.c_[p2, np.ones(n)]
+    l2 = (F @ x1.T).T
+    assert (np.abs((x2 * l2).sum(1)) / np.hypot(l2[:, 0], l2[:, 1])).max() < 1e-6
+    q = ctx.initializer_reconstruct([0, n], p1, p2, [0], F[None], g["inliers_F"])
+    assert q["ok"][0] and np.abs(q["R21"][0] - R).max() < 1e-7 and np.abs(q["t21"][0] - t / np.linalg.norm(t)).max() < 1e-6
+    assert q["triangulated"].all()
+    assert np.abs(q["p3d"] * np.linalg.norm(t) - X).max() < 1e-5
+    ctx.close()
