@@ -5,6 +5,8 @@ systems: models agree up to sign / rounding, scores to float accuracy) and again
 path performs the oracle's operations in the same order without FMA contraction and must agree BIT FOR BIT (models, float
 scores, winning iterations, inlier flags).
 """
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -180,6 +182,37 @@ def test_oracle_reconstruct_h_candidates(ora):
     assert not q["triangulated"].any() and not q["R21"].any()
 
 
+GOLDEN = Path(__file__).resolve().parent / "golden" / "initializer_cvrng.npz"
+
+
+def try_initialize(run_ransac, run_reconstruct, p1, p2, sets):
+    """Initializer::TryInitialize (Initializer.cpp:9-87) on top of the two entry points."""
+    r = run_ransac(p1, p2, sets)
+    use_h = bool(r["score_H"] / (r["score_H"] + r["score_F"]) > 0.4)
+    q = run_reconstruct(p1, p2, use_h, r["H21"] if use_h else r["F21"], r["inliers_H"] if use_h else r["inliers_F"])
+    return use_h, r, q
+
+
+def test_reference_test_initializer_scene(ora):
+    """The reference's own test, test/test_initializer.cpp:10-140, with EXACTLY its data: landmarks on three depth layers, second
+    camera at t = (1, 0, 0), pixel noise sigma 2 drawn from the default cv::RNG (tools/make_initializer_fixture.py).  Like the
+    test: TryInitialize on the F scene, then ba::TwoViewBACeres on the result, scale normalised by |t|."""
+    fx = np.load(GOLDEN)
+    p1, p2 = fx["px1F"], fx["px2F"]
+    use_h, r, q = try_initialize(ora.initializer_ransac, ora.initializer_reconstruct, p1, p2, ora.initializer_sets(12, 200))
+    assert not use_h and q["ok"] and q["triangulated"].all()                         # "Initialize succeeded", 12 inliers
+    assert np.abs(q["R21"] - np.eye(3)).max() < 0.05 and np.linalg.norm(q["t21"] - fx["t2"]) < 0.15
+    T2 = np.c_[q["R21"], q["t21"]]
+    T2b, inl, pts, st, cnt = ora.two_view_ba(np.eye(4)[:3], T2, p1, p2, q["triangulated"], q["p3d"])
+    scale = np.linalg.norm(T2b[:, 3])
+    assert cnt >= 10 and np.linalg.norm(T2b[:, 3] / scale - fx["t2"]) < 0.1 and np.abs(T2b[:, :3] - np.eye(3)).max() < 0.05
+    err = np.linalg.norm(pts[inl] / scale - fx["landmarks_F"][inl], axis=1)
+    assert np.median(err) < 0.3                                                      # 2 px of noise on 12 points, depths 2 .. 4
+    # the planar scene of the same test file: sh / (sh + sf) < 0.4 sends it to ReconstructF, which cannot decide on a plane
+    use_h, r, q = try_initialize(ora.initializer_ransac, ora.initializer_reconstruct, fx["px1H"], fx["px2H"], ora.initializer_sets(12, 200))
+    assert not use_h and not q["ok"]
+
+
 # ---- CUDA path -------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_gpu_ransac_is_bit_exact(ora):
@@ -276,4 +309,38 @@ def test_gpu_initializer_properties_at_full_size():
     assert q["ok"][0] and np.abs(q["R21"][0] - R).max() < 1e-7 and np.abs(q["t21"][0] - t / np.linalg.norm(t)).max() < 1e-6
     assert q["triangulated"].all()
     assert np.abs(q["p3d"] * np.linalg.norm(t) - X).max() < 1e-5
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reference_test_initializer_scene(ora):
+    """test/test_initializer.cpp's two scenes through the device path: every output equals the oracle's bit for bit, and the
+    two-view BA that follows in the reference's test lands on the same pose."""
+    from ygz_slam_b200 import Context
+    fx = np.load(GOLDEN)
+    ctx = Context(0)
+    sets = ora.initializer_sets(12, 200)
+    for tag in ("F", "H"):
+        p1, p2 = fx["px1" + tag], fx["px2" + tag]
+        use_o, ro, qo = try_initialize(ora.initializer_ransac, ora.initializer_reconstruct, p1, p2, sets)
+
+        def g_ransac(a, b, s_):
+            g = ctx.initializer_ransac([0, len(a)], a, b, s_[None])
+            return dict(H21=g["H21"][0], F21=g["F21"][0], score_H=g["score_H"][0], score_F=g["score_F"][0], inliers_H=g["inliers_H"], inliers_F=g["inliers_F"])
+
+        def g_recon(a, b, uh, model, inl):
+            g = ctx.initializer_reconstruct([0, len(a)], a, b, [int(uh)], model[None], inl)
+            return dict(ok=bool(g["ok"][0]), R21=g["R21"][0], t21=g["t21"][0], p3d=g["p3d"], triangulated=g["triangulated"], n_good=g["n_good"][0])
+
+        use_g, rg, qg = try_initialize(g_ransac, g_recon, p1, p2, sets)
+        assert use_g == use_o and qg["ok"] == qo["ok"]
+        assert np.array_equal(rg["F21"], ro["F21"]) and np.array_equal(rg["H21"], ro["H21"])
+        assert rg["score_F"].tobytes() == ro["score_F"].tobytes() and rg["score_H"].tobytes() == ro["score_H"].tobytes()
+        assert np.array_equal(qg["R21"], qo["R21"]) and np.array_equal(qg["t21"], qo["t21"]) and np.array_equal(qg["p3d"], qo["p3d"])
+        assert np.array_equal(qg["n_good"], qo["n_good"]) and np.array_equal(qg["triangulated"], qo["triangulated"])
+        if qo["ok"]:
+            T2 = np.c_[qo["R21"], qo["t21"]]
+            wT, winl, wpts, _, _ = ora.two_view_ba(np.eye(4)[:3], T2, p1, p2, qo["triangulated"], qo["p3d"])
+            gT, ginl, gpts, _ = ctx.two_view_ba([0, 12], np.eye(4)[:3], T2, p1, p2, qg["triangulated"], qg["p3d"])
+            assert np.abs(gT[0] - wT).max() < 1e-6 and np.array_equal(ginl, winl) and np.abs(gpts - wpts).max() < 1e-6
     ctx.close()
