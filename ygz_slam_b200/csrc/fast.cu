@@ -20,7 +20,9 @@
 // Each tile owns whole cells, so it reduces candidates with two 64-bit shared-memory atomics
 //     first = min (raster << 32 | score bits)          -> the earliest candidate and its score
 //     best  = max (orderable(score) << 32 | ~raster)   -> the best non-NaN score, earliest on ties
-// and merge_cells_kernel replays the level order.  All f32 maths is unfused (-fmad=false).
+// and merge_cells_kernel replays the level order.  The f32 maths is written with the explicit
+// round-to-nearest intrinsics (__fmul_rn / __fadd_rn ...), which ptxas never contracts into FMA; the
+// file does not depend on -fmad=false (build.py passes that to align.cu, track.cu, initializer.cu).
 #include <cuda.h>
 
 #include <mutex>
