@@ -866,6 +866,7 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
             } else {
                 st[0] = iters; st[1] = trials_total; st[2] = chi_first; st[3] = chi_last; st[4] = lambda; st[5] = n_out_tot;
             }
+            st[6] = 0.0; st[7] = 0.0;   // (unused by this kernel generation; the host copies all 8 slots)
         }
     }
 }

@@ -429,6 +429,9 @@ int ygzb_tracker_create(ygzb_frames* f, int n_streams, int max_jobs, const doubl
     if (rc == YGZB_OK) rc = check_cuda(ctx, cudaMallocHost((void**)&t->h_kfjobs, sizeof(ygzb_keyframe_job) * S), "cudaMallocHost");
     if (rc == YGZB_OK) rc = dalloc(ctx, &t->d_kfjobs, S);
     if (rc == YGZB_OK) rc = dalloc(ctx, &t->d_kfres, S);
+    // (a result record carries YGZB_TRACK_RING pose slots and only the first n_local are written by a job: the whole record is
+    //  copied back, so start from zeros rather than from whatever cudaMalloc returned)
+    if (rc == YGZB_OK) rc = check_cuda(ctx, cudaMemsetAsync(t->d_kfres, 0, sizeof(ygzb_keyframe_result) * S, ctx->stream), "memset");
     if (rc == YGZB_OK) rc = check_cuda(ctx, cudaEventCreateWithFlags(&t->staged, cudaEventDisableTiming), "cudaEventCreate");
     if (rc == YGZB_OK) rc = check_cuda(ctx, cudaStreamCreateWithFlags(&t->front, cudaStreamNonBlocking), "cudaStreamCreate");
     for (cudaEvent_t* e : {&t->e_fill, &t->e_front, &t->e_main, &t->e_up})
