@@ -45,3 +45,37 @@ def test_klt_golden(oracle, gold):
     assert np.percentile(d, 99) < 0.01 and np.median(d) < 1e-3
     assert np.abs(err[both] - gold["lk_err"][both]).max() < 0.05
     assert both.sum() > 0.9 * len(wst) - 3
+
+
+# ---- cv::RNG (the RANSAC minimal sets of Initializer::TryInitialize), tests/golden/cv_rng_sets.npz from tools/make_cv_rng_fixture.py
+RNG_GOLD = Path(__file__).resolve().parent / "golden" / "cv_rng_sets.npz"
+
+
+def _mwc_stream(count, state=0xFFFFFFFF):
+    """cv::RNG::next() written from OpenCV's operations.hpp: state = (unsigned)state * CV_RNG_COEFF + (state >> 32)."""
+    out = np.zeros(count, np.int64)
+    for i in range(count):
+        state = ((state & 0xFFFFFFFF) * 4164903690 + (state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        out[i] = state & 0xFFFFFFFF
+    return out
+
+
+def test_cv_rng_uniform_golden():
+    """OpenCV's own draws (cv2.randu on theRNG() reset to the default state) are next() % b of the multiply-with-carry stream:
+    this pins the coefficient, the default state and RNG::uniform(int, int) of the restatement every other test relies on."""
+    g = np.load(RNG_GOLD)
+    stream = _mwc_stream(64)
+    for key in g.files:
+        if key.startswith("uniform_"):
+            b = int(key.split("_")[1])
+            assert np.array_equal(g[key].astype(np.int64), stream % b), key
+
+
+def test_initializer_sets_golden(oracle):
+    """The oracle's minimal sets (a fresh default cv::RNG, draws without replacement) equal the sets drawn with OpenCV's generator."""
+    g = np.load(RNG_GOLD)
+    keys = [k for k in g.files if k.startswith("sets_")]
+    assert len(keys) >= 3
+    for key in keys:
+        n = int(key.split("_")[1])
+        assert np.array_equal(oracle.initializer_sets(n, 200), g[key]), key

@@ -162,3 +162,15 @@ def test_fast_nonmax_rule_is_switchable(oracle, synth_frames):
         oracle.lib.ora_set_fast_nonmax_strict(0)
     assert set(keep_ge.tolist()) <= set(keep_gt.tolist()) and len(keep_gt) >= len(keep_ge)
     assert np.array_equal(oracle.fast_nonmax(xy, sc), keep_ge)
+
+
+@pytest.mark.parametrize("n", [57, 100, 777, 1500])
+def test_initializer_sets_match_live_cv_rng(oracle, n):
+    """cv::RNG pinned against OpenCV itself: cv2.setRNGSeed(0) resets theRNG() to the default-constructed state of the
+    reference's `cv::RNG rng` (Initializer.cpp:25), cv2.randu on one CV_32S element with range [0, b) is one rng.uniform(0, b)
+    (b not a power of two: those take randu's bit-mask path); the swap-with-last draw of Initializer.cpp:33-49 on top."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from make_cv_rng_fixture import sets_from_cv2
+    assert np.array_equal(oracle.initializer_sets(n, 50), sets_from_cv2(n, 50))
