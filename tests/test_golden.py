@@ -79,3 +79,34 @@ def test_initializer_sets_golden(oracle):
     for key in keys:
         n = int(key.split("_")[1])
         assert np.array_equal(oracle.initializer_sets(n, 200), g[key]), key
+
+
+# ---- OpenCV's own ORB orientation / descriptor (tests/golden/cv2_orb.npz from tools/make_orb_fixture.py)
+ORB_GOLD = Path(__file__).resolve().parent / "golden" / "cv2_orb.npz"
+
+
+def _orb_blur_numpy(img, kernel):
+    """7 x 7 separable Gaussian, BORDER_REFLECT_101, in double precision, rounded to uint8 (what cv2.ORB applies before it
+    computes descriptors; see tools/make_orb_fixture.py)."""
+    r = len(kernel) // 2
+    pad = np.pad(img.astype(np.float64), r, mode="reflect")
+    rows = sum(kernel[k] * pad[:, k:k + img.shape[1]] for k in range(2 * r + 1))
+    out = sum(kernel[k] * rows[k:k + img.shape[0], :] for k in range(2 * r + 1))
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def test_ic_angle_and_orb_descriptor_golden(oracle):
+    """IC_Angle (with the canonical umax table) and ComputeOrbDescriptor equal OpenCV's ORB bit for bit on 500 key-points."""
+    from ygz_slam_b200 import synth
+    g = np.load(ORB_GOLD)
+    img = synth.stream_frame(int(g["frame"]))[0]
+    h, w = img.shape
+    px, py = g["px"].astype(np.float64), g["py"].astype(np.float64)
+    lvl = np.zeros(len(px), np.int32)
+    ang, _ = oracle.describe(oracle.build_pyramid(img, 3), w, h, 3, px, py, lvl)
+    assert np.array_equal(ang.view(np.uint32), g["cv_angle"].view(np.uint32))           # ICAngles of cv2.ORB.detect
+    J = _orb_blur_numpy(img, g["blur_kernel"])
+    ang_j, desc_j = oracle.describe(oracle.build_pyramid(J, 3), w, h, 3, px, py, lvl)
+    assert np.array_equal(ang_j.view(np.uint32), g["angle_on_blurred"].view(np.uint32))  # (the blurred image is reproduced)
+    assert np.array_equal(desc_j, g["cv_desc"])                                          # computeOrbDescriptors of cv2.ORB.compute
+    assert len(px) == 500 and len(np.unique(desc_j, axis=0)) > 450

@@ -174,3 +174,23 @@ def test_initializer_sets_match_live_cv_rng(oracle, n):
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
     from make_cv_rng_fixture import sets_from_cv2
     assert np.array_equal(oracle.initializer_sets(n, 50), sets_from_cv2(n, 50))
+
+
+@pytest.mark.parametrize("frame", [1, 2, 7])
+def test_ic_angle_and_orb_descriptor_match_live_cv2_orb(oracle, frame):
+    """FeatureDetector::IC_Angle / ComputeOrbDescriptor are OpenCV's ORB code (via ORB-SLAM): angle and descriptor of 2000
+    key-points per frame equal cv2.ORB's bit for bit (tools/make_orb_fixture.py explains the blur and the provided angle)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from make_orb_fixture import cv2_orb_pins, orb_blur
+    from ygz_slam_b200 import synth
+    img = synth.stream_frame(frame)[0]
+    px, py, cv_angle, ang_j, cv_desc = cv2_orb_pins(oracle, img, 2000)
+    assert len(px) > 1000
+    h, w = img.shape
+    lvl = np.zeros(len(px), np.int32)
+    ang, _ = oracle.describe(oracle.build_pyramid(img, 3), w, h, 3, px.astype(np.float64), py.astype(np.float64), lvl)
+    assert np.array_equal(ang.view(np.uint32), cv_angle.view(np.uint32))
+    _, desc_j = oracle.describe(oracle.build_pyramid(orb_blur(img), 3), w, h, 3, px.astype(np.float64), py.astype(np.float64), lvl)
+    assert np.array_equal(desc_j, cv_desc)
