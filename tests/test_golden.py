@@ -110,3 +110,30 @@ def test_ic_angle_and_orb_descriptor_golden(oracle):
     assert np.array_equal(ang_j.view(np.uint32), g["angle_on_blurred"].view(np.uint32))  # (the blurred image is reproduced)
     assert np.array_equal(desc_j, g["cv_desc"])                                          # computeOrbDescriptors of cv2.ORB.compute
     assert len(px) == 500 and len(np.unique(desc_j, axis=0)) > 450
+
+
+# ---- OpenCV's FAST 9/16 with non-maximum suppression (tests/golden/cv2_fast9.npz from tools/make_fast_fixture.py)
+def _fast9_chain(oracle, img, threshold):
+    """oracle detector (arc = 9) -> closed-form score -> oracle 3 x 3 suppression: rows of (y, x, score) in raster order."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from fast_closed_form import score_closed_form
+    xy = oracle.fast_detect(img, threshold, arc=9)
+    sc = score_closed_form(img, xy, 9)
+    keep = oracle.fast_nonmax(xy, sc)
+    return xy, sc, np.array(sorted((int(xy[i, 1]), int(xy[i, 0]), int(sc[i])) for i in keep), np.int32)
+
+
+def test_fast_score_and_nonmax_golden(oracle):
+    """Score definition and suppression rule of the oracle's FAST equal OpenCV's (arc 9, the only arc both implement); the
+    arc-10 score the product is checked against is the same closed form with arc = 10."""
+    from ygz_slam_b200 import synth
+    g = np.load(Path(__file__).resolve().parent / "golden" / "cv2_fast9.npz")
+    img = synth.stream_frame(int(g["frame"]))[0]
+    _, _, got = _fast9_chain(oracle, img, int(g["threshold"]))
+    assert np.array_equal(got, g["yx_score"].astype(np.int32)) and len(got) > 2000
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from fast_closed_form import score_closed_form
+    xy10 = oracle.fast_detect(img, 15)
+    assert np.array_equal(score_closed_form(img, xy10, 10), oracle.fast_score(img, xy10))

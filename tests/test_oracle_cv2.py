@@ -194,3 +194,20 @@ def test_ic_angle_and_orb_descriptor_match_live_cv2_orb(oracle, frame):
     assert np.array_equal(ang.view(np.uint32), cv_angle.view(np.uint32))
     _, desc_j = oracle.describe(oracle.build_pyramid(orb_blur(img), 3), w, h, 3, px.astype(np.float64), py.astype(np.float64), lvl)
     assert np.array_equal(desc_j, cv_desc)
+
+
+@pytest.mark.parametrize("frame", [2, 5, 9])
+def test_fast_score_and_nonmax_match_live_cv2_fast9(oracle, frame):
+    """Detector (arc 9) -> closed-form score -> 3 x 3 suppression of the oracle == cv2 FAST 9/16 with nonmaxSuppression:
+    same corners, same responses (tools/make_fast_fixture.py)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from make_fast_fixture import cv2_fast9_nms, score_closed_form
+    from ygz_slam_b200 import synth
+    img = synth.stream_frame(frame)[0]
+    xy = oracle.fast_detect(img, 15, arc=9)
+    sc = score_closed_form(img, xy, 9)
+    keep = oracle.fast_nonmax(xy, sc)
+    got = np.array(sorted((int(xy[i, 1]), int(xy[i, 0]), int(sc[i])) for i in keep), np.int32)
+    assert np.array_equal(got, cv2_fast9_nms(img)) and len(got) > 2000
