@@ -211,3 +211,74 @@ def test_fast_score_and_nonmax_match_live_cv2_fast9(oracle, frame):
     keep = oracle.fast_nonmax(xy, sc)
     got = np.array(sorted((int(xy[i, 1]), int(xy[i, 0]), int(sc[i])) for i in keep), np.int32)
     assert np.array_equal(got, cv2_fast9_nms(img)) and len(got) > 2000
+
+
+def test_shi_tomasi_agrees_with_cv2_min_eigenvalue(oracle, synth_frames):
+    """FeatureDetector::ShiTomasiScore (:467-507) is the smaller eigenvalue of the 8 x 8 gradient matrix built from central
+    differences over x in [u-4, u+4), y in [v-4, v+4), divided by 2 * 64: cv2.cornerMinEigenVal(blockSize = 8, ksize = 1) is the
+    same quantity (same window anchor, Sobel aperture 1 = central difference) scaled by 1 / (8 * 255)^2, in float32 with another
+    summation order -- so structure (window, anchor, formula) must agree to float precision; the 1-ulp pin is the numpy re-derivation."""
+    g = synth_frames[2][0]
+    ev = cv2.cornerMinEigenVal(g, blockSize=8, ksize=1, borderType=cv2.BORDER_REFLECT_101).astype(np.float64) * 2040.0 ** 2 / 128.0
+    rng = np.random.default_rng(0)
+    us, vs = rng.integers(20, 620, 600), rng.integers(20, 460, 600)
+    got = np.array([oracle.shi_tomasi(g, u, v) for u, v in zip(us, vs)])
+    want = ev[vs, us]
+    assert np.all(np.abs(got - want) <= 2e-4 * np.maximum(1.0, np.abs(want)))
+    assert got.max() > 100 and (got > 1).sum() > 100
+
+
+# ---- two-view geometry of the Initializer against OpenCV's own decompositions ------------------------------------------
+def _two_view_scenes():
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import test_initializer as ti
+    return ti
+
+
+_KF = np.array([[np.float32(520.9), 0, np.float32(325.1)], [0, np.float32(521.0), np.float32(249.7)], [0, 0, 1.0]], np.float64)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_decompose_e_and_triangulate_match_cv2(oracle, seed):
+    """Initializer::DecomposeE (Initializer.cpp:643-675) and ::Triangulate (:615-641) are textbook constructions OpenCV also
+    ships: the four (R, t) candidates of ReconstructF equal cv2.decomposeEssentialMat of E = K^T F K, the triangulated points equal
+    cv2.triangulatePoints (the same DLT) for the selected pose."""
+    ti = _two_view_scenes()
+    p1, p2, R, t, n_out = ti.two_view(seed, noise=0.2)
+    r = oracle.initializer_ransac(p1, p2, oracle.initializer_sets(len(p1), 200))
+    q = oracle.initializer_reconstruct(p1, p2, 0, r["F21"], r["inliers_F"])
+    assert q["ok"]
+    R1, R2, tc = cv2.decomposeEssentialMat(_KF.T @ r["F21"] @ _KF)
+    seen = set()
+    for c in q["candidates"][:4]:
+        Rc, tcand = c[:9].reshape(3, 3), c[9:]
+        which = int(np.abs(Rc - R2).max() < np.abs(Rc - R1).max())
+        sign = int(np.abs(tcand + tc.ravel()).max() < np.abs(tcand - tc.ravel()).max())
+        assert np.abs(Rc - (R1, R2)[which]).max() < 1e-12 and np.abs(tcand - (1 - 2 * sign) * tc.ravel()).max() < 1e-12
+        seen.add((which, sign))
+    assert len(seen) == 4                                   # all four combinations, each once
+    tri = q["triangulated"]
+    P1 = _KF @ np.c_[np.eye(3), np.zeros(3)]
+    P2 = _KF @ np.c_[q["R21"], q["t21"]]
+    X = cv2.triangulatePoints(P1, P2, p1[tri].T.copy(), p2[tri].T.copy())
+    X = (X[:3] / X[3]).T
+    assert tri.sum() > 200 and np.abs(X - q["p3d"][tri]).max() < 1e-9 * np.abs(X).max()
+
+
+def test_reconstruct_h_candidates_contain_cv2_decomposition(oracle):
+    """ReconstructH (Initializer.cpp:330-513) enumerates Faugeras' eight (R, t, n) hypotheses; OpenCV's decomposeHomographyMat
+    (Malis & Vargas, an analytically different route) returns the four physically distinct ones: each must be among the eight
+    (rotation to 1e-6 -- the reference builds its rotations from float cos / sin --, translation direction up to sign)."""
+    ti = _two_view_scenes()
+    for seed, noise in ((0, 0.0), (1, 0.3)):
+        p1, p2, R, t, _ = ti.planar_scene(seed, noise=noise)
+        r = oracle.initializer_ransac(p1, p2, oracle.initializer_sets(len(p1), 200))
+        q = oracle.initializer_reconstruct(p1, p2, 1, r["H21"], r["inliers_H"])
+        n, Rs, ts, _ = cv2.decomposeHomographyMat(r["H21"], _KF)
+        assert n == 4
+        for Rc, tc in zip(Rs, ts):
+            tn = tc.ravel() / np.linalg.norm(tc)
+            errs = [max(np.abs(c[:9].reshape(3, 3) - Rc).max(), min(np.abs(c[9:] - tn).max(), np.abs(c[9:] + tn).max())) for c in q["candidates"]]
+            assert min(errs) < 1e-6
