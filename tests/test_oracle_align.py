@@ -32,6 +32,36 @@ def test_se3_exp_log_roundtrip(oracle):
             assert np.allclose(T, se3.se3_exp(v), atol=1e-10)
 
 
+def test_se3_exp_log_against_scipy(oracle):
+    """Third-party check of the Sophus restatement (se3.cpp:170-220, so3.cpp:127-202): exp([upsilon; omega]) is the matrix
+    exponential of the 4 x 4 twist (scipy.linalg.expm), its rotation scipy's Rotation.from_rotvec; log inverts both --
+    including tiny angles (Taylor branch) and angles close to pi."""
+    from scipy.linalg import expm, logm
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(3)
+    for scale in (1e-9, 1e-5, 1e-2, 0.7, 3.0):
+        for _ in range(8):
+            v = rng.normal(0, 1, 6)
+            v[3:] *= scale / np.linalg.norm(v[3:])
+            w = v[3:]
+            twist = np.zeros((4, 4))
+            twist[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]
+            twist[:3, 3] = v[:3]
+            want = expm(twist)
+            T = oracle.se3_exp(v)
+            # Sophus evaluates (1 - cos(theta)) / theta^2 literally above SMALL_EPS = 1e-10 (se3.cpp:182-193): for tiny angles the
+            # cancellation costs eps / theta^2 in that coefficient, i.e. eps * |upsilon| / theta in the translation -- kept, it is
+            # the reference's arithmetic
+            tol = 1e-12 * max(1.0, np.abs(want).max()) + 1e-15 * np.linalg.norm(v[:3]) / scale
+            assert np.abs(T - want[:3]).max() < tol
+            assert np.abs(T[:, :3] - Rotation.from_rotvec(w).as_matrix()).max() < 1e-14
+            back = oracle.se3_log(T)
+            assert np.abs(back[3:] - Rotation.from_matrix(T[:, :3]).as_rotvec()).max() < 1e-9 * max(1.0, scale) + 1e-15
+            if scale >= 1e-2:    # (logm loses digits for tiny rotations; the round trip above covers those)
+                L = np.real(logm(np.vstack([T, [0, 0, 0, 1]])))
+                assert np.abs(back[:3] - L[:3, 3]).max() < 1e-9 and np.abs(back[3:] - [L[2, 1], L[0, 2], L[1, 0]]).max() < 1e-9
+
+
 def test_find_direct_projection_converges_to_ground_truth(oracle):
     s = _scene(oracle)
     rng = np.random.default_rng(7)
