@@ -271,7 +271,6 @@ __device__ __noinline__ void ceres_linearise(const double* __restrict__ pose, do
 // Every CTA keeps its own replica of the poses and of the LM scalars and takes the same (deterministic) decisions.
 constexpr int kClusterSize = 8;
 constexpr int kMaxCluster = 16;           // non-portable cluster size (opt-in attribute)
-constexpr size_t kObsPerCtaFull = 1000;   // observations per CTA below which a smaller cluster wins (measured)
 
 struct ClusterWs {            // per problem, in global memory
     double red[4][kMaxCluster][4];
@@ -872,92 +871,8 @@ __global__ void __launch_bounds__(kBAThreads) local_ba_kernel(const BAArgs a, Cl
 }
 
 // ---- pose-only refinement ----------------------------------------------------------------------------------
-struct Jet6 {
-    double a;
-    double v[6];
-};
-__device__ __forceinline__ Jet6 jc(double c) {
-    Jet6 r;
-    r.a = c;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) r.v[i] = 0;
-    return r;
-}
-__device__ __forceinline__ Jet6 operator+(const Jet6& x, const Jet6& y) {
-    Jet6 r;
-    r.a = x.a + y.a;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) r.v[i] = x.v[i] + y.v[i];
-    return r;
-}
-__device__ __forceinline__ Jet6 operator-(const Jet6& x, const Jet6& y) {
-    Jet6 r;
-    r.a = x.a - y.a;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) r.v[i] = x.v[i] - y.v[i];
-    return r;
-}
-__device__ __forceinline__ Jet6 operator*(const Jet6& x, const Jet6& y) {
-    Jet6 r;
-    r.a = x.a * y.a;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) r.v[i] = x.a * y.v[i] + x.v[i] * y.a;
-    return r;
-}
-__device__ __forceinline__ Jet6 operator/(const Jet6& x, const Jet6& y) {
-    const double inv = 1.0 / y.a, q = x.a * inv;
-    Jet6 r;
-    r.a = q;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) r.v[i] = (x.v[i] - q * y.v[i]) * inv;
-    return r;
-}
-
-// ceres::AngleAxisRotatePoint, pose jets: P[0..2] = t, P[3..5] = angle-axis
-__device__ void project_jet(const double pose[6], const double X[3], Jet6* p0, Jet6* p1, Jet6* p2) {
-    Jet6 P[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        P[i] = jc(pose[i]);
-        P[i].v[i] = 1.0;
-    }
-    const Jet6 pt[3] = {jc(X[0]), jc(X[1]), jc(X[2])};
-    const Jet6 theta2 = P[3] * P[3] + P[4] * P[4] + P[5] * P[5];
-    Jet6 out[3];
-    if (theta2.a > 2.2204460492503131e-16) {
-        Jet6 theta, costheta, sintheta;
-        {
-            const double s = sqrt(theta2.a), d = 1.0 / (2.0 * s);
-            theta.a = s;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) theta.v[i] = theta2.v[i] * d;
-            const double c = cos(s), sn = sin(s);
-            costheta.a = c;
-            sintheta.a = sn;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                costheta.v[i] = -sn * theta.v[i];
-                sintheta.v[i] = c * theta.v[i];
-            }
-        }
-        const Jet6 inv = jc(1.0) / theta;
-        const Jet6 w[3] = {P[3] * inv, P[4] * inv, P[5] * inv};
-        const Jet6 wxp[3] = {w[1] * pt[2] - w[2] * pt[1], w[2] * pt[0] - w[0] * pt[2], w[0] * pt[1] - w[1] * pt[0]};
-        const Jet6 tmp = (w[0] * pt[0] + w[1] * pt[1] + w[2] * pt[2]) * (jc(1.0) - costheta);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) out[i] = pt[i] * costheta + wxp[i] * sintheta + w[i] * tmp;
-    } else {
-        const Jet6 wxp[3] = {P[4] * pt[2] - P[5] * pt[1], P[5] * pt[0] - P[3] * pt[2], P[3] * pt[1] - P[4] * pt[0]};
-#pragma unroll
-        for (int i = 0; i < 3; ++i) out[i] = pt[i] + wxp[i];
-    }
-    *p0 = out[0] + P[0];
-    *p1 = out[1] + P[1];
-    *p2 = out[2] + P[2];
-}
-
 // value + partials with respect to the angle-axis only: the rotation of the pose, differentiated ONCE per evaluation instead
-// of once per point (the jets of project_jet spent two thirds of the kernel's FP64 instructions re-deriving it per point)
+// of once per point (round 1's six-partial jets spent two thirds of the kernel's FP64 instructions re-deriving it per point)
 struct Jet3 {
     double a;
     double v[3];
